@@ -1,0 +1,264 @@
+/*
+ * snapb200.h -- C ABI of the B200-native alignment core for SNAP-RNA (andrewmagis/snap-rnaseq).
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes, and replaces one reference interface, cited as file:line relative to the reference
+ * tree.  The reference host code (AlignerContext, SingleAligner/PairedAligner loops, FASTQ/SAM/BAM I/O,
+ * AlignmentFilter) stays as it is; an `AlignerExtension` (SNAPLib/AlignerContext.h:132-163) that owns the
+ * per-thread loop drains reads into batches and calls these functions -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns SNAPB200_OK (0) or a negative error code and never aborts the process
+ *     (the reference's error model is fprintf(stderr)+soft_exit(1), SNAPLib/exit.h:26; the shim maps a
+ *     non-zero return to soft_exit(1)); snapb200_last_error() gives the message;
+ *   - "not aligned" is a value, not an error: status NotFound / location 0xffffffff (SNAPLib/Genome.h:29);
+ *   - the caller owns all host buffers; the library owns all device memory;
+ *   - there is no CPU fallback: if no CUDA device is usable every compute entry point fails with
+ *     SNAPB200_ERR_CUDA.
+ */
+#ifndef SNAPB200_H
+#define SNAPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNAPB200_ABI_VERSION 1
+
+enum {
+    SNAPB200_OK = 0,
+    SNAPB200_ERR_ARG = -1,     /* bad argument / unsupported parameter combination           */
+    SNAPB200_ERR_IO = -2,      /* index directory unreadable or malformed                     */
+    SNAPB200_ERR_CUDA = -3,    /* no device, launch failure, out of device memory             */
+    SNAPB200_ERR_LIMIT = -4    /* a reference pool limit was hit (the reference would soft_exit) */
+};
+
+/* AlignmentResult, SNAPLib/Read.h:41 */
+enum { SNAPB200_NOT_FOUND = 0, SNAPB200_SINGLE_HIT = 1, SNAPB200_MULTIPLE_HITS = 2 };
+/* Direction, SNAPLib/directions.h:26-31 */
+enum { SNAPB200_FORWARD = 0, SNAPB200_RC = 1 };
+
+#define SNAPB200_INVALID_LOCATION 0xffffffffu /* InvalidGenomeLocation, SNAPLib/Genome.h:29 */
+#define SNAPB200_MAX_K 31                     /* MAX_K, SNAPLib/LandauVishkin.h:9 */
+#define SNAPB200_MAX_READ_LENGTH 500          /* MAX_READ_LENGTH, SNAPLib/Read.h:45 */
+#define SNAPB200_UNUSED_SCORE 0xffff          /* BaseAligner::UnusedScoreValue, SNAPLib/BaseAligner.h:261 */
+
+typedef struct snapb200_index snapb200_index; /* opaque; a GenomeIndex + Genome resident in HBM */
+
+/* ---- index / genome ------------------------------------------------------------------------------- */
+
+typedef struct {
+    uint32_t n_bases;             /* Genome::getCountOfBases()                                  */
+    uint32_t n_pieces;            /* Genome::getNumPieces()                                     */
+    uint32_t seed_len;            /* GenomeIndex::getSeedLength()                               */
+    uint32_t n_hash_tables;       /* 4^(seedLen-16), SNAPLib/GenomeIndex.cpp:316                */
+    uint32_t overflow_table_size; /* in 32-bit words                                            */
+    uint32_t chromosome_padding;
+    uint64_t hash_table_entries;  /* sum of tableSize over all tables (12 B each)               */
+    uint64_t device_bytes;        /* HBM held by this handle                                    */
+    int32_t device;
+} snapb200_index_info;
+
+/* Replaces GenomeIndex::loadFromDirectory (SNAPLib/GenomeIndex.cpp:844-963) + Genome::loadFromFile
+ * (SNAPLib/Genome.cpp:161-261): reads `GenomeIndex`, `GenomeIndexHash`, `OverflowTable`, `Genome` from
+ * `dir` and places them in the HBM of CUDA device `device`. */
+int snapb200_index_open(const char *dir, int device, snapb200_index **out);
+
+/* Same, from host memory already laid out like the files (used by tests and by hosts that keep the
+ * reference's in-memory index): `tables` = concatenation of n_hash_tables tables of 12-byte entries
+ * {key,value1,value2} (SNAPLib/HashTable.h:119-123), `table_sizes[i]` entries each; `overflow` =
+ * OverflowTable words; `bases` = n_bases genome bytes (1 byte/base, 'n' padding included);
+ * piece_offsets = Piece::beginningOffset of each piece (SNAPLib/Genome.h:155-158). */
+int snapb200_index_from_memory(int device, uint32_t seed_len, uint32_t chromosome_padding,
+                               uint32_t n_hash_tables, const uint64_t *table_sizes, const void *tables,
+                               const uint32_t *overflow, uint32_t overflow_words,
+                               const uint8_t *bases, uint32_t n_bases,
+                               const uint32_t *piece_offsets, uint32_t n_pieces,
+                               snapb200_index **out);
+
+int snapb200_index_info_get(const snapb200_index *idx, snapb200_index_info *info);
+void snapb200_index_close(snapb200_index *idx);
+
+/* ---- read batches --------------------------------------------------------------------------------- */
+
+/* n clipped reads in ASCII (Read::getData/getQuality/getDataLength, SNAPLib/Read.h:335-339), upper case
+ * (Read::init upper-cases, SNAPLib/Read.h:307-327).  Read i occupies bases[offsets[i] .. offsets[i+1]). */
+typedef struct {
+    uint32_t n;
+    const uint32_t *offsets; /* n+1 entries, offsets[0] == 0 */
+    const uint8_t *bases;
+    const uint8_t *quals;
+} snapb200_read_batch;
+
+/* ---- single-end: BaseAligner ---------------------------------------------------------------------- */
+
+/* Constructor + setter arguments of BaseAligner (SNAPLib/BaseAligner.cpp:46-61, BaseAligner.h:138-142). */
+typedef struct {
+    uint32_t max_hits;             /* maxHitsToConsider (-h)                                     */
+    uint32_t max_k;                /* maxK (-d)                                                  */
+    uint32_t max_read_size;        /* maxReadSize (MAX_READ_LENGTH in both run loops)            */
+    uint32_t num_seeds;            /* maxSeedsToUseFromCommandLine (-n); 0 => use seed_coverage  */
+    double seed_coverage;          /* maxSeedCoverage (-sc)                                      */
+    uint32_t extra_search_depth;   /* -D                                                         */
+    uint32_t explore_popular_seeds; /* -x                                                        */
+    uint32_t stop_on_first_hit;    /* -f                                                         */
+    uint32_t max_hits_to_get;      /* AlignRead's maxHitsToGet (0 => no multi-hit capture)       */
+} snapb200_single_params;
+
+/* Out-parameters of BaseAligner::AlignRead (SNAPLib/BaseAligner.cpp:510-524) plus the two probabilities
+ * computeMAPQ consumed and the per-read counters (BaseAligner.h:167-171), for checking. */
+typedef struct {
+    uint32_t location;  /* *genomeLocation (0xffffffff when none)                               */
+    int32_t score;      /* *finalScore (0xffff when unused)                                     */
+    int32_t mapq;       /* *mapq (0 where the reference leaves it unwritten)                    */
+    uint8_t status;     /* return value: NotFound/SingleHit/MultipleHits                        */
+    uint8_t direction;  /* *hitDirection                                                        */
+    uint16_t popular_seeds_skipped;
+    uint32_t n_lookups; /* lookupSeed calls for this read (nHashTableLookups delta)             */
+    uint32_t n_scored;  /* candidate locations LV-scored (nLocationsScored delta)               */
+    double p_all;       /* probabilityOfAllCandidates at exit                                   */
+    double p_best;      /* probabilityOfBestCandidate at exit                                   */
+} snapb200_single_result;
+
+/* Replaces BaseAligner::AlignRead, 5-argument form (SNAPLib/BaseAligner.cpp:196-200), for a batch. */
+int snapb200_single_batch(snapb200_index *idx, const snapb200_single_params *params,
+                          const snapb200_read_batch *reads, snapb200_single_result *results);
+
+/* Replaces the 13-argument AlignRead with maxHitsToGet > 0 (SNAPLib/BaseAligner.cpp:510-524, 940-975;
+ * caller SNAPLib/PairedAligner.cpp:584-614).  hit_* are [n][params->max_hits_to_get]; hit_counts[i] =
+ * *multiHitsFound. */
+int snapb200_single_multihit_batch(snapb200_index *idx, const snapb200_single_params *params,
+                                   const snapb200_read_batch *reads, snapb200_single_result *results,
+                                   int32_t *hit_counts, uint32_t *hit_locations, uint8_t *hit_rcs,
+                                   int32_t *hit_scores);
+
+/* ---- paired-end: ChimericPairedEndAligner over IntersectingPairedEndAligner ------------------------- */
+
+/* Constructor arguments of IntersectingPairedEndAligner (SNAPLib/IntersectingPairedEndAligner.cpp:34-49)
+ * and ChimericPairedEndAligner (SNAPLib/ChimericPairedEndAligner.cpp:41-61). */
+typedef struct {
+    uint32_t max_hits;            /* maxHits of the single-end fallback BaseAligner (-h)         */
+    uint32_t max_k;               /* -d                                                          */
+    uint32_t max_read_size;
+    uint32_t num_seeds;           /* -n (0 => seed_coverage)                                     */
+    double seed_coverage;
+    uint32_t min_spacing;         /* -s min                                                      */
+    uint32_t max_spacing;         /* -s max                                                      */
+    uint32_t force_spacing;       /* -fs                                                         */
+    uint32_t max_big_hits;        /* intersectingAlignerMaxHits (-H)                             */
+    uint32_t extra_search_depth;  /* -D                                                          */
+    uint32_t max_candidate_pool_size; /* -mcp                                                    */
+} snapb200_paired_params;
+
+/* PairedAlignmentResult (SNAPLib/PairedEndAligner.h:31-56) fields the aligners fill, plus the pair
+ * probabilities fed to computeMAPQ (IntersectingPairedEndAligner.cpp:741). */
+typedef struct {
+    uint32_t location[2];
+    int32_t score[2];
+    int32_t mapq[2];
+    uint8_t status[2];
+    uint8_t direction[2];
+    uint8_t from_align_together;
+    uint8_t aligned_as_pair;
+    uint16_t pad;
+    uint32_t n_lv_calls; /* scoreLocation calls in the intersecting aligner for this pair          */
+    uint32_t n_lookups;  /* lookupSeed calls in the intersecting aligner for this pair             */
+    double p_all;        /* probabilityOfAllPairs  (0 when the intersecting aligner returned early) */
+    double p_best;       /* probabilityOfBestPair                                                  */
+} snapb200_paired_result;
+
+/* Replaces ChimericPairedEndAligner::align (SNAPLib/ChimericPairedEndAligner.cpp:74-128), i.e.
+ * IntersectingPairedEndAligner::align (SNAPLib/IntersectingPairedEndAligner.cpp:141-753) plus the
+ * per-end BaseAligner fallback with mapq/4.  reads0->n must equal reads1->n. */
+int snapb200_paired_batch(snapb200_index *idx, const snapb200_paired_params *params,
+                          const snapb200_read_batch *reads0, const snapb200_read_batch *reads1,
+                          snapb200_paired_result *results);
+
+/* ---- CIGAR: LandauVishkinWithCigar at SAM-write time ------------------------------------------------ */
+
+/* Replaces SAMFormat::computeCigarString's aligner call (SNAPLib/SAM.cpp:1159-1189) for a batch: read i
+ * (clipped, as given to the aligner; reverse-complemented on the device when directions[i]==RC, as
+ * SAM.cpp:870-880 does) is re-aligned against genome[locations[i], +len) with k = MAX_K-1 and the
+ * COMPACT_CIGAR_STRING written NUL-terminated to cigars + i*cigar_stride.  edit_distance[i] is the return
+ * value of LandauVishkinWithCigar::computeEditDistance (-1: > k, -2: buffer too small, -3: location invalid
+ * or off the end of the genome, where the reference prints "*").  Soft-clip decoration stays on the host. */
+int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_batch *reads, const uint32_t *locations,
+                         const uint8_t *directions, int use_m, char *cigars, uint32_t cigar_stride,
+                         int32_t *edit_distance);
+
+/* ---- building blocks exposed for known-answer tests -------------------------------------------------- */
+
+/* LandauVishkin<+1/-1>::computeEditDistance (SNAPLib/LandauVishkin.h:211-455) on explicit strings.
+ * Item i: text = texts[text_offsets[i] .. text_offsets[i+1]), pattern/quality likewise.  For
+ * text_direction == -1 the text is given in memory order and is walked backwards from its END (the
+ * reference is handed a pointer one past the last byte).  Bytes outside either string never match.
+ * quals may be NULL (then match_probability is not produced).  Outputs: score (-1 if > k),
+ * match_probability, net_indel. */
+int snapb200_lv_batch(int device, int text_direction, uint32_t n, const uint32_t *text_offsets,
+                      const uint8_t *texts, const uint32_t *pattern_offsets, const uint8_t *patterns,
+                      const uint8_t *quals, const int32_t *k, int32_t *score, double *match_probability,
+                      int32_t *net_indel);
+
+/* LandauVishkinWithCigar::computeEditDistance (SNAPLib/LandauVishkin.cpp:252-535) on explicit strings,
+ * COMPACT_CIGAR_STRING format. */
+int snapb200_lv_cigar_batch(int device, uint32_t n, const uint32_t *text_offsets, const uint8_t *texts,
+                            const uint32_t *pattern_offsets, const uint8_t *patterns, const int32_t *k,
+                            int use_m, char *cigars, uint32_t cigar_stride, int32_t *edit_distance);
+
+/* GenomeIndex::lookupSeed (SNAPLib/GenomeIndex.cpp:971-1011) for n seeds given as ASCII (seed_len bytes
+ * each, contiguous).  n_hits is [n][2] (forward, reverse complement); up to max_out hits per direction are
+ * copied to hits[(i*2+dir)*max_out ..].  A seed containing a non-ACGT byte yields 0/0. */
+int snapb200_lookup_seed_batch(snapb200_index *idx, uint32_t n, const uint8_t *seeds, uint32_t max_out,
+                               uint32_t *n_hits, uint32_t *hits);
+
+/* computeMAPQ (SNAPLib/mapq.h:32-65), evaluated on the device the way the aligner kernels do. */
+int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, const double *p_best,
+                        const int32_t *score, const int32_t *popular_seeds_skipped, int32_t *mapq);
+
+/* ---- device-resident sessions (what bench.py times; also what a pipelined host uses) ---------------- */
+
+typedef struct snapb200_session snapb200_session; /* device buffers + stream for batches of <= max_reads */
+
+int snapb200_session_create(snapb200_index *idx, uint32_t max_pairs_or_reads, uint32_t max_read_len,
+                            snapb200_session **out);
+void snapb200_session_destroy(snapb200_session *s);
+/* async H2D of a batch into mate slot 0/1 (slot 0 for single-end) from (preferably pinned) host memory */
+int snapb200_session_upload(snapb200_session *s, int slot, const snapb200_read_batch *reads);
+/* run the kernels on the resident batch; no host<->device copies */
+int snapb200_session_run_single(snapb200_session *s, const snapb200_single_params *p);
+int snapb200_session_run_paired(snapb200_session *s, const snapb200_paired_params *p);
+/* async D2H of the results of the last run, then stream synchronize */
+int snapb200_session_download_single(snapb200_session *s, snapb200_single_result *results);
+int snapb200_session_download_paired(snapb200_session *s, snapb200_paired_result *results);
+int snapb200_session_sync(snapb200_session *s);
+/* CUDA-event time of the last run's kernels (ms), kernel launches issued by the last run, and the number
+ * of launches since the session was created. */
+int snapb200_session_last_run(const snapb200_session *s, float *kernel_ms, uint32_t *launches,
+                              uint64_t *total_launches);
+
+/* ---- statistics (AlignerStats, SNAPLib/AlignerStats.h:45-60) ------------------------------------------ */
+
+typedef struct {
+    int64_t total_reads, useful_reads, single_hits, multi_hits, not_found, errors, aligned_as_pairs, lv_calls;
+    int64_t n_hash_table_lookups, n_locations_scored, n_hits_ignored_popularity, n_reads_ignored_ns;
+    int64_t mapq_histogram[71];
+} snapb200_stats;
+#define SNAPB200_STATS_WORDS (12 + 71)
+
+/* Accumulated over every batch run on this index handle since the last reset; a flat int64 vector so that
+ * the multi-GPU host can sum it with one all-reduce (NCCL), as AlignerStats::add does per thread
+ * (SNAPLib/AlignerStats.cpp:75-102). */
+int snapb200_stats_get(snapb200_index *idx, snapb200_stats *out);
+int snapb200_stats_reset(snapb200_index *idx);
+
+const char *snapb200_last_error(void);
+int snapb200_abi_version(void);
+int snapb200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPB200_H */

@@ -1,0 +1,400 @@
+// ref_driver.cpp -- C API over the UNMODIFIED reference classes (TEST INFRASTRUCTURE ONLY).
+//
+// Linked by oracle/build_ref.py against the reference's own objects into oracle/_ref/libsnapref.so.
+// It contains no alignment logic of its own: every function constructs the reference object the run
+// loops construct (SNAPLib/SingleAligner.cpp:167-181, SNAPLib/PairedAligner.cpp:459-481) and calls the
+// reference method, copying its out-parameters into the structs of include/snapb200.h so that the
+// oracle port, the reference and the CUDA library can be compared field by field.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load this.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <pthread.h>
+#include <map>
+#include <set>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+// The reference keeps the probabilities computeMAPQ consumes in private members; the driver reads them.
+#define private public
+#define protected public
+#include "stdafx.h"
+#include "Compat.h"
+#include "Genome.h"
+#include "GenomeIndex.h"
+#include "Seed.h"
+#include "Read.h"
+#include "LandauVishkin.h"
+#include "BaseAligner.h"
+#include "IntersectingPairedEndAligner.h"
+#include "ChimericPairedEndAligner.h"
+#include "mapq.h"
+#include "Tables.h"
+#include "BigAlloc.h"
+#undef private
+#undef protected
+
+#include "../include/snapb200.h"
+
+extern "C" {
+
+int ref_init(void)
+{
+    initializeLVProbabilitiesToPhredPlus33(); // SNAPLib/AlignerOptions.cpp:84 does this for every run
+    return 0;
+}
+
+void *ref_index_load(const char *dir)
+{
+    ref_init();
+    char *d = strdup(dir);
+    GenomeIndex *idx = GenomeIndex::loadFromDirectory(d);
+    free(d);
+    return idx;
+}
+
+int ref_index_info(void *h, snapb200_index_info *info)
+{
+    GenomeIndex *idx = (GenomeIndex *)h;
+    memset(info, 0, sizeof(*info));
+    info->n_bases = idx->getGenome()->getCountOfBases();
+    info->n_pieces = idx->getGenome()->getNumPieces();
+    info->seed_len = idx->getSeedLength();
+    info->n_hash_tables = idx->nHashTables;
+    info->overflow_table_size = idx->overflowTableSize;
+    info->chromosome_padding = idx->getGenome()->chromosomePadding;
+    for (unsigned i = 0; i < idx->nHashTables; i++) info->hash_table_entries += idx->hashTables[i]->GetTableSize();
+    info->device = -1;
+    return 0;
+}
+
+// copies genome bytes [from, from+len) (no bounds games: caller stays inside [0,nBases))
+int ref_genome_bytes(void *h, unsigned from, unsigned len, unsigned char *out)
+{
+    GenomeIndex *idx = (GenomeIndex *)h;
+    const Genome *g = idx->getGenome();
+    if ((size_t)from + len > g->getCountOfBases()) return -1;
+    memcpy(out, g->bases + from, len);
+    return 0;
+}
+
+int ref_piece_offsets(void *h, unsigned *out)
+{
+    const Genome *g = ((GenomeIndex *)h)->getGenome();
+    for (int i = 0; i < g->getNumPieces(); i++) out[i] = g->getPieces()[i].beginningOffset;
+    return g->getNumPieces();
+}
+
+int ref_lookup_seed_batch(void *h, unsigned n, const unsigned char *seeds, unsigned max_out, unsigned *n_hits,
+                          unsigned *hits)
+{
+    GenomeIndex *idx = (GenomeIndex *)h;
+    unsigned L = idx->getSeedLength();
+    for (unsigned i = 0; i < n; i++) {
+        const char *s = (const char *)seeds + (size_t)i * L;
+        unsigned nh[2] = {0, 0};
+        const unsigned *hp[2] = {NULL, NULL};
+        if (Seed::DoesTextRepresentASeed(s, L)) {
+            Seed seed(s, L);
+            idx->lookupSeed(seed, &nh[0], &hp[0], &nh[1], &hp[1]);
+        }
+        for (int d = 0; d < 2; d++) {
+            n_hits[i * 2 + d] = nh[d];
+            for (unsigned j = 0; j < nh[d] && j < max_out; j++) hits[((size_t)i * 2 + d) * max_out + j] = hp[d][j];
+        }
+    }
+    return 0;
+}
+
+// Explicit-string LV.  The reference compares 8 bytes at a time and may peek past either string, so each
+// string is copied into a padded buffer whose padding can never match the other string's padding.
+static const int PAD = 64;
+
+int ref_lv_batch(int text_direction, unsigned n, const unsigned *text_offsets, const unsigned char *texts,
+                 const unsigned *pattern_offsets, const unsigned char *patterns, const unsigned char *quals,
+                 const int *k, int *score, double *match_probability, int *net_indel)
+{
+    ref_init();
+    LandauVishkin<1> *fwd = new LandauVishkin<1>();
+    LandauVishkin<-1> *rev = new LandauVishkin<-1>();
+    std::vector<char> tbuf, pbuf, qbuf;
+    for (unsigned i = 0; i < n; i++) {
+        int tl = text_offsets[i + 1] - text_offsets[i];
+        int pl = pattern_offsets[i + 1] - pattern_offsets[i];
+        tbuf.assign(tl + 2 * PAD, 1);
+        pbuf.assign(pl + 2 * PAD, 0);
+        qbuf.assign(pl + 2 * PAD, '!');
+        memcpy(&tbuf[PAD], texts + text_offsets[i], tl);
+        memcpy(&pbuf[PAD], patterns + pattern_offsets[i], pl);
+        if (quals) memcpy(&qbuf[PAD], quals + pattern_offsets[i], pl);
+        double prob = 0;
+        int indel = 0;
+        int s;
+        if (text_direction == 1) {
+            s = fwd->computeEditDistance(&tbuf[PAD], tl, &pbuf[PAD], quals ? &qbuf[PAD] : NULL, pl, k[i],
+                                         quals ? &prob : NULL, 0, &indel);
+        } else {
+            s = rev->computeEditDistance(&tbuf[PAD] + tl, tl, &pbuf[PAD], quals ? &qbuf[PAD] : NULL, pl, k[i],
+                                         quals ? &prob : NULL, 0, &indel);
+        }
+        score[i] = s;
+        if (match_probability) match_probability[i] = prob;
+        if (net_indel) net_indel[i] = indel;
+    }
+    delete fwd;
+    delete rev;
+    return 0;
+}
+
+int ref_lv_cigar_batch(unsigned n, const unsigned *text_offsets, const unsigned char *texts,
+                       const unsigned *pattern_offsets, const unsigned char *patterns, const int *k, int use_m,
+                       char *cigars, unsigned cigar_stride, int *edit_distance)
+{
+    LandauVishkinWithCigar *lv = new LandauVishkinWithCigar();
+    std::vector<char> tbuf, pbuf;
+    for (unsigned i = 0; i < n; i++) {
+        int tl = text_offsets[i + 1] - text_offsets[i];
+        int pl = pattern_offsets[i + 1] - pattern_offsets[i];
+        tbuf.assign(tl + 2 * PAD, 1);
+        pbuf.assign(pl + 2 * PAD, 0);
+        memcpy(&tbuf[PAD], texts + text_offsets[i], tl);
+        memcpy(&pbuf[PAD], patterns + pattern_offsets[i], pl);
+        std::vector<unsigned> tokens;
+        char *out = cigars + (size_t)i * cigar_stride;
+        memset(out, 0, cigar_stride);
+        edit_distance[i] = lv->computeEditDistance(&tbuf[PAD], tl, &pbuf[PAD], pl, k[i], out, cigar_stride,
+                                                   use_m != 0, tokens);
+    }
+    delete lv;
+    return 0;
+}
+
+int ref_mapq_batch(unsigned n, const double *p_all, const double *p_best, const int *score, const int *popular,
+                   int *mapq)
+{
+    for (unsigned i = 0; i < n; i++) mapq[i] = computeMAPQ(p_all[i], p_best[i], score[i], popular[i]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Threaded batch drivers.  One aligner object per thread, exactly like the reference's run loops.
+// ------------------------------------------------------------------------------------------------
+struct SingleJob {
+    GenomeIndex *idx;
+    const snapb200_single_params *p;
+    const snapb200_read_batch *reads;
+    snapb200_single_result *res;
+    int *hit_counts;
+    unsigned *hit_locations;
+    unsigned char *hit_rcs;
+    int *hit_scores;
+    unsigned begin, end;
+};
+
+static void *single_worker(void *arg)
+{
+    SingleJob *j = (SingleJob *)arg;
+    const snapb200_single_params *p = j->p;
+    BaseAligner *a = new BaseAligner(j->idx, p->max_hits, p->max_k, p->max_read_size, p->num_seeds, p->seed_coverage,
+                                     p->extra_search_depth, NULL, NULL, NULL, NULL);
+    a->setExplorePopularSeeds(p->explore_popular_seeds != 0);
+    a->setStopOnFirstHit(p->stop_on_first_hit != 0);
+    unsigned mh = p->max_hits_to_get;
+    std::vector<char> bases, quals; // padded copies: the reference reads 8 bytes at a time past the read
+    bool *rcs = mh ? new bool[mh] : NULL;
+    for (unsigned i = j->begin; i < j->end; i++) {
+        unsigned off = j->reads->offsets[i], len = j->reads->offsets[i + 1] - off;
+        bases.assign(len + PAD, '\n');
+        quals.assign(len + PAD, '\n');
+        memcpy(&bases[0], j->reads->bases + off, len);
+        memcpy(&quals[0], j->reads->quals + off, len);
+        Read read;
+        read.init(NULL, 0, &bases[0], &quals[0], len);
+        snapb200_single_result *r = &j->res[i];
+        memset(r, 0, sizeof(*r));
+        unsigned loc = InvalidGenomeLocation;
+        Direction dir = FORWARD;
+        int score = 0, mapq = 0;
+        _int64 l0 = a->getNHashTableLookups(), s0 = a->getLocationsScored();
+        a->probabilityOfAllCandidates = 0;
+        a->probabilityOfBestCandidate = 0;
+        a->popularSeedsSkipped = 0;
+        AlignmentResult st;
+        if (mh) {
+            int found = 0;
+            st = a->AlignRead(&read, &loc, &dir, &score, &mapq, 0, 0, FORWARD, (int)mh, &found,
+                              j->hit_locations + (size_t)i * mh, rcs, j->hit_scores + (size_t)i * mh);
+            j->hit_counts[i] = found;
+            for (int q = 0; q < found; q++) j->hit_rcs[(size_t)i * mh + q] = rcs[q] ? 1 : 0;
+        } else {
+            st = a->AlignRead(&read, &loc, &dir, &score, &mapq);
+        }
+        r->status = (uint8_t)st;
+        r->location = loc;
+        r->direction = (uint8_t)dir;
+        r->score = score;
+        r->mapq = mapq;
+        r->popular_seeds_skipped = (uint16_t)a->popularSeedsSkipped;
+        r->n_lookups = (uint32_t)(a->getNHashTableLookups() - l0);
+        r->n_scored = (uint32_t)(a->getLocationsScored() - s0);
+        r->p_all = a->probabilityOfAllCandidates;
+        r->p_best = a->probabilityOfBestCandidate;
+    }
+    delete[] rcs;
+    delete a;
+    return NULL;
+}
+
+static int run_single(void *h, const snapb200_single_params *p, const snapb200_read_batch *reads,
+                      snapb200_single_result *res, int *hc, unsigned *hl, unsigned char *hr, int *hs, int nthreads)
+{
+    ref_init();
+    if (nthreads < 1) nthreads = 1;
+    std::vector<SingleJob> jobs(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        SingleJob &j = jobs[t];
+        j.idx = (GenomeIndex *)h; j.p = p; j.reads = reads; j.res = res;
+        j.hit_counts = hc; j.hit_locations = hl; j.hit_rcs = hr; j.hit_scores = hs;
+        j.begin = (unsigned)((unsigned long long)reads->n * t / nthreads);
+        j.end = (unsigned)((unsigned long long)reads->n * (t + 1) / nthreads);
+    }
+    if (nthreads == 1) { single_worker(&jobs[0]); return 0; }
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, single_worker, &jobs[t]);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+
+int ref_single_batch(void *h, const snapb200_single_params *p, const snapb200_read_batch *reads,
+                     snapb200_single_result *res, int nthreads)
+{
+    snapb200_single_params q = *p;
+    q.max_hits_to_get = 0;
+    return run_single(h, &q, reads, res, NULL, NULL, NULL, NULL, nthreads);
+}
+
+int ref_single_multihit_batch(void *h, const snapb200_single_params *p, const snapb200_read_batch *reads,
+                              snapb200_single_result *res, int *hit_counts, unsigned *hit_locations,
+                              unsigned char *hit_rcs, int *hit_scores, int nthreads)
+{
+    return run_single(h, p, reads, res, hit_counts, hit_locations, hit_rcs, hit_scores, nthreads);
+}
+
+struct PairedJob {
+    GenomeIndex *idx;
+    const snapb200_paired_params *p;
+    const snapb200_read_batch *r0, *r1;
+    snapb200_paired_result *res;
+    unsigned begin, end;
+};
+
+static void *paired_worker(void *arg)
+{
+    PairedJob *j = (PairedJob *)arg;
+    const snapb200_paired_params *p = j->p;
+    GenomeIndex *index = j->idx;
+    // SNAPLib/PairedAligner.cpp:459-481
+    size_t pool = IntersectingPairedEndAligner::getBigAllocatorReservation(
+        index, p->max_big_hits, p->max_read_size, index->getSeedLength(), p->num_seeds, p->seed_coverage, p->max_k,
+        p->extra_search_depth, p->max_candidate_pool_size);
+    BigAllocator *alloc = new BigAllocator(pool);
+    IntersectingPairedEndAligner *inter = new IntersectingPairedEndAligner(
+        index, p->max_read_size, p->max_hits, p->max_k, p->num_seeds, p->seed_coverage, p->min_spacing, p->max_spacing,
+        p->max_big_hits, p->extra_search_depth, p->max_candidate_pool_size, alloc);
+    ChimericPairedEndAligner *chim = new ChimericPairedEndAligner(
+        index, p->max_read_size, p->max_hits, p->max_k, p->num_seeds, p->seed_coverage, p->min_spacing, p->max_spacing,
+        p->force_spacing != 0, p->extra_search_depth, inter);
+    std::vector<char> b[2], q[2];
+    for (unsigned i = j->begin; i < j->end; i++) {
+        Read reads[2];
+        const snapb200_read_batch *rb[2] = {j->r0, j->r1};
+        for (int e = 0; e < 2; e++) {
+            unsigned off = rb[e]->offsets[i], len = rb[e]->offsets[i + 1] - off;
+            b[e].assign(len + PAD, '\n');
+            q[e].assign(len + PAD, '\n');
+            memcpy(&b[e][0], rb[e]->bases + off, len);
+            memcpy(&q[e][0], rb[e]->quals + off, len);
+            reads[e].init(NULL, 0, &b[e][0], &q[e][0], len);
+        }
+        PairedAlignmentResult pr;
+        memset(&pr, 0, sizeof(pr)); // the reference leaves this uninitialised (PairedAligner.cpp:577)
+        pr.location[0] = pr.location[1] = InvalidGenomeLocation;
+        _int64 s0 = inter->getLocationsScored();
+        inter->countOfHashTableLookups[0] = inter->countOfHashTableLookups[1] = 0;
+        chim->align(&reads[0], &reads[1], &pr);
+        snapb200_paired_result *r = &j->res[i];
+        memset(r, 0, sizeof(*r));
+        for (int e = 0; e < 2; e++) {
+            r->location[e] = pr.location[e];
+            r->score[e] = pr.score[e];
+            r->mapq[e] = pr.mapq[e];
+            r->status[e] = (uint8_t)pr.status[e];
+            r->direction[e] = (uint8_t)pr.direction[e];
+        }
+        r->from_align_together = pr.fromAlignTogether;
+        r->aligned_as_pair = pr.alignedAsPair;
+        r->n_lv_calls = (uint32_t)(inter->getLocationsScored() - s0);
+        r->n_lookups = inter->countOfHashTableLookups[0] + inter->countOfHashTableLookups[1];
+        r->p_all = NAN; // locals of align() in the reference; only the port and the CUDA path expose them
+        r->p_best = NAN;
+    }
+    delete chim;
+    inter->~IntersectingPairedEndAligner();
+    delete alloc;
+    return NULL;
+}
+
+int ref_paired_batch(void *h, const snapb200_paired_params *p, const snapb200_read_batch *r0,
+                     const snapb200_read_batch *r1, snapb200_paired_result *res, int nthreads)
+{
+    ref_init();
+    if (nthreads < 1) nthreads = 1;
+    std::vector<PairedJob> jobs(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        PairedJob &j = jobs[t];
+        j.idx = (GenomeIndex *)h; j.p = p; j.r0 = r0; j.r1 = r1; j.res = res;
+        j.begin = (unsigned)((unsigned long long)r0->n * t / nthreads);
+        j.end = (unsigned)((unsigned long long)r0->n * (t + 1) / nthreads);
+    }
+    if (nthreads == 1) { paired_worker(&jobs[0]); return 0; }
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, paired_worker, &jobs[t]);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+
+// SAMFormat::computeCigarString's aligner call (SNAPLib/SAM.cpp:1159-1189): text = genome at location,
+// textLen = patternLen = read length, k = MAX_K-1.  RC reads are complemented first (SAM.cpp getSAMData).
+int ref_cigar_batch(void *h, const snapb200_read_batch *reads, const unsigned *locations,
+                    const unsigned char *directions, int use_m, char *cigars, unsigned cigar_stride,
+                    int *edit_distance)
+{
+    GenomeIndex *idx = (GenomeIndex *)h;
+    const Genome *genome = idx->getGenome();
+    LandauVishkinWithCigar *lv = new LandauVishkinWithCigar();
+    std::vector<char> pbuf;
+    for (unsigned i = 0; i < reads->n; i++) {
+        unsigned off = reads->offsets[i], len = reads->offsets[i + 1] - off;
+        char *out = cigars + (size_t)i * cigar_stride;
+        memset(out, 0, cigar_stride);
+        if (locations[i] == InvalidGenomeLocation) { edit_distance[i] = -3; continue; }
+        const char *ref = genome->getSubstring(locations[i], len);
+        if (ref == NULL) { edit_distance[i] = -3; continue; }
+        pbuf.assign(len + PAD, 0);
+        if (directions[i] == RC) {
+            for (unsigned q = 0; q < len; q++) pbuf[q] = COMPLEMENT[reads->bases[off + len - 1 - q]];
+        } else {
+            memcpy(&pbuf[0], reads->bases + off, len);
+        }
+        std::vector<unsigned> tokens;
+        edit_distance[i] = lv->computeEditDistance(ref, len, &pbuf[0], len, MAX_K - 1, out, cigar_stride, use_m != 0,
+                                                   tokens);
+    }
+    delete lv;
+    return 0;
+}
+
+} // extern "C"

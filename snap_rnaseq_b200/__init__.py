@@ -1,0 +1,204 @@
+"""snap_rnaseq_b200 -- B200-native alignment core for SNAP-RNA behind a C ABI (include/snapb200.h).
+
+This Python layer is only a binding: it loads the in-tree ``libsnapb200.so`` (hand-written sm_100a CUDA) and
+mirrors the reference's class names for the path (GenomeIndex, BaseAligner, ChimericPairedEndAligner,
+LandauVishkin, SAMFormat.computeCigarString) in batch form.  There is no CPU implementation here: if the
+library is missing or no CUDA device is present, calls fail.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+from ._abi import (Batch, IndexInfo, PairedParams, SingleParams, paired_defaults, single_defaults,  # noqa: F401
+                   PAIRED_RESULT, SINGLE_RESULT)
+from ._binding import BatchLib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libsnapb200.so")
+_lib = None
+
+
+class Snapb200(BatchLib):
+    """The C ABI of libsnapb200.so."""
+
+    def __init__(self, cdll, device=0):
+        super().__init__(cdll, "snapb200_", device=device)
+        cdll.snapb200_last_error.restype = C.c_char_p
+
+    def load_index(self, d, device=None):
+        h = C.c_void_p()
+        dev = self.device if device is None else device
+        self._check(self.lib.snapb200_index_open(str(d).encode(), C.c_int(dev), C.byref(h)), "index_open")
+        return h
+
+    def index_from_memory(self, seed_len, padding, table_sizes, tables, overflow, bases, piece_offsets, device=None):
+        h = C.c_void_p()
+        dev = self.device if device is None else device
+        ts = np.ascontiguousarray(table_sizes, np.uint64)
+        tb = np.ascontiguousarray(tables, np.uint32)
+        ov = np.ascontiguousarray(overflow, np.uint32)
+        bs = np.ascontiguousarray(bases, np.uint8)
+        po = np.ascontiguousarray(piece_offsets, np.uint32)
+        self._check(self.lib.snapb200_index_from_memory(
+            C.c_int(dev), C.c_uint32(seed_len), C.c_uint32(padding), C.c_uint32(len(ts)),
+            ts.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), ov.ctypes.data_as(C.c_void_p),
+            C.c_uint32(ov.size), bs.ctypes.data_as(C.c_void_p), C.c_uint32(bs.size), po.ctypes.data_as(C.c_void_p),
+            C.c_uint32(po.size), C.byref(h)), "index_from_memory")
+        return h
+
+    def index_info(self, h):
+        info = IndexInfo()
+        self._check(self.lib.snapb200_index_info_get(h, C.byref(info)), "index_info_get")
+        return info
+
+    def close_index(self, h):
+        self.lib.snapb200_index_close.restype = None
+        self.lib.snapb200_index_close(h)
+
+    def stats(self, h):
+        w = np.zeros(A.STATS_WORDS, np.int64)
+        self._check(self.lib.snapb200_stats_get(h, w.ctypes.data_as(C.c_void_p)), "stats_get")
+        return w
+
+    def stats_reset(self, h):
+        self._check(self.lib.snapb200_stats_reset(h), "stats_reset")
+
+    def device_count(self):
+        return int(self.lib.snapb200_device_count())
+
+
+class Session:
+    """Device-resident batch (snapb200_session_*): upload once, run the kernels, download."""
+
+    def __init__(self, lib, index, max_items, max_read_len=A.MAX_READ_LENGTH):
+        self.lib = lib
+        self.h = C.c_void_p()
+        lib._check(lib.lib.snapb200_session_create(index, C.c_uint32(max_items), C.c_uint32(max_read_len), C.byref(self.h)),
+                   "session_create")
+
+    def upload(self, slot, batch):
+        self.lib._check(self.lib.lib.snapb200_session_upload(self.h, C.c_int(slot), batch.byref()), "session_upload")
+
+    def upload_raw(self, slot, n, offsets_ptr, bases_ptr, quals_ptr):
+        rb = A.ReadBatch(n, C.cast(offsets_ptr, C.POINTER(C.c_uint32)), C.cast(bases_ptr, C.POINTER(C.c_uint8)),
+                         C.cast(quals_ptr, C.POINTER(C.c_uint8)))
+        self.lib._check(self.lib.lib.snapb200_session_upload(self.h, C.c_int(slot), C.byref(rb)), "session_upload")
+
+    def run_single(self, params):
+        self.lib._check(self.lib.lib.snapb200_session_run_single(self.h, C.byref(params)), "session_run_single")
+
+    def run_paired(self, params):
+        self.lib._check(self.lib.lib.snapb200_session_run_paired(self.h, C.byref(params)), "session_run_paired")
+
+    def download_single(self, out):
+        self.lib._check(self.lib.lib.snapb200_session_download_single(self.h, out.ctypes.data_as(C.c_void_p)), "download_single")
+        return out
+
+    def download_paired(self, out):
+        self.lib._check(self.lib.lib.snapb200_session_download_paired(self.h, out.ctypes.data_as(C.c_void_p)), "download_paired")
+        return out
+
+    def download_paired_ptr(self, ptr):
+        self.lib._check(self.lib.lib.snapb200_session_download_paired(self.h, C.c_void_p(ptr)), "download_paired")
+
+    def sync(self):
+        self.lib._check(self.lib.lib.snapb200_session_sync(self.h), "session_sync")
+
+    def last_run(self):
+        ms, n, tot = C.c_float(), C.c_uint32(), C.c_uint64()
+        self.lib._check(self.lib.lib.snapb200_session_last_run(self.h, C.byref(ms), C.byref(n), C.byref(tot)), "last_run")
+        return ms.value, n.value, tot.value
+
+    def close(self):
+        if self.h:
+            self.lib.lib.snapb200_session_destroy.restype = None
+            self.lib.lib.snapb200_session_destroy(self.h)
+            self.h = None
+
+
+def lib(device=0):
+    """Load libsnapb200.so.  Raises if it has not been built: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing -- build it with `python -m snap_rnaseq_b200.build` "
+                               "(nvcc, sm_100a).  This package has no CPU fallback.")
+        _lib = Snapb200(C.CDLL(SO_PATH), device=device)
+    _lib.device = device
+    return _lib
+
+
+# ---- the reference's names for this path, in batch form ---------------------------------------------------------
+class GenomeIndex:
+    """GenomeIndex::loadFromDirectory (SNAPLib/GenomeIndex.cpp:844-963) -> index + genome resident in HBM."""
+
+    def __init__(self, handle, device):
+        self.h, self.device = handle, device
+
+    @classmethod
+    def loadFromDirectory(cls, directory, device=0):
+        return cls(lib(device).load_index(directory, device), device)
+
+    def getSeedLength(self):
+        return lib(self.device).index_info(self.h).seed_len
+
+    def getCountOfBases(self):
+        return lib(self.device).index_info(self.h).n_bases
+
+    def lookupSeed(self, seeds, max_out=64):
+        return lib(self.device).lookup(self.h, seeds, max_out)
+
+    def close(self):
+        if self.h:
+            lib(self.device).close_index(self.h)
+            self.h = None
+
+
+class BaseAligner:
+    """BaseAligner (SNAPLib/BaseAligner.h:41-143): same constructor arguments, AlignRead over a batch."""
+
+    def __init__(self, index, maxHitsToConsider, maxK, maxReadSize, maxSeedsToUse, maxSeedCoverage, extraSearchDepth):
+        self.index = index
+        self.params = SingleParams(max_hits=maxHitsToConsider, max_k=maxK, max_read_size=maxReadSize,
+                                   num_seeds=maxSeedsToUse, seed_coverage=maxSeedCoverage,
+                                   extra_search_depth=extraSearchDepth)
+
+    def setExplorePopularSeeds(self, v):
+        self.params.explore_popular_seeds = int(bool(v))
+
+    def setStopOnFirstHit(self, v):
+        self.params.stop_on_first_hit = int(bool(v))
+
+    def AlignRead(self, batch, maxHitsToGet=0):
+        L = lib(self.index.device)
+        if maxHitsToGet:
+            p = SingleParams.from_buffer_copy(self.params)
+            p.max_hits_to_get = maxHitsToGet
+            return L.single_multihit(self.index.h, p, batch)
+        return L.single(self.index.h, self.params, batch)
+
+
+class ChimericPairedEndAligner:
+    """ChimericPairedEndAligner over IntersectingPairedEndAligner (SNAPLib/ChimericPairedEndAligner.cpp:41-61,
+    SNAPLib/IntersectingPairedEndAligner.cpp:34-49): align() over a batch of pairs."""
+
+    def __init__(self, index, maxReadSize, maxHits, maxK, maxSeeds, maxSeedCoverage, minSpacing, maxSpacing, forceSpacing,
+                 extraSearchDepth, maxBigHits=16000, maxCandidatePoolSize=1000000):
+        self.index = index
+        self.params = PairedParams(max_hits=maxHits, max_k=maxK, max_read_size=maxReadSize, num_seeds=maxSeeds,
+                                   seed_coverage=maxSeedCoverage, min_spacing=minSpacing, max_spacing=maxSpacing,
+                                   force_spacing=int(bool(forceSpacing)), max_big_hits=maxBigHits,
+                                   extra_search_depth=extraSearchDepth, max_candidate_pool_size=maxCandidatePoolSize)
+
+    def align(self, batch0, batch1):
+        return lib(self.index.device).paired(self.index.h, self.params, batch0, batch1)
+
+
+class SAMFormat:
+    """The aligner call inside SAMFormat::computeCigarString (SNAPLib/SAM.cpp:1159-1189)."""
+
+    @staticmethod
+    def computeCigarString(index, batch, locations, directions, useM=False):
+        return lib(index.device).cigar(index.h, batch, locations, directions, useM)

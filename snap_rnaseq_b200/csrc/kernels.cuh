@@ -1,0 +1,396 @@
+// kernels.cuh -- the __global__ entry points.  One warp per work item, persistent grid, dynamic work fetch.
+#pragma once
+#include "paired.cuh"
+
+#define WARPS_PER_CTA 8
+#define CTA_THREADS (WARPS_PER_CTA * 32)
+
+struct DevBatch {  // a snapb200_read_batch resident in HBM
+    const uint32_t *offsets;
+    const uint8_t *bases, *quals;
+    uint32_t n;
+};
+
+struct Counters {  // device-side counters read back after each launch group
+    uint32_t work;        // next work item
+    uint32_t n_retry;     // items that overflowed the small scratch tier
+    uint32_t n_fallback;  // pairs that need the single-end fallback
+    uint32_t n_fix;       // mapq fix-up requests
+    uint32_t n_limit;     // items that hit a reference pool limit
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ uint32_t round8(uint32_t x) { return (x + 7u) & ~7u; }
+__host__ __device__ inline size_t lv_shared_bytes() { return ((size_t)LV_CELLS * 2 + 15) & ~(size_t)15; }
+
+__device__ __forceinline__ uint32_t fetch_work(uint32_t *counter)
+{
+    uint32_t w = 0;
+    if (lane_id() == 0) w = atomicAdd(counter, 1u);
+    return __shfl_sync(FULL_MASK, w, 0);
+}
+
+// ---- single end ---------------------------------------------------------------------------------------
+// Work item p in [0, n_items): result slot = positions ? positions[p] : p; read = items ? items[slot] : slot, where a
+// read id is idx*2+mate when two batches are given (fallback of pairs) and idx otherwise.
+struct SingleArgs {
+    DevIndex ix;
+    SingleCfg cfg;
+    DevBatch b[2];
+    int two_batches;
+    const uint32_t *positions, *items;
+    uint32_t n_items;
+    snapb200_single_result *results;
+    int32_t *mh_counts; uint32_t *mh_locs; uint8_t *mh_rcs; int32_t *mh_scores;
+    // scratch, laid out [warp slot][...]
+    Elem *pool; int2 *anchors; int *lists; uint32_t *epochs; uint32_t *hit_count, *hit_loc; uint8_t *hit_rc;
+    Counters *ctr; uint32_t *retry_list; MapqFix *fix; uint32_t fix_cap;
+    unsigned long long *stats;
+    int mapq_divisor;
+};
+
+__host__ __device__ inline size_t single_warp_shared(uint32_t rl)
+{
+    size_t s = (sizeof(SingleSm) + 15) & ~(size_t)15;
+    s += lv_shared_bytes();
+    s += 4 * (size_t)rl;                       // D[2], Q[2]
+    s += ((size_t)rl + 2 * WIN_SLACK + 15) & ~(size_t)15;  // W
+    return s;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) single_kernel(const SingleArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const size_t per_warp = single_warp_shared(a.cfg.rl);
+    uint8_t *base = smem + per_warp * warp;
+    SingleSm *sm = (SingleSm *)base;
+    base += (sizeof(SingleSm) + 15) & ~(size_t)15;
+    int16_t *L = (int16_t *)base;
+    base += lv_shared_bytes();
+    ReadView v;
+    v.D[0] = base; v.D[1] = base + a.cfg.rl; v.Q[0] = base + 2 * a.cfg.rl; v.Q[1] = base + 3 * a.cfg.rl;
+    uint8_t *W = base + 4 * a.cfg.rl;
+    const uint32_t slot = blockIdx.x * WARPS_PER_CTA + warp;
+    SingleScratch sc;
+    sc.pool = a.pool + (size_t)slot * a.cfg.pool_cap;
+    sc.anchors[0] = a.anchors + (size_t)slot * 2 * (a.cfg.tmask + 1);
+    sc.anchors[1] = sc.anchors[0] + (a.cfg.tmask + 1);
+    sc.list_head = a.lists + (size_t)slot * 2 * a.cfg.n_lists;
+    sc.list_tail = sc.list_head + a.cfg.n_lists;
+    sc.epoch = a.epochs + slot;
+    sc.hit_count = a.hit_count ? a.hit_count + (size_t)slot * MAXK : nullptr;
+    sc.hit_loc = a.hit_loc ? a.hit_loc + (size_t)slot * MAXK * 512 : nullptr;
+    sc.hit_rc = a.hit_rc ? a.hit_rc + (size_t)slot * MAXK * 512 : nullptr;
+    MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
+    for (;;) {
+        const uint32_t p = fetch_work(&a.ctr->work);
+        if (p >= a.n_items) break;
+        const uint32_t rslot = a.positions ? a.positions[p] : p;
+        const uint32_t id = a.items ? a.items[rslot] : rslot;
+        const DevBatch &b = a.two_batches ? a.b[id & 1] : a.b[0];
+        const uint32_t ridx = a.two_batches ? id >> 1 : id;
+        const uint32_t off = b.offsets[ridx], len = b.offsets[ridx + 1] - off;
+        const uint32_t mh = a.cfg.max_hits_to_get;
+        bool ok = single_align_warp(a.ix, a.cfg, sc, sm, v, W, L, b.bases + off, b.quals + off, len, rslot, fix, a.mapq_divisor,
+                                    mh ? a.mh_counts + rslot : nullptr, mh ? a.mh_locs + (size_t)rslot * mh : nullptr,
+                                    mh ? a.mh_rcs + (size_t)rslot * mh : nullptr, mh ? a.mh_scores + (size_t)rslot * mh : nullptr,
+                                    a.stats + 11);
+        if (lane == 0) {
+            snapb200_single_result *r = &a.results[rslot];
+            if (!ok) {
+                r->status = STATUS_RETRY;
+                a.retry_list[atomicAdd(&a.ctr->n_retry, 1u)] = rslot;
+            } else {
+                r->location = sm->out_loc;
+                r->score = sm->out_score;
+                r->mapq = sm->out_mapq;
+                r->status = (uint8_t)sm->out_status;
+                r->direction = (uint8_t)sm->out_dir;
+                r->popular_seeds_skipped = (uint16_t)sm->popular;
+                r->n_lookups = sm->n_lookups;
+                r->n_scored = sm->n_scored;
+                r->p_all = sm->p_all;
+                r->p_best = sm->p_best;
+                atomicAdd(a.stats + 8, (unsigned long long)sm->n_lookups);
+                atomicAdd(a.stats + 9, (unsigned long long)sm->n_scored);
+                atomicAdd(a.stats + 10, (unsigned long long)sm->popular);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- paired end ------------------------------------------------------------------------------------------
+struct PairedArgs {
+    DevIndex ix;
+    PairedCfg cfg;
+    DevBatch b[2];
+    const uint32_t *positions;  // retry list or null
+    uint32_t n_items;
+    snapb200_paired_result *results;
+    uint32_t force_spacing;
+    Cand *cands; Mate *mates; Anchor *anchors;  // [warp slot][...]
+    Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
+    unsigned long long *stats;
+};
+
+__host__ __device__ inline size_t paired_warp_shared(uint32_t rl)
+{
+    size_t s = (sizeof(PairedSm) + 15) & ~(size_t)15;
+    s += lv_shared_bytes();
+    s += 8 * (size_t)rl;
+    s += ((size_t)rl + 2 * WIN_SLACK + 15) & ~(size_t)15;
+    return s;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) paired_kernel(const PairedArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const size_t per_warp = paired_warp_shared(a.cfg.rl);
+    uint8_t *base = smem + per_warp * warp;
+    PairedSm *sm = (PairedSm *)base;
+    base += (sizeof(PairedSm) + 15) & ~(size_t)15;
+    int16_t *L = (int16_t *)base;
+    base += lv_shared_bytes();
+    ReadView v[2];
+    for (int w = 0; w < 2; w++) {
+        v[w].D[0] = base + (4 * w + 0) * a.cfg.rl; v[w].D[1] = base + (4 * w + 1) * a.cfg.rl;
+        v[w].Q[0] = base + (4 * w + 2) * a.cfg.rl; v[w].Q[1] = base + (4 * w + 3) * a.cfg.rl;
+    }
+    uint8_t *W = base + 8 * a.cfg.rl;
+    const uint32_t slot = blockIdx.x * WARPS_PER_CTA + warp;
+    PairedScratch sc;
+    sc.cands = a.cands + (size_t)slot * a.cfg.cand_cap;
+    sc.mates[0] = a.mates + (size_t)slot * 2 * a.cfg.mate_cap;
+    sc.mates[1] = sc.mates[0] + a.cfg.mate_cap;
+    sc.anchors = a.anchors + (size_t)slot * a.cfg.anchor_cap;
+    MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
+    for (;;) {
+        const uint32_t p = fetch_work(&a.ctr->work);
+        if (p >= a.n_items) break;
+        const uint32_t pi = a.positions ? a.positions[p] : p;
+        snapb200_paired_result *r = &a.results[pi];
+        uint32_t len[2], off[2];
+        for (int w = 0; w < 2; w++) { off[w] = a.b[w].offsets[pi]; len[w] = a.b[w].offsets[pi + 1] - off[w]; }
+        if (lane == 0) {  // ChimericPairedEndAligner::align prologue (:74-80); untouched fields read as zero
+            r->location[0] = r->location[1] = INVALID_LOC;
+            r->score[0] = r->score[1] = 0; r->mapq[0] = r->mapq[1] = 0;
+            r->status[0] = r->status[1] = SNAPB200_NOT_FOUND;
+            r->direction[0] = r->direction[1] = 0;
+            r->from_align_together = 0; r->aligned_as_pair = 0; r->pad = 0;
+            r->n_lv_calls = 0; r->n_lookups = 0; r->p_all = 0; r->p_best = 0;
+        }
+        __syncwarp();
+        if (len[0] < 50 && len[1] < 50) continue;
+        uint32_t ns = 0;
+        for (int w = 0; w < 2; w++) {
+            v[w].len = len[w];
+            ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w]);
+        }
+        int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, W, L, r, pi, fix);
+        if (lane == 0) {
+            if (rc == 2) {
+                if (a.cfg.hard_limit) {
+                    r->status[0] = r->status[1] = STATUS_LIMIT;
+                    atomicAdd(&a.ctr->n_limit, 1u);
+                } else {
+                    r->status[0] = r->status[1] = STATUS_RETRY;
+                    a.retry_list[atomicAdd(&a.ctr->n_retry, 1u)] = pi;
+                }
+            } else {
+                if (rc == 1) {
+                    r->n_lv_calls = sm->n_lv;
+                    r->n_lookups = sm->n_look[0] + sm->n_look[1];
+                    atomicAdd(a.stats + 8, (unsigned long long)r->n_lookups);
+                    atomicAdd(a.stats + 9, (unsigned long long)sm->n_lv);
+                    atomicAdd(a.stats + 10, (unsigned long long)(sm->popular[0] + sm->popular[1]));
+                }
+                r->from_align_together = 1;
+                r->aligned_as_pair = 1;
+                bool fallback;
+                if (a.force_spacing) {  // ChimericPairedEndAligner.cpp:92-99
+                    if (r->status[0] == SNAPB200_NOT_FOUND) r->from_align_together = 0;
+                    fallback = false;
+                } else {
+                    fallback = r->status[0] == SNAPB200_NOT_FOUND || r->status[1] == SNAPB200_NOT_FOUND;
+                }
+                if (fallback) a.fallback_list[atomicAdd(&a.ctr->n_fallback, 1u)] = pi;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Fold the single-end fallback results into the pair records (ChimericPairedEndAligner.cpp:110-119):
+// thread t handles fallback entry t>>1, end t&1.
+__global__ void merge_fallback_kernel(const uint32_t *fallback_list, uint32_t n_fallback, const snapb200_single_result *sr,
+                                      snapb200_paired_result *results)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_fallback) return;
+    uint32_t pi = fallback_list[t >> 1], e = t & 1;
+    const snapb200_single_result &s = sr[pi * 2 + e];
+    snapb200_paired_result *r = &results[pi];
+    r->status[e] = s.status;
+    r->location[e] = s.location;
+    r->direction[e] = s.direction;
+    r->score[e] = s.score;
+    r->mapq[e] = s.mapq / 4;  // heavy quality penalty for chimeric reads
+    if (e == 0) { r->from_align_together = 0; r->aligned_as_pair = 0; }
+}
+
+// status / mapq histogram of the final records (one thread per read)
+__global__ void stats_single_kernel(const snapb200_single_result *r, uint32_t n, unsigned long long *stats)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint8_t st = r[t].status;
+    atomicAdd(stats + 0, 1ull);
+    atomicAdd(stats + (st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4), 1ull);
+    if (st != SNAPB200_NOT_FOUND) { int q = r[t].mapq; if (q >= 0 && q <= 70) atomicAdd(stats + 12 + q, 1ull); }
+}
+__global__ void stats_paired_kernel(const snapb200_paired_result *r, uint32_t n, unsigned long long *stats)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    const snapb200_paired_result &p = r[t >> 1];
+    int e = t & 1;
+    uint8_t st = p.status[e];
+    atomicAdd(stats + 0, 1ull);
+    atomicAdd(stats + (st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4), 1ull);
+    if (p.aligned_as_pair) atomicAdd(stats + 6, 1ull);
+    if (st != SNAPB200_NOT_FOUND) { int q = p.mapq[e]; if (q >= 0 && q <= 70) atomicAdd(stats + 12 + q, 1ull); }
+}
+
+// ---- CIGAR against the resident genome (SAM.cpp:1159-1189) ---------------------------------------------------
+struct CigarArgs {
+    DevIndex ix;
+    DevBatch b;
+    const uint32_t *locations;
+    const uint8_t *directions;
+    int use_m;
+    char *cigars;
+    uint32_t stride;
+    int32_t *edit_distance;
+    uint32_t rl;
+    Counters *ctr;
+};
+
+__host__ __device__ inline size_t cigar_warp_shared(uint32_t rl)
+{
+    return lv_shared_bytes() + (size_t)rl + (((size_t)rl + 2 * WIN_SLACK + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) cigar_kernel(const CigarArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    uint8_t *base = smem + cigar_warp_shared(a.rl) * warp;
+    int16_t *L = (int16_t *)base;
+    uint8_t *P = base + lv_shared_bytes();
+    uint8_t *W = P + a.rl;
+    for (;;) {
+        const uint32_t i = fetch_work(&a.ctr->work);
+        if (i >= a.b.n) break;
+        const uint32_t off = a.b.offsets[i], len = a.b.offsets[i + 1] - off;
+        const uint32_t loc = a.locations[i];
+        char *out = a.cigars + (size_t)i * a.stride;
+        for (uint32_t j = lane; j < a.stride; j += 32) out[j] = 0;
+        __syncwarp();
+        if (loc == INVALID_LOC || !substring_ok(a.ix, loc, len)) {
+            if (lane == 0) a.edit_distance[i] = -3;
+            continue;
+        }
+        const bool rc = a.directions[i] == SNAPB200_RC;
+        for (uint32_t j = lane; j < len; j += 32) P[j] = rc ? rc_base(a.b.bases[off + len - 1 - j]) : a.b.bases[off + j];
+        stage_window(a.ix, loc, len, W);
+        LvStr s;
+        s.p = P; s.ps = 1; s.plen = (int)len;
+        s.t = W + WIN_SLACK; s.ts = 1; s.tlen = (int)len;
+        s.t_lo = -WIN_SLACK; s.t_hi = (int)len + WIN_SLACK;
+        int e = lv_cigar_warp(s, MAXK - 1, L, out, (int)a.stride, a.use_m != 0);
+        if (lane == 0) a.edit_distance[i] = e;
+        __syncwarp();
+    }
+}
+
+// ---- building blocks on explicit strings (known-answer tests) ----------------------------------------------
+struct LvArgs {
+    DevIndex ix;  // only the probability tables are used
+    int dir;
+    uint32_t n;
+    const uint32_t *text_off, *pat_off;
+    const uint8_t *texts, *pats, *quals;
+    const int32_t *k;
+    int32_t *score, *indel;
+    double *prob;
+    int use_m; char *cigars; uint32_t stride;  // CIGAR variant when cigars != null
+    uint32_t max_text, max_pat;
+    Counters *ctr;
+};
+
+__host__ __device__ inline size_t lvtest_warp_shared(uint32_t max_text, uint32_t max_pat)
+{
+    return lv_shared_bytes() + ((max_text + 15) & ~15u) + 2 * (size_t)((max_pat + 15) & ~15u);
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) lv_kernel(const LvArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    uint8_t *base = smem + lvtest_warp_shared(a.max_text, a.max_pat) * warp;
+    int16_t *L = (int16_t *)base;
+    uint8_t *T = base + lv_shared_bytes();
+    uint8_t *P = T + ((a.max_text + 15) & ~15u);
+    uint8_t *Q = P + ((a.max_pat + 15) & ~15u);
+    for (;;) {
+        const uint32_t i = fetch_work(&a.ctr->work);
+        if (i >= a.n) break;
+        const uint32_t to = a.text_off[i], tl = a.text_off[i + 1] - to, po = a.pat_off[i], pl = a.pat_off[i + 1] - po;
+        for (uint32_t j = lane; j < tl; j += 32) T[j] = a.texts[to + j];
+        for (uint32_t j = lane; j < pl; j += 32) { P[j] = a.pats[po + j]; if (a.quals) Q[j] = a.quals[po + j]; }
+        __syncwarp();
+        LvStr s;
+        s.p = P; s.ps = 1; s.plen = (int)pl;
+        s.tlen = (int)tl; s.t_lo = 0; s.t_hi = (int)tl;
+        if (a.dir > 0) { s.t = T; s.ts = 1; } else { s.t = T + tl - 1; s.ts = -1; }  // backward: text(i) = T[tl-1-i]
+        if (a.cigars) {
+            char *out = a.cigars + (size_t)i * a.stride;
+            for (uint32_t j = lane; j < a.stride; j += 32) out[j] = 0;
+            __syncwarp();
+            int e = lv_cigar_warp(s, a.k[i], L, out, (int)a.stride, a.use_m != 0);
+            if (lane == 0) a.score[i] = e;
+        } else {
+            double prob;
+            int indel;
+            int e = lv_score_warp(s, a.quals ? Q : nullptr, 1, a.k[i], a.ix, L, &prob, &indel);
+            if (lane == 0) { a.score[i] = e; a.prob[i] = prob; a.indel[i] = indel; }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void lookup_kernel(const DevIndex ix, uint32_t n, const uint8_t *seeds, uint32_t max_out, uint32_t *n_hits, uint32_t *hits)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t f, r;
+    HitList hl[2] = {{nullptr, 0}, {nullptr, 0}};
+    if (pack_seed(seeds + (size_t)i * ix.seed_len, ix.seed_len, &f, &r)) lookup_seed(ix, f, r, hl, nullptr);
+    for (int d = 0; d < 2; d++) {
+        n_hits[i * 2 + d] = hl[d].n;
+        for (uint32_t j = 0; j < hl[d].n && j < max_out; j++) hits[((size_t)i * 2 + d) * max_out + j] = hl[d].hits[j];
+    }
+}
+
+__global__ void mapq_kernel(uint32_t n, const double *p_all, const double *p_best, const int32_t *score, const int32_t *popular,
+                            int32_t *mapq, uint8_t *near_integer)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ni;
+    mapq[i] = compute_mapq_dev(p_all[i], p_best[i], score[i], popular[i], &ni);
+    near_integer[i] = ni;
+}

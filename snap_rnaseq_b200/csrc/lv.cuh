@@ -1,0 +1,315 @@
+// lv.cuh -- warp-cooperative Landau-Vishkin bounded edit distance (score+probability, and CIGAR).
+//
+// Replaces LandauVishkin<+1/-1>::computeEditDistance (SNAPLib/LandauVishkin.h:211-455) and
+// LandauVishkinWithCigar::computeEditDistance (SNAPLib/LandauVishkin.cpp:252-535).
+//
+// Mapping to the hardware: the reference fills L[e][d] one diagonal at a time in the order 0,+1,-1,...
+// and returns at the first diagonal that reaches the end of the pattern.  Cells of one row depend only on
+// the previous row, so here the 2e+1 diagonals of row e are extended by different lanes at once and the
+// winner is the reaching diagonal with the smallest rank in the reference's visiting order -- the same
+// answer, one row per step instead of one cell per step.  Row 0 (the long exact-match run) is compared 32
+// bytes per step with a ballot.  L lives in shared memory as a triangular int16 table (961 cells for
+// k <= 30); the action matrix A is not stored: an action is a pure function of three cells of the row
+// above and is recomputed during the backtrace, which the leader lane runs (it is a dependent chain).
+// Both strings are staged in shared memory by the caller, so the inner loops never touch HBM.
+#pragma once
+#include "common.cuh"
+
+#define LV_CELLS (MAXK * MAXK)  // rows 0..30, row e has 2e+1 cells starting at e*e
+
+struct LvStr {
+    const uint8_t *p;  // pattern(i) = p[i*ps] for 0 <= i < plen
+    int ps, plen;
+    const uint8_t *t;  // text(i) = t[i*ts] for t_lo <= i < t_hi (bytes that really exist)
+    int ts, tlen;      // tlen: the textLen the reference is given
+    int t_lo, t_hi;
+};
+
+// Bytes outside the pattern are 0x00 and bytes outside the readable text are 0x01: they never match, which
+// is what the reference's peek-then-clamp (LandauVishkin.h:325-354) amounts to whenever it is defined.
+__device__ __forceinline__ int lv_pat(const LvStr &s, int i) { return ((unsigned)i < (unsigned)s.plen) ? s.p[i * s.ps] : 0x00; }
+__device__ __forceinline__ int lv_txt(const LvStr &s, int i) { return (i >= s.t_lo && i < s.t_hi) ? s.t[i * s.ts] : 0x01; }
+
+__device__ __forceinline__ int lv_get(const int16_t *L, int e, int d)
+{  // cells with |d| > e are never written by the reference and keep their constructor value -2
+    return (d >= -e && d <= e) ? (int)L[e * e + d + e] : -2;
+}
+
+// One cell: best of (substitution, deletion, insertion) from the row above, then extend along the diagonal.
+__device__ __forceinline__ int lv_cell(const LvStr &s, const int16_t *L, int e, int d)
+{
+    int best = lv_get(L, e - 1, d) + 1;
+    int left = lv_get(L, e - 1, d - 1);
+    if (left > best) best = left;
+    int right = lv_get(L, e - 1, d + 1) + 1;
+    if (right > best) best = right;
+    if (lv_pat(s, best) == lv_txt(s, d + best)) {
+        int dend = min(s.plen, s.tlen - d);
+        if (best < dend) {
+            do { best++; } while (best < dend && lv_pat(s, best) == lv_txt(s, d + best));
+        } else {
+            best = dend;  // the reference's 8-byte loop clamps to `end` even when it starts beyond it
+        }
+    }
+    return best;
+}
+
+// 'X','D','I' chosen at cell (e,d): recomputed from the row above (ties: X, then D, then I; LandauVishkin.h:312-323)
+__device__ __forceinline__ char lv_action(const int16_t *L, int e, int d)
+{
+    int best = lv_get(L, e - 1, d) + 1;
+    char a = 'X';
+    int left = lv_get(L, e - 1, d - 1);
+    if (left > best) { best = left; a = 'D'; }
+    int right = lv_get(L, e - 1, d + 1) + 1;
+    if (right > best) a = 'I';
+    return a;
+}
+
+// Row 0: length of the common prefix, 32 positions per step.
+__device__ __forceinline__ int lv_row0(const LvStr &s, int end)
+{
+    int lane = lane_id();
+    for (int base = 0; base < end; base += 32) {
+        int i = base + lane;
+        bool mism = (i < end) && (lv_pat(s, i) != lv_txt(s, i));
+        unsigned b = __ballot_sync(FULL_MASK, mism);
+        if (b) return base + __ffs(b) - 1;
+    }
+    return end;
+}
+
+// rank of diagonal d in the visiting order 0,+1,-1,+2,-2,... (score) or 0,-1,+1,-2,+2,... (CIGAR)
+__device__ __forceinline__ int lv_rank_score(int d) { return d == 0 ? 0 : (d > 0 ? 2 * d - 1 : -2 * d); }
+__device__ __forceinline__ int lv_unrank_score(int r) { return r == 0 ? 0 : ((r & 1) ? (r + 1) / 2 : -(r / 2)); }
+__device__ __forceinline__ int lv_rank_cigar(int d) { return d == 0 ? 0 : (d < 0 ? -2 * d - 1 : 2 * d); }
+__device__ __forceinline__ int lv_unrank_cigar(int r) { return r == 0 ? 0 : ((r & 1) ? -((r + 1) / 2) : r / 2); }
+
+// Fills rows 1..k until some diagonal reaches plen.  Returns e (and the winning diagonal) or -1.
+template <bool CIGAR_ORDER>
+__device__ __forceinline__ int lv_rows(const LvStr &s, int16_t *L, int k, int *win_d)
+{
+    const int lane = lane_id();
+    for (int e = 1; e <= k; e++) {
+        int found = 0x7fffffff;
+        for (int idx = lane; idx < 2 * e + 1; idx += 32) {
+            int d = idx - e;
+            int best = lv_cell(s, L, e, d);
+            L[e * e + idx] = (int16_t)best;
+            if (best == s.plen) found = min(found, CIGAR_ORDER ? lv_rank_cigar(d) : lv_rank_score(d));
+        }
+        __syncwarp();
+        int win = __reduce_min_sync(FULL_MASK, found);
+        if (win != 0x7fffffff) {
+            *win_d = CIGAR_ORDER ? lv_unrank_cigar(win) : lv_unrank_score(win);
+            return e;
+        }
+    }
+    return -1;
+}
+
+// LandauVishkin<DIR>::computeEditDistance.  q: quality(i) = q[i*qs] or NULL.  All lanes return the same
+// values.  L: LV_CELLS int16 in shared memory private to this warp.
+__device__ int lv_score_warp(const LvStr &s, const uint8_t *q, int qs, int k, const DevIndex &ix, int16_t *L,
+                             double *match_prob, int *net_indel)
+{
+    const int lane = lane_id();
+    *net_indel = 0;
+    *match_prob = 0.0;
+    if (k > MAXK - 1) k = MAXK - 1;
+    const int plen = s.plen;
+    int end = min(plen, s.tlen);
+    int l0 = lv_row0(s, end);
+    if (l0 == end) {  // LandauVishkin.h:290-305
+        int result = plen > end ? plen - end : 0;
+        if (q) *match_prob = ix.perfect[plen];
+        return result > k ? -1 : result;
+    }
+    if (lane == 0) L[0] = (int16_t)l0;
+    __syncwarp();
+    int d = 0;
+    int e = lv_rows<false>(s, L, k, &d);
+    if (e < 0) return -1;
+    if (!q) return e;
+    // backtrace (LandauVishkin.h:379-431): a dependent chain, run by the leader lane
+    double prob = 1.0;
+    int indel = 0;
+    if (lane == 0) {
+        char act[MAXK + 1];
+        short matched[MAXK + 1];
+        int cur_d = d;
+        for (int ce = e; ce >= 1; ce--) {
+            char a = lv_action(L, ce, cur_d);
+            int here = (ce == e) ? plen : lv_get(L, ce, cur_d);
+            act[ce] = a;
+            if (a == 'I') {
+                matched[ce] = (short)(here - lv_get(L, ce - 1, cur_d + 1) - 1);
+                cur_d++;
+            } else if (a == 'D') {
+                matched[ce] = (short)(here - lv_get(L, ce - 1, cur_d - 1));
+                cur_d--;
+            } else {
+                matched[ce] = (short)(here - lv_get(L, ce - 1, cur_d) - 1);
+            }
+        }
+        int ce = 1;
+        int offset = L[0];
+        while (ce <= e) {
+            char a = act[ce];
+            int count = 1;
+            while (ce + 1 <= e && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
+            if (a == 'I') {
+                prob *= ix.indel[count];
+                offset += count;
+                indel += count;
+            } else if (a == 'D') {
+                prob *= ix.indel[count];
+                offset -= count;
+                indel -= count;
+            } else {
+                for (int i = 0; i < count; i++) {
+                    int qi = min(plen - 1, max(offset, 0));
+                    prob *= ix.phred[q[qi * qs]];
+                    offset++;
+                }
+            }
+            offset += matched[ce];
+            ce++;
+        }
+        prob *= ix.perfect[plen - e];
+    }
+    *match_prob = shfl_f64(prob, 0);
+    *net_indel = __shfl_sync(FULL_MASK, indel, 0);
+    return e;
+}
+
+// ---- CIGAR ----------------------------------------------------------------------------------------------
+struct CigarOut { char *buf; int left; };
+
+// writeCigar, COMPACT_CIGAR_STRING case (SNAPLib/LandauVishkin.cpp:27-64): "%d%c"; false if it does not fit.
+__device__ inline bool cigar_put(CigarOut &o, int count, char code)
+{
+    if (count <= 0) return true;
+    if (o.left == 0) return false;
+    char tmp[12];
+    int n = 0;
+    int c = count;
+    while (c > 0) { tmp[n++] = (char)('0' + c % 10); c /= 10; }
+    int w = n + 1;
+    if (w > o.left - 1) return false;
+    for (int i = 0; i < n; i++) o.buf[i] = tmp[n - 1 - i];
+    o.buf[n] = code;
+    o.buf[w] = 0;
+    o.buf += w;
+    o.left -= w;
+    return true;
+}
+
+// LandauVishkinWithCigar::computeEditDistance, COMPACT_CIGAR_STRING.  The leader lane writes the string.
+__device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int cigar_len, bool use_m)
+{
+    const int lane = lane_id();
+    const int plen = s.plen;
+    int end = min(plen, s.tlen);
+    int l0 = lv_row0(s, end);
+    int rc = 0;
+    if (l0 == end) {  // LandauVishkin.cpp:284-306
+        if (lane == 0) {
+            CigarOut o = {cigar, cigar_len};
+            if (use_m) {
+                if (!cigar_put(o, plen, 'M')) rc = -2;
+            } else {
+                if (!cigar_put(o, end, '=')) rc = -2;
+                else if (plen > end && !cigar_put(o, plen - end, 'X')) rc = -2;
+            }
+        }
+        return __shfl_sync(FULL_MASK, rc, 0);
+    }
+    if (lane == 0) L[0] = (int16_t)l0;
+    __syncwarp();
+    int d = 0;
+    int e = lv_rows<true>(s, L, k, &d);
+    if (e < 0) return -1;
+    // can e plain mismatches explain it?  (LandauVishkin.cpp:357-366)
+    int straight = 0;
+    for (int base = 0; base < end; base += 32) {
+        int i = base + lane;
+        bool mism = (i < end) && (lv_pat(s, i) != lv_txt(s, i));
+        straight += __popc(__ballot_sync(FULL_MASK, mism));
+    }
+    straight += plen - end;
+    if (lane == 0) {
+        CigarOut o = {cigar, cigar_len};
+        bool ok = true;
+        if (straight == e) {
+            if (use_m) {
+                ok = cigar_put(o, plen, 'M');
+            } else {
+                int start = 0;
+                bool matching = lv_pat(s, 0) == lv_txt(s, 0);
+                for (int i = 0; i < end && ok; i++) {
+                    bool m = lv_pat(s, i) == lv_txt(s, i);
+                    if (m != matching) {
+                        ok = cigar_put(o, i - start, matching ? '=' : 'X');
+                        matching = m;
+                        start = i;
+                    }
+                }
+                if (ok && plen > start) {
+                    if (!matching) {
+                        ok = cigar_put(o, plen - start, 'X');
+                    } else {
+                        ok = cigar_put(o, end - start, '=');
+                        if (ok && plen > end) ok = cigar_put(o, plen - end, 'X');
+                    }
+                }
+            }
+        } else {
+            // backtrace, LandauVishkin.cpp:441-531
+            char act[MAXK + 1];
+            short matched[MAXK + 1];
+            int cur_d = d;
+            for (int ce = e; ce >= 1; ce--) {
+                char a = lv_action(L, ce, cur_d);
+                act[ce] = a;
+                int here = lv_get(L, ce, cur_d);
+                if (a == 'I') {
+                    matched[ce] = (short)(here - lv_get(L, ce - 1, cur_d + 1) - 1);
+                    cur_d++;
+                } else if (a == 'D') {
+                    matched[ce] = (short)(here - lv_get(L, ce - 1, cur_d - 1));
+                    cur_d--;
+                } else {
+                    matched[ce] = (short)(here - lv_get(L, ce - 1, cur_d) - 1);
+                }
+            }
+            int acc_m = 0;
+            if (use_m) acc_m = L[0];
+            else if (L[0] > 0) ok = cigar_put(o, L[0], '=');
+            int ce = 1;
+            while (ce <= e && ok) {
+                char a = act[ce];
+                int count = 1;
+                while (ce + 1 <= e && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
+                if (use_m) {
+                    if (a == 'X') {
+                        acc_m += count;
+                    } else {
+                        if (acc_m != 0) { ok = cigar_put(o, acc_m, 'M'); acc_m = 0; }
+                        if (ok) ok = cigar_put(o, count, a);
+                    }
+                } else {
+                    ok = cigar_put(o, count, a);
+                }
+                if (ok && matched[ce] > 0) {
+                    if (use_m) acc_m += matched[ce];
+                    else ok = cigar_put(o, matched[ce], '=');
+                }
+                ce++;
+            }
+            if (ok && use_m && acc_m != 0) ok = cigar_put(o, acc_m, 'M');
+        }
+        rc = ok ? e : -2;
+    }
+    return __shfl_sync(FULL_MASK, rc, 0);
+}

@@ -1,0 +1,543 @@
+// paired.cuh -- paired-end set-intersection aligner, one warp per pair.
+//
+// Replaces IntersectingPairedEndAligner::align / scoreLocation / HashTableHitSet / MergeAnchor
+// (SNAPLib/IntersectingPairedEndAligner.cpp:141-1371).  The single-end fallback of
+// ChimericPairedEndAligner::align (SNAPLib/ChimericPairedEndAligner.cpp:74-128) is a second launch of the
+// single-end kernel over the pairs this kernel could not place (see snapb200.cu).
+//
+// Hardware mapping: phase 1 probes all seeds of both mates at once (one lane per seed); in phase 2 every lane
+// owns one lookup of a hit set, so the per-step "binary search in every lookup, take the maximum" of the
+// reference becomes one search per lane plus a warp max-reduction; phase 3 scores candidates with the
+// warp-cooperative Landau-Vishkin of lv.cuh, the leader lane keeping the merge/MAPQ bookkeeping in the
+// reference's order.
+#pragma once
+#include "single.cuh"
+
+struct __align__(8) Mate {  // ScoringMateCandidate (IntersectingPairedEndAligner.h:401-423)
+    double prob;
+    uint32_t loc, best_possible, score, score_limit;
+    uint32_t seed_offset;
+    int32_t genome_offset;
+};
+struct Cand {  // ScoringCandidate (:425-447)
+    int32_t next, anchor;
+    uint32_t mate_index, loc;
+    uint16_t seed_offset;
+    uint8_t set_pair, best_possible;
+};
+struct __align__(8) Anchor {  // MergeAnchor (:364-393)
+    double prob;
+    uint32_t loc_more, loc_fewer;
+    int32_t pair_score;
+    int32_t pad;
+};
+
+struct PairedCfg {
+    uint32_t max_k, num_seeds, extra, min_spacing, max_spacing, max_big_hits;
+    double seed_coverage;
+    uint32_t cand_cap, mate_cap, anchor_cap;  // this scratch tier
+    uint32_t hard_limit;                       // 1: caps are the reference's pool sizes (overflow = its soft_exit)
+    uint32_t rl;
+};
+
+struct PairedScratch {
+    Cand *cands;
+    Mate *mates[2];
+    Anchor *anchors;
+};
+
+#define STATUS_LIMIT 0xfd  // the reference's candidate pools would have overflowed (it exits)
+
+struct PairedSm {
+    // hit sets [read][dir], filled by the leader in phase 1 (HashTableHitSet::recordLookup)
+    unsigned long long hits[2][2][MAX_LOOKUPS];
+    uint32_t nhits[2][2][MAX_LOOKUPS];
+    uint16_t seedoff[2][2][MAX_LOOKUPS];
+    uint8_t setid[2][2][MAX_LOOKUPS];
+    uint8_t exhausted[2][2][MAX_LOOKUPS];
+    int8_t cur_set[2][2];
+    uint8_t n_lookups[2][2];
+    // phase 1 staging: raw lookup results per scheduled seed
+    unsigned long long raw_hits[2][MAX_LOOKUPS];
+    uint32_t raw_n[2][MAX_LOOKUPS];
+    uint16_t sched_off[MAX_LOOKUPS];
+    uint8_t sched_wrap[MAX_LOOKUPS];
+    uint32_t n_sched;
+    uint32_t used[16];
+    uint32_t total_hits[2][2], popular[2], n_look[2];
+    int score_list[32];
+    // phase 3 exchange
+    double p_all, p_best, f_prob, m_prob;
+    uint32_t best_pair_score, score_limit, n_cands, n_anchors, n_mates[2], max_used_list;
+    uint32_t best_loc[2], best_score[2];
+    int best_dir[2];
+    int act, ci, stop, overflow, list, f_off, m_off, fs, ms;
+    uint32_t c_loc, c_seedoff, c_sp, mi, m_loc, m_seedoff, m_limit, low_mate;
+    uint32_t n_lv;
+};
+
+// ---- warp-parallel HashTableHitSet: lane i owns lookup i ------------------------------------------------
+struct LaneLookup {
+    const uint32_t *hits;
+    uint32_t nh, cur, so, sid;
+    bool act;
+};
+
+__device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, int w, int d)
+{
+    LaneLookup l;
+    const int lane = lane_id();
+    l.act = lane < (int)sm->n_lookups[w][d];
+    l.hits = l.act ? (const uint32_t *)sm->hits[w][d][lane] : nullptr;
+    l.nh = l.act ? sm->nhits[w][d][lane] : 0;
+    l.so = l.act ? sm->seedoff[w][d][lane] : 0;
+    l.sid = l.act ? sm->setid[w][d][lane] : 0;
+    l.cur = 0;
+    return l;
+}
+
+__device__ __forceinline__ bool is_within(uint32_t a, uint32_t b, uint32_t dist)
+{  // Util.h:538-541 with its unsigned wrap-around
+    return (a <= b && (uint32_t)(a + dist) >= b) || (a >= b && a <= (uint32_t)(b + dist));
+}
+
+// max over lanes of (ok ? val : 0) with the reference's "first strictly greater wins" tie rule; returns whether
+// any lane had ok && val > 0, the winning value and that lane's seed offset.
+__device__ __forceinline__ bool pick_max(bool ok, uint32_t val, uint32_t so, uint32_t *best, uint32_t *best_so)
+{
+    uint32_t v = ok ? val : 0;
+    uint32_t m = __reduce_max_sync(FULL_MASK, v);
+    if (m == 0) return false;
+    unsigned who = __ballot_sync(FULL_MASK, ok && val == m);
+    int src = __ffs(who) - 1;
+    *best = m;
+    *best_so = __shfl_sync(FULL_MASK, so, src);
+    return true;
+}
+
+// getFirstHit (:1270-1284)
+__device__ __forceinline__ bool hs_first(LaneLookup &l, uint32_t *most_recent, uint32_t *loc, uint32_t *so)
+{
+    bool ok = l.act && l.nh > 0;
+    uint32_t val = ok ? __ldg(&l.hits[0]) - l.so : 0;
+    *loc = 0;
+    if (!pick_max(ok, val, l.so, loc, so)) return false;
+    *most_recent = *loc;
+    return true;
+}
+
+// getNextHitLessThanOrEqualTo, "traditional" branch (:1219-1263)
+__device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent, uint32_t max_loc, uint32_t *loc, uint32_t *so)
+{
+    bool found = false;
+    uint32_t val = 0;
+    if (l.act) {
+        int lo = (int)l.cur, hi = (int)l.nh - 1;
+        uint32_t want = max_loc + l.so;
+        while (lo <= hi) {
+            int probe = (lo + hi) / 2;
+            uint32_t h = __ldg(&l.hits[probe]);
+            if (h <= want && (probe == 0 || __ldg(&l.hits[probe - 1]) > want)) {
+                found = true;
+                val = h - l.so;
+                l.cur = (uint32_t)probe;
+                break;
+            }
+            if (h > want) lo = probe + 1; else hi = probe - 1;
+        }
+        if (lo > hi) l.cur = l.nh;
+    }
+    if (!pick_max(found, val, l.so, loc, so)) return false;
+    *most_recent = *loc;
+    return true;
+}
+
+// getNextLowerHit (:1286-1322)
+__device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_recent, uint32_t *loc, uint32_t *so)
+{
+    bool ok = false;
+    uint32_t val = 0;
+    if (l.act) {
+        if (l.cur != l.nh && __ldg(&l.hits[l.cur]) - l.so == *most_recent) l.cur++;
+        if (l.cur != l.nh) {
+            uint32_t h = __ldg(&l.hits[l.cur]);
+            val = h - l.so;
+            ok = h >= l.so;
+        }
+    }
+    if (!pick_max(ok, val, l.so, loc, so)) return false;
+    *most_recent = *loc;
+    return true;
+}
+
+// computeBestPossibleScoreForCurrentHit (:901-929); merge_dist = maxK (firstInit(maxSeeds, maxK), :114)
+__device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, const uint8_t *exhausted, int cur_set,
+                                                     uint32_t most_recent, uint32_t merge_dist)
+{
+    bool miss = false;
+    if (l.act) {
+        uint32_t target = most_recent + l.so;
+        bool close = (l.cur != l.nh && is_within(__ldg(&l.hits[l.cur]), target, merge_dist)) ||
+                     (l.cur != 0 && is_within(__ldg(&l.hits[l.cur - 1]), target, merge_dist));
+        miss = !close;
+    }
+    uint32_t best = 0;
+    for (int s = 0; s <= cur_set; s++) {
+        uint32_t c = exhausted[s] + __popc(__ballot_sync(FULL_MASK, miss && l.sid == (uint32_t)s));
+        best = max(best, c);
+    }
+    return best;
+}
+
+// leader: the seed schedule of one mate (IntersectingPairedEndAligner.cpp:259-339); every non-N seed is a lookup
+__device__ __forceinline__ void schedule_seeds_paired(PairedSm *sm, const uint8_t *read, uint32_t len, uint32_t seed_len,
+                                                      uint32_t max_seeds)
+{
+    const uint32_t n_possible = len - seed_len + 1;
+    for (int i = 0; i < 16; i++) sm->used[i] = 0;
+    uint32_t next = 0, wrap = 0, n = 0;
+    while (n < n_possible && n < max_seeds) {
+        if (next >= n_possible) {
+            wrap++;
+            if (wrap >= seed_len) break;
+            next = wrapped_seed(seed_len, wrap);
+        }
+        while (next < n_possible && (sm->used[next >> 5] >> (next & 31) & 1)) next++;
+        if (next >= n_possible) continue;
+        sm->used[next >> 5] |= 1u << (next & 31);
+        bool ok = true;
+        for (uint32_t i = 0; i < seed_len; i++) ok &= base2(read[next + i]) >= 0;
+        if (!ok) { next++; continue; }  // :296-302
+        sm->sched_off[n] = (uint16_t)next;
+        sm->sched_wrap[n] = (uint8_t)wrap;
+        n++;
+        if ((max_seeds - n + 1) * seed_len + next < n_possible)  // :333-338 (n == countOfHashTableLookups here)
+            next += (n_possible + next) / (max_seeds - n + 1);
+        else
+            next += seed_len;
+    }
+    sm->n_sched = n;
+}
+
+// IntersectingPairedEndAligner::align.  All lanes.  v[0], v[1]: both mates staged (len set, Ns counted by caller).
+// Returns 0 = returned early leaving the result untouched, 1 = produced a result, 2 = scratch tier overflow.
+__device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, const PairedScratch &sc, PairedSm *sm,
+                                     const ReadView *v, uint32_t total_ns, uint8_t *W, int16_t *L,
+                                     snapb200_paired_result *r, uint32_t pair_index, const MapqFixList &fix)
+{
+    const int lane = lane_id();
+    const uint32_t seed_len = ix.seed_len, max_k = cfg.max_k, extra = cfg.extra;
+    const uint32_t max_spacing = cfg.max_spacing, min_spacing = cfg.min_spacing;
+    const uint32_t rlen[2] = {v[0].len, v[1].len};
+    uint32_t max_seeds = cfg.num_seeds ? cfg.num_seeds : (uint32_t)(max(rlen[0], rlen[1]) * cfg.seed_coverage / seed_len);
+    if (max_seeds > MAX_LOOKUPS) max_seeds = MAX_LOOKUPS;  // rejected on the host; belt and braces
+    if (rlen[0] < 50 || rlen[1] < 50) return 0;  // :186-188
+    if (total_ns > max_k) return 0;              // :226-228
+
+    // ---- phase 1 (:259-340) ----
+    if (lane == 0) {
+        for (int w = 0; w < 2; w++) {
+            sm->popular[w] = 0; sm->n_look[w] = 0;
+            for (int d = 0; d < 2; d++) { sm->total_hits[w][d] = 0; sm->n_lookups[w][d] = 0; sm->cur_set[w][d] = -1; }
+        }
+        sm->overflow = 0;
+        sm->n_lv = 0;
+    }
+    for (int w = 0; w < 2; w++) {
+        __syncwarp();
+        if (lane == 0) schedule_seeds_paired(sm, v[w].D[0], rlen[w], seed_len, max_seeds);
+        __syncwarp();
+        const uint32_t n_sched = sm->n_sched;
+        if ((uint32_t)lane < n_sched) {  // all seeds of this mate probed at once
+            uint64_t sf, sr;
+            HitList hl[2];
+            pack_seed(v[w].D[0] + sm->sched_off[lane], seed_len, &sf, &sr);
+            lookup_seed(ix, sf, sr, hl, nullptr);
+            for (int d = 0; d < 2; d++) { sm->raw_hits[d][lane] = (unsigned long long)hl[d].hits; sm->raw_n[d][lane] = hl[d].n; }
+        }
+        __syncwarp();
+        if (lane == 0) {  // recordLookup in order (:859-899)
+            bool begins[2] = {true, true};
+            uint32_t prev_wrap = 0;
+            for (uint32_t j = 0; j < n_sched; j++) {
+                if (sm->sched_wrap[j] != prev_wrap) { begins[0] = begins[1] = true; prev_wrap = sm->sched_wrap[j]; }
+                for (int d = 0; d < 2; d++) {
+                    uint32_t n = sm->raw_n[d][j];
+                    uint32_t offset = d == 0 ? sm->sched_off[j] : rlen[w] - seed_len - sm->sched_off[j];
+                    if (n < cfg.max_big_hits) {
+                        sm->total_hits[w][d] += n;
+                        if (begins[d]) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
+                        begins[d] = false;
+                        if (n == 0) {
+                            sm->exhausted[w][d][sm->cur_set[w][d]]++;
+                        } else {
+                            const uint32_t *hp = (const uint32_t *)sm->raw_hits[d][j];
+                            while (n > 0 && __ldg(&hp[n - 1]) < offset) n--;  // trim meaningless hits (:882-884)
+                            uint32_t k = sm->n_lookups[w][d]++;
+                            sm->hits[w][d][k] = (unsigned long long)hp;
+                            sm->nhits[w][d][k] = n;
+                            sm->seedoff[w][d][k] = (uint16_t)offset;
+                            sm->setid[w][d][k] = (uint8_t)sm->cur_set[w][d];
+                        }
+                    } else {
+                        sm->popular[w]++;
+                    }
+                }
+            }
+            sm->n_look[w] = n_sched;
+        }
+    }
+    __syncwarp();
+    const int more = (sm->total_hits[0][0] + sm->total_hits[0][1] > sm->total_hits[1][0] + sm->total_hits[1][1]) ? 0 : 1;  // :342
+    const int fewer = 1 - more;
+    // setPairDirection (:351): set pair sp uses read0 in direction sp, read1 in direction 1-sp
+    if (lane == 0) {
+        for (uint32_t k = 0; k <= max_k + extra; k++) sm->score_list[k] = -1;
+        sm->n_cands = 0; sm->n_mates[0] = sm->n_mates[1] = 0; sm->n_anchors = 0; sm->max_used_list = 0;
+    }
+    __syncwarp();
+
+    // ---- phase 2 (:359-511) ----
+    uint32_t n_cands = 0, max_used_list = 0;
+    for (int sp = 0; sp < 2; sp++) {
+        const int dir_of[2] = {sp, 1 - sp};
+        LaneLookup lf = load_lookup(sm, fewer, dir_of[fewer]);
+        LaneLookup lm = load_lookup(sm, more, dir_of[more]);
+        const uint8_t *exh_f = sm->exhausted[fewer][dir_of[fewer]], *exh_m = sm->exhausted[more][dir_of[more]];
+        const int cs_f = sm->cur_set[fewer][dir_of[fewer]], cs_m = sm->cur_set[more][dir_of[more]];
+        uint32_t mr_f = 0, mr_m = 0;  // mostRecentLocationReturned of each set
+        uint32_t f_loc, f_off = 0, m_loc, m_off = 0;
+        bool out_of_more = false;
+        uint32_t n_mates = 0, last_mate_loc = 0;
+        Mate *mates = sc.mates[sp];
+        if (!hs_first(lf, &mr_f, &f_loc, &f_off)) continue;
+        m_loc = INVALID_LOC;
+        for (;;) {
+            if (m_loc > f_loc + max_spacing) {
+                if (!hs_next_le(lm, &mr_m, f_loc + max_spacing, &m_loc, &m_off)) break;
+            }
+            if (m_loc + max_spacing < f_loc && (n_mates == 0 || !is_within(last_mate_loc, f_loc, max_spacing))) {
+                if (!hs_next_le(lf, &mr_f, m_loc + max_spacing, &f_loc, &f_off)) break;
+                continue;
+            }
+            while (m_loc + max_spacing >= f_loc && !out_of_more) {
+                uint32_t bp = hs_best_possible(lm, exh_m, cs_m, mr_m, max_k);
+                if (n_mates >= cfg.mate_cap) return 2;
+                if (lane == 0) {
+                    Mate *m = &mates[n_mates];
+                    m->loc = m_loc; m->best_possible = bp; m->seed_offset = m_off;
+                    m->score = (uint32_t)-2; m->score_limit = (uint32_t)-1; m->prob = 0; m->genome_offset = 0;
+                }
+                n_mates++;
+                last_mate_loc = m_loc;
+                if (!hs_next_lower(lm, &mr_m, &m_loc, &m_off)) {
+                    m_loc = 0;
+                    out_of_more = true;
+                    break;
+                }
+            }
+            uint32_t bp_fewer = hs_best_possible(lf, exh_f, cs_f, mr_f, max_k);
+            uint32_t low_mate = max_k + extra;
+            if (lane == 0) {  // lowest bestPossibleScore among mates in range (:469-475); the leader wrote them
+                for (int i = (int)n_mates - 1; i >= 0; i--) {
+                    if (mates[i].loc > f_loc + max_spacing) break;
+                    low_mate = min(low_mate, mates[i].best_possible);
+                }
+            }
+            low_mate = __shfl_sync(FULL_MASK, low_mate, 0);
+            if (low_mate + bp_fewer <= max_k + extra) {
+                if (n_cands >= cfg.cand_cap) return 2;
+                if (lane == 0) {
+                    Cand *c = &sc.cands[n_cands];
+                    c->loc = f_loc; c->set_pair = (uint8_t)sp; c->mate_index = n_mates - 1; c->seed_offset = (uint16_t)f_off;
+                    c->best_possible = (uint8_t)bp_fewer; c->next = sm->score_list[low_mate + bp_fewer]; c->anchor = -1;
+                    sm->score_list[low_mate + bp_fewer] = (int)n_cands;
+                }
+                n_cands++;
+                max_used_list = max(max_used_list, low_mate + bp_fewer);
+            }
+            if (!hs_next_lower(lf, &mr_f, &f_loc, &f_off)) break;
+        }
+    }
+    __syncwarp();
+
+    // ---- phase 3 (:516-720) ----
+    if (lane == 0) {
+        sm->n_cands = n_cands;
+        sm->list = 0;
+        sm->score_limit = max_k + extra;
+        sm->p_all = 0; sm->p_best = 0;
+        sm->best_pair_score = 65536;
+        sm->stop = 0;
+    }
+    __syncwarp();
+    for (;;) {
+        if (lane == 0) {
+            uint32_t list = (uint32_t)sm->list;
+            while (list <= max_used_list && list <= sm->score_limit && sm->score_list[list] < 0) list++;
+            sm->list = (int)list;
+            if (sm->stop || list > max_used_list || list > sm->score_limit) {
+                sm->act = 0;
+            } else {
+                int ci = sm->score_list[list];
+                const Cand *c = &sc.cands[ci];
+                sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
+                sm->act = 1;
+                sm->n_lv++;
+            }
+        }
+        __syncwarp();
+        if (!sm->act) break;
+        const uint32_t sp = sm->c_sp;
+        const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
+        double f_prob;
+        int f_off;
+        const int fs = score_location_warp(ix, v[fewer], dir_f, sm->c_loc, sm->c_seedoff, (int)sm->score_limit, false, W, L,
+                                           &f_prob, &f_off);
+        __syncwarp();
+        if (fs != -1) {
+            const uint32_t f_score = (uint32_t)fs;
+            for (;;) {  // mates of this candidate (:559-711)
+                if (lane == 0) {
+                    Mate *m = &sc.mates[sp][sm->mi];
+                    int act = 0;
+                    if (!is_within(m->loc, sm->c_loc, min_spacing) && m->best_possible <= sm->score_limit - f_score) {
+                        act = 1;
+                        if (m->score == (uint32_t)-2 || (m->score == (uint32_t)-1 && m->score_limit < sm->score_limit - f_score)) {
+                            act = 2;
+                            sm->m_loc = m->loc; sm->m_seedoff = m->seed_offset; sm->m_limit = sm->score_limit - f_score;
+                            sm->n_lv++;
+                        }
+                    }
+                    sm->act = act;
+                }
+                __syncwarp();
+                const int act = sm->act;
+                if (act == 2) {
+                    double m_prob;
+                    int m_off;
+                    int ms = score_location_warp(ix, v[more], dir_m, sm->m_loc, sm->m_seedoff, (int)sm->m_limit, false, W, L,
+                                                 &m_prob, &m_off);
+                    __syncwarp();
+                    if (lane == 0) {
+                        Mate *m = &sc.mates[sp][sm->mi];
+                        m->score = (uint32_t)ms; m->prob = m_prob; m->genome_offset = m_off; m->score_limit = sm->m_limit;
+                    }
+                }
+                if (lane == 0) {
+                    Mate *m = &sc.mates[sp][sm->mi];
+                    Cand *c = &sc.cands[sm->ci];
+                    if (act != 0 && m->score != (uint32_t)-1) {
+                        const double pair_prob = m->prob * f_prob;
+                        const uint32_t pair_score = m->score + f_score;
+                        const uint32_t new_more = m->loc + (uint32_t)m->genome_offset, new_fewer = c->loc + (uint32_t)f_off;
+                        int an = c->anchor;
+                        const int ci = sm->ci;
+                        if (an < 0) {  // look for a merge anchor among neighbouring candidates (:598-627)
+                            for (int j = ci - 1; j >= 0 && is_within(sc.cands[j].loc, new_fewer, 50) && sc.cands[j].set_pair == c->set_pair; j--) {
+                                if (sc.cands[j].anchor >= 0) { c->anchor = an = sc.cands[j].anchor; break; }
+                            }
+                            if (an < 0) {
+                                // the reference's second scan starts one above and walks DOWN (:615-619); below index 0 it
+                                // reads out of bounds there, which is treated as the end of the scan here
+                                for (int j = ci + 1; j >= 0 && j < (int)sm->n_cands && is_within(sc.cands[j].loc, new_fewer, 50) &&
+                                                 sc.cands[j].set_pair == c->set_pair; j--) {
+                                    if (sc.cands[j].anchor >= 0) { c->anchor = an = sc.cands[j].anchor; break; }
+                                }
+                            }
+                        }
+                        bool merged;
+                        double old_prob;
+                        if (an < 0) {
+                            if (sm->n_anchors >= cfg.anchor_cap) {
+                                sm->overflow = 1;
+                                merged = true;
+                                old_prob = 0;
+                            } else {
+                                Anchor *ma = &sc.anchors[sm->n_anchors];
+                                ma->loc_more = new_more; ma->loc_fewer = new_fewer; ma->prob = pair_prob; ma->pair_score = (int)pair_score;
+                                c->anchor = (int)sm->n_anchors++;
+                                merged = false;
+                                old_prob = 0;
+                            }
+                        } else {  // MergeAnchor::checkMerge (:1324-1371)
+                            Anchor *ma = &sc.anchors[an];
+                            uint32_t dm = ma->loc_more > new_more ? ma->loc_more - new_more : new_more - ma->loc_more;
+                            uint32_t df = ma->loc_fewer > new_fewer ? ma->loc_fewer - new_fewer : new_fewer - ma->loc_fewer;
+                            if (ma->loc_more == INVALID_LOC || !(dm < 50 && df < 50)) {
+                                ma->loc_more = new_more; ma->loc_fewer = new_fewer; ma->prob = pair_prob; ma->pair_score = (int)pair_score;
+                                old_prob = 0;
+                                merged = false;
+                            } else if ((int)pair_score < ma->pair_score || ((int)pair_score == ma->pair_score && pair_prob > ma->prob)) {
+                                old_prob = ma->prob;
+                                ma->prob = pair_prob;
+                                ma->pair_score = (int)pair_score;
+                                merged = false;
+                            } else {
+                                old_prob = 0;
+                                merged = true;
+                            }
+                        }
+                        if (!merged) {
+                            double t = sm->p_all - old_prob;
+                            sm->p_all = 0 > t ? 0 : t;
+                            if (pair_score <= max_k && (pair_score < sm->best_pair_score ||
+                                                        (pair_score == sm->best_pair_score && pair_prob > sm->p_best))) {
+                                sm->best_pair_score = pair_score;
+                                sm->p_best = pair_prob;
+                                sm->best_loc[fewer] = new_fewer; sm->best_loc[more] = new_more;
+                                sm->best_score[fewer] = f_score; sm->best_score[more] = m->score;
+                                sm->best_dir[fewer] = dir_f; sm->best_dir[more] = dir_m;
+                                sm->score_limit = pair_score + extra;
+                            }
+                            sm->p_all += pair_prob;
+                            if (sm->p_all >= 4.9) sm->stop = 1;  // nothing rescues a 0 MAPQ (:693-698)
+                        }
+                    }
+                    int go_on = 1;
+                    if (sm->stop || sm->overflow) go_on = 0;
+                    else if (sm->mi == 0 || !is_within(sc.mates[sp][sm->mi - 1].loc, c->loc, max_spacing)) go_on = 0;
+                    else sm->mi--;
+                    sm->act = go_on;
+                }
+                __syncwarp();
+                if (!sm->act) break;
+            }
+        }
+        if (sm->overflow) return 2;
+        if (lane == 0 && !sm->stop) sm->score_list[sm->list] = sc.cands[sm->ci].next;
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        if (sm->best_pair_score == 65536) {
+            for (int w = 0; w < 2; w++) {
+                r->location[w] = INVALID_LOC; r->mapq[w] = 0; r->score[w] = -1; r->status[w] = SNAPB200_NOT_FOUND;
+            }
+        } else {
+            for (int w = 0; w < 2; w++) {
+                bool near_int;
+                int popular = (int)(sm->popular[0] + sm->popular[1]);
+                int mq = compute_mapq_dev(sm->p_all, sm->p_best, (int)sm->best_score[w], popular, &near_int);
+                if (near_int) {
+                    uint32_t slot = atomicAdd(fix.count, 1u);
+                    if (slot < fix.cap) {
+                        MapqFix f;
+                        f.index = pair_index; f.end = (uint32_t)w; f.p_all = sm->p_all; f.p_best = sm->p_best;
+                        f.score = (int)sm->best_score[w]; f.popular = popular; f.divisor = 1; f.is_paired_rule = 1;
+                        fix.items[slot] = f;
+                    }
+                }
+                r->location[w] = sm->best_loc[w];
+                r->direction[w] = (uint8_t)sm->best_dir[w];
+                r->mapq[w] = mq;
+                r->status[w] = mq > 10 ? SNAPB200_SINGLE_HIT : SNAPB200_MULTIPLE_HITS;
+                r->score[w] = (int)sm->best_score[w];
+            }
+        }
+        r->p_all = sm->p_all;
+        r->p_best = sm->p_best;
+    }
+    __syncwarp();
+    return 1;
+}

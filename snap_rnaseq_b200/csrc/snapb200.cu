@@ -1,0 +1,1135 @@
+// snapb200.cu -- C ABI of the B200 alignment core (include/snapb200.h): index residency, scratch tiers,
+// launches, pinned double-buffered batch pipeline, statistics.  Host side of the library; all alignment
+// arithmetic is in the kernels (kernels.cuh and the headers it includes).  There is no CPU path.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+thread_local char g_last_error[512] = "";
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *snapb200_last_error(void) { return g_last_error; }
+extern "C" int snapb200_abi_version(void) { return SNAPB200_ABI_VERSION; }
+extern "C" int snapb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ---- small RAII-free helpers ------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, bool zero_new = false)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        if (zero_new) cudaMemset(p, 0, want);
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// pow(double,int) as the reference's gnu++98 build evaluates it (libstdc++ std::pow(double,int) ==
+// __builtin_powi == libgcc __powidf2), used for pow(1 - SNP_PROB, seedLen) (BaseAligner.cpp:1227)
+static double powi_ref(double x, int m)
+{
+    unsigned n = m < 0 ? -(unsigned)m : (unsigned)m;
+    double y = (n % 2) ? x : 1;
+    while (n >>= 1) {
+        x = x * x;
+        if (n % 2) y *= x;
+    }
+    return m < 0 ? 1 / y : y;
+}
+
+// computeMAPQ with libm, for the device's rare "too close to an integer to call" requests (mapq.h:32-65)
+static int compute_mapq_host(double p_all, double p_best, int score, int popular)
+{
+    if (!(p_all > p_best)) p_all = p_best;
+    if (p_all == p_best && popular == 0 && score < 5) return 70;
+    double correct = p_best / p_all;
+    int base;
+    if (correct >= 1) base = 69;
+    else {
+        int v = (int)(-10 * log10(1 - correct));
+        base = v < 69 ? v : 69;
+    }
+    int pen = popular - 10;
+    if (pen < 0) pen = 0;
+    base -= pen / 2;
+    return base > 0 ? base : 0;
+}
+
+#define FIX_CAP 65536
+
+struct snapb200_index {
+    int device = 0;
+    int sm_count = 0;
+    DevIndex dev;
+    snapb200_index_info info;
+    std::vector<void *> allocs;
+    cudaStream_t stream = nullptr;
+    // scratch shared by the synchronous batch entry points (sessions own theirs)
+    unsigned long long *stats = nullptr;  // SNAPB200_STATS_WORDS counters in HBM
+    struct snapb200_session *batch_session[2] = {nullptr, nullptr};
+};
+
+static int upload(snapb200_index *x, const void *src, size_t bytes, void **dst, size_t pad_before = 0, size_t pad_after = 0, int pad_byte = 0)
+{
+    void *p = nullptr;
+    size_t total = bytes + pad_before + pad_after;
+    if (total == 0) total = 16;
+    cudaError_t e = cudaMalloc(&p, total);
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+    x->allocs.push_back(p);
+    x->info.device_bytes += total;
+    if (pad_before || pad_after) CUDA_TRY(cudaMemset(p, pad_byte, total));
+    if (bytes) CUDA_TRY(cudaMemcpy((char *)p + pad_before, src, bytes, cudaMemcpyHostToDevice));
+    *dst = (char *)p + pad_before;
+    return 0;
+}
+
+static int finish_index(snapb200_index *x)
+{
+    // probability tables, computed on the host with libm exactly like LandauVishkin.cpp:601-653
+    const double snp = 0.001, gap_open = 0.001, gap_extend = 0.5;
+    std::vector<double> phred(256), indel(64), perfect(SNAPB200_MAX_READ_LENGTH + 1);
+    indel[0] = 1.0;
+    indel[1] = gap_open;
+    for (int i = 2; i < 64; i++) indel[i] = indel[i - 1] * gap_extend;
+    for (int i = 0; i < 256; i++) phred[i] = snp;
+    for (int i = 33; i <= 93 + 33; i++) phred[i] = 1.0 - (1.0 - pow(10.0, -1.0 * (i - 33.0) / 10.0)) * (1.0 - snp);
+    perfect[0] = 1.0;
+    for (int i = 1; i <= SNAPB200_MAX_READ_LENGTH; i++) perfect[i] = perfect[i - 1] * (1 - snp);
+    void *p;
+    int rc;
+    if ((rc = upload(x, phred.data(), phred.size() * 8, &p))) return rc;
+    x->dev.phred = (const double *)p;
+    if ((rc = upload(x, indel.data(), indel.size() * 8, &p))) return rc;
+    x->dev.indel = (const double *)p;
+    if ((rc = upload(x, perfect.data(), perfect.size() * 8, &p))) return rc;
+    x->dev.perfect = (const double *)p;
+    x->dev.seed_prob = powi_ref(1 - snp, (int)x->dev.seed_len);
+    CUDA_TRY(cudaMalloc((void **)&x->stats, SNAPB200_STATS_WORDS * 8));
+    CUDA_TRY(cudaMemset(x->stats, 0, SNAPB200_STATS_WORDS * 8));
+    CUDA_TRY(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, x->device));
+    x->sm_count = prop.multiProcessorCount;
+    x->info.device = x->device;
+    return 0;
+}
+
+static int make_index(int device, uint32_t seed_len, uint32_t padding, uint32_t n_tables, const uint64_t *table_sizes,
+                      const void *tables, const uint32_t *overflow, uint32_t overflow_words, const uint8_t *bases,
+                      uint32_t n_bases, const uint32_t *piece_offsets, uint32_t n_pieces, snapb200_index **out)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_error(SNAPB200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return set_error(SNAPB200_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    if (seed_len < 16 || seed_len > 25) return set_error(SNAPB200_ERR_ARG, "seed length %u unsupported (16..25, SeedSequencer.h)", seed_len);
+    uint32_t expect_tables = 1;
+    for (uint32_t i = 16; i < seed_len; i++) expect_tables *= 4;
+    if (n_tables != expect_tables) return set_error(SNAPB200_ERR_IO, "index has %u hash tables, seed length %u needs %u", n_tables, seed_len, expect_tables);
+    CUDA_TRY(cudaSetDevice(device));
+    snapb200_index *x = new snapb200_index();
+    x->device = device;
+    memset(&x->dev, 0, sizeof(x->dev));
+    memset(&x->info, 0, sizeof(x->info));
+    std::vector<uint64_t> start(n_tables);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_tables; i++) { start[i] = total; total += table_sizes[i]; }
+    void *p;
+    int rc = 0;
+    do {
+        if ((rc = upload(x, tables, total * sizeof(HtEntry), &p))) break;
+        x->dev.tables = (const HtEntry *)p;
+        if ((rc = upload(x, start.data(), n_tables * 8, &p))) break;
+        x->dev.table_start = (const uint64_t *)p;
+        if ((rc = upload(x, table_sizes, n_tables * 8, &p))) break;
+        x->dev.table_size = (const uint64_t *)p;
+        if ((rc = upload(x, overflow, (size_t)overflow_words * 4, &p, 0, 16))) break;
+        x->dev.overflow = (const uint32_t *)p;
+        if ((rc = upload(x, bases, n_bases, &p, GENOME_PAD, GENOME_PAD, 'n'))) break;
+        x->dev.genome = (const uint8_t *)p;
+        if ((rc = upload(x, piece_offsets, (size_t)n_pieces * 4, &p))) break;
+        x->dev.piece_begin = (const uint32_t *)p;
+        x->dev.n_bases = n_bases; x->dev.n_pieces = n_pieces; x->dev.seed_len = seed_len; x->dev.n_tables = n_tables;
+        x->dev.padding = padding;
+        x->info.n_bases = n_bases; x->info.n_pieces = n_pieces; x->info.seed_len = seed_len; x->info.n_hash_tables = n_tables;
+        x->info.overflow_table_size = overflow_words; x->info.chromosome_padding = padding; x->info.hash_table_entries = total;
+        rc = finish_index(x);
+    } while (0);
+    if (rc) { snapb200_index_close(x); return rc; }
+    *out = x;
+    return 0;
+}
+
+extern "C" int snapb200_index_from_memory(int device, uint32_t seed_len, uint32_t chromosome_padding, uint32_t n_hash_tables,
+                                          const uint64_t *table_sizes, const void *tables, const uint32_t *overflow,
+                                          uint32_t overflow_words, const uint8_t *bases, uint32_t n_bases,
+                                          const uint32_t *piece_offsets, uint32_t n_pieces, snapb200_index **out)
+{
+    if (!out || !table_sizes || !tables || !bases) return set_error(SNAPB200_ERR_ARG, "null argument");
+    return make_index(device, seed_len, chromosome_padding, n_hash_tables, table_sizes, tables, overflow, overflow_words, bases,
+                      n_bases, piece_offsets, n_pieces, out);
+}
+
+static bool read_file(const std::string &path, std::vector<char> &out)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize((size_t)sz);
+    size_t got = sz ? fread(out.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    return got == (size_t)sz;
+}
+
+// File formats: GenomeIndex.cpp:646-710 (GenomeIndex, OverflowTable, GenomeIndexHash), HashTable.cpp:181-215
+// (per table: u32 magic 0xb111b010, size_t tableSize, size_t usedElementCount, entries), Genome.cpp:126-158.
+extern "C" int snapb200_index_open(const char *dir, int device, snapb200_index **out)
+{
+    if (!dir || !out) return set_error(SNAPB200_ERR_ARG, "null argument");
+    std::string d(dir);
+    std::vector<char> meta, ovf, hash, genome;
+    if (!read_file(d + "/GenomeIndex", meta)) return set_error(SNAPB200_ERR_IO, "cannot read %s/GenomeIndex", dir);
+    meta.push_back(0);
+    unsigned major, minor, n_tables, overflow_words, seed_len, padding;
+    if (sscanf(meta.data(), "%u %u %u %u %u %u", &major, &minor, &n_tables, &overflow_words, &seed_len, &padding) != 6)
+        return set_error(SNAPB200_ERR_IO, "%s/GenomeIndex: expected six integers", dir);
+    if (!read_file(d + "/OverflowTable", ovf) || ovf.size() < (size_t)overflow_words * 4)
+        return set_error(SNAPB200_ERR_IO, "cannot read %s/OverflowTable (%u words expected)", dir, overflow_words);
+    if (!read_file(d + "/GenomeIndexHash", hash)) return set_error(SNAPB200_ERR_IO, "cannot read %s/GenomeIndexHash", dir);
+    std::vector<uint64_t> sizes(n_tables);
+    std::vector<char> entries;
+    entries.reserve(hash.size());
+    size_t pos = 0;
+    for (unsigned i = 0; i < n_tables; i++) {
+        if (pos + 20 > hash.size()) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash truncated at table %u", i);
+        uint32_t magic;
+        uint64_t size, used;
+        memcpy(&magic, &hash[pos], 4); memcpy(&size, &hash[pos + 4], 8); memcpy(&used, &hash[pos + 12], 8);
+        pos += 20;
+        if (magic != 0xb111b010u) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash: bad magic at table %u", i);
+        if (size == 0 || pos + size * 12 > hash.size()) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash: bad size at table %u", i);
+        sizes[i] = size;
+        entries.insert(entries.end(), hash.begin() + pos, hash.begin() + pos + size * 12);
+        pos += size * 12;
+    }
+    std::vector<char>().swap(hash);
+    if (!read_file(d + "/Genome", genome)) return set_error(SNAPB200_ERR_IO, "cannot read %s/Genome", dir);
+    unsigned n_bases = 0, n_pieces = 0;
+    size_t gp = 0;
+    {
+        size_t eol = std::find(genome.begin(), genome.end(), '\n') - genome.begin();
+        if (eol >= genome.size()) return set_error(SNAPB200_ERR_IO, "Genome: no header line");
+        std::string line(genome.begin(), genome.begin() + eol);
+        if (sscanf(line.c_str(), "%u %u", &n_bases, &n_pieces) != 2) return set_error(SNAPB200_ERR_IO, "Genome: bad header");
+        gp = eol + 1;
+    }
+    std::vector<uint32_t> pieces(n_pieces);
+    for (unsigned i = 0; i < n_pieces; i++) {
+        size_t eol = std::find(genome.begin() + gp, genome.end(), '\n') - genome.begin();
+        if (eol >= genome.size()) return set_error(SNAPB200_ERR_IO, "Genome: truncated piece table");
+        pieces[i] = (uint32_t)atoi(std::string(genome.begin() + gp, genome.begin() + eol).c_str());
+        gp = eol + 1;
+    }
+    if (gp + n_bases > genome.size()) return set_error(SNAPB200_ERR_IO, "Genome: %u bases expected", n_bases);
+    return make_index(device, seed_len, padding, n_tables, sizes.data(), entries.data(), (const uint32_t *)ovf.data(), overflow_words,
+                      (const uint8_t *)genome.data() + gp, n_bases, pieces.data(), n_pieces, out);
+}
+
+extern "C" int snapb200_index_info_get(const snapb200_index *idx, snapb200_index_info *info)
+{
+    if (!idx || !info) return set_error(SNAPB200_ERR_ARG, "null argument");
+    *info = idx->info;
+    return 0;
+}
+
+// ---- sessions ---------------------------------------------------------------------------------------------------
+struct snapb200_session {
+    snapb200_index *idx = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t max_items = 0, max_read_len = 0;
+    // resident batch
+    DevBuf offsets[2], bases[2], quals[2];
+    uint32_t n[2] = {0, 0};
+    uint32_t max_len_seen = 0;
+    // results + lists
+    DevBuf single_res, paired_res, fb_single_res, retry_list, fallback_list, fb_positions, fix, counters;
+    DevBuf mh_counts, mh_locs, mh_rcs, mh_scores;
+    // scratch tiers
+    DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
+    DevBuf p_cands, p_mates, p_anchors;
+    uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
+    uint32_t anchors_warps = 0;
+    // last run
+    float last_ms = 0;
+    uint32_t last_launches = 0;
+    uint64_t total_launches = 0;
+    uint32_t last_n = 0;
+    int last_kind = 0;  // 1 single, 2 paired
+    std::vector<MapqFix> host_fix;
+    int limit_hit = 0;
+};
+
+static uint32_t next_pow2(uint32_t v)
+{
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+extern "C" int snapb200_session_create(snapb200_index *idx, uint32_t max_items, uint32_t max_read_len, snapb200_session **out)
+{
+    if (!idx || !out) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (max_read_len > SNAPB200_MAX_READ_LENGTH) return set_error(SNAPB200_ERR_ARG, "max_read_len %u > MAX_READ_LENGTH", max_read_len);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    snapb200_session *s = new snapb200_session();
+    s->idx = idx;
+    s->max_items = max_items;
+    s->max_read_len = max_read_len;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&s->ev0));
+    CUDA_TRY(cudaEventCreate(&s->ev1));
+    int rc;
+    if ((rc = s->counters.ensure(sizeof(Counters)))) return rc;
+    if ((rc = s->fix.ensure(sizeof(MapqFix) * FIX_CAP))) return rc;
+    *out = s;
+    return 0;
+}
+
+extern "C" void snapb200_session_destroy(snapb200_session *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->idx->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    DevBuf *all[] = {&s->offsets[0], &s->offsets[1], &s->bases[0], &s->bases[1], &s->quals[0], &s->quals[1], &s->single_res,
+                     &s->paired_res, &s->fb_single_res, &s->retry_list, &s->fallback_list, &s->fb_positions, &s->fix, &s->counters,
+                     &s->mh_counts, &s->mh_locs, &s->mh_rcs, &s->mh_scores, &s->s_pool, &s->s_anchors, &s->s_lists, &s->s_epochs,
+                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors};
+    for (DevBuf *b : all) b->release();
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" void snapb200_index_close(snapb200_index *x)
+{
+    if (!x) return;
+    cudaSetDevice(x->device);
+    for (int i = 0; i < 2; i++) if (x->batch_session[i]) snapb200_session_destroy(x->batch_session[i]);
+    for (void *p : x->allocs) cudaFree(p);
+    if (x->stats) cudaFree(x->stats);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+}
+
+static int validate_batch(const snapb200_read_batch *b, uint32_t *max_len)
+{
+    if (!b || (b->n && (!b->offsets || !b->bases || !b->quals))) return set_error(SNAPB200_ERR_ARG, "null read batch");
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < b->n; i++) {
+        if (b->offsets[i + 1] < b->offsets[i]) return set_error(SNAPB200_ERR_ARG, "read offsets not monotonic at %u", i);
+        m = std::max(m, b->offsets[i + 1] - b->offsets[i]);
+    }
+    // the reference aborts on reads longer than maxReadSize (BaseAligner.cpp:609-613)
+    if (m > SNAPB200_MAX_READ_LENGTH) return set_error(SNAPB200_ERR_ARG, "read of %u bases exceeds MAX_READ_LENGTH %d", m, SNAPB200_MAX_READ_LENGTH);
+    *max_len = m;
+    return 0;
+}
+
+extern "C" int snapb200_session_upload(snapb200_session *s, int slot, const snapb200_read_batch *reads)
+{
+    if (!s || slot < 0 || slot > 1) return set_error(SNAPB200_ERR_ARG, "bad session/slot");
+    uint32_t m = 0;
+    int rc = validate_batch(reads, &m);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(s->idx->device));
+    const uint32_t n = reads->n;
+    const size_t nb = n ? reads->offsets[n] : 0;
+    if ((rc = s->offsets[slot].ensure((size_t)(n + 1) * 4))) return rc;
+    if ((rc = s->bases[slot].ensure(nb + 16))) return rc;
+    if ((rc = s->quals[slot].ensure(nb + 16))) return rc;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(s->offsets[slot].p, reads->offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+        if (nb) {
+            CUDA_TRY(cudaMemcpyAsync(s->bases[slot].p, reads->bases, nb, cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(s->quals[slot].p, reads->quals, nb, cudaMemcpyHostToDevice, s->stream));
+        }
+    }
+    s->n[slot] = n;
+    if (slot == 0) s->max_len_seen = m; else s->max_len_seen = std::max(s->max_len_seen, m);
+    return 0;
+}
+
+static DevBatch dev_batch(const snapb200_session *s, int slot)
+{
+    DevBatch b;
+    b.offsets = s->offsets[slot].as<uint32_t>();
+    b.bases = s->bases[slot].as<uint8_t>();
+    b.quals = s->quals[slot].as<uint8_t>();
+    b.n = s->n[slot];
+    return b;
+}
+
+static int read_counters(snapb200_session *s, Counters *c)
+{
+    CUDA_TRY(cudaMemcpyAsync(c, s->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int reset_work(snapb200_session *s)
+{
+    CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, sizeof(uint32_t), s->stream));  // Counters::work
+    return 0;
+}
+
+// grid: as many CTAs as fit, a multiple of the SM count
+template <class K>
+static int grid_for(K kernel, size_t smem, int sm_count, int *ctas_per_sm)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CTA_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    *ctas_per_sm = per_sm;
+    return per_sm * sm_count;
+}
+
+static const size_t SCRATCH_BUDGET = (size_t)24 << 30;  // HBM the scratch of one launch may take
+
+struct SingleTier { uint32_t pool_cap, tsize; int grid; };
+
+static int launch_single(snapb200_session *s, const SingleCfg &cfg_in, const SingleTier &tier, const DevBatch b[2], int two_batches,
+                         const uint32_t *positions, uint32_t n_items, snapb200_single_result *results, int mapq_divisor)
+{
+    snapb200_index *x = s->idx;
+    SingleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ix = x->dev;
+    a.cfg = cfg_in;
+    a.cfg.pool_cap = tier.pool_cap;
+    a.cfg.tmask = tier.tsize - 1;
+    a.b[0] = b[0];
+    a.b[1] = b[1];
+    a.two_batches = two_batches;
+    a.positions = positions;
+    a.items = nullptr;
+    a.n_items = n_items;
+    a.results = results;
+    a.mh_counts = s->mh_counts.as<int32_t>(); a.mh_locs = s->mh_locs.as<uint32_t>();
+    a.mh_rcs = s->mh_rcs.as<uint8_t>(); a.mh_scores = s->mh_scores.as<int32_t>();
+    const size_t warps = (size_t)tier.grid * WARPS_PER_CTA;
+    int rc;
+    if ((rc = s->s_pool.ensure(warps * tier.pool_cap * sizeof(Elem)))) return rc;
+    // anchors carry an epoch tag and must start zeroed; re-zero when the geometry changes
+    const size_t anchor_bytes = warps * 2 * tier.tsize * sizeof(int2);
+    if (anchor_bytes > s->s_anchors.cap || s->anchors_tsize != tier.tsize || s->anchors_warps != warps) {
+        if ((rc = s->s_anchors.ensure(anchor_bytes))) return rc;
+        CUDA_TRY(cudaMemsetAsync(s->s_anchors.p, 0, anchor_bytes, s->stream));
+        if ((rc = s->s_epochs.ensure(warps * 4))) return rc;
+        CUDA_TRY(cudaMemsetAsync(s->s_epochs.p, 0, warps * 4, s->stream));
+        s->anchors_tsize = tier.tsize;
+        s->anchors_warps = (uint32_t)warps;
+    }
+    if ((rc = s->s_lists.ensure(warps * 2 * a.cfg.n_lists * sizeof(int)))) return rc;
+    if (a.cfg.max_hits_to_get) {
+        if ((rc = s->s_hitc.ensure(warps * MAXK * 4))) return rc;
+        if ((rc = s->s_hitl.ensure(warps * MAXK * 512 * 4))) return rc;
+        if ((rc = s->s_hitr.ensure(warps * MAXK * 512))) return rc;
+        a.hit_count = s->s_hitc.as<uint32_t>(); a.hit_loc = s->s_hitl.as<uint32_t>(); a.hit_rc = s->s_hitr.as<uint8_t>();
+    }
+    a.pool = s->s_pool.as<Elem>(); a.anchors = s->s_anchors.as<int2>(); a.lists = s->s_lists.as<int>();
+    a.epochs = s->s_epochs.as<uint32_t>();
+    a.ctr = s->counters.as<Counters>(); a.retry_list = s->retry_list.as<uint32_t>();
+    a.fix = s->fix.as<MapqFix>(); a.fix_cap = FIX_CAP;
+    a.stats = x->stats;
+    a.mapq_divisor = mapq_divisor;
+    if ((rc = reset_work(s))) return rc;
+    const size_t smem = single_warp_shared(a.cfg.rl) * WARPS_PER_CTA;
+    single_kernel<<<tier.grid, CTA_THREADS, smem, s->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    s->last_launches++;
+    return 0;
+}
+
+static int single_cfg_from(const snapb200_index *x, const snapb200_single_params *p, uint32_t max_len, SingleCfg *cfg)
+{
+    if (!p) return set_error(SNAPB200_ERR_ARG, "null params");
+    if (p->max_k + p->extra_search_depth >= MAXK) return set_error(SNAPB200_ERR_ARG, "max_k + extra_search_depth must be < %d (SingleAligner.cpp:117-121)", MAXK);
+    if (p->max_hits == 0) return set_error(SNAPB200_ERR_ARG, "max_hits must be > 0");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->max_hits = p->max_hits; cfg->max_k = p->max_k; cfg->num_seeds = p->num_seeds; cfg->extra = p->extra_search_depth;
+    cfg->explore = p->explore_popular_seeds; cfg->stop_first = p->stop_on_first_hit; cfg->max_hits_to_get = p->max_hits_to_get;
+    cfg->seed_coverage = p->seed_coverage;
+    uint32_t ctor_seeds = p->num_seeds ? p->num_seeds : (uint32_t)(int)(p->seed_coverage * p->max_read_size / x->dev.seed_len);
+    if (ctor_seeds == 0) return set_error(SNAPB200_ERR_ARG, "num_seeds/seed_coverage give zero seeds");
+    cfg->n_lists = ctor_seeds + 1;
+    cfg->rl = std::max(32u, (max_len + 15) & ~15u);
+    return 0;
+}
+
+// Small tier: enough for almost every read; large tier: the bound implied by the reference's loop
+// ((maxSeeds+1) seed directions of at most maxHits hits), with fewer resident warps if HBM would not hold it.
+static void single_tiers(const snapb200_index *x, const SingleCfg &cfg, uint32_t max_len, SingleTier *small_t, SingleTier *large_t)
+{
+    uint32_t max_seeds = cfg.num_seeds ? cfg.num_seeds : (uint32_t)(int)(cfg.seed_coverage * max_len / x->dev.seed_len);
+    uint64_t bound = (uint64_t)cfg.max_hits * (max_seeds + 1);
+    if (bound < 64) bound = 64;
+    if (bound > (1u << 24)) bound = 1u << 24;
+    int per_sm = 1;
+    size_t smem = single_warp_shared(cfg.rl) * WARPS_PER_CTA;
+    int grid = grid_for(single_kernel, smem, x->sm_count, &per_sm);
+    small_t->pool_cap = (uint32_t)std::min<uint64_t>(bound, 1024);
+    small_t->tsize = next_pow2(small_t->pool_cap * 2);
+    small_t->grid = grid;
+    large_t->pool_cap = (uint32_t)bound;
+    large_t->tsize = next_pow2((uint32_t)std::min<uint64_t>(bound * 2, 1u << 25));
+    size_t per_warp = (size_t)large_t->pool_cap * sizeof(Elem) + (size_t)large_t->tsize * 2 * sizeof(int2);
+    size_t warps = std::max<size_t>(1, SCRATCH_BUDGET / per_warp);
+    int g = (int)std::min<size_t>((size_t)grid, std::max<size_t>(1, warps / WARPS_PER_CTA));
+    large_t->grid = g;
+}
+
+// run the single-end aligner over result slots [0,n_items) (positions == null) or the listed ones
+static int run_single_tiers(snapb200_session *s, const SingleCfg &cfg, uint32_t max_len, const DevBatch b[2], int two_batches,
+                            const uint32_t *positions, uint32_t n_items, snapb200_single_result *results, int mapq_divisor)
+{
+    if (n_items == 0) return 0;
+    SingleTier small_t, large_t;
+    single_tiers(s->idx, cfg, max_len, &small_t, &large_t);
+    int rc;
+    if ((rc = s->retry_list.ensure(((size_t)std::max(n_items, s->max_items) + 1) * 4))) return rc;
+    CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
+    if ((rc = launch_single(s, cfg, small_t, b, two_batches, positions, n_items, results, mapq_divisor))) return rc;
+    if (small_t.pool_cap == large_t.pool_cap) return 0;
+    Counters c;
+    if ((rc = read_counters(s, &c))) return rc;
+    if (c.n_retry == 0) return 0;
+    // rerun the overflowed reads with the full-size pools; the retry list holds their result slots
+    std::vector<uint32_t> list(c.n_retry);
+    CUDA_TRY(cudaMemcpyAsync(list.data(), s->retry_list.p, (size_t)c.n_retry * 4, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::sort(list.begin(), list.end());
+    DevBuf tmp;
+    if ((rc = tmp.ensure((size_t)c.n_retry * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, list.data(), (size_t)c.n_retry * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
+    rc = launch_single(s, cfg, large_t, b, two_batches, tmp.as<uint32_t>(), c.n_retry, results, mapq_divisor);
+    if (!rc) {
+        Counters c2;
+        rc = read_counters(s, &c2);
+        if (!rc && c2.n_retry) rc = set_error(SNAPB200_ERR_LIMIT, "%u reads overflowed the full-size candidate pool", c2.n_retry);
+    }
+    tmp.release();
+    return rc;
+}
+
+static int begin_run(snapb200_session *s)
+{
+    CUDA_TRY(cudaSetDevice(s->idx->device));
+    s->last_launches = 0;
+    s->host_fix.clear();
+    s->limit_hit = 0;
+    CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, sizeof(Counters), s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    return 0;
+}
+
+static int end_run(snapb200_session *s)
+{
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    Counters c;
+    int rc = read_counters(s, &c);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    s->total_launches += s->last_launches;
+    uint32_t nfix = std::min<uint32_t>(c.n_fix, FIX_CAP);
+    if (c.n_fix > FIX_CAP) return set_error(SNAPB200_ERR_LIMIT, "too many mapq fix-up requests (%u)", c.n_fix);
+    s->host_fix.resize(nfix);
+    if (nfix) CUDA_TRY(cudaMemcpy(s->host_fix.data(), s->fix.p, sizeof(MapqFix) * nfix, cudaMemcpyDeviceToHost));
+    s->limit_hit = c.n_limit != 0;
+    return 0;
+}
+
+extern "C" int snapb200_session_run_single(snapb200_session *s, const snapb200_single_params *p)
+{
+    if (!s) return set_error(SNAPB200_ERR_ARG, "null session");
+    SingleCfg cfg;
+    int rc = single_cfg_from(s->idx, p, s->max_len_seen, &cfg);
+    if (rc) return rc;
+    if ((rc = begin_run(s))) return rc;
+    const uint32_t n = s->n[0];
+    if ((rc = s->single_res.ensure((size_t)std::max(n, 1u) * sizeof(snapb200_single_result)))) return rc;
+    if (cfg.max_hits_to_get) {
+        size_t mh = cfg.max_hits_to_get;
+        if ((rc = s->mh_counts.ensure((size_t)std::max(n, 1u) * 4))) return rc;
+        if ((rc = s->mh_locs.ensure((size_t)std::max(n, 1u) * mh * 4))) return rc;
+        if ((rc = s->mh_rcs.ensure((size_t)std::max(n, 1u) * mh))) return rc;
+        if ((rc = s->mh_scores.ensure((size_t)std::max(n, 1u) * mh * 4))) return rc;
+    }
+    DevBatch b[2] = {dev_batch(s, 0), dev_batch(s, 0)};
+    if ((rc = run_single_tiers(s, cfg, s->max_len_seen, b, 0, nullptr, n, s->single_res.as<snapb200_single_result>(), 1))) return rc;
+    if (n) {
+        stats_single_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->single_res.as<snapb200_single_result>(), n, s->idx->stats);
+        s->last_launches++;
+    }
+    s->last_kind = 1;
+    s->last_n = n;
+    return end_run(s);
+}
+
+__global__ void expand_fallback_kernel(const uint32_t *fallback_list, uint32_t n, uint32_t *positions)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 2 * n) positions[t] = fallback_list[t >> 1] * 2 + (t & 1);
+}
+
+static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, const PairedCfg &cfg, int grid, const uint32_t *positions,
+                         uint32_t n_items)
+{
+    snapb200_index *x = s->idx;
+    PairedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ix = x->dev;
+    a.cfg = cfg;
+    a.b[0] = dev_batch(s, 0);
+    a.b[1] = dev_batch(s, 1);
+    a.positions = positions;
+    a.n_items = n_items;
+    a.results = s->paired_res.as<snapb200_paired_result>();
+    a.force_spacing = p->force_spacing;
+    const size_t warps = (size_t)grid * WARPS_PER_CTA;
+    int rc;
+    if ((rc = s->p_cands.ensure(warps * cfg.cand_cap * sizeof(Cand)))) return rc;
+    if ((rc = s->p_mates.ensure(warps * 2 * cfg.mate_cap * sizeof(Mate)))) return rc;
+    if ((rc = s->p_anchors.ensure(warps * cfg.anchor_cap * sizeof(Anchor)))) return rc;
+    a.cands = s->p_cands.as<Cand>(); a.mates = s->p_mates.as<Mate>(); a.anchors = s->p_anchors.as<Anchor>();
+    a.ctr = s->counters.as<Counters>();
+    a.retry_list = s->retry_list.as<uint32_t>(); a.fallback_list = s->fallback_list.as<uint32_t>();
+    a.fix = s->fix.as<MapqFix>(); a.fix_cap = FIX_CAP;
+    a.stats = x->stats;
+    if ((rc = reset_work(s))) return rc;
+    const size_t smem = paired_warp_shared(cfg.rl) * WARPS_PER_CTA;
+    paired_kernel<<<grid, CTA_THREADS, smem, s->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    s->last_launches++;
+    return 0;
+}
+
+extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_paired_params *p)
+{
+    if (!s || !p) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (s->n[0] != s->n[1]) return set_error(SNAPB200_ERR_ARG, "mate batches differ in size (%u vs %u)", s->n[0], s->n[1]);
+    snapb200_index *x = s->idx;
+    if (p->max_k + p->extra_search_depth >= MAXK) return set_error(SNAPB200_ERR_ARG, "max_k + extra_search_depth must be < %d", MAXK);
+    const uint32_t num_seeds = std::min(p->num_seeds, 30u);  // MAX_MAX_SEEDS (IntersectingPairedEndAligner.h:93)
+    uint32_t ctor_seeds = num_seeds ? num_seeds : (uint32_t)(p->max_read_size * p->seed_coverage / x->dev.seed_len);
+    uint32_t run_seeds = num_seeds ? num_seeds : (uint32_t)(s->max_len_seen * p->seed_coverage / x->dev.seed_len);
+    if (run_seeds > MAX_LOOKUPS) return set_error(SNAPB200_ERR_ARG, "%u seeds per mate requested; this build holds %d lookups per hit set", run_seeds, MAX_LOOKUPS);
+    if (ctor_seeds == 0) return set_error(SNAPB200_ERR_ARG, "num_seeds/seed_coverage give zero seeds");
+    int rc;
+    if ((rc = begin_run(s))) return rc;
+    const uint32_t n = s->n[0];
+    const uint32_t rl = std::max(32u, (s->max_len_seen + 15) & ~15u);
+    if ((rc = s->paired_res.ensure((size_t)std::max(n, 1u) * sizeof(snapb200_paired_result)))) return rc;
+    if ((rc = s->retry_list.ensure(((size_t)std::max(2 * n, s->max_items) + 1) * 4))) return rc;
+    if ((rc = s->fallback_list.ensure(((size_t)n + 1) * 4))) return rc;
+    PairedCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.max_k = p->max_k; cfg.num_seeds = num_seeds; cfg.extra = p->extra_search_depth; cfg.min_spacing = p->min_spacing;
+    cfg.max_spacing = p->max_spacing; cfg.max_big_hits = p->max_big_hits; cfg.seed_coverage = p->seed_coverage; cfg.rl = rl;
+    // the reference's pool sizes (IntersectingPairedEndAligner.cpp:128-138)
+    uint64_t ref_pool = std::min<uint64_t>(p->max_candidate_pool_size, (uint64_t)p->max_big_hits * ctor_seeds * 2);
+    int per_sm = 1;
+    const size_t smem = paired_warp_shared(rl) * WARPS_PER_CTA;
+    int grid = grid_for(paired_kernel, smem, x->sm_count, &per_sm);
+    if (n) {
+        // small tier
+        cfg.cand_cap = (uint32_t)std::min<uint64_t>(ref_pool, 2048);
+        cfg.mate_cap = (uint32_t)std::min<uint64_t>(ref_pool / 2, 2048);
+        cfg.anchor_cap = cfg.cand_cap;
+        cfg.hard_limit = (cfg.cand_cap == ref_pool && cfg.mate_cap == ref_pool / 2) ? 1 : 0;
+        if ((rc = launch_paired(s, p, cfg, grid, nullptr, n))) return rc;
+        Counters c;
+        if ((rc = read_counters(s, &c))) return rc;
+        if (c.n_retry) {
+            std::vector<uint32_t> list(c.n_retry);
+            CUDA_TRY(cudaMemcpyAsync(list.data(), s->retry_list.p, (size_t)c.n_retry * 4, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            std::sort(list.begin(), list.end());
+            DevBuf tmp;
+            if ((rc = tmp.ensure((size_t)c.n_retry * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(tmp.p, list.data(), (size_t)c.n_retry * 4, cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
+            PairedCfg big = cfg;
+            big.cand_cap = (uint32_t)ref_pool; big.mate_cap = (uint32_t)(ref_pool / 2); big.anchor_cap = (uint32_t)ref_pool;
+            big.hard_limit = 1;
+            size_t per_warp = (size_t)big.cand_cap * sizeof(Cand) + (size_t)big.mate_cap * 2 * sizeof(Mate) + (size_t)big.anchor_cap * sizeof(Anchor);
+            size_t warps = std::max<size_t>(1, SCRATCH_BUDGET / std::max<size_t>(per_warp, 1));
+            int g = (int)std::min<size_t>((size_t)grid, std::max<size_t>(1, warps / WARPS_PER_CTA));
+            rc = launch_paired(s, p, big, g, tmp.as<uint32_t>(), c.n_retry);
+            if (!rc) rc = read_counters(s, &c);
+            tmp.release();
+            if (rc) return rc;
+        }
+        // single-end fallback for the pairs the intersecting aligner could not place
+        if (c.n_fallback) {
+            const uint32_t nf = c.n_fallback;
+            if ((rc = s->fb_single_res.ensure((size_t)2 * n * sizeof(snapb200_single_result)))) return rc;
+            if ((rc = s->fb_positions.ensure((size_t)2 * nf * 4))) return rc;
+            expand_fallback_kernel<<<(2 * nf + 255) / 256, 256, 0, s->stream>>>(s->fallback_list.as<uint32_t>(), nf, s->fb_positions.as<uint32_t>());
+            s->last_launches++;
+            snapb200_single_params sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.max_hits = p->max_hits; sp.max_k = p->max_k; sp.max_read_size = p->max_read_size; sp.num_seeds = p->num_seeds;
+            sp.seed_coverage = p->seed_coverage; sp.extra_search_depth = p->extra_search_depth;
+            SingleCfg scfg;
+            if ((rc = single_cfg_from(x, &sp, s->max_len_seen, &scfg))) return rc;
+            DevBatch b[2] = {dev_batch(s, 0), dev_batch(s, 1)};
+            if ((rc = run_single_tiers(s, scfg, s->max_len_seen, b, 1, s->fb_positions.as<uint32_t>(), 2 * nf,
+                                       s->fb_single_res.as<snapb200_single_result>(), 4))) return rc;
+            merge_fallback_kernel<<<(2 * nf + 255) / 256, 256, 0, s->stream>>>(s->fallback_list.as<uint32_t>(), nf,
+                                                                               s->fb_single_res.as<snapb200_single_result>(),
+                                                                               s->paired_res.as<snapb200_paired_result>());
+            s->last_launches++;
+        }
+        stats_paired_kernel<<<(2 * n + 255) / 256, 256, 0, s->stream>>>(s->paired_res.as<snapb200_paired_result>(), n, x->stats);
+        s->last_launches++;
+    }
+    s->last_kind = 2;
+    s->last_n = n;
+    return end_run(s);
+}
+
+extern "C" int snapb200_session_download_single(snapb200_session *s, snapb200_single_result *results)
+{
+    if (!s || s->last_kind != 1) return set_error(SNAPB200_ERR_ARG, "no single-end run to download");
+    CUDA_TRY(cudaSetDevice(s->idx->device));
+    if (s->last_n) {
+        CUDA_TRY(cudaMemcpyAsync(results, s->single_res.p, (size_t)s->last_n * sizeof(snapb200_single_result), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    for (const MapqFix &f : s->host_fix) {  // see compute_mapq_dev
+        snapb200_single_result *r = &results[f.index];
+        int mq = compute_mapq_host(f.p_all, f.p_best, f.score, f.popular);
+        r->mapq = mq;
+        r->status = mq >= 10 ? SNAPB200_SINGLE_HIT : SNAPB200_MULTIPLE_HITS;
+    }
+    return 0;
+}
+
+extern "C" int snapb200_session_download_paired(snapb200_session *s, snapb200_paired_result *results)
+{
+    if (!s || s->last_kind != 2) return set_error(SNAPB200_ERR_ARG, "no paired-end run to download");
+    CUDA_TRY(cudaSetDevice(s->idx->device));
+    if (s->last_n) {
+        CUDA_TRY(cudaMemcpyAsync(results, s->paired_res.p, (size_t)s->last_n * sizeof(snapb200_paired_result), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    for (const MapqFix &f : s->host_fix) {
+        int mq = compute_mapq_host(f.p_all, f.p_best, f.score, f.popular);
+        if (f.is_paired_rule) {
+            snapb200_paired_result *r = &results[f.index];
+            r->mapq[f.end] = mq;
+            r->status[f.end] = mq > 10 ? SNAPB200_SINGLE_HIT : SNAPB200_MULTIPLE_HITS;
+        } else {  // single-end fallback: index = pair*2+end, mapq/4 (ChimericPairedEndAligner.cpp:115)
+            snapb200_paired_result *r = &results[f.index >> 1];
+            r->status[f.index & 1] = mq >= 10 ? SNAPB200_SINGLE_HIT : SNAPB200_MULTIPLE_HITS;
+            r->mapq[f.index & 1] = mq / f.divisor;
+        }
+    }
+    if (s->limit_hit) return set_error(SNAPB200_ERR_LIMIT, "a pair exceeded the reference's candidate pool (-mcp); the reference exits here");
+    return 0;
+}
+
+extern "C" int snapb200_session_sync(snapb200_session *s)
+{
+    if (!s) return set_error(SNAPB200_ERR_ARG, "null session");
+    CUDA_TRY(cudaSetDevice(s->idx->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int snapb200_session_last_run(const snapb200_session *s, float *kernel_ms, uint32_t *launches, uint64_t *total_launches)
+{
+    if (!s) return set_error(SNAPB200_ERR_ARG, "null session");
+    if (kernel_ms) *kernel_ms = s->last_ms;
+    if (launches) *launches = s->last_launches;
+    if (total_launches) *total_launches = s->total_launches;
+    return 0;
+}
+
+// ---- synchronous batch entry points: chunked, double-buffered over two sessions ------------------------------
+static const uint32_t CHUNK = 1u << 18;
+
+static snapb200_read_batch sub_batch(const snapb200_read_batch *b, uint32_t lo, uint32_t hi, std::vector<uint32_t> &off_store)
+{
+    snapb200_read_batch r;
+    r.n = hi - lo;
+    const uint32_t base = b->offsets[lo];
+    if (base == 0) {
+        r.offsets = b->offsets + lo;
+    } else {
+        off_store.resize(r.n + 1);
+        for (uint32_t i = 0; i <= r.n; i++) off_store[i] = b->offsets[lo + i] - base;
+        r.offsets = off_store.data();
+    }
+    r.bases = b->bases + base;
+    r.quals = b->quals + base;
+    return r;
+}
+
+static int get_batch_sessions(snapb200_index *idx, snapb200_session **s)
+{
+    for (int i = 0; i < 2; i++) {
+        if (!idx->batch_session[i]) {
+            int rc = snapb200_session_create(idx, CHUNK, SNAPB200_MAX_READ_LENGTH, &idx->batch_session[i]);
+            if (rc) return rc;
+        }
+        s[i] = idx->batch_session[i];
+    }
+    return 0;
+}
+
+static int single_batch_impl(snapb200_index *idx, const snapb200_single_params *params, const snapb200_read_batch *reads,
+                             snapb200_single_result *results, int32_t *hit_counts, uint32_t *hit_locations, uint8_t *hit_rcs,
+                             int32_t *hit_scores)
+{
+    if (!idx || !params || !reads || (reads->n && !results)) return set_error(SNAPB200_ERR_ARG, "null argument");
+    uint32_t m;
+    int rc = validate_batch(reads, &m);
+    if (rc) return rc;
+    snapb200_session *s[2];
+    if ((rc = get_batch_sessions(idx, s))) return rc;
+    const uint32_t n = reads->n;
+    const uint32_t mh = params->max_hits_to_get;
+    std::vector<uint32_t> off_store[2];
+    // upload chunk c+1 while chunk c computes: uploads are asynchronous on the other session's stream
+    uint32_t n_chunks = (n + CHUNK - 1) / CHUNK;
+    if (n_chunks) {
+        snapb200_read_batch sb = sub_batch(reads, 0, std::min(n, CHUNK), off_store[0]);
+        if ((rc = snapb200_session_upload(s[0], 0, &sb))) return rc;
+    }
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
+        snapb200_session *cur = s[c & 1];
+        if (c + 1 < n_chunks) {
+            const uint32_t lo2 = hi, hi2 = std::min(n, lo2 + CHUNK);
+            snapb200_read_batch sb = sub_batch(reads, lo2, hi2, off_store[(c + 1) & 1]);
+            if ((rc = snapb200_session_upload(s[(c + 1) & 1], 0, &sb))) return rc;
+        }
+        if ((rc = snapb200_session_run_single(cur, params))) return rc;
+        if ((rc = snapb200_session_download_single(cur, results + lo))) return rc;
+        if (mh) {
+            const uint32_t k = hi - lo;
+            CUDA_TRY(cudaMemcpy(hit_counts + lo, cur->mh_counts.p, (size_t)k * 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hit_locations + (size_t)lo * mh, cur->mh_locs.p, (size_t)k * mh * 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hit_rcs + (size_t)lo * mh, cur->mh_rcs.p, (size_t)k * mh, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hit_scores + (size_t)lo * mh, cur->mh_scores.p, (size_t)k * mh * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
+}
+
+extern "C" int snapb200_single_batch(snapb200_index *idx, const snapb200_single_params *params, const snapb200_read_batch *reads,
+                                     snapb200_single_result *results)
+{
+    if (!params) return set_error(SNAPB200_ERR_ARG, "null params");
+    snapb200_single_params p = *params;
+    p.max_hits_to_get = 0;
+    return single_batch_impl(idx, &p, reads, results, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int snapb200_single_multihit_batch(snapb200_index *idx, const snapb200_single_params *params,
+                                              const snapb200_read_batch *reads, snapb200_single_result *results,
+                                              int32_t *hit_counts, uint32_t *hit_locations, uint8_t *hit_rcs, int32_t *hit_scores)
+{
+    if (!params) return set_error(SNAPB200_ERR_ARG, "null params");
+    if (params->max_hits_to_get && (!hit_counts || !hit_locations || !hit_rcs || !hit_scores)) return set_error(SNAPB200_ERR_ARG, "null multi-hit output");
+    return single_batch_impl(idx, params, reads, results, hit_counts, hit_locations, hit_rcs, hit_scores);
+}
+
+extern "C" int snapb200_paired_batch(snapb200_index *idx, const snapb200_paired_params *params, const snapb200_read_batch *reads0,
+                                     const snapb200_read_batch *reads1, snapb200_paired_result *results)
+{
+    if (!idx || !params || !reads0 || !reads1 || (reads0->n && !results)) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (reads0->n != reads1->n) return set_error(SNAPB200_ERR_ARG, "mate batches differ in size");
+    uint32_t m0, m1;
+    int rc;
+    if ((rc = validate_batch(reads0, &m0)) || (rc = validate_batch(reads1, &m1))) return rc;
+    snapb200_session *s[2];
+    if ((rc = get_batch_sessions(idx, s))) return rc;
+    const uint32_t n = reads0->n;
+    std::vector<uint32_t> off_store[2][2];
+    uint32_t n_chunks = (n + CHUNK - 1) / CHUNK;
+    auto up = [&](uint32_t c) -> int {
+        const uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
+        snapb200_read_batch a = sub_batch(reads0, lo, hi, off_store[c & 1][0]);
+        snapb200_read_batch b = sub_batch(reads1, lo, hi, off_store[c & 1][1]);
+        int r = snapb200_session_upload(s[c & 1], 0, &a);
+        if (!r) r = snapb200_session_upload(s[c & 1], 1, &b);
+        return r;
+    };
+    if (n_chunks && (rc = up(0))) return rc;
+    int limit_rc = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t lo = c * CHUNK;
+        snapb200_session *cur = s[c & 1];
+        if (c + 1 < n_chunks && (rc = up(c + 1))) return rc;
+        if ((rc = snapb200_session_run_paired(cur, params))) return rc;
+        rc = snapb200_session_download_paired(cur, results + lo);
+        if (rc == SNAPB200_ERR_LIMIT) limit_rc = rc; else if (rc) return rc;
+    }
+    return limit_rc;
+}
+
+// ---- CIGAR -----------------------------------------------------------------------------------------------------
+extern "C" int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_batch *reads, const uint32_t *locations,
+                                    const uint8_t *directions, int use_m, char *cigars, uint32_t cigar_stride, int32_t *edit_distance)
+{
+    if (!idx || !reads || (reads->n && (!locations || !directions || !cigars || !edit_distance))) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (cigar_stride < 2) return set_error(SNAPB200_ERR_ARG, "cigar_stride too small");
+    uint32_t m;
+    int rc = validate_batch(reads, &m);
+    if (rc) return rc;
+    const uint32_t n = reads->n;
+    if (!n) return 0;
+    snapb200_session *s[2];
+    if ((rc = get_batch_sessions(idx, s))) return rc;
+    snapb200_session *ss = s[0];
+    if ((rc = snapb200_session_upload(ss, 0, reads))) return rc;
+    DevBuf d_loc, d_dir, d_cig, d_ed;
+    do {
+        if ((rc = d_loc.ensure((size_t)n * 4)) || (rc = d_dir.ensure(n)) || (rc = d_cig.ensure((size_t)n * cigar_stride)) || (rc = d_ed.ensure((size_t)n * 4))) break;
+        cudaMemcpyAsync(d_loc.p, locations, (size_t)n * 4, cudaMemcpyHostToDevice, ss->stream);
+        cudaMemcpyAsync(d_dir.p, directions, n, cudaMemcpyHostToDevice, ss->stream);
+        CigarArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ix = idx->dev; a.b = dev_batch(ss, 0); a.locations = d_loc.as<uint32_t>(); a.directions = d_dir.as<uint8_t>();
+        a.use_m = use_m; a.cigars = d_cig.as<char>(); a.stride = cigar_stride; a.edit_distance = d_ed.as<int32_t>();
+        a.rl = std::max(32u, (m + 15) & ~15u); a.ctr = ss->counters.as<Counters>();
+        if ((rc = reset_work(ss))) break;
+        size_t smem = cigar_warp_shared(a.rl) * WARPS_PER_CTA;
+        int per_sm;
+        int grid = grid_for(cigar_kernel, smem, idx->sm_count, &per_sm);
+        cigar_kernel<<<grid, CTA_THREADS, smem, ss->stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "cigar_kernel launch: %s", cudaGetErrorString(e)); break; }
+        ss->total_launches++;
+        cudaMemcpyAsync(cigars, d_cig.p, (size_t)n * cigar_stride, cudaMemcpyDeviceToHost, ss->stream);
+        cudaMemcpyAsync(edit_distance, d_ed.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ss->stream);
+        e = cudaStreamSynchronize(ss->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "cigar_kernel: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    d_loc.release(); d_dir.release(); d_cig.release(); d_ed.release();
+    return rc;
+}
+
+// ---- building blocks --------------------------------------------------------------------------------------------
+struct TableOnlyIndex {  // probability tables on a device, for the explicit-string LV entry points
+    int device = -1;
+    snapb200_index *x = nullptr;
+};
+static TableOnlyIndex g_tables[16];
+
+static int tables_for(int device, snapb200_index **out)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(SNAPB200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev || device >= 16) return set_error(SNAPB200_ERR_ARG, "device %d out of range", device);
+    if (!g_tables[device].x) {
+        CUDA_TRY(cudaSetDevice(device));
+        snapb200_index *x = new snapb200_index();
+        x->device = device;
+        memset(&x->dev, 0, sizeof(x->dev));
+        memset(&x->info, 0, sizeof(x->info));
+        x->dev.seed_len = 20;
+        int rc = finish_index(x);
+        if (rc) { snapb200_index_close(x); return rc; }
+        g_tables[device].x = x;
+    }
+    *out = g_tables[device].x;
+    CUDA_TRY(cudaSetDevice(device));
+    return 0;
+}
+
+static int lv_common(int device, int dir, uint32_t n, const uint32_t *text_offsets, const uint8_t *texts, const uint32_t *pattern_offsets,
+                     const uint8_t *patterns, const uint8_t *quals, const int32_t *k, int32_t *score, double *prob, int32_t *indel,
+                     int use_m, char *cigars, uint32_t stride)
+{
+    snapb200_index *x;
+    int rc = tables_for(device, &x);
+    if (rc) return rc;
+    if (!n) return 0;
+    if (!text_offsets || !pattern_offsets || !texts || !patterns || !k || !score) return set_error(SNAPB200_ERR_ARG, "null argument");
+    uint32_t max_t = 0, max_p = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        max_t = std::max(max_t, text_offsets[i + 1] - text_offsets[i]);
+        max_p = std::max(max_p, pattern_offsets[i + 1] - pattern_offsets[i]);
+    }
+    if (max_p > SNAPB200_MAX_READ_LENGTH || max_t > SNAPB200_MAX_READ_LENGTH + 64) return set_error(SNAPB200_ERR_ARG, "string too long for the LV test entry point");
+    const size_t tb = text_offsets[n], pb = pattern_offsets[n];
+    DevBuf d_to, d_po, d_t, d_p, d_q, d_k, d_s, d_pr, d_in, d_c, d_ctr;
+    cudaStream_t st = x->stream;
+    do {
+        if ((rc = d_to.ensure((size_t)(n + 1) * 4)) || (rc = d_po.ensure((size_t)(n + 1) * 4)) || (rc = d_t.ensure(tb + 16)) || (rc = d_p.ensure(pb + 16)) ||
+            (rc = d_q.ensure(pb + 16)) || (rc = d_k.ensure((size_t)n * 4)) || (rc = d_s.ensure((size_t)n * 4)) || (rc = d_pr.ensure((size_t)n * 8)) ||
+            (rc = d_in.ensure((size_t)n * 4)) || (rc = d_ctr.ensure(sizeof(Counters)))) break;
+        if (cigars && (rc = d_c.ensure((size_t)n * stride))) break;
+        cudaMemcpyAsync(d_to.p, text_offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_po.p, pattern_offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st);
+        if (tb) cudaMemcpyAsync(d_t.p, texts, tb, cudaMemcpyHostToDevice, st);
+        if (pb) cudaMemcpyAsync(d_p.p, patterns, pb, cudaMemcpyHostToDevice, st);
+        if (pb && quals) cudaMemcpyAsync(d_q.p, quals, pb, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_k.p, k, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(d_ctr.p, 0, sizeof(Counters), st);
+        LvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ix = x->dev; a.dir = dir; a.n = n; a.text_off = d_to.as<uint32_t>(); a.pat_off = d_po.as<uint32_t>();
+        a.texts = d_t.as<uint8_t>(); a.pats = d_p.as<uint8_t>(); a.quals = quals ? d_q.as<uint8_t>() : nullptr; a.k = d_k.as<int32_t>();
+        a.score = d_s.as<int32_t>(); a.indel = d_in.as<int32_t>(); a.prob = d_pr.as<double>();
+        a.use_m = use_m; a.cigars = cigars ? d_c.as<char>() : nullptr; a.stride = stride;
+        a.max_text = std::max(16u, max_t); a.max_pat = std::max(16u, max_p); a.ctr = d_ctr.as<Counters>();
+        size_t smem = lvtest_warp_shared(a.max_text, a.max_pat) * WARPS_PER_CTA;
+        int per_sm;
+        int grid = grid_for(lv_kernel, smem, x->sm_count, &per_sm);
+        lv_kernel<<<grid, CTA_THREADS, smem, st>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "lv_kernel launch: %s", cudaGetErrorString(e)); break; }
+        cudaMemcpyAsync(score, d_s.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (prob) cudaMemcpyAsync(prob, d_pr.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+        if (indel) cudaMemcpyAsync(indel, d_in.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (cigars) cudaMemcpyAsync(cigars, d_c.p, (size_t)n * stride, cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "lv_kernel: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    DevBuf *all[] = {&d_to, &d_po, &d_t, &d_p, &d_q, &d_k, &d_s, &d_pr, &d_in, &d_c, &d_ctr};
+    for (DevBuf *b : all) b->release();
+    return rc;
+}
+
+extern "C" int snapb200_lv_batch(int device, int text_direction, uint32_t n, const uint32_t *text_offsets, const uint8_t *texts,
+                                 const uint32_t *pattern_offsets, const uint8_t *patterns, const uint8_t *quals, const int32_t *k,
+                                 int32_t *score, double *match_probability, int32_t *net_indel)
+{
+    if (text_direction != 1 && text_direction != -1) return set_error(SNAPB200_ERR_ARG, "text_direction must be +1 or -1");
+    return lv_common(device, text_direction, n, text_offsets, texts, pattern_offsets, patterns, quals, k, score, match_probability, net_indel, 0,
+                     nullptr, 0);
+}
+
+extern "C" int snapb200_lv_cigar_batch(int device, uint32_t n, const uint32_t *text_offsets, const uint8_t *texts,
+                                       const uint32_t *pattern_offsets, const uint8_t *patterns, const int32_t *k, int use_m, char *cigars,
+                                       uint32_t cigar_stride, int32_t *edit_distance)
+{
+    if (n && (!cigars || cigar_stride < 2)) return set_error(SNAPB200_ERR_ARG, "bad cigar buffer");
+    return lv_common(device, 1, n, text_offsets, texts, pattern_offsets, patterns, nullptr, k, edit_distance, nullptr, nullptr, use_m, cigars,
+                     cigar_stride);
+}
+
+extern "C" int snapb200_lookup_seed_batch(snapb200_index *idx, uint32_t n, const uint8_t *seeds, uint32_t max_out, uint32_t *n_hits,
+                                          uint32_t *hits)
+{
+    if (!idx || (n && (!seeds || !n_hits || (max_out && !hits)))) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (!n) return 0;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    DevBuf d_s, d_n, d_h;
+    int rc;
+    const size_t L = idx->dev.seed_len;
+    do {
+        if ((rc = d_s.ensure(n * L)) || (rc = d_n.ensure((size_t)n * 8)) || (rc = d_h.ensure((size_t)n * 2 * std::max(max_out, 1u) * 4))) break;
+        cudaMemcpyAsync(d_s.p, seeds, n * L, cudaMemcpyHostToDevice, idx->stream);
+        cudaMemsetAsync(d_h.p, 0, (size_t)n * 2 * std::max(max_out, 1u) * 4, idx->stream);
+        lookup_kernel<<<(n + 127) / 128, 128, 0, idx->stream>>>(idx->dev, n, d_s.as<uint8_t>(), max_out, d_n.as<uint32_t>(), d_h.as<uint32_t>());
+        cudaMemcpyAsync(n_hits, d_n.p, (size_t)n * 8, cudaMemcpyDeviceToHost, idx->stream);
+        if (max_out) cudaMemcpyAsync(hits, d_h.p, (size_t)n * 2 * max_out * 4, cudaMemcpyDeviceToHost, idx->stream);
+        cudaError_t e = cudaStreamSynchronize(idx->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "lookup_kernel: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    d_s.release(); d_n.release(); d_h.release();
+    return rc;
+}
+
+extern "C" int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, const double *p_best, const int32_t *score,
+                                   const int32_t *popular_seeds_skipped, int32_t *mapq)
+{
+    snapb200_index *x;
+    int rc = tables_for(device, &x);
+    if (rc) return rc;
+    if (!n) return 0;
+    if (!p_all || !p_best || !score || !popular_seeds_skipped || !mapq) return set_error(SNAPB200_ERR_ARG, "null argument");
+    DevBuf a, b, c, d, o, f;
+    std::vector<uint8_t> flags(n);
+    do {
+        if ((rc = a.ensure((size_t)n * 8)) || (rc = b.ensure((size_t)n * 8)) || (rc = c.ensure((size_t)n * 4)) || (rc = d.ensure((size_t)n * 4)) ||
+            (rc = o.ensure((size_t)n * 4)) || (rc = f.ensure(n))) break;
+        cudaMemcpyAsync(a.p, p_all, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream);
+        cudaMemcpyAsync(b.p, p_best, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream);
+        cudaMemcpyAsync(c.p, score, (size_t)n * 4, cudaMemcpyHostToDevice, x->stream);
+        cudaMemcpyAsync(d.p, popular_seeds_skipped, (size_t)n * 4, cudaMemcpyHostToDevice, x->stream);
+        mapq_kernel<<<(n + 255) / 256, 256, 0, x->stream>>>(n, a.as<double>(), b.as<double>(), c.as<int32_t>(), d.as<int32_t>(), o.as<int32_t>(), f.as<uint8_t>());
+        cudaMemcpyAsync(mapq, o.p, (size_t)n * 4, cudaMemcpyDeviceToHost, x->stream);
+        cudaMemcpyAsync(flags.data(), f.p, n, cudaMemcpyDeviceToHost, x->stream);
+        cudaError_t e = cudaStreamSynchronize(x->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "mapq_kernel: %s", cudaGetErrorString(e)); break; }
+        for (uint32_t i = 0; i < n; i++) if (flags[i]) mapq[i] = compute_mapq_host(p_all[i], p_best[i], score[i], popular_seeds_skipped[i]);
+    } while (0);
+    DevBuf *all[] = {&a, &b, &c, &d, &o, &f};
+    for (DevBuf *q : all) q->release();
+    return rc;
+}
+
+// ---- statistics -----------------------------------------------------------------------------------------------------
+extern "C" int snapb200_stats_get(snapb200_index *idx, snapb200_stats *out)
+{
+    if (!idx || !out) return set_error(SNAPB200_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long w[SNAPB200_STATS_WORDS];
+    CUDA_TRY(cudaMemcpy(w, idx->stats, sizeof(w), cudaMemcpyDeviceToHost));
+    int64_t *o = (int64_t *)out;
+    for (int i = 0; i < SNAPB200_STATS_WORDS; i++) o[i] = (int64_t)w[i];
+    out->useful_reads = out->total_reads - out->n_reads_ignored_ns;
+    out->lv_calls = out->n_locations_scored;
+    return 0;
+}
+
+extern "C" int snapb200_stats_reset(snapb200_index *idx)
+{
+    if (!idx) return set_error(SNAPB200_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    CUDA_TRY(cudaMemset(idx->stats, 0, SNAPB200_STATS_WORDS * 8));
+    return 0;
+}

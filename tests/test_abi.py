@@ -1,0 +1,79 @@
+"""The C-ABI library loads and exports every symbol include/snapb200.h declares (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "snapb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(snapb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for s in ("snapb200_index_open", "snapb200_single_batch", "snapb200_single_multihit_batch", "snapb200_paired_batch",
+              "snapb200_cigar_batch", "snapb200_stats_get", "snapb200_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import snap_rnaseq_b200 as S
+    from snap_rnaseq_b200 import build as B
+    B.build()
+    lib = C.CDLL(S.SO_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/snapb200.h but not exported"
+    lib.snapb200_abi_version.restype = C.c_int
+    assert lib.snapb200_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof of every struct, as gcc sees include/snapb200.h, against the ctypes/numpy mirrors."""
+    import subprocess
+
+    from snap_rnaseq_b200 import _abi as A
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "snapb200.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(snapb200_single_params), sizeof(snapb200_paired_params),'
+        ' sizeof(snapb200_single_result), sizeof(snapb200_paired_result), sizeof(snapb200_index_info), sizeof(snapb200_stats),'
+        ' offsetof(snapb200_single_result,p_all), offsetof(snapb200_paired_result,p_all), offsetof(snapb200_paired_result,n_lv_calls));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    assert got[0] == C.sizeof(A.SingleParams)
+    assert got[1] == C.sizeof(A.PairedParams)
+    assert got[2] == A.SINGLE_RESULT.itemsize
+    assert got[3] == A.PAIRED_RESULT.itemsize
+    assert got[4] == C.sizeof(A.IndexInfo)
+    assert got[5] == A.STATS_WORDS * 8
+    assert got[6] == A.SINGLE_RESULT.fields["p_all"][1]
+    assert got[7] == A.PAIRED_RESULT.fields["p_all"][1]
+    assert got[8] == A.PAIRED_RESULT.fields["n_lv_calls"][1]
+
+
+def test_no_gpu_means_failure_not_fallback():
+    """Without a CUDA device every compute entry point must fail loudly (there is no CPU path)."""
+    import snap_rnaseq_b200 as S
+    L = S.lib()
+    if L.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        L.lv(1, [b"abc"], [b"abc"], None, [2])
+    with pytest.raises(RuntimeError):
+        L.load_index("/nonexistent")
+
+
+def test_product_does_not_reference_the_oracle():
+    """The package must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "snap_rnaseq_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "liboracle" not in txt and "libsnapref" not in txt and "from oracle" not in txt and "import oracle" not in txt, f

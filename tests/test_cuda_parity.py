@@ -1,0 +1,193 @@
+"""Parity tests proper: the CUDA library, through its C ABI, against the reference's KATs, the committed golden
+outputs of the compiled reference, and the oracle (port, and the reference itself when oracle/_ref is present) on
+fresh seeded inputs.  Everything here needs a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as P
+from conftest import assert_records_equal
+from snap_rnaseq_b200 import _abi as A
+from snap_rnaseq_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle(cuda, small_index_dir):
+    h = cuda.load_index(small_index_dir)
+    yield h
+    cuda.close_index(h)
+
+
+def test_score_kats(cuda):
+    P.check_score_kats(cuda)
+
+
+def test_cigar_kats(cuda):
+    P.check_cigar_kats(cuda)
+
+
+def test_golden_lv(cuda, golden):
+    P.check_golden_lv(cuda, golden)
+
+
+def test_golden_mapq(cuda, golden):
+    P.check_golden_mapq(cuda, golden)
+
+
+def test_golden_lookup(cuda, handle, golden):
+    P.check_golden_lookup(cuda, handle, golden)
+
+
+def test_golden_single(cuda, handle, golden):
+    P.check_golden_single(cuda, handle, golden)
+
+
+def test_golden_multihit(cuda, handle, golden):
+    P.check_golden_multihit(cuda, handle, golden)
+
+
+def test_golden_paired(cuda, handle, golden):
+    P.check_golden_paired(cuda, handle, golden)
+
+
+def test_golden_cigar(cuda, handle, golden):
+    P.check_golden_cigar(cuda, handle, golden)
+
+
+def test_empty(cuda, handle):
+    P.check_empty(cuda, handle)
+
+
+def test_index_info(cuda, handle, port, small_index_dir):
+    a, b = cuda.index_info(handle), port.index_info(port.load_index(small_index_dir))
+    for f in ("n_bases", "n_pieces", "seed_len", "n_hash_tables", "overflow_table_size", "chromosome_padding", "hash_table_entries"):
+        assert getattr(a, f) == getattr(b, f), f
+    assert a.device_bytes > a.n_bases
+
+
+# ---- differential tests on fresh inputs (port always; compiled reference too when it is on the box) ----
+def _checkers(port, request):
+    out = [("port", port)]
+    from oracle import oracle as O
+    if O.have_ref():
+        out.append(("ref", O.ref()))
+    return out
+
+
+@pytest.mark.parametrize("rlen,err,max_k,seed", [(100, 0.02, 15, 31), (150, 0.01, 15, 32), (250, 0.04, 20, 33), (62, 0.05, 15, 34)])
+def test_fresh_paired_and_single(cuda, handle, port, small_index_dir, request, rlen, err, max_k, seed):
+    from tests_genome import small_genome
+    contigs = small_genome()
+    sim = synth.simulate(contigs, 3000, rlen, paired=True, err=err, seed=seed, junk_frac=0.03, n_rate=0.02,
+                         frag=(max(250, rlen + 20), max(450, rlen + 200)))
+    b0, b1 = sim["batches"]
+    pp = A.paired_defaults(max_k=max_k)
+    ps = A.single_defaults(max_k=min(max_k, 20))
+    got_p = cuda.paired(handle, pp, b0, b1)
+    got_s = cuda.single(handle, ps, b1)
+    for name, chk in _checkers(port, request):
+        hc = chk.load_index(small_index_dir)
+        assert_records_equal(chk.paired(hc, pp, b0, b1), got_p, what=f"paired vs {name}")
+        assert_records_equal(chk.single(hc, ps, b1), got_s, what=f"single vs {name}")
+        cg, ed = cuda.cigar(handle, b1, got_s["location"], got_s["direction"], False)
+        cw, ew = chk.cigar(hc, b1, got_s["location"], got_s["direction"], False)
+        assert cg == cw and np.array_equal(ed, ew)
+
+
+def test_parameter_variants(cuda, handle, port, small_index_dir):
+    """-x, -f, seed coverage instead of seed count, small -h (popular seeds skipped), -fs."""
+    from tests_genome import small_genome
+    contigs = small_genome()
+    sim = synth.simulate(contigs, 2000, 100, paired=True, err=0.03, seed=41, junk_frac=0.05)
+    b0, b1 = sim["batches"]
+    hp = port.load_index(small_index_dir)
+    for kw in (dict(explore_popular_seeds=1, max_hits=4), dict(stop_on_first_hit=1), dict(num_seeds=0, seed_coverage=2.0),
+               dict(max_hits=2), dict(max_k=8, extra_search_depth=1), dict(num_seeds=60)):
+        ps = A.single_defaults(**kw)
+        assert_records_equal(port.single(hp, ps, b0), cuda.single(handle, ps, b0), what=f"single {kw}")
+    for kw in (dict(force_spacing=1), dict(min_spacing=0, max_spacing=300), dict(max_big_hits=3), dict(num_seeds=0, seed_coverage=1.5),
+               dict(max_hits=2), dict(num_seeds=25), dict(max_candidate_pool_size=64)):
+        pp = A.paired_defaults(**kw)
+        try:
+            want = port.paired(hp, pp, b0, b1)
+        except RuntimeError:
+            want = None  # the reference would exit: pool exhausted
+        if want is None:
+            with pytest.raises(RuntimeError):
+                cuda.paired(handle, pp, b0, b1)
+        else:
+            assert_records_equal(want, cuda.paired(handle, pp, b0, b1), what=f"paired {kw}")
+
+
+def test_ragged_and_edge_reads(cuda, handle, port, small_index_dir):
+    """Ragged lengths incl. empty, < seedLen, < 50, all-N, and reads at the very start/end of contigs."""
+    from tests_genome import small_genome
+    contigs = small_genome()
+    c1 = contigs["chr1"].tobytes().decode()
+    c3 = contigs["chr3"].tobytes().decode()
+    seqs = ["", "A", c1[:19], c1[:20], c1[:49], c1[:50], c1[:100], c1[-100:], c3[-75:], c3[-60:] + "ACGTACGTAC", "N" * 80,
+            c1[5:65] + "N" * 10 + c1[75:125], c1[200:300][::-1], c1[1000:1100], c1[1000:1040] + c1[1043:1103], c1[2000:2050] + "GG" + c1[2050:2098]]
+    b0 = A.Batch.from_strings(seqs)
+    b1 = A.Batch.from_strings(list(reversed(seqs)))
+    hp = port.load_index(small_index_dir)
+    assert_records_equal(port.single(hp, A.single_defaults(), b0), cuda.single(handle, A.single_defaults(), b0), what="ragged single")
+    assert_records_equal(port.paired(hp, A.paired_defaults(), b0, b1), cuda.paired(handle, A.paired_defaults(), b0, b1), what="ragged paired")
+
+
+def test_scratch_tier_overflow_is_invisible(cuda, handle, port, small_index_dir):
+    """Reads drawn from the repeat families overflow the small scratch tier and are rerun in the large one; results
+    must not depend on that."""
+    from tests_genome import small_genome
+    contigs = small_genome()
+    sim = synth.simulate(contigs, 1500, 100, paired=True, err=0.01, seed=77)
+    b0, b1 = sim["batches"]
+    hp = port.load_index(small_index_dir)
+    ps = A.single_defaults(max_hits=16000, num_seeds=8, max_k=15)
+    assert_records_equal(port.single(hp, ps, b0), cuda.single(handle, ps, b0), what="large maxHits single")
+
+
+def test_stats_and_session(cuda, handle, golden):
+    import snap_rnaseq_b200 as S
+    from conftest import batch_from
+    b0, b1 = batch_from(golden, "pair0"), batch_from(golden, "pair1")
+    cuda.stats_reset(handle)
+    sess = S.Session(cuda, handle, b0.n, 128)
+    sess.upload(0, b0)
+    sess.upload(1, b1)
+    sess.run_paired(A.paired_defaults())
+    out = np.zeros(b0.n, A.PAIRED_RESULT)
+    sess.download_paired(out)
+    assert_records_equal(golden["paired_res"], out, what="session paired")
+    ms, launches, total = sess.last_run()
+    assert ms > 0 and launches >= 2 and total >= launches
+    w = cuda.stats(handle)
+    assert w[0] == 2 * b0.n                      # total_reads
+    assert w[2] + w[3] + w[4] == 2 * b0.n        # single + multi + not found
+    st = golden["paired_res"]["status"]
+    assert w[2] == int((st == 1).sum()) and w[3] == int((st == 2).sum()) and w[4] == int((st == 0).sum())
+    sess.close()
+
+
+def test_large_batch_properties(cuda, handle):
+    """At a size the oracle would take too long for: chunking/order independence and determinism."""
+    from tests_genome import small_genome
+    contigs = small_genome()
+    n = 300_000  # > one 262144-read chunk: exercises the double-buffered pipeline
+    sim = synth.simulate(contigs, n, 100, paired=True, err=0.02, seed=5)
+    b0, b1 = sim["batches"]
+    pp = A.paired_defaults()
+    full = cuda.paired(handle, pp, b0, b1)
+    again = cuda.paired(handle, pp, b0, b1)
+    assert_records_equal(full, again, what="determinism")
+    lo, hi = 262000, 262400  # straddles the chunk boundary
+    part = cuda.paired(handle, pp, b0.slice(lo, hi), b1.slice(lo, hi))
+    assert_records_equal(full[lo:hi], part, what="chunk independence")
+    # swapping the mates swaps the per-end fields
+    sw = cuda.paired(handle, pp, b1.slice(0, 2000), b0.slice(0, 2000))
+    for f in ("location", "score", "mapq", "status", "direction"):
+        assert np.array_equal(sw[f][:, ::-1], full[f][:2000]), f
+    ok = full["status"][:, 0] != 0
+    assert ok.mean() > 0.9

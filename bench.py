@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- reads aligned per second on the paired-end hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo: sm_100a kernels behind the C ABI
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
+
+Workload (BASELINE.json configs[1], "C2"): 100 Mbp repeat-injected synthetic genome (4 x 25 Mbp, seed 20/21),
+index seed length 20, WGsim-model 2x100 bp FR pairs (2 % error, 15 % of mutations indels, fragment 250-450),
+`snap-rna paired` default options (-d 15 -n 8 -h 16000 -H 16000 -s 50 1000).  One step = one pass of
+ChimericPairedEndAligner::align over one batch of pairs per GPU.  The index and genome are replicated per GPU;
+reads are sharded (each rank aligns its own batch, no collective on the data path) => weak scaling.  NCCL is used
+only for the end-of-run AlignerStats all-reduce and the timing reduction.
+
+JSON keys: see the task contract.  `value` times the kernels with the batch already resident in HBM; `e2e` times
+snapb200_paired_batch (the C-ABI call the reference's AlignerExtension would make) from pinned host buffers,
+host<->device copies included; `roofline` is the dominant kernel (paired_kernel) against the measured HBM copy
+peak; `cpu_baseline` is the compiled reference (oracle/_ref) on the host cores over a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads_aligned_per_sec"
+UNIT = "reads/s"
+GENOME_CONTIGS = [25_000_000] * 4
+READ_LEN = 100
+PAIRS_PER_STEP = 1_000_000          # per GPU
+CPU_SAMPLE_PAIRS = 200_000
+
+
+def workload_config(n_gpus, pairs):
+    return {"workload": "C2: snap paired, 100 Mbp repeat-injected synthetic genome (4x25 Mbp), seed 20, 2x100bp WGsim pairs e=2%",
+            "pairs_per_step_per_gpu": pairs, "read_len": READ_LEN, "options": "-d 15 -n 8 -h 16000 -H 16000 -s 50 1000 -D 2",
+            "parallelism": f"reads sharded over {n_gpus} GPU(s), index replicated", "l2": "inputs larger than L2 (1.76 GB index + genome, 0.4 GB batch)"}
+
+
+def make_genome():
+    from snap_rnaseq_b200 import synth
+    contigs = synth.random_contigs(GENOME_CONTIGS, seed=20)
+    synth.inject_repeats(contigs, frac=0.05, seed=21)
+    return contigs
+
+
+def make_pairs(contigs, n, seed):
+    from snap_rnaseq_b200 import synth
+    sim = synth.simulate(contigs, n, READ_LEN, paired=True, err=0.02, indel_frac=0.15, seed=seed)
+    return sim["batches"]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def pinned_batch(batch):
+    """Copy a Batch into pinned host memory (torch) and return (torch tensors, raw pointers)."""
+    import torch
+    t = {k: torch.from_numpy(getattr(batch, k).copy()).pin_memory() for k in ("offsets", "bases", "quals")}
+    return t
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import snap_rnaseq_b200 as S
+    from snap_rnaseq_b200 import _abi as A
+    from snap_rnaseq_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this library has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = S.lib(local)
+    pairs = args.pairs
+    contigs = make_genome()
+    bases, offs = synth.snap_layout(contigs, 500)
+    t0 = time.time()
+    h = L.build_index(bases, offs, list(contigs), seed_len=20, device=local)
+    t_index = time.time() - t0
+    b0, b1 = make_pairs(contigs, pairs, seed=1000 + rank)
+    params = A.paired_defaults()
+
+    # ---- kernels on an HBM-resident batch (value) ----
+    sess = S.Session(L, h, pairs, 128)
+    sess.upload(0, b0)
+    sess.upload(1, b1)
+    sess.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sess.run_paired(params)
+    L.stats_reset(h)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches = 0
+    main_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sess.run_paired(params)          # returns after its stream has drained (counters are read back)
+        launches += sess.last_run()[1]
+        main_ms.append(sess.main_kernel_ms())
+    sess.sync()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.finish()
+    stats = L.stats(h)
+    out = np.zeros(pairs, A.PAIRED_RESULT)
+    sess.download_paired(out)
+
+    # ---- end to end through the C ABI from pinned host memory (e2e) ----
+    pin0, pin1 = pinned_batch(b0), pinned_batch(b1)
+    res_pin = torch.empty(pairs * A.PAIRED_RESULT.itemsize, dtype=torch.uint8).pin_memory()
+
+    def rb(pin, n):
+        return A.ReadBatch(n, C.cast(pin["offsets"].data_ptr(), C.POINTER(C.c_uint32)), C.cast(pin["bases"].data_ptr(), C.POINTER(C.c_uint8)),
+                           C.cast(pin["quals"].data_ptr(), C.POINTER(C.c_uint8)))
+
+    r0, r1 = rb(pin0, pairs), rb(pin1, pairs)
+
+    def e2e_step():
+        rc = L.lib.snapb200_paired_batch(h, C.byref(params), C.byref(r0), C.byref(r1), C.c_void_p(res_pin.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(L.lib.snapb200_last_error())
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt_e2e = time.perf_counter() - t1
+    barrier()
+    e2e_res = np.frombuffer(res_pin.numpy(), dtype=A.PAIRED_RESULT)
+    same = all(np.array_equal(e2e_res[f], out[f]) for f in ("location", "mapq", "status", "score", "direction"))
+
+    # ---- reductions: max time over ranks, summed stats (the AlignerStats all-reduce over NCCL) ----
+    tv = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+    sv = torch.from_numpy(stats.astype(np.int64)).cuda()
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sv, op=dist.ReduceOp.SUM)
+    dt_max, dt_e2e_max = [float(x) for x in tv.cpu()]
+    tot = sv.cpu().numpy()
+
+    if rank == 0:
+        reads_per_step = 2 * pairs * world
+        value = reads_per_step * args.steps / dt_max
+        e2e_value = reads_per_step * e2e_steps / dt_e2e_max
+        h2d = int(b0.bases.size + b0.quals.size + b0.offsets.size * 4 + b1.bases.size + b1.quals.size + b1.offsets.size * 4)
+        d2h = int(pairs * A.PAIRED_RESULT.itemsize)
+        # algorithmic bytes of the dominant kernel per launch (counters are this rank's, per step)
+        steps = args.steps
+        per = lambda i: float(stats[i]) / steps
+        n_lv = float(out["n_lv_calls"].sum())
+        alg_bytes = 12.0 * per(12) + 4.0 * per(13) + n_lv * (READ_LEN + 31) + 2.0 * (2 * READ_LEN) * pairs + 56.0 * pairs
+        k_ms = float(np.mean(main_ms))
+        peak, peak_src = measured_peaks()
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/u32 integer + f64 probabilities", "data": "synthetic", "config": workload_config(world, pairs),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "matches_resident_run": bool(same)},
+            "roofline": {"bound": "hbm", "kernel": "paired_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "per_pair": {"table_probes": per(12) / pairs, "hit_words": per(13) / pairs, "lv_locations": n_lv / pairs,
+                                      "lookups": float(out["n_lookups"].mean())}},
+            "index_build_s": t_index,
+            "stats_allreduce": {"total_reads": int(tot[0]), "single_hits": int(tot[2]), "multi_hits": int(tot[3]), "not_found": int(tot[4]),
+                                "aligned_as_pairs": int(tot[6]), "locations_scored": int(tot[9]), "lookups": int(tot[8])},
+            "aligned_fraction": float((out["status"] != 0).mean()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(L, h, b0, b1, params, out)
+        print(json.dumps(line))
+    sess.close()
+    L.close_index(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(L, h, b0, b1, params, gpu_out):
+    """The compiled reference (oracle/_ref) on the host cores, over a bounded sample of the same batch.  The index
+    it loads is the device-built one written in the reference's file format (lookup-equivalent; tests check that)."""
+    import tempfile
+
+    from oracle import oracle as O
+    from snap_rnaseq_b200 import _abi as A
+    n = min(CPU_SAMPLE_PAIRS, b0.n)
+    s0, s1 = b0.slice(0, n), b1.slice(0, n)
+    cores = os.cpu_count() or 1
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as tmp:
+        d = os.path.join(tmp, "idx")
+        L.save_index(h, d)
+        if O.have_ref():
+            impl, kind = O.ref(threads=cores), "reference"
+        else:
+            impl, kind, cores = O.port(), "port", 1
+        hc = impl.load_index(d)
+        t0 = time.perf_counter()
+        res = impl.paired(hc, params, s0, s1)
+        dt = time.perf_counter() - t0
+    agree = all(np.array_equal(res[f], gpu_out[f][:n]) for f in ("location", "mapq", "status", "score", "direction"))
+    return {"value": 2 * n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {n} pairs of the rank-0 batch, {cores} threads, aligner calls only (no I/O)",
+            "bit_exact_vs_gpu_on_sample": bool(agree)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, built from /root/reference) on the host
+    cores: its own indexer, its own ChimericPairedEndAligner, all threads.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import tempfile
+
+    from oracle import oracle as O
+    from snap_rnaseq_b200 import _abi as A
+    from snap_rnaseq_b200 import synth
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cores = os.cpu_count() or 1
+    contigs = make_genome()
+    n = CPU_SAMPLE_PAIRS
+    b0, b1 = make_pairs(contigs, n, seed=1000)
+    params = A.paired_defaults()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as tmp:
+        if O.have_ref():
+            fa = os.path.join(tmp, "g.fa")
+            synth.write_fasta(fa, contigs)
+            d = os.path.join(tmp, "idx")
+            O.ref_build_index(fa, d, seed_len=20, threads=cores)
+            impl, kind = O.ref(threads=cores), "reference"
+        else:
+            raise SystemExit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not present on this box"}))
+        hc = impl.load_index(d)
+        for _ in range(min(args.warmup, 1)):
+            impl.paired(hc, params, b0.slice(0, 20000), b1.slice(0, 20000))
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            impl.paired(hc, params, b0, b1)
+        dt = time.perf_counter() - t0
+    value = 2 * n * steps / dt
+    cfg = workload_config(world, n)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/u32 integer + f64 probabilities", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{n} pairs per step, {cores} threads, ChimericPairedEndAligner::align only (no I/O)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,18 @@ int snapb200_index_from_memory(int device, uint32_t seed_len, uint32_t chromosom
                                const uint32_t *piece_offsets, uint32_t n_pieces,
                                snapb200_index **out);
 
+/* Device-side index construction: replaces GenomeIndex::BuildIndexToDirectory (SNAPLib/GenomeIndex.cpp:348-720)
+ * with a sort-based build whose lookupSeed results are identical.  `bases` is the genome in the reference's
+ * in-memory layout (1 byte/base, `chromosome_padding` 'n' before every piece and after the last one,
+ * SNAPLib/FASTA.cpp:68-126); piece_names may be NULL.  slack: extra table capacity, reference default 0.3. */
+int snapb200_index_build(int device, const uint8_t *bases, uint32_t n_bases, const uint32_t *piece_offsets,
+                         const char *const *piece_names, uint32_t n_pieces, uint32_t seed_len,
+                         uint32_t chromosome_padding, double slack, snapb200_index **out);
+
+/* Writes the four files of the reference's index directory (formats: SNAPLib/GenomeIndex.cpp:646-710,
+ * SNAPLib/HashTable.cpp:181-215, SNAPLib/Genome.cpp:126-158) so the reference can load this index. */
+int snapb200_index_save(snapb200_index *idx, const char *dir);
+
 int snapb200_index_info_get(const snapb200_index *idx, snapb200_index_info *info);
 void snapb200_index_close(snapb200_index *idx);
 
@@ -238,15 +250,20 @@ int snapb200_session_sync(snapb200_session *s);
  * of launches since the session was created. */
 int snapb200_session_last_run(const snapb200_session *s, float *kernel_ms, uint32_t *launches,
                               uint64_t *total_launches);
+/* CUDA-event time (ms) of the dominant kernel of the last run alone: the first single_kernel / paired_kernel
+ * launch (small scratch tier, all items).  Used for the roofline figure. */
+int snapb200_session_main_kernel_ms(const snapb200_session *s, float *main_ms);
 
 /* ---- statistics (AlignerStats, SNAPLib/AlignerStats.h:45-60) ------------------------------------------ */
 
 typedef struct {
     int64_t total_reads, useful_reads, single_hits, multi_hits, not_found, errors, aligned_as_pairs, lv_calls;
     int64_t n_hash_table_lookups, n_locations_scored, n_hits_ignored_popularity, n_reads_ignored_ns;
+    int64_t n_table_probes;   /* 12-byte hash-table slots examined by lookupSeed (>= 1 per lookup)          */
+    int64_t n_hit_words_read; /* 4-byte hit-list words the aligners consumed (votes, binary-search probes) */
     int64_t mapq_histogram[71];
 } snapb200_stats;
-#define SNAPB200_STATS_WORDS (12 + 71)
+#define SNAPB200_STATS_WORDS (14 + 71)
 
 /* Accumulated over every batch run on this index handle since the last reset; a flat int64 vector so that
  * the multi-GPU host can sum it with one all-reduce (NCCL), as AlignerStats::add does per thread

@@ -48,6 +48,23 @@ class Snapb200(BatchLib):
             C.c_uint32(po.size), C.byref(h)), "index_from_memory")
         return h
 
+    def build_index(self, bases, piece_offsets, piece_names=None, seed_len=20, padding=500, slack=0.3, device=None):
+        """snapb200_index_build: sort-based index construction on the device (lookup-equivalent to the reference's)."""
+        h = C.c_void_p()
+        dev = self.device if device is None else device
+        bs = np.ascontiguousarray(bases, np.uint8)
+        po = np.ascontiguousarray(piece_offsets, np.uint32)
+        names = None
+        if piece_names is not None:
+            names = (C.c_char_p * len(piece_names))(*[n.encode() for n in piece_names])
+        self._check(self.lib.snapb200_index_build(
+            C.c_int(dev), bs.ctypes.data_as(C.c_void_p), C.c_uint32(bs.size), po.ctypes.data_as(C.c_void_p), names,
+            C.c_uint32(po.size), C.c_uint32(seed_len), C.c_uint32(padding), C.c_double(slack), C.byref(h)), "index_build")
+        return h
+
+    def save_index(self, h, directory):
+        self._check(self.lib.snapb200_index_save(h, str(directory).encode()), "index_save")
+
     def index_info(self, h):
         info = IndexInfo()
         self._check(self.lib.snapb200_index_info_get(h, C.byref(info)), "index_info_get")
@@ -111,6 +128,11 @@ class Session:
         self.lib._check(self.lib.lib.snapb200_session_last_run(self.h, C.byref(ms), C.byref(n), C.byref(tot)), "last_run")
         return ms.value, n.value, tot.value
 
+    def main_kernel_ms(self):
+        ms = C.c_float()
+        self.lib._check(self.lib.lib.snapb200_session_main_kernel_ms(self.h, C.byref(ms)), "main_kernel_ms")
+        return ms.value
+
     def close(self):
         if self.h:
             self.lib.lib.snapb200_session_destroy.restype = None
@@ -140,6 +162,16 @@ class GenomeIndex:
     @classmethod
     def loadFromDirectory(cls, directory, device=0):
         return cls(lib(device).load_index(directory, device), device)
+
+    @classmethod
+    def BuildIndex(cls, contigs, seedLen=20, chromosomePadding=500, slack=0.3, device=0):
+        """GenomeIndex::BuildIndexToDirectory (SNAPLib/GenomeIndex.cpp:348-720), on the device, from a dict of contigs."""
+        from .synth import snap_layout
+        bases, offs = snap_layout(contigs, chromosomePadding)
+        return cls(lib(device).build_index(bases, offs, list(contigs), seedLen, chromosomePadding, slack, device), device)
+
+    def saveToDirectory(self, directory):
+        lib(self.device).save_index(self.h, directory)
 
     def getSeedLength(self):
         return lib(self.device).index_info(self.h).seed_len

@@ -62,10 +62,10 @@ PAIRED_RESULT = np.dtype([
     ("n_lv_calls", "<u4"), ("n_lookups", "<u4"), ("p_all", "<f8"), ("p_best", "<f8"),
 ], align=True)
 
-STATS_WORDS = 12 + 71
+STATS_WORDS = 14 + 71
 STATS_FIELDS = ["total_reads", "useful_reads", "single_hits", "multi_hits", "not_found", "errors",
                 "aligned_as_pairs", "lv_calls", "n_hash_table_lookups", "n_locations_scored",
-                "n_hits_ignored_popularity", "n_reads_ignored_ns"]
+                "n_hits_ignored_popularity", "n_reads_ignored_ns", "n_table_probes", "n_hit_words_read"]
 
 assert SINGLE_RESULT.itemsize == 40, SINGLE_RESULT.itemsize
 assert PAIRED_RESULT.itemsize == 56, PAIRED_RESULT.itemsize

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(CTA_THREADS) single_kernel(const SingleArgs a)
                 atomicAdd(a.stats + 8, (unsigned long long)sm->n_lookups);
                 atomicAdd(a.stats + 9, (unsigned long long)sm->n_scored);
                 atomicAdd(a.stats + 10, (unsigned long long)sm->popular);
+                atomicAdd(a.stats + 12, (unsigned long long)sm->n_probes);
+                atomicAdd(a.stats + 13, (unsigned long long)sm->n_hit_words);
             }
         }
         __syncwarp();
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(CTA_THREADS) paired_kernel(const PairedArgs a)
                     atomicAdd(a.stats + 8, (unsigned long long)r->n_lookups);
                     atomicAdd(a.stats + 9, (unsigned long long)sm->n_lv);
                     atomicAdd(a.stats + 10, (unsigned long long)(sm->popular[0] + sm->popular[1]));
+                    atomicAdd(a.stats + 12, (unsigned long long)sm->n_probes);
+                    atomicAdd(a.stats + 13, (unsigned long long)sm->n_hit_words);
                 }
                 r->from_align_together = 1;
                 r->aligned_as_pair = 1;
@@ -249,7 +253,7 @@ __global__ void stats_single_kernel(const snapb200_single_result *r, uint32_t n,
     uint8_t st = r[t].status;
     atomicAdd(stats + 0, 1ull);
     atomicAdd(stats + (st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4), 1ull);
-    if (st != SNAPB200_NOT_FOUND) { int q = r[t].mapq; if (q >= 0 && q <= 70) atomicAdd(stats + 12 + q, 1ull); }
+    if (st != SNAPB200_NOT_FOUND) { int q = r[t].mapq; if (q >= 0 && q <= 70) atomicAdd(stats + 14 + q, 1ull); }
 }
 __global__ void stats_paired_kernel(const snapb200_paired_result *r, uint32_t n, unsigned long long *stats)
 {
@@ -261,7 +265,7 @@ __global__ void stats_paired_kernel(const snapb200_paired_result *r, uint32_t n,
     atomicAdd(stats + 0, 1ull);
     atomicAdd(stats + (st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4), 1ull);
     if (p.aligned_as_pair) atomicAdd(stats + 6, 1ull);
-    if (st != SNAPB200_NOT_FOUND) { int q = p.mapq[e]; if (q >= 0 && q <= 70) atomicAdd(stats + 12 + q, 1ull); }
+    if (st != SNAPB200_NOT_FOUND) { int q = p.mapq[e]; if (q >= 0 && q <= 70) atomicAdd(stats + 14 + q, 1ull); }
 }
 
 // ---- CIGAR against the resident genome (SAM.cpp:1159-1189) ---------------------------------------------------

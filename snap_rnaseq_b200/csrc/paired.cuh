@@ -73,13 +73,14 @@ struct PairedSm {
     int best_dir[2];
     int act, ci, stop, overflow, list, f_off, m_off, fs, ms;
     uint32_t c_loc, c_seedoff, c_sp, mi, m_loc, m_seedoff, m_limit, low_mate;
-    uint32_t n_lv;
+    uint32_t n_lv, n_probes, n_hit_words;
 };
 
 // ---- warp-parallel HashTableHitSet: lane i owns lookup i ------------------------------------------------
 struct LaneLookup {
     const uint32_t *hits;
     uint32_t nh, cur, so, sid;
+    uint32_t words;  // hit-list words this lane has read (accounting for the roofline figure)
     bool act;
 };
 
@@ -93,6 +94,7 @@ __device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, int w, int
     l.so = l.act ? sm->seedoff[w][d][lane] : 0;
     l.sid = l.act ? sm->setid[w][d][lane] : 0;
     l.cur = 0;
+    l.words = 0;
     return l;
 }
 
@@ -120,6 +122,7 @@ __device__ __forceinline__ bool hs_first(LaneLookup &l, uint32_t *most_recent, u
 {
     bool ok = l.act && l.nh > 0;
     uint32_t val = ok ? __ldg(&l.hits[0]) - l.so : 0;
+    l.words += ok;
     *loc = 0;
     if (!pick_max(ok, val, l.so, loc, so)) return false;
     *most_recent = *loc;
@@ -137,6 +140,7 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
         while (lo <= hi) {
             int probe = (lo + hi) / 2;
             uint32_t h = __ldg(&l.hits[probe]);
+            l.words += 2;
             if (h <= want && (probe == 0 || __ldg(&l.hits[probe - 1]) > want)) {
                 found = true;
                 val = h - l.so;
@@ -159,6 +163,7 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
     uint32_t val = 0;
     if (l.act) {
         if (l.cur != l.nh && __ldg(&l.hits[l.cur]) - l.so == *most_recent) l.cur++;
+        l.words += 2;
         if (l.cur != l.nh) {
             uint32_t h = __ldg(&l.hits[l.cur]);
             val = h - l.so;
@@ -242,6 +247,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         }
         sm->overflow = 0;
         sm->n_lv = 0;
+        sm->n_probes = sm->n_hit_words = 0;
     }
     for (int w = 0; w < 2; w++) {
         __syncwarp();
@@ -251,9 +257,11 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         if ((uint32_t)lane < n_sched) {  // all seeds of this mate probed at once
             uint64_t sf, sr;
             HitList hl[2];
+            uint32_t np = 0;
             pack_seed(v[w].D[0] + sm->sched_off[lane], seed_len, &sf, &sr);
-            lookup_seed(ix, sf, sr, hl, nullptr);
+            lookup_seed(ix, sf, sr, hl, &np);
             for (int d = 0; d < 2; d++) { sm->raw_hits[d][lane] = (unsigned long long)hl[d].hits; sm->raw_n[d][lane] = hl[d].n; }
+            atomicAdd(&sm->n_probes, np + (hl[0].n > 1) + (hl[1].n > 1));  // table slots + overflow count words
         }
         __syncwarp();
         if (lane == 0) {  // recordLookup in order (:859-899)
@@ -358,6 +366,8 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             }
             if (!hs_next_lower(lf, &mr_f, &f_loc, &f_off)) break;
         }
+        uint32_t words = __reduce_add_sync(FULL_MASK, lf.words + lm.words);
+        if (lane == 0) sm->n_hit_words += words;
     }
     __syncwarp();
 

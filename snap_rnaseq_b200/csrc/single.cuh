@@ -46,7 +46,7 @@ struct SingleSm {  // per-warp shared state: everything leader and warp sections
     unsigned long long cand_mask;
     uint32_t lowest_unseen[2], n_applied[2];
     uint32_t most_seeds, best_score, best_loc, second_best, second_loc, score_limit, popular;
-    uint32_t n_used, highest_list, n_lookups, n_scored, epoch;
+    uint32_t n_used, highest_list, n_lookups, n_scored, epoch, n_probes, n_hit_words;
     uint32_t out_loc;
     int out_score, out_mapq, out_dir, out_status;
     int action, cand_elem, cand_dir, cand_any_nearby, sc, loc_off, overflow, force, list, alloc_in_chunk;
@@ -507,6 +507,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
         sm->out_loc = INVALID_LOC; sm->out_dir = SNAPB200_FORWARD; sm->out_score = UNUSED_SCORE; sm->out_mapq = 0;
         sm->out_status = SNAPB200_NOT_FOUND;
         sm->p_all = sm->p_best = 0; sm->popular = 0; sm->n_lookups = sm->n_scored = 0; sm->overflow = 0;
+        sm->n_probes = sm->n_hit_words = 0;
         if (cfg.max_hits_to_get > 0) {
             for (int i = 0; i < MAXK; i++) sc.hit_count[i] = 0;
             *mh_found = 0;
@@ -544,16 +545,18 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
         const uint32_t n_sched = sm->n_sched;
         // warp section: all scheduled seeds are probed at once, one per lane
         HitList my[2] = {{nullptr, 0}, {nullptr, 0}};
+        uint32_t my_probes = 0;
         if ((uint32_t)lane < n_sched) {
             uint64_t sf, sr;
             pack_seed(v.D[0] + sm->sched_off[lane], seed_len, &sf, &sr);
-            lookup_seed(ix, sf, sr, my, nullptr);
+            lookup_seed(ix, sf, sr, my, &my_probes);
         }
         bool out = false;
         for (uint32_t j = 0; j < n_sched; j++) {
             if (sm->n_applied[0] + sm->n_applied[1] >= max_seeds) { out = true; break; }
             const uint32_t seed_at = sm->sched_off[j];
-            if (lane == 0) { sm->most_seeds = (uint32_t)sm->sched_wrap[j] + 1; sm->n_lookups++; }
+            const uint32_t probes_j = __shfl_sync(FULL_MASK, my_probes, (int)j);
+            if (lane == 0) { sm->most_seeds = (uint32_t)sm->sched_wrap[j] + 1; sm->n_lookups++; sm->n_probes += probes_j; }
             bool applied = false;
             for (int dir = 0; dir < 2; dir++) {
                 const uint32_t n = __shfl_sync(FULL_MASK, my[dir].n, (int)j);
@@ -589,7 +592,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
                     __syncwarp();
                     if (sm->overflow) return false;
                 }
-                if (lane == 0) sm->n_applied[dir]++;
+                if (lane == 0) { sm->n_applied[dir]++; sm->n_hit_words += lim + (n > 1 ? 1 : 0); }
                 applied = true;
             }
             __syncwarp();

@@ -191,3 +191,43 @@ def test_large_batch_properties(cuda, handle):
         assert np.array_equal(sw[f][:, ::-1], full[f][:2000]), f
     ok = full["status"][:, 0] != 0
     assert ok.mean() > 0.9
+
+
+# ---- device-side index construction (lookup-equivalent to GenomeIndex::BuildIndexToDirectory) ----
+@pytest.mark.parametrize("seed_len", [20, 16, 23])
+def test_index_build_equivalence(cuda, port, tmp_path, seed_len, golden, small_index_dir):
+    from tests_genome import small_genome
+    contigs = small_genome()
+    bases, offs = synth.snap_layout(contigs, 500)
+    h = cuda.build_index(bases, offs, list(contigs), seed_len=seed_len)
+    try:
+        info = cuda.index_info(h)
+        assert info.n_bases == bases.size and info.seed_len == seed_len
+        d = tmp_path / f"built_{seed_len}"
+        cuda.save_index(h, d)
+        # the saved directory must be loadable by the CPU checkers, and lookups must agree with the device
+        rng = np.random.default_rng(seed_len)
+        flat = np.concatenate(list(contigs.values()))
+        seeds = [flat[o:o + seed_len].tobytes() for o in rng.integers(0, flat.size - seed_len, 400)]
+        seeds += [synth.BASES[rng.integers(0, 4, size=seed_len)].tobytes() for _ in range(100)]
+        nh_c, hits_c = cuda.lookup(h, seeds, 64)
+        checkers = [("port", port)]
+        from oracle import oracle as O
+        if O.have_ref():
+            checkers.append(("ref", O.ref()))
+        sim = synth.simulate(contigs, 1500, 100, paired=True, err=0.03, seed=91, junk_frac=0.03)
+        b0, b1 = sim["batches"]
+        got = cuda.paired(h, A.paired_defaults(), b0, b1)
+        for name, chk in checkers:
+            hc = chk.load_index(str(d))
+            nh, hits = chk.lookup(hc, seeds, 64)
+            np.testing.assert_array_equal(nh, nh_c)
+            np.testing.assert_array_equal(hits, hits_c)
+            assert_records_equal(chk.paired(hc, A.paired_defaults(), b0, b1), got, what=f"paired on device-built index vs {name}")
+        if seed_len == 20:
+            # same genome as the reference-built golden index: identical lookup answers and alignments
+            P.check_golden_lookup(cuda, h, golden)
+            P.check_golden_paired(cuda, h, golden)
+            P.check_golden_single(cuda, h, golden)
+    finally:
+        cuda.close_index(h)

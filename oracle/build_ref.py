@@ -110,6 +110,15 @@ def main():
             [os.path.join(work, "ref_driver.o")] + libs)
         run(["g++", "-o", os.path.join(OUT, "snap-rna")] + lib_objs + [os.path.join(work, "Main.o")] + libs)
         run(["g++", "-o", os.path.join(OUT, "ref_unit_tests")] + lib_objs + test_objs + libs)
+        # The drop-in demonstration: the reference's host code + GpuAlignerExtension + libsnapb200.so.  This one IS the
+        # product's reference-side binding; it lives in _ref/ only because it links reference objects.
+        pkg = os.path.join(os.path.dirname(HERE), "snap_rnaseq_b200")
+        so = os.path.join(pkg, "libsnapb200.so")
+        if os.path.exists(so):
+            run(["g++"] + CXXFLAGS + inc + ["-I" + os.path.join(pkg, "host"), "-I" + os.path.join(os.path.dirname(HERE), "include"),
+                 "-c", os.path.join(pkg, "host", "snap_rna_b200_main.cpp"), "-o", os.path.join(work, "b200_main.o")])
+            run(["g++", "-o", os.path.join(OUT, "snap-rna-b200")] + lib_objs + [os.path.join(work, "b200_main.o"), so,
+                 "-Wl,-rpath," + pkg] + libs)
         print("build_ref: built", ", ".join(sorted(os.listdir(OUT))))
     finally:
         shutil.rmtree(work, ignore_errors=True)

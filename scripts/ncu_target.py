@@ -1,0 +1,19 @@
+"""Small fixed workload for ncu captures: one paired step (100k pairs, C2 genome) + one single-end step."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import snap_rnaseq_b200 as S
+from snap_rnaseq_b200 import synth, _abi as A
+import bench
+L = S.lib(0)
+contigs = bench.make_genome()
+bases, offs = synth.snap_layout(contigs, 500)
+h = L.build_index(bases, offs, list(contigs), seed_len=20)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+b0, b1 = bench.make_pairs(contigs, n, 1000)
+sess = S.Session(L, h, n, 128)
+sess.upload(0, b0); sess.upload(1, b1)
+for _ in range(2):
+    sess.run_paired(A.paired_defaults())
+sess.run_single(A.single_defaults())
+print("ok", sess.last_run())

@@ -77,14 +77,21 @@ __global__ void ib_fill_overflow_kernel(const uint32_t *run_id_incl, const uint3
     overflow[off + 1 + (i - s)] = vals[i];
 }
 
-// leader run of each canonical seed: counts seeds per hash table
+// leader run of each canonical seed: counts seeds per hash table.  Runs are sorted by key, so a block sees only one or
+// two distinct tables: aggregate per warp before touching the global counters.
 __global__ void ib_count_tables_kernel(const unsigned long long *keys, const uint32_t *run_start, uint32_t n_runs, unsigned long long *table_count)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_runs) return;
-    uint64_t canon = keys[run_start[r]] >> 1;
-    if (r > 0 && (keys[run_start[r - 1]] >> 1) == canon) return;
-    atomicAdd(&table_count[(uint32_t)(canon >> 32)], 1ull);
+    bool leader = false;
+    uint32_t table = 0xffffffffu;
+    if (r < n_runs) {
+        uint64_t canon = keys[run_start[r]] >> 1;
+        leader = !(r > 0 && (keys[run_start[r - 1]] >> 1) == canon);
+        table = (uint32_t)(canon >> 32);
+    }
+    if (!leader) table = 0xffffffffu;
+    unsigned peers = __match_any_sync(FULL_MASK, table);
+    if (leader && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&table_count[table], (unsigned long long)__popc(peers));
 }
 
 __global__ void ib_insert_kernel(const unsigned long long *keys, const uint32_t *run_start, const uint32_t *ovf_off, const uint32_t *vals,

@@ -135,6 +135,7 @@ struct PairedArgs {
     Cand *cands; Mate *mates; Anchor *anchors;  // [warp slot][...]
     Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
     unsigned long long *stats;
+    unsigned long long *prof;  // optional cycle accounting [8]
 };
 
 __host__ __device__ inline size_t paired_warp_shared(uint32_t rl)
@@ -191,7 +192,14 @@ __global__ void __launch_bounds__(CTA_THREADS) paired_kernel(const PairedArgs a)
             v[w].len = len[w];
             ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w]);
         }
+        if (lane == 0) for (int q = 0; q < 6; q++) sm->t_phase[q] = 0;
+        long long t_s = clock64();
         int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, W, L, r, pi, fix);
+        if (lane == 0 && a.prof) {
+            atomicAdd(a.prof + 0, (unsigned long long)(clock64() - t_s));
+            for (int q = 1; q < 5; q++) atomicAdd(a.prof + q, (unsigned long long)sm->t_phase[q]);
+            atomicAdd(a.prof + 5, 1ull);
+        }
         if (lane == 0) {
             if (rc == 2) {
                 if (a.cfg.hard_limit) {

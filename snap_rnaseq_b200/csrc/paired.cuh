@@ -74,6 +74,7 @@ struct PairedSm {
     int act, ci, stop, overflow, list, f_off, m_off, fs, ms;
     uint32_t c_loc, c_seedoff, c_sp, mi, m_loc, m_seedoff, m_limit, low_mate;
     uint32_t n_lv, n_probes, n_hit_words;
+    long long t_phase[6];  // cycle accounting (SNAPB200_PROF): stage, phase1, phase2, lv, leader3, other
 };
 
 // ---- warp-parallel HashTableHitSet: lane i owns lookup i ------------------------------------------------
@@ -239,6 +240,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     if (rlen[0] < 50 || rlen[1] < 50) return 0;  // :186-188
     if (total_ns > max_k) return 0;              // :226-228
 
+    long long t_a = clock64();
     // ---- phase 1 (:259-340) ----
     if (lane == 0) {
         for (int w = 0; w < 2; w++) {
@@ -305,6 +307,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     }
     __syncwarp();
 
+    long long t_b = clock64();
     // ---- phase 2 (:359-511) ----
     uint32_t n_cands = 0, max_used_list = 0;
     for (int sp = 0; sp < 2; sp++) {
@@ -371,6 +374,8 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     }
     __syncwarp();
 
+    long long t_c = clock64();
+    long long t_lv = 0;
     // ---- phase 3 (:516-720) ----
     if (lane == 0) {
         sm->n_cands = n_cands;
@@ -402,8 +407,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
         double f_prob;
         int f_off;
+        long long t_x = clock64();
         const int fs = score_location_warp(ix, v[fewer], dir_f, sm->c_loc, sm->c_seedoff, (int)sm->score_limit, false, W, L,
                                            &f_prob, &f_off);
+        t_lv += clock64() - t_x;
         __syncwarp();
         if (fs != -1) {
             const uint32_t f_score = (uint32_t)fs;
@@ -426,8 +433,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 if (act == 2) {
                     double m_prob;
                     int m_off;
+                    long long t_y = clock64();
                     int ms = score_location_warp(ix, v[more], dir_m, sm->m_loc, sm->m_seedoff, (int)sm->m_limit, false, W, L,
                                                  &m_prob, &m_off);
+                    t_lv += clock64() - t_y;
                     __syncwarp();
                     if (lane == 0) {
                         Mate *m = &sc.mates[sp][sm->mi];
@@ -520,6 +529,8 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     }
 
     if (lane == 0) {
+        long long t_d = clock64();
+        sm->t_phase[1] = t_b - t_a; sm->t_phase[2] = t_c - t_b; sm->t_phase[3] = t_lv; sm->t_phase[4] = (t_d - t_c) - t_lv;
         if (sm->best_pair_score == 65536) {
             for (int w = 0; w < 2; w++) {
                 r->location[w] = INVALID_LOC; r->mapq[w] = 0; r->score[w] = -1; r->status[w] = SNAPB200_NOT_FOUND;

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -100,6 +101,7 @@ struct snapb200_index {
     // scratch shared by the synchronous batch entry points (sessions own theirs)
     unsigned long long *stats = nullptr;  // SNAPB200_STATS_WORDS counters in HBM
     struct snapb200_session *batch_session[2] = {nullptr, nullptr};
+    std::mutex batch_mutex;  // the synchronous *_batch entry points share the two sessions above: one caller at a time
 };
 
 static int upload(snapb200_index *x, const void *src, size_t bytes, void **dst, size_t pad_before = 0, size_t pad_after = 0, int pad_byte = 0)
@@ -660,8 +662,19 @@ static int launch_single(snapb200_session *s, const SingleCfg &cfg_in, const Sin
     const size_t smem = single_warp_shared(a.cfg.rl) * WARPS_PER_CTA;
     const bool time_it = s->main_pending && mapq_divisor == 1;
     if (time_it) CUDA_TRY(cudaEventRecord(s->evm0, s->stream));
+    const bool prof = getenv("SNAPB200_PROF") != nullptr;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, s->stream); }
     single_kernel<<<tier.grid, CTA_THREADS, smem, s->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
+    if (prof) {
+        cudaEventRecord(pe1, s->stream);
+        cudaEventSynchronize(pe1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe0, pe1);
+        fprintf(stderr, "[snapb200 prof] single_kernel grid=%d items=%u pool_cap=%u divisor=%d: %.2f ms\n", tier.grid, n_items, tier.pool_cap, mapq_divisor, ms);
+        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+    }
     if (time_it) { CUDA_TRY(cudaEventRecord(s->evm1, s->stream)); s->main_pending = false; }
     s->last_launches++;
     return 0;
@@ -826,6 +839,14 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     a.retry_list = s->retry_list.as<uint32_t>(); a.fallback_list = s->fallback_list.as<uint32_t>();
     a.fix = s->fix.as<MapqFix>(); a.fix_cap = FIX_CAP;
     a.stats = x->stats;
+    a.prof = nullptr;
+    static DevBuf prof_buf;
+    const bool prof = getenv("SNAPB200_PROF") != nullptr;
+    if (prof) {
+        if ((rc = prof_buf.ensure(64))) return rc;
+        CUDA_TRY(cudaMemsetAsync(prof_buf.p, 0, 64, s->stream));
+        a.prof = prof_buf.as<unsigned long long>();
+    }
     if ((rc = reset_work(s))) return rc;
     const size_t smem = paired_warp_shared(cfg.rl) * WARPS_PER_CTA;
     const bool time_it = s->main_pending;
@@ -834,6 +855,14 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     CUDA_TRY(cudaGetLastError());
     if (time_it) { CUDA_TRY(cudaEventRecord(s->evm1, s->stream)); s->main_pending = false; }
     s->last_launches++;
+    if (prof) {
+        unsigned long long h[8];
+        CUDA_TRY(cudaMemcpyAsync(h, prof_buf.p, 64, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        double tot = (double)h[0];
+        fprintf(stderr, "[snapb200 prof] paired_kernel grid=%d items=%llu cycles/item=%.0f  phase1 %.1f%%  phase2 %.1f%%  lv %.1f%%  leader3 %.1f%%\n", grid,
+                h[5], h[5] ? tot / h[5] : 0.0, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot);
+    }
     return 0;
 }
 
@@ -1027,6 +1056,7 @@ static int single_batch_impl(snapb200_index *idx, const snapb200_single_params *
     uint32_t m;
     int rc = validate_batch(reads, &m);
     if (rc) return rc;
+    std::lock_guard<std::mutex> guard(idx->batch_mutex);
     snapb200_session *s[2];
     if ((rc = get_batch_sessions(idx, s))) return rc;
     const uint32_t n = reads->n;
@@ -1085,6 +1115,7 @@ extern "C" int snapb200_paired_batch(snapb200_index *idx, const snapb200_paired_
     uint32_t m0, m1;
     int rc;
     if ((rc = validate_batch(reads0, &m0)) || (rc = validate_batch(reads1, &m1))) return rc;
+    std::lock_guard<std::mutex> guard(idx->batch_mutex);
     snapb200_session *s[2];
     if ((rc = get_batch_sessions(idx, s))) return rc;
     const uint32_t n = reads0->n;
@@ -1122,6 +1153,7 @@ extern "C" int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_bat
     if (rc) return rc;
     const uint32_t n = reads->n;
     if (!n) return 0;
+    std::lock_guard<std::mutex> guard(idx->batch_mutex);
     snapb200_session *s[2];
     if ((rc = get_batch_sessions(idx, s))) return rc;
     snapb200_session *ss = s[0];

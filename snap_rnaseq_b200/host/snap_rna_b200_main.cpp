@@ -1,0 +1,45 @@
+// snap-rna-b200: the reference's command line with the alignment core on the GPU.
+//
+// Same sub-commands and options as apps/snap/Main.cpp:54-84 of the reference; the only difference is that the
+// single/paired contexts are constructed with a GpuAlignerExtension (the two-line change INTEGRATION.md shows).
+// `index` and `transcriptome` are the reference's own host-side builders.
+#include <stdio.h>
+#include <string.h>
+
+#include "stdafx.h"
+#include "GenomeIndex.h"
+#include "PairedAligner.h"
+#include "SingleAligner.h"
+#include "exit.h"
+
+#include "GpuAlignerExtension.h"
+
+int main(int argc, const char **argv)
+{
+    const char *version = "0.1alpha-b200";
+    printf("Welcome to SNAP-RNA version %s.\n\n", version);
+    if (argc < 2) {
+        fprintf(stderr, "Usage: snap-rna-b200 <index|transcriptome|single|paired> [<options>]\n");
+        soft_exit(1);
+    } else if (strcmp(argv[1], "index") == 0) {
+        GenomeIndex::runIndexer(argc - 2, argv + 2);
+    } else if (strcmp(argv[1], "transcriptome") == 0) {
+        GenomeIndex::runTranscriptomeIndexer(argc - 2, argv + 2);
+    } else {
+        for (int i = 1; i < argc;) {
+            unsigned nArgsConsumed = 0;
+            if (strcmp(argv[i], "single") == 0) {
+                SingleAlignerContext single(new GpuAlignerExtension());
+                single.runAlignment(argc - (i + 1), argv + i + 1, version, &nArgsConsumed);
+            } else if (strcmp(argv[i], "paired") == 0) {
+                PairedAlignerContext paired(new GpuAlignerExtension());
+                paired.runAlignment(argc - (i + 1), argv + i + 1, version, &nArgsConsumed);
+            } else {
+                fprintf(stderr, "Invalid command: %s\n", argv[i]);
+                soft_exit(1);
+            }
+            i += nArgsConsumed + 1;
+        }
+    }
+    return 0;
+}

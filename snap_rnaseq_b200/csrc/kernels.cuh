@@ -21,7 +21,12 @@ struct Counters {  // device-side counters read back after each launch group
 };
 
 __device__ __forceinline__ uint32_t round8(uint32_t x) { return (x + 7u) & ~7u; }
-__host__ __device__ inline size_t lv_shared_bytes() { return ((size_t)LV_CELLS * 2 + 15) & ~(size_t)15; }
+// the L buffer: the triangular table of the warp mode (961 cells) or the rolling row pairs of the lane mode (70 cells x 32 lanes)
+__host__ __device__ inline size_t lv_shared_bytes()
+{
+    size_t cells = LV_CELLS > LANE_ROLL_CELLS * 32 ? LV_CELLS : LANE_ROLL_CELLS * 32;
+    return (cells * 2 + 15) & ~(size_t)15;
+}
 
 __device__ __forceinline__ uint32_t fetch_work(uint32_t *counter)
 {
@@ -132,7 +137,7 @@ struct PairedArgs {
     uint32_t n_items;
     snapb200_paired_result *results;
     uint32_t force_spacing;
-    Cand *cands; Mate *mates; Anchor *anchors;  // [warp slot][...]
+    Cand *cands; Mate *mates; Anchor *anchors; int16_t *lane_tables;  // [warp slot][...]
     Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
     unsigned long long *stats;
     unsigned long long *prof;  // optional cycle accounting [8]
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(CTA_THREADS) paired_kernel(const PairedArgs a)
     sc.mates[0] = a.mates + (size_t)slot * 2 * a.cfg.mate_cap;
     sc.mates[1] = sc.mates[0] + a.cfg.mate_cap;
     sc.anchors = a.anchors + (size_t)slot * a.cfg.anchor_cap;
+    sc.lane_table = a.lane_tables + (size_t)slot * LANE_TABLE_CELLS * 32;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
     for (;;) {
         const uint32_t p = fetch_work(&a.ctr->work);
@@ -192,13 +198,14 @@ __global__ void __launch_bounds__(CTA_THREADS) paired_kernel(const PairedArgs a)
             v[w].len = len[w];
             ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w]);
         }
-        if (lane == 0) for (int q = 0; q < 6; q++) sm->t_phase[q] = 0;
+        if (lane == 0) for (int q = 0; q < 12; q++) sm->t_phase[q] = 0;
         long long t_s = clock64();
         int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, W, L, r, pi, fix);
         if (lane == 0 && a.prof) {
             atomicAdd(a.prof + 0, (unsigned long long)(clock64() - t_s));
             for (int q = 1; q < 5; q++) atomicAdd(a.prof + q, (unsigned long long)sm->t_phase[q]);
             atomicAdd(a.prof + 5, 1ull);
+            for (int q = 5; q < 10; q++) atomicAdd(a.prof + q + 1, (unsigned long long)sm->t_phase[q]);
         }
         if (lane == 0) {
             if (rc == 2) {

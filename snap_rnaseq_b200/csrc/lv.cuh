@@ -313,3 +313,151 @@ __device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int
     }
     return __shfl_sync(FULL_MASK, rc, 0);
 }
+
+// =================================================================================================================
+// Lane-level Landau-Vishkin: 32 candidates per warp, one per lane.
+//
+// The warp-cooperative routine above spends a whole warp on one candidate, which is the right trade for the common
+// pair (two or three candidates) but not for reads from repeat families, where one pair scores thousands of
+// candidates and the kernel becomes issue bound.  For those, every lane runs the *same* algorithm on its own
+// candidate: cells are visited in the reference's order (so the first diagonal to reach the end of the pattern is
+// the reference's), strings are compared four bytes per step (XOR + find-first-set, as the reference does with
+// eight), the pattern comes from the read staged in shared memory and the text straight from the genome in HBM
+// through L1 (a candidate's window is two or three 128-byte lines, touched by one lane only).  The per-lane L table
+// is interleaved in shared memory (cell c of lane l at L[c*32+l]) so that lanes walking the table in lockstep never
+// conflict.  Preconditions (checked by the caller): k <= LANE_KMAX, textLen >= patternLen + k (always true for
+// windows inside the genome), and the 4-byte over-reads stay inside readable memory.
+// =================================================================================================================
+#define LANE_KMAX 17                      // largest score limit handled in lane mode (defaults: 15+2 paired, 14+2 single)
+#define LANE_ROW (2 * LANE_KMAX + 1)      // cells of one row of the rolling pair kept in shared memory
+#define LANE_ROLL_CELLS (2 * LANE_ROW)    // per lane: previous row + current row
+#define LANE_TABLE_CELLS ((LANE_KMAX + 1) * (LANE_KMAX + 1))  // per lane: the full triangular table, spilled to HBM scratch
+
+__device__ __forceinline__ uint32_t ld4_any(const uint8_t *p)
+{  // unaligned 4-byte little-endian load from shared or global memory (reads the two enclosing aligned words)
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (unsigned)(a & 3) * 8);
+}
+
+// four consecutive string bytes starting at index i, byte 0 of the result = string(i)
+template <int DIR>
+__device__ __forceinline__ uint32_t str4(const uint8_t *base, int i)
+{
+    if (DIR > 0) return ld4_any(base + i);
+    return __byte_perm(ld4_any(base - i - 3), 0, 0x0123);
+}
+
+// length of the common run of pattern[pi..] and text[ti..], at most plen - pi
+template <int DIR>
+__device__ __forceinline__ int lane_run(const uint8_t *p, const uint8_t *t, int pi, int ti, int plen)
+{
+    const int rem = plen - pi;
+    int n = 0;
+    while (n < rem) {
+        uint32_t x = str4<DIR>(p, pi + n) ^ str4<DIR>(t, ti + n);
+        if (x) { n += (__ffs((int)x) - 1) >> 3; break; }
+        n += 4;
+    }
+    return n < rem ? n : rem;
+}
+
+// full table (HBM scratch): cell (e,d) of this lane at T[(e*e+d+e)*32]; cells outside the band read as -2
+__device__ __forceinline__ int lane_get(const int16_t *T, int e, int d)
+{
+    return (d >= -e && d <= e) ? (int)T[(e * e + d + e) * 32] : -2;
+}
+// rolling rows (shared): row parity (e&1), diagonal d of this lane at R[((e&1)*LANE_ROW + d + LANE_KMAX)*32]
+__device__ __forceinline__ int roll_get(const int16_t *R, int e, int d)
+{
+    return (d >= -e && d <= e) ? (int)R[(((e & 1) * LANE_ROW) + d + LANE_KMAX) * 32] : -2;
+}
+
+// LandauVishkin<DIR>::computeEditDistance for this lane's candidate.  All 32 lanes must call it together (it uses
+// a warp vote to stop early); `live_in` is false for lanes without a candidate.  p/t point at string index 0 and are
+// walked with stride DIR; q likewise.  R = this lane's column of the rolling rows in shared memory, T = this lane's
+// column of the full table in HBM scratch (written on the way, read only by the backtrace of successful lanes).
+// k may differ between lanes.  Returns the score or -1.
+template <int DIR>
+__device__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int16_t *R, int16_t *T, const DevIndex &ix,
+                       bool live_in, double *match_prob, int *net_indel)
+{
+    int result = -1, win_d = 0;
+    *match_prob = 0.0;
+    *net_indel = 0;
+    bool live = live_in;
+    int l0 = 0;
+    if (live) {
+        l0 = lane_run<DIR>(p, t, 0, 0, plen);
+        R[LANE_KMAX * 32] = (int16_t)l0;
+        T[0] = (int16_t)l0;
+        if (l0 == plen) {  // LandauVishkin.h:290-305 (text is never shorter than the pattern here)
+            result = 0;
+            *match_prob = ix.perfect[plen];
+            live = false;
+        }
+    }
+    const int kmax = min(k > 0 ? k : 0, LANE_KMAX);
+    for (int e = 1; e <= LANE_KMAX; e++) {
+        if (live && e > kmax) live = false;
+        if (!__any_sync(FULL_MASK, live)) break;
+        for (int r = 0; r <= 2 * e; r++) {
+            if (live) {
+                const int d = lv_unrank_score(r);
+                int best = roll_get(R, e - 1, d) + 1;
+                int left = roll_get(R, e - 1, d - 1);
+                if (left > best) best = left;
+                int right = roll_get(R, e - 1, d + 1) + 1;
+                if (right > best) best = right;
+                if (best < plen) best += lane_run<DIR>(p, t, best, d + best, plen);
+                R[(((e & 1) * LANE_ROW) + d + LANE_KMAX) * 32] = (int16_t)best;
+                T[(e * e + d + e) * 32] = (int16_t)best;
+                if (best == plen) { result = e; win_d = d; live = false; }
+            }
+        }
+    }
+    if (result >= 1) {  // backtrace, LandauVishkin.h:379-431
+        char act[LANE_KMAX + 1];
+        short matched[LANE_KMAX + 1];
+        int cur_d = win_d;
+        for (int ce = result; ce >= 1; ce--) {
+            int up = lane_get(T, ce - 1, cur_d) + 1, left = lane_get(T, ce - 1, cur_d - 1), right = lane_get(T, ce - 1, cur_d + 1) + 1;
+            int best = up;
+            char a = 'X';
+            if (left > best) { best = left; a = 'D'; }
+            if (right > best) { best = right; a = 'I'; }
+            const int here = (ce == result) ? plen : lane_get(T, ce, cur_d);
+            act[ce] = a;
+            matched[ce] = (short)(here - best);  // bases matched after the edit = L[ce][d] - (value before extension)
+            cur_d += a == 'I' ? 1 : (a == 'D' ? -1 : 0);
+        }
+        double prob = 1.0;
+        int indel = 0, ce = 1, offset = l0;
+        while (ce <= result) {
+            const char a = act[ce];
+            int count = 1;
+            while (ce + 1 <= result && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
+            if (a == 'I') {
+                prob *= ix.indel[count];
+                offset += count;
+                indel += count;
+            } else if (a == 'D') {
+                prob *= ix.indel[count];
+                offset -= count;
+                indel -= count;
+            } else {
+                for (int i = 0; i < count; i++) {
+                    int qi = min(plen - 1, max(offset, 0));
+                    prob *= ix.phred[q[qi * DIR]];
+                    offset++;
+                }
+            }
+            offset += matched[ce];
+            ce++;
+        }
+        prob *= ix.perfect[plen - result];
+        *match_prob = prob;
+        *net_indel = indel;
+    }
+    return result;
+}

@@ -13,18 +13,39 @@
 #pragma once
 #include "single.cuh"
 
+#define SC_NONE (-3)       // "score not computed yet" in the look-ahead caches below
+#define MATE_LOOKAHEAD_ROUNDS 2  // mates scored ahead per candidate of a lane-mode batch
+#define LANE_MIN_BATCH 3   // fewer pending locations than this: the warp-cooperative LV is cheaper
+
 struct __align__(8) Mate {  // ScoringMateCandidate (IntersectingPairedEndAligner.h:401-423)
     double prob;
     uint32_t loc, best_possible, score, score_limit;
     uint32_t seed_offset;
     int32_t genome_offset;
+    // look-ahead cache: the true LV outcome for limit s_k (s_score = -1: distance > s_k)
+    double s_prob;
+    int16_t s_score;
+    uint8_t s_k;
+    int8_t s_off;
+    uint32_t pad;
 };
-struct Cand {  // ScoringCandidate (:425-447)
+struct __align__(8) Cand {  // ScoringCandidate (:425-447)
     int32_t next, anchor;
     uint32_t mate_index, loc;
     uint16_t seed_offset;
     uint8_t set_pair, best_possible;
+    // look-ahead cache of the fewer end's score (see phase 3)
+    int16_t c_score;
+    uint8_t c_k;
+    int8_t c_off;
+    double c_prob;
 };
+// is the outcome of scoring this mate with limit `limit` already determined by the look-ahead cache?
+__device__ __forceinline__ bool mate_known(const Mate *m, uint32_t limit)
+{
+    return m->s_score >= 0 || (m->s_score == -1 && m->s_k >= limit);  // a stored distance is exact for every limit
+}
+
 struct __align__(8) Anchor {  // MergeAnchor (:364-393)
     double prob;
     uint32_t loc_more, loc_fewer;
@@ -44,6 +65,7 @@ struct PairedScratch {
     Cand *cands;
     Mate *mates[2];
     Anchor *anchors;
+    int16_t *lane_table;  // LANE_TABLE_CELLS * 32 cells: the full L tables of a lane-mode batch
 };
 
 #define STATUS_LIMIT 0xfd  // the reference's candidate pools would have overflowed (it exits)
@@ -71,10 +93,12 @@ struct PairedSm {
     uint32_t best_pair_score, score_limit, n_cands, n_anchors, n_mates[2], max_used_list;
     uint32_t best_loc[2], best_score[2];
     int best_dir[2];
-    int act, ci, stop, overflow, list, f_off, m_off, fs, ms;
+    int act, act2, ci, stop, overflow, list, f_off, m_off, fs, ms;
+    uint32_t n_batch;
+    uint32_t batch_ids[32];
     uint32_t c_loc, c_seedoff, c_sp, mi, m_loc, m_seedoff, m_limit, low_mate;
     uint32_t n_lv, n_probes, n_hit_words;
-    long long t_phase[6];  // cycle accounting (SNAPB200_PROF): stage, phase1, phase2, lv, leader3, other
+    long long t_phase[12];  // cycle accounting (SNAPB200_PROF): stage, phase1, phase2, lv, leader3, other
 };
 
 // ---- warp-parallel HashTableHitSet: lane i owns lookup i ------------------------------------------------
@@ -338,6 +362,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     Mate *m = &mates[n_mates];
                     m->loc = m_loc; m->best_possible = bp; m->seed_offset = m_off;
                     m->score = (uint32_t)-2; m->score_limit = (uint32_t)-1; m->prob = 0; m->genome_offset = 0;
+                    m->s_score = SC_NONE; m->s_k = 0;
                 }
                 n_mates++;
                 last_mate_loc = m_loc;
@@ -362,6 +387,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     Cand *c = &sc.cands[n_cands];
                     c->loc = f_loc; c->set_pair = (uint8_t)sp; c->mate_index = n_mates - 1; c->seed_offset = (uint16_t)f_off;
                     c->best_possible = (uint8_t)bp_fewer; c->next = sm->score_list[low_mate + bp_fewer]; c->anchor = -1;
+                    c->c_score = SC_NONE; c->c_k = 0;
                     sm->score_list[low_mate + bp_fewer] = (int)n_cands;
                 }
                 n_cands++;
@@ -377,6 +403,11 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     long long t_c = clock64();
     long long t_lv = 0;
     // ---- phase 3 (:516-720) ----
+    // The visiting order of candidates (lists 0,1,2..., LIFO inside a list) and of a candidate's mates is fixed once
+    // phase 2 is done, and an LV result for limit k is (d <= k ? (d, probability, netIndel) : -1) with d, probability and
+    // netIndel independent of k.  So scores are computed AHEAD of their use, 32 locations per warp (one per lane,
+    // lv_lane) with the current limit, which only ever shrinks, and are committed one by one in the reference's order
+    // with the limit in force at that moment.  Counters (nLocationsScored) advance at commit time only.
     if (lane == 0) {
         sm->n_cands = n_cands;
         sm->list = 0;
@@ -399,31 +430,143 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
                 sm->act = 1;
                 sm->n_lv++;
+                // is this candidate's score already known?  If not, gather the next unscored candidates in visiting order.
+                sm->n_batch = 0;
+                if (c->c_score == SC_NONE) {
+                    uint32_t l = list;
+                    int j = ci;
+                    uint32_t nb = 0;
+                    const bool lane_ok = sm->score_limit <= LANE_KMAX;
+                    while (nb < 32) {
+                        if (j < 0) {
+                            l++;
+                            if (!lane_ok || l > max_used_list || l > sm->score_limit) break;
+                            j = sm->score_list[l];
+                            continue;
+                        }
+                        if (sc.cands[j].c_score == SC_NONE) sm->batch_ids[nb++] = (uint32_t)j;
+                        j = sc.cands[j].next;
+                        if (!lane_ok) break;
+                    }
+                    sm->n_batch = nb;
+                }
             }
         }
         __syncwarp();
         if (!sm->act) break;
         const uint32_t sp = sm->c_sp;
         const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
-        double f_prob;
-        int f_off;
         long long t_x = clock64();
-        const int fs = score_location_warp(ix, v[fewer], dir_f, sm->c_loc, sm->c_seedoff, (int)sm->score_limit, false, W, L,
-                                           &f_prob, &f_off);
-        t_lv += clock64() - t_x;
+        const uint32_t n_batch = sm->n_batch;
+        if (n_batch >= LANE_MIN_BATCH) {
+            // lane mode: lane i scores candidate batch_ids[i] with K = current limit
+            const int K = (int)sm->score_limit;
+            bool act_l = (uint32_t)lane < n_batch;
+            Cand *cl = act_l ? &sc.cands[sm->batch_ids[lane]] : nullptr;
+            int s = SC_NONE, off = 0;
+            double pr = 0;
+            const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
+            score_location_lane(ix, v[fewer], dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+            if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
+            __syncwarp();
+            if (lane == 0) { sm->t_phase[5] += clock64() - t_x; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; }
+            // Mate look-ahead: a candidate whose fewer end scored s will ask its mates for a score with limit <= K - s.
+            // Each lane walks the mates of its own candidate and, per round, one still-unknown mate per lane is scored.
+            {
+                long long t_m = clock64();
+                bool walking = act_l && s >= 0;
+                const int Km = K - (s > 0 ? s : 0);
+                const uint32_t spl = act_l ? cl->set_pair : 0;
+                const int dml = more == 0 ? (int)spl : 1 - (int)spl;
+                const uint32_t cloc = act_l ? cl->loc : 0;
+                uint32_t j = act_l ? cl->mate_index : 0;
+                Mate *mbase = sc.mates[spl];
+                uint32_t n_done = 0;
+                for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
+                    Mate *mt = nullptr;
+                    while (walking) {
+                        Mate *q = &mbase[j];
+                        const bool needs = !is_within(q->loc, cloc, min_spacing) && q->best_possible <= (uint32_t)Km &&
+                                           (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < (uint32_t)Km)) &&
+                                           !mate_known(q, (uint32_t)Km);
+                        if (j == 0 || !is_within(mbase[j - 1].loc, cloc, max_spacing)) walking = false; else j--;
+                        if (needs) { mt = q; break; }
+                    }
+                    if (!__any_sync(FULL_MASK, mt != nullptr)) break;
+                    // the same mate may be wanted by several candidates of the batch: one lane scores it, with the largest limit
+                    const unsigned long long key = (unsigned long long)mt;
+                    const unsigned peers = __match_any_sync(FULL_MASK, key);
+                    int gmax = 0;
+                    for (int src = 0; src < 32; src++) {
+                        int kk = __shfl_sync(FULL_MASK, Km, src);
+                        if ((peers >> src) & 1) gmax = max(gmax, kk);
+                    }
+                    const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
+                    int s2 = SC_NONE, off2 = 0;
+                    double pr2 = 0;
+                    score_location_lane(ix, v[more], dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, L + lane, sc.lane_table + lane, mine,
+                                        &s2, &pr2, &off2);
+                    if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
+                    n_done += __popc(__ballot_sync(FULL_MASK, mine));
+                    __syncwarp();
+                }
+                if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; }
+            }
+        }
+        if (lane == 0) sm->act = sc.cands[sm->ci].c_score == SC_NONE;
         __syncwarp();
+        if (sm->act) {  // warp mode for this one candidate (small batch, large limit, or a window at the genome's edge)
+            double pr;
+            int off;
+            const int K = (int)sm->score_limit;
+            long long t_w = clock64();
+            int s = score_location_warp(ix, v[fewer], dir_f, sm->c_loc, sm->c_seedoff, K, false, W, L, &pr, &off);
+            __syncwarp();
+            if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; }
+            if (lane == 0) { Cand *c = &sc.cands[sm->ci]; c->c_score = (int16_t)s; c->c_k = (uint8_t)K; c->c_off = (int8_t)off; c->c_prob = pr; }
+            __syncwarp();
+        }
+        t_lv += clock64() - t_x;
+        int fs, f_off;
+        double f_prob;
+        {
+            const Cand *c = &sc.cands[sm->ci];
+            const int cs = c->c_score;
+            fs = (cs >= 0 && (uint32_t)cs <= sm->score_limit) ? cs : -1;
+            f_prob = fs >= 0 ? c->c_prob : 0.0;
+            f_off = fs >= 0 ? (int)c->c_off : 0;
+        }
         if (fs != -1) {
             const uint32_t f_score = (uint32_t)fs;
             for (;;) {  // mates of this candidate (:559-711)
                 if (lane == 0) {
                     Mate *m = &sc.mates[sp][sm->mi];
                     int act = 0;
+                    sm->n_batch = 0;
                     if (!is_within(m->loc, sm->c_loc, min_spacing) && m->best_possible <= sm->score_limit - f_score) {
                         act = 1;
-                        if (m->score == (uint32_t)-2 || (m->score == (uint32_t)-1 && m->score_limit < sm->score_limit - f_score)) {
+                        const uint32_t m_limit = sm->score_limit - f_score;
+                        if (m->score == (uint32_t)-2 || (m->score == (uint32_t)-1 && m->score_limit < m_limit)) {
                             act = 2;
-                            sm->m_loc = m->loc; sm->m_seedoff = m->seed_offset; sm->m_limit = sm->score_limit - f_score;
+                            sm->m_loc = m->loc; sm->m_seedoff = m->seed_offset; sm->m_limit = m_limit;
                             sm->n_lv++;
+                            if (!mate_known(m, m_limit)) {
+                                // not known well enough: gather the mates further down this candidate's range that will need a score
+                                uint32_t nb = 0;
+                                const bool lane_ok = m_limit <= LANE_KMAX;
+                                uint32_t j = sm->mi;
+                                for (;;) {
+                                    Mate *q = &sc.mates[sp][j];
+                                    if (!is_within(q->loc, sm->c_loc, min_spacing) && q->best_possible <= m_limit &&
+                                        (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < m_limit)) &&
+                                        !mate_known(q, m_limit))
+                                        sm->batch_ids[nb++] = j;
+                                    if (!lane_ok || nb >= 32) break;
+                                    if (j == 0 || !is_within(sc.mates[sp][j - 1].loc, sm->c_loc, max_spacing)) break;
+                                    j--;
+                                }
+                                sm->n_batch = nb;
+                            }
                         }
                     }
                     sm->act = act;
@@ -431,17 +574,41 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 __syncwarp();
                 const int act = sm->act;
                 if (act == 2) {
-                    double m_prob;
-                    int m_off;
                     long long t_y = clock64();
-                    int ms = score_location_warp(ix, v[more], dir_m, sm->m_loc, sm->m_seedoff, (int)sm->m_limit, false, W, L,
-                                                 &m_prob, &m_off);
-                    t_lv += clock64() - t_y;
-                    __syncwarp();
-                    if (lane == 0) {
-                        Mate *m = &sc.mates[sp][sm->mi];
-                        m->score = (uint32_t)ms; m->prob = m_prob; m->genome_offset = m_off; m->score_limit = sm->m_limit;
+                    const uint32_t nb = sm->n_batch;
+                    const int K = (int)sm->m_limit;
+                    if (nb >= LANE_MIN_BATCH) {
+                        bool act_l = (uint32_t)lane < nb;
+                        Mate *ml = act_l ? &sc.mates[sp][sm->batch_ids[lane]] : nullptr;
+                        int s = SC_NONE, off = 0;
+                        double pr = 0;
+                        score_location_lane(ix, v[more], dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+                        if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
+                        __syncwarp();
+                        if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; }
                     }
+                    if (lane == 0) { const Mate *m = &sc.mates[sp][sm->mi]; sm->act2 = !mate_known(m, sm->m_limit); }
+                    __syncwarp();
+                    if (sm->act2) {
+                        double m_prob;
+                        int m_off;
+                        long long t_w = clock64();
+                        int ms = score_location_warp(ix, v[more], dir_m, sm->m_loc, sm->m_seedoff, K, false, W, L, &m_prob, &m_off);
+                        __syncwarp();
+                        if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; }
+                        if (lane == 0) { Mate *m = &sc.mates[sp][sm->mi]; m->s_score = (int16_t)ms; m->s_k = (uint8_t)K; m->s_off = (int8_t)m_off; m->s_prob = m_prob; }
+                        __syncwarp();
+                    }
+                    if (lane == 0) {  // commit: what scoreLocation(limit = m_limit) returns
+                        Mate *m = &sc.mates[sp][sm->mi];
+                        const int d = m->s_score;
+                        const bool ok = d >= 0 && (uint32_t)d <= sm->m_limit;
+                        m->score = ok ? (uint32_t)d : (uint32_t)-1;
+                        m->prob = ok ? m->s_prob : 0.0;
+                        m->genome_offset = ok ? (int)m->s_off : 0;
+                        m->score_limit = sm->m_limit;
+                    }
+                    t_lv += clock64() - t_y;
                 }
                 if (lane == 0) {
                     Mate *m = &sc.mates[sp][sm->mi];

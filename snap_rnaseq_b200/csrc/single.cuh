@@ -155,6 +155,36 @@ __device__ int score_location_warp(const DevIndex &ix, const ReadView &v, int di
     return s1 + s2;
 }
 
+// The same scoring step for 32 candidates at once, one per lane (see lv_lane in lv.cuh).  v: the read (shared memory);
+// dir/loc/seed_offset: this lane's candidate; K <= LANE_KMAX: the score limit; R: this lane's column of the
+// interleaved rolling rows (shared) and T its column of the full table (HBM scratch).  Lanes whose genome window is not entirely inside the genome return SC_NONE_LANE and are
+// left to score_location_warp.  All 32 lanes must call this together.
+#define SC_NONE_LANE (-3)
+__device__ void score_location_lane(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset, int K,
+                                    int16_t *R, int16_t *T, bool active, int *score, double *match_prob, int *loc_offset)
+{
+    const uint32_t rlen = v.len;
+    // same test as getSubstring(loc, rlen + MAX_K) != NULL; the 4-byte loads stay within +-16 bytes of that window
+    bool ok = active && substring_ok(ix, loc, rlen + MAXK);
+    *score = SC_NONE_LANE;
+    *match_prob = 0;
+    *loc_offset = 0;
+    const int seed_len = (int)ix.seed_len;
+    const int tail = (int)seed_offset + seed_len;
+    const uint8_t *g = ix.genome + loc;
+    double p1 = 0, p2 = 0;
+    int dummy, off = 0;
+    int s1 = lv_lane<1>(v.D[dir] + tail, (int)rlen - tail, g + tail, v.Q[dir] + tail, K, R, T, ix, ok, &p1, &dummy);
+    const bool ok2 = ok && s1 != -1;
+    int s2 = lv_lane<-1>(v.D[dir] + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q[dir] + (int)seed_offset - 1,
+                         K - (s1 > 0 ? s1 : 0), R, T, ix, ok2, &p2, &off);
+    if (!ok) return;
+    if (s1 == -1 || s2 == -1) { *score = -1; return; }
+    *score = s1 + s2;
+    *match_prob = p1 * p2 * ix.seed_prob;
+    *loc_offset = off;
+}
+
 // computeMAPQ (SNAPLib/mapq.h:32-65).  *near_integer is set when the log10 value is so close to an integer that
 // the truncation could depend on the last ulp of log10; the host then repeats the evaluation with libm.
 __device__ __forceinline__ int compute_mapq_dev(double p_all, double p_best, int score, int popular, bool *near_integer)

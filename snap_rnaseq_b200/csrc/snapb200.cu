@@ -466,7 +466,7 @@ struct snapb200_session {
     DevBuf mh_counts, mh_locs, mh_rcs, mh_scores;
     // scratch tiers
     DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
-    DevBuf p_cands, p_mates, p_anchors;
+    DevBuf p_cands, p_mates, p_anchors, p_lane_tables;
     uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
     uint32_t anchors_warps = 0;
     // last run
@@ -515,7 +515,7 @@ extern "C" void snapb200_session_destroy(snapb200_session *s)
     DevBuf *all[] = {&s->offsets[0], &s->offsets[1], &s->bases[0], &s->bases[1], &s->quals[0], &s->quals[1], &s->single_res,
                      &s->paired_res, &s->fb_single_res, &s->retry_list, &s->fallback_list, &s->fb_positions, &s->fix, &s->counters,
                      &s->mh_counts, &s->mh_locs, &s->mh_rcs, &s->mh_scores, &s->s_pool, &s->s_anchors, &s->s_lists, &s->s_epochs,
-                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors};
+                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables};
     for (DevBuf *b : all) b->release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -834,7 +834,9 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     if ((rc = s->p_cands.ensure(warps * cfg.cand_cap * sizeof(Cand)))) return rc;
     if ((rc = s->p_mates.ensure(warps * 2 * cfg.mate_cap * sizeof(Mate)))) return rc;
     if ((rc = s->p_anchors.ensure(warps * cfg.anchor_cap * sizeof(Anchor)))) return rc;
+    if ((rc = s->p_lane_tables.ensure(warps * LANE_TABLE_CELLS * 32 * sizeof(int16_t)))) return rc;
     a.cands = s->p_cands.as<Cand>(); a.mates = s->p_mates.as<Mate>(); a.anchors = s->p_anchors.as<Anchor>();
+    a.lane_tables = s->p_lane_tables.as<int16_t>();
     a.ctr = s->counters.as<Counters>();
     a.retry_list = s->retry_list.as<uint32_t>(); a.fallback_list = s->fallback_list.as<uint32_t>();
     a.fix = s->fix.as<MapqFix>(); a.fix_cap = FIX_CAP;
@@ -843,8 +845,8 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     static DevBuf prof_buf;
     const bool prof = getenv("SNAPB200_PROF") != nullptr;
     if (prof) {
-        if ((rc = prof_buf.ensure(64))) return rc;
-        CUDA_TRY(cudaMemsetAsync(prof_buf.p, 0, 64, s->stream));
+        if ((rc = prof_buf.ensure(128))) return rc;
+        CUDA_TRY(cudaMemsetAsync(prof_buf.p, 0, 128, s->stream));
         a.prof = prof_buf.as<unsigned long long>();
     }
     if ((rc = reset_work(s))) return rc;
@@ -856,12 +858,14 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     if (time_it) { CUDA_TRY(cudaEventRecord(s->evm1, s->stream)); s->main_pending = false; }
     s->last_launches++;
     if (prof) {
-        unsigned long long h[8];
-        CUDA_TRY(cudaMemcpyAsync(h, prof_buf.p, 64, cudaMemcpyDeviceToHost, s->stream));
+        unsigned long long h[16];
+        CUDA_TRY(cudaMemcpyAsync(h, prof_buf.p, 128, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         double tot = (double)h[0];
         fprintf(stderr, "[snapb200 prof] paired_kernel grid=%d items=%llu cycles/item=%.0f  phase1 %.1f%%  phase2 %.1f%%  lv %.1f%%  leader3 %.1f%%\n", grid,
                 h[5], h[5] ? tot / h[5] : 0.0, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot);
+        fprintf(stderr, "[snapb200 prof]   lane mode: %llu batches, %.1f locations/batch, %.0f cycles/batch (%.1f%% of kernel cycles); warp mode: %llu calls, %.0f cycles/call (%.1f%%)\n",
+                h[7], h[7] ? (double)h[8] / h[7] : 0.0, h[7] ? (double)h[6] / h[7] : 0.0, 100 * h[6] / tot, h[10], h[10] ? (double)h[9] / h[10] : 0.0, 100 * h[9] / tot);
     }
     return 0;
 }

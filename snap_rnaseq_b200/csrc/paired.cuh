@@ -105,6 +105,7 @@ struct PairedSm {
 struct LaneLookup {
     const uint32_t *hits;
     uint32_t nh, cur, so, sid;
+    uint32_t cur_val, prev_val;  // hits[cur] (if cur < nh) and hits[cur-1] (if cur > 0), kept in registers
     uint32_t words;  // hit-list words this lane has read (accounting for the roofline figure)
     bool act;
 };
@@ -120,6 +121,9 @@ __device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, int w, int
     l.sid = l.act ? sm->setid[w][d][lane] : 0;
     l.cur = 0;
     l.words = 0;
+    l.cur_val = l.nh > 0 ? __ldg(&l.hits[0]) : 0;
+    l.prev_val = 0;
+    l.words += l.nh > 0;
     return l;
 }
 
@@ -146,8 +150,7 @@ __device__ __forceinline__ bool pick_max(bool ok, uint32_t val, uint32_t so, uin
 __device__ __forceinline__ bool hs_first(LaneLookup &l, uint32_t *most_recent, uint32_t *loc, uint32_t *so)
 {
     bool ok = l.act && l.nh > 0;
-    uint32_t val = ok ? __ldg(&l.hits[0]) - l.so : 0;
-    l.words += ok;
+    uint32_t val = ok ? l.cur_val - l.so : 0;
     *loc = 0;
     if (!pick_max(ok, val, l.so, loc, so)) return false;
     *most_recent = *loc;
@@ -165,16 +168,22 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
         while (lo <= hi) {
             int probe = (lo + hi) / 2;
             uint32_t h = __ldg(&l.hits[probe]);
+            uint32_t hp = probe == 0 ? 0 : __ldg(&l.hits[probe - 1]);
             l.words += 2;
-            if (h <= want && (probe == 0 || __ldg(&l.hits[probe - 1]) > want)) {
+            if (h <= want && (probe == 0 || hp > want)) {
                 found = true;
                 val = h - l.so;
                 l.cur = (uint32_t)probe;
+                l.cur_val = h;
+                l.prev_val = hp;
                 break;
             }
             if (h > want) lo = probe + 1; else hi = probe - 1;
         }
-        if (lo > hi) l.cur = l.nh;
+        if (lo > hi) {
+            l.cur = l.nh;
+            l.prev_val = l.nh > 0 ? __ldg(&l.hits[l.nh - 1]) : 0;
+        }
     }
     if (!pick_max(found, val, l.so, loc, so)) return false;
     *most_recent = *loc;
@@ -187,12 +196,14 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
     bool ok = false;
     uint32_t val = 0;
     if (l.act) {
-        if (l.cur != l.nh && __ldg(&l.hits[l.cur]) - l.so == *most_recent) l.cur++;
-        l.words += 2;
+        if (l.cur != l.nh && l.cur_val - l.so == *most_recent) {
+            l.cur++;
+            l.prev_val = l.cur_val;
+            if (l.cur != l.nh) { l.cur_val = __ldg(&l.hits[l.cur]); l.words++; }
+        }
         if (l.cur != l.nh) {
-            uint32_t h = __ldg(&l.hits[l.cur]);
-            val = h - l.so;
-            ok = h >= l.so;
+            val = l.cur_val - l.so;
+            ok = l.cur_val >= l.so;
         }
     }
     if (!pick_max(ok, val, l.so, loc, so)) return false;
@@ -207,8 +218,7 @@ __device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, const 
     bool miss = false;
     if (l.act) {
         uint32_t target = most_recent + l.so;
-        bool close = (l.cur != l.nh && is_within(__ldg(&l.hits[l.cur]), target, merge_dist)) ||
-                     (l.cur != 0 && is_within(__ldg(&l.hits[l.cur - 1]), target, merge_dist));
+        bool close = (l.cur != l.nh && is_within(l.cur_val, target, merge_dist)) || (l.cur != 0 && is_within(l.prev_val, target, merge_dist));
         miss = !close;
     }
     uint32_t best = 0;
@@ -373,14 +383,24 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 }
             }
             uint32_t bp_fewer = hs_best_possible(lf, exh_f, cs_f, mr_f, max_k);
+            // lowest bestPossibleScore among the mates in range (:469-475): scan back from the newest mate, 32 per step
             uint32_t low_mate = max_k + extra;
-            if (lane == 0) {  // lowest bestPossibleScore among mates in range (:469-475); the leader wrote them
-                for (int i = (int)n_mates - 1; i >= 0; i--) {
-                    if (mates[i].loc > f_loc + max_spacing) break;
-                    low_mate = min(low_mate, mates[i].best_possible);
+            __syncwarp();  // the leader's mate records must be visible to the other lanes
+            for (int top = (int)n_mates - 1; top >= 0; top -= 32) {
+                const int i = top - lane;
+                bool stop = false;
+                uint32_t bp = 0xffffffffu;
+                if (i >= 0) {
+                    if (mates[i].loc > f_loc + max_spacing) stop = true; else bp = mates[i].best_possible;
                 }
+                const unsigned stops = __ballot_sync(FULL_MASK, stop);
+                if (stops) {  // lanes beyond the first out-of-range mate do not count
+                    const int first = __ffs((int)stops) - 1;
+                    if (lane >= first) bp = 0xffffffffu;
+                }
+                low_mate = min(low_mate, __reduce_min_sync(FULL_MASK, bp));
+                if (stops) break;
             }
-            low_mate = __shfl_sync(FULL_MASK, low_mate, 0);
             if (low_mate + bp_fewer <= max_k + extra) {
                 if (n_cands >= cfg.cand_cap) return 2;
                 if (lane == 0) {

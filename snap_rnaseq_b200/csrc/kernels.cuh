@@ -63,7 +63,7 @@ __host__ __device__ inline size_t single_warp_shared(uint32_t rl)
     return s;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) single_kernel(const SingleArgs a)
+__global__ void __launch_bounds__(CTA_THREADS, 3) single_kernel(const SingleArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -152,7 +152,7 @@ __host__ __device__ inline size_t paired_warp_shared(uint32_t rl)
     return s;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) paired_kernel(const PairedArgs a)
+__global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();

@@ -110,7 +110,7 @@ __device__ __forceinline__ int lv_rows(const LvStr &s, int16_t *L, int k, int *w
 
 // LandauVishkin<DIR>::computeEditDistance.  q: quality(i) = q[i*qs] or NULL.  All lanes return the same
 // values.  L: LV_CELLS int16 in shared memory private to this warp.
-__device__ int lv_score_warp(const LvStr &s, const uint8_t *q, int qs, int k, const DevIndex &ix, int16_t *L,
+__device__ __noinline__ int lv_score_warp(const LvStr &s, const uint8_t *q, int qs, int k, const DevIndex &ix, int16_t *L,
                              double *match_prob, int *net_indel)
 {
     const int lane = lane_id();
@@ -379,7 +379,7 @@ __device__ __forceinline__ int roll_get(const int16_t *R, int e, int d)
 // column of the full table in HBM scratch (written on the way, read only by the backtrace of successful lanes).
 // k may differ between lanes.  Returns the score or -1.
 template <int DIR>
-__device__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int16_t *R, int16_t *T, const DevIndex &ix,
+__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int16_t *R, int16_t *T, const DevIndex &ix,
                        bool live_in, double *match_prob, int *net_indel)
 {
     int result = -1, win_d = 0;

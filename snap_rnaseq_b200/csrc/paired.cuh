@@ -211,9 +211,10 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
     return true;
 }
 
-// computeBestPossibleScoreForCurrentHit (:901-929); merge_dist = maxK (firstInit(maxSeeds, maxK), :114)
-__device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, const uint8_t *exhausted, int cur_set,
-                                                     uint32_t most_recent, uint32_t merge_dist)
+// computeBestPossibleScoreForCurrentHit (:901-929); merge_dist = maxK (firstInit(maxSeeds, maxK), :114).
+// exh_mine = exhausted[l.sid] and max_exh = max over sets of exhausted[] are constant during phase 2.
+__device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, uint32_t exh_mine, uint32_t max_exh, uint32_t most_recent,
+                                                     uint32_t merge_dist)
 {
     bool miss = false;
     if (l.act) {
@@ -221,12 +222,10 @@ __device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, const 
         bool close = (l.cur != l.nh && is_within(l.cur_val, target, merge_dist)) || (l.cur != 0 && is_within(l.prev_val, target, merge_dist));
         miss = !close;
     }
-    uint32_t best = 0;
-    for (int s = 0; s <= cur_set; s++) {
-        uint32_t c = exhausted[s] + __popc(__ballot_sync(FULL_MASK, miss && l.sid == (uint32_t)s));
-        best = max(best, c);
-    }
-    return best;
+    // misses per disjoint hit set: lanes of the same set that missed find each other with one match
+    const unsigned peers = __match_any_sync(FULL_MASK, miss ? l.sid : 0xffffffffu);
+    const uint32_t mine = miss ? exh_mine + (uint32_t)__popc(peers) : 0u;
+    return max(max_exh, __reduce_max_sync(FULL_MASK, mine));
 }
 
 // leader: the seed schedule of one mate (IntersectingPairedEndAligner.cpp:259-339); every non-N seed is a lookup
@@ -350,6 +349,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         LaneLookup lm = load_lookup(sm, more, dir_of[more]);
         const uint8_t *exh_f = sm->exhausted[fewer][dir_of[fewer]], *exh_m = sm->exhausted[more][dir_of[more]];
         const int cs_f = sm->cur_set[fewer][dir_of[fewer]], cs_m = sm->cur_set[more][dir_of[more]];
+        uint32_t maxexh_f = 0, maxexh_m = 0;
+        for (int q = 0; q <= cs_f; q++) maxexh_f = max(maxexh_f, (uint32_t)exh_f[q]);
+        for (int q = 0; q <= cs_m; q++) maxexh_m = max(maxexh_m, (uint32_t)exh_m[q]);
+        const uint32_t exhl_f = lf.act ? exh_f[lf.sid] : 0, exhl_m = lm.act ? exh_m[lm.sid] : 0;
         uint32_t mr_f = 0, mr_m = 0;  // mostRecentLocationReturned of each set
         uint32_t f_loc, f_off = 0, m_loc, m_off = 0;
         bool out_of_more = false;
@@ -366,7 +369,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 continue;
             }
             while (m_loc + max_spacing >= f_loc && !out_of_more) {
-                uint32_t bp = hs_best_possible(lm, exh_m, cs_m, mr_m, max_k);
+                uint32_t bp = hs_best_possible(lm, exhl_m, maxexh_m, mr_m, max_k);
                 if (n_mates >= cfg.mate_cap) return 2;
                 if (lane == 0) {
                     Mate *m = &mates[n_mates];
@@ -382,7 +385,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     break;
                 }
             }
-            uint32_t bp_fewer = hs_best_possible(lf, exh_f, cs_f, mr_f, max_k);
+            uint32_t bp_fewer = hs_best_possible(lf, exhl_f, maxexh_f, mr_f, max_k);
             // lowest bestPossibleScore among the mates in range (:469-475): scan back from the newest mate, 32 per step
             uint32_t low_mate = max_k + extra;
             __syncwarp();  // the leader's mate records must be visible to the other lanes

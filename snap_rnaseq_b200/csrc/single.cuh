@@ -107,7 +107,7 @@ __device__ __forceinline__ bool substring_ok(const DevIndex &ix, uint32_t offset
 
 // The scoring step shared by BaseAligner::score (BaseAligner.cpp:1158-1242) and
 // IntersectingPairedEndAligner::scoreLocation (:755-841).  All lanes; uniform results.
-__device__ int score_location_warp(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset,
+__device__ __noinline__ int score_location_warp(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset,
                                    int score_limit, bool single_variant, uint8_t *W, int16_t *L, double *match_prob,
                                    int *loc_offset)
 {
@@ -160,7 +160,7 @@ __device__ int score_location_warp(const DevIndex &ix, const ReadView &v, int di
 // interleaved rolling rows (shared) and T its column of the full table (HBM scratch).  Lanes whose genome window is not entirely inside the genome return SC_NONE_LANE and are
 // left to score_location_warp.  All 32 lanes must call this together.
 #define SC_NONE_LANE (-3)
-__device__ void score_location_lane(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset, int K,
+__device__ __noinline__ void score_location_lane(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset, int K,
                                     int16_t *R, int16_t *T, bool active, int *score, double *match_prob, int *loc_offset)
 {
     const uint32_t rlen = v.len;
@@ -363,7 +363,7 @@ __device__ __forceinline__ bool after_score(const SingleCfg &cfg, const SingleSc
 struct MapqFixList { MapqFix *items; uint32_t *count; uint32_t cap; };
 
 // BaseAligner::score (BaseAligner.cpp:977-1399).  All lanes; returns true when a final answer was produced.
-__device__ bool single_score(const DevIndex &ix, const SingleCfg &cfg, const SingleScratch &sc, SingleSm *sm,
+__device__ __noinline__ bool single_score(const DevIndex &ix, const SingleCfg &cfg, const SingleScratch &sc, SingleSm *sm,
                              const ReadView &v, uint8_t *W, int16_t *L, bool force_in, uint32_t read_index,
                              const MapqFixList &fix, int mapq_divisor)
 {

@@ -899,8 +899,9 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
     int grid = grid_for(paired_kernel, smem, x->sm_count, &per_sm);
     if (n) {
         // small tier
-        cfg.cand_cap = (uint32_t)std::min<uint64_t>(ref_pool, 2048);
-        cfg.mate_cap = (uint32_t)std::min<uint64_t>(ref_pool / 2, 2048);
+        // first tier: ~1.4 MB of candidate records per warp (5 GB at full occupancy) holds all but pathological pairs
+        cfg.cand_cap = (uint32_t)std::min<uint64_t>(ref_pool, 12288);
+        cfg.mate_cap = (uint32_t)std::min<uint64_t>(ref_pool / 2, 12288);
         cfg.anchor_cap = cfg.cand_cap;
         cfg.hard_limit = (cfg.cand_cap == ref_pool && cfg.mate_cap == ref_pool / 2) ? 1 : 0;
         if ((rc = launch_paired(s, p, cfg, grid, nullptr, n))) return rc;

@@ -247,8 +247,9 @@ private:
         std::vector<unsigned> idOff, off;             // n+1
         std::vector<uint8_t> cbases, cquals;          // clipped, what the aligner sees
         std::vector<uint32_t> coff;
+        std::vector<const char *> readGroups;         // Read::getReadGroup(): owned by the reader context, outlives the batch
         ReadStore() { clear(); }
-        void clear() { ids.clear(); bases.clear(); quals.clear(); cbases.clear(); cquals.clear(); idOff.assign(1, 0); off.assign(1, 0); coff.assign(1, 0); }
+        void clear() { ids.clear(); bases.clear(); quals.clear(); cbases.clear(); cquals.clear(); readGroups.clear(); idOff.assign(1, 0); off.assign(1, 0); coff.assign(1, 0); }
         unsigned size() const { return (unsigned)off.size() - 1; }
         void add(Read *r)
         {
@@ -260,11 +261,13 @@ private:
             cbases.insert(cbases.end(), (const uint8_t *)r->getData(), (const uint8_t *)r->getData() + r->getDataLength());
             cquals.insert(cquals.end(), (const uint8_t *)r->getQuality(), (const uint8_t *)r->getQuality() + r->getDataLength());
             coff.push_back((uint32_t)cbases.size());
+            readGroups.push_back(r->getReadGroup());
         }
         void get(unsigned i, Read *r, ReadClippingType clipping)
         {
             r->init(&ids[idOff[i]], idOff[i + 1] - idOff[i], &bases[off[i]], &quals[off[i]], off[i + 1] - off[i]);
             r->clip(clipping);
+            r->setReadGroup(readGroups[i]);
         }
         snapb200_read_batch batch() const
         {

@@ -199,3 +199,33 @@ def write_fastq(path, batch, sim, mate=0):
             s1 = int(st[0] if np.ndim(st) else st) + 1
             e1 = int((st[1] if np.ndim(st) else st)) + len(b)
             f.write(f"@{names[sim['contig'][i]]}_{s1}_{e1}_0:0:0_0:0:0_{i:x}/{mate + 1}\n{b}\n+\n{q}\n".encode())
+
+
+def make_gtf(path, contigs, seed=31, gene_frac=0.03, decoy="chrDecoy"):
+    """Synthetic annotation: a decoy transcript first (its id sorts lowest; the reference dereferences a NULL piece for
+    transcriptome hits that start in the padding before the FIRST transcript), then non-overlapping
+    multi-exon '+'-strand genes (2-6 exons of 150-600 bp, introns 200-2000 bp) over ~gene_frac of each contig."""
+    rng = np.random.default_rng(seed)
+    lines = []
+    attr = 'gene_id "{g}"; transcript_id "{t}"; gene_name "{g}"; transcript_name "{t}";'
+    if decoy in contigs:
+        lines.append("\t".join([decoy, "synth", "exon", "101", "900", ".", "+", ".", attr.format(g="AAAA_decoy", t="AAAA_decoy_t")]))
+    gid = 0
+    for name, seq in contigs.items():
+        if name == decoy:
+            continue
+        pos, budget = 2000, int(len(seq) * gene_frac)
+        while budget > 0 and pos < len(seq) - 12000:
+            n_ex = int(rng.integers(2, 7))
+            g, t = f"G{gid:05d}", f"T{gid:05d}"
+            p = pos
+            for _ in range(n_ex):
+                ln = int(rng.integers(150, 601))
+                lines.append("\t".join([name, "synth", "exon", str(p + 1), str(p + ln), ".", "+", ".", attr.format(g=g, t=t)]))
+                budget -= ln
+                p += ln + int(rng.integers(200, 2001))
+            gid += 1
+            pos = p + int(rng.integers(3000, 30000))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return len(lines)

@@ -1,0 +1,76 @@
+"""End to end through the reference's own command line: `snap-rna` (the compiled reference, CPU) against
+`snap-rna-b200` (the same host code with GpuAlignerExtension + libsnapb200.so) must write the same SAM records.
+Needs a GPU and oracle/_ref (which travels to the GPU box)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from snap_rnaseq_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "snap-rna")
+B200 = os.path.join(ROOT, "oracle", "_ref", "snap-rna-b200")
+
+
+def run(cmd, cwd):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, " ".join(cmd) + "\n" + r.stdout[-3000:]
+    return r.stdout
+
+
+def sam_records(path):
+    recs = [l for l in open(path).read().split("\n") if l and not l.startswith("@")]
+    return sorted(recs)
+
+
+def assert_same(a, b, n):
+    assert len(a) == n and len(b) == n, (len(a), len(b))
+    bad = [(x, y) for x, y in zip(a, b) if x != y]
+    if bad:
+        msg = [f"{len(bad)} of {n} SAM records differ"]
+        for x, y in bad[:6]:
+            fx, fy = x.split("\t"), y.split("\t")
+            diff = [(i, fx[i], fy[i]) for i in range(min(len(fx), len(fy))) if fx[i] != fy[i]]
+            msg.append(f"  {fx[0]} flag {fx[1]}: (field, reference, b200) = {diff[:4]}  nfields {len(fx)}/{len(fy)}")
+        raise AssertionError("\n".join(msg))
+
+
+@pytest.fixture(scope="module")
+def workspace(tmp_path_factory):
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("oracle/_ref/snap-rna(-b200) not built")
+    d = str(tmp_path_factory.mktemp("dropin"))
+    contigs = {"chrDecoy": synth.random_contigs([2000], seed=99)["chr1"]}
+    contigs.update(synth.random_contigs([300000, 200000], seed=20))
+    synth.inject_repeats({k: v for k, v in contigs.items() if k != "chrDecoy"}, frac=0.04, seed=21, max_len=800, max_copies=60)
+    synth.write_fasta(os.path.join(d, "g.fa"), contigs)
+    synth.make_gtf(os.path.join(d, "a.gtf"), contigs)
+    run([REF, "index", "g.fa", "gidx", "-s", "20", "-t1"], d)
+    run([REF, "transcriptome", "a.gtf", "g.fa", "tidx", "-t1", "-s", "20"], d)
+    real = {k: v for k, v in contigs.items() if k != "chrDecoy"}
+    sim1 = synth.simulate(real, 4000, 100, err=0.02, seed=5, junk_frac=0.01)
+    synth.write_fastq(os.path.join(d, "s.fq"), sim1["batches"][0], sim1)
+    sim2 = synth.simulate(real, 4000, 100, paired=True, err=0.02, seed=6, junk_frac=0.01)
+    synth.write_fastq(os.path.join(d, "p1.fq"), sim2["batches"][0], sim2, mate=0)
+    synth.write_fastq(os.path.join(d, "p2.fq"), sim2["batches"][1], sim2, mate=1)
+    return d
+
+
+def test_single_end_sam_identical(workspace):
+    d = workspace
+    run([REF, "single", "gidx", "tidx", "a.gtf", "s.fq", "-o", "ref_s.sam", "-t", "2"], d)
+    run([B200, "single", "gidx", "tidx", "a.gtf", "s.fq", "-o", "gpu_s.sam", "-t", "2"], d)
+    a, b = sam_records(os.path.join(d, "ref_s.sam")), sam_records(os.path.join(d, "gpu_s.sam"))
+    assert_same(a, b, 4000)
+
+
+def test_paired_end_sam_identical(workspace):
+    d = workspace
+    run([REF, "paired", "gidx", "tidx", "a.gtf", "p1.fq", "p2.fq", "-o", "ref_p.sam", "-t", "2"], d)
+    run([B200, "paired", "gidx", "tidx", "a.gtf", "p1.fq", "p2.fq", "-o", "gpu_p.sam", "-t", "2"], d)
+    a, b = sam_records(os.path.join(d, "ref_p.sam")), sam_records(os.path.join(d, "gpu_p.sam"))
+    assert_same(a, b, 8000)

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -100,8 +101,12 @@ struct snapb200_index {
     cudaStream_t stream = nullptr;
     // scratch shared by the synchronous batch entry points (sessions own theirs)
     unsigned long long *stats = nullptr;  // SNAPB200_STATS_WORDS counters in HBM
+    // The synchronous *_batch entry points run on one of two internal sessions (own stream + device buffers each), so two
+    // host threads (the reference runs -t N of them) can have batches in flight at once: the tail of one batch's kernels
+    // overlaps the head of the other's.  A third concurrent caller waits.
     struct snapb200_session *batch_session[2] = {nullptr, nullptr};
-    std::mutex batch_mutex;  // the synchronous *_batch entry points share the two sessions above: one caller at a time
+    std::mutex batch_mutex[2];
+    std::atomic<unsigned> batch_rr{0};
 };
 
 static int upload(snapb200_index *x, const void *src, size_t bytes, void **dst, size_t pad_before = 0, size_t pad_after = 0, int pad_byte = 0)
@@ -1022,7 +1027,17 @@ extern "C" int snapb200_session_main_kernel_ms(const snapb200_session *s, float 
 }
 
 // ---- synchronous batch entry points: chunked, double-buffered over two sessions ------------------------------
-static const uint32_t CHUNK = 1u << 18;
+static const uint32_t CHUNK_DEFAULT = 1u << 20;
+// reads (pairs) per internal launch group; SNAPB200_CHUNK overrides it (used by the tests to force multi-chunk batches)
+static uint32_t chunk_size()
+{
+    const char *e = getenv("SNAPB200_CHUNK");
+    if (e) {
+        long v = atol(e);
+        if (v >= 1024 && v <= (1l << 24)) return (uint32_t)v;
+    }
+    return CHUNK_DEFAULT;
+}
 
 static snapb200_read_batch sub_batch(const snapb200_read_batch *b, uint32_t lo, uint32_t hi, std::vector<uint32_t> &off_store)
 {
@@ -1041,17 +1056,30 @@ static snapb200_read_batch sub_batch(const snapb200_read_batch *b, uint32_t lo, 
     return r;
 }
 
-static int get_batch_sessions(snapb200_index *idx, snapb200_session **s)
-{
-    for (int i = 0; i < 2; i++) {
-        if (!idx->batch_session[i]) {
-            int rc = snapb200_session_create(idx, CHUNK, SNAPB200_MAX_READ_LENGTH, &idx->batch_session[i]);
+// RAII: one of the index's two internal sessions, locked for the duration of a *_batch call
+struct BatchSlot {
+    snapb200_index *idx;
+    int slot = -1;
+    snapb200_session *s = nullptr;
+    explicit BatchSlot(snapb200_index *i) : idx(i)
+    {
+        for (int k = 0; k < 2 && slot < 0; k++) if (idx->batch_mutex[k].try_lock()) slot = k;
+        if (slot < 0) {
+            slot = (int)(idx->batch_rr.fetch_add(1) & 1);
+            idx->batch_mutex[slot].lock();
+        }
+    }
+    int open()
+    {
+        if (!idx->batch_session[slot]) {
+            int rc = snapb200_session_create(idx, CHUNK_DEFAULT, SNAPB200_MAX_READ_LENGTH, &idx->batch_session[slot]);
             if (rc) return rc;
         }
-        s[i] = idx->batch_session[i];
+        s = idx->batch_session[slot];
+        return 0;
     }
-    return 0;
-}
+    ~BatchSlot() { idx->batch_mutex[slot].unlock(); }
+};
 
 static int single_batch_impl(snapb200_index *idx, const snapb200_single_params *params, const snapb200_read_batch *reads,
                              snapb200_single_result *results, int32_t *hit_counts, uint32_t *hit_locations, uint8_t *hit_rcs,
@@ -1061,26 +1089,17 @@ static int single_batch_impl(snapb200_index *idx, const snapb200_single_params *
     uint32_t m;
     int rc = validate_batch(reads, &m);
     if (rc) return rc;
-    std::lock_guard<std::mutex> guard(idx->batch_mutex);
-    snapb200_session *s[2];
-    if ((rc = get_batch_sessions(idx, s))) return rc;
+    BatchSlot slot(idx);
+    if ((rc = slot.open())) return rc;
+    snapb200_session *cur = slot.s;
     const uint32_t n = reads->n;
     const uint32_t mh = params->max_hits_to_get;
-    std::vector<uint32_t> off_store[2];
-    // upload chunk c+1 while chunk c computes: uploads are asynchronous on the other session's stream
-    uint32_t n_chunks = (n + CHUNK - 1) / CHUNK;
-    if (n_chunks) {
-        snapb200_read_batch sb = sub_batch(reads, 0, std::min(n, CHUNK), off_store[0]);
-        if ((rc = snapb200_session_upload(s[0], 0, &sb))) return rc;
-    }
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
-        snapb200_session *cur = s[c & 1];
-        if (c + 1 < n_chunks) {
-            const uint32_t lo2 = hi, hi2 = std::min(n, lo2 + CHUNK);
-            snapb200_read_batch sb = sub_batch(reads, lo2, hi2, off_store[(c + 1) & 1]);
-            if ((rc = snapb200_session_upload(s[(c + 1) & 1], 0, &sb))) return rc;
-        }
+    std::vector<uint32_t> off_store;
+    const uint32_t CHUNK = chunk_size();
+    for (uint32_t lo = 0; lo < n; lo += CHUNK) {
+        const uint32_t hi = std::min(n, lo + CHUNK);
+        snapb200_read_batch sb = sub_batch(reads, lo, hi, off_store);
+        if ((rc = snapb200_session_upload(cur, 0, &sb))) return rc;
         if ((rc = snapb200_session_run_single(cur, params))) return rc;
         if ((rc = snapb200_session_download_single(cur, results + lo))) return rc;
         if (mh) {
@@ -1120,26 +1139,18 @@ extern "C" int snapb200_paired_batch(snapb200_index *idx, const snapb200_paired_
     uint32_t m0, m1;
     int rc;
     if ((rc = validate_batch(reads0, &m0)) || (rc = validate_batch(reads1, &m1))) return rc;
-    std::lock_guard<std::mutex> guard(idx->batch_mutex);
-    snapb200_session *s[2];
-    if ((rc = get_batch_sessions(idx, s))) return rc;
+    BatchSlot slot(idx);
+    if ((rc = slot.open())) return rc;
+    snapb200_session *cur = slot.s;
     const uint32_t n = reads0->n;
-    std::vector<uint32_t> off_store[2][2];
-    uint32_t n_chunks = (n + CHUNK - 1) / CHUNK;
-    auto up = [&](uint32_t c) -> int {
-        const uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
-        snapb200_read_batch a = sub_batch(reads0, lo, hi, off_store[c & 1][0]);
-        snapb200_read_batch b = sub_batch(reads1, lo, hi, off_store[c & 1][1]);
-        int r = snapb200_session_upload(s[c & 1], 0, &a);
-        if (!r) r = snapb200_session_upload(s[c & 1], 1, &b);
-        return r;
-    };
-    if (n_chunks && (rc = up(0))) return rc;
+    std::vector<uint32_t> off_store[2];
     int limit_rc = 0;
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t lo = c * CHUNK;
-        snapb200_session *cur = s[c & 1];
-        if (c + 1 < n_chunks && (rc = up(c + 1))) return rc;
+    const uint32_t CHUNK = chunk_size();
+    for (uint32_t lo = 0; lo < n; lo += CHUNK) {
+        const uint32_t hi = std::min(n, lo + CHUNK);
+        snapb200_read_batch a = sub_batch(reads0, lo, hi, off_store[0]);
+        snapb200_read_batch b = sub_batch(reads1, lo, hi, off_store[1]);
+        if ((rc = snapb200_session_upload(cur, 0, &a)) || (rc = snapb200_session_upload(cur, 1, &b))) return rc;
         if ((rc = snapb200_session_run_paired(cur, params))) return rc;
         rc = snapb200_session_download_paired(cur, results + lo);
         if (rc == SNAPB200_ERR_LIMIT) limit_rc = rc; else if (rc) return rc;
@@ -1158,10 +1169,9 @@ extern "C" int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_bat
     if (rc) return rc;
     const uint32_t n = reads->n;
     if (!n) return 0;
-    std::lock_guard<std::mutex> guard(idx->batch_mutex);
-    snapb200_session *s[2];
-    if ((rc = get_batch_sessions(idx, s))) return rc;
-    snapb200_session *ss = s[0];
+    BatchSlot slot(idx);
+    if ((rc = slot.open())) return rc;
+    snapb200_session *ss = slot.s;
     if ((rc = snapb200_session_upload(ss, 0, reads))) return rc;
     DevBuf d_loc, d_dir, d_cig, d_ed;
     do {

@@ -175,11 +175,15 @@ def test_large_batch_properties(cuda, handle):
     """At a size the oracle would take too long for: chunking/order independence and determinism."""
     from tests_genome import small_genome
     contigs = small_genome()
-    n = 300_000  # > one 262144-read chunk: exercises the double-buffered pipeline
+    n = 300_000
     sim = synth.simulate(contigs, n, 100, paired=True, err=0.02, seed=5)
     b0, b1 = sim["batches"]
     pp = A.paired_defaults()
-    full = cuda.paired(handle, pp, b0, b1)
+    os.environ["SNAPB200_CHUNK"] = "262144"  # two internal launch groups
+    try:
+        full = cuda.paired(handle, pp, b0, b1)
+    finally:
+        del os.environ["SNAPB200_CHUNK"]
     again = cuda.paired(handle, pp, b0, b1)
     assert_records_equal(full, again, what="determinism")
     lo, hi = 262000, 262400  # straddles the chunk boundary
@@ -231,3 +235,28 @@ def test_index_build_equivalence(cuda, port, tmp_path, seed_len, golden, small_i
             P.check_golden_single(cuda, h, golden)
     finally:
         cuda.close_index(h)
+
+
+def test_concurrent_callers(cuda, handle, golden):
+    """Two host threads in the C ABI at once (as the reference's -t N worker threads would be): each gets its own
+    internal session; results must be those of the serial calls."""
+    import threading
+
+    from conftest import batch_from
+    b0, b1 = batch_from(golden, "pair0"), batch_from(golden, "pair1")
+    bs = batch_from(golden, "single")
+    out = {}
+
+    def work(tag):
+        for i in range(3):
+            out[(tag, i, "p")] = cuda.paired(handle, A.paired_defaults(), b0, b1)
+            out[(tag, i, "s")] = cuda.single(handle, A.single_defaults(), bs)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert len(out) == 18
+    for k, v in out.items():
+        assert_records_equal(golden["paired_res" if k[2] == "p" else "single_res"], v, what=f"concurrent {k}")

@@ -271,7 +271,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(L, h, b0, b1, params, out)
-        print(json.dumps(line))
+        emit(line)
     for s_ in sessions:
         s_.close()
     L.close_index(h)
@@ -333,7 +333,8 @@ def run_reference(args):
             O.ref_build_index(fa, d, seed_len=20, threads=cores)
             impl, kind = O.ref(threads=cores), "reference"
         else:
-            raise SystemExit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not present on this box"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref not present on this box"})
+            return
         hc = impl.load_index(d)
         for _ in range(min(args.warmup, 1)):
             impl.paired(hc, params, b0.slice(0, 20000), b1.slice(0, 20000))
@@ -350,10 +351,32 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{n} pairs per step, {cores} threads, ChimericPairedEndAligner::align only (no I/O)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print (NCCL's version banner goes to stdout) is sent to stderr; the one JSON line is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -269,6 +269,10 @@ def run_ours(args):
                                 "aligned_as_pairs": int(tot[6]), "locations_scored": int(tot[9]), "lookups": int(tot[8])},
             "aligned_fraction": float((out["status"] != 0).mean()),
         }
+        try:
+            line["probe_stage"] = probe_stage(L, h, bases.size)
+        except Exception as e:  # diagnostics only
+            line["probe_stage"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(L, h, b0, b1, params, out)
         emit(line)
@@ -277,6 +281,26 @@ def run_ours(args):
     L.close_index(h)
     if world > 1:
         dist.destroy_process_group()
+
+
+def probe_stage(L, h, n_bases):
+    """Stage 2 (index probes) in isolation against the random-32-byte-sector gather ceiling measured in the same run
+    (MEASURED_PEAKS.json only has the sequential copy peak).  See scripts/probe_roofline.py / profiles/README.md."""
+    info = L.index_info(h)
+    table_bytes = int(info.hash_table_entries) * 12
+    rng = np.random.default_rng(3)
+    n = 1 << 24
+    pos = rng.integers(500, n_bases - 600, size=n, dtype=np.uint32)
+    ms, slots, counts, hits, gms = C.c_float(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+    L._check(L.lib.snapb200_probe_bench(h, C.c_uint32(n), pos.ctypes.data_as(C.c_void_p), C.c_uint32(5), C.byref(ms), C.byref(slots),
+                                        C.byref(counts), C.byref(hits)), "probe_bench")
+    L._check(L.lib.snapb200_gather_bench(C.c_int(L.device), C.c_uint64(table_bytes), C.c_uint32(n), C.c_uint32(5), C.byref(gms)), "gather_bench")
+    sectors = slots.value + counts.value
+    ach = sectors / (ms.value * 1e-3)
+    peak = n / (gms.value * 1e-3)
+    return {"kernel": "probe_bench_kernel (lookup_seed, one lane per seed)", "lookups": n, "ms": ms.value, "lookups_per_s": n / (ms.value * 1e-3),
+            "table_slots_per_lookup": slots.value / n, "bound": "hbm random 32B sectors", "achieved": ach, "peak": peak, "unit": "sectors/s",
+            "frac": ach / peak, "peak_source": f"random-sector gather over {table_bytes >> 20} MiB measured in this run (snapb200_gather_bench)"}
 
 
 def cpu_baseline(L, h, b0, b1, params, gpu_out):

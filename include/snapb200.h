@@ -226,6 +226,17 @@ int snapb200_lv_cigar_batch(int device, uint32_t n, const uint32_t *text_offsets
 int snapb200_lookup_seed_batch(snapb200_index *idx, uint32_t n, const uint8_t *seeds, uint32_t max_out,
                                uint32_t *n_hits, uint32_t *hits);
 
+/* Diagnostics for the roofline of stage 2 (index probes) in isolation.
+ * snapb200_probe_bench: n seeds taken from the resident genome at `positions[i]` (seed_len bases each; positions with a
+ *   non-ACGT base count as a lookup of nothing) are packed and looked up exactly as the aligners do -- one lane per seed,
+ *   both directions resolved, overflow count words read -- `iters` times; returns the CUDA-event time of one pass and the
+ *   totals of one pass: table slots examined (12 B each), overflow count words read (4 B each), hits reported.
+ * snapb200_gather_bench: the ceiling to compare against: `n` independent uniformly random 32-byte sector reads over a
+ *   `bytes`-sized buffer, one per thread, `iters` passes; returns the time of one pass. */
+int snapb200_probe_bench(snapb200_index *idx, uint32_t n, const uint32_t *positions, uint32_t iters, float *ms_per_pass,
+                         uint64_t *slots_examined, uint64_t *count_words, uint64_t *hits_reported);
+int snapb200_gather_bench(int device, uint64_t bytes, uint32_t n, uint32_t iters, float *ms_per_pass);
+
 /* computeMAPQ (SNAPLib/mapq.h:32-65), evaluated on the device the way the aligner kernels do. */
 int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, const double *p_best,
                         const int32_t *score, const int32_t *popular_seeds_skipped, int32_t *mapq);

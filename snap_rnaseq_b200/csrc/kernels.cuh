@@ -413,3 +413,53 @@ __global__ void mapq_kernel(uint32_t n, const double *p_all, const double *p_bes
     mapq[i] = compute_mapq_dev(p_all[i], p_best[i], score[i], popular[i], &ni);
     near_integer[i] = ni;
 }
+
+// ---- stage-2 roofline diagnostics -----------------------------------------------------------------------------------
+// setup (not timed): pack the seed at each genome position the way stage 1 does from the staged read
+__global__ void probe_pack_kernel(const DevIndex ix, uint32_t n, const uint32_t *positions, ulonglong2 *packed)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t f = 0, r = 0;
+    bool ok = pack_seed(ix.genome + positions[i], ix.seed_len, &f, &r);
+    packed[i] = ok ? make_ulonglong2(f, r) : make_ulonglong2(~0ull, ~0ull);
+}
+
+// timed: stage 2 alone -- one lane per packed seed, both directions resolved, overflow count words read
+__global__ void probe_bench_kernel(const DevIndex ix, uint32_t n, const ulonglong2 *packed, unsigned long long *totals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t probes = 0, counts = 0, hits = 0;
+    if (i < n) {
+        ulonglong2 s = packed[i];
+        if (s.x != ~0ull) {
+            HitList hl[2] = {{nullptr, 0}, {nullptr, 0}};
+            lookup_seed(ix, s.x, s.y, hl, &probes);
+            counts = (hl[0].n > 1) + (hl[1].n > 1 && s.x != s.y);
+            hits = hl[0].n + hl[1].n;
+        }
+    }
+    // block-level totals: same-address atomics are ~1 per cycle at L2, so one set per block, not per warp
+    __shared__ unsigned int blk[3];
+    if (threadIdx.x < 3) blk[threadIdx.x] = 0;
+    __syncthreads();
+    probes = __reduce_add_sync(FULL_MASK, probes);
+    counts = __reduce_add_sync(FULL_MASK, counts);
+    hits = __reduce_add_sync(FULL_MASK, hits);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&blk[0], probes); atomicAdd(&blk[1], counts); atomicAdd(&blk[2], hits); }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(totals + threadIdx.x, (unsigned long long)blk[threadIdx.x]);
+}
+
+__global__ void gather_bench_kernel(const uint4 *buf, unsigned long long n_sectors, uint32_t n, uint32_t salt, unsigned long long *sink)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // one uniformly random 32-byte sector per thread (two 16-byte loads of the same sector)
+    unsigned long long h = ((unsigned long long)i + 1) * 0x9E3779B97F4A7C15ull + (unsigned long long)salt * 0xD1B54A32D192ED03ull;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    unsigned long long sector = h % n_sectors;
+    uint4 a = __ldg(buf + sector * 2), b = __ldg(buf + sector * 2 + 1);
+    unsigned x = a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
+    if (x == 0x12345678u) atomicAdd(sink, 1ull);  // keeps the loads alive
+}

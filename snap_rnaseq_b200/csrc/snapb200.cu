@@ -1353,6 +1353,78 @@ extern "C" int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, 
     return rc;
 }
 
+// ---- stage-2 roofline diagnostics ------------------------------------------------------------------------------------------
+extern "C" int snapb200_probe_bench(snapb200_index *idx, uint32_t n, const uint32_t *positions, uint32_t iters, float *ms_per_pass,
+                                    uint64_t *slots_examined, uint64_t *count_words, uint64_t *hits_reported)
+{
+    if (!idx || !positions || !n || !iters || !ms_per_pass) return set_error(SNAPB200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    for (uint32_t i = 0; i < n; i++)
+        if ((uint64_t)positions[i] + idx->dev.seed_len > idx->dev.n_bases) return set_error(SNAPB200_ERR_ARG, "position %u out of range", positions[i]);
+    DevBuf d_pos, d_tot, d_packed;
+    int rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if ((rc = d_pos.ensure((size_t)n * 4)) || (rc = d_tot.ensure(32)) || (rc = d_packed.ensure((size_t)n * 16))) break;
+        cudaMemcpyAsync(d_pos.p, positions, (size_t)n * 4, cudaMemcpyHostToDevice, idx->stream);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int T = 256;
+        probe_pack_kernel<<<(n + T - 1) / T, T, 0, idx->stream>>>(idx->dev, n, d_pos.as<uint32_t>(), d_packed.as<ulonglong2>());
+        probe_bench_kernel<<<(n + T - 1) / T, T, 0, idx->stream>>>(idx->dev, n, d_packed.as<ulonglong2>(), d_tot.as<unsigned long long>());  // warm-up
+        cudaMemsetAsync(d_tot.p, 0, 32, idx->stream);
+        cudaEventRecord(e0, idx->stream);
+        for (uint32_t it = 0; it < iters; it++)
+            probe_bench_kernel<<<(n + T - 1) / T, T, 0, idx->stream>>>(idx->dev, n, d_packed.as<ulonglong2>(), d_tot.as<unsigned long long>());
+        cudaEventRecord(e1, idx->stream);
+        cudaError_t e = cudaStreamSynchronize(idx->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "probe_bench_kernel: %s", cudaGetErrorString(e)); break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_pass = ms / iters;
+        unsigned long long tot[4];
+        cudaMemcpy(tot, d_tot.p, 32, cudaMemcpyDeviceToHost);
+        if (slots_examined) *slots_examined = tot[0] / iters;
+        if (count_words) *count_words = tot[1] / iters;
+        if (hits_reported) *hits_reported = tot[2] / iters;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    d_pos.release(); d_tot.release(); d_packed.release();
+    return rc;
+}
+
+extern "C" int snapb200_gather_bench(int device, uint64_t bytes, uint32_t n, uint32_t iters, float *ms_per_pass)
+{
+    snapb200_index *x;
+    int rc = tables_for(device, &x);
+    if (rc) return rc;
+    if (bytes < 4096 || !n || !iters || !ms_per_pass) return set_error(SNAPB200_ERR_ARG, "bad argument");
+    DevBuf buf, sink;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if ((rc = buf.ensure(bytes)) || (rc = sink.ensure(8))) break;
+        cudaMemsetAsync(buf.p, 0x5a, bytes, x->stream);
+        cudaMemsetAsync(sink.p, 0, 8, x->stream);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int T = 256;
+        const unsigned long long n_sectors = bytes / 32;
+        gather_bench_kernel<<<(n + T - 1) / T, T, 0, x->stream>>>(buf.as<uint4>(), n_sectors, n, 0, sink.as<unsigned long long>());
+        cudaEventRecord(e0, x->stream);
+        for (uint32_t it = 0; it < iters; it++)
+            gather_bench_kernel<<<(n + T - 1) / T, T, 0, x->stream>>>(buf.as<uint4>(), n_sectors, n, it + 1, sink.as<unsigned long long>());
+        cudaEventRecord(e1, x->stream);
+        cudaError_t e = cudaStreamSynchronize(x->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "gather_bench_kernel: %s", cudaGetErrorString(e)); break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_pass = ms / iters;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    buf.release(); sink.release();
+    return rc;
+}
+
 // ---- statistics -----------------------------------------------------------------------------------------------------
 extern "C" int snapb200_stats_get(snapb200_index *idx, snapb200_stats *out)
 {

@@ -39,9 +39,10 @@ CPU_SAMPLE_PAIRS = 200_000
 
 
 def workload_config(n_gpus, pairs):
-    return {"workload": "C2: snap paired, 100 Mbp repeat-injected synthetic genome (4x25 Mbp), seed 20, 2x100bp WGsim pairs e=2%",
+    mbp = sum(GENOME_CONTIGS) // 1_000_000
+    return {"workload": f"{'C2: ' if mbp == 100 else ''}snap paired, {mbp} Mbp repeat-injected synthetic genome ({len(GENOME_CONTIGS)}x25 Mbp), seed 20, 2x100bp WGsim pairs e=2%",
             "pairs_per_step_per_gpu": pairs, "read_len": READ_LEN, "options": "-d 15 -n 8 -h 16000 -H 16000 -s 50 1000 -D 2",
-            "parallelism": f"reads sharded over {n_gpus} GPU(s), index replicated; 2 host threads / 2 streams per GPU keep two batches in flight", "l2": "inputs larger than L2 (1.76 GB index + genome, 0.4 GB batch)"}
+            "parallelism": f"reads sharded over {n_gpus} GPU(s), index replicated; 2 host threads / 2 streams per GPU keep two batches in flight", "l2": "inputs larger than L2 (index + genome >= 1.76 GB, 0.4 GB batch per step)"}
 
 
 def make_genome():
@@ -408,7 +409,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--genome-mbp", type=int, default=100, help="synthetic genome size (contigs of 25 Mbp); 100 = the C2 workload")
     args = ap.parse_args()
+    if args.genome_mbp != 100:
+        global GENOME_CONTIGS
+        GENOME_CONTIGS = [25_000_000] * max(1, args.genome_mbp // 25)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

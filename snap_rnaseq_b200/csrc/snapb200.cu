@@ -157,8 +157,10 @@ static int finish_index(snapb200_index *x)
 
 static int make_index(int device, uint32_t seed_len, uint32_t padding, uint32_t n_tables, const uint64_t *table_sizes,
                       const void *tables, const uint32_t *overflow, uint32_t overflow_words, const uint8_t *bases,
-                      uint32_t n_bases, const uint32_t *piece_offsets, uint32_t n_pieces, snapb200_index **out)
+                      uint32_t n_bases, const uint32_t *piece_offsets, uint32_t n_pieces, snapb200_index **out,
+                      void *adopt_tables = nullptr, void *adopt_overflow = nullptr)
 {
+    // adopt_*: device allocations (from the device-side builder) to take over instead of uploading host copies
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return set_error(SNAPB200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -178,13 +180,21 @@ static int make_index(int device, uint32_t seed_len, uint32_t padding, uint32_t 
     void *p;
     int rc = 0;
     do {
-        if ((rc = upload(x, tables, total * sizeof(HtEntry), &p))) break;
+        if (adopt_tables) {
+            x->allocs.push_back(adopt_tables);
+            x->info.device_bytes += total * sizeof(HtEntry);
+            p = adopt_tables;
+        } else if ((rc = upload(x, tables, total * sizeof(HtEntry), &p))) break;
         x->dev.tables = (const HtEntry *)p;
         if ((rc = upload(x, start.data(), n_tables * 8, &p))) break;
         x->dev.table_start = (const uint64_t *)p;
         if ((rc = upload(x, table_sizes, n_tables * 8, &p))) break;
         x->dev.table_size = (const uint64_t *)p;
-        if ((rc = upload(x, overflow, (size_t)overflow_words * 4, &p, 0, 16))) break;
+        if (adopt_overflow) {
+            x->allocs.push_back(adopt_overflow);
+            x->info.device_bytes += (size_t)overflow_words * 4;
+            p = adopt_overflow;
+        } else if ((rc = upload(x, overflow, (size_t)overflow_words * 4, &p, 0, 16))) break;
         x->dev.overflow = (const uint32_t *)p;
         if ((rc = upload(x, bases, n_bases, &p, GENOME_PAD, GENOME_PAD, 'n'))) break;
         x->dev.genome = (const uint8_t *)p;
@@ -301,6 +311,7 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
     if (!bases || !out || (n_pieces && !piece_offsets)) return set_error(SNAPB200_ERR_ARG, "null argument");
     if (seed_len < 16 || seed_len > 25) return set_error(SNAPB200_ERR_ARG, "seed length %u unsupported (16..25)", seed_len);
     if (n_bases > 0xfffffff0u || n_bases <= seed_len + 1) return set_error(SNAPB200_ERR_ARG, "genome size %u out of range", n_bases);
+    if (n_bases >= 0x7fffffffu) return set_error(SNAPB200_ERR_ARG, "the device index builder sorts at most 2^31-1 positions in one pass (genome of %u bases); build with the reference's indexer and use snapb200_index_open", n_bases);
     if (!(slack >= 0.05)) slack = 0.3;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(SNAPB200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -318,8 +329,6 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
     uint64_t *d_tstart = nullptr, *d_tsize = nullptr;
     int rc = 0;
     std::vector<uint64_t> sizes(n_tables), starts(n_tables), counts(n_tables);
-    std::vector<char> h_tables;
-    std::vector<uint32_t> h_overflow;
     uint32_t overflow_words = 0;
     do {
         if ((rc = dev_alloc(&d_genome, (size_t)n_bases + 64))) break;
@@ -386,17 +395,18 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
             CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaDeviceSynchronize());
-        // hand the result to the common constructor (keeps one code path for residency)
-        h_tables.resize(total * sizeof(HtEntry));
-        CUDA_TRY(cudaMemcpy(h_tables.data(), d_tables, h_tables.size(), cudaMemcpyDeviceToHost));
-        h_overflow.resize((size_t)overflow_words + 1);
-        if (overflow_words) CUDA_TRY(cudaMemcpy(h_overflow.data(), d_overflow, (size_t)overflow_words * 4, cudaMemcpyDeviceToHost));
     } while (0);
-    void *frees[] = {d_genome, k0, k1, d_nvalid, d_tcount, v0, v1, head, rid, run_start, need, ovf_off, d_overflow, tmp, d_tables, d_tstart, d_tsize};
+    if (!d_overflow && !rc) rc = dev_alloc(&d_overflow, 4);  // a genome without repeated seeds still gets a table to point at
+    void *frees[] = {d_genome, k0, k1, d_nvalid, d_tcount, v0, v1, head, rid, run_start, need, ovf_off, tmp, d_tstart, d_tsize};
     for (void *p : frees) if (p) cudaFree(p);
-    if (rc) return rc;
-    rc = make_index(device, seed_len, chromosome_padding, n_tables, sizes.data(), h_tables.data(), h_overflow.data(), overflow_words, bases, n_bases,
-                    piece_offsets, n_pieces, out);
+    if (rc) {
+        if (d_tables) cudaFree(d_tables);
+        if (d_overflow) cudaFree(d_overflow);
+        return rc;
+    }
+    // the tables and the overflow table stay where they were built; the common constructor adopts them
+    rc = make_index(device, seed_len, chromosome_padding, n_tables, sizes.data(), nullptr, nullptr, overflow_words, bases, n_bases, piece_offsets,
+                    n_pieces, out, d_tables, d_overflow);
     if (!rc) {
         (*out)->table_used = counts;
         for (uint32_t i = 0; i < n_pieces; i++) (*out)->piece_names.push_back(piece_names && piece_names[i] ? piece_names[i] : ("piece" + std::to_string(i)));

@@ -34,13 +34,14 @@ METRIC = "reads_aligned_per_sec"
 UNIT = "reads/s"
 GENOME_CONTIGS = [25_000_000] * 4
 READ_LEN = 100
+ERR_RATE = 0.02
 PAIRS_PER_STEP = 1_000_000          # per GPU
 CPU_SAMPLE_PAIRS = 200_000
 
 
 def workload_config(n_gpus, pairs):
     mbp = sum(GENOME_CONTIGS) // 1_000_000
-    return {"workload": f"{'C2: ' if mbp == 100 else ''}snap paired, {mbp} Mbp repeat-injected synthetic genome ({len(GENOME_CONTIGS)}x25 Mbp), seed 20, 2x100bp WGsim pairs e=2%",
+    return {"workload": f"{'C2: ' if mbp == 100 else ''}snap paired, {mbp} Mbp repeat-injected synthetic genome ({len(GENOME_CONTIGS)}x25 Mbp), seed 20, 2x{READ_LEN}bp WGsim pairs e={ERR_RATE:.0%}",
             "pairs_per_step_per_gpu": pairs, "read_len": READ_LEN, "options": "-d 15 -n 8 -h 16000 -H 16000 -s 50 1000 -D 2",
             "parallelism": f"reads sharded over {n_gpus} GPU(s), index replicated; 2 host threads / 2 streams per GPU keep two batches in flight", "l2": "inputs larger than L2 (index + genome >= 1.76 GB, 0.4 GB batch per step)"}
 
@@ -54,7 +55,7 @@ def make_genome():
 
 def make_pairs(contigs, n, seed):
     from snap_rnaseq_b200 import synth
-    sim = synth.simulate(contigs, n, READ_LEN, paired=True, err=0.02, indel_frac=0.15, seed=seed)
+    sim = synth.simulate(contigs, n, READ_LEN, paired=True, err=ERR_RATE, indel_frac=0.15, seed=seed)
     return sim["batches"]
 
 
@@ -146,7 +147,7 @@ def run_ours(args):
     batches = [(b0, b1), make_pairs(contigs, pairs, seed=2000 + rank)]
     sessions = []
     for (x0, x1) in batches:
-        s_ = S.Session(L, h, pairs, 128)
+        s_ = S.Session(L, h, pairs, max(128, READ_LEN + 8))
         s_.upload(0, x0)
         s_.upload(1, x1)
         s_.sync()
@@ -410,7 +411,12 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--genome-mbp", type=int, default=100, help="synthetic genome size (contigs of 25 Mbp); 100 = the C2 workload")
+    ap.add_argument("--read-len", type=int, default=100, help="read length (C2: 100, C3: 150)")
+    ap.add_argument("--err", type=float, default=0.02, help="per-base mutation rate of the simulated reads (C2: 0.02, C3: 0.01)")
     args = ap.parse_args()
+    global READ_LEN, ERR_RATE
+    READ_LEN = args.read_len
+    ERR_RATE = args.err
     if args.genome_mbp != 100:
         global GENOME_CONTIGS
         GENOME_CONTIGS = [25_000_000] * max(1, args.genome_mbp // 25)

@@ -55,13 +55,23 @@ __global__ void ib_run_start_kernel(const uint32_t *head, const uint32_t *run_id
     if (i < n && head[i]) run_start[run_id_incl[i] - 1] = i;
 }
 
-__global__ void ib_run_need_kernel(const uint32_t *run_start, uint32_t n_runs, uint32_t *need)
+__global__ void ib_run_need_kernel(const uint32_t *run_start, uint32_t n_runs, uint32_t *need, unsigned long long *total)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mine = 0;
     if (r < n_runs) {
         uint32_t c = run_start[r + 1] - run_start[r];
-        need[r] = c >= 2 ? c + 1 : 0;
+        mine = c >= 2 ? c + 1 : 0;
+        need[r] = mine;
     }
+    // 64-bit grand total (block-aggregated) so the caller can refuse inputs whose 32-bit offsets would wrap
+    __shared__ unsigned long long blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    unsigned w = __reduce_add_sync(FULL_MASK, mine);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&blk, (unsigned long long)w);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(total, blk);
 }
 
 __global__ void ib_fill_overflow_kernel(const uint32_t *run_id_incl, const uint32_t *run_start, const uint32_t *ovf_off, const uint32_t *vals,

@@ -311,7 +311,6 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
     if (!bases || !out || (n_pieces && !piece_offsets)) return set_error(SNAPB200_ERR_ARG, "null argument");
     if (seed_len < 16 || seed_len > 25) return set_error(SNAPB200_ERR_ARG, "seed length %u unsupported (16..25)", seed_len);
     if (n_bases > 0xfffffff0u || n_bases <= seed_len + 1) return set_error(SNAPB200_ERR_ARG, "genome size %u out of range", n_bases);
-    if (n_bases >= 0x7fffffffu) return set_error(SNAPB200_ERR_ARG, "the device index builder sorts at most 2^31-1 positions in one pass (genome of %u bases); build with the reference's indexer and use snapb200_index_open", n_bases);
     if (!(slack >= 0.05)) slack = 0.3;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(SNAPB200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -343,9 +342,9 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
         CUDA_TRY(cudaGetLastError());
         size_t tmp_bytes = 0;
         const int end_bit = 2 * (int)seed_len + 1 > 63 ? 64 : 64;  // invalid keys (all ones) must sort last: use all bits
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, (int)n_pos, 0, end_bit);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, (unsigned long long)n_pos, 0, end_bit);
         CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, (int)n_pos, 0, end_bit));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, (unsigned long long)n_pos, 0, end_bit));
         unsigned long long n_valid64 = 0;
         CUDA_TRY(cudaMemcpy(&n_valid64, d_nvalid, 8, cudaMemcpyDeviceToHost));
         const uint32_t n_valid = (uint32_t)n_valid64;
@@ -357,25 +356,35 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
             if ((rc = dev_alloc(&head, n_valid)) || (rc = dev_alloc(&rid, n_valid))) break;
             ib_heads_kernel<<<(n_valid + T - 1) / T, T>>>(k1, n_valid, head);
             tmp_bytes = 0;
-            cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, head, rid, (int)n_valid);
+            cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, head, rid, (unsigned long long)n_valid);
             CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-            CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, rid, (int)n_valid));
+            CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, rid, (unsigned long long)n_valid));
             cudaFree(tmp); tmp = nullptr;
             CUDA_TRY(cudaMemcpy(&n_runs, rid + (n_valid - 1), 4, cudaMemcpyDeviceToHost));
-            if ((rc = dev_alloc(&run_start, (size_t)n_runs + 1)) || (rc = dev_alloc(&need, (size_t)n_runs + 1)) || (rc = dev_alloc(&ovf_off, (size_t)n_runs + 1))) break;
+            // buffers are released as soon as they are dead: at 3.1 Gbp the peak stays near 120 GB of the 180 GB
+            if ((rc = dev_alloc(&run_start, (size_t)n_runs + 1))) break;
             ib_run_start_kernel<<<(n_valid + T - 1) / T, T>>>(head, rid, n_valid, run_start);
             CUDA_TRY(cudaMemcpy(run_start + n_runs, &n_valid, 4, cudaMemcpyHostToDevice));
-            ib_run_need_kernel<<<(n_runs + T - 1) / T, T>>>(run_start, n_runs, need);
+            cudaFree(head); head = nullptr;
+            if ((rc = dev_alloc(&need, (size_t)n_runs + 1)) || (rc = dev_alloc(&ovf_off, (size_t)n_runs + 1))) break;
+            CUDA_TRY(cudaMemset(d_nvalid, 0, 8));
+            ib_run_need_kernel<<<(n_runs + T - 1) / T, T>>>(run_start, n_runs, need, d_nvalid);
             CUDA_TRY(cudaMemset(need + n_runs, 0, 4));
+            unsigned long long need_total = 0;  // 64-bit total first: the 32-bit prefix sum below must not wrap
+            CUDA_TRY(cudaMemcpy(&need_total, d_nvalid, 8, cudaMemcpyDeviceToHost));
+            if ((uint64_t)n_bases + need_total > 0xfffffff0ull) { rc = set_error(SNAPB200_ERR_LIMIT, "too many overflow entries for this seed length (GenomeIndex.cpp:492-495)"); break; }
             tmp_bytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, need, ovf_off, (int)n_runs + 1);
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, need, ovf_off, (unsigned long long)n_runs + 1);
             CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, need, ovf_off, (int)n_runs + 1));
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, need, ovf_off, (unsigned long long)n_runs + 1));
             cudaFree(tmp); tmp = nullptr;
+            cudaFree(need); need = nullptr;
             CUDA_TRY(cudaMemcpy(&overflow_words, ovf_off + n_runs, 4, cudaMemcpyDeviceToHost));
-            if ((uint64_t)n_bases + overflow_words > 0xfffffff0ull) { rc = set_error(SNAPB200_ERR_LIMIT, "too many overflow entries for this seed length (GenomeIndex.cpp:492-495)"); break; }
             if ((rc = dev_alloc(&d_overflow, (size_t)overflow_words + 4))) break;
             ib_fill_overflow_kernel<<<(n_valid + T - 1) / T, T>>>(rid, run_start, ovf_off, v1, n_valid, d_overflow);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(rid); rid = nullptr;
             ib_count_tables_kernel<<<(n_runs + T - 1) / T, T>>>(k1, run_start, n_runs, d_tcount);
             CUDA_TRY(cudaGetLastError());
         }

@@ -4,9 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            # this repo: sm_100a kernels behind the C ABI
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
 
-Workload (BASELINE.json configs[1], "C2"): 100 Mbp repeat-injected synthetic genome (4 x 25 Mbp, seed 20/21),
-index seed length 20, WGsim-model 2x100 bp FR pairs (2 % error, 15 % of mutations indels, fragment 250-450),
-`snap-rna paired` default options (-d 15 -n 8 -h 16000 -H 16000 -s 50 1000).  One step = one pass of
+Workload (default, BASELINE.json configs[2] "C3", the configuration the metric and the target are quoted on; it fits
+one GPU): 3.1 Gbp repeat-injected synthetic genome (124 x 25 Mbp, seeds 20/21; 47 GB of hash tables, built on the device in
+about 2 s), index seed length 20, WGsim-model 2x150 bp FR pairs (1 % error, 15 % of mutations indels, fragment 250-450),
+`snap-rna paired` default options (-d 15 -n 8 -h 16000 -H 16000 -s 50 1000).  `--config c2` runs configs[1] (100 Mbp,
+2x100 bp, 2 %).  One step = one pass of
 ChimericPairedEndAligner::align over one batch of pairs per GPU.  The index and genome are replicated per GPU;
 reads are sharded (each rank aligns its own batch, no collective on the data path) => weak scaling.  NCCL is used
 only for the end-of-run AlignerStats all-reduce and the timing reduction.
@@ -41,7 +43,8 @@ CPU_SAMPLE_PAIRS = 200_000
 
 def workload_config(n_gpus, pairs):
     mbp = sum(GENOME_CONTIGS) // 1_000_000
-    return {"workload": f"{'C2: ' if mbp == 100 else ''}snap paired, {mbp} Mbp repeat-injected synthetic genome ({len(GENOME_CONTIGS)}x25 Mbp), seed 20, 2x{READ_LEN}bp WGsim pairs e={ERR_RATE:.0%}",
+    tag = "C3: " if (mbp, READ_LEN) == (3100, 150) else "C2: " if (mbp, READ_LEN) == (100, 100) else ""
+    return {"workload": f"{tag}snap paired, {mbp} Mbp repeat-injected synthetic genome ({len(GENOME_CONTIGS)}x25 Mbp), seed 20, 2x{READ_LEN}bp WGsim pairs e={ERR_RATE:.0%}",
             "pairs_per_step_per_gpu": pairs, "read_len": READ_LEN, "options": "-d 15 -n 8 -h 16000 -H 16000 -s 50 1000 -D 2",
             "parallelism": f"reads sharded over {n_gpus} GPU(s), index replicated; 2 host threads / 2 streams per GPU keep two batches in flight", "l2": "inputs larger than L2 (index + genome >= 1.76 GB, 0.4 GB batch per step)"}
 
@@ -315,8 +318,7 @@ def cpu_baseline(L, h, b0, b1, params, gpu_out):
     n = min(CPU_SAMPLE_PAIRS, b0.n)
     s0, s1 = b0.slice(0, n), b1.slice(0, n)
     cores = os.cpu_count() or 1
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    with tempfile.TemporaryDirectory(dir=base) as tmp:
+    with tempfile.TemporaryDirectory(dir=scratch_dir(sum(GENOME_CONTIGS) * 18)) as tmp:
         d = os.path.join(tmp, "idx")
         L.save_index(h, d)
         if O.have_ref():
@@ -333,9 +335,25 @@ def cpu_baseline(L, h, b0, b1, params, gpu_out):
             "bit_exact_vs_gpu_on_sample": bool(agree)}
 
 
+def scratch_dir(need_bytes):
+    """A RAM-backed scratch directory when it has room for `need_bytes`, else the regular temp dir."""
+    import shutil
+    for d in ("/dev/shm", None):
+        try:
+            if d is None or (os.path.isdir(d) and shutil.disk_usage(d).free > need_bytes * 1.2):
+                return d
+        except OSError:
+            pass
+    return None
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation (oracle/_ref, built from /root/reference) on the host
-    cores: its own indexer, its own ChimericPairedEndAligner, all threads.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref, compiled from /root/reference):
+    its GenomeIndex loader, its ChimericPairedEndAligner over IntersectingPairedEndAligner + BaseAligner, all host threads.
+    Rank 0 only.  The index files: at 100 Mbp the reference's own indexer builds them (14 s); at 3.1 Gbp it needs ~70 GB and
+    tens of minutes, so there the lookup-equivalent index built on the GPU is written in the reference's
+    file format (tests/test_cuda_parity.py::test_index_build_equivalence) and the reference loads that.  Nothing of this
+    repo is on the timed path."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -346,21 +364,31 @@ def run_reference(args):
     from snap_rnaseq_b200 import synth
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
+    if not O.have_ref():
+        emit({"impl": "reference", "unavailable": "oracle/_ref not present on this box"})
+        return
     contigs = make_genome()
     n = CPU_SAMPLE_PAIRS
     b0, b1 = make_pairs(contigs, n, seed=1000)
     params = A.paired_defaults()
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    with tempfile.TemporaryDirectory(dir=base) as tmp:
-        if O.have_ref():
+    mbp = sum(GENOME_CONTIGS) // 1_000_000
+    index_how = "reference indexer (snap-rna index -s 20)"
+    with tempfile.TemporaryDirectory(dir=scratch_dir(mbp * 18_000_000)) as tmp:
+        d = os.path.join(tmp, "idx")
+        if mbp <= 200:
             fa = os.path.join(tmp, "g.fa")
             synth.write_fasta(fa, contigs)
-            d = os.path.join(tmp, "idx")
             O.ref_build_index(fa, d, seed_len=20, threads=cores)
-            impl, kind = O.ref(threads=cores), "reference"
         else:
-            emit({"impl": "reference", "unavailable": "oracle/_ref not present on this box"})
-            return
+            import snap_rnaseq_b200 as S
+            L = S.lib(int(os.environ.get("LOCAL_RANK", "0")))
+            bases, offs = synth.snap_layout(contigs, 500)
+            h = L.build_index(bases, offs, list(contigs), seed_len=20)
+            L.save_index(h, d)
+            L.close_index(h)
+            del bases
+            index_how = "lookup-equivalent index built on the GPU, saved in the reference's file format"
+        impl = O.ref(threads=cores)
         hc = impl.load_index(d)
         for _ in range(min(args.warmup, 1)):
             impl.paired(hc, params, b0.slice(0, 20000), b1.slice(0, 20000))
@@ -371,10 +399,11 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = 2 * n * steps / dt
     cfg = workload_config(world, n)
+    cfg["index"] = index_how
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u32 integer + f64 probabilities", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": f"{n} pairs per step, {cores} threads, ChimericPairedEndAligner::align only (no I/O)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -410,16 +439,21 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--genome-mbp", type=int, default=100, help="synthetic genome size (contigs of 25 Mbp); 100 = the C2 workload")
-    ap.add_argument("--read-len", type=int, default=100, help="read length (C2: 100, C3: 150)")
-    ap.add_argument("--err", type=float, default=0.02, help="per-base mutation rate of the simulated reads (C2: 0.02, C3: 0.01)")
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "custom"],
+                    help="c3 (default) = BASELINE.json configs[2]: 3.1 Gbp genome, 2x150 bp, 1 %% error; c2 = configs[1]: 100 Mbp, 2x100 bp, 2 %%")
+    ap.add_argument("--genome-mbp", type=int, default=None, help="with --config custom: synthetic genome size (contigs of 25 Mbp)")
+    ap.add_argument("--read-len", type=int, default=None, help="with --config custom: read length")
+    ap.add_argument("--err", type=float, default=None, help="with --config custom: per-base mutation rate of the simulated reads")
     args = ap.parse_args()
+    preset = {"c3": (3100, 150, 0.01), "c2": (100, 100, 0.02), "custom": (100, 100, 0.02)}[args.config]
+    args.genome_mbp = args.genome_mbp or preset[0]
+    args.read_len = args.read_len or preset[1]
+    args.err = args.err if args.err is not None else preset[2]
     global READ_LEN, ERR_RATE
     READ_LEN = args.read_len
     ERR_RATE = args.err
-    if args.genome_mbp != 100:
-        global GENOME_CONTIGS
-        GENOME_CONTIGS = [25_000_000] * max(1, args.genome_mbp // 25)
+    global GENOME_CONTIGS
+    GENOME_CONTIGS = [25_000_000] * max(1, args.genome_mbp // 25)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

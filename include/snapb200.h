@@ -147,6 +147,22 @@ int snapb200_single_multihit_batch(snapb200_index *idx, const snapb200_single_pa
                                    int32_t *hit_counts, uint32_t *hit_locations, uint8_t *hit_rcs,
                                    int32_t *hit_scores);
 
+/* Replaces BaseAligner::CharacterizeSeeds (SNAPLib/BaseAligner.cpp:206-508; callers
+ * AlignmentFilter::UnalignedRead / FindPartialMatches, SNAPLib/AlignmentFilter.cpp:758, 968-971) for a batch:
+ * the seed schedule and lookups of AlignRead without scoring.  The reference fills two
+ * std::map<unsigned location, std::set<unsigned seedOffset>> per read (forward, RC); here segment
+ * s = 2*i + direction holds that map's (location, seed offset) tuples in ascending (location, seed offset)
+ * order -- the in-order traversal of the reference's containers -- at positions
+ * [seg_offsets[s], seg_offsets[s+1]) of locations[] / seed_offsets[].  seg_offsets has 2*n+1 entries and is
+ * always filled, so seg_offsets[2*n] is the number of tuples.  locations/seed_offsets may both be NULL
+ * (count only); otherwise `capacity` is their length in tuples and SNAPB200_ERR_ARG is returned if it is too
+ * small (2 * max_hits * seeds-per-read tuples per read always suffice).  Of `params`, max_hits, max_k,
+ * num_seeds, seed_coverage and explore_popular_seeds are used (the partialAligner of
+ * SNAPLib/PairedAligner.cpp:518-527 is max_hits 300, num_seeds 12). */
+int snapb200_characterize_batch(snapb200_index *idx, const snapb200_single_params *params,
+                                const snapb200_read_batch *reads, uint64_t *seg_offsets,
+                                uint32_t *locations, uint16_t *seed_offsets, uint64_t capacity);
+
 /* ---- paired-end: ChimericPairedEndAligner over IntersectingPairedEndAligner ------------------------- */
 
 /* Constructor arguments of IntersectingPairedEndAligner (SNAPLib/IntersectingPairedEndAligner.cpp:34-49)

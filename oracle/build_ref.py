@@ -41,6 +41,9 @@ PATCHES = [
 # operator= without a return value (ContaminationFilter.h:41)
 INLINE_PATCHES = [
     ("SNAPLib/ContaminationFilter.h", 41, "count = rhs.count; };", "count = rhs.count; return *this; };"),
+    # the one-word change of INTEGRATION.md section 3: CharacterizeSeeds becomes virtual so that the extension's
+    # GpuSeedCharacterizer can serve it from device results (no effect on the reference's own behaviour)
+    ("SNAPLib/BaseAligner.h", 88, "AlignmentResult", "virtual AlignmentResult"),
 ]
 
 CXXFLAGS = ["-O3", "-fPIC", "-w", "-fpermissive", "-std=gnu++98", "-Wno-format", "-msse", "-pthread"]

@@ -397,4 +397,52 @@ int ref_cigar_batch(void *h, const snapb200_read_batch *reads, const unsigned *l
     return 0;
 }
 
+// BaseAligner::CharacterizeSeeds (SNAPLib/BaseAligner.cpp:206-508) with the partialAligner construction of
+// SNAPLib/PairedAligner.cpp:518-527; the two seed_maps are flattened in iteration order.
+int ref_characterize_batch(void *h, const snapb200_single_params *p, const snapb200_read_batch *reads,
+                           unsigned long long *seg_offsets, unsigned *locations, unsigned short *seed_offsets,
+                           unsigned long long capacity, int nthreads)
+{
+    (void)nthreads;
+    ref_init();
+    GenomeIndex *idx = (GenomeIndex *)h;
+    BaseAligner *a = new BaseAligner(idx, p->max_hits, p->max_k, p->max_read_size, p->num_seeds, p->seed_coverage,
+                                     p->extra_search_depth, NULL, NULL, NULL, NULL);
+    a->setExplorePopularSeeds(p->explore_popular_seeds != 0);
+    a->setStopOnFirstHit(p->stop_on_first_hit != 0);
+    std::vector<char> bases, quals;
+    unsigned long long pos = 0;
+    int rc = 0;
+    seg_offsets[0] = 0;
+    for (unsigned i = 0; i < reads->n && !rc; i++) {
+        unsigned off = reads->offsets[i], len = reads->offsets[i + 1] - off;
+        bases.assign(len + PAD, '\n');
+        quals.assign(len + PAD, '\n');
+        memcpy(&bases[0], reads->bases + off, len);
+        memcpy(&quals[0], reads->quals + off, len);
+        Read read;
+        read.init(NULL, 0, &bases[0], &quals[0], len);
+        seed_map maps[2];
+        unsigned loc = InvalidGenomeLocation;
+        Direction dir = FORWARD;
+        int score = 0, mapq = 0;
+        a->CharacterizeSeeds(&read, &loc, &dir, &score, &mapq, 0, 0, FORWARD, maps[0], maps[1]);
+        for (int d = 0; d < 2 && !rc; d++) {
+            for (seed_map::iterator it = maps[d].begin(); it != maps[d].end() && !rc; ++it) {
+                for (std::set<unsigned>::iterator js = it->second.begin(); js != it->second.end(); ++js) {
+                    if (locations) {
+                        if (pos >= capacity) { rc = SNAPB200_ERR_ARG; break; }
+                        locations[pos] = it->first;
+                        seed_offsets[pos] = (unsigned short)*js;
+                    }
+                    pos++;
+                }
+            }
+            seg_offsets[2 * (size_t)i + d + 1] = pos;
+        }
+    }
+    delete a;
+    return rc;
+}
+
 } // extern "C"

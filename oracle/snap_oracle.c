@@ -1095,6 +1095,95 @@ int oracle_single_batch(void *h, const snapb200_single_params *p, const snapb200
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* BaseAligner::CharacterizeSeeds (BaseAligner.cpp:206-508)                                           */
+/* ------------------------------------------------------------------------------------------------ */
+/* The reference inserts (location -> seed offset) into one std::map<unsigned, std::set<unsigned>> per
+ * direction; the tuples of a map in ascending (location, seedOffset) order are its in-order traversal.
+ * Segment 2*i+dir of the output holds them for read i.  Two passes over the reads when the caller wants
+ * the tuples: seg_offsets is always complete. */
+typedef struct { uint32_t loc; uint16_t off; } char_tuple;
+static int char_tuple_cmp(const void *pa, const void *pb)
+{
+    const char_tuple *a = (const char_tuple *)pa, *b = (const char_tuple *)pb;
+    if (a->loc != b->loc) return a->loc < b->loc ? -1 : 1;
+    return (int)a->off - (int)b->off;
+}
+typedef struct { char_tuple *t; size_t n, cap; } char_vec;
+static void char_push(char_vec *v, uint32_t loc, uint32_t off)
+{
+    if (v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 256; v->t = (char_tuple *)realloc(v->t, v->cap * sizeof(char_tuple)); }
+    v->t[v->n].loc = loc; v->t[v->n].off = (uint16_t)off; v->n++;
+}
+
+static void characterize_read(const oracle_index *x, const snapb200_single_params *p, const uint8_t *bases, uint32_t len,
+                              char_vec out[2])
+{
+    const uint32_t seed_len = x->seed_len;
+    out[0].n = out[1].n = 0;
+    if (len < seed_len) return; /* :277-282 */
+    uint32_t n_count = 0;
+    for (uint32_t i = 0; i < len; i++) n_count += bases[i] == 'N';
+    if (n_count > p->max_k) return; /* :303-306 */
+    const uint32_t max_seeds = seeds_to_use(p->num_seeds, p->seed_coverage, len, seed_len);
+    uint8_t used[SNAPB200_MAX_READ_LENGTH + 8];
+    memset(used, 0, sizeof(used));
+    const uint32_t n_possible = len - seed_len + 1;
+    uint32_t next = 0, wrap = 0, applied[2] = {0, 0};
+    while (applied[0] + applied[1] < max_seeds) {
+        if (next >= n_possible) { /* :330-342 */
+            wrap++;
+            if (wrap >= seed_len) return;
+            next = wrapped_seed(seed_len, wrap);
+        }
+        while (next < n_possible && used[next]) next++;
+        if (next >= n_possible) continue;
+        used[next] = 1;
+        uint64_t sf, sr;
+        if (!pack_seed(bases + next, seed_len, &sf, &sr)) continue; /* :362-364 */
+        hit_list hl[2];
+        lookup_seed(x, sf, sr, hl, NULL);
+        for (int dir = 0; dir < 2; dir++) {
+            if (hl[dir].n > p->max_hits && !p->explore_popular_seeds) continue; /* :394-401 */
+            const uint32_t offset = dir == 0 ? next : len - seed_len - next;
+            const uint32_t lim = hl[dir].n < p->max_hits ? hl[dir].n : p->max_hits;
+            for (uint32_t i = 0; i < lim; i++) {
+                const uint32_t hit = hl[dir].hits[i];
+                if (hit < offset) continue; /* :446-450 */
+                char_push(&out[dir], hit - offset, next); /* the FORWARD offset goes into both maps, :455-478 */
+            }
+            applied[dir]++;
+        }
+        next += seed_len; /* :497 */
+    }
+}
+
+int oracle_characterize_batch(void *h, const snapb200_single_params *p, const snapb200_read_batch *reads,
+                              uint64_t *seg_offsets, uint32_t *locations, uint16_t *seed_offsets, uint64_t capacity)
+{
+    const oracle_index *x = (const oracle_index *)h;
+    char_vec v[2] = {{NULL, 0, 0}, {NULL, 0, 0}};
+    uint64_t pos = 0;
+    int rc = 0;
+    seg_offsets[0] = 0;
+    for (uint32_t i = 0; i < reads->n; i++) {
+        const uint32_t off = reads->offsets[i], len = reads->offsets[i + 1] - off;
+        characterize_read(x, p, reads->bases + off, len, v);
+        for (int dir = 0; dir < 2; dir++) {
+            qsort(v[dir].t, v[dir].n, sizeof(char_tuple), char_tuple_cmp);
+            if (locations) {
+                if (pos + v[dir].n > capacity) { rc = SNAPB200_ERR_ARG; goto done; }
+                for (size_t q = 0; q < v[dir].n; q++) { locations[pos + q] = v[dir].t[q].loc; seed_offsets[pos + q] = v[dir].t[q].off; }
+            }
+            pos += v[dir].n;
+            seg_offsets[2 * (size_t)i + dir + 1] = pos;
+        }
+    }
+done:
+    free(v[0].t); free(v[1].t);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* IntersectingPairedEndAligner + ChimericPairedEndAligner                                            */
 /* ------------------------------------------------------------------------------------------------ */
 #define MAX_LOOKUPS 64

@@ -7,12 +7,15 @@ import snap_rnaseq_b200 as S
 from snap_rnaseq_b200 import synth, _abi as A
 import bench
 L = S.lib(0)
+if len(sys.argv) > 2 and sys.argv[2] == "c3":
+    bench.GENOME_CONTIGS = [25_000_000] * 124
+    bench.READ_LEN, bench.ERR_RATE = 150, 0.01
 contigs = bench.make_genome()
 bases, offs = synth.snap_layout(contigs, 500)
 h = L.build_index(bases, offs, list(contigs), seed_len=20)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
 b0, b1 = bench.make_pairs(contigs, n, 1000)
-sess = S.Session(L, h, n, 128)
+sess = S.Session(L, h, n, 256)
 sess.upload(0, b0); sess.upload(1, b1)
 p = A.paired_defaults()
 for it in range(3):

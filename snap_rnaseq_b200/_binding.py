@@ -110,6 +110,21 @@ class BatchLib:
         self._check(self.fn("single_multihit_batch")(*args), "single_multihit_batch")
         return res[:batch.n], cnt[:batch.n], locs[:batch.n], rcs[:batch.n], scores[:batch.n]
 
+    def characterize(self, handle, params, batch):
+        """BaseAligner::CharacterizeSeeds for a batch -> (seg_offsets[2n+1], locations, seed_offsets); segment 2*i+dir."""
+        seg = np.zeros(2 * batch.n + 1, np.uint64)
+        f = self.fn("characterize_batch")
+        tail = [C.c_int(self.threads)] if self.threads is not None else []
+        pseg = seg.ctypes.data_as(C.POINTER(C.c_uint64))
+        self._check(f(handle, C.byref(params), batch.byref(), pseg, None, None, C.c_uint64(0), *tail), "characterize_batch")
+        total = int(seg[-1])
+        locs = np.zeros(max(total, 1), np.uint32)
+        offs = np.zeros(max(total, 1), np.uint16)
+        self._check(f(handle, C.byref(params), batch.byref(), pseg, A.p32u(locs), offs.ctypes.data_as(C.POINTER(C.c_uint16)),
+                      C.c_uint64(total), *tail), "characterize_batch")
+        assert int(seg[-1]) == total
+        return seg, locs[:total], offs[:total]
+
     def paired(self, handle, params, b0, b1):
         assert b0.n == b1.n
         res = np.zeros(max(b0.n, 1), A.PAIRED_RESULT)

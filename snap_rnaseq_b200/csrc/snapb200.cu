@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "index_build.cuh"
+#include "characterize.cuh"  // after kernels.cuh: uses DevBatch, Counters, fetch_work
 #include <sys/stat.h>
 
 thread_local char g_last_error[512] = "";
@@ -1216,6 +1217,100 @@ extern "C" int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_bat
         if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "cigar_kernel: %s", cudaGetErrorString(e)); break; }
     } while (0);
     d_loc.release(); d_dir.release(); d_cig.release(); d_ed.release();
+    return rc;
+}
+
+// ---- CharacterizeSeeds -------------------------------------------------------------------------------------------
+extern "C" int snapb200_characterize_batch(snapb200_index *idx, const snapb200_single_params *params, const snapb200_read_batch *reads,
+                                           uint64_t *seg_offsets, uint32_t *locations, uint16_t *seed_offsets, uint64_t capacity)
+{
+    if (!idx || !params || !reads || !seg_offsets) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if ((locations == nullptr) != (seed_offsets == nullptr)) return set_error(SNAPB200_ERR_ARG, "locations and seed_offsets must both be given or both be NULL");
+    uint32_t m;
+    int rc = validate_batch(reads, &m);
+    if (rc) return rc;
+    if (params->max_k > MAXK) return set_error(SNAPB200_ERR_ARG, "max_k %u > MAX_K", params->max_k);
+    const uint32_t n = reads->n;
+    seg_offsets[0] = 0;
+    if (!n) return 0;
+    BatchSlot slot(idx);
+    if ((rc = slot.open())) return rc;
+    snapb200_session *ss = slot.s;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    // reads per launch group: segment ids must fit the key bits above location and seed offset
+    const uint32_t CHUNK = std::min(chunk_size(), 1u << (64 - CHAR_SEG_SHIFT - 2));
+    std::vector<uint32_t> off_store;
+    DevBuf d_seg, d_off, d_keys0, d_keys1, d_tmp, d_loc, d_so;
+    uint64_t base = 0;
+    for (uint32_t lo = 0; lo < n && !rc; lo += CHUNK) {
+        const uint32_t hi = std::min(n, lo + CHUNK), k = hi - lo;
+        snapb200_read_batch sb = sub_batch(reads, lo, hi, off_store);
+        if ((rc = snapb200_session_upload(ss, 0, &sb))) break;
+        const size_t n_seg = (size_t)2 * k;
+        if ((rc = d_seg.ensure((n_seg + 1) * 8)) || (rc = d_off.ensure((n_seg + 1) * 8))) break;
+        CharArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ix = idx->dev; a.b = dev_batch(ss, 0);
+        a.max_hits = params->max_hits; a.max_k = params->max_k; a.num_seeds = params->num_seeds;
+        a.explore = params->explore_popular_seeds; a.seed_coverage = params->seed_coverage;
+        a.rl = std::max(32u, (m + 15) & ~15u);
+        a.ctr = ss->counters.as<Counters>();
+        const size_t smem = char_warp_shared(a.rl) * WARPS_PER_CTA;
+        int per_sm;
+        const int grid_c = grid_for(characterize_kernel<false>, smem, idx->sm_count, &per_sm);
+        const int grid_e = grid_for(characterize_kernel<true>, smem, idx->sm_count, &per_sm);
+        // pass 1: segment sizes
+        cudaMemsetAsync(d_seg.p, 0, (n_seg + 1) * 8, ss->stream);
+        if ((rc = reset_work(ss))) break;
+        a.seg = d_seg.as<unsigned long long>();
+        characterize_kernel<false><<<grid_c, CTA_THREADS, smem, ss->stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize_kernel launch: %s", cudaGetErrorString(e)); break; }
+        ss->total_launches++;
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_seg.as<unsigned long long>(), d_off.as<unsigned long long>(), n_seg + 1, ss->stream);
+        if ((rc = d_tmp.ensure(tmp_bytes))) break;
+        e = cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_seg.as<unsigned long long>(), d_off.as<unsigned long long>(), n_seg + 1, ss->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize scan: %s", cudaGetErrorString(e)); break; }
+        cudaMemcpyAsync(seg_offsets + (size_t)2 * lo, d_off.p, (n_seg + 1) * 8, cudaMemcpyDeviceToHost, ss->stream);
+        e = cudaStreamSynchronize(ss->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize_kernel: %s", cudaGetErrorString(e)); break; }
+        const uint64_t total = seg_offsets[(size_t)2 * lo + n_seg];
+        if (base) for (size_t q = 0; q <= n_seg; q++) seg_offsets[(size_t)2 * lo + q] += base;
+        if (locations && total) {
+            if (base + total > capacity) {
+                rc = set_error(SNAPB200_ERR_ARG, "characterize: output capacity %llu too small (reads %u..%u alone need %llu more tuples)",
+                               (unsigned long long)capacity, lo, hi, (unsigned long long)total);
+                break;
+            }
+            if ((rc = d_keys0.ensure(total * 8)) || (rc = d_keys1.ensure(total * 8)) || (rc = d_loc.ensure(total * 4)) || (rc = d_so.ensure(total * 2))) break;
+            // pass 2: one key per tuple, then order every segment
+            if ((rc = reset_work(ss))) break;
+            a.seg = d_off.as<unsigned long long>();
+            a.keys = d_keys0.as<unsigned long long>();
+            characterize_kernel<true><<<grid_e, CTA_THREADS, smem, ss->stream>>>(a);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize_kernel launch: %s", cudaGetErrorString(e)); break; }
+            ss->total_launches++;
+            int seg_bits = 1;
+            while (((size_t)1 << seg_bits) < n_seg) seg_bits++;
+            cub::DoubleBuffer<unsigned long long> kb(d_keys0.as<unsigned long long>(), d_keys1.as<unsigned long long>());
+            tmp_bytes = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, kb, (unsigned long long)total, 0, CHAR_SEG_SHIFT + seg_bits, ss->stream);
+            if ((rc = d_tmp.ensure(tmp_bytes))) break;
+            e = cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, kb, (unsigned long long)total, 0, CHAR_SEG_SHIFT + seg_bits, ss->stream);
+            if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize sort: %s", cudaGetErrorString(e)); break; }
+            const unsigned blocks = (unsigned)((total + 255) / 256);
+            characterize_split_kernel<<<blocks, 256, 0, ss->stream>>>(kb.Current(), total, d_loc.as<uint32_t>(), d_so.as<uint16_t>());
+            ss->total_launches++;
+            cudaMemcpyAsync(locations + base, d_loc.p, total * 4, cudaMemcpyDeviceToHost, ss->stream);
+            cudaMemcpyAsync(seed_offsets + base, d_so.p, total * 2, cudaMemcpyDeviceToHost, ss->stream);
+            e = cudaStreamSynchronize(ss->stream);
+            if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize emit: %s", cudaGetErrorString(e)); break; }
+        }
+        base += total;
+    }
+    d_seg.release(); d_off.release(); d_keys0.release(); d_keys1.release(); d_tmp.release(); d_loc.release(); d_so.release();
     return rc;
 }
 

@@ -18,6 +18,7 @@
 #pragma once
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,71 @@ public:
     static bool ignoreMismatchedIDs(PairedAlignerContext *c) { return c->ignoreMismatchedIDs; }
 };
 
+// BaseAligner::CharacterizeSeeds served from the device.  AlignmentFilter holds a
+// `BaseAligner *specialAligner` and calls CharacterizeSeeds on it for unaligned / suspicious reads
+// (SNAPLib/AlignmentFilter.cpp:758, 968-971); the extension computes the seed maps of every read of a batch with
+// one snapb200_characterize_batch call per mate and this subclass hands the filter the maps of the read it asks
+// about.  Needs the one-word change `virtual` on BaseAligner::CharacterizeSeeds (SNAPLib/BaseAligner.h:88); the
+// base class's own CPU implementation is never run.
+class GpuSeedCharacterizer : public BaseAligner {
+public:
+    GpuSeedCharacterizer(GenomeIndex *index, unsigned maxHits, unsigned maxK, unsigned nSeeds, double coverage, unsigned extraDepth,
+                         bool explorePopular)
+        : BaseAligner(index, maxHits, maxK, MAX_READ_LENGTH, nSeeds, coverage, extraDepth, NULL, NULL)
+    {
+        setExplorePopularSeeds(explorePopular);  // SingleAligner.cpp:183, PairedAligner.cpp:529
+        params_.max_hits = maxHits; params_.max_k = maxK; params_.max_read_size = MAX_READ_LENGTH; params_.num_seeds = nSeeds;
+        params_.seed_coverage = coverage; params_.extra_search_depth = extraDepth; params_.explore_popular_seeds = explorePopular ? 1 : 0;
+        params_.stop_on_first_hit = 0; params_.max_hits_to_get = 0;
+        current_[0] = current_[1] = NULL;
+        index_ = 0;
+    }
+
+    // one device call per mate for the whole batch; returns the library's status
+    int compute(snapb200_index *idx, int mate, const snapb200_read_batch *reads)
+    {
+        Maps &m = maps_[mate];
+        m.seg.assign((size_t)2 * reads->n + 1, 0);
+        int rc = snapb200_characterize_batch(idx, &params_, reads, &m.seg[0], NULL, NULL, 0);
+        if (rc != SNAPB200_OK) return rc;
+        const size_t total = (size_t)m.seg[(size_t)2 * reads->n];
+        m.loc.resize(total + 1); m.off.resize(total + 1);
+        return snapb200_characterize_batch(idx, &params_, reads, &m.seg[0], &m.loc[0], &m.off[0], total);
+    }
+
+    // the filter is about to be run on read i of the batch, whose mates live at r0 / r1 (r0 may be NULL: single end)
+    void select(unsigned i, const Read *r0, const Read *r1) { index_ = i; current_[0] = r0; current_[1] = r1; }
+
+    virtual AlignmentResult CharacterizeSeeds(Read *inputRead, unsigned *genomeLocation, Direction *hitDirection, int *finalScore,
+                                              int *mapq, unsigned searchRadius, unsigned searchLocation, Direction searchDirection,
+                                              seed_map &map, seed_map &mapRC)
+    {
+        (void)mapq; (void)searchRadius; (void)searchLocation; (void)searchDirection;
+        *genomeLocation = InvalidGenomeLocation;   // what the reference leaves in its out-parameters (BaseAligner.cpp:250-252)
+        if (hitDirection != NULL) *hitDirection = FORWARD;
+        if (finalScore != NULL) *finalScore = 0xffff;
+        const int mate = (inputRead == current_[1] && current_[0] != NULL) ? 1 : 0;
+        const Maps &m = maps_[mate];
+        seed_map *out[2] = {&map, &mapRC};
+        for (int d = 0; d < 2; d++) {
+            const size_t s = (size_t)2 * index_ + d;
+            seed_map::iterator at = out[d]->end();
+            for (uint64_t q = m.seg[s]; q < m.seg[s + 1]; q++) {  // ascending (location, offset): always appended at the end
+                if (at == out[d]->end() || at->first != m.loc[q]) at = out[d]->insert(out[d]->end(), seed_map::value_type(m.loc[q], std::set<unsigned>()));
+                at->second.insert(at->second.end(), (unsigned)m.off[q]);
+            }
+        }
+        return NotFound;
+    }
+
+private:
+    struct Maps { std::vector<uint64_t> seg; std::vector<uint32_t> loc; std::vector<uint16_t> off; };
+    Maps maps_[2];
+    snapb200_single_params params_;
+    const Read *current_[2];
+    unsigned index_;
+};
+
 class GpuAlignerExtension : public AlignerExtension {
 public:
     explicit GpuAlignerExtension(int device = 0, unsigned batchReads = 1u << 17)
@@ -86,9 +152,10 @@ public:
         SingleAlignerContext *sc = (SingleAlignerContext *)ctx;
         if (genome_ == NULL) attach(ctx->options);
         snapb200_single_params p = singleParams(ctx);
-        // the CPU aligner the filter needs for CharacterizeSeeds (SURVEY.md 8f row f1 keeps this on the host for now)
-        BaseAligner *partial = new BaseAligner(ctx->index, ctx->maxHits, ctx->maxDist, MAX_READ_LENGTH, ctx->numSeedsFromCommandLine,
-                                               ctx->seedCoverage, ctx->extraSearchDepth, NULL, NULL);
+        // the aligner AlignmentFilter calls CharacterizeSeeds on (SingleAligner.cpp:168 passes g_aligner); served from the device
+        GpuSeedCharacterizer *partial = new GpuSeedCharacterizer(ctx->index, ctx->maxHits, ctx->maxDist, ctx->numSeedsFromCommandLine,
+                                                                 ctx->seedCoverage, ctx->extraSearchDepth,
+                                                                 ctx->options->explorePopularSeeds);
         ReadStore store;
         std::vector<snapb200_single_result> tres, gres, cres;
         Read *read;
@@ -108,6 +175,7 @@ public:
             tres.resize(store.size()); gres.resize(store.size());
             check(snapb200_single_batch(transcriptome_, &p, &rb, &tres[0]));
             check(snapb200_single_batch(genome_, &p, &rb, &gres[0]));
+            check(partial->compute(genome_, 0, &rb));
             bool needContam = false;
             std::vector<AlignmentResult> final(store.size(), NotFound);
             // replay, in input order
@@ -124,6 +192,7 @@ public:
                 Direction direction = FORWARD;
                 int score = 0, mapq = 0;
                 bool isTranscriptome = false;
+                partial->select(i, NULL, &r);
                 AlignmentFilter filter(NULL, &r, ctx->index->getGenome(), ctx->transcriptome->getGenome(), ctx->gtf, 0, 0,
                                        ctx->options->confDiff, ctx->options->maxDist.start, ctx->index->getSeedLength(), partial);
                 filter.AddAlignment(tres[i].location, tres[i].direction, tres[i].score, tres[i].mapq, true, true);
@@ -161,7 +230,9 @@ public:
         snapb200_single_params tp = singleParams(ctx);  // transcriptomeAligner, PairedAligner.cpp:512
         const unsigned maxHitsToGet = 1000;             // PairedAligner.cpp:584
         tp.max_hits_to_get = maxHitsToGet;
-        BaseAligner *partial = new BaseAligner(ctx->index, 300, ctx->maxDist, MAX_READ_LENGTH, 12, ctx->seedCoverage, ctx->extraSearchDepth, NULL, NULL);
+        // partialAligner, PairedAligner.cpp:518-527: maxHits 300, 12 seeds; its CharacterizeSeeds is served from the device
+        GpuSeedCharacterizer *partial = new GpuSeedCharacterizer(ctx->index, 300, ctx->maxDist, 12, ctx->seedCoverage, ctx->extraSearchDepth,
+                                                                 ctx->options->explorePopularSeeds);
         ReadStore s0, s1;
         std::vector<snapb200_paired_result> res, cres;
         std::vector<snapb200_single_result> t0, t1;
@@ -194,6 +265,8 @@ public:
             check(snapb200_single_multihit_batch(transcriptome_, &tp, &b0, &t0[0], &n0[0], &l0[0], &rc0[0], &sc0[0]));
             check(snapb200_single_multihit_batch(transcriptome_, &tp, &b1, &t1[0], &n1[0], &l1[0], &rc1[0], &sc1[0]));
             check(snapb200_paired_batch(genome_, &pp, &b0, &b1, &res[0]));
+            check(partial->compute(genome_, 0, &b0));
+            check(partial->compute(genome_, 1, &b1));
             for (unsigned i = 0; i < n; i++) {
                 Read r0, r1;
                 s0.get(i, &r0, ctx->clipping); s1.get(i, &r1, ctx->clipping);
@@ -205,6 +278,7 @@ public:
                     continue;
                 }
                 toReference(res[i], &result);
+                partial->select(i, &r0, &r1);
                 AlignmentFilter filter(&r0, &r1, ctx->index->getGenome(), ctx->transcriptome->getGenome(), ctx->gtf, pp.min_spacing,
                                        pp.max_spacing, ctx->options->confDiff, ctx->options->maxDist.start, ctx->index->getSeedLength(), partial);
                 for (int k = 0; k < n0[i]; k++) filter.AddAlignment(l0[(size_t)i * maxHitsToGet + k], rc0[(size_t)i * maxHitsToGet + k], sc0[(size_t)i * maxHitsToGet + k], 0, true, false);

@@ -20,6 +20,11 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_characterize():
+    return np.load(os.path.join(GOLDEN, "characterize_cases.npz"))
+
+
+@pytest.fixture(scope="session")
 def small_index_dir(tmp_path_factory):
     d = tmp_path_factory.mktemp("golden_index")
     with tarfile.open(os.path.join(GOLDEN, "small_index.tar.gz")) as tf:

@@ -96,3 +96,28 @@ def check_empty(impl, h):
     e = A.Batch.from_strings([])
     assert len(impl.single(h, A.single_defaults(), e)) == 0
     assert len(impl.paired(h, A.paired_defaults(), e, e)) == 0
+    seg, locs, offs = impl.characterize(h, A.single_defaults(), e)
+    assert list(seg) == [0] and len(locs) == 0 and len(offs) == 0
+
+
+# BaseAligner::CharacterizeSeeds (BaseAligner.cpp:206-508): golden = the compiled reference's seed maps, flattened
+CHARACTERIZE_CASES = {
+    "partial": ("r100", dict(max_hits=300, num_seeds=12, max_k=15)),
+    "popular": ("r100", dict(max_hits=4, num_seeds=12, max_k=15)),
+    "explore": ("r150", dict(max_hits=3, num_seeds=20, max_k=15, explore_popular_seeds=1)),
+    "coverage": ("r150", dict(max_hits=300, num_seeds=0, seed_coverage=2.5, max_k=8)),
+}
+
+
+def check_golden_characterize(impl, h, gc):
+    for name, (rs, kw) in CHARACTERIZE_CASES.items():
+        b = batch_from(gc, rs)
+        seg, locs, offs = impl.characterize(h, A.single_defaults(**kw), b)
+        np.testing.assert_array_equal(seg, gc[name + "_seg"], err_msg=name)
+        np.testing.assert_array_equal(locs, gc[name + "_locs"], err_msg=name)
+        np.testing.assert_array_equal(offs, gc[name + "_offs"], err_msg=name)
+        # properties of a flattened std::map<location, std::set<offset>>: strictly ascending (location, offset) per segment
+        key = locs.astype(np.uint64) * 512 + offs
+        starts = np.zeros(key.size, bool)
+        starts[seg[:-1][seg[:-1] < key.size].astype(np.int64)] = True
+        assert np.all((np.diff(key.astype(np.int64)) > 0) | starts[1:]), name

@@ -57,6 +57,47 @@ def test_golden_cigar(cuda, handle, golden):
     P.check_golden_cigar(cuda, handle, golden)
 
 
+def test_golden_characterize(cuda, handle, golden_characterize):
+    P.check_golden_characterize(cuda, handle, golden_characterize)
+
+
+def test_characterize_fresh_and_edges(cuda, handle, port, small_index_dir, request):
+    """CharacterizeSeeds on fresh reads (incl. repeat-family reads with thousands of tuples), ragged/edge reads, the
+    multi-chunk path, the count-only call and the capacity check."""
+    from tests_genome import small_genome
+    contigs = small_genome()
+    c1 = contigs["chr1"].tobytes().decode()
+    edge = A.Batch.from_strings(["", "A", c1[:19], c1[:20], c1[:49], c1[-100:], "N" * 80, c1[5:65] + "N" * 10 + c1[75:125],
+                                 c1[300:400][::-1], c1[1000:1100]])
+    sim = synth.simulate(contigs, 3000, 100, paired=True, err=0.03, seed=55, junk_frac=0.05, n_rate=0.02)
+    b0, b1 = sim["batches"]
+    for name, chk in _checkers(port, request):
+        hc = chk.load_index(small_index_dir)
+        for b, kw in ((edge, dict(max_hits=300, num_seeds=12)), (b0, dict(max_hits=300, num_seeds=12)),
+                      (b1, dict(max_hits=16000, num_seeds=25, max_k=14)), (b0, dict(max_hits=2, num_seeds=40, explore_popular_seeds=1))):
+            ps = A.single_defaults(**kw)
+            want, got = chk.characterize(hc, ps, b), cuda.characterize(handle, ps, b)
+            for w, g, what in zip(want, got, ("seg_offsets", "locations", "seed_offsets")):
+                np.testing.assert_array_equal(w, g, err_msg=f"{what} vs {name} {kw}")
+    ps = A.single_defaults(max_hits=300, num_seeds=12)
+    full = cuda.characterize(handle, ps, b0)
+    os.environ["SNAPB200_CHUNK"] = "1024"  # three internal launch groups
+    try:
+        chunked = cuda.characterize(handle, ps, b0)
+    finally:
+        del os.environ["SNAPB200_CHUNK"]
+    for w, g in zip(full, chunked):
+        np.testing.assert_array_equal(w, g)
+    # capacity too small is an argument error, not a truncated answer
+    import ctypes as C
+    seg = np.zeros(2 * b0.n + 1, np.uint64)
+    locs = np.zeros(4, np.uint32)
+    offs = np.zeros(4, np.uint16)
+    rc = cuda.lib.snapb200_characterize_batch(handle, C.byref(ps), b0.byref(), seg.ctypes.data_as(C.c_void_p), A.p32u(locs),
+                                              offs.ctypes.data_as(C.c_void_p), C.c_uint64(4))
+    assert rc == -1 and int(seg[-1]) == int(full[0][-1])
+
+
 def test_empty(cuda, handle):
     P.check_empty(cuda, handle)
 

@@ -51,5 +51,9 @@ def test_golden_cigar(impl, handle, golden):
     P.check_golden_cigar(impl, handle, golden)
 
 
+def test_golden_characterize(impl, handle, golden_characterize):
+    P.check_golden_characterize(impl, handle, golden_characterize)
+
+
 def test_empty(impl, handle):
     P.check_empty(impl, handle)

@@ -18,7 +18,10 @@ b0, b1 = bench.make_pairs(contigs, n, 1000)
 sess = S.Session(L, h, n, 256)
 sess.upload(0, b0); sess.upload(1, b1)
 p = A.paired_defaults()
-for it in range(3):
+sweep = os.environ.get("PROF_SWEEP", "").split(",") if os.environ.get("PROF_SWEEP") else [None] * 3
+for it, cfg in enumerate(sweep):
+    if cfg is not None:
+        os.environ["SNAPB200_CTAS_PER_SM"] = cfg
     sess.run_paired(p)
     ms, launches, _ = sess.last_run()
     print("run %d total %.1f ms main %.1f ms launches %d" % (it, ms, sess.main_kernel_ms(), launches))

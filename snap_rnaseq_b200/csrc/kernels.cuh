@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) single_kernel(const SingleArgs
     sc.hit_loc = a.hit_loc ? a.hit_loc + (size_t)slot * MAXK * 512 : nullptr;
     sc.hit_rc = a.hit_rc ? a.hit_rc + (size_t)slot * MAXK * 512 : nullptr;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
+    #pragma unroll 1
     for (;;) {
         const uint32_t p = fetch_work(&a.ctr->work);
         if (p >= a.n_items) break;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
     int16_t *L = (int16_t *)base;
     base += lv_shared_bytes();
     ReadView v[2];
+    #pragma unroll 1
     for (int w = 0; w < 2; w++) {
         v[w].D[0] = base + (4 * w + 0) * a.cfg.rl; v[w].D[1] = base + (4 * w + 1) * a.cfg.rl;
         v[w].Q[0] = base + (4 * w + 2) * a.cfg.rl; v[w].Q[1] = base + (4 * w + 3) * a.cfg.rl;
@@ -176,12 +178,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
     sc.anchors = a.anchors + (size_t)slot * a.cfg.anchor_cap;
     sc.lane_table = a.lane_tables + (size_t)slot * LANE_TABLE_CELLS * 32;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
+    #pragma unroll 1
     for (;;) {
         const uint32_t p = fetch_work(&a.ctr->work);
         if (p >= a.n_items) break;
         const uint32_t pi = a.positions ? a.positions[p] : p;
         snapb200_paired_result *r = &a.results[pi];
         uint32_t len[2], off[2];
+        #pragma unroll 1
         for (int w = 0; w < 2; w++) { off[w] = a.b[w].offsets[pi]; len[w] = a.b[w].offsets[pi + 1] - off[w]; }
         if (lane == 0) {  // ChimericPairedEndAligner::align prologue (:74-80); untouched fields read as zero
             r->location[0] = r->location[1] = INVALID_LOC;
@@ -193,18 +197,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
         }
         __syncwarp();
         if (len[0] < 50 && len[1] < 50) continue;
-        uint32_t ns = 0;
+        uint32_t ns = 0, n_bad[2];
+        #pragma unroll 1
         for (int w = 0; w < 2; w++) {
             v[w].len = len[w];
-            ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w]);
+            ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w], &n_bad[w]);
         }
         if (lane == 0) for (int q = 0; q < 12; q++) sm->t_phase[q] = 0;
         long long t_s = clock64();
-        int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, W, L, r, pi, fix);
+        int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, n_bad, W, L, r, pi, fix);
         if (lane == 0 && a.prof) {
             atomicAdd(a.prof + 0, (unsigned long long)(clock64() - t_s));
+            #pragma unroll 1
             for (int q = 1; q < 5; q++) atomicAdd(a.prof + q, (unsigned long long)sm->t_phase[q]);
             atomicAdd(a.prof + 5, 1ull);
+            #pragma unroll 1
             for (int q = 5; q < 10; q++) atomicAdd(a.prof + q + 1, (unsigned long long)sm->t_phase[q]);
         }
         if (lane == 0) {
@@ -310,12 +317,14 @@ __global__ void __launch_bounds__(CTA_THREADS) cigar_kernel(const CigarArgs a)
     int16_t *L = (int16_t *)base;
     uint8_t *P = base + lv_shared_bytes();
     uint8_t *W = P + a.rl;
+    #pragma unroll 1
     for (;;) {
         const uint32_t i = fetch_work(&a.ctr->work);
         if (i >= a.b.n) break;
         const uint32_t off = a.b.offsets[i], len = a.b.offsets[i + 1] - off;
         const uint32_t loc = a.locations[i];
         char *out = a.cigars + (size_t)i * a.stride;
+        #pragma unroll 1
         for (uint32_t j = lane; j < a.stride; j += 32) out[j] = 0;
         __syncwarp();
         if (loc == INVALID_LOC || !substring_ok(a.ix, loc, len)) {
@@ -323,6 +332,7 @@ __global__ void __launch_bounds__(CTA_THREADS) cigar_kernel(const CigarArgs a)
             continue;
         }
         const bool rc = a.directions[i] == SNAPB200_RC;
+        #pragma unroll 1
         for (uint32_t j = lane; j < len; j += 32) P[j] = rc ? rc_base(a.b.bases[off + len - 1 - j]) : a.b.bases[off + j];
         stage_window(a.ix, loc, len, W);
         LvStr s;
@@ -364,11 +374,14 @@ __global__ void __launch_bounds__(CTA_THREADS) lv_kernel(const LvArgs a)
     uint8_t *T = base + lv_shared_bytes();
     uint8_t *P = T + ((a.max_text + 15) & ~15u);
     uint8_t *Q = P + ((a.max_pat + 15) & ~15u);
+    #pragma unroll 1
     for (;;) {
         const uint32_t i = fetch_work(&a.ctr->work);
         if (i >= a.n) break;
         const uint32_t to = a.text_off[i], tl = a.text_off[i + 1] - to, po = a.pat_off[i], pl = a.pat_off[i + 1] - po;
+        #pragma unroll 1
         for (uint32_t j = lane; j < tl; j += 32) T[j] = a.texts[to + j];
+        #pragma unroll 1
         for (uint32_t j = lane; j < pl; j += 32) { P[j] = a.pats[po + j]; if (a.quals) Q[j] = a.quals[po + j]; }
         __syncwarp();
         LvStr s;
@@ -377,6 +390,7 @@ __global__ void __launch_bounds__(CTA_THREADS) lv_kernel(const LvArgs a)
         if (a.dir > 0) { s.t = T; s.ts = 1; } else { s.t = T + tl - 1; s.ts = -1; }  // backward: text(i) = T[tl-1-i]
         if (a.cigars) {
             char *out = a.cigars + (size_t)i * a.stride;
+            #pragma unroll 1
             for (uint32_t j = lane; j < a.stride; j += 32) out[j] = 0;
             __syncwarp();
             int e = lv_cigar_warp(s, a.k[i], L, out, (int)a.stride, a.use_m != 0);
@@ -398,8 +412,10 @@ __global__ void lookup_kernel(const DevIndex ix, uint32_t n, const uint8_t *seed
     uint64_t f, r;
     HitList hl[2] = {{nullptr, 0}, {nullptr, 0}};
     if (pack_seed(seeds + (size_t)i * ix.seed_len, ix.seed_len, &f, &r)) lookup_seed(ix, f, r, hl, nullptr);
+    #pragma unroll 1
     for (int d = 0; d < 2; d++) {
         n_hits[i * 2 + d] = hl[d].n;
+        #pragma unroll 1
         for (uint32_t j = 0; j < hl[d].n && j < max_out; j++) hits[((size_t)i * 2 + d) * max_out + j] = hl[d].hits[j];
     }
 }

@@ -31,6 +31,7 @@ __device__ __forceinline__ bool pack_seed(const uint8_t *text, uint32_t len, uin
 {
     uint64_t f = 0, r = 0;
     bool ok = true;
+    #pragma unroll 1
     for (uint32_t i = 0; i < len; i++) {
         int v = base2(text[i]);
         ok &= v >= 0;
@@ -82,6 +83,7 @@ __device__ __forceinline__ void lookup_seed(const DevIndex &ix, uint64_t fwd, ui
     uint32_t key = __ldg(&e->key), v1 = __ldg(&e->v1);
     if (!(key == lo && v1 != INVALID_LOC)) {
         uint64_t n = 0;
+        #pragma unroll 1
         do {
             n++;
             if (n > size + 5) { e = nullptr; break; }

@@ -46,6 +46,7 @@ __device__ __forceinline__ int lv_cell(const LvStr &s, const int16_t *L, int e, 
     if (lv_pat(s, best) == lv_txt(s, d + best)) {
         int dend = min(s.plen, s.tlen - d);
         if (best < dend) {
+            #pragma unroll 1
             do { best++; } while (best < dend && lv_pat(s, best) == lv_txt(s, d + best));
         } else {
             best = dend;  // the reference's 8-byte loop clamps to `end` even when it starts beyond it
@@ -70,6 +71,7 @@ __device__ __forceinline__ char lv_action(const int16_t *L, int e, int d)
 __device__ __forceinline__ int lv_row0(const LvStr &s, int end)
 {
     int lane = lane_id();
+    #pragma unroll 1
     for (int base = 0; base < end; base += 32) {
         int i = base + lane;
         bool mism = (i < end) && (lv_pat(s, i) != lv_txt(s, i));
@@ -90,8 +92,10 @@ template <bool CIGAR_ORDER>
 __device__ __forceinline__ int lv_rows(const LvStr &s, int16_t *L, int k, int *win_d)
 {
     const int lane = lane_id();
+    #pragma unroll 1
     for (int e = 1; e <= k; e++) {
         int found = 0x7fffffff;
+        #pragma unroll 1
         for (int idx = lane; idx < 2 * e + 1; idx += 32) {
             int d = idx - e;
             int best = lv_cell(s, L, e, d);
@@ -138,6 +142,7 @@ __device__ __noinline__ int lv_score_warp(const LvStr &s, const uint8_t *q, int 
         char act[MAXK + 1];
         short matched[MAXK + 1];
         int cur_d = d;
+        #pragma unroll 1
         for (int ce = e; ce >= 1; ce--) {
             char a = lv_action(L, ce, cur_d);
             int here = (ce == e) ? plen : lv_get(L, ce, cur_d);
@@ -154,9 +159,11 @@ __device__ __noinline__ int lv_score_warp(const LvStr &s, const uint8_t *q, int 
         }
         int ce = 1;
         int offset = L[0];
+        #pragma unroll 1
         while (ce <= e) {
             char a = act[ce];
             int count = 1;
+            #pragma unroll 1
             while (ce + 1 <= e && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
             if (a == 'I') {
                 prob *= ix.indel[count];
@@ -167,6 +174,7 @@ __device__ __noinline__ int lv_score_warp(const LvStr &s, const uint8_t *q, int 
                 offset -= count;
                 indel -= count;
             } else {
+                #pragma unroll 1
                 for (int i = 0; i < count; i++) {
                     int qi = min(plen - 1, max(offset, 0));
                     prob *= ix.phred[q[qi * qs]];
@@ -194,9 +202,11 @@ __device__ inline bool cigar_put(CigarOut &o, int count, char code)
     char tmp[12];
     int n = 0;
     int c = count;
+    #pragma unroll 1
     while (c > 0) { tmp[n++] = (char)('0' + c % 10); c /= 10; }
     int w = n + 1;
     if (w > o.left - 1) return false;
+    #pragma unroll 1
     for (int i = 0; i < n; i++) o.buf[i] = tmp[n - 1 - i];
     o.buf[n] = code;
     o.buf[w] = 0;
@@ -232,6 +242,7 @@ __device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int
     if (e < 0) return -1;
     // can e plain mismatches explain it?  (LandauVishkin.cpp:357-366)
     int straight = 0;
+    #pragma unroll 1
     for (int base = 0; base < end; base += 32) {
         int i = base + lane;
         bool mism = (i < end) && (lv_pat(s, i) != lv_txt(s, i));
@@ -247,6 +258,7 @@ __device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int
             } else {
                 int start = 0;
                 bool matching = lv_pat(s, 0) == lv_txt(s, 0);
+                #pragma unroll 1
                 for (int i = 0; i < end && ok; i++) {
                     bool m = lv_pat(s, i) == lv_txt(s, i);
                     if (m != matching) {
@@ -269,6 +281,7 @@ __device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int
             char act[MAXK + 1];
             short matched[MAXK + 1];
             int cur_d = d;
+            #pragma unroll 1
             for (int ce = e; ce >= 1; ce--) {
                 char a = lv_action(L, ce, cur_d);
                 act[ce] = a;
@@ -287,9 +300,11 @@ __device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int
             if (use_m) acc_m = L[0];
             else if (L[0] > 0) ok = cigar_put(o, L[0], '=');
             int ce = 1;
+            #pragma unroll 1
             while (ce <= e && ok) {
                 char a = act[ce];
                 int count = 1;
+                #pragma unroll 1
                 while (ce + 1 <= e && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
                 if (use_m) {
                     if (a == 'X') {
@@ -354,6 +369,7 @@ __device__ __forceinline__ int lane_run(const uint8_t *p, const uint8_t *t, int 
 {
     const int rem = plen - pi;
     int n = 0;
+    #pragma unroll 1
     while (n < rem) {
         uint32_t x = str4<DIR>(p, pi + n) ^ str4<DIR>(t, ti + n);
         if (x) { n += (__ffs((int)x) - 1) >> 3; break; }
@@ -398,9 +414,11 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
         }
     }
     const int kmax = min(k > 0 ? k : 0, LANE_KMAX);
+    #pragma unroll 1
     for (int e = 1; e <= LANE_KMAX; e++) {
         if (live && e > kmax) live = false;
         if (!__any_sync(FULL_MASK, live)) break;
+        #pragma unroll 1
         for (int r = 0; r <= 2 * e; r++) {
             if (live) {
                 const int d = lv_unrank_score(r);
@@ -420,6 +438,7 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
         char act[LANE_KMAX + 1];
         short matched[LANE_KMAX + 1];
         int cur_d = win_d;
+        #pragma unroll 1
         for (int ce = result; ce >= 1; ce--) {
             int up = lane_get(T, ce - 1, cur_d) + 1, left = lane_get(T, ce - 1, cur_d - 1), right = lane_get(T, ce - 1, cur_d + 1) + 1;
             int best = up;
@@ -433,9 +452,11 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
         }
         double prob = 1.0;
         int indel = 0, ce = 1, offset = l0;
+        #pragma unroll 1
         while (ce <= result) {
             const char a = act[ce];
             int count = 1;
+            #pragma unroll 1
             while (ce + 1 <= result && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
             if (a == 'I') {
                 prob *= ix.indel[count];
@@ -446,6 +467,7 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
                 offset -= count;
                 indel -= count;
             } else {
+                #pragma unroll 1
                 for (int i = 0; i < count; i++) {
                     int qi = min(plen - 1, max(offset, 0));
                     prob *= ix.phred[q[qi * DIR]];

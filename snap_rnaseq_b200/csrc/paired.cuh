@@ -70,6 +70,16 @@ struct PairedScratch {
 
 #define STATUS_LIMIT 0xfd  // the reference's candidate pools would have overflowed (it exits)
 
+// phase 1 staging (raw lookup results per scheduled seed); lives in the Landau-Vishkin buffer, which is idle until phase 3
+struct Phase1Sm {
+    unsigned long long raw_hits[2][MAX_LOOKUPS];
+    uint32_t raw_n[2][MAX_LOOKUPS];
+    uint32_t raw_last[2][MAX_LOOKUPS];  // last word of each hit list (the trim test of recordLookup), loaded by the probing lane
+    uint16_t sched_off[MAX_LOOKUPS];
+    uint8_t sched_wrap[MAX_LOOKUPS];
+    uint32_t used[16];
+};
+
 struct PairedSm {
     // hit sets [read][dir], filled by the leader in phase 1 (HashTableHitSet::recordLookup)
     unsigned long long hits[2][2][MAX_LOOKUPS];
@@ -79,13 +89,7 @@ struct PairedSm {
     uint8_t exhausted[2][2][MAX_LOOKUPS];
     int8_t cur_set[2][2];
     uint8_t n_lookups[2][2];
-    // phase 1 staging: raw lookup results per scheduled seed
-    unsigned long long raw_hits[2][MAX_LOOKUPS];
-    uint32_t raw_n[2][MAX_LOOKUPS];
-    uint16_t sched_off[MAX_LOOKUPS];
-    uint8_t sched_wrap[MAX_LOOKUPS];
-    uint32_t n_sched;
-    uint32_t used[16];
+    uint32_t n_sched_w[2];
     uint32_t total_hits[2][2], popular[2], n_look[2];
     int score_list[32];
     // phase 3 exchange
@@ -106,6 +110,7 @@ struct LaneLookup {
     const uint32_t *hits;
     uint32_t nh, cur, so, sid;
     uint32_t cur_val, prev_val;  // hits[cur] (if cur < nh) and hits[cur-1] (if cur > 0), kept in registers
+    uint32_t next_val;           // hits[cur+1] (if cur+1 < nh): requested when cur is set, so stepping down never waits for L2
     uint32_t words;  // hit-list words this lane has read (accounting for the roofline figure)
     bool act;
 };
@@ -122,9 +127,24 @@ __device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, int w, int
     l.cur = 0;
     l.words = 0;
     l.cur_val = l.nh > 0 ? __ldg(&l.hits[0]) : 0;
+    l.next_val = l.nh > 1 ? __ldg(&l.hits[1]) : 0;
     l.prev_val = 0;
     l.words += l.nh > 0;
     return l;
+}
+
+// Ask L2 for the genome window [loc, loc + span) of a location that phase 3 may score: lanes 0..3 touch one 128-byte line
+// each.  DRAM bandwidth is nearly idle on this path (ncu: < 1 % of peak) while a scored location otherwise starts with a
+// chain of dependent DRAM misses, so every candidate and mate is requested as soon as phase 2 creates it.
+__device__ __forceinline__ void prefetch_window(const DevIndex &ix, uint32_t loc, uint32_t span)
+{
+    // lane 0: the MAX_K bytes before loc that the backward Landau-Vishkin may look at; lanes 1..: loc, loc+128, ..., loc+span-1
+    const int lane = lane_id();
+    const long long o = lane == 0 ? -(long long)MAXK - 1 : (long long)(lane - 1) * 128;
+    if (o < (long long)span + 128) {
+        const long long at = (long long)loc + (o < (long long)span ? o : (long long)span - 1);
+        if (at >= -GENOME_PAD && at < (long long)ix.n_bases + GENOME_PAD) asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.genome + at));
+    }
 }
 
 __device__ __forceinline__ bool is_within(uint32_t a, uint32_t b, uint32_t dist)
@@ -165,6 +185,7 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
     if (l.act) {
         int lo = (int)l.cur, hi = (int)l.nh - 1;
         uint32_t want = max_loc + l.so;
+        #pragma unroll 1
         while (lo <= hi) {
             int probe = (lo + hi) / 2;
             uint32_t h = __ldg(&l.hits[probe]);
@@ -176,6 +197,7 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
                 l.cur = (uint32_t)probe;
                 l.cur_val = h;
                 l.prev_val = hp;
+                l.next_val = (uint32_t)probe + 1 < l.nh ? __ldg(&l.hits[probe + 1]) : 0;
                 break;
             }
             if (h > want) lo = probe + 1; else hi = probe - 1;
@@ -199,7 +221,11 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
         if (l.cur != l.nh && l.cur_val - l.so == *most_recent) {
             l.cur++;
             l.prev_val = l.cur_val;
-            if (l.cur != l.nh) { l.cur_val = __ldg(&l.hits[l.cur]); l.words++; }
+            if (l.cur != l.nh) {
+                l.cur_val = l.next_val;
+                l.words++;
+                if (l.cur + 1 < l.nh) l.next_val = __ldg(&l.hits[l.cur + 1]);
+            }
         }
         if (l.cur != l.nh) {
             val = l.cur_val - l.so;
@@ -228,40 +254,89 @@ __device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, uint32
     return max(max_exh, __reduce_max_sync(FULL_MASK, mine));
 }
 
-// leader: the seed schedule of one mate (IntersectingPairedEndAligner.cpp:259-339); every non-N seed is a lookup
-__device__ __forceinline__ void schedule_seeds_paired(PairedSm *sm, const uint8_t *read, uint32_t len, uint32_t seed_len,
-                                                      uint32_t max_seeds)
+// leader: the seed schedule of one mate (IntersectingPairedEndAligner.cpp:259-339); every non-N seed is a lookup.
+// Offsets go to sched_off[slot0..]; all_acgt: the read has no base that could invalidate a seed (skips the per-seed test).
+__device__ __forceinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, int w, uint32_t slot0, const uint8_t *read, uint32_t len, uint32_t seed_len,
+                                                      uint32_t max_seeds, bool all_acgt)
 {
     const uint32_t n_possible = len - seed_len + 1;
-    for (int i = 0; i < 16; i++) sm->used[i] = 0;
+    #pragma unroll 1
+    for (int i = 0; i < 16; i++) p1->used[i] = 0;
     uint32_t next = 0, wrap = 0, n = 0;
+    #pragma unroll 1
     while (n < n_possible && n < max_seeds) {
         if (next >= n_possible) {
             wrap++;
             if (wrap >= seed_len) break;
             next = wrapped_seed(seed_len, wrap);
         }
-        while (next < n_possible && (sm->used[next >> 5] >> (next & 31) & 1)) next++;
+        #pragma unroll 1
+        while (next < n_possible && (p1->used[next >> 5] >> (next & 31) & 1)) next++;
         if (next >= n_possible) continue;
-        sm->used[next >> 5] |= 1u << (next & 31);
-        bool ok = true;
-        for (uint32_t i = 0; i < seed_len; i++) ok &= base2(read[next + i]) >= 0;
-        if (!ok) { next++; continue; }  // :296-302
-        sm->sched_off[n] = (uint16_t)next;
-        sm->sched_wrap[n] = (uint8_t)wrap;
+        p1->used[next >> 5] |= 1u << (next & 31);
+        if (!all_acgt) {
+            bool ok = true;
+            #pragma unroll 1
+            for (uint32_t i = 0; i < seed_len; i++) ok &= base2(read[next + i]) >= 0;
+            if (!ok) { next++; continue; }  // :296-302
+        }
+        p1->sched_off[slot0 + n] = (uint16_t)next;
+        p1->sched_wrap[slot0 + n] = (uint8_t)wrap;
         n++;
         if ((max_seeds - n + 1) * seed_len + next < n_possible)  // :333-338 (n == countOfHashTableLookups here)
             next += (n_possible + next) / (max_seeds - n + 1);
         else
             next += seed_len;
     }
-    sm->n_sched = n;
+    sm->n_sched_w[w] = n;
 }
 
-// IntersectingPairedEndAligner::align.  All lanes.  v[0], v[1]: both mates staged (len set, Ns counted by caller).
+// leader: HashTableHitSet::recordLookup for the lookups of mate w in schedule order (:859-899); results at slot0..
+__device__ __forceinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits)
+{
+    bool begins[2] = {true, true};
+    uint32_t prev_wrap = 0;
+    const uint32_t n_sched = sm->n_sched_w[w];
+    #pragma unroll 1
+    for (uint32_t jj = 0; jj < n_sched; jj++) {
+        const uint32_t j = slot0 + jj;
+        if (p1->sched_wrap[j] != prev_wrap) { begins[0] = begins[1] = true; prev_wrap = p1->sched_wrap[j]; }
+        #pragma unroll 1
+        for (int d = 0; d < 2; d++) {
+            uint32_t n = p1->raw_n[d][j];
+            uint32_t offset = d == 0 ? p1->sched_off[j] : rlen - seed_len - p1->sched_off[j];
+            if (n < max_big_hits) {
+                sm->total_hits[w][d] += n;
+                if (begins[d]) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
+                begins[d] = false;
+                if (n == 0) {
+                    sm->exhausted[w][d][sm->cur_set[w][d]]++;
+                } else {
+                    const uint32_t *hp = (const uint32_t *)p1->raw_hits[d][j];
+                    if (p1->raw_last[d][j] < offset) {  // trim meaningless hits (:882-884); only at the very start of the genome
+                        n--;
+                        #pragma unroll 1
+                        while (n > 0 && __ldg(&hp[n - 1]) < offset) n--;
+                    }
+                    uint32_t k = sm->n_lookups[w][d]++;
+                    sm->hits[w][d][k] = (unsigned long long)hp;
+                    sm->nhits[w][d][k] = n;
+                    sm->seedoff[w][d][k] = (uint16_t)offset;
+                    sm->setid[w][d][k] = (uint8_t)sm->cur_set[w][d];
+                }
+            } else {
+                sm->popular[w]++;
+            }
+        }
+    }
+    sm->n_look[w] = n_sched;
+}
+
+// IntersectingPairedEndAligner::align.  All lanes.  v[0], v[1]: both mates staged (len set, Ns and non-ACGT bases
+// counted by the caller: total_ns, n_bad[2]).
 // Returns 0 = returned early leaving the result untouched, 1 = produced a result, 2 = scratch tier overflow.
 __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, const PairedScratch &sc, PairedSm *sm,
-                                     const ReadView *v, uint32_t total_ns, uint8_t *W, int16_t *L,
+                                     const ReadView *v, uint32_t total_ns, const uint32_t *n_bad, uint8_t *W, int16_t *L,
                                      snapb200_paired_result *r, uint32_t pair_index, const MapqFixList &fix)
 {
     const int lane = lane_id();
@@ -276,58 +351,56 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     long long t_a = clock64();
     // ---- phase 1 (:259-340) ----
     if (lane == 0) {
+        #pragma unroll 1
         for (int w = 0; w < 2; w++) {
             sm->popular[w] = 0; sm->n_look[w] = 0;
+            #pragma unroll 1
             for (int d = 0; d < 2; d++) { sm->total_hits[w][d] = 0; sm->n_lookups[w][d] = 0; sm->cur_set[w][d] = -1; }
         }
         sm->overflow = 0;
         sm->n_lv = 0;
         sm->n_probes = sm->n_hit_words = 0;
     }
-    for (int w = 0; w < 2; w++) {
+    // Both mates' seeds are probed in one round (mate w on lanes 16w..) when they fit the 32 lanes, so the dependent
+    // chain table entry -> overflow count word -> last hit word is paid once per pair, not once per mate.
+    Phase1Sm *p1 = (Phase1Sm *)L;
+    const bool together = max_seeds <= MAX_LOOKUPS / 2;
+    #pragma unroll 1
+    for (int pass = 0; pass < (together ? 1 : 2); pass++) {
         __syncwarp();
-        if (lane == 0) schedule_seeds_paired(sm, v[w].D[0], rlen[w], seed_len, max_seeds);
+        if (lane == 0) {
+            if (together) {
+                schedule_seeds_paired(sm, p1, 0, 0, v[0].D[0], rlen[0], seed_len, max_seeds, n_bad[0] == 0);
+                schedule_seeds_paired(sm, p1, 1, MAX_LOOKUPS / 2, v[1].D[0], rlen[1], seed_len, max_seeds, n_bad[1] == 0);
+            } else {
+                schedule_seeds_paired(sm, p1, pass, 0, v[pass].D[0], rlen[pass], seed_len, max_seeds, n_bad[pass] == 0);
+            }
+        }
         __syncwarp();
-        const uint32_t n_sched = sm->n_sched;
-        if ((uint32_t)lane < n_sched) {  // all seeds of this mate probed at once
+        const int w = together ? lane >> 4 : pass;
+        const uint32_t jj = together ? (uint32_t)lane & 15u : (uint32_t)lane;
+        if (jj < sm->n_sched_w[w]) {
             uint64_t sf, sr;
             HitList hl[2];
             uint32_t np = 0;
-            pack_seed(v[w].D[0] + sm->sched_off[lane], seed_len, &sf, &sr);
+            pack_seed(v[w].D[0] + p1->sched_off[lane], seed_len, &sf, &sr);
             lookup_seed(ix, sf, sr, hl, &np);
-            for (int d = 0; d < 2; d++) { sm->raw_hits[d][lane] = (unsigned long long)hl[d].hits; sm->raw_n[d][lane] = hl[d].n; }
+            #pragma unroll 1
+            for (int d = 0; d < 2; d++) {
+                p1->raw_hits[d][lane] = (unsigned long long)hl[d].hits;
+                p1->raw_n[d][lane] = hl[d].n;
+                p1->raw_last[d][lane] = (hl[d].n > 0 && hl[d].n < cfg.max_big_hits) ? __ldg(&hl[d].hits[hl[d].n - 1]) : 0xffffffffu;
+            }
             atomicAdd(&sm->n_probes, np + (hl[0].n > 1) + (hl[1].n > 1));  // table slots + overflow count words
         }
         __syncwarp();
-        if (lane == 0) {  // recordLookup in order (:859-899)
-            bool begins[2] = {true, true};
-            uint32_t prev_wrap = 0;
-            for (uint32_t j = 0; j < n_sched; j++) {
-                if (sm->sched_wrap[j] != prev_wrap) { begins[0] = begins[1] = true; prev_wrap = sm->sched_wrap[j]; }
-                for (int d = 0; d < 2; d++) {
-                    uint32_t n = sm->raw_n[d][j];
-                    uint32_t offset = d == 0 ? sm->sched_off[j] : rlen[w] - seed_len - sm->sched_off[j];
-                    if (n < cfg.max_big_hits) {
-                        sm->total_hits[w][d] += n;
-                        if (begins[d]) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
-                        begins[d] = false;
-                        if (n == 0) {
-                            sm->exhausted[w][d][sm->cur_set[w][d]]++;
-                        } else {
-                            const uint32_t *hp = (const uint32_t *)sm->raw_hits[d][j];
-                            while (n > 0 && __ldg(&hp[n - 1]) < offset) n--;  // trim meaningless hits (:882-884)
-                            uint32_t k = sm->n_lookups[w][d]++;
-                            sm->hits[w][d][k] = (unsigned long long)hp;
-                            sm->nhits[w][d][k] = n;
-                            sm->seedoff[w][d][k] = (uint16_t)offset;
-                            sm->setid[w][d][k] = (uint8_t)sm->cur_set[w][d];
-                        }
-                    } else {
-                        sm->popular[w]++;
-                    }
-                }
+        if (lane == 0) {
+            if (together) {
+                record_lookups_paired(sm, p1, 0, 0, rlen[0], seed_len, cfg.max_big_hits);
+                record_lookups_paired(sm, p1, 1, MAX_LOOKUPS / 2, rlen[1], seed_len, cfg.max_big_hits);
+            } else {
+                record_lookups_paired(sm, p1, pass, 0, rlen[pass], seed_len, cfg.max_big_hits);
             }
-            sm->n_look[w] = n_sched;
         }
     }
     __syncwarp();
@@ -335,6 +408,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     const int fewer = 1 - more;
     // setPairDirection (:351): set pair sp uses read0 in direction sp, read1 in direction 1-sp
     if (lane == 0) {
+        #pragma unroll 1
         for (uint32_t k = 0; k <= max_k + extra; k++) sm->score_list[k] = -1;
         sm->n_cands = 0; sm->n_mates[0] = sm->n_mates[1] = 0; sm->n_anchors = 0; sm->max_used_list = 0;
     }
@@ -343,6 +417,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     long long t_b = clock64();
     // ---- phase 2 (:359-511) ----
     uint32_t n_cands = 0, max_used_list = 0;
+    #pragma unroll 1
     for (int sp = 0; sp < 2; sp++) {
         const int dir_of[2] = {sp, 1 - sp};
         LaneLookup lf = load_lookup(sm, fewer, dir_of[fewer]);
@@ -350,7 +425,9 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         const uint8_t *exh_f = sm->exhausted[fewer][dir_of[fewer]], *exh_m = sm->exhausted[more][dir_of[more]];
         const int cs_f = sm->cur_set[fewer][dir_of[fewer]], cs_m = sm->cur_set[more][dir_of[more]];
         uint32_t maxexh_f = 0, maxexh_m = 0;
+        #pragma unroll 1
         for (int q = 0; q <= cs_f; q++) maxexh_f = max(maxexh_f, (uint32_t)exh_f[q]);
+        #pragma unroll 1
         for (int q = 0; q <= cs_m; q++) maxexh_m = max(maxexh_m, (uint32_t)exh_m[q]);
         const uint32_t exhl_f = lf.act ? exh_f[lf.sid] : 0, exhl_m = lm.act ? exh_m[lm.sid] : 0;
         uint32_t mr_f = 0, mr_m = 0;  // mostRecentLocationReturned of each set
@@ -360,6 +437,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         Mate *mates = sc.mates[sp];
         if (!hs_first(lf, &mr_f, &f_loc, &f_off)) continue;
         m_loc = INVALID_LOC;
+        #pragma unroll 1
         for (;;) {
             if (m_loc > f_loc + max_spacing) {
                 if (!hs_next_le(lm, &mr_m, f_loc + max_spacing, &m_loc, &m_off)) break;
@@ -368,9 +446,11 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 if (!hs_next_le(lf, &mr_f, m_loc + max_spacing, &f_loc, &f_off)) break;
                 continue;
             }
+            #pragma unroll 1
             while (m_loc + max_spacing >= f_loc && !out_of_more) {
                 uint32_t bp = hs_best_possible(lm, exhl_m, maxexh_m, mr_m, max_k);
                 if (n_mates >= cfg.mate_cap) return 2;
+                prefetch_window(ix, m_loc, rlen[more] + MAXK);
                 if (lane == 0) {
                     Mate *m = &mates[n_mates];
                     m->loc = m_loc; m->best_possible = bp; m->seed_offset = m_off;
@@ -389,6 +469,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             // lowest bestPossibleScore among the mates in range (:469-475): scan back from the newest mate, 32 per step
             uint32_t low_mate = max_k + extra;
             __syncwarp();  // the leader's mate records must be visible to the other lanes
+            #pragma unroll 1
             for (int top = (int)n_mates - 1; top >= 0; top -= 32) {
                 const int i = top - lane;
                 bool stop = false;
@@ -406,6 +487,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             }
             if (low_mate + bp_fewer <= max_k + extra) {
                 if (n_cands >= cfg.cand_cap) return 2;
+                prefetch_window(ix, f_loc, rlen[fewer] + MAXK);
                 if (lane == 0) {
                     Cand *c = &sc.cands[n_cands];
                     c->loc = f_loc; c->set_pair = (uint8_t)sp; c->mate_index = n_mates - 1; c->seed_offset = (uint16_t)f_off;
@@ -440,9 +522,11 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         sm->stop = 0;
     }
     __syncwarp();
+    #pragma unroll 1
     for (;;) {
         if (lane == 0) {
             uint32_t list = (uint32_t)sm->list;
+            #pragma unroll 1
             while (list <= max_used_list && list <= sm->score_limit && sm->score_list[list] < 0) list++;
             sm->list = (int)list;
             if (sm->stop || list > max_used_list || list > sm->score_limit) {
@@ -460,6 +544,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     int j = ci;
                     uint32_t nb = 0;
                     const bool lane_ok = sm->score_limit <= LANE_KMAX;
+                    #pragma unroll 1
                     while (nb < 32) {
                         if (j < 0) {
                             l++;
@@ -505,8 +590,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 uint32_t j = act_l ? cl->mate_index : 0;
                 Mate *mbase = sc.mates[spl];
                 uint32_t n_done = 0;
+                #pragma unroll 1
                 for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
                     Mate *mt = nullptr;
+                    #pragma unroll 1
                     while (walking) {
                         Mate *q = &mbase[j];
                         const bool needs = !is_within(q->loc, cloc, min_spacing) && q->best_possible <= (uint32_t)Km &&
@@ -520,6 +607,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     const unsigned long long key = (unsigned long long)mt;
                     const unsigned peers = __match_any_sync(FULL_MASK, key);
                     int gmax = 0;
+                    #pragma unroll 1
                     for (int src = 0; src < 32; src++) {
                         int kk = __shfl_sync(FULL_MASK, Km, src);
                         if ((peers >> src) & 1) gmax = max(gmax, kk);
@@ -561,6 +649,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         }
         if (fs != -1) {
             const uint32_t f_score = (uint32_t)fs;
+            #pragma unroll 1
             for (;;) {  // mates of this candidate (:559-711)
                 if (lane == 0) {
                     Mate *m = &sc.mates[sp][sm->mi];
@@ -578,6 +667,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                                 uint32_t nb = 0;
                                 const bool lane_ok = m_limit <= LANE_KMAX;
                                 uint32_t j = sm->mi;
+                                #pragma unroll 1
                                 for (;;) {
                                     Mate *q = &sc.mates[sp][j];
                                     if (!is_within(q->loc, sm->c_loc, min_spacing) && q->best_possible <= m_limit &&
@@ -643,12 +733,14 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                         int an = c->anchor;
                         const int ci = sm->ci;
                         if (an < 0) {  // look for a merge anchor among neighbouring candidates (:598-627)
+                            #pragma unroll 1
                             for (int j = ci - 1; j >= 0 && is_within(sc.cands[j].loc, new_fewer, 50) && sc.cands[j].set_pair == c->set_pair; j--) {
                                 if (sc.cands[j].anchor >= 0) { c->anchor = an = sc.cands[j].anchor; break; }
                             }
                             if (an < 0) {
                                 // the reference's second scan starts one above and walks DOWN (:615-619); below index 0 it
                                 // reads out of bounds there, which is treated as the end of the scan here
+                                #pragma unroll 1
                                 for (int j = ci + 1; j >= 0 && j < (int)sm->n_cands && is_within(sc.cands[j].loc, new_fewer, 50) &&
                                                  sc.cands[j].set_pair == c->set_pair; j--) {
                                     if (sc.cands[j].anchor >= 0) { c->anchor = an = sc.cands[j].anchor; break; }
@@ -722,10 +814,12 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         long long t_d = clock64();
         sm->t_phase[1] = t_b - t_a; sm->t_phase[2] = t_c - t_b; sm->t_phase[3] = t_lv; sm->t_phase[4] = (t_d - t_c) - t_lv;
         if (sm->best_pair_score == 65536) {
+            #pragma unroll 1
             for (int w = 0; w < 2; w++) {
                 r->location[w] = INVALID_LOC; r->mapq[w] = 0; r->score[w] = -1; r->status[w] = SNAPB200_NOT_FOUND;
             }
         } else {
+            #pragma unroll 1
             for (int w = 0; w < 2; w++) {
                 bool near_int;
                 int popular = (int)(sm->popular[0] + sm->popular[1]);

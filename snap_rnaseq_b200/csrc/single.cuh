@@ -64,14 +64,15 @@ struct ReadView {  // a read staged in shared memory in both orientations
     uint32_t len;
 };
 
-// all lanes; returns the number of 'N' bases
-__device__ __forceinline__ uint32_t stage_read(const ReadView &v, const uint8_t *bases, const uint8_t *quals)
+// all lanes; returns the number of 'N' bases; *n_not_acgt (optional): bases that cannot be part of a seed
+__device__ __forceinline__ uint32_t stage_read(const ReadView &v, const uint8_t *bases, const uint8_t *quals, uint32_t *n_not_acgt = nullptr)
 {
     const int lane = lane_id();
-    uint32_t ns = 0;
+    uint32_t ns = 0, bad = 0;
+    #pragma unroll 1
     for (uint32_t base = 0; base < v.len; base += 32) {
         uint32_t i = base + lane;
-        bool is_n = false;
+        bool is_n = false, is_bad = false;
         if (i < v.len) {
             uint8_t b = bases[i], q = quals[i];
             v.D[0][i] = b;
@@ -79,10 +80,13 @@ __device__ __forceinline__ uint32_t stage_read(const ReadView &v, const uint8_t 
             v.D[1][v.len - 1 - i] = rc_base(b);
             v.Q[1][v.len - 1 - i] = q;
             is_n = b == 'N';
+            is_bad = base2(b) < 0;
         }
         ns += __popc(__ballot_sync(FULL_MASK, is_n));
+        bad += __popc(__ballot_sync(FULL_MASK, is_bad));
     }
     __syncwarp();
+    if (n_not_acgt) *n_not_acgt = bad;
     return ns;
 }
 
@@ -93,6 +97,7 @@ __device__ __forceinline__ void stage_window(const DevIndex &ix, uint32_t loc, u
     const int lane = lane_id();
     const int n = (int)rlen + 2 * WIN_SLACK;
     const long long g0 = (long long)loc - WIN_SLACK;
+    #pragma unroll 1
     for (int j = lane; j < n; j += 32) {
         long long g = g0 + j;
         W[j] = (g >= -100 && g < (long long)ix.n_bases + 100) ? __ldg(ix.genome + g) : (uint8_t)0x01;
@@ -122,9 +127,11 @@ __device__ __noinline__ int score_location_warp(const DevIndex &ix, const ReadVi
             end_off = ix.n_bases;
         } else if (single_variant) {  // getNextPieceAfterLocation(loc)
             end_off = ix.n_bases;
+            #pragma unroll 1
             for (uint32_t i = 0; i < ix.n_pieces; i++) if (ix.piece_begin[i] > loc) { end_off = ix.piece_begin[i]; break; }
         } else {  // getPieceAtLocation(loc + rlen + MAX_K)
             end_off = 0;
+            #pragma unroll 1
             for (uint32_t i = 0; i < ix.n_pieces; i++) if (ix.piece_begin[i] <= loc + rlen + MAXK) end_off = ix.piece_begin[i];
         }
         glen = end_off - loc - 1;
@@ -219,6 +226,7 @@ __device__ __forceinline__ int find_element(const SingleScratch &sc, uint32_t tm
     int2 a = sc.anchors[dir][cand_slot(base, tmask)];
     if ((uint32_t)a.y != epoch) return -1;
     int e = a.x;
+    #pragma unroll 1
     while (e >= 0 && sc.pool[e].base != base) e = sc.pool[e].h_next;
     return e;
 }
@@ -369,6 +377,7 @@ __device__ __noinline__ bool single_score(const DevIndex &ix, const SingleCfg &c
 {
     const int lane = lane_id();
     if (lane == 0) {
+        #pragma unroll 1
         for (int d = 0; d < 2; d++) {
             uint32_t q = sm->n_applied[d] / sm->most_seeds;
             if (q > sm->lowest_unseen[d]) sm->lowest_unseen[d] = q;
@@ -376,9 +385,11 @@ __device__ __noinline__ bool single_score(const DevIndex &ix, const SingleCfg &c
         sm->list = (int)sm->highest_list;
         sm->force = force_in;
     }
+    #pragma unroll 1
     for (;;) {
         if (lane == 0) {
             int list = sm->list;
+            #pragma unroll 1
             while (list > 0 && sc.list_head[list] < 0) { list--; sm->highest_list = (uint32_t)list; }
             sm->list = list;
             int action = ACT_ELEMENT;
@@ -425,11 +436,13 @@ __device__ __noinline__ bool single_score(const DevIndex &ix, const SingleCfg &c
         if (action == ACT_RETURN_TRUE) return true;
         if (action == ACT_RETURN_FALSE) return false;
         // candidates of this element, ascending bit order
+        #pragma unroll 1
         for (;;) {
             if (lane == 0) {
                 Elem *el = &sc.pool[sm->cand_elem];
                 unsigned long long mask = sm->cand_mask;
                 int have = 0;
+                #pragma unroll 1
                 while (mask) {
                     int idx = __ffsll((long long)mask) - 1;
                     unsigned long long bit = 1ull << idx;
@@ -478,16 +491,19 @@ __device__ __forceinline__ void schedule_seeds_single(SingleSm *sm, const uint8_
     const uint32_t n_possible = len - seed_len + 1;
     uint32_t next = sm->next, wrap = sm->wrap, n = 0;
     sm->terminal = 0;
+    #pragma unroll 1
     while (n < 32) {
         if (next >= n_possible) {
             wrap++;
             if (wrap >= seed_len) { sm->terminal = 1; break; }
             next = wrapped_seed(seed_len, wrap);
         }
+        #pragma unroll 1
         while (next < n_possible && (sm->used[next >> 5] >> (next & 31) & 1)) next++;
         if (next >= n_possible) continue;
         sm->used[next >> 5] |= 1u << (next & 31);
         bool ok = true;
+        #pragma unroll 1
         for (uint32_t i = 0; i < seed_len; i++) ok &= base2(read[next + i]) >= 0;
         if (!ok) continue;  // seeds with N are skipped without counting (:742-744)
         sm->sched_off[n] = (uint16_t)next;
@@ -508,9 +524,12 @@ __device__ __forceinline__ void fill_hits(const SingleCfg &cfg, const SingleScra
     if (want == 0) return;
     int nf = 0;
     int first = 0;
+    #pragma unroll 1
     while (first < MAXK && sc.hit_count[first] == 0) first++;
     int last = min(first + 4, MAXK);
+    #pragma unroll 1
     for (int dist = first; dist < last; dist++) {
+        #pragma unroll 1
         for (uint32_t i = 0; i < sc.hit_count[dist]; i++) {
             uint32_t flat = (uint32_t)dist * 512 + i;
             locs[nf] = flat < MAXK * 512 ? sc.hit_loc[flat] : 0;
@@ -539,6 +558,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
         sm->p_all = sm->p_best = 0; sm->popular = 0; sm->n_lookups = sm->n_scored = 0; sm->overflow = 0;
         sm->n_probes = sm->n_hit_words = 0;
         if (cfg.max_hits_to_get > 0) {
+            #pragma unroll 1
             for (int i = 0; i < MAXK; i++) sc.hit_count[i] = 0;
             *mh_found = 0;
         }
@@ -556,7 +576,9 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
         sm->epoch = ++(*sc.epoch);
         sm->n_used = 0;
         sm->highest_list = 0;
+        #pragma unroll 1
         for (uint32_t i = 0; i < cfg.n_lists; i++) sc.list_head[i] = sc.list_tail[i] = -1;
+        #pragma unroll 1
         for (int i = 0; i < 16; i++) sm->used[i] = 0;
         sm->next = 0; sm->wrap = 0;
         sm->lowest_unseen[0] = sm->lowest_unseen[1] = 0;
@@ -568,6 +590,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
     }
     __syncwarp();
     bool answered = false, skip_fill = false;
+    #pragma unroll 1
     for (;;) {
         if (sm->n_applied[0] + sm->n_applied[1] >= max_seeds) break;
         if (lane == 0) schedule_seeds_single(sm, v.D[0], len, seed_len);
@@ -582,12 +605,14 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
             lookup_seed(ix, sf, sr, my, &my_probes);
         }
         bool out = false;
+        #pragma unroll 1
         for (uint32_t j = 0; j < n_sched; j++) {
             if (sm->n_applied[0] + sm->n_applied[1] >= max_seeds) { out = true; break; }
             const uint32_t seed_at = sm->sched_off[j];
             const uint32_t probes_j = __shfl_sync(FULL_MASK, my_probes, (int)j);
             if (lane == 0) { sm->most_seeds = (uint32_t)sm->sched_wrap[j] + 1; sm->n_lookups++; sm->n_probes += probes_j; }
             bool applied = false;
+            #pragma unroll 1
             for (int dir = 0; dir < 2; dir++) {
                 const uint32_t n = __shfl_sync(FULL_MASK, my[dir].n, (int)j);
                 const uint32_t *hits = (const uint32_t *)shfl_u64((uint64_t)my[dir].hits, (int)j);
@@ -597,6 +622,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
                 }
                 const uint32_t offset = dir == 0 ? seed_at : len - seed_len - seed_at;
                 const uint32_t lim = min(n, cfg.max_hits);
+                #pragma unroll 1
                 for (uint32_t base = 0; base < lim; base += 32) {
                     uint32_t i = base + lane;
                     int e = -2;  // -2: not a usable hit (BaseAligner.cpp:848-853)
@@ -614,6 +640,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
                     if (lane == 0) {
                         uint32_t cnt = min(32u, lim - base);
                         sm->alloc_in_chunk = 0;
+                        #pragma unroll 1
                         for (uint32_t q = 0; q < cnt && !sm->overflow; q++) {
                             if (sm->hit_elem[q] == -2) continue;
                             vote_hit(cfg, sc, sm, sm->hit_locs[q], sm->hit_elem[q], dir, offset);

@@ -922,6 +922,10 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
     int per_sm = 1;
     const size_t smem = paired_warp_shared(rl) * WARPS_PER_CTA;
     int grid = grid_for(paired_kernel, smem, x->sm_count, &per_sm);
+    if (const char *e = getenv("SNAPB200_CTAS_PER_SM")) {  // experiments only: fewer resident CTAs than fit
+        int v = atoi(e);
+        if (v >= 1 && v < per_sm) { per_sm = v; grid = v * x->sm_count; }
+    }
     if (n) {
         // small tier
         // first tier: ~1.4 MB of candidate records per warp (5 GB at full occupancy) holds all but pathological pairs

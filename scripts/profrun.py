@@ -1,7 +1,12 @@
 """Cycle-accounting run of the paired path (SNAPB200_PROF=1): where does a pair's time go?"""
 import os, sys, time
 os.environ["SNAPB200_PROF"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+if os.environ.get("PROF_PLAIN"):  # time the production build instead (no phase breakdown)
+    del os.environ["SNAPB200_PROF"]
+else:                             # the cycle accounting lives in the -DSNAPB200_PROFILE build (python -m snap_rnaseq_b200.build --profile)
+    os.environ["SNAPB200_SO"] = os.path.join(ROOT, "snap_rnaseq_b200", "libsnapb200_prof.so")
 import numpy as np
 import snap_rnaseq_b200 as S
 from snap_rnaseq_b200 import synth, _abi as A

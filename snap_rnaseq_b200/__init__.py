@@ -16,7 +16,8 @@ from ._abi import (Batch, IndexInfo, PairedParams, SingleParams, paired_defaults
 from ._binding import BatchLib
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsnapb200.so")
+# SNAPB200_SO: load another build of the same library (scripts/profrun.py uses the -DSNAPB200_PROFILE build)
+SO_PATH = os.environ.get("SNAPB200_SO") or os.path.join(_HERE, "libsnapb200.so")
 _lib = None
 
 

@@ -21,20 +21,28 @@ def stale():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
-        return SO
+SO_PROFILE = os.path.join(HERE, "libsnapb200_prof.so")  # same library with the cycle accounting compiled in (scripts/profrun.py)
+
+
+def build(force=False, verbose=False, profile=False):
+    if profile:
+        out, extra = SO_PROFILE, ["-DSNAPB200_PROFILE"]
+        if not force and os.path.exists(out) and not any(os.path.getmtime(s) > os.path.getmtime(out) for s in sources()):
+            return out
+    else:
+        out, extra = SO, []
+        if not force and not stale():
+            return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "snapb200.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "snapb200.cu")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("nvcc failed building libsnapb200.so")
     if verbose:
         print(r.stdout)
-    return SO
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(SO)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))

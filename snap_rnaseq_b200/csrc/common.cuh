@@ -16,6 +16,14 @@
 
 #include "../../include/snapb200.h"
 
+// Cycle accounting of paired_kernel (scripts/profrun.py) is compiled in only with -DSNAPB200_PROFILE: the kernels are
+// instruction-cache bound, so code that is not needed is kept out of them.
+#ifdef SNAPB200_PROFILE
+#define PROF(...) __VA_ARGS__
+#else
+#define PROF(...)
+#endif
+
 #define FULL_MASK 0xffffffffu
 #define MAXK SNAPB200_MAX_K           // 31
 #define INVALID_LOC 0xffffffffu

@@ -141,7 +141,8 @@ struct PairedArgs {
     Cand *cands; Mate *mates; Anchor *anchors; int16_t *lane_tables;  // [warp slot][...]
     Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
     unsigned long long *stats;
-    unsigned long long *prof;  // optional cycle accounting [8]
+    unsigned long long *prof;  // optional cycle accounting [8] (builds with -DSNAPB200_PROFILE)
+    uint32_t smem_per_warp;    // paired_warp_shared(cfg.rl), computed on the host
 };
 
 __host__ __device__ inline size_t paired_warp_shared(uint32_t rl)
@@ -157,8 +158,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const size_t per_warp = paired_warp_shared(a.cfg.rl);
-    uint8_t *base = smem + per_warp * warp;
+    uint8_t *base = smem + a.smem_per_warp * (uint32_t)warp;
     PairedSm *sm = (PairedSm *)base;
     base += (sizeof(PairedSm) + 15) & ~(size_t)15;
     int16_t *L = (int16_t *)base;
@@ -203,17 +203,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
             v[w].len = len[w];
             ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w], &n_bad[w]);
         }
-        if (lane == 0) for (int q = 0; q < 12; q++) sm->t_phase[q] = 0;
-        long long t_s = clock64();
+        PROF(if (lane == 0) for (int q = 0; q < 12; q++) sm->t_phase[q] = 0; long long t_s = clock64();)
         int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, n_bad, W, L, r, pi, fix);
-        if (lane == 0 && a.prof) {
+        PROF(if (lane == 0 && a.prof) {
             atomicAdd(a.prof + 0, (unsigned long long)(clock64() - t_s));
-            #pragma unroll 1
             for (int q = 1; q < 5; q++) atomicAdd(a.prof + q, (unsigned long long)sm->t_phase[q]);
             atomicAdd(a.prof + 5, 1ull);
-            #pragma unroll 1
             for (int q = 5; q < 10; q++) atomicAdd(a.prof + q + 1, (unsigned long long)sm->t_phase[q]);
-        }
+        })
         if (lane == 0) {
             if (rc == 2) {
                 if (a.cfg.hard_limit) {
@@ -246,6 +243,43 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
             }
         }
         __syncwarp();
+    }
+}
+
+// ---- work ordering for the paired path ------------------------------------------------------------------------------------
+// Pairs differ in cost by four orders of magnitude (median 2 scored locations, maximum several thousand: reads from repeat
+// families), and a warp keeps one pair until it is done.  Served in input order, the heavy pairs that happen to come late
+// leave most SMs idle at the end of a launch, and heavy and ordinary pairs executing side by side on an SM compete for the
+// instruction cache.  So before the aligner runs, this kernel estimates each pair's weight from four index probes (first
+// and last seed of each mate) and the host sorts the pairs heaviest first (stable: ordinary pairs stay in input order).
+// The order changes nothing in the results: pairs are independent and every pair writes only its own record.
+// Thread t: pair t>>2, mate (t>>1)&1, seed at the start (t&1 == 0) or the end of the mate.
+__global__ void weigh_pairs_kernel(const DevIndex ix, const DevBatch b0, const DevBatch b1, uint32_t n, uint32_t max_big_hits,
+                                   uint32_t *keys, uint32_t *vals)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pair = t >> 2;
+    uint32_t w = 0;
+    if (pair < n) {
+        const DevBatch &b = (t >> 1) & 1 ? b1 : b0;
+        const uint32_t off = b.offsets[pair], len = b.offsets[pair + 1] - off;
+        if (len >= ix.seed_len) {
+            const uint8_t *seed = b.bases + off + ((t & 1) ? len - ix.seed_len : 0);
+            uint64_t f, r;
+            if (pack_seed(seed, ix.seed_len, &f, &r)) {
+                HitList hl[2];
+                lookup_seed(ix, f, r, hl, nullptr);
+                w = min(hl[0].n, max_big_hits) + min(hl[1].n, max_big_hits);
+            }
+        }
+    }
+    w += __shfl_xor_sync(FULL_MASK, w, 1);
+    w += __shfl_xor_sync(FULL_MASK, w, 2);
+    if (pair < n && (t & 3) == 0) {
+        // 16-bit sort key, ascending = heaviest first; everything light shares the last key and keeps its input order
+        const uint32_t q = w >> 3;
+        keys[pair] = q == 0 ? 0xffffu : 0xfffeu - min(q, 0xfffeu);
+        vals[pair] = pair;
     }
 }
 

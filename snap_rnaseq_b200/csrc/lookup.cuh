@@ -77,23 +77,47 @@ __device__ __forceinline__ void lookup_seed(const DevIndex &ix, uint64_t fwd, ui
     out[0].hits = out[1].hits = nullptr;
     const HtEntry *t = ix.tables + ix.table_start[hi];
     const uint64_t size = ix.table_size[hi];
-    uint64_t idx = ht_hash(lo) % size;
     uint32_t np = 1;
-    const HtEntry *e = &t[idx];
-    uint32_t key = __ldg(&e->key), v1 = __ldg(&e->v1);
-    if (!(key == lo && v1 != INVALID_LOC)) {
-        uint64_t n = 0;
-        #pragma unroll 1
-        do {
-            n++;
-            if (n > size + 5) { e = nullptr; break; }
-            idx = (n < 5) ? (idx + n * n) % size : (idx + 1) % size;
-            e = &t[idx];
-            key = __ldg(&e->key);
-            v1 = __ldg(&e->v1);
-            np++;
-        } while (key != lo && v1 != INVALID_LOC);
-        if (e && v1 == INVALID_LOC) e = nullptr;
+    const HtEntry *e;
+    uint32_t key, v1;
+    if (size <= 0xffffffffull) {  // every real table: 32-bit remainders instead of the 64-bit software routine
+        const uint32_t sz = (uint32_t)size;
+        uint32_t idx = ht_hash(lo) % sz;
+        e = &t[idx];
+        key = __ldg(&e->key); v1 = __ldg(&e->v1);
+        if (!(key == lo && v1 != INVALID_LOC)) {
+            uint32_t n = 0;
+            #pragma unroll 1
+            do {
+                n++;
+                if (n > sz && n - sz > 5) { e = nullptr; break; }
+                const uint32_t step = n < 5 ? n * n : 1u;  // +1,+4,+9,+16, then linear (HashTable.h:74-105)
+                idx = (uint32_t)(((uint64_t)idx + step) % sz);
+                e = &t[idx];
+                key = __ldg(&e->key);
+                v1 = __ldg(&e->v1);
+                np++;
+            } while (key != lo && v1 != INVALID_LOC);
+            if (e && v1 == INVALID_LOC) e = nullptr;
+        }
+    } else {
+        uint64_t idx = ht_hash(lo) % size;
+        e = &t[idx];
+        key = __ldg(&e->key); v1 = __ldg(&e->v1);
+        if (!(key == lo && v1 != INVALID_LOC)) {
+            uint64_t n = 0;
+            #pragma unroll 1
+            do {
+                n++;
+                if (n > size + 5) { e = nullptr; break; }
+                idx = (n < 5) ? (idx + n * n) % size : (idx + 1) % size;
+                e = &t[idx];
+                key = __ldg(&e->key);
+                v1 = __ldg(&e->v1);
+                np++;
+            } while (key != lo && v1 != INVALID_LOC);
+            if (e && v1 == INVALID_LOC) e = nullptr;
+        }
     }
     if (probes) *probes = np;
     if (!e) return;

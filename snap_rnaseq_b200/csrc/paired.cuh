@@ -256,7 +256,7 @@ __device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, uint32
 
 // leader: the seed schedule of one mate (IntersectingPairedEndAligner.cpp:259-339); every non-N seed is a lookup.
 // Offsets go to sched_off[slot0..]; all_acgt: the read has no base that could invalidate a seed (skips the per-seed test).
-__device__ __forceinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, int w, uint32_t slot0, const uint8_t *read, uint32_t len, uint32_t seed_len,
+__device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, int w, uint32_t slot0, const uint8_t *read, uint32_t len, uint32_t seed_len,
                                                       uint32_t max_seeds, bool all_acgt)
 {
     const uint32_t n_possible = len - seed_len + 1;
@@ -292,7 +292,7 @@ __device__ __forceinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1
 }
 
 // leader: HashTableHitSet::recordLookup for the lookups of mate w in schedule order (:859-899); results at slot0..
-__device__ __forceinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits)
+__device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits)
 {
     bool begins[2] = {true, true};
     uint32_t prev_wrap = 0;
@@ -348,7 +348,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     if (rlen[0] < 50 || rlen[1] < 50) return 0;  // :186-188
     if (total_ns > max_k) return 0;              // :226-228
 
-    long long t_a = clock64();
+    PROF(long long t_a = clock64();)
     // ---- phase 1 (:259-340) ----
     if (lane == 0) {
         #pragma unroll 1
@@ -414,7 +414,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     }
     __syncwarp();
 
-    long long t_b = clock64();
+    PROF(long long t_b = clock64();)
     // ---- phase 2 (:359-511) ----
     uint32_t n_cands = 0, max_used_list = 0;
     #pragma unroll 1
@@ -505,8 +505,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     }
     __syncwarp();
 
-    long long t_c = clock64();
-    long long t_lv = 0;
+    PROF(long long t_c = clock64(); long long t_lv = 0;)
     // ---- phase 3 (:516-720) ----
     // The visiting order of candidates (lists 0,1,2..., LIFO inside a list) and of a candidate's mates is fixed once
     // phase 2 is done, and an LV result for limit k is (d <= k ? (d, probability, netIndel) : -1) with d, probability and
@@ -564,7 +563,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         if (!sm->act) break;
         const uint32_t sp = sm->c_sp;
         const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
-        long long t_x = clock64();
+        PROF(long long t_x = clock64();)
         const uint32_t n_batch = sm->n_batch;
         if (n_batch >= LANE_MIN_BATCH) {
             // lane mode: lane i scores candidate batch_ids[i] with K = current limit
@@ -577,11 +576,11 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             score_location_lane(ix, v[fewer], dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
             if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
             __syncwarp();
-            if (lane == 0) { sm->t_phase[5] += clock64() - t_x; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; }
+            PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_x; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
             // Mate look-ahead: a candidate whose fewer end scored s will ask its mates for a score with limit <= K - s.
             // Each lane walks the mates of its own candidate and, per round, one still-unknown mate per lane is scored.
             {
-                long long t_m = clock64();
+                PROF(long long t_m = clock64();)
                 bool walking = act_l && s >= 0;
                 const int Km = K - (s > 0 ? s : 0);
                 const uint32_t spl = act_l ? cl->set_pair : 0;
@@ -621,7 +620,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     n_done += __popc(__ballot_sync(FULL_MASK, mine));
                     __syncwarp();
                 }
-                if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; }
+                PROF(if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; })
             }
         }
         if (lane == 0) sm->act = sc.cands[sm->ci].c_score == SC_NONE;
@@ -630,14 +629,14 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             double pr;
             int off;
             const int K = (int)sm->score_limit;
-            long long t_w = clock64();
+            PROF(long long t_w = clock64();)
             int s = score_location_warp(ix, v[fewer], dir_f, sm->c_loc, sm->c_seedoff, K, false, W, L, &pr, &off);
             __syncwarp();
-            if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; }
+            PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
             if (lane == 0) { Cand *c = &sc.cands[sm->ci]; c->c_score = (int16_t)s; c->c_k = (uint8_t)K; c->c_off = (int8_t)off; c->c_prob = pr; }
             __syncwarp();
         }
-        t_lv += clock64() - t_x;
+        PROF(t_lv += clock64() - t_x;)
         int fs, f_off;
         double f_prob;
         {
@@ -687,7 +686,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 __syncwarp();
                 const int act = sm->act;
                 if (act == 2) {
-                    long long t_y = clock64();
+                    PROF(long long t_y = clock64();)
                     const uint32_t nb = sm->n_batch;
                     const int K = (int)sm->m_limit;
                     if (nb >= LANE_MIN_BATCH) {
@@ -698,17 +697,17 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                         score_location_lane(ix, v[more], dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
                         if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
                         __syncwarp();
-                        if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; }
+                        PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; })
                     }
                     if (lane == 0) { const Mate *m = &sc.mates[sp][sm->mi]; sm->act2 = !mate_known(m, sm->m_limit); }
                     __syncwarp();
                     if (sm->act2) {
                         double m_prob;
                         int m_off;
-                        long long t_w = clock64();
+                        PROF(long long t_w = clock64();)
                         int ms = score_location_warp(ix, v[more], dir_m, sm->m_loc, sm->m_seedoff, K, false, W, L, &m_prob, &m_off);
                         __syncwarp();
-                        if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; }
+                        PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
                         if (lane == 0) { Mate *m = &sc.mates[sp][sm->mi]; m->s_score = (int16_t)ms; m->s_k = (uint8_t)K; m->s_off = (int8_t)m_off; m->s_prob = m_prob; }
                         __syncwarp();
                     }
@@ -721,7 +720,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                         m->genome_offset = ok ? (int)m->s_off : 0;
                         m->score_limit = sm->m_limit;
                     }
-                    t_lv += clock64() - t_y;
+                    PROF(t_lv += clock64() - t_y;)
                 }
                 if (lane == 0) {
                     Mate *m = &sc.mates[sp][sm->mi];
@@ -811,8 +810,8 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     }
 
     if (lane == 0) {
-        long long t_d = clock64();
-        sm->t_phase[1] = t_b - t_a; sm->t_phase[2] = t_c - t_b; sm->t_phase[3] = t_lv; sm->t_phase[4] = (t_d - t_c) - t_lv;
+        PROF(long long t_d = clock64();)
+        PROF(sm->t_phase[1] = t_b - t_a; sm->t_phase[2] = t_c - t_b; sm->t_phase[3] = t_lv; sm->t_phase[4] = (t_d - t_c) - t_lv;)
         if (sm->best_pair_score == 65536) {
             #pragma unroll 1
             for (int w = 0; w < 2; w++) {

@@ -492,6 +492,7 @@ struct snapb200_session {
     // scratch tiers
     DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
     DevBuf p_cands, p_mates, p_anchors, p_lane_tables;
+    DevBuf w_keys[2], w_vals[2], w_tmp;  // work ordering of the paired path (weigh_pairs_kernel + radix sort)
     uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
     uint32_t anchors_warps = 0;
     // last run
@@ -540,7 +541,8 @@ extern "C" void snapb200_session_destroy(snapb200_session *s)
     DevBuf *all[] = {&s->offsets[0], &s->offsets[1], &s->bases[0], &s->bases[1], &s->quals[0], &s->quals[1], &s->single_res,
                      &s->paired_res, &s->fb_single_res, &s->retry_list, &s->fallback_list, &s->fb_positions, &s->fix, &s->counters,
                      &s->mh_counts, &s->mh_locs, &s->mh_rcs, &s->mh_scores, &s->s_pool, &s->s_anchors, &s->s_lists, &s->s_epochs,
-                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables};
+                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables,
+                     &s->w_keys[0], &s->w_keys[1], &s->w_vals[0], &s->w_vals[1], &s->w_tmp};
     for (DevBuf *b : all) b->release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -868,7 +870,11 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     a.stats = x->stats;
     a.prof = nullptr;
     static DevBuf prof_buf;
+#ifdef SNAPB200_PROFILE
     const bool prof = getenv("SNAPB200_PROF") != nullptr;
+#else
+    const bool prof = false;
+#endif
     if (prof) {
         if ((rc = prof_buf.ensure(128))) return rc;
         CUDA_TRY(cudaMemsetAsync(prof_buf.p, 0, 128, s->stream));
@@ -876,6 +882,7 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     }
     if ((rc = reset_work(s))) return rc;
     const size_t smem = paired_warp_shared(cfg.rl) * WARPS_PER_CTA;
+    a.smem_per_warp = (uint32_t)paired_warp_shared(cfg.rl);
     const bool time_it = s->main_pending;
     if (time_it) CUDA_TRY(cudaEventRecord(s->evm0, s->stream));
     paired_kernel<<<grid, CTA_THREADS, smem, s->stream>>>(a);
@@ -933,7 +940,24 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
         cfg.mate_cap = (uint32_t)std::min<uint64_t>(ref_pool / 2, 12288);
         cfg.anchor_cap = cfg.cand_cap;
         cfg.hard_limit = (cfg.cand_cap == ref_pool && cfg.mate_cap == ref_pool / 2) ? 1 : 0;
-        if ((rc = launch_paired(s, p, cfg, grid, nullptr, n))) return rc;
+        // heaviest pairs first (see weigh_pairs_kernel); SNAPB200_NO_ORDER=1 serves them in input order (experiments)
+        const uint32_t *order = nullptr;
+        if (n >= 4096 && !getenv("SNAPB200_NO_ORDER")) {
+            for (int q = 0; q < 2; q++) if ((rc = s->w_keys[q].ensure((size_t)n * 4)) || (rc = s->w_vals[q].ensure((size_t)n * 4))) return rc;
+            weigh_pairs_kernel<<<(unsigned)(((size_t)4 * n + 255) / 256), 256, 0, s->stream>>>(x->dev, dev_batch(s, 0), dev_batch(s, 1), n, p->max_big_hits,
+                                                                                           s->w_keys[0].as<uint32_t>(), s->w_vals[0].as<uint32_t>());
+            CUDA_TRY(cudaGetLastError());
+            s->last_launches++;
+            cub::DoubleBuffer<uint32_t> kb(s->w_keys[0].as<uint32_t>(), s->w_keys[1].as<uint32_t>());
+            cub::DoubleBuffer<uint32_t> vb(s->w_vals[0].as<uint32_t>(), s->w_vals[1].as<uint32_t>());
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 16, s->stream);
+            if ((rc = s->w_tmp.ensure(tmp_bytes))) return rc;
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->w_tmp.p, tmp_bytes, kb, vb, (int)n, 0, 16, s->stream));
+            s->last_launches += 2;  // histogram + onesweep
+            order = vb.Current();
+        }
+        if ((rc = launch_paired(s, p, cfg, grid, order, n))) return rc;
         Counters c;
         if ((rc = read_counters(s, &c))) return rc;
         if (c.n_retry) {

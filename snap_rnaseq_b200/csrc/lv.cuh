@@ -35,6 +35,31 @@ __device__ __forceinline__ int lv_get(const int16_t *L, int e, int d)
     return (d >= -e && d <= e) ? (int)L[e * e + d + e] : -2;
 }
 
+__device__ __forceinline__ uint32_t lv_ld4(const uint8_t *p)
+{  // unaligned 4-byte little-endian load (shared or global memory): the two enclosing aligned words, funnel-shifted
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (unsigned)(a & 3) * 8);
+}
+
+// first index i in [from, dend) with pattern(i) != text(d + i), or dend.  Four positions per step while eight more bytes
+// of both strings exist in memory (the word loads look at most seven bytes past the four they need), then byte by byte.
+__device__ __forceinline__ int lv_extend(const LvStr &s, int from, int d, int dend)
+{
+    int i = from;
+    #pragma unroll 1
+    while (i + 8 <= dend && d + i >= s.t_lo && d + i + 8 <= s.t_hi) {
+        const uint32_t a = s.ps > 0 ? lv_ld4(s.p + i) : __byte_perm(lv_ld4(s.p - i - 3), 0, 0x0123);
+        const uint32_t b = s.ts > 0 ? lv_ld4(s.t + (d + i)) : __byte_perm(lv_ld4(s.t - (d + i) - 3), 0, 0x0123);
+        const uint32_t x = a ^ b;
+        if (x) return i + ((__ffs((int)x) - 1) >> 3);
+        i += 4;
+    }
+    #pragma unroll 1
+    while (i < dend && lv_pat(s, i) == lv_txt(s, d + i)) i++;
+    return i;
+}
+
 // One cell: best of (substitution, deletion, insertion) from the row above, then extend along the diagonal.
 __device__ __forceinline__ int lv_cell(const LvStr &s, const int16_t *L, int e, int d)
 {
@@ -46,8 +71,7 @@ __device__ __forceinline__ int lv_cell(const LvStr &s, const int16_t *L, int e, 
     if (lv_pat(s, best) == lv_txt(s, d + best)) {
         int dend = min(s.plen, s.tlen - d);
         if (best < dend) {
-            #pragma unroll 1
-            do { best++; } while (best < dend && lv_pat(s, best) == lv_txt(s, d + best));
+            best = lv_extend(s, best + 1, d, dend);
         } else {
             best = dend;  // the reference's 8-byte loop clamps to `end` even when it starts beyond it
         }
@@ -114,9 +138,12 @@ __device__ __forceinline__ int lv_rows(const LvStr &s, int16_t *L, int k, int *w
 
 // LandauVishkin<DIR>::computeEditDistance.  q: quality(i) = q[i*qs] or NULL.  All lanes return the same
 // values.  L: LV_CELLS int16 in shared memory private to this warp.
-__device__ __noinline__ int lv_score_warp(const LvStr &s, const uint8_t *q, int qs, int k, const DevIndex &ix, int16_t *L,
+__device__ __noinline__ int lv_score_warp(const LvStr &s_in, const uint8_t *q, int qs, int k, const DevIndex &ix, int16_t *L,
                              double *match_prob, int *net_indel)
 {
+    // a private copy: the caller's struct sits on its stack, and through the reference every field would be re-read from
+    // local memory after each store to L (ncu: lv_pat/lv_txt were 45 % of the kernel's local-memory instructions)
+    const LvStr s = {s_in.p, s_in.ps, s_in.plen, s_in.t, s_in.ts, s_in.tlen, s_in.t_lo, s_in.t_hi};
     const int lane = lane_id();
     *net_indel = 0;
     *match_prob = 0.0;
@@ -216,8 +243,9 @@ __device__ inline bool cigar_put(CigarOut &o, int count, char code)
 }
 
 // LandauVishkinWithCigar::computeEditDistance, COMPACT_CIGAR_STRING.  The leader lane writes the string.
-__device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int cigar_len, bool use_m)
+__device__ int lv_cigar_warp(const LvStr &s_in, int k, int16_t *L, char *cigar, int cigar_len, bool use_m)
 {
+    const LvStr s = {s_in.p, s_in.ps, s_in.plen, s_in.t, s_in.ts, s_in.tlen, s_in.t_lo, s_in.t_hi};
     const int lane = lane_id();
     const int plen = s.plen;
     int end = min(plen, s.tlen);
@@ -348,32 +376,35 @@ __device__ int lv_cigar_warp(const LvStr &s, int k, int16_t *L, char *cigar, int
 #define LANE_ROLL_CELLS (2 * LANE_ROW)    // per lane: previous row + current row
 #define LANE_TABLE_CELLS ((LANE_KMAX + 1) * (LANE_KMAX + 1))  // per lane: the full triangular table, spilled to HBM scratch
 
-__device__ __forceinline__ uint32_t ld4_any(const uint8_t *p)
-{  // unaligned 4-byte little-endian load from shared or global memory (reads the two enclosing aligned words)
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
-    return __funnelshift_r(w[0], w[1], (unsigned)(a & 3) * 8);
-}
-
-// four consecutive string bytes starting at index i, byte 0 of the result = string(i)
-template <int DIR>
-__device__ __forceinline__ uint32_t str4(const uint8_t *base, int i)
-{
-    if (DIR > 0) return ld4_any(base + i);
-    return __byte_perm(ld4_any(base - i - 3), 0, 0x0123);
-}
-
-// length of the common run of pattern[pi..] and text[ti..], at most plen - pi
+// length of the common run of pattern[pi..] and text[ti..], at most plen - pi.  Both strings are walked one aligned
+// 32-bit word per step (the byte alignment of each string is constant along the run, so the funnel-shift amounts are
+// too); the text word of the NEXT step is requested before the current one is compared, which takes the L1/L2 latency
+// of the genome off the dependent chain.  Words up to seven bytes beyond either string are read (never compared).
 template <int DIR>
 __device__ __forceinline__ int lane_run(const uint8_t *p, const uint8_t *t, int pi, int ti, int plen)
 {
     const int rem = plen - pi;
+    if (rem <= 0) return 0;
+    // first byte compared in memory order: string(i) lives at base + DIR * i; a step covers 4 bytes at [a, a+3]
+    const uintptr_t pa = (uintptr_t)(DIR > 0 ? p + pi : p - pi - 3), ta = (uintptr_t)(DIR > 0 ? t + ti : t - ti - 3);
+    const uint32_t *pw = (const uint32_t *)(pa & ~(uintptr_t)3), *tw = (const uint32_t *)(ta & ~(uintptr_t)3);
+    const unsigned psh = (unsigned)(pa & 3) * 8, tsh = (unsigned)(ta & 3) * 8;
+    uint32_t p0 = pw[0], p1 = pw[1], t0 = tw[0], t1 = tw[1];
     int n = 0;
     #pragma unroll 1
-    while (n < rem) {
-        uint32_t x = str4<DIR>(p, pi + n) ^ str4<DIR>(t, ti + n);
-        if (x) { n += (__ffs((int)x) - 1) >> 3; break; }
+    for (;;) {
+        // the words the next step needs: one further along the walk (up for DIR > 0, down for DIR < 0)
+        pw += DIR; tw += DIR;
+        const uint32_t pn = DIR > 0 ? pw[1] : pw[0], tn = DIR > 0 ? tw[1] : tw[0];
+        uint32_t x = __funnelshift_r(p0, p1, psh) ^ __funnelshift_r(t0, t1, tsh);
+        if (x) {
+            if (DIR < 0) x = __byte_perm(x, 0, 0x0123);  // string order is descending addresses
+            n += (__ffs((int)x) - 1) >> 3;
+            break;
+        }
         n += 4;
+        if (n >= rem) break;
+        if (DIR > 0) { p0 = p1; p1 = pn; t0 = t1; t1 = tn; } else { p1 = p0; p0 = pn; t1 = t0; t0 = tn; }
     }
     return n < rem ? n : rem;
 }

@@ -15,7 +15,7 @@
 
 #define SC_NONE (-3)       // "score not computed yet" in the look-ahead caches below
 #define MATE_LOOKAHEAD_ROUNDS 2  // mates scored ahead per candidate of a lane-mode batch
-#define LANE_MIN_BATCH 3   // fewer pending locations than this: the warp-cooperative LV is cheaper
+#define LANE_MIN_BATCH 3   // fewer pending locations than this: the warp-cooperative LV is used (measured: no gain from lane mode below it)
 
 struct __align__(8) Mate {  // ScoringMateCandidate (IntersectingPairedEndAligner.h:401-423)
     double prob;
@@ -294,21 +294,21 @@ __device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, i
 // leader: HashTableHitSet::recordLookup for the lookups of mate w in schedule order (:859-899); results at slot0..
 __device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits)
 {
-    bool begins[2] = {true, true};
+    uint32_t begins = 3;  // bit d: the next lookup of direction d starts a new disjoint hit set
     uint32_t prev_wrap = 0;
     const uint32_t n_sched = sm->n_sched_w[w];
     #pragma unroll 1
     for (uint32_t jj = 0; jj < n_sched; jj++) {
         const uint32_t j = slot0 + jj;
-        if (p1->sched_wrap[j] != prev_wrap) { begins[0] = begins[1] = true; prev_wrap = p1->sched_wrap[j]; }
+        if (p1->sched_wrap[j] != prev_wrap) { begins = 3; prev_wrap = p1->sched_wrap[j]; }
         #pragma unroll 1
         for (int d = 0; d < 2; d++) {
             uint32_t n = p1->raw_n[d][j];
             uint32_t offset = d == 0 ? p1->sched_off[j] : rlen - seed_len - p1->sched_off[j];
             if (n < max_big_hits) {
                 sm->total_hits[w][d] += n;
-                if (begins[d]) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
-                begins[d] = false;
+                if (begins >> d & 1) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
+                begins &= ~(1u << d);
                 if (n == 0) {
                     sm->exhausted[w][d][sm->cur_set[w][d]]++;
                 } else {
@@ -342,10 +342,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     const int lane = lane_id();
     const uint32_t seed_len = ix.seed_len, max_k = cfg.max_k, extra = cfg.extra;
     const uint32_t max_spacing = cfg.max_spacing, min_spacing = cfg.min_spacing;
-    const uint32_t rlen[2] = {v[0].len, v[1].len};
-    uint32_t max_seeds = cfg.num_seeds ? cfg.num_seeds : (uint32_t)(max(rlen[0], rlen[1]) * cfg.seed_coverage / seed_len);
+    const uint32_t rlen0 = v[0].len, rlen1 = v[1].len;
+    uint32_t max_seeds = cfg.num_seeds ? cfg.num_seeds : (uint32_t)(max(rlen0, rlen1) * cfg.seed_coverage / seed_len);
     if (max_seeds > MAX_LOOKUPS) max_seeds = MAX_LOOKUPS;  // rejected on the host; belt and braces
-    if (rlen[0] < 50 || rlen[1] < 50) return 0;  // :186-188
+    if (rlen0 < 50 || rlen1 < 50) return 0;  // :186-188
     if (total_ns > max_k) return 0;              // :226-228
 
     PROF(long long t_a = clock64();)
@@ -370,10 +370,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         __syncwarp();
         if (lane == 0) {
             if (together) {
-                schedule_seeds_paired(sm, p1, 0, 0, v[0].D[0], rlen[0], seed_len, max_seeds, n_bad[0] == 0);
-                schedule_seeds_paired(sm, p1, 1, MAX_LOOKUPS / 2, v[1].D[0], rlen[1], seed_len, max_seeds, n_bad[1] == 0);
+                schedule_seeds_paired(sm, p1, 0, 0, v[0].D[0], rlen0, seed_len, max_seeds, n_bad[0] == 0);
+                schedule_seeds_paired(sm, p1, 1, MAX_LOOKUPS / 2, v[1].D[0], rlen1, seed_len, max_seeds, n_bad[1] == 0);
             } else {
-                schedule_seeds_paired(sm, p1, pass, 0, v[pass].D[0], rlen[pass], seed_len, max_seeds, n_bad[pass] == 0);
+                schedule_seeds_paired(sm, p1, pass, 0, v[pass].D[0], pass ? rlen1 : rlen0, seed_len, max_seeds, n_bad[pass] == 0);
             }
         }
         __syncwarp();
@@ -396,16 +396,17 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         __syncwarp();
         if (lane == 0) {
             if (together) {
-                record_lookups_paired(sm, p1, 0, 0, rlen[0], seed_len, cfg.max_big_hits);
-                record_lookups_paired(sm, p1, 1, MAX_LOOKUPS / 2, rlen[1], seed_len, cfg.max_big_hits);
+                record_lookups_paired(sm, p1, 0, 0, rlen0, seed_len, cfg.max_big_hits);
+                record_lookups_paired(sm, p1, 1, MAX_LOOKUPS / 2, rlen1, seed_len, cfg.max_big_hits);
             } else {
-                record_lookups_paired(sm, p1, pass, 0, rlen[pass], seed_len, cfg.max_big_hits);
+                record_lookups_paired(sm, p1, pass, 0, pass ? rlen1 : rlen0, seed_len, cfg.max_big_hits);
             }
         }
     }
     __syncwarp();
     const int more = (sm->total_hits[0][0] + sm->total_hits[0][1] > sm->total_hits[1][0] + sm->total_hits[1][1]) ? 0 : 1;  // :342
     const int fewer = 1 - more;
+    const uint32_t span_f = (fewer ? rlen1 : rlen0) + MAXK, span_m = (more ? rlen1 : rlen0) + MAXK;  // genome window of a scored location
     // setPairDirection (:351): set pair sp uses read0 in direction sp, read1 in direction 1-sp
     if (lane == 0) {
         #pragma unroll 1
@@ -450,7 +451,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             while (m_loc + max_spacing >= f_loc && !out_of_more) {
                 uint32_t bp = hs_best_possible(lm, exhl_m, maxexh_m, mr_m, max_k);
                 if (n_mates >= cfg.mate_cap) return 2;
-                prefetch_window(ix, m_loc, rlen[more] + MAXK);
+                prefetch_window(ix, m_loc, span_m);
                 if (lane == 0) {
                     Mate *m = &mates[n_mates];
                     m->loc = m_loc; m->best_possible = bp; m->seed_offset = m_off;
@@ -487,7 +488,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             }
             if (low_mate + bp_fewer <= max_k + extra) {
                 if (n_cands >= cfg.cand_cap) return 2;
-                prefetch_window(ix, f_loc, rlen[fewer] + MAXK);
+                prefetch_window(ix, f_loc, span_f);
                 if (lane == 0) {
                     Cand *c = &sc.cands[n_cands];
                     c->loc = f_loc; c->set_pair = (uint8_t)sp; c->mate_index = n_mates - 1; c->seed_offset = (uint16_t)f_off;

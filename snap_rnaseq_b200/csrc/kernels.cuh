@@ -138,7 +138,7 @@ struct PairedArgs {
     uint32_t n_items;
     snapb200_paired_result *results;
     uint32_t force_spacing;
-    Cand *cands; Mate *mates; Anchor *anchors; int16_t *lane_tables;  // [warp slot][...]
+    Cand *cands; Mate *mates; Anchor *anchors; int16_t *lane_tables; uint32_t *order;  // [warp slot][...]
     Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
     unsigned long long *stats;
     unsigned long long *prof;  // optional cycle accounting [8] (builds with -DSNAPB200_PROFILE)
@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
     sc.mates[1] = sc.mates[0] + a.cfg.mate_cap;
     sc.anchors = a.anchors + (size_t)slot * a.cfg.anchor_cap;
     sc.lane_table = a.lane_tables + (size_t)slot * LANE_TABLE_CELLS * 32;
+    sc.order = a.order + (size_t)slot * a.cfg.cand_cap;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
     #pragma unroll 1
     for (;;) {

@@ -29,8 +29,8 @@ struct __align__(8) Mate {  // ScoringMateCandidate (IntersectingPairedEndAligne
     int8_t s_off;
     uint32_t pad;
 };
-struct __align__(8) Cand {  // ScoringCandidate (:425-447)
-    int32_t next, anchor;
+struct __align__(8) Cand {  // ScoringCandidate (:425-447); `list` = the score list it is on (bestPossibleScore of the pair)
+    int32_t list, anchor;
     uint32_t mate_index, loc;
     uint16_t seed_offset;
     uint8_t set_pair, best_possible;
@@ -66,6 +66,7 @@ struct PairedScratch {
     Mate *mates[2];
     Anchor *anchors;
     int16_t *lane_table;  // LANE_TABLE_CELLS * 32 cells: the full L tables of a lane-mode batch
+    uint32_t *order;      // cand_cap entries: candidate indices in phase 3's visiting order
 };
 
 #define STATUS_LIMIT 0xfd  // the reference's candidate pools would have overflowed (it exits)
@@ -91,10 +92,10 @@ struct PairedSm {
     uint8_t n_lookups[2][2];
     uint32_t n_sched_w[2];
     uint32_t total_hits[2][2], popular[2], n_look[2];
-    int score_list[32];
+    uint32_t list_pos[32];   // counting sort of the candidates by score list (phase 2 -> 3)
     // phase 3 exchange
     double p_all, p_best, f_prob, m_prob;
-    uint32_t best_pair_score, score_limit, n_cands, n_anchors, n_mates[2], max_used_list;
+    uint32_t best_pair_score, score_limit, n_cands, n_anchors, n_mates[2], pos;
     uint32_t best_loc[2], best_score[2];
     int best_dir[2];
     int act, act2, ci, stop, overflow, list, f_off, m_off, fs, ms;
@@ -410,14 +411,13 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     // setPairDirection (:351): set pair sp uses read0 in direction sp, read1 in direction 1-sp
     if (lane == 0) {
         #pragma unroll 1
-        for (uint32_t k = 0; k <= max_k + extra; k++) sm->score_list[k] = -1;
-        sm->n_cands = 0; sm->n_mates[0] = sm->n_mates[1] = 0; sm->n_anchors = 0; sm->max_used_list = 0;
+        sm->n_cands = 0; sm->n_mates[0] = sm->n_mates[1] = 0; sm->n_anchors = 0;
     }
     __syncwarp();
 
     PROF(long long t_b = clock64();)
     // ---- phase 2 (:359-511) ----
-    uint32_t n_cands = 0, max_used_list = 0;
+    uint32_t n_cands = 0;
     #pragma unroll 1
     for (int sp = 0; sp < 2; sp++) {
         const int dir_of[2] = {sp, 1 - sp};
@@ -492,12 +492,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 if (lane == 0) {
                     Cand *c = &sc.cands[n_cands];
                     c->loc = f_loc; c->set_pair = (uint8_t)sp; c->mate_index = n_mates - 1; c->seed_offset = (uint16_t)f_off;
-                    c->best_possible = (uint8_t)bp_fewer; c->next = sm->score_list[low_mate + bp_fewer]; c->anchor = -1;
+                    c->best_possible = (uint8_t)bp_fewer; c->list = (int)(low_mate + bp_fewer); c->anchor = -1;
                     c->c_score = SC_NONE; c->c_k = 0;
-                    sm->score_list[low_mate + bp_fewer] = (int)n_cands;
                 }
                 n_cands++;
-                max_used_list = max(max_used_list, low_mate + bp_fewer);
             }
             if (!hs_next_lower(lf, &mr_f, &f_loc, &f_off)) break;
         }
@@ -513,9 +511,43 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     // netIndel independent of k.  So scores are computed AHEAD of their use, 32 locations per warp (one per lane,
     // lv_lane) with the current limit, which only ever shrinks, and are committed one by one in the reference's order
     // with the limit in force at that moment.  Counters (nLocationsScored) advance at commit time only.
+    // The reference keeps one LIFO list of candidates per bestPossibleScore and serves list 0, 1, 2, ... (:516-530).  Every
+    // list is filled in ascending candidate index, so the visiting order is: by list, then by descending index -- a
+    // counting sort, done here by the whole warp, instead of 32 linked lists that the leader would have to chase through HBM.
+    {
+        sm->list_pos[lane] = 0;
+        __syncwarp();
+        #pragma unroll 1
+        for (uint32_t b0 = 0; b0 < n_cands; b0 += 32) {
+            const uint32_t i = b0 + lane;
+            const uint32_t l = i < n_cands ? (uint32_t)sc.cands[i].list : 0xffffffffu;
+            const unsigned peers = __match_any_sync(FULL_MASK, l);
+            if (i < n_cands && lane == __ffs((int)peers) - 1) sm->list_pos[l] += __popc(peers);
+            __syncwarp();
+        }
+        uint32_t cnt = sm->list_pos[lane], start = cnt;  // inclusive scan over the (at most 31) lists
+        #pragma unroll 1
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL_MASK, start, o);
+            if (lane >= o) start += up;
+        }
+        __syncwarp();
+        sm->list_pos[lane] = start - cnt;
+        __syncwarp();
+        #pragma unroll 1
+        for (int top = (int)n_cands - 1; top >= 0; top -= 32) {
+            const int i = top - lane;  // lane 0 holds the highest index: visited first within its list
+            const uint32_t l = i >= 0 ? (uint32_t)sc.cands[i].list : 0xffffffffu;
+            const unsigned peers = __match_any_sync(FULL_MASK, l);
+            if (i >= 0) sc.order[sm->list_pos[l] + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;
+            __syncwarp();
+            if (i >= 0 && lane == __ffs((int)peers) - 1) sm->list_pos[l] += __popc(peers);
+            __syncwarp();
+        }
+    }
     if (lane == 0) {
         sm->n_cands = n_cands;
-        sm->list = 0;
+        sm->pos = 0;
         sm->score_limit = max_k + extra;
         sm->p_all = 0; sm->p_best = 0;
         sm->best_pair_score = 65536;
@@ -525,40 +557,32 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
     #pragma unroll 1
     for (;;) {
         if (lane == 0) {
-            uint32_t list = (uint32_t)sm->list;
-            #pragma unroll 1
-            while (list <= max_used_list && list <= sm->score_limit && sm->score_list[list] < 0) list++;
-            sm->list = (int)list;
-            if (sm->stop || list > max_used_list || list > sm->score_limit) {
-                sm->act = 0;
-            } else {
-                int ci = sm->score_list[list];
+            int act = 0;
+            sm->n_batch = 0;
+            if (!sm->stop && sm->pos < n_cands) {
+                const int ci = (int)sc.order[sm->pos];
                 const Cand *c = &sc.cands[ci];
-                sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
-                sm->act = 1;
-                sm->n_lv++;
-                // is this candidate's score already known?  If not, gather the next unscored candidates in visiting order.
-                sm->n_batch = 0;
-                if (c->c_score == SC_NONE) {
-                    uint32_t l = list;
-                    int j = ci;
-                    uint32_t nb = 0;
-                    const bool lane_ok = sm->score_limit <= LANE_KMAX;
-                    #pragma unroll 1
-                    while (nb < 32) {
-                        if (j < 0) {
-                            l++;
-                            if (!lane_ok || l > max_used_list || l > sm->score_limit) break;
-                            j = sm->score_list[l];
-                            continue;
-                        }
-                        if (sc.cands[j].c_score == SC_NONE) sm->batch_ids[nb++] = (uint32_t)j;
-                        j = sc.cands[j].next;
-                        if (!lane_ok) break;
-                    }
-                    sm->n_batch = nb;
+                if ((uint32_t)c->list <= sm->score_limit) {  // lists beyond the limit are never served (:527-530)
+                    sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
+                    sm->n_lv++;
+                    // score not known yet: the warp gathers the unscored candidates among the next 32 in visiting order
+                    act = (c->c_score == SC_NONE && sm->score_limit <= LANE_KMAX) ? 2 : 1;
                 }
             }
+            sm->act = act;
+        }
+        __syncwarp();
+        if (sm->act == 2) {
+            const uint32_t at = sm->pos + (uint32_t)lane;
+            bool want = false;
+            uint32_t j = 0;
+            if (at < n_cands) {
+                j = sc.order[at];
+                want = sc.cands[j].c_score == SC_NONE && (uint32_t)sc.cands[j].list <= sm->score_limit;
+            }
+            const unsigned m = __ballot_sync(FULL_MASK, want);
+            if (want) sm->batch_ids[__popc(m & ((1u << lane) - 1u))] = j;
+            if (lane == 0) sm->n_batch = (uint32_t)__popc(m);
         }
         __syncwarp();
         if (!sm->act) break;
@@ -806,7 +830,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             }
         }
         if (sm->overflow) return 2;
-        if (lane == 0 && !sm->stop) sm->score_list[sm->list] = sc.cands[sm->ci].next;
+        if (lane == 0 && !sm->stop) sm->pos++;
         __syncwarp();
     }
 

@@ -491,7 +491,7 @@ struct snapb200_session {
     DevBuf mh_counts, mh_locs, mh_rcs, mh_scores;
     // scratch tiers
     DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
-    DevBuf p_cands, p_mates, p_anchors, p_lane_tables;
+    DevBuf p_cands, p_mates, p_anchors, p_lane_tables, p_order;
     DevBuf w_keys[2], w_vals[2], w_tmp;  // work ordering of the paired path (weigh_pairs_kernel + radix sort)
     uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
     uint32_t anchors_warps = 0;
@@ -541,7 +541,7 @@ extern "C" void snapb200_session_destroy(snapb200_session *s)
     DevBuf *all[] = {&s->offsets[0], &s->offsets[1], &s->bases[0], &s->bases[1], &s->quals[0], &s->quals[1], &s->single_res,
                      &s->paired_res, &s->fb_single_res, &s->retry_list, &s->fallback_list, &s->fb_positions, &s->fix, &s->counters,
                      &s->mh_counts, &s->mh_locs, &s->mh_rcs, &s->mh_scores, &s->s_pool, &s->s_anchors, &s->s_lists, &s->s_epochs,
-                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables,
+                     &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables, &s->p_order,
                      &s->w_keys[0], &s->w_keys[1], &s->w_vals[0], &s->w_vals[1], &s->w_tmp};
     for (DevBuf *b : all) b->release();
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -862,8 +862,10 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     if ((rc = s->p_mates.ensure(warps * 2 * cfg.mate_cap * sizeof(Mate)))) return rc;
     if ((rc = s->p_anchors.ensure(warps * cfg.anchor_cap * sizeof(Anchor)))) return rc;
     if ((rc = s->p_lane_tables.ensure(warps * LANE_TABLE_CELLS * 32 * sizeof(int16_t)))) return rc;
+    if ((rc = s->p_order.ensure(warps * cfg.cand_cap * sizeof(uint32_t)))) return rc;
     a.cands = s->p_cands.as<Cand>(); a.mates = s->p_mates.as<Mate>(); a.anchors = s->p_anchors.as<Anchor>();
     a.lane_tables = s->p_lane_tables.as<int16_t>();
+    a.order = s->p_order.as<uint32_t>();
     a.ctr = s->counters.as<Counters>();
     a.retry_list = s->retry_list.as<uint32_t>(); a.fallback_list = s->fallback_list.as<uint32_t>();
     a.fix = s->fix.as<MapqFix>(); a.fix_cap = FIX_CAP;
@@ -972,7 +974,7 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
             PairedCfg big = cfg;
             big.cand_cap = (uint32_t)ref_pool; big.mate_cap = (uint32_t)(ref_pool / 2); big.anchor_cap = (uint32_t)ref_pool;
             big.hard_limit = 1;
-            size_t per_warp = (size_t)big.cand_cap * sizeof(Cand) + (size_t)big.mate_cap * 2 * sizeof(Mate) + (size_t)big.anchor_cap * sizeof(Anchor);
+            size_t per_warp = (size_t)big.cand_cap * (sizeof(Cand) + sizeof(uint32_t)) + (size_t)big.mate_cap * 2 * sizeof(Mate) + (size_t)big.anchor_cap * sizeof(Anchor);
             size_t warps = std::max<size_t>(1, SCRATCH_BUDGET / std::max<size_t>(per_warp, 1));
             int g = (int)std::min<size_t>((size_t)grid, std::max<size_t>(1, warps / WARPS_PER_CTA));
             rc = launch_paired(s, p, big, g, tmp.as<uint32_t>(), c.n_retry);

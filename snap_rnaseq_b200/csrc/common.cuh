@@ -51,6 +51,12 @@ struct DevIndex {
     uint32_t n_bases, n_pieces, seed_len, n_tables, padding;
 };
 
+// The descriptors of the indices open on this device.  Kernels receive a slot number: out-of-line device functions then
+// read the descriptor through the constant cache instead of through a by-reference copy on the caller's stack (which was
+// most of the kernels' local-memory traffic).
+#define MAX_INDEX_SLOTS 16
+__constant__ DevIndex c_index[MAX_INDEX_SLOTS];  // the library is one translation unit (snapb200.cu)
+
 // mapq fix-up request: the device's log10 landed within 1e-9 of an integer, where a last-ulp difference
 // from glibc could change the truncation; the host re-evaluates computeMAPQ for these with libm.
 struct MapqFix {

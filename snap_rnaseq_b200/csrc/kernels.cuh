@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t fetch_work(uint32_t *counter)
 // Work item p in [0, n_items): result slot = positions ? positions[p] : p; read = items ? items[slot] : slot, where a
 // read id is idx*2+mate when two batches are given (fallback of pairs) and idx otherwise.
 struct SingleArgs {
-    DevIndex ix;
+    int ix_slot;  // c_index[] entry of the index
     SingleCfg cfg;
     DevBatch b[2];
     int two_batches;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) single_kernel(const SingleArgs
     int16_t *L = (int16_t *)base;
     base += lv_shared_bytes();
     ReadView v;
-    v.D[0] = base; v.D[1] = base + a.cfg.rl; v.Q[0] = base + 2 * a.cfg.rl; v.Q[1] = base + 3 * a.cfg.rl;
+    v.base = base; v.rl = a.cfg.rl; v.len = 0;
     uint8_t *W = base + 4 * a.cfg.rl;
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + warp;
     SingleScratch sc;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) single_kernel(const SingleArgs
         const uint32_t ridx = a.two_batches ? id >> 1 : id;
         const uint32_t off = b.offsets[ridx], len = b.offsets[ridx + 1] - off;
         const uint32_t mh = a.cfg.max_hits_to_get;
-        bool ok = single_align_warp(a.ix, a.cfg, sc, sm, v, W, L, b.bases + off, b.quals + off, len, rslot, fix, a.mapq_divisor,
+        bool ok = single_align_warp(a.ix_slot, a.cfg, sc, sm, v, W, L, b.bases + off, b.quals + off, len, rslot, fix, a.mapq_divisor,
                                     mh ? a.mh_counts + rslot : nullptr, mh ? a.mh_locs + (size_t)rslot * mh : nullptr,
                                     mh ? a.mh_rcs + (size_t)rslot * mh : nullptr, mh ? a.mh_scores + (size_t)rslot * mh : nullptr,
                                     a.stats + 11);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) single_kernel(const SingleArgs
 
 // ---- paired end ------------------------------------------------------------------------------------------
 struct PairedArgs {
-    DevIndex ix;
+    int ix_slot;  // c_index[] entry of the index
     PairedCfg cfg;
     DevBatch b[2];
     const uint32_t *positions;  // retry list or null
@@ -163,18 +163,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
     base += (sizeof(PairedSm) + 15) & ~(size_t)15;
     int16_t *L = (int16_t *)base;
     base += lv_shared_bytes();
-    ReadView v[2];
-    #pragma unroll 1
-    for (int w = 0; w < 2; w++) {
-        v[w].D[0] = base + (4 * w + 0) * a.cfg.rl; v[w].D[1] = base + (4 * w + 1) * a.cfg.rl;
-        v[w].Q[0] = base + (4 * w + 2) * a.cfg.rl; v[w].Q[1] = base + (4 * w + 3) * a.cfg.rl;
-    }
+    uint8_t *const rbase = base;  // mate w: four arrays of rl bytes at rbase + 4*w*rl
     uint8_t *W = base + 8 * a.cfg.rl;
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + warp;
     PairedScratch sc;
     sc.cands = a.cands + (size_t)slot * a.cfg.cand_cap;
-    sc.mates[0] = a.mates + (size_t)slot * 2 * a.cfg.mate_cap;
-    sc.mates[1] = sc.mates[0] + a.cfg.mate_cap;
+    sc.mates = a.mates + (size_t)slot * 2 * a.cfg.mate_cap;
+    sc.mate_cap = a.cfg.mate_cap;
     sc.anchors = a.anchors + (size_t)slot * a.cfg.anchor_cap;
     sc.lane_table = a.lane_tables + (size_t)slot * LANE_TABLE_CELLS * 32;
     sc.order = a.order + (size_t)slot * a.cfg.cand_cap;
@@ -185,9 +180,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
         if (p >= a.n_items) break;
         const uint32_t pi = a.positions ? a.positions[p] : p;
         snapb200_paired_result *r = &a.results[pi];
-        uint32_t len[2], off[2];
-        #pragma unroll 1
-        for (int w = 0; w < 2; w++) { off[w] = a.b[w].offsets[pi]; len[w] = a.b[w].offsets[pi + 1] - off[w]; }
+        const uint32_t off0 = a.b[0].offsets[pi], len0 = a.b[0].offsets[pi + 1] - off0;
+        const uint32_t off1 = a.b[1].offsets[pi], len1 = a.b[1].offsets[pi + 1] - off1;
         if (lane == 0) {  // ChimericPairedEndAligner::align prologue (:74-80); untouched fields read as zero
             r->location[0] = r->location[1] = INVALID_LOC;
             r->score[0] = r->score[1] = 0; r->mapq[0] = r->mapq[1] = 0;
@@ -197,15 +191,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
             r->n_lv_calls = 0; r->n_lookups = 0; r->p_all = 0; r->p_best = 0;
         }
         __syncwarp();
-        if (len[0] < 50 && len[1] < 50) continue;
-        uint32_t ns = 0, n_bad[2];
-        #pragma unroll 1
-        for (int w = 0; w < 2; w++) {
-            v[w].len = len[w];
-            ns += stage_read(v[w], a.b[w].bases + off[w], a.b[w].quals + off[w], &n_bad[w]);
-        }
+        if (len0 < 50 && len1 < 50) continue;
+        uint32_t n_bad0, n_bad1;
+        const ReadView v0 = {rbase, a.cfg.rl, len0}, v1 = {rbase + 4 * a.cfg.rl, a.cfg.rl, len1};
+        uint32_t ns = stage_read(v0, a.b[0].bases + off0, a.b[0].quals + off0, &n_bad0);
+        ns += stage_read(v1, a.b[1].bases + off1, a.b[1].quals + off1, &n_bad1);
         PROF(if (lane == 0) for (int q = 0; q < 12; q++) sm->t_phase[q] = 0; long long t_s = clock64();)
-        int rc = paired_intersect_warp(a.ix, a.cfg, sc, sm, v, ns, n_bad, W, L, r, pi, fix);
+        int rc = paired_intersect_warp(a.ix_slot, a.cfg, sc, sm, rbase, len0, len1, ns, n_bad0, n_bad1, W, L, r, pi, fix);
         PROF(if (lane == 0 && a.prof) {
             atomicAdd(a.prof + 0, (unsigned long long)(clock64() - t_s));
             for (int q = 1; q < 5; q++) atomicAdd(a.prof + q, (unsigned long long)sm->t_phase[q]);
@@ -382,7 +374,7 @@ __global__ void __launch_bounds__(CTA_THREADS) cigar_kernel(const CigarArgs a)
 
 // ---- building blocks on explicit strings (known-answer tests) ----------------------------------------------
 struct LvArgs {
-    DevIndex ix;  // only the probability tables are used
+    int ix_slot;  // c_index[] entry; only the probability tables are used
     int dir;
     uint32_t n;
     const uint32_t *text_off, *pat_off;
@@ -433,7 +425,7 @@ __global__ void __launch_bounds__(CTA_THREADS) lv_kernel(const LvArgs a)
         } else {
             double prob;
             int indel;
-            int e = lv_score_warp(s, a.quals ? Q : nullptr, 1, a.k[i], a.ix, L, &prob, &indel);
+            int e = lv_score_warp(s, a.quals ? Q : nullptr, 1, a.k[i], a.ix_slot, L, &prob, &indel);
             if (lane == 0) { a.score[i] = e; a.prob[i] = prob; a.indel[i] = indel; }
         }
         __syncwarp();

@@ -138,9 +138,10 @@ __device__ __forceinline__ int lv_rows(const LvStr &s, int16_t *L, int k, int *w
 
 // LandauVishkin<DIR>::computeEditDistance.  q: quality(i) = q[i*qs] or NULL.  All lanes return the same
 // values.  L: LV_CELLS int16 in shared memory private to this warp.
-__device__ __noinline__ int lv_score_warp(const LvStr &s_in, const uint8_t *q, int qs, int k, const DevIndex &ix, int16_t *L,
+__device__ __noinline__ int lv_score_warp(const LvStr &s_in, const uint8_t *q, int qs, int k, int ix_slot, int16_t *L,
                              double *match_prob, int *net_indel)
 {
+    const DevIndex &ix = c_index[ix_slot];  // only the probability tables are used
     // a private copy: the caller's struct sits on its stack, and through the reference every field would be re-read from
     // local memory after each store to L (ncu: lv_pat/lv_txt were 45 % of the kernel's local-memory instructions)
     const LvStr s = {s_in.p, s_in.ps, s_in.plen, s_in.t, s_in.ts, s_in.tlen, s_in.t_lo, s_in.t_hi};
@@ -426,9 +427,10 @@ __device__ __forceinline__ int roll_get(const int16_t *R, int e, int d)
 // column of the full table in HBM scratch (written on the way, read only by the backtrace of successful lanes).
 // k may differ between lanes.  Returns the score or -1.
 template <int DIR>
-__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int16_t *R, int16_t *T, const DevIndex &ix,
+__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int16_t *R, int16_t *T, int ix_slot,
                        bool live_in, double *match_prob, int *net_indel)
 {
+    const DevIndex &ix = c_index[ix_slot];  // only the probability tables are used
     int result = -1, win_d = 0;
     *match_prob = 0.0;
     *net_indel = 0;

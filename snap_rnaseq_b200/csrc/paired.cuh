@@ -63,7 +63,9 @@ struct PairedCfg {
 
 struct PairedScratch {
     Cand *cands;
-    Mate *mates[2];
+    Mate *mates;          // two arrays of mate_cap entries, one per set pair
+    uint32_t mate_cap;
+    __device__ __forceinline__ Mate *mates_of(uint32_t sp) const { return mates + (size_t)sp * mate_cap; }
     Anchor *anchors;
     int16_t *lane_table;  // LANE_TABLE_CELLS * 32 cells: the full L tables of a lane-mode batch
     uint32_t *order;      // cand_cap entries: candidate indices in phase 3's visiting order
@@ -336,14 +338,16 @@ __device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm 
 // IntersectingPairedEndAligner::align.  All lanes.  v[0], v[1]: both mates staged (len set, Ns and non-ACGT bases
 // counted by the caller: total_ns, n_bad[2]).
 // Returns 0 = returned early leaving the result untouched, 1 = produced a result, 2 = scratch tier overflow.
-__device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, const PairedScratch &sc, PairedSm *sm,
-                                     const ReadView *v, uint32_t total_ns, const uint32_t *n_bad, uint8_t *W, int16_t *L,
+__device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const PairedScratch &sc, PairedSm *sm,
+                                     uint8_t *rbase, uint32_t rlen0, uint32_t rlen1, uint32_t total_ns, uint32_t n_bad0, uint32_t n_bad1, uint8_t *W, int16_t *L,
                                      snapb200_paired_result *r, uint32_t pair_index, const MapqFixList &fix)
 {
     const int lane = lane_id();
+    const DevIndex &ix = c_index[ix_slot];
+    // mate w staged at rbase + 4*w*rl (see ReadView); built on demand so that nothing is indexed dynamically
+    auto view = [&](int w) { ReadView r = {rbase + (uint32_t)w * 4u * cfg.rl, cfg.rl, w ? rlen1 : rlen0}; return r; };
     const uint32_t seed_len = ix.seed_len, max_k = cfg.max_k, extra = cfg.extra;
     const uint32_t max_spacing = cfg.max_spacing, min_spacing = cfg.min_spacing;
-    const uint32_t rlen0 = v[0].len, rlen1 = v[1].len;
     uint32_t max_seeds = cfg.num_seeds ? cfg.num_seeds : (uint32_t)(max(rlen0, rlen1) * cfg.seed_coverage / seed_len);
     if (max_seeds > MAX_LOOKUPS) max_seeds = MAX_LOOKUPS;  // rejected on the host; belt and braces
     if (rlen0 < 50 || rlen1 < 50) return 0;  // :186-188
@@ -371,10 +375,10 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         __syncwarp();
         if (lane == 0) {
             if (together) {
-                schedule_seeds_paired(sm, p1, 0, 0, v[0].D[0], rlen0, seed_len, max_seeds, n_bad[0] == 0);
-                schedule_seeds_paired(sm, p1, 1, MAX_LOOKUPS / 2, v[1].D[0], rlen1, seed_len, max_seeds, n_bad[1] == 0);
+                schedule_seeds_paired(sm, p1, 0, 0, view(0).D(0), rlen0, seed_len, max_seeds, n_bad0 == 0);
+                schedule_seeds_paired(sm, p1, 1, MAX_LOOKUPS / 2, view(1).D(0), rlen1, seed_len, max_seeds, n_bad1 == 0);
             } else {
-                schedule_seeds_paired(sm, p1, pass, 0, v[pass].D[0], pass ? rlen1 : rlen0, seed_len, max_seeds, n_bad[pass] == 0);
+                schedule_seeds_paired(sm, p1, pass, 0, view(pass).D(0), pass ? rlen1 : rlen0, seed_len, max_seeds, (pass ? n_bad1 : n_bad0) == 0);
             }
         }
         __syncwarp();
@@ -384,7 +388,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             uint64_t sf, sr;
             HitList hl[2];
             uint32_t np = 0;
-            pack_seed(v[w].D[0] + p1->sched_off[lane], seed_len, &sf, &sr);
+            pack_seed(view(w).D(0) + p1->sched_off[lane], seed_len, &sf, &sr);
             lookup_seed(ix, sf, sr, hl, &np);
             #pragma unroll 1
             for (int d = 0; d < 2; d++) {
@@ -435,7 +439,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
         uint32_t f_loc, f_off = 0, m_loc, m_off = 0;
         bool out_of_more = false;
         uint32_t n_mates = 0, last_mate_loc = 0;
-        Mate *mates = sc.mates[sp];
+        Mate *mates = sc.mates_of(sp);
         if (!hs_first(lf, &mr_f, &f_loc, &f_off)) continue;
         m_loc = INVALID_LOC;
         #pragma unroll 1
@@ -598,7 +602,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             int s = SC_NONE, off = 0;
             double pr = 0;
             const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
-            score_location_lane(ix, v[fewer], dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+            score_location_lane(ix_slot, view(fewer), dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
             if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
             __syncwarp();
             PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_x; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
@@ -612,7 +616,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                 const int dml = more == 0 ? (int)spl : 1 - (int)spl;
                 const uint32_t cloc = act_l ? cl->loc : 0;
                 uint32_t j = act_l ? cl->mate_index : 0;
-                Mate *mbase = sc.mates[spl];
+                Mate *mbase = sc.mates_of(spl);
                 uint32_t n_done = 0;
                 #pragma unroll 1
                 for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
@@ -639,7 +643,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
                     int s2 = SC_NONE, off2 = 0;
                     double pr2 = 0;
-                    score_location_lane(ix, v[more], dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, L + lane, sc.lane_table + lane, mine,
+                    score_location_lane(ix_slot, view(more), dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, L + lane, sc.lane_table + lane, mine,
                                         &s2, &pr2, &off2);
                     if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
                     n_done += __popc(__ballot_sync(FULL_MASK, mine));
@@ -655,7 +659,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             int off;
             const int K = (int)sm->score_limit;
             PROF(long long t_w = clock64();)
-            int s = score_location_warp(ix, v[fewer], dir_f, sm->c_loc, sm->c_seedoff, K, false, W, L, &pr, &off);
+            int s = score_location_warp(ix_slot, view(fewer), dir_f, sm->c_loc, sm->c_seedoff, K, false, W, L, &pr, &off);
             __syncwarp();
             PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
             if (lane == 0) { Cand *c = &sc.cands[sm->ci]; c->c_score = (int16_t)s; c->c_k = (uint8_t)K; c->c_off = (int8_t)off; c->c_prob = pr; }
@@ -676,7 +680,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
             #pragma unroll 1
             for (;;) {  // mates of this candidate (:559-711)
                 if (lane == 0) {
-                    Mate *m = &sc.mates[sp][sm->mi];
+                    Mate *m = &sc.mates_of(sp)[sm->mi];
                     int act = 0;
                     sm->n_batch = 0;
                     if (!is_within(m->loc, sm->c_loc, min_spacing) && m->best_possible <= sm->score_limit - f_score) {
@@ -693,13 +697,13 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                                 uint32_t j = sm->mi;
                                 #pragma unroll 1
                                 for (;;) {
-                                    Mate *q = &sc.mates[sp][j];
+                                    Mate *q = &sc.mates_of(sp)[j];
                                     if (!is_within(q->loc, sm->c_loc, min_spacing) && q->best_possible <= m_limit &&
                                         (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < m_limit)) &&
                                         !mate_known(q, m_limit))
                                         sm->batch_ids[nb++] = j;
                                     if (!lane_ok || nb >= 32) break;
-                                    if (j == 0 || !is_within(sc.mates[sp][j - 1].loc, sm->c_loc, max_spacing)) break;
+                                    if (j == 0 || !is_within(sc.mates_of(sp)[j - 1].loc, sm->c_loc, max_spacing)) break;
                                     j--;
                                 }
                                 sm->n_batch = nb;
@@ -716,28 +720,28 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     const int K = (int)sm->m_limit;
                     if (nb >= LANE_MIN_BATCH) {
                         bool act_l = (uint32_t)lane < nb;
-                        Mate *ml = act_l ? &sc.mates[sp][sm->batch_ids[lane]] : nullptr;
+                        Mate *ml = act_l ? &sc.mates_of(sp)[sm->batch_ids[lane]] : nullptr;
                         int s = SC_NONE, off = 0;
                         double pr = 0;
-                        score_location_lane(ix, v[more], dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+                        score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
                         if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
                         __syncwarp();
                         PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; })
                     }
-                    if (lane == 0) { const Mate *m = &sc.mates[sp][sm->mi]; sm->act2 = !mate_known(m, sm->m_limit); }
+                    if (lane == 0) { const Mate *m = &sc.mates_of(sp)[sm->mi]; sm->act2 = !mate_known(m, sm->m_limit); }
                     __syncwarp();
                     if (sm->act2) {
                         double m_prob;
                         int m_off;
                         PROF(long long t_w = clock64();)
-                        int ms = score_location_warp(ix, v[more], dir_m, sm->m_loc, sm->m_seedoff, K, false, W, L, &m_prob, &m_off);
+                        int ms = score_location_warp(ix_slot, view(more), dir_m, sm->m_loc, sm->m_seedoff, K, false, W, L, &m_prob, &m_off);
                         __syncwarp();
                         PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
-                        if (lane == 0) { Mate *m = &sc.mates[sp][sm->mi]; m->s_score = (int16_t)ms; m->s_k = (uint8_t)K; m->s_off = (int8_t)m_off; m->s_prob = m_prob; }
+                        if (lane == 0) { Mate *m = &sc.mates_of(sp)[sm->mi]; m->s_score = (int16_t)ms; m->s_k = (uint8_t)K; m->s_off = (int8_t)m_off; m->s_prob = m_prob; }
                         __syncwarp();
                     }
                     if (lane == 0) {  // commit: what scoreLocation(limit = m_limit) returns
-                        Mate *m = &sc.mates[sp][sm->mi];
+                        Mate *m = &sc.mates_of(sp)[sm->mi];
                         const int d = m->s_score;
                         const bool ok = d >= 0 && (uint32_t)d <= sm->m_limit;
                         m->score = ok ? (uint32_t)d : (uint32_t)-1;
@@ -748,7 +752,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     PROF(t_lv += clock64() - t_y;)
                 }
                 if (lane == 0) {
-                    Mate *m = &sc.mates[sp][sm->mi];
+                    Mate *m = &sc.mates_of(sp)[sm->mi];
                     Cand *c = &sc.cands[sm->ci];
                     if (act != 0 && m->score != (uint32_t)-1) {
                         const double pair_prob = m->prob * f_prob;
@@ -821,7 +825,7 @@ __device__ int paired_intersect_warp(const DevIndex &ix, const PairedCfg &cfg, c
                     }
                     int go_on = 1;
                     if (sm->stop || sm->overflow) go_on = 0;
-                    else if (sm->mi == 0 || !is_within(sc.mates[sp][sm->mi - 1].loc, c->loc, max_spacing)) go_on = 0;
+                    else if (sm->mi == 0 || !is_within(sc.mates_of(sp)[sm->mi - 1].loc, c->loc, max_spacing)) go_on = 0;
                     else sm->mi--;
                     sm->act = go_on;
                 }

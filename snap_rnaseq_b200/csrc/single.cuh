@@ -58,14 +58,17 @@ struct SingleSm {  // per-warp shared state: everything leader and warp sections
     int hit_elem[32];
 };
 
-struct ReadView {  // a read staged in shared memory in both orientations
-    uint8_t *D[2];  // D[FORWARD] = read, D[RC] = reverse complement (BaseAligner.cpp:638-650)
-    uint8_t *Q[2];  // Q[RC] = reversed quality
-    uint32_t len;
+struct ReadView {  // a read staged in shared memory in both orientations: four arrays of `rl` bytes back to back
+    uint8_t *base;
+    uint32_t rl, len;
+    // D(FORWARD) = read, D(RC) = reverse complement (BaseAligner.cpp:638-650); Q(RC) = reversed quality.  Computed, not
+    // stored: a view is three registers, is passed by value and never has to live in local memory.
+    __device__ __forceinline__ uint8_t *D(int dir) const { return base + (uint32_t)dir * rl; }
+    __device__ __forceinline__ uint8_t *Q(int dir) const { return base + (2u + (uint32_t)dir) * rl; }
 };
 
 // all lanes; returns the number of 'N' bases; *n_not_acgt (optional): bases that cannot be part of a seed
-__device__ __forceinline__ uint32_t stage_read(const ReadView &v, const uint8_t *bases, const uint8_t *quals, uint32_t *n_not_acgt = nullptr)
+__device__ __forceinline__ uint32_t stage_read(const ReadView v, const uint8_t *bases, const uint8_t *quals, uint32_t *n_not_acgt = nullptr)
 {
     const int lane = lane_id();
     uint32_t ns = 0, bad = 0;
@@ -75,10 +78,10 @@ __device__ __forceinline__ uint32_t stage_read(const ReadView &v, const uint8_t 
         bool is_n = false, is_bad = false;
         if (i < v.len) {
             uint8_t b = bases[i], q = quals[i];
-            v.D[0][i] = b;
-            v.Q[0][i] = q;
-            v.D[1][v.len - 1 - i] = rc_base(b);
-            v.Q[1][v.len - 1 - i] = q;
+            v.D(0)[i] = b;
+            v.Q(0)[i] = q;
+            v.D(1)[v.len - 1 - i] = rc_base(b);
+            v.Q(1)[v.len - 1 - i] = q;
             is_n = b == 'N';
             is_bad = base2(b) < 0;
         }
@@ -112,10 +115,11 @@ __device__ __forceinline__ bool substring_ok(const DevIndex &ix, uint32_t offset
 
 // The scoring step shared by BaseAligner::score (BaseAligner.cpp:1158-1242) and
 // IntersectingPairedEndAligner::scoreLocation (:755-841).  All lanes; uniform results.
-__device__ __noinline__ int score_location_warp(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset,
+__device__ __noinline__ int score_location_warp(int ix_slot, const ReadView v, int dir, uint32_t loc, uint32_t seed_offset,
                                    int score_limit, bool single_variant, uint8_t *W, int16_t *L, double *match_prob,
                                    int *loc_offset)
 {
+    const DevIndex &ix = c_index[ix_slot];
     const uint32_t rlen = v.len;
     uint32_t glen = rlen + MAXK;
     bool have = substring_ok(ix, loc, glen);
@@ -146,17 +150,17 @@ __device__ __noinline__ int score_location_warp(const DevIndex &ix, const ReadVi
     double p1, p2;
     int dummy;
     // forward: read tail against the genome after the seed
-    s.p = v.D[dir] + tail; s.ps = 1; s.plen = (int)rlen - tail;
+    s.p = v.D(dir) + tail; s.ps = 1; s.plen = (int)rlen - tail;
     s.t = W + WIN_SLACK + tail; s.ts = 1; s.tlen = (int)glen - tail;
     s.t_lo = -(WIN_SLACK + tail); s.t_hi = wn - (WIN_SLACK + tail);
-    int s1 = lv_score_warp(s, v.Q[dir] + tail, 1, score_limit, ix, L, &p1, &dummy);
+    int s1 = lv_score_warp(s, v.Q(dir) + tail, 1, score_limit, ix_slot, L, &p1, &dummy);
     if (s1 == -1) return -1;
     __syncwarp();
     // backward: read head (reversed) against the genome before the seed
-    s.p = v.D[dir] + seed_offset - 1; s.ps = -1; s.plen = (int)seed_offset;
+    s.p = v.D(dir) + seed_offset - 1; s.ps = -1; s.plen = (int)seed_offset;
     s.t = W + WIN_SLACK + seed_offset - 1; s.ts = -1; s.tlen = (int)seed_offset + MAXK;
     s.t_lo = (int)seed_offset - (int)rlen - WIN_SLACK; s.t_hi = WIN_SLACK + (int)seed_offset;
-    int s2 = lv_score_warp(s, v.Q[dir] + seed_offset - 1, -1, score_limit - s1, ix, L, &p2, loc_offset);
+    int s2 = lv_score_warp(s, v.Q(dir) + seed_offset - 1, -1, score_limit - s1, ix_slot, L, &p2, loc_offset);
     if (s2 == -1) { *loc_offset = 0; return -1; }
     *match_prob = p1 * p2 * ix.seed_prob;
     return s1 + s2;
@@ -167,9 +171,10 @@ __device__ __noinline__ int score_location_warp(const DevIndex &ix, const ReadVi
 // interleaved rolling rows (shared) and T its column of the full table (HBM scratch).  Lanes whose genome window is not entirely inside the genome return SC_NONE_LANE and are
 // left to score_location_warp.  All 32 lanes must call this together.
 #define SC_NONE_LANE (-3)
-__device__ __noinline__ void score_location_lane(const DevIndex &ix, const ReadView &v, int dir, uint32_t loc, uint32_t seed_offset, int K,
+__device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, int dir, uint32_t loc, uint32_t seed_offset, int K,
                                     int16_t *R, int16_t *T, bool active, int *score, double *match_prob, int *loc_offset)
 {
+    const DevIndex &ix = c_index[ix_slot];
     const uint32_t rlen = v.len;
     // same test as getSubstring(loc, rlen + MAX_K) != NULL; the 4-byte loads stay within +-16 bytes of that window
     bool ok = active && substring_ok(ix, loc, rlen + MAXK);
@@ -181,10 +186,10 @@ __device__ __noinline__ void score_location_lane(const DevIndex &ix, const ReadV
     const uint8_t *g = ix.genome + loc;
     double p1 = 0, p2 = 0;
     int dummy, off = 0;
-    int s1 = lv_lane<1>(v.D[dir] + tail, (int)rlen - tail, g + tail, v.Q[dir] + tail, K, R, T, ix, ok, &p1, &dummy);
+    int s1 = lv_lane<1>(v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, R, T, ix_slot, ok, &p1, &dummy);
     const bool ok2 = ok && s1 != -1;
-    int s2 = lv_lane<-1>(v.D[dir] + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q[dir] + (int)seed_offset - 1,
-                         K - (s1 > 0 ? s1 : 0), R, T, ix, ok2, &p2, &off);
+    int s2 = lv_lane<-1>(v.D(dir) + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q(dir) + (int)seed_offset - 1,
+                         K - (s1 > 0 ? s1 : 0), R, T, ix_slot, ok2, &p2, &off);
     if (!ok) return;
     if (s1 == -1 || s2 == -1) { *score = -1; return; }
     *score = s1 + s2;
@@ -371,8 +376,8 @@ __device__ __forceinline__ bool after_score(const SingleCfg &cfg, const SingleSc
 struct MapqFixList { MapqFix *items; uint32_t *count; uint32_t cap; };
 
 // BaseAligner::score (BaseAligner.cpp:977-1399).  All lanes; returns true when a final answer was produced.
-__device__ __noinline__ bool single_score(const DevIndex &ix, const SingleCfg &cfg, const SingleScratch &sc, SingleSm *sm,
-                             const ReadView &v, uint8_t *W, int16_t *L, bool force_in, uint32_t read_index,
+__device__ __noinline__ bool single_score(int ix_slot, const SingleCfg &cfg, const SingleScratch &sc, SingleSm *sm,
+                             const ReadView v, uint8_t *W, int16_t *L, bool force_in, uint32_t read_index,
                              const MapqFixList &fix, int mapq_divisor)
 {
     const int lane = lane_id();
@@ -464,7 +469,7 @@ __device__ __noinline__ bool single_score(const DevIndex &ix, const SingleCfg &c
             if (!sm->action) break;
             double prob;
             int loc_off;
-            int s = score_location_warp(ix, v, sm->cand_dir, sm->cand_loc, sm->cand_seedoff, (int)sm->score_limit, true, W, L,
+            int s = score_location_warp(ix_slot, v, sm->cand_dir, sm->cand_loc, sm->cand_seedoff, (int)sm->score_limit, true, W, L,
                                         &prob, &loc_off);
             __syncwarp();
             if (lane == 0) {
@@ -544,13 +549,14 @@ __device__ __forceinline__ void fill_hits(const SingleCfg &cfg, const SingleScra
 
 // BaseAligner::AlignRead (searchRadius == 0).  All lanes.  Result fields are left in *sm (out_*, p_all, ...).
 // Returns false if the scratch tier overflowed (the read must be rerun with a larger tier).
-__device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, const SingleScratch &sc, SingleSm *sm,
+__device__ bool single_align_warp(int ix_slot, const SingleCfg &cfg, const SingleScratch &sc, SingleSm *sm,
                                   ReadView &v, uint8_t *W, int16_t *L, const uint8_t *bases, const uint8_t *quals,
                                   uint32_t len, uint32_t read_index, const MapqFixList &fix, int mapq_divisor,
                                   int32_t *mh_found, uint32_t *mh_locs, uint8_t *mh_rcs, int32_t *mh_scores,
                                   unsigned long long *stat_ns_ignored)
 {
     const int lane = lane_id();
+    const DevIndex &ix = c_index[ix_slot];
     const uint32_t seed_len = ix.seed_len;
     if (lane == 0) {
         sm->out_loc = INVALID_LOC; sm->out_dir = SNAPB200_FORWARD; sm->out_score = UNUSED_SCORE; sm->out_mapq = 0;
@@ -593,7 +599,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
     #pragma unroll 1
     for (;;) {
         if (sm->n_applied[0] + sm->n_applied[1] >= max_seeds) break;
-        if (lane == 0) schedule_seeds_single(sm, v.D[0], len, seed_len);
+        if (lane == 0) schedule_seeds_single(sm, v.D(0), len, seed_len);
         __syncwarp();
         const uint32_t n_sched = sm->n_sched;
         // warp section: all scheduled seeds are probed at once, one per lane
@@ -601,7 +607,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
         uint32_t my_probes = 0;
         if ((uint32_t)lane < n_sched) {
             uint64_t sf, sr;
-            pack_seed(v.D[0] + sm->sched_off[lane], seed_len, &sf, &sr);
+            pack_seed(v.D(0) + sm->sched_off[lane], seed_len, &sf, &sr);
             lookup_seed(ix, sf, sr, my, &my_probes);
         }
         bool out = false;
@@ -653,7 +659,7 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
                 applied = true;
             }
             __syncwarp();
-            if (applied && single_score(ix, cfg, sc, sm, v, W, L, false, read_index, fix, mapq_divisor)) { answered = true; break; }
+            if (applied && single_score(ix_slot, cfg, sc, sm, v, W, L, false, read_index, fix, mapq_divisor)) { answered = true; break; }
         }
         if (answered || out) break;
         if (sm->terminal) {
@@ -664,14 +670,14 @@ __device__ bool single_align_warp(const DevIndex &ix, const SingleCfg &cfg, cons
                 // mostSeedsContainingAnyParticularBase = wrapCount+1 (:722), whether or not a lookup followed
                 if (lane == 0) sm->most_seeds = seed_len;
                 __syncwarp();
-                single_score(ix, cfg, sc, sm, v, W, L, true, read_index, fix, mapq_divisor);
+                single_score(ix_slot, cfg, sc, sm, v, W, L, true, read_index, fix, mapq_divisor);
                 answered = true;
                 skip_fill = true;
             }
             break;
         }
     }
-    if (!answered) single_score(ix, cfg, sc, sm, v, W, L, true, read_index, fix, mapq_divisor);
+    if (!answered) single_score(ix_slot, cfg, sc, sm, v, W, L, true, read_index, fix, mapq_divisor);
     if (lane == 0 && !skip_fill) fill_hits(cfg, sc, mh_found, mh_locs, mh_rcs, mh_scores);
     __syncwarp();
     return true;

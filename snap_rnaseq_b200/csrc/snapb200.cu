@@ -19,6 +19,9 @@
 
 thread_local char g_last_error[512] = "";
 
+static std::mutex g_slot_mutex;
+static bool g_slot_used[64][MAX_INDEX_SLOTS];
+
 int set_error(int code, const char *fmt, ...)
 {
     va_list ap;
@@ -93,6 +96,7 @@ static int compute_mapq_host(double p_all, double p_best, int score, int popular
 
 struct snapb200_index {
     int device = 0;
+    int slot = -1;  // position of `dev` in this device's c_index[]
     int sm_count = 0;
     DevIndex dev;
     snapb200_index_info info;
@@ -153,6 +157,14 @@ static int finish_index(snapb200_index *x)
     CUDA_TRY(cudaGetDeviceProperties(&prop, x->device));
     x->sm_count = prop.multiProcessorCount;
     x->info.device = x->device;
+    // publish the descriptor in constant memory
+    {
+        std::lock_guard<std::mutex> g(g_slot_mutex);
+        if (x->device < 0 || x->device >= 64) return set_error(SNAPB200_ERR_ARG, "device %d out of range", x->device);
+        for (int q = 0; q < MAX_INDEX_SLOTS && x->slot < 0; q++) if (!g_slot_used[x->device][q]) { g_slot_used[x->device][q] = true; x->slot = q; }
+        if (x->slot < 0) return set_error(SNAPB200_ERR_ARG, "more than %d indices open on device %d", MAX_INDEX_SLOTS, x->device);
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_index, &x->dev, sizeof(DevIndex), (size_t)x->slot * sizeof(DevIndex)));
     return 0;
 }
 
@@ -558,6 +570,7 @@ extern "C" void snapb200_index_close(snapb200_index *x)
     cudaSetDevice(x->device);
     for (int i = 0; i < 2; i++) if (x->batch_session[i]) snapb200_session_destroy(x->batch_session[i]);
     for (void *p : x->allocs) cudaFree(p);
+    if (x->slot >= 0) { std::lock_guard<std::mutex> g(g_slot_mutex); g_slot_used[x->device][x->slot] = false; }
     if (x->stats) cudaFree(x->stats);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
@@ -646,7 +659,7 @@ static int launch_single(snapb200_session *s, const SingleCfg &cfg_in, const Sin
     snapb200_index *x = s->idx;
     SingleArgs a;
     memset(&a, 0, sizeof(a));
-    a.ix = x->dev;
+    a.ix_slot = x->slot;
     a.cfg = cfg_in;
     a.cfg.pool_cap = tier.pool_cap;
     a.cfg.tmask = tier.tsize - 1;
@@ -848,7 +861,7 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     snapb200_index *x = s->idx;
     PairedArgs a;
     memset(&a, 0, sizeof(a));
-    a.ix = x->dev;
+    a.ix_slot = x->slot;
     a.cfg = cfg;
     a.b[0] = dev_batch(s, 0);
     a.b[1] = dev_batch(s, 1);
@@ -1404,7 +1417,7 @@ static int lv_common(int device, int dir, uint32_t n, const uint32_t *text_offse
         cudaMemsetAsync(d_ctr.p, 0, sizeof(Counters), st);
         LvArgs a;
         memset(&a, 0, sizeof(a));
-        a.ix = x->dev; a.dir = dir; a.n = n; a.text_off = d_to.as<uint32_t>(); a.pat_off = d_po.as<uint32_t>();
+        a.ix_slot = x->slot; a.dir = dir; a.n = n; a.text_off = d_to.as<uint32_t>(); a.pat_off = d_po.as<uint32_t>();
         a.texts = d_t.as<uint8_t>(); a.pats = d_p.as<uint8_t>(); a.quals = quals ? d_q.as<uint8_t>() : nullptr; a.k = d_k.as<int32_t>();
         a.score = d_s.as<int32_t>(); a.indel = d_in.as<int32_t>(); a.prob = d_pr.as<double>();
         a.use_m = use_m; a.cigars = cigars ? d_c.as<char>() : nullptr; a.stride = stride;

@@ -9,7 +9,10 @@ L = S.lib(0)
 if len(sys.argv) > 2 and sys.argv[2] == "c3":
     bench.GENOME_CONTIGS = [25_000_000] * 124
     bench.READ_LEN, bench.ERR_RATE = 150, 0.01
-contigs = bench.make_genome()
+if os.environ.get("PROF_NOREPEAT"):  # ordinary pairs only: no repeat families in the genome
+    contigs = synth.random_contigs(bench.GENOME_CONTIGS, seed=20)
+else:
+    contigs = bench.make_genome()
 bases, offs = synth.snap_layout(contigs, 500)
 h = L.build_index(bases, offs, list(contigs), seed_len=20)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000

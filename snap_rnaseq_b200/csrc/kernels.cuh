@@ -243,21 +243,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
 // Pairs differ in cost by four orders of magnitude (median 2 scored locations, maximum several thousand: reads from repeat
 // families), and a warp keeps one pair until it is done.  Served in input order, the heavy pairs that happen to come late
 // leave most SMs idle at the end of a launch, and heavy and ordinary pairs executing side by side on an SM compete for the
-// instruction cache.  So before the aligner runs, this kernel estimates each pair's weight from four index probes (first
-// and last seed of each mate) and the host sorts the pairs heaviest first (stable: ordinary pairs stay in input order).
+// instruction cache.  So before the aligner runs, this kernel estimates each pair's weight from eight index probes (four seeds spread over
+// each mate) and the host sorts the pairs heaviest first (stable: ordinary pairs stay in input order).
 // The order changes nothing in the results: pairs are independent and every pair writes only its own record.
-// Thread t: pair t>>2, mate (t>>1)&1, seed at the start (t&1 == 0) or the end of the mate.
+// Thread t: pair t>>4, mate (t>>3)&1, seed number t&7 of eight spread evenly over the mate.
+#define WEIGH_SEEDS 8  // per mate
 __global__ void weigh_pairs_kernel(const DevIndex ix, const DevBatch b0, const DevBatch b1, uint32_t n, uint32_t max_big_hits,
                                    uint32_t *keys, uint32_t *vals)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t pair = t >> 2;
+    const uint32_t pair = t >> 4;
     uint32_t w = 0;
     if (pair < n) {
-        const DevBatch &b = (t >> 1) & 1 ? b1 : b0;
+        const DevBatch &b = (t >> 3) & 1 ? b1 : b0;
         const uint32_t off = b.offsets[pair], len = b.offsets[pair + 1] - off;
         if (len >= ix.seed_len) {
-            const uint8_t *seed = b.bases + off + ((t & 1) ? len - ix.seed_len : 0);
+            const uint8_t *seed = b.bases + off + (size_t)(len - ix.seed_len) * (t & 7) / (WEIGH_SEEDS - 1);
             uint64_t f, r;
             if (pack_seed(seed, ix.seed_len, &f, &r)) {
                 HitList hl[2];
@@ -268,9 +269,11 @@ __global__ void weigh_pairs_kernel(const DevIndex ix, const DevBatch b0, const D
     }
     w += __shfl_xor_sync(FULL_MASK, w, 1);
     w += __shfl_xor_sync(FULL_MASK, w, 2);
-    if (pair < n && (t & 3) == 0) {
+    w += __shfl_xor_sync(FULL_MASK, w, 4);
+    w += __shfl_xor_sync(FULL_MASK, w, 8);
+    if (pair < n && (t & 15) == 0) {
         // 16-bit sort key, ascending = heaviest first; everything light shares the last key and keeps its input order
-        const uint32_t q = w >> 3;
+        const uint32_t q = w >> 5;
         keys[pair] = q == 0 ? 0xffffu : 0xfffeu - min(q, 0xfffeu);
         vals[pair] = pair;
     }

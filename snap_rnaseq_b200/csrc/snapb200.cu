@@ -959,7 +959,7 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
         const uint32_t *order = nullptr;
         if (n >= 4096 && !getenv("SNAPB200_NO_ORDER")) {
             for (int q = 0; q < 2; q++) if ((rc = s->w_keys[q].ensure((size_t)n * 4)) || (rc = s->w_vals[q].ensure((size_t)n * 4))) return rc;
-            weigh_pairs_kernel<<<(unsigned)(((size_t)4 * n + 255) / 256), 256, 0, s->stream>>>(x->dev, dev_batch(s, 0), dev_batch(s, 1), n, p->max_big_hits,
+            weigh_pairs_kernel<<<(unsigned)(((size_t)16 * n + 255) / 256), 256, 0, s->stream>>>(x->dev, dev_batch(s, 0), dev_batch(s, 1), n, p->max_big_hits,
                                                                                            s->w_keys[0].as<uint32_t>(), s->w_vals[0].as<uint32_t>());
             CUDA_TRY(cudaGetLastError());
             s->last_launches++;

@@ -41,6 +41,19 @@ PAIRS_PER_STEP = 1_000_000          # per GPU
 CPU_SAMPLE_PAIRS = 200_000
 
 
+def measured_traffic(pairs):
+    """dram__bytes_read + dram__bytes_write of paired_kernel per launch, from the committed `ncu --set full` capture of the
+    same configuration (profiles/r1s2_traffic.json: bytes per pair of a 200 k-pair launch), scaled to this launch's pairs.
+    None for configurations that were not captured."""
+    if (sum(GENOME_CONTIGS) // 1_000_000, READ_LEN) != (3100, 150):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1s2_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_pair"]) * pairs
+    except Exception:
+        return None
+
+
 def workload_config(n_gpus, pairs):
     mbp = sum(GENOME_CONTIGS) // 1_000_000
     tag = "C3: " if (mbp, READ_LEN) == (3100, 150) else "C2: " if (mbp, READ_LEN) == (100, 100) else ""
@@ -266,7 +279,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "matches_resident_run": bool(same)},
             "roofline": {"bound": "hbm", "kernel": "paired_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": peak_src, "traffic": measured_traffic(pairs), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "per_pair": {"table_probes": per(12) / pairs, "hit_words": per(13) / pairs, "lv_locations": n_lv / pairs,
                                       "lookups": float(out["n_lookups"].mean())}},
             "index_build_s": t_index,

@@ -29,7 +29,7 @@ p = A.paired_defaults()
 sweep = os.environ.get("PROF_SWEEP", "").split(",") if os.environ.get("PROF_SWEEP") else [None] * 3
 for it, cfg in enumerate(sweep):
     if cfg is not None:
-        os.environ["SNAPB200_CTAS_PER_SM"] = cfg
+        os.environ[os.environ.get("PROF_SWEEP_VAR", "SNAPB200_CTAS_PER_SM")] = cfg
     sess.run_paired(p)
     ms, launches, _ = sess.last_run()
     print("run %d total %.1f ms main %.1f ms launches %d" % (it, ms, sess.main_kernel_ms(), launches))

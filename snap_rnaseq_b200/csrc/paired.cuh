@@ -85,7 +85,10 @@ struct Phase1Sm {
 
 struct PairedSm {
     // hit sets [read][dir], filled by the leader in phase 1 (HashTableHitSet::recordLookup)
-    unsigned long long hits[2][2][MAX_LOOKUPS];
+    // hit list of lookup k: overflow-table word offset of its first hit, or -- for a seed with exactly one hit, which the
+    // index stores inside the hash-table entry -- the hit itself (bit k of inline_mask set)
+    uint32_t hitref[2][2][MAX_LOOKUPS];
+    uint32_t inline_mask[2][2];
     uint32_t nhits[2][2][MAX_LOOKUPS];
     uint16_t seedoff[2][2][MAX_LOOKUPS];
     uint8_t setid[2][2][MAX_LOOKUPS];
@@ -105,12 +108,14 @@ struct PairedSm {
     uint32_t batch_ids[32];
     uint32_t c_loc, c_seedoff, c_sp, mi, m_loc, m_seedoff, m_limit, low_mate;
     uint32_t n_lv, n_probes, n_hit_words;
-    long long t_phase[12];  // cycle accounting (SNAPB200_PROF): stage, phase1, phase2, lv, leader3, other
+    PROF(long long t_phase[12];)  // cycle accounting (-DSNAPB200_PROFILE): stage, phase1, phase2, lv, leader3, other
 };
 
 // ---- warp-parallel HashTableHitSet: lane i owns lookup i ------------------------------------------------
 struct LaneLookup {
-    const uint32_t *hits;
+    const uint32_t *hits;  // in the overflow table; unused when the only hit is held inline
+    uint32_t single;       // the inline hit
+    bool inl;
     uint32_t nh, cur, so, sid;
     uint32_t cur_val, prev_val;  // hits[cur] (if cur < nh) and hits[cur-1] (if cur > 0), kept in registers
     uint32_t next_val;           // hits[cur+1] (if cur+1 < nh): requested when cur is set, so stepping down never waits for L2
@@ -118,19 +123,24 @@ struct LaneLookup {
     bool act;
 };
 
-__device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, int w, int d)
+// hit i of a lane's list (an inline list has at most one hit, so i is 0 there)
+__device__ __forceinline__ uint32_t hit_at(const LaneLookup &l, uint32_t i) { return l.inl ? l.single : __ldg(&l.hits[i]); }
+
+__device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, const uint32_t *overflow, int w, int d)
 {
     LaneLookup l;
     const int lane = lane_id();
     l.act = lane < (int)sm->n_lookups[w][d];
-    l.hits = l.act ? (const uint32_t *)sm->hits[w][d][lane] : nullptr;
+    l.single = l.act ? sm->hitref[w][d][lane] : 0;
+    l.inl = l.act && (sm->inline_mask[w][d] >> lane & 1);
+    l.hits = overflow + (l.inl ? 0u : l.single);
     l.nh = l.act ? sm->nhits[w][d][lane] : 0;
     l.so = l.act ? sm->seedoff[w][d][lane] : 0;
     l.sid = l.act ? sm->setid[w][d][lane] : 0;
     l.cur = 0;
     l.words = 0;
-    l.cur_val = l.nh > 0 ? __ldg(&l.hits[0]) : 0;
-    l.next_val = l.nh > 1 ? __ldg(&l.hits[1]) : 0;
+    l.cur_val = l.nh > 0 ? hit_at(l, 0) : 0;
+    l.next_val = l.nh > 1 ? hit_at(l, 1) : 0;
     l.prev_val = 0;
     l.words += l.nh > 0;
     return l;
@@ -191,8 +201,8 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
         #pragma unroll 1
         while (lo <= hi) {
             int probe = (lo + hi) / 2;
-            uint32_t h = __ldg(&l.hits[probe]);
-            uint32_t hp = probe == 0 ? 0 : __ldg(&l.hits[probe - 1]);
+            uint32_t h = hit_at(l, (uint32_t)probe);
+            uint32_t hp = probe == 0 ? 0 : hit_at(l, (uint32_t)probe - 1);
             l.words += 2;
             if (h <= want && (probe == 0 || hp > want)) {
                 found = true;
@@ -200,14 +210,14 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
                 l.cur = (uint32_t)probe;
                 l.cur_val = h;
                 l.prev_val = hp;
-                l.next_val = (uint32_t)probe + 1 < l.nh ? __ldg(&l.hits[probe + 1]) : 0;
+                l.next_val = (uint32_t)probe + 1 < l.nh ? hit_at(l, (uint32_t)probe + 1) : 0;
                 break;
             }
             if (h > want) lo = probe + 1; else hi = probe - 1;
         }
         if (lo > hi) {
             l.cur = l.nh;
-            l.prev_val = l.nh > 0 ? __ldg(&l.hits[l.nh - 1]) : 0;
+            l.prev_val = l.nh > 0 ? hit_at(l, l.nh - 1) : 0;
         }
     }
     if (!pick_max(found, val, l.so, loc, so)) return false;
@@ -227,7 +237,7 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
             if (l.cur != l.nh) {
                 l.cur_val = l.next_val;
                 l.words++;
-                if (l.cur + 1 < l.nh) l.next_val = __ldg(&l.hits[l.cur + 1]);
+                if (l.cur + 1 < l.nh) l.next_val = hit_at(l, l.cur + 1);
             }
         }
         if (l.cur != l.nh) {
@@ -295,7 +305,8 @@ __device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, i
 }
 
 // leader: HashTableHitSet::recordLookup for the lookups of mate w in schedule order (:859-899); results at slot0..
-__device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits)
+__device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits,
+                                                   const uint32_t *overflow)
 {
     uint32_t begins = 3;  // bit d: the next lookup of direction d starts a new disjoint hit set
     uint32_t prev_wrap = 0;
@@ -316,13 +327,15 @@ __device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm 
                     sm->exhausted[w][d][sm->cur_set[w][d]]++;
                 } else {
                     const uint32_t *hp = (const uint32_t *)p1->raw_hits[d][j];
+                    const bool single = n == 1;  // the hit sits in the hash-table entry; raw_last is that hit
                     if (p1->raw_last[d][j] < offset) {  // trim meaningless hits (:882-884); only at the very start of the genome
                         n--;
                         #pragma unroll 1
                         while (n > 0 && __ldg(&hp[n - 1]) < offset) n--;
                     }
                     uint32_t k = sm->n_lookups[w][d]++;
-                    sm->hits[w][d][k] = (unsigned long long)hp;
+                    sm->hitref[w][d][k] = single ? p1->raw_last[d][j] : (uint32_t)(hp - overflow);
+                    if (single) sm->inline_mask[w][d] |= 1u << k;
                     sm->nhits[w][d][k] = n;
                     sm->seedoff[w][d][k] = (uint16_t)offset;
                     sm->setid[w][d][k] = (uint8_t)sm->cur_set[w][d];
@@ -360,7 +373,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
         for (int w = 0; w < 2; w++) {
             sm->popular[w] = 0; sm->n_look[w] = 0;
             #pragma unroll 1
-            for (int d = 0; d < 2; d++) { sm->total_hits[w][d] = 0; sm->n_lookups[w][d] = 0; sm->cur_set[w][d] = -1; }
+            for (int d = 0; d < 2; d++) { sm->total_hits[w][d] = 0; sm->n_lookups[w][d] = 0; sm->cur_set[w][d] = -1; sm->inline_mask[w][d] = 0; }
         }
         sm->overflow = 0;
         sm->n_lv = 0;
@@ -401,10 +414,10 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
         __syncwarp();
         if (lane == 0) {
             if (together) {
-                record_lookups_paired(sm, p1, 0, 0, rlen0, seed_len, cfg.max_big_hits);
-                record_lookups_paired(sm, p1, 1, MAX_LOOKUPS / 2, rlen1, seed_len, cfg.max_big_hits);
+                record_lookups_paired(sm, p1, 0, 0, rlen0, seed_len, cfg.max_big_hits, ix.overflow);
+                record_lookups_paired(sm, p1, 1, MAX_LOOKUPS / 2, rlen1, seed_len, cfg.max_big_hits, ix.overflow);
             } else {
-                record_lookups_paired(sm, p1, pass, 0, pass ? rlen1 : rlen0, seed_len, cfg.max_big_hits);
+                record_lookups_paired(sm, p1, pass, 0, pass ? rlen1 : rlen0, seed_len, cfg.max_big_hits, ix.overflow);
             }
         }
     }
@@ -424,11 +437,11 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
     uint32_t n_cands = 0;
     #pragma unroll 1
     for (int sp = 0; sp < 2; sp++) {
-        const int dir_of[2] = {sp, 1 - sp};
-        LaneLookup lf = load_lookup(sm, fewer, dir_of[fewer]);
-        LaneLookup lm = load_lookup(sm, more, dir_of[more]);
-        const uint8_t *exh_f = sm->exhausted[fewer][dir_of[fewer]], *exh_m = sm->exhausted[more][dir_of[more]];
-        const int cs_f = sm->cur_set[fewer][dir_of[fewer]], cs_m = sm->cur_set[more][dir_of[more]];
+        const int d_fewer = fewer ? 1 - sp : sp, d_more = more ? 1 - sp : sp;  // set pair sp: read 0 in direction sp, read 1 in 1-sp
+        LaneLookup lf = load_lookup(sm, ix.overflow, fewer, d_fewer);
+        LaneLookup lm = load_lookup(sm, ix.overflow, more, d_more);
+        const uint8_t *exh_f = sm->exhausted[fewer][d_fewer], *exh_m = sm->exhausted[more][d_more];
+        const int cs_f = sm->cur_set[fewer][d_fewer], cs_m = sm->cur_set[more][d_more];
         uint32_t maxexh_f = 0, maxexh_m = 0;
         #pragma unroll 1
         for (int q = 0; q <= cs_f; q++) maxexh_f = max(maxexh_f, (uint32_t)exh_f[q]);

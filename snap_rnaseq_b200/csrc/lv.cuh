@@ -35,45 +35,29 @@ __device__ __forceinline__ int lv_get(const int16_t *L, int e, int d)
     return (d >= -e && d <= e) ? (int)L[e * e + d + e] : -2;
 }
 
-__device__ __forceinline__ uint32_t lv_ld4(const uint8_t *p)
-{  // unaligned 4-byte little-endian load (shared or global memory): the two enclosing aligned words, funnel-shifted
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
-    return __funnelshift_r(w[0], w[1], (unsigned)(a & 3) * 8);
-}
-
-// first index i in [from, dend) with pattern(i) != text(d + i), or dend.  Four positions per step while eight more bytes
-// of both strings exist in memory (the word loads look at most seven bytes past the four they need), then byte by byte.
-__device__ __forceinline__ int lv_extend(const LvStr &s, int from, int d, int dend)
-{
-    int i = from;
-    #pragma unroll 1
-    while (i + 8 <= dend && d + i >= s.t_lo && d + i + 8 <= s.t_hi) {
-        const uint32_t a = s.ps > 0 ? lv_ld4(s.p + i) : __byte_perm(lv_ld4(s.p - i - 3), 0, 0x0123);
-        const uint32_t b = s.ts > 0 ? lv_ld4(s.t + (d + i)) : __byte_perm(lv_ld4(s.t - (d + i) - 3), 0, 0x0123);
-        const uint32_t x = a ^ b;
-        if (x) return i + ((__ffs((int)x) - 1) >> 3);
-        i += 4;
-    }
-    #pragma unroll 1
-    while (i < dend && lv_pat(s, i) == lv_txt(s, d + i)) i++;
-    return i;
-}
-
-// One cell: best of (substitution, deletion, insertion) from the row above, then extend along the diagonal.
-__device__ __forceinline__ int lv_cell(const LvStr &s, const int16_t *L, int e, int d)
+// One cell, first part: best of (substitution, deletion, insertion) from the row above, then up to LV_QUICK positions of
+// extension along the diagonal by this lane alone.  *more: the diagonal is still matching at the returned position and has
+// not reached *dend -- the long runs (there are one or two per row) are finished by the whole warp, see lv_rows.
+#define LV_QUICK 4
+__device__ __forceinline__ int lv_cell_start(const LvStr &s, const int16_t *L, int e, int d, int *dend, bool *more)
 {
     int best = lv_get(L, e - 1, d) + 1;
     int left = lv_get(L, e - 1, d - 1);
     if (left > best) best = left;
     int right = lv_get(L, e - 1, d + 1) + 1;
     if (right > best) best = right;
+    *more = false;
+    *dend = 0;
     if (lv_pat(s, best) == lv_txt(s, d + best)) {
-        int dend = min(s.plen, s.tlen - d);
-        if (best < dend) {
-            best = lv_extend(s, best + 1, d, dend);
+        const int de = min(s.plen, s.tlen - d);
+        *dend = de;
+        if (best < de) {
+            const int lim = min(de, best + LV_QUICK);
+            #pragma unroll 1
+            do { best++; } while (best < lim && lv_pat(s, best) == lv_txt(s, d + best));
+            *more = best == lim && best < de && lv_pat(s, best) == lv_txt(s, d + best);
         } else {
-            best = dend;  // the reference's 8-byte loop clamps to `end` even when it starts beyond it
+            best = de;  // the reference's 8-byte loop clamps to `end` even when it starts beyond it
         }
     }
     return best;
@@ -120,11 +104,35 @@ __device__ __forceinline__ int lv_rows(const LvStr &s, int16_t *L, int k, int *w
     for (int e = 1; e <= k; e++) {
         int found = 0x7fffffff;
         #pragma unroll 1
-        for (int idx = lane; idx < 2 * e + 1; idx += 32) {
-            int d = idx - e;
-            int best = lv_cell(s, L, e, d);
-            L[e * e + idx] = (int16_t)best;
-            if (best == s.plen) found = min(found, CIGAR_ORDER ? lv_rank_cigar(d) : lv_rank_score(d));
+        for (int idx0 = 0; idx0 < 2 * e + 1; idx0 += 32) {
+            const int idx = idx0 + lane, d = idx - e;
+            const bool mine = idx < 2 * e + 1;
+            int best = 0, dend = 0;
+            bool more = false;
+            if (mine) best = lv_cell_start(s, L, e, d, &dend, &more);
+            // Diagonals that are still matching: one at a time, the whole warp compares 32 positions per step.  A lane on
+            // its own would walk a 100-base exact run in 100 steps while the other lanes of the row wait for it.
+            unsigned pend = __ballot_sync(FULL_MASK, more);
+            #pragma unroll 1
+            while (pend) {
+                const int src = __ffs((int)pend) - 1;
+                const int dd = __shfl_sync(FULL_MASK, d, src), de = __shfl_sync(FULL_MASK, dend, src);
+                int pos = __shfl_sync(FULL_MASK, best, src);
+                #pragma unroll 1
+                for (;;) {
+                    const int i = pos + lane;
+                    const bool stop = i >= de || lv_pat(s, i) != lv_txt(s, dd + i);
+                    const unsigned bm = __ballot_sync(FULL_MASK, stop);
+                    if (bm) { pos += __ffs((int)bm) - 1; break; }
+                    pos += 32;
+                }
+                if (lane == src) best = pos;
+                pend &= pend - 1;
+            }
+            if (mine) {
+                L[e * e + idx] = (int16_t)best;
+                if (best == s.plen) found = min(found, CIGAR_ORDER ? lv_rank_cigar(d) : lv_rank_score(d));
+            }
         }
         __syncwarp();
         int win = __reduce_min_sync(FULL_MASK, found);

@@ -382,7 +382,8 @@ __device__ int lv_cigar_warp(const LvStr &s_in, int k, int16_t *L, char *cigar, 
 // =================================================================================================================
 #define LANE_KMAX 17                      // largest score limit handled in lane mode (defaults: 15+2 paired, 14+2 single)
 #define LANE_ROW (2 * LANE_KMAX + 1)      // cells of one row of the rolling pair kept in shared memory
-#define LANE_ROLL_CELLS (2 * LANE_ROW)    // per lane: previous row + current row
+#define LANE_ROWP (LANE_ROW + 2)          // ... plus one cell either side, so that a row's out-of-band neighbours exist
+#define LANE_ROLL_CELLS (2 * LANE_ROWP)   // per lane: previous row + current row
 #define LANE_TABLE_CELLS ((LANE_KMAX + 1) * (LANE_KMAX + 1))  // per lane: the full triangular table, spilled to HBM scratch
 
 // length of the common run of pattern[pi..] and text[ti..], at most plen - pi.  Both strings are walked one aligned
@@ -423,11 +424,7 @@ __device__ __forceinline__ int lane_get(const int16_t *T, int e, int d)
 {
     return (d >= -e && d <= e) ? (int)T[(e * e + d + e) * 32] : -2;
 }
-// rolling rows (shared): row parity (e&1), diagonal d of this lane at R[((e&1)*LANE_ROW + d + LANE_KMAX)*32]
-__device__ __forceinline__ int roll_get(const int16_t *R, int e, int d)
-{
-    return (d >= -e && d <= e) ? (int)R[(((e & 1) * LANE_ROW) + d + LANE_KMAX) * 32] : -2;
-}
+// rolling rows (shared): row parity (e&1), diagonal d of this lane at R[((e&1)*LANE_ROWP + d + LANE_KMAX + 1)*32]
 
 // LandauVishkin<DIR>::computeEditDistance for this lane's candidate.  All 32 lanes must call it together (it uses
 // a warp vote to stop early); `live_in` is false for lanes without a candidate.  p/t point at string index 0 and are
@@ -446,7 +443,7 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
     int l0 = 0;
     if (live) {
         l0 = lane_run<DIR>(p, t, 0, 0, plen);
-        R[LANE_KMAX * 32] = (int16_t)l0;
+        R[(LANE_KMAX + 1) * 32] = (int16_t)l0;
         T[0] = (int16_t)l0;
         if (l0 == plen) {  // LandauVishkin.h:290-305 (text is never shorter than the pattern here)
             result = 0;
@@ -459,20 +456,27 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
     for (int e = 1; e <= LANE_KMAX; e++) {
         if (live && e > kmax) live = false;
         if (!__any_sync(FULL_MASK, live)) break;
+        // this lane's column of the previous and the current row, centred on diagonal 0
+        int16_t *prev = R + ((((e - 1) & 1) * LANE_ROWP) + LANE_KMAX + 1) * 32, *cur = R + (((e & 1) * LANE_ROWP) + LANE_KMAX + 1) * 32;
+        int16_t *Te = T + (e * e + e) * 32;
+        if (live) {  // cells just outside the band of row e-1 read as -2 (never written by the reference); no range tests below
+            prev[e * 32] = -2; prev[-e * 32] = -2; prev[(e + 1) * 32] = -2; prev[-(e + 1) * 32] = -2;
+        }
+        int d = 0;  // visiting order 0,+1,-1,+2,-2,...
         #pragma unroll 1
         for (int r = 0; r <= 2 * e; r++) {
             if (live) {
-                const int d = lv_unrank_score(r);
-                int best = roll_get(R, e - 1, d) + 1;
-                int left = roll_get(R, e - 1, d - 1);
+                int best = (int)prev[d * 32] + 1;
+                const int left = (int)prev[(d - 1) * 32];
                 if (left > best) best = left;
-                int right = roll_get(R, e - 1, d + 1) + 1;
+                const int right = (int)prev[(d + 1) * 32] + 1;
                 if (right > best) best = right;
                 if (best < plen) best += lane_run<DIR>(p, t, best, d + best, plen);
-                R[(((e & 1) * LANE_ROW) + d + LANE_KMAX) * 32] = (int16_t)best;
-                T[(e * e + d + e) * 32] = (int16_t)best;
+                cur[d * 32] = (int16_t)best;
+                Te[d * 32] = (int16_t)best;
                 if (best == plen) { result = e; win_d = d; live = false; }
             }
+            d = d > 0 ? -d : 1 - d;
         }
     }
     if (result >= 1) {  // backtrace, LandauVishkin.h:379-431

@@ -21,10 +21,12 @@ struct Counters {  // device-side counters read back after each launch group
 };
 
 __device__ __forceinline__ uint32_t round8(uint32_t x) { return (x + 7u) & ~7u; }
-// the L buffer: the triangular table of the warp mode (961 cells) or the rolling row pairs of the lane mode (70 cells x 32 lanes)
-__host__ __device__ inline size_t lv_shared_bytes()
+// the L buffer: the triangular table of the warp mode (961 cells) or, in kernels that use it, the rolling row pairs of
+// the lane mode (lane_roll_cells(lane_k) cells x 32 lanes)
+__host__ __device__ inline size_t lv_shared_bytes(int lane_k = 0)
 {
-    size_t cells = LV_CELLS > LANE_ROLL_CELLS * 32 ? LV_CELLS : LANE_ROLL_CELLS * 32;
+    size_t lane_cells = lane_k > 0 ? (size_t)lane_roll_cells(lane_k) * 32 : 0;
+    size_t cells = LV_CELLS > lane_cells ? LV_CELLS : lane_cells;
     return (cells * 2 + 15) & ~(size_t)15;
 }
 
@@ -142,13 +144,13 @@ struct PairedArgs {
     Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
     unsigned long long *stats;
     unsigned long long *prof;  // optional cycle accounting [8] (builds with -DSNAPB200_PROFILE)
-    uint32_t smem_per_warp;    // paired_warp_shared(cfg.rl), computed on the host
+    uint32_t smem_per_warp;    // paired_warp_shared(cfg.rl, cfg.lane_k), computed on the host
 };
 
-__host__ __device__ inline size_t paired_warp_shared(uint32_t rl)
+__host__ __device__ inline size_t paired_warp_shared(uint32_t rl, uint32_t lane_k)
 {
     size_t s = (sizeof(PairedSm) + 15) & ~(size_t)15;
-    s += lv_shared_bytes();
+    s += lv_shared_bytes((int)lane_k);
     s += 8 * (size_t)rl;
     s += ((size_t)rl + 2 * WIN_SLACK + 15) & ~(size_t)15;
     return s;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
     PairedSm *sm = (PairedSm *)base;
     base += (sizeof(PairedSm) + 15) & ~(size_t)15;
     int16_t *L = (int16_t *)base;
-    base += lv_shared_bytes();
+    base += lv_shared_bytes((int)a.cfg.lane_k);
     uint8_t *const rbase = base;  // mate w: four arrays of rl bytes at rbase + 4*w*rl
     uint8_t *W = base + 8 * a.cfg.rl;
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + warp;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
     sc.mates = a.mates + (size_t)slot * 2 * a.cfg.mate_cap;
     sc.mate_cap = a.cfg.mate_cap;
     sc.anchors = a.anchors + (size_t)slot * a.cfg.anchor_cap;
-    sc.lane_table = a.lane_tables + (size_t)slot * LANE_TABLE_CELLS * 32;
+    sc.lane_table = a.lane_tables + (size_t)slot * lane_table_cells((int)a.cfg.lane_k) * 32;
     sc.order = a.order + (size_t)slot * a.cfg.cand_cap;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
     #pragma unroll 1

@@ -377,14 +377,15 @@ __device__ int lv_cigar_warp(const LvStr &s_in, int k, int16_t *L, char *cigar, 
 // eight), the pattern comes from the read staged in shared memory and the text straight from the genome in HBM
 // through L1 (a candidate's window is two or three 128-byte lines, touched by one lane only).  The per-lane L table
 // is interleaved in shared memory (cell c of lane l at L[c*32+l]) so that lanes walking the table in lockstep never
-// conflict.  Preconditions (checked by the caller): k <= LANE_KMAX, textLen >= patternLen + k (always true for
+// conflict.  Preconditions (checked by the caller): k <= kl, textLen >= patternLen + k (always true for
 // windows inside the genome), and the 4-byte over-reads stay inside readable memory.
 // =================================================================================================================
-#define LANE_KMAX 17                      // largest score limit handled in lane mode (defaults: 15+2 paired, 14+2 single)
-#define LANE_ROW (2 * LANE_KMAX + 1)      // cells of one row of the rolling pair kept in shared memory
-#define LANE_ROWP (LANE_ROW + 2)          // ... plus one cell either side, so that a row's out-of-band neighbours exist
-#define LANE_ROLL_CELLS (2 * LANE_ROWP)   // per lane: previous row + current row
-#define LANE_TABLE_CELLS ((LANE_KMAX + 1) * (LANE_KMAX + 1))  // per lane: the full triangular table, spilled to HBM scratch
+// The largest score limit handled in lane mode, `kl`, is a property of the launch: max_k + extra_search_depth of the
+// run (17 with the paired defaults, 22 for the -d 20 stress configuration), so the shared-memory rows are as wide as the
+// run can need and no wider.
+__host__ __device__ inline int lane_rowp(int kl) { return 2 * kl + 3; }  // a row: diagonals -kl..kl plus one cell either side, so that a row's out-of-band neighbours exist
+__host__ __device__ inline int lane_roll_cells(int kl) { return 2 * lane_rowp(kl); }          // per lane: previous row + current row (shared memory)
+__host__ __device__ inline int lane_table_cells(int kl) { return (kl + 1) * (kl + 1); }       // per lane: the full triangular table (HBM scratch)
 
 // length of the common run of pattern[pi..] and text[ti..], at most plen - pi.  Both strings are walked one aligned
 // 32-bit word per step (the byte alignment of each string is constant along the run, so the funnel-shift amounts are
@@ -424,7 +425,7 @@ __device__ __forceinline__ int lane_get(const int16_t *T, int e, int d)
 {
     return (d >= -e && d <= e) ? (int)T[(e * e + d + e) * 32] : -2;
 }
-// rolling rows (shared): row parity (e&1), diagonal d of this lane at R[((e&1)*LANE_ROWP + d + LANE_KMAX + 1)*32]
+// rolling rows (shared): row parity (e&1), diagonal d of this lane at R[((e&1)*rowp + d + kl + 1)*32]
 
 // LandauVishkin<DIR>::computeEditDistance for this lane's candidate.  All 32 lanes must call it together (it uses
 // a warp vote to stop early); `live_in` is false for lanes without a candidate.  p/t point at string index 0 and are
@@ -432,9 +433,10 @@ __device__ __forceinline__ int lane_get(const int16_t *T, int e, int d)
 // column of the full table in HBM scratch (written on the way, read only by the backtrace of successful lanes).
 // k may differ between lanes.  Returns the score or -1.
 template <int DIR>
-__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int16_t *R, int16_t *T, int ix_slot,
+__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int kl, int16_t *R, int16_t *T, int ix_slot,
                        bool live_in, double *match_prob, int *net_indel)
 {
+    const int rowp = lane_rowp(kl);
     const DevIndex &ix = c_index[ix_slot];  // only the probability tables are used
     int result = -1, win_d = 0;
     *match_prob = 0.0;
@@ -443,7 +445,7 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
     int l0 = 0;
     if (live) {
         l0 = lane_run<DIR>(p, t, 0, 0, plen);
-        R[(LANE_KMAX + 1) * 32] = (int16_t)l0;
+        R[(kl + 1) * 32] = (int16_t)l0;
         T[0] = (int16_t)l0;
         if (l0 == plen) {  // LandauVishkin.h:290-305 (text is never shorter than the pattern here)
             result = 0;
@@ -451,13 +453,13 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
             live = false;
         }
     }
-    const int kmax = min(k > 0 ? k : 0, LANE_KMAX);
+    const int kmax = min(k > 0 ? k : 0, kl);
     #pragma unroll 1
-    for (int e = 1; e <= LANE_KMAX; e++) {
+    for (int e = 1; e <= kl; e++) {
         if (live && e > kmax) live = false;
         if (!__any_sync(FULL_MASK, live)) break;
         // this lane's column of the previous and the current row, centred on diagonal 0
-        int16_t *prev = R + ((((e - 1) & 1) * LANE_ROWP) + LANE_KMAX + 1) * 32, *cur = R + (((e & 1) * LANE_ROWP) + LANE_KMAX + 1) * 32;
+        int16_t *prev = R + ((((e - 1) & 1) * rowp) + kl + 1) * 32, *cur = R + (((e & 1) * rowp) + kl + 1) * 32;
         int16_t *Te = T + (e * e + e) * 32;
         if (live) {  // cells just outside the band of row e-1 read as -2 (never written by the reference); no range tests below
             prev[e * 32] = -2; prev[-e * 32] = -2; prev[(e + 1) * 32] = -2; prev[-(e + 1) * 32] = -2;
@@ -480,8 +482,8 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
         }
     }
     if (result >= 1) {  // backtrace, LandauVishkin.h:379-431
-        char act[LANE_KMAX + 1];
-        short matched[LANE_KMAX + 1];
+        char act[MAXK + 1];
+        short matched[MAXK + 1];
         int cur_d = win_d;
         #pragma unroll 1
         for (int ce = result; ce >= 1; ce--) {

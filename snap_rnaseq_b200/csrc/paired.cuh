@@ -58,6 +58,7 @@ struct PairedCfg {
     double seed_coverage;
     uint32_t cand_cap, mate_cap, anchor_cap;  // this scratch tier
     uint32_t hard_limit;                       // 1: caps are the reference's pool sizes (overflow = its soft_exit)
+    uint32_t lane_k;                           // largest score limit scored in lane mode = max_k + extra (sizes the LV rows)
     uint32_t rl;
 };
 
@@ -67,7 +68,7 @@ struct PairedScratch {
     uint32_t mate_cap;
     __device__ __forceinline__ Mate *mates_of(uint32_t sp) const { return mates + (size_t)sp * mate_cap; }
     Anchor *anchors;
-    int16_t *lane_table;  // LANE_TABLE_CELLS * 32 cells: the full L tables of a lane-mode batch
+    int16_t *lane_table;  // lane_table_cells(cfg.lane_k) * 32 cells: the full L tables of a lane-mode batch
     uint32_t *order;      // cand_cap entries: candidate indices in phase 3's visiting order
 };
 
@@ -583,7 +584,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                     sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
                     sm->n_lv++;
                     // score not known yet: the warp gathers the unscored candidates among the next 32 in visiting order
-                    act = (c->c_score == SC_NONE && sm->score_limit <= LANE_KMAX) ? 2 : 1;
+                    act = (c->c_score == SC_NONE && sm->score_limit <= cfg.lane_k) ? 2 : 1;
                 }
             }
             sm->act = act;
@@ -615,7 +616,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             int s = SC_NONE, off = 0;
             double pr = 0;
             const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
-            score_location_lane(ix_slot, view(fewer), dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+            score_location_lane(ix_slot, view(fewer), dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
             if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
             __syncwarp();
             PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_x; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
@@ -656,7 +657,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                     const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
                     int s2 = SC_NONE, off2 = 0;
                     double pr2 = 0;
-                    score_location_lane(ix_slot, view(more), dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, L + lane, sc.lane_table + lane, mine,
+                    score_location_lane(ix_slot, view(more), dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, (int)cfg.lane_k, L + lane, sc.lane_table + lane, mine,
                                         &s2, &pr2, &off2);
                     if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
                     n_done += __popc(__ballot_sync(FULL_MASK, mine));
@@ -706,7 +707,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                             if (!mate_known(m, m_limit)) {
                                 // not known well enough: gather the mates further down this candidate's range that will need a score
                                 uint32_t nb = 0;
-                                const bool lane_ok = m_limit <= LANE_KMAX;
+                                const bool lane_ok = m_limit <= cfg.lane_k;
                                 uint32_t j = sm->mi;
                                 #pragma unroll 1
                                 for (;;) {
@@ -736,7 +737,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                         Mate *ml = act_l ? &sc.mates_of(sp)[sm->batch_ids[lane]] : nullptr;
                         int s = SC_NONE, off = 0;
                         double pr = 0;
-                        score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+                        score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
                         if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
                         __syncwarp();
                         PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; })

@@ -167,11 +167,11 @@ __device__ __noinline__ int score_location_warp(int ix_slot, const ReadView v, i
 }
 
 // The same scoring step for 32 candidates at once, one per lane (see lv_lane in lv.cuh).  v: the read (shared memory);
-// dir/loc/seed_offset: this lane's candidate; K <= LANE_KMAX: the score limit; R: this lane's column of the
+// dir/loc/seed_offset: this lane's candidate; K <= kl: the score limit (kl: the launch's lane-mode limit); R: this lane's column of the
 // interleaved rolling rows (shared) and T its column of the full table (HBM scratch).  Lanes whose genome window is not entirely inside the genome return SC_NONE_LANE and are
 // left to score_location_warp.  All 32 lanes must call this together.
 #define SC_NONE_LANE (-3)
-__device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, int dir, uint32_t loc, uint32_t seed_offset, int K,
+__device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, int dir, uint32_t loc, uint32_t seed_offset, int K, int kl,
                                     int16_t *R, int16_t *T, bool active, int *score, double *match_prob, int *loc_offset)
 {
     const DevIndex &ix = c_index[ix_slot];
@@ -186,10 +186,10 @@ __device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, 
     const uint8_t *g = ix.genome + loc;
     double p1 = 0, p2 = 0;
     int dummy, off = 0;
-    int s1 = lv_lane<1>(v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, R, T, ix_slot, ok, &p1, &dummy);
+    int s1 = lv_lane<1>(v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, kl, R, T, ix_slot, ok, &p1, &dummy);
     const bool ok2 = ok && s1 != -1;
     int s2 = lv_lane<-1>(v.D(dir) + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q(dir) + (int)seed_offset - 1,
-                         K - (s1 > 0 ? s1 : 0), R, T, ix_slot, ok2, &p2, &off);
+                         K - (s1 > 0 ? s1 : 0), kl, R, T, ix_slot, ok2, &p2, &off);
     if (!ok) return;
     if (s1 == -1 || s2 == -1) { *score = -1; return; }
     *score = s1 + s2;

@@ -874,7 +874,7 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     if ((rc = s->p_cands.ensure(warps * cfg.cand_cap * sizeof(Cand)))) return rc;
     if ((rc = s->p_mates.ensure(warps * 2 * cfg.mate_cap * sizeof(Mate)))) return rc;
     if ((rc = s->p_anchors.ensure(warps * cfg.anchor_cap * sizeof(Anchor)))) return rc;
-    if ((rc = s->p_lane_tables.ensure(warps * LANE_TABLE_CELLS * 32 * sizeof(int16_t)))) return rc;
+    if ((rc = s->p_lane_tables.ensure(warps * lane_table_cells((int)cfg.lane_k) * 32 * sizeof(int16_t)))) return rc;
     if ((rc = s->p_order.ensure(warps * cfg.cand_cap * sizeof(uint32_t)))) return rc;
     a.cands = s->p_cands.as<Cand>(); a.mates = s->p_mates.as<Mate>(); a.anchors = s->p_anchors.as<Anchor>();
     a.lane_tables = s->p_lane_tables.as<int16_t>();
@@ -896,8 +896,8 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
         a.prof = prof_buf.as<unsigned long long>();
     }
     if ((rc = reset_work(s))) return rc;
-    const size_t smem = paired_warp_shared(cfg.rl) * WARPS_PER_CTA;
-    a.smem_per_warp = (uint32_t)paired_warp_shared(cfg.rl);
+    const size_t smem = paired_warp_shared(cfg.rl, cfg.lane_k) * WARPS_PER_CTA;
+    a.smem_per_warp = (uint32_t)paired_warp_shared(cfg.rl, cfg.lane_k);
     const bool time_it = s->main_pending;
     if (time_it) CUDA_TRY(cudaEventRecord(s->evm0, s->stream));
     paired_kernel<<<grid, CTA_THREADS, smem, s->stream>>>(a);
@@ -942,7 +942,8 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
     // the reference's pool sizes (IntersectingPairedEndAligner.cpp:128-138)
     uint64_t ref_pool = std::min<uint64_t>(p->max_candidate_pool_size, (uint64_t)p->max_big_hits * ctor_seeds * 2);
     int per_sm = 1;
-    const size_t smem = paired_warp_shared(rl) * WARPS_PER_CTA;
+    cfg.lane_k = p->max_k + p->extra_search_depth;  // < MAXK (checked above)
+    const size_t smem = paired_warp_shared(rl, cfg.lane_k) * WARPS_PER_CTA;
     int grid = grid_for(paired_kernel, smem, x->sm_count, &per_sm);
     if (const char *e = getenv("SNAPB200_CTAS_PER_SM")) {  // experiments only: fewer resident CTAs than fit
         int v = atoi(e);

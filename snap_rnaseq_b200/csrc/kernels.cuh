@@ -248,36 +248,38 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs
 // instruction cache.  So before the aligner runs, this kernel estimates each pair's weight from eight index probes (four seeds spread over
 // each mate) and the host sorts the pairs heaviest first (stable: ordinary pairs stay in input order).
 // The order changes nothing in the results: pairs are independent and every pair writes only its own record.
-// Thread t: pair t>>4, mate (t>>3)&1, seed number t&7 of eight spread evenly over the mate.
-#define WEIGH_SEEDS 8  // per mate
-__global__ void weigh_pairs_kernel(const DevIndex ix, const DevBatch b0, const DevBatch b1, uint32_t n, uint32_t max_big_hits,
-                                   uint32_t *keys, uint32_t *vals)
+// Thread t: item t / (8 * MATES), mate (t>>3) & (MATES-1), seed number t&7 of eight spread evenly over the read.  MATES = 2
+// for pairs, 1 for the single-end aligner (whose heavy reads vote and score thousands of locations just the same).
+#define WEIGH_SEEDS 8  // per read
+template <int MATES>
+__global__ void weigh_kernel(const DevIndex ix, const DevBatch b0, const DevBatch b1, uint32_t n, uint32_t max_hits,
+                             uint32_t *keys, uint32_t *vals)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t pair = t >> 4;
+    const uint32_t item = t / (WEIGH_SEEDS * MATES);
     uint32_t w = 0;
-    if (pair < n) {
-        const DevBatch &b = (t >> 3) & 1 ? b1 : b0;
-        const uint32_t off = b.offsets[pair], len = b.offsets[pair + 1] - off;
+    if (item < n) {
+        const DevBatch &b = (MATES == 2 && ((t >> 3) & 1)) ? b1 : b0;
+        const uint32_t off = b.offsets[item], len = b.offsets[item + 1] - off;
         if (len >= ix.seed_len) {
             const uint8_t *seed = b.bases + off + (size_t)(len - ix.seed_len) * (t & 7) / (WEIGH_SEEDS - 1);
             uint64_t f, r;
             if (pack_seed(seed, ix.seed_len, &f, &r)) {
                 HitList hl[2];
                 lookup_seed(ix, f, r, hl, nullptr);
-                w = min(hl[0].n, max_big_hits) + min(hl[1].n, max_big_hits);
+                w = min(hl[0].n, max_hits) + min(hl[1].n, max_hits);
             }
         }
     }
     w += __shfl_xor_sync(FULL_MASK, w, 1);
     w += __shfl_xor_sync(FULL_MASK, w, 2);
     w += __shfl_xor_sync(FULL_MASK, w, 4);
-    w += __shfl_xor_sync(FULL_MASK, w, 8);
-    if (pair < n && (t & 15) == 0) {
+    if (MATES == 2) w += __shfl_xor_sync(FULL_MASK, w, 8);
+    if (item < n && t % (WEIGH_SEEDS * MATES) == 0) {
         // 16-bit sort key, ascending = heaviest first; everything light shares the last key and keeps its input order
-        const uint32_t q = w >> 5;
-        keys[pair] = q == 0 ? 0xffffu : 0xfffeu - min(q, 0xfffeu);
-        vals[pair] = pair;
+        const uint32_t q = w >> (MATES == 2 ? 5 : 4);
+        keys[item] = q == 0 ? 0xffffu : 0xfffeu - min(q, 0xfffeu);
+        vals[item] = item;
     }
 }
 

@@ -504,7 +504,7 @@ struct snapb200_session {
     // scratch tiers
     DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
     DevBuf p_cands, p_mates, p_anchors, p_lane_tables, p_order;
-    DevBuf w_keys[2], w_vals[2], w_tmp;  // work ordering of the paired path (weigh_pairs_kernel + radix sort)
+    DevBuf w_keys[2], w_vals[2], w_tmp;  // work ordering of the paired path (weigh_kernel + radix sort)
     uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
     uint32_t anchors_warps = 0;
     // last run
@@ -651,6 +651,33 @@ static int grid_for(K kernel, size_t smem, int sm_count, int *ctas_per_sm)
 
 static const size_t SCRATCH_BUDGET = (size_t)24 << 30;  // HBM the scratch of one launch may take
 
+// Heaviest items first: weigh_kernel + a stable 16-bit radix sort of the item indices.  *order = nullptr when the batch is too
+// small to bother (or SNAPB200_NO_ORDER is set).  mates: 2 = pairs (both resident batches), 1 = single reads (batch 0).
+static int work_order(snapb200_session *s, int mates, uint32_t n, uint32_t max_hits, const uint32_t **order)
+{
+    *order = nullptr;
+    if (n < 4096 || getenv("SNAPB200_NO_ORDER")) return 0;
+    snapb200_index *x = s->idx;
+    int rc;
+    for (int q = 0; q < 2; q++) if ((rc = s->w_keys[q].ensure((size_t)n * 4)) || (rc = s->w_vals[q].ensure((size_t)n * 4))) return rc;
+    const unsigned blocks = (unsigned)(((size_t)WEIGH_SEEDS * mates * n + 255) / 256);
+    if (mates == 2)
+        weigh_kernel<2><<<blocks, 256, 0, s->stream>>>(x->dev, dev_batch(s, 0), dev_batch(s, 1), n, max_hits, s->w_keys[0].as<uint32_t>(), s->w_vals[0].as<uint32_t>());
+    else
+        weigh_kernel<1><<<blocks, 256, 0, s->stream>>>(x->dev, dev_batch(s, 0), dev_batch(s, 0), n, max_hits, s->w_keys[0].as<uint32_t>(), s->w_vals[0].as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    s->last_launches++;
+    cub::DoubleBuffer<uint32_t> kb(s->w_keys[0].as<uint32_t>(), s->w_keys[1].as<uint32_t>());
+    cub::DoubleBuffer<uint32_t> vb(s->w_vals[0].as<uint32_t>(), s->w_vals[1].as<uint32_t>());
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 16, s->stream);
+    if ((rc = s->w_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->w_tmp.p, tmp_bytes, kb, vb, (int)n, 0, 16, s->stream));
+    s->last_launches += 2;  // histogram + onesweep
+    *order = vb.Current();
+    return 0;
+}
+
 struct SingleTier { uint32_t pool_cap, tsize; int grid; };
 
 static int launch_single(snapb200_session *s, const SingleCfg &cfg_in, const SingleTier &tier, const DevBatch b[2], int two_batches,
@@ -738,7 +765,13 @@ static int single_cfg_from(const snapb200_index *x, const snapb200_single_params
 
 // Small tier: enough for almost every read; large tier: the bound implied by the reference's loop
 // ((maxSeeds+1) seed directions of at most maxHits hits), with fewer resident warps if HBM would not hold it.
-static void single_tiers(const snapb200_index *x, const SingleCfg &cfg, uint32_t max_len, SingleTier *small_t, SingleTier *large_t)
+// Scratch tiers of the single-end aligner: every read first tries a small element pool at full occupancy; a read that
+// overflows it is aborted and rerun from scratch in the next tier (deterministic, so the result cannot depend on the
+// tier).  The last tier has the reference's own pool size (maxHits * (maxSeeds + 1) elements, BaseAligner.cpp:130), which
+// at -h 16000 is 23 MB per warp and leaves room for only ~800 warps -- hence the middle tier, which still runs at full
+// occupancy and takes all but a handful of the reads that outgrow the first.
+#define MAX_SINGLE_TIERS 3
+static int single_tiers(const snapb200_index *x, const SingleCfg &cfg, uint32_t max_len, SingleTier *tiers)
 {
     uint32_t max_seeds = cfg.num_seeds ? cfg.num_seeds : (uint32_t)(int)(cfg.seed_coverage * max_len / x->dev.seed_len);
     uint64_t bound = (uint64_t)cfg.max_hits * (max_seeds + 1);
@@ -747,48 +780,51 @@ static void single_tiers(const snapb200_index *x, const SingleCfg &cfg, uint32_t
     int per_sm = 1;
     size_t smem = single_warp_shared(cfg.rl) * WARPS_PER_CTA;
     int grid = grid_for(single_kernel, smem, x->sm_count, &per_sm);
-    small_t->pool_cap = (uint32_t)std::min<uint64_t>(bound, 1024);
-    small_t->tsize = next_pow2(small_t->pool_cap * 2);
-    small_t->grid = grid;
-    large_t->pool_cap = (uint32_t)bound;
-    large_t->tsize = next_pow2((uint32_t)std::min<uint64_t>(bound * 2, 1u << 25));
-    size_t per_warp = (size_t)large_t->pool_cap * sizeof(Elem) + (size_t)large_t->tsize * 2 * sizeof(int2);
-    size_t warps = std::max<size_t>(1, SCRATCH_BUDGET / per_warp);
-    int g = (int)std::min<size_t>((size_t)grid, std::max<size_t>(1, warps / WARPS_PER_CTA));
-    large_t->grid = g;
+    const uint64_t caps[MAX_SINGLE_TIERS] = {2048, 16384, bound};
+    int n = 0;
+    for (int i = 0; i < MAX_SINGLE_TIERS; i++) {
+        const uint64_t cap = std::min<uint64_t>(caps[i], bound);
+        if (n > 0 && cap <= tiers[n - 1].pool_cap) continue;
+        SingleTier &t = tiers[n++];
+        t.pool_cap = (uint32_t)cap;
+        t.tsize = next_pow2((uint32_t)std::min<uint64_t>(cap * 2, 1u << 25));
+        size_t per_warp = (size_t)t.pool_cap * sizeof(Elem) + (size_t)t.tsize * 2 * sizeof(int2);
+        size_t warps = std::max<size_t>(1, SCRATCH_BUDGET / per_warp);
+        t.grid = (int)std::min<size_t>((size_t)grid, std::max<size_t>(1, warps / WARPS_PER_CTA));
+    }
+    return n;
 }
-
-// run the single-end aligner over result slots [0,n_items) (positions == null) or the listed ones
 static int run_single_tiers(snapb200_session *s, const SingleCfg &cfg, uint32_t max_len, const DevBatch b[2], int two_batches,
                             const uint32_t *positions, uint32_t n_items, snapb200_single_result *results, int mapq_divisor)
 {
     if (n_items == 0) return 0;
-    SingleTier small_t, large_t;
-    single_tiers(s->idx, cfg, max_len, &small_t, &large_t);
+    SingleTier tiers[MAX_SINGLE_TIERS];
+    const int n_tiers = single_tiers(s->idx, cfg, max_len, tiers);
     int rc;
     if ((rc = s->retry_list.ensure(((size_t)std::max(n_items, s->max_items) + 1) * 4))) return rc;
-    CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
-    if ((rc = launch_single(s, cfg, small_t, b, two_batches, positions, n_items, results, mapq_divisor))) return rc;
-    if (small_t.pool_cap == large_t.pool_cap) return 0;
-    Counters c;
-    if ((rc = read_counters(s, &c))) return rc;
-    if (c.n_retry == 0) return 0;
-    // rerun the overflowed reads with the full-size pools; the retry list holds their result slots
-    std::vector<uint32_t> list(c.n_retry);
-    CUDA_TRY(cudaMemcpyAsync(list.data(), s->retry_list.p, (size_t)c.n_retry * 4, cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    std::sort(list.begin(), list.end());
     DevBuf tmp;
-    if ((rc = tmp.ensure((size_t)c.n_retry * 4))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(tmp.p, list.data(), (size_t)c.n_retry * 4, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
-    rc = launch_single(s, cfg, large_t, b, two_batches, tmp.as<uint32_t>(), c.n_retry, results, mapq_divisor);
-    if (!rc) {
-        Counters c2;
-        rc = read_counters(s, &c2);
-        if (!rc && c2.n_retry) rc = set_error(SNAPB200_ERR_LIMIT, "%u reads overflowed the full-size candidate pool", c2.n_retry);
+    const uint32_t *pos = positions;
+    uint32_t n = n_items;
+    for (int t = 0; t < n_tiers; t++) {
+        CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
+        if ((rc = launch_single(s, cfg, tiers[t], b, two_batches, pos, n, results, mapq_divisor))) break;
+        if (t + 1 == n_tiers && n_tiers == 1) break;  // one tier = the reference's pool: nothing can overflow it
+        Counters c;
+        if ((rc = read_counters(s, &c))) break;
+        if (c.n_retry == 0) break;
+        if (t + 1 == n_tiers) { rc = set_error(SNAPB200_ERR_LIMIT, "%u reads overflowed the full-size candidate pool", c.n_retry); break; }
+        // rerun the overflowed reads in the next tier; the retry list holds their result slots
+        std::vector<uint32_t> list(c.n_retry);
+        CUDA_TRY(cudaMemcpyAsync(list.data(), s->retry_list.p, (size_t)c.n_retry * 4, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        std::sort(list.begin(), list.end());
+        if ((rc = tmp.ensure((size_t)c.n_retry * 4))) break;
+        CUDA_TRY(cudaMemcpyAsync(tmp.p, list.data(), (size_t)c.n_retry * 4, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));  // `list` goes out of scope
+        pos = tmp.as<uint32_t>();
+        n = c.n_retry;
     }
-    tmp.release();
+    if (tmp.p) { cudaStreamSynchronize(s->stream); tmp.release(); }
     return rc;
 }
 
@@ -839,7 +875,9 @@ extern "C" int snapb200_session_run_single(snapb200_session *s, const snapb200_s
         if ((rc = s->mh_scores.ensure((size_t)std::max(n, 1u) * mh * 4))) return rc;
     }
     DevBatch b[2] = {dev_batch(s, 0), dev_batch(s, 0)};
-    if ((rc = run_single_tiers(s, cfg, s->max_len_seen, b, 0, nullptr, n, s->single_res.as<snapb200_single_result>(), 1))) return rc;
+    const uint32_t *order = nullptr;  // heaviest reads first, as in the paired path
+    if ((rc = work_order(s, 1, n, p->max_hits, &order))) return rc;
+    if ((rc = run_single_tiers(s, cfg, s->max_len_seen, b, 0, order, n, s->single_res.as<snapb200_single_result>(), 1))) return rc;
     if (n) {
         stats_single_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->single_res.as<snapb200_single_result>(), n, s->idx->stats);
         s->last_launches++;
@@ -956,23 +994,9 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
         cfg.mate_cap = (uint32_t)std::min<uint64_t>(ref_pool / 2, 12288);
         cfg.anchor_cap = cfg.cand_cap;
         cfg.hard_limit = (cfg.cand_cap == ref_pool && cfg.mate_cap == ref_pool / 2) ? 1 : 0;
-        // heaviest pairs first (see weigh_pairs_kernel); SNAPB200_NO_ORDER=1 serves them in input order (experiments)
+        // heaviest pairs first (see weigh_kernel); SNAPB200_NO_ORDER=1 serves them in input order (experiments)
         const uint32_t *order = nullptr;
-        if (n >= 4096 && !getenv("SNAPB200_NO_ORDER")) {
-            for (int q = 0; q < 2; q++) if ((rc = s->w_keys[q].ensure((size_t)n * 4)) || (rc = s->w_vals[q].ensure((size_t)n * 4))) return rc;
-            weigh_pairs_kernel<<<(unsigned)(((size_t)16 * n + 255) / 256), 256, 0, s->stream>>>(x->dev, dev_batch(s, 0), dev_batch(s, 1), n, p->max_big_hits,
-                                                                                           s->w_keys[0].as<uint32_t>(), s->w_vals[0].as<uint32_t>());
-            CUDA_TRY(cudaGetLastError());
-            s->last_launches++;
-            cub::DoubleBuffer<uint32_t> kb(s->w_keys[0].as<uint32_t>(), s->w_keys[1].as<uint32_t>());
-            cub::DoubleBuffer<uint32_t> vb(s->w_vals[0].as<uint32_t>(), s->w_vals[1].as<uint32_t>());
-            size_t tmp_bytes = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 16, s->stream);
-            if ((rc = s->w_tmp.ensure(tmp_bytes))) return rc;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->w_tmp.p, tmp_bytes, kb, vb, (int)n, 0, 16, s->stream));
-            s->last_launches += 2;  // histogram + onesweep
-            order = vb.Current();
-        }
+        if ((rc = work_order(s, 2, n, p->max_big_hits, &order))) return rc;
         if ((rc = launch_paired(s, p, cfg, grid, order, n))) return rc;
         Counters c;
         if ((rc = read_counters(s, &c))) return rc;

@@ -229,3 +229,50 @@ def make_gtf(path, contigs, seed=31, gene_frac=0.03, decoy="chrDecoy"):
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     return len(lines)
+
+
+def transcripts_from_gtf(gtf_path, contigs):
+    """Transcript sequences (exons concatenated in file order, '+' strand) of a GTF written by make_gtf: {transcript_id: bases}."""
+    import re
+    exons = {}
+    for line in open(gtf_path):
+        f = line.rstrip("\n").split("\t")
+        if len(f) < 9 or f[2] != "exon":
+            continue
+        tid = re.search(r'transcript_id "([^"]+)"', f[8]).group(1)
+        exons.setdefault(tid, []).append((f[0], int(f[3]) - 1, int(f[4])))
+    return {t: np.concatenate([contigs[c][a:b] for c, a, b in ex]) for t, ex in exons.items()}
+
+
+def simulate_rna(contigs, gtf_path, n, read_len, *, spliced_frac=0.5, chimeric_frac=0.01, err=0.02, seed=11, junk_frac=0.005,
+                 decoy="chrDecoy"):
+    """BASELINE.json configs[3]: n FR pairs, `spliced_frac` of the fragments drawn from spliced transcripts (so reads span exon
+    junctions), the rest from the genome, `chimeric_frac` of the pairs with mate 2 taken from another pair.  Returns [Batch, Batch]."""
+    rng = np.random.default_rng(seed)
+    real = {k: v for k, v in contigs.items() if k != decoy}
+    tx = {k: v for k, v in transcripts_from_gtf(gtf_path, contigs).items() if "decoy" not in k}
+    frag = (max(250, read_len + 20), max(450, read_len + 200))
+    tx = {k: v for k, v in tx.items() if len(v) > frag[1] + 64}
+    n_sp = int(n * spliced_frac) if tx else 0
+    parts = [simulate(real, n - n_sp, read_len, paired=True, err=err, seed=seed + 1, junk_frac=junk_frac, frag=frag)["batches"]]
+    if n_sp:
+        parts.append(simulate(tx, n_sp, read_len, paired=True, err=err, seed=seed + 2, frag=frag)["batches"])
+    order = rng.permutation(n)
+    out = []
+    for mate in range(2):
+        reads = np.concatenate([p[mate].bases.reshape(-1, read_len) for p in parts])[order]
+        quals = np.concatenate([p[mate].quals.reshape(-1, read_len) for p in parts])[order]
+        out.append([reads, quals])
+    k = int(n * chimeric_frac)
+    if k:
+        a, b = rng.choice(n, size=k, replace=False), rng.choice(n, size=k, replace=False)
+        out[1][0][a], out[1][1][a] = out[1][0][b].copy(), out[1][1][b].copy()
+    return [_to_batch(r, q) for r, q in out]
+
+
+def write_fastq_plain(path, batch, mate=0, prefix="r"):
+    """FASTQ with ids <prefix><serial>/<mate> (mates of a pair share the id up to the slash, as Read::checkIdMatch wants)."""
+    with open(path, "wb") as f:
+        for i in range(batch.n):
+            b, q = batch.read(i)
+            f.write(f"@{prefix}{i:x}/{mate + 1}\n{b}\n+\n{q}\n".encode())

@@ -238,6 +238,59 @@ def test_large_batch_properties(cuda, handle):
     assert ok.mean() > 0.9
 
 
+# ---- medium-sized differential run: large enough for the work-ordering pass (>= 4096 items), lane-mode batches of 32, the
+# order array and the scratch tiers to be exercised against the reference itself ----
+@pytest.fixture(scope="module")
+def medium(cuda, tmp_path_factory):
+    contigs = synth.random_contigs([900_000, 700_000, 400_000], seed=120)
+    synth.inject_repeats(contigs, frac=0.08, seed=121, min_len=150, max_len=2000, max_copies=300)
+    bases, offs = synth.snap_layout(contigs, 500)
+    h = cuda.build_index(bases, offs, list(contigs), seed_len=20)
+    d = tmp_path_factory.mktemp("medium") / "idx"
+    cuda.save_index(h, d)
+    yield contigs, h, str(d)
+    cuda.close_index(h)
+
+
+def _best_checker(port):
+    from oracle import oracle as O
+    return ("ref", O.ref(threads=8)) if O.have_ref() else ("port", port)
+
+
+@pytest.mark.parametrize("rlen,err,max_k,n", [(150, 0.01, 15, 24000), (100, 0.03, 15, 16000), (250, 0.04, 20, 6000)])
+def test_medium_genome_paired(cuda, port, medium, rlen, err, max_k, n):
+    contigs, h, d = medium
+    sim = synth.simulate(contigs, n, rlen, paired=True, err=err, indel_frac=0.15, seed=rlen, junk_frac=0.01, n_rate=0.01,
+                         frag=(max(250, rlen + 20), max(450, rlen + 200)))
+    b0, b1 = sim["batches"]
+    pp = A.paired_defaults(max_k=max_k)
+    got = cuda.paired(h, pp, b0, b1)
+    name, chk = _best_checker(port)
+    want = chk.paired(chk.load_index(d), pp, b0, b1)
+    assert_records_equal(want, got, what=f"medium paired {rlen}bp vs {name}")
+    assert int(got["n_lv_calls"].max()) > 200  # repeat-family pairs are in the set
+
+
+def test_medium_genome_single_multihit_characterize(cuda, port, medium):
+    contigs, h, d = medium
+    sim = synth.simulate(contigs, 12000, 100, paired=True, err=0.02, indel_frac=0.15, seed=77, junk_frac=0.02, n_rate=0.01)
+    b0, b1 = sim["batches"]
+    name, chk = _best_checker(port)
+    hc = chk.load_index(d)
+    ps = A.single_defaults()
+    assert_records_equal(chk.single(hc, ps, b0), cuda.single(h, ps, b0), what=f"medium single vs {name}")
+    pm = A.single_defaults(max_hits_to_get=1000, max_hits=16000, num_seeds=8, max_k=15)  # transcriptomeAligner, PairedAligner.cpp:512
+    want, got = chk.single_multihit(hc, pm, b1), cuda.single_multihit(h, pm, b1)
+    assert_records_equal(want[0], got[0], what=f"medium multihit vs {name}")
+    np.testing.assert_array_equal(want[1], got[1])
+    for i in range(b1.n):
+        k = int(want[1][i])
+        assert np.array_equal(want[2][i, :k], got[2][i, :k]) and np.array_equal(want[3][i, :k], got[3][i, :k]) and np.array_equal(want[4][i, :k], got[4][i, :k]), i
+    pc = A.single_defaults(max_hits=300, num_seeds=12, max_k=15)  # partialAligner, PairedAligner.cpp:518-527
+    for w, g in zip(chk.characterize(hc, pc, b0), cuda.characterize(h, pc, b0)):
+        np.testing.assert_array_equal(w, g)
+
+
 # ---- device-side index construction (lookup-equivalent to GenomeIndex::BuildIndexToDirectory) ----
 @pytest.mark.parametrize("seed_len", [20, 16, 23])
 def test_index_build_equivalence(cuda, port, tmp_path, seed_len, golden, small_index_dir):

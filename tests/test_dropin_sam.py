@@ -57,6 +57,10 @@ def workspace(tmp_path_factory):
     sim2 = synth.simulate(real, 4000, 100, paired=True, err=0.02, seed=6, junk_frac=0.01)
     synth.write_fastq(os.path.join(d, "p1.fq"), sim2["batches"][0], sim2, mate=0)
     synth.write_fastq(os.path.join(d, "p2.fq"), sim2["batches"][1], sim2, mate=1)
+    # BASELINE.json configs[3]: half of the fragments from spliced transcripts (junction-spanning reads), 1 % chimeric pairs
+    r0, r1 = synth.simulate_rna(contigs, os.path.join(d, "a.gtf"), 4000, 100, seed=8)
+    synth.write_fastq_plain(os.path.join(d, "x1.fq"), r0, mate=0)
+    synth.write_fastq_plain(os.path.join(d, "x2.fq"), r1, mate=1)
     return d
 
 
@@ -74,3 +78,14 @@ def test_paired_end_sam_identical(workspace):
     run([B200, "paired", "gidx", "tidx", "a.gtf", "p1.fq", "p2.fq", "-o", "gpu_p.sam", "-t", "2"], d)
     a, b = sam_records(os.path.join(d, "ref_p.sam")), sam_records(os.path.join(d, "gpu_p.sam"))
     assert_same(a, b, 8000)
+
+
+def test_rna_mode_spliced_and_chimeric_pairs_sam_identical(workspace):
+    """C4: spliced (junction-spanning) and chimeric pairs through the whole RNA pipeline -- transcriptome + genome alignment on
+    the device, AlignmentFilter / GTF / splice-junction CIGARs / CharacterizeSeeds consumers on the host, unchanged."""
+    d = workspace
+    run([REF, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "ref_x.sam", "-t", "2"], d)
+    run([B200, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "gpu_x.sam", "-t", "2"], d)
+    a, b = sam_records(os.path.join(d, "ref_x.sam")), sam_records(os.path.join(d, "gpu_x.sam"))
+    assert_same(a, b, 8000)
+    assert sum("N" in r.split("\t")[5] for r in a) > 30  # spliced alignments (N in the CIGAR) are really in there

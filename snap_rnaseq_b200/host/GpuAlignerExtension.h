@@ -23,6 +23,7 @@
 #include <vector>
 
 #include <pthread.h>
+#include <sys/time.h>
 
 #include "AlignerContext.h"
 #include "AlignmentFilter.h"
@@ -241,9 +242,12 @@ public:
         std::vector<uint8_t> rc0, rc1;
         Read *read0, *read1;
         bool more = true;
+        double tDrain = 0, tAbi = 0, tReplay = 0, tMark;
+        unsigned long nReads = 0;
         while (more) {
             s0.clear(); s1.clear();
             std::vector<char> skip;
+            tMark = now();
             while (s0.size() < batch_ && (more = supplier->getNextReadPair(&read0, &read1))) {
                 if (!AlignerContext2::ignoreMismatchedIDs(pc)) Read::checkIdMatch(read0, read1);
                 ctx->stats->totalReads += 2;
@@ -257,7 +261,10 @@ public:
                 skip.push_back(bad);
             }
             const unsigned n = s0.size();
+            tDrain += now() - tMark;
             if (n == 0) break;
+            nReads += 2ul * n;
+            tMark = now();
             snapb200_read_batch b0 = s0.batch(), b1 = s1.batch();
             res.resize(n); t0.resize(n); t1.resize(n); n0.resize(n); n1.resize(n);
             l0.resize((size_t)n * maxHitsToGet); l1.resize((size_t)n * maxHitsToGet); rc0.resize((size_t)n * maxHitsToGet);
@@ -267,6 +274,8 @@ public:
             check(snapb200_paired_batch(genome_, &pp, &b0, &b1, &res[0]));
             check(partial->compute(genome_, 0, &b0));
             check(partial->compute(genome_, 1, &b1));
+            tAbi += now() - tMark;
+            tMark = now();
             for (unsigned i = 0; i < n; i++) {
                 Read r0, r1;
                 s0.get(i, &r0, ctx->clipping); s1.get(i, &r1, ctx->clipping);
@@ -306,7 +315,9 @@ public:
                 AlignerContext2::writePair(pc, &r0, &r1, &result);
                 AlignerContext2::updateStats(pc, &r0, &r1, &result);
             }
+            tReplay += now() - tMark;
         }
+        report("paired", tDrain, tAbi, tReplay, nReads);
         snapb200_stats st;
         if (snapb200_stats_get(genome_, &st) == SNAPB200_OK) ctx->stats->lvCalls = st.n_locations_scored;
         delete partial;
@@ -394,6 +405,20 @@ private:
         *slot = it->second;
         *name = dir;
         pthread_mutex_unlock(&lock);
+    }
+
+    // SNAPB200_SHIM_TIMING=1: per worker thread, seconds spent draining the supplier, inside the C ABI and replaying the
+    // host post-processing (printed to stderr when the thread finishes)
+    static double now()
+    {
+        struct timeval tv;
+        gettimeofday(&tv, NULL);
+        return tv.tv_sec + tv.tv_usec * 1e-6;
+    }
+    static void report(const char *what, double drain, double abi, double replay, unsigned long reads)
+    {
+        if (getenv("SNAPB200_SHIM_TIMING") != NULL)
+            fprintf(stderr, "[snapb200 shim] %s thread: %lu reads, drain %.2f s, C ABI %.2f s, host replay %.2f s\n", what, reads, drain, abi, replay);
     }
 
     static void check(int rc)

@@ -147,20 +147,6 @@ __device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, const uint
     return l;
 }
 
-// Ask L2 for the genome window [loc, loc + span) of a location that phase 3 may score: lanes 0..3 touch one 128-byte line
-// each.  DRAM bandwidth is nearly idle on this path (ncu: < 1 % of peak) while a scored location otherwise starts with a
-// chain of dependent DRAM misses, so every candidate and mate is requested as soon as phase 2 creates it.
-__device__ __forceinline__ void prefetch_window(const DevIndex &ix, uint32_t loc, uint32_t span)
-{
-    // lane 0: the MAX_K bytes before loc that the backward Landau-Vishkin may look at; lanes 1..: loc, loc+128, ..., loc+span-1
-    const int lane = lane_id();
-    const long long o = lane == 0 ? -(long long)MAXK - 1 : (long long)(lane - 1) * 128;
-    if (o < (long long)span + 128) {
-        const long long at = (long long)loc + (o < (long long)span ? o : (long long)span - 1);
-        if (at >= -GENOME_PAD && at < (long long)ix.n_bases + GENOME_PAD) asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.genome + at));
-    }
-}
-
 __device__ __forceinline__ bool is_within(uint32_t a, uint32_t b, uint32_t dist)
 {  // Util.h:538-541 with its unsigned wrap-around
     return (a <= b && (uint32_t)(a + dist) >= b) || (a >= b && a <= (uint32_t)(b + dist));
@@ -425,7 +411,6 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
     __syncwarp();
     const int more = (sm->total_hits[0][0] + sm->total_hits[0][1] > sm->total_hits[1][0] + sm->total_hits[1][1]) ? 0 : 1;  // :342
     const int fewer = 1 - more;
-    const uint32_t span_f = (fewer ? rlen1 : rlen0) + MAXK, span_m = (more ? rlen1 : rlen0) + MAXK;  // genome window of a scored location
     // setPairDirection (:351): set pair sp uses read0 in direction sp, read1 in direction 1-sp
     if (lane == 0) {
         #pragma unroll 1
@@ -469,7 +454,6 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             while (m_loc + max_spacing >= f_loc && !out_of_more) {
                 uint32_t bp = hs_best_possible(lm, exhl_m, maxexh_m, mr_m, max_k);
                 if (n_mates >= cfg.mate_cap) return 2;
-                prefetch_window(ix, m_loc, span_m);
                 if (lane == 0) {
                     Mate *m = &mates[n_mates];
                     m->loc = m_loc; m->best_possible = bp; m->seed_offset = m_off;
@@ -506,7 +490,6 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             }
             if (low_mate + bp_fewer <= max_k + extra) {
                 if (n_cands >= cfg.cand_cap) return 2;
-                prefetch_window(ix, f_loc, span_f);
                 if (lane == 0) {
                     Cand *c = &sc.cands[n_cands];
                     c->loc = f_loc; c->set_pair = (uint8_t)sp; c->mate_index = n_mates - 1; c->seed_offset = (uint16_t)f_off;

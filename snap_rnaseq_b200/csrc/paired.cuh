@@ -11,6 +11,7 @@
 // warp-cooperative Landau-Vishkin of lv.cuh, the leader lane keeping the merge/MAPQ bookkeeping in the
 // reference's order.
 #pragma once
+#include <cstddef>
 #include "single.cuh"
 
 #define SC_NONE (-3)       // "score not computed yet" in the look-ahead caches below
@@ -99,6 +100,8 @@ struct PairedSm {
     uint32_t n_sched_w[2];
     uint32_t total_hits[2][2], popular[2], n_look[2];
     uint32_t list_pos[32];   // counting sort of the candidates by score list (phase 2 -> 3)
+    uint32_t ring_loc[32];   // phase 2: location and bestPossibleScore of the newest 32 mates (entry i at i & 31)
+    uint32_t ring_bp[32];
     // phase 3 exchange
     double p_all, p_best, f_prob, m_prob;
     uint32_t best_pair_score, score_limit, n_cands, n_anchors, n_mates[2], pos;
@@ -149,7 +152,8 @@ __device__ __forceinline__ LaneLookup load_lookup(const PairedSm *sm, const uint
 
 __device__ __forceinline__ bool is_within(uint32_t a, uint32_t b, uint32_t dist)
 {  // Util.h:538-541 with its unsigned wrap-around
-    return (a <= b && (uint32_t)(a + dist) >= b) || (a >= b && a <= (uint32_t)(b + dist));
+    // (a <= b && a + dist >= b) || (a >= b && a <= b + dist), as one select instead of a chain of branches
+    return a <= b ? (uint32_t)(a + dist) >= b : a <= (uint32_t)(b + dist);
 }
 
 // max over lanes of (ok ? val : 0) with the reference's "first strictly greater wins" tie rule; returns whether
@@ -159,7 +163,7 @@ __device__ __forceinline__ bool pick_max(bool ok, uint32_t val, uint32_t so, uin
     uint32_t v = ok ? val : 0;
     uint32_t m = __reduce_max_sync(FULL_MASK, v);
     if (m == 0) return false;
-    unsigned who = __ballot_sync(FULL_MASK, ok && val == m);
+    unsigned who = __ballot_sync(FULL_MASK, v == m);  // m > 0, so v == m implies ok
     int src = __ffs(who) - 1;
     *best = m;
     *best_so = __shfl_sync(FULL_MASK, so, src);
@@ -212,26 +216,18 @@ __device__ __forceinline__ bool hs_next_le(LaneLookup &l, uint32_t *most_recent,
     return true;
 }
 
-// getNextLowerHit (:1286-1322)
+// getNextLowerHit (:1286-1322).  A lane without a lookup has nh == cur == 0 and falls through everything.
 __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_recent, uint32_t *loc, uint32_t *so)
 {
-    bool ok = false;
-    uint32_t val = 0;
-    if (l.act) {
-        if (l.cur != l.nh && l.cur_val - l.so == *most_recent) {
-            l.cur++;
-            l.prev_val = l.cur_val;
-            if (l.cur != l.nh) {
-                l.cur_val = l.next_val;
-                l.words++;
-                if (l.cur + 1 < l.nh) l.next_val = hit_at(l, l.cur + 1);
-            }
-        }
-        if (l.cur != l.nh) {
-            val = l.cur_val - l.so;
-            ok = l.cur_val >= l.so;
-        }
+    if (l.cur != l.nh && l.cur_val - l.so == *most_recent) {
+        l.cur++;
+        l.prev_val = l.cur_val;
+        l.cur_val = l.next_val;
+        l.words += l.cur != l.nh;
+        if (l.cur + 1 < l.nh) l.next_val = __ldg(&l.hits[l.cur + 1]);  // never an inline list: those have at most one hit
     }
+    const uint32_t val = l.cur_val - l.so;
+    const bool ok = l.cur != l.nh && l.cur_val >= l.so;
     if (!pick_max(ok, val, l.so, loc, so)) return false;
     *most_recent = *loc;
     return true;
@@ -242,12 +238,9 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
 __device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, uint32_t exh_mine, uint32_t max_exh, uint32_t most_recent,
                                                      uint32_t merge_dist)
 {
-    bool miss = false;
-    if (l.act) {
-        uint32_t target = most_recent + l.so;
-        bool close = (l.cur != l.nh && is_within(l.cur_val, target, merge_dist)) || (l.cur != 0 && is_within(l.prev_val, target, merge_dist));
-        miss = !close;
-    }
+    const uint32_t target = most_recent + l.so;
+    const bool close = ((l.cur != l.nh) & is_within(l.cur_val, target, merge_dist)) | ((l.cur != 0) & is_within(l.prev_val, target, merge_dist));
+    const bool miss = l.act & !close;
     // misses per disjoint hit set: lanes of the same set that missed find each other with one match
     const unsigned peers = __match_any_sync(FULL_MASK, miss ? l.sid : 0xffffffffu);
     const uint32_t mine = miss ? exh_mine + (uint32_t)__popc(peers) : 0u;
@@ -459,6 +452,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                     m->loc = m_loc; m->best_possible = bp; m->seed_offset = m_off;
                     m->score = (uint32_t)-2; m->score_limit = (uint32_t)-1; m->prob = 0; m->genome_offset = 0;
                     m->s_score = SC_NONE; m->s_k = 0;
+                    sm->ring_loc[n_mates & 31] = m_loc; sm->ring_bp[n_mates & 31] = bp;
                 }
                 n_mates++;
                 last_mate_loc = m_loc;
@@ -471,14 +465,17 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             uint32_t bp_fewer = hs_best_possible(lf, exhl_f, maxexh_f, mr_f, max_k);
             // lowest bestPossibleScore among the mates in range (:469-475): scan back from the newest mate, 32 per step
             uint32_t low_mate = max_k + extra;
-            __syncwarp();  // the leader's mate records must be visible to the other lanes
+            __syncwarp();  // the mate records and the ring must be visible to all lanes
             #pragma unroll 1
             for (int top = (int)n_mates - 1; top >= 0; top -= 32) {
                 const int i = top - lane;
                 bool stop = false;
                 uint32_t bp = 0xffffffffu;
                 if (i >= 0) {
-                    if (mates[i].loc > f_loc + max_spacing) stop = true; else bp = mates[i].best_possible;
+                    // the newest 32 mates are in the shared-memory ring; older ones (rare: more than 32 mates in range) in HBM
+                    const bool recent = top == (int)n_mates - 1;
+                    const uint32_t mloc = recent ? sm->ring_loc[i & 31] : mates[i].loc;
+                    if (mloc > f_loc + max_spacing) stop = true; else bp = recent ? sm->ring_bp[i & 31] : mates[i].best_possible;
                 }
                 const unsigned stops = __ballot_sync(FULL_MASK, stop);
                 if (stops) {  // lanes beyond the first out-of-range mate do not count

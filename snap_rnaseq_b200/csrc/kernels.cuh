@@ -2,7 +2,9 @@
 #pragma once
 #include "paired.cuh"
 
+#ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 8
+#endif
 #define CTA_THREADS (WARPS_PER_CTA * 32)
 
 struct DevBatch {  // a snapb200_read_batch resident in HBM
@@ -65,7 +67,7 @@ __host__ __device__ inline size_t single_warp_shared(uint32_t rl)
     return s;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 3) single_kernel(const SingleArgs a)
+__global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) single_kernel(const SingleArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -156,7 +158,7 @@ __host__ __device__ inline size_t paired_warp_shared(uint32_t rl, uint32_t lane_
     return s;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 3) paired_kernel(const PairedArgs a)
+__global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) paired_kernel(const PairedArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();

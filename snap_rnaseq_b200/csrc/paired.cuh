@@ -15,8 +15,13 @@
 #include "single.cuh"
 
 #define SC_NONE (-3)       // "score not computed yet" in the look-ahead caches below
+// Tunables (measured on C3, ms per million pairs: look-ahead rounds 1/2/3 = 117/95/96; minimum lane batch 2/3/6 = 102/95/95)
+#ifndef MATE_LOOKAHEAD_ROUNDS
 #define MATE_LOOKAHEAD_ROUNDS 2  // mates scored ahead per candidate of a lane-mode batch
-#define LANE_MIN_BATCH 3   // fewer pending locations than this: the warp-cooperative LV is used (measured: no gain from lane mode below it)
+#endif
+#ifndef LANE_MIN_BATCH
+#define LANE_MIN_BATCH 3  // fewer pending locations than this: the warp-cooperative LV is used
+#endif
 
 struct __align__(8) Mate {  // ScoringMateCandidate (IntersectingPairedEndAligner.h:401-423)
     double prob;

@@ -112,7 +112,7 @@ struct PairedSm {
     uint32_t best_pair_score, score_limit, n_cands, n_anchors, n_mates[2], pos;
     uint32_t best_loc[2], best_score[2];
     int best_dir[2];
-    int act, act2, ci, stop, overflow, list, f_off, m_off, fs, ms;
+    int act, act2, ci, stop, overflow, state, f_off, m_off, fs, ms;
     uint32_t n_batch;
     uint32_t batch_ids[32];
     uint32_t c_loc, c_seedoff, c_sp, mi, m_loc, m_seedoff, m_limit, low_mate;
@@ -548,6 +548,13 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             __syncwarp();
         }
     }
+    // Phase 3 proper is a leader-driven state machine.  Lane 0 walks candidates and their mates in the reference's order for
+    // as long as every score it needs is already known (from the look-ahead below, or because the location was scored
+    // before): candidates whose fewer end does not fit the limit, mates that are out of range or already failed, commits
+    // and merges cost no warp-wide step at all.  Only when a score is missing does it hand over to the warp, which scores
+    // that location together with the next ones in visiting order, and then picks up exactly where it stopped.
+    enum { NEED_DONE = 0, NEED_OVERFLOW, NEED_CAND_BATCH, NEED_CAND_WARP, NEED_MATE };
+    enum { ST_PICK = 0, ST_PICK_RESUME, ST_MATES, ST_MATES_RESUME };
     if (lane == 0) {
         sm->n_cands = n_cands;
         sm->pos = 0;
@@ -555,192 +562,87 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
         sm->p_all = 0; sm->p_best = 0;
         sm->best_pair_score = 65536;
         sm->stop = 0;
+        sm->state = ST_PICK;
     }
     __syncwarp();
     #pragma unroll 1
     for (;;) {
         if (lane == 0) {
-            int act = 0;
-            sm->n_batch = 0;
-            if (!sm->stop && sm->pos < n_cands) {
-                const int ci = (int)sc.order[sm->pos];
-                const Cand *c = &sc.cands[ci];
-                if ((uint32_t)c->list <= sm->score_limit) {  // lists beyond the limit are never served (:527-530)
-                    sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
-                    sm->n_lv++;
-                    // score not known yet: the warp gathers the unscored candidates among the next 32 in visiting order
-                    act = (c->c_score == SC_NONE && sm->score_limit <= cfg.lane_k) ? 2 : 1;
-                }
-            }
-            sm->act = act;
-        }
-        __syncwarp();
-        if (sm->act == 2) {
-            const uint32_t at = sm->pos + (uint32_t)lane;
-            bool want = false;
-            uint32_t j = 0;
-            if (at < n_cands) {
-                j = sc.order[at];
-                want = sc.cands[j].c_score == SC_NONE && (uint32_t)sc.cands[j].list <= sm->score_limit;
-            }
-            const unsigned m = __ballot_sync(FULL_MASK, want);
-            if (want) sm->batch_ids[__popc(m & ((1u << lane) - 1u))] = j;
-            if (lane == 0) sm->n_batch = (uint32_t)__popc(m);
-        }
-        __syncwarp();
-        if (!sm->act) break;
-        const uint32_t sp = sm->c_sp;
-        const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
-        PROF(long long t_x = clock64();)
-        const uint32_t n_batch = sm->n_batch;
-        if (n_batch >= LANE_MIN_BATCH) {
-            // lane mode: lane i scores candidate batch_ids[i] with K = current limit
-            const int K = (int)sm->score_limit;
-            bool act_l = (uint32_t)lane < n_batch;
-            Cand *cl = act_l ? &sc.cands[sm->batch_ids[lane]] : nullptr;
-            int s = SC_NONE, off = 0;
-            double pr = 0;
-            const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
-            score_location_lane(ix_slot, view(fewer), dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
-            if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
-            __syncwarp();
-            PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_x; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
-            // Mate look-ahead: a candidate whose fewer end scored s will ask its mates for a score with limit <= K - s.
-            // Each lane walks the mates of its own candidate and, per round, one still-unknown mate per lane is scored.
-            {
-                PROF(long long t_m = clock64();)
-                bool walking = act_l && s >= 0;
-                const int Km = K - (s > 0 ? s : 0);
-                const uint32_t spl = act_l ? cl->set_pair : 0;
-                const int dml = more == 0 ? (int)spl : 1 - (int)spl;
-                const uint32_t cloc = act_l ? cl->loc : 0;
-                uint32_t j = act_l ? cl->mate_index : 0;
-                Mate *mbase = sc.mates_of(spl);
-                uint32_t n_done = 0;
-                #pragma unroll 1
-                for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
-                    Mate *mt = nullptr;
-                    #pragma unroll 1
-                    while (walking) {
-                        Mate *q = &mbase[j];
-                        const bool needs = !is_within(q->loc, cloc, min_spacing) && q->best_possible <= (uint32_t)Km &&
-                                           (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < (uint32_t)Km)) &&
-                                           !mate_known(q, (uint32_t)Km);
-                        if (j == 0 || !is_within(mbase[j - 1].loc, cloc, max_spacing)) walking = false; else j--;
-                        if (needs) { mt = q; break; }
-                    }
-                    if (!__any_sync(FULL_MASK, mt != nullptr)) break;
-                    // the same mate may be wanted by several candidates of the batch: one lane scores it, with the largest limit
-                    const unsigned long long key = (unsigned long long)mt;
-                    const unsigned peers = __match_any_sync(FULL_MASK, key);
-                    int gmax = 0;
-                    #pragma unroll 1
-                    for (int src = 0; src < 32; src++) {
-                        int kk = __shfl_sync(FULL_MASK, Km, src);
-                        if ((peers >> src) & 1) gmax = max(gmax, kk);
-                    }
-                    const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
-                    int s2 = SC_NONE, off2 = 0;
-                    double pr2 = 0;
-                    score_location_lane(ix_slot, view(more), dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, (int)cfg.lane_k, L + lane, sc.lane_table + lane, mine,
-                                        &s2, &pr2, &off2);
-                    if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
-                    n_done += __popc(__ballot_sync(FULL_MASK, mine));
-                    __syncwarp();
-                }
-                PROF(if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; })
-            }
-        }
-        if (lane == 0) sm->act = sc.cands[sm->ci].c_score == SC_NONE;
-        __syncwarp();
-        if (sm->act) {  // warp mode for this one candidate (small batch, large limit, or a window at the genome's edge)
-            double pr;
-            int off;
-            const int K = (int)sm->score_limit;
-            PROF(long long t_w = clock64();)
-            int s = score_location_warp(ix_slot, view(fewer), dir_f, sm->c_loc, sm->c_seedoff, K, false, W, L, &pr, &off);
-            __syncwarp();
-            PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
-            if (lane == 0) { Cand *c = &sc.cands[sm->ci]; c->c_score = (int16_t)s; c->c_k = (uint8_t)K; c->c_off = (int8_t)off; c->c_prob = pr; }
-            __syncwarp();
-        }
-        PROF(t_lv += clock64() - t_x;)
-        int fs, f_off;
-        double f_prob;
-        {
-            const Cand *c = &sc.cands[sm->ci];
-            const int cs = c->c_score;
-            fs = (cs >= 0 && (uint32_t)cs <= sm->score_limit) ? cs : -1;
-            f_prob = fs >= 0 ? c->c_prob : 0.0;
-            f_off = fs >= 0 ? (int)c->c_off : 0;
-        }
-        if (fs != -1) {
-            const uint32_t f_score = (uint32_t)fs;
+            int need = -1;
             #pragma unroll 1
-            for (;;) {  // mates of this candidate (:559-711)
-                if (lane == 0) {
-                    Mate *m = &sc.mates_of(sp)[sm->mi];
+            while (need < 0) {
+                if (sm->state <= ST_PICK_RESUME) {  // the next candidate in visiting order (:516-557)
+                    const bool resume = sm->state == ST_PICK_RESUME;
+                    if (!resume && (sm->stop || sm->pos >= n_cands)) { need = NEED_DONE; break; }
+                    const int ci = resume ? sm->ci : (int)sc.order[sm->pos];
+                    const Cand *c = &sc.cands[ci];
+                    if (!resume) {
+                        if ((uint32_t)c->list > sm->score_limit) { need = NEED_DONE; break; }  // lists beyond the limit are never served (:527-530)
+                        sm->n_lv++;
+                    }
+                    const int cs = c->c_score;
+                    if (cs == SC_NONE) {  // not scored yet: the warp scores it and the next unscored candidates in visiting order
+                        sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair;
+                        sm->state = ST_PICK_RESUME;
+                        need = sm->score_limit <= cfg.lane_k ? NEED_CAND_BATCH : NEED_CAND_WARP;
+                        break;
+                    }
+                    if (!(cs >= 0 && (uint32_t)cs <= sm->score_limit)) {  // scoreLocation says -1 for the limit in force: next candidate
+                        sm->pos++;
+                        sm->state = ST_PICK;
+                        continue;
+                    }
+                    sm->ci = ci; sm->c_loc = c->loc; sm->c_sp = c->set_pair; sm->mi = c->mate_index;
+                    sm->fs = cs; sm->f_prob = c->c_prob; sm->f_off = (int)c->c_off;
+                    sm->state = ST_MATES;
+                }
+                // mates of the current candidate (:559-711)
+                const uint32_t sp = sm->c_sp;
+                const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
+                const uint32_t f_score = (uint32_t)sm->fs;
+                const double f_prob = sm->f_prob;
+                const int f_off = sm->f_off;
+                Mate *mbase = sc.mates_of(sp);
+                Cand *c = &sc.cands[sm->ci];
+                #pragma unroll 1
+                for (;;) {
+                    Mate *m = &mbase[sm->mi];
                     int act = 0;
-                    sm->n_batch = 0;
-                    if (!is_within(m->loc, sm->c_loc, min_spacing) && m->best_possible <= sm->score_limit - f_score) {
+                    if (sm->state == ST_MATES_RESUME) {  // the warp has just scored this mate for sm->m_limit
+                        act = 2;
+                        sm->state = ST_MATES;
+                    } else if (!is_within(m->loc, sm->c_loc, min_spacing) && m->best_possible <= sm->score_limit - f_score) {
                         act = 1;
                         const uint32_t m_limit = sm->score_limit - f_score;
                         if (m->score == (uint32_t)-2 || (m->score == (uint32_t)-1 && m->score_limit < m_limit)) {
                             act = 2;
-                            sm->m_loc = m->loc; sm->m_seedoff = m->seed_offset; sm->m_limit = m_limit;
+                            sm->m_limit = m_limit;
                             sm->n_lv++;
                             if (!mate_known(m, m_limit)) {
                                 // not known well enough: gather the mates further down this candidate's range that will need a score
+                                sm->m_loc = m->loc; sm->m_seedoff = m->seed_offset;
                                 uint32_t nb = 0;
                                 const bool lane_ok = m_limit <= cfg.lane_k;
                                 uint32_t j = sm->mi;
                                 #pragma unroll 1
                                 for (;;) {
-                                    Mate *q = &sc.mates_of(sp)[j];
+                                    Mate *q = &mbase[j];
                                     if (!is_within(q->loc, sm->c_loc, min_spacing) && q->best_possible <= m_limit &&
                                         (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < m_limit)) &&
                                         !mate_known(q, m_limit))
                                         sm->batch_ids[nb++] = j;
                                     if (!lane_ok || nb >= 32) break;
-                                    if (j == 0 || !is_within(sc.mates_of(sp)[j - 1].loc, sm->c_loc, max_spacing)) break;
+                                    if (j == 0 || !is_within(mbase[j - 1].loc, sm->c_loc, max_spacing)) break;
                                     j--;
                                 }
                                 sm->n_batch = nb;
+                                sm->state = ST_MATES_RESUME;
+                                need = NEED_MATE;
+                                break;
                             }
                         }
                     }
-                    sm->act = act;
-                }
-                __syncwarp();
-                const int act = sm->act;
-                if (act == 2) {
-                    PROF(long long t_y = clock64();)
-                    const uint32_t nb = sm->n_batch;
-                    const int K = (int)sm->m_limit;
-                    if (nb >= LANE_MIN_BATCH) {
-                        bool act_l = (uint32_t)lane < nb;
-                        Mate *ml = act_l ? &sc.mates_of(sp)[sm->batch_ids[lane]] : nullptr;
-                        int s = SC_NONE, off = 0;
-                        double pr = 0;
-                        score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
-                        if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
-                        __syncwarp();
-                        PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; })
-                    }
-                    if (lane == 0) { const Mate *m = &sc.mates_of(sp)[sm->mi]; sm->act2 = !mate_known(m, sm->m_limit); }
-                    __syncwarp();
-                    if (sm->act2) {
-                        double m_prob;
-                        int m_off;
-                        PROF(long long t_w = clock64();)
-                        int ms = score_location_warp(ix_slot, view(more), dir_m, sm->m_loc, sm->m_seedoff, K, false, W, L, &m_prob, &m_off);
-                        __syncwarp();
-                        PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
-                        if (lane == 0) { Mate *m = &sc.mates_of(sp)[sm->mi]; m->s_score = (int16_t)ms; m->s_k = (uint8_t)K; m->s_off = (int8_t)m_off; m->s_prob = m_prob; }
-                        __syncwarp();
-                    }
-                    if (lane == 0) {  // commit: what scoreLocation(limit = m_limit) returns
-                        Mate *m = &sc.mates_of(sp)[sm->mi];
+                    if (act == 2) {  // commit: what scoreLocation(limit = m_limit) returns
                         const int d = m->s_score;
                         const bool ok = d >= 0 && (uint32_t)d <= sm->m_limit;
                         m->score = ok ? (uint32_t)d : (uint32_t)-1;
@@ -748,11 +650,6 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                         m->genome_offset = ok ? (int)m->s_off : 0;
                         m->score_limit = sm->m_limit;
                     }
-                    PROF(t_lv += clock64() - t_y;)
-                }
-                if (lane == 0) {
-                    Mate *m = &sc.mates_of(sp)[sm->mi];
-                    Cand *c = &sc.cands[sm->ci];
                     if (act != 0 && m->score != (uint32_t)-1) {
                         const double pair_prob = m->prob * f_prob;
                         const uint32_t pair_score = m->score + f_score;
@@ -822,19 +719,137 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                             if (sm->p_all >= 4.9) sm->stop = 1;  // nothing rescues a 0 MAPQ (:693-698)
                         }
                     }
-                    int go_on = 1;
-                    if (sm->stop || sm->overflow) go_on = 0;
-                    else if (sm->mi == 0 || !is_within(sc.mates_of(sp)[sm->mi - 1].loc, c->loc, max_spacing)) go_on = 0;
+                    bool go_on = true;
+                    if (sm->stop || sm->overflow) go_on = false;
+                    else if (sm->mi == 0 || !is_within(mbase[sm->mi - 1].loc, c->loc, max_spacing)) go_on = false;
                     else sm->mi--;
-                    sm->act = go_on;
+                    if (!go_on) {  // done with this candidate
+                        if (sm->overflow) need = NEED_OVERFLOW;
+                        else { if (!sm->stop) sm->pos++; sm->state = ST_PICK; }
+                        break;
+                    }
                 }
+            }
+            sm->act = need;
+        }
+        __syncwarp();
+        const int need = sm->act;
+        if (need == NEED_DONE) break;
+        if (need == NEED_OVERFLOW) return 2;
+        PROF(long long t_x = clock64();)
+        const uint32_t sp = sm->c_sp;
+        const int dir_f = fewer == 0 ? (int)sp : 1 - (int)sp, dir_m = more == 0 ? (int)sp : 1 - (int)sp;
+        if (need == NEED_MATE) {
+            const uint32_t nb = sm->n_batch;
+            const int K = (int)sm->m_limit;
+            if (nb >= LANE_MIN_BATCH) {
+                PROF(long long t_y = clock64();)
+                bool act_l = (uint32_t)lane < nb;
+                Mate *ml = act_l ? &sc.mates_of(sp)[sm->batch_ids[lane]] : nullptr;
+                int s = SC_NONE, off = 0;
+                double pr = 0;
+                score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+                if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
                 __syncwarp();
-                if (!sm->act) break;
+                PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; })
+            }
+            if (lane == 0) { const Mate *m = &sc.mates_of(sp)[sm->mi]; sm->act2 = !mate_known(m, sm->m_limit); }
+            __syncwarp();
+            if (sm->act2) {
+                double m_prob;
+                int m_off;
+                PROF(long long t_w = clock64();)
+                int ms = score_location_warp(ix_slot, view(more), dir_m, sm->m_loc, sm->m_seedoff, K, false, W, L, &m_prob, &m_off);
+                __syncwarp();
+                PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
+                if (lane == 0) { Mate *m = &sc.mates_of(sp)[sm->mi]; m->s_score = (int16_t)ms; m->s_k = (uint8_t)K; m->s_off = (int8_t)m_off; m->s_prob = m_prob; }
+            }
+            __syncwarp();
+            PROF(t_lv += clock64() - t_x;)
+            continue;
+        }
+        // a candidate's fewer end
+        uint32_t n_batch = 0;
+        if (need == NEED_CAND_BATCH) {  // the unscored candidates among the next 32 positions of the visiting order
+            const uint32_t at = sm->pos + (uint32_t)lane;
+            bool want = false;
+            uint32_t j = 0;
+            if (at < n_cands) {
+                j = sc.order[at];
+                want = sc.cands[j].c_score == SC_NONE && (uint32_t)sc.cands[j].list <= sm->score_limit;
+            }
+            const unsigned m = __ballot_sync(FULL_MASK, want);
+            if (want) sm->batch_ids[__popc(m & ((1u << lane) - 1u))] = j;
+            n_batch = (uint32_t)__popc(m);
+            __syncwarp();
+        }
+        if (n_batch >= LANE_MIN_BATCH) {
+            // lane mode: lane i scores candidate batch_ids[i] with K = current limit
+            PROF(long long t_y = clock64();)
+            const int K = (int)sm->score_limit;
+            bool act_l = (uint32_t)lane < n_batch;
+            Cand *cl = act_l ? &sc.cands[sm->batch_ids[lane]] : nullptr;
+            int s = SC_NONE, off = 0;
+            double pr = 0;
+            const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
+            score_location_lane(ix_slot, view(fewer), dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+            if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
+            __syncwarp();
+            PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
+            // Mate look-ahead: a candidate whose fewer end scored s will ask its mates for a score with limit <= K - s.
+            // Each lane walks the mates of its own candidate and, per round, one still-unknown mate per lane is scored.
+            {
+                PROF(long long t_m = clock64();)
+                bool walking = act_l && s >= 0;
+                const int Km = K - (s > 0 ? s : 0);
+                const uint32_t spl = act_l ? cl->set_pair : 0;
+                const int dml = more == 0 ? (int)spl : 1 - (int)spl;
+                const uint32_t cloc = act_l ? cl->loc : 0;
+                uint32_t j = act_l ? cl->mate_index : 0;
+                Mate *mbase = sc.mates_of(spl);
+                uint32_t n_done = 0;
+                #pragma unroll 1
+                for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
+                    Mate *mt = nullptr;
+                    #pragma unroll 1
+                    while (walking) {
+                        Mate *q = &mbase[j];
+                        const bool needs = !is_within(q->loc, cloc, min_spacing) && q->best_possible <= (uint32_t)Km &&
+                                           (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < (uint32_t)Km)) &&
+                                           !mate_known(q, (uint32_t)Km);
+                        if (j == 0 || !is_within(mbase[j - 1].loc, cloc, max_spacing)) walking = false; else j--;
+                        if (needs) { mt = q; break; }
+                    }
+                    if (!__any_sync(FULL_MASK, mt != nullptr)) break;
+                    // the same mate may be wanted by several candidates of the batch: one lane scores it, with the largest limit
+                    const unsigned peers = __match_any_sync(FULL_MASK, (unsigned long long)mt);
+                    const int gmax = __reduce_max_sync(peers, Km);
+                    const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
+                    int s2 = SC_NONE, off2 = 0;
+                    double pr2 = 0;
+                    score_location_lane(ix_slot, view(more), dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, (int)cfg.lane_k, L + lane, sc.lane_table + lane, mine,
+                                        &s2, &pr2, &off2);
+                    if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
+                    n_done += __popc(__ballot_sync(FULL_MASK, mine));
+                    __syncwarp();
+                }
+                PROF(if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; })
             }
         }
-        if (sm->overflow) return 2;
-        if (lane == 0 && !sm->stop) sm->pos++;
+        if (lane == 0) sm->act2 = sc.cands[sm->ci].c_score == SC_NONE;
         __syncwarp();
+        if (sm->act2) {  // warp mode for this one candidate (small batch, large limit, or a window at the genome's edge)
+            double pr;
+            int off;
+            const int K = (int)sm->score_limit;
+            PROF(long long t_w = clock64();)
+            int s = score_location_warp(ix_slot, view(fewer), dir_f, sm->c_loc, sm->c_seedoff, K, false, W, L, &pr, &off);
+            __syncwarp();
+            PROF(if (lane == 0) { sm->t_phase[8] += clock64() - t_w; sm->t_phase[9] += 1; })
+            if (lane == 0) { Cand *c = &sc.cands[sm->ci]; c->c_score = (int16_t)s; c->c_k = (uint8_t)K; c->c_off = (int8_t)off; c->c_prob = pr; }
+        }
+        __syncwarp();
+        PROF(t_lv += clock64() - t_x;)
     }
 
     if (lane == 0) {

@@ -342,10 +342,14 @@ def cpu_baseline(L, h, b0, b1, params, gpu_out):
         t0 = time.perf_counter()
         res = impl.paired(hc, params, s0, s1)
         dt = time.perf_counter() - t0
-    agree = all(np.array_equal(res[f], gpu_out[f][:n]) for f in ("location", "mapq", "status", "score", "direction"))
+    fields = ("location", "mapq", "status", "score", "direction")
+    agree = all(np.array_equal(res[f], gpu_out[f][:n]) for f in fields)
+    same = np.ones((n, 2), bool)  # per read: location, strand, edit distance, MAPQ and status all identical
+    for f in fields:
+        same &= res[f] == gpu_out[f][:n]
     return {"value": 2 * n / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"first {n} pairs of the rank-0 batch, {cores} threads, aligner calls only (no I/O)",
-            "bit_exact_vs_gpu_on_sample": bool(agree)}
+            "bit_exact_vs_gpu_on_sample": bool(agree), "reads_bit_exact_pct": float(100.0 * same.mean()), "reads_compared": int(2 * n)}
 
 
 def scratch_dir(need_bytes):

@@ -242,7 +242,7 @@ public:
         std::vector<uint8_t> rc0, rc1;
         Read *read0, *read1;
         bool more = true;
-        double tDrain = 0, tAbi = 0, tReplay = 0, tMark;
+        double tDrain = 0, tAbi = 0, tReplay = 0, tMark, tCall[3] = {0, 0, 0}, tAlloc = 0;
         unsigned long nReads = 0;
         while (more) {
             s0.clear(); s1.clear();
@@ -269,11 +269,15 @@ public:
             res.resize(n); t0.resize(n); t1.resize(n); n0.resize(n); n1.resize(n);
             l0.resize((size_t)n * maxHitsToGet); l1.resize((size_t)n * maxHitsToGet); rc0.resize((size_t)n * maxHitsToGet);
             rc1.resize((size_t)n * maxHitsToGet); sc0.resize((size_t)n * maxHitsToGet); sc1.resize((size_t)n * maxHitsToGet);
+            double tc = now();
             check(snapb200_single_multihit_batch(transcriptome_, &tp, &b0, &t0[0], &n0[0], &l0[0], &rc0[0], &sc0[0]));
             check(snapb200_single_multihit_batch(transcriptome_, &tp, &b1, &t1[0], &n1[0], &l1[0], &rc1[0], &sc1[0]));
+            tCall[0] += now() - tc; tc = now();
             check(snapb200_paired_batch(genome_, &pp, &b0, &b1, &res[0]));
+            tCall[1] += now() - tc; tc = now();
             check(partial->compute(genome_, 0, &b0));
             check(partial->compute(genome_, 1, &b1));
+            tCall[2] += now() - tc;
             tAbi += now() - tMark;
             tMark = now();
             for (unsigned i = 0; i < n; i++) {
@@ -318,6 +322,10 @@ public:
             tReplay += now() - tMark;
         }
         report("paired", tDrain, tAbi, tReplay, nReads);
+        if (getenv("SNAPB200_SHIM_TIMING") != NULL)
+            fprintf(stderr, "[snapb200 shim]   C ABI split: transcriptome multi-hit x2 %.2f s, paired %.2f s, CharacterizeSeeds x2 %.2f s, host buffers %.2f s\n",
+                    tCall[0], tCall[1], tCall[2], tAbi - tCall[0] - tCall[1] - tCall[2]);
+        (void)tAlloc;
         snapb200_stats st;
         if (snapb200_stats_get(genome_, &st) == SNAPB200_OK) ctx->stats->lvCalls = st.n_locations_scored;
         delete partial;

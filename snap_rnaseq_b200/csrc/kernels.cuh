@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) paired_kernel
     sc.lane_table = a.lane_tables + (size_t)slot * lane_table_cells((int)a.cfg.lane_k) * 32;
     sc.order = a.order + (size_t)slot * a.cfg.cand_cap;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
+    if (lane < 5) sm->acc[lane] = 0;  // the run counters are summed per warp and flushed once (five global atomics per pair otherwise)
+    __syncwarp();
     #pragma unroll 1
     for (;;) {
         const uint32_t p = fetch_work(&a.ctr->work);
@@ -221,11 +223,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) paired_kernel
                 if (rc == 1) {
                     r->n_lv_calls = sm->n_lv;
                     r->n_lookups = sm->n_look[0] + sm->n_look[1];
-                    atomicAdd(a.stats + 8, (unsigned long long)r->n_lookups);
-                    atomicAdd(a.stats + 9, (unsigned long long)sm->n_lv);
-                    atomicAdd(a.stats + 10, (unsigned long long)(sm->popular[0] + sm->popular[1]));
-                    atomicAdd(a.stats + 12, (unsigned long long)sm->n_probes);
-                    atomicAdd(a.stats + 13, (unsigned long long)sm->n_hit_words);
+                    sm->acc[0] += r->n_lookups; sm->acc[1] += sm->n_lv; sm->acc[2] += sm->popular[0] + sm->popular[1];
+                    sm->acc[3] += sm->n_probes; sm->acc[4] += sm->n_hit_words;
                 }
                 r->from_align_together = 1;
                 r->aligned_as_pair = 1;
@@ -240,6 +239,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) paired_kernel
             }
         }
         __syncwarp();
+    }
+    __syncwarp();
+    if (lane < 5 && sm->acc[lane]) {
+        // words 8, 9, 10, 12, 13: n_hash_table_lookups, n_locations_scored, n_hits_ignored_popularity, n_table_probes, n_hit_words_read
+        atomicAdd(a.stats + (lane < 3 ? 8 + lane : 9 + lane), sm->acc[lane]);
     }
 }
 
@@ -303,27 +307,40 @@ __global__ void merge_fallback_kernel(const uint32_t *fallback_list, uint32_t n_
     if (e == 0) { r->from_align_together = 0; r->aligned_as_pair = 0; }
 }
 
-// status / mapq histogram of the final records (one thread per read)
+// status / mapq histogram of the final records (one thread per read).  Counted in shared memory per block and flushed with
+// one global atomic per non-zero counter: a global atomic per read on the same handful of addresses took 3 ms per million
+// pairs (ncu launch list), 4 % of a step.
+__device__ __forceinline__ void stats_count(unsigned int *blk, bool valid, uint8_t st, int mapq, bool as_pair)
+{
+    if (valid) {
+        atomicAdd(&blk[0], 1u);
+        atomicAdd(&blk[st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4], 1u);
+        if (as_pair) atomicAdd(&blk[6], 1u);
+        if (st != SNAPB200_NOT_FOUND && mapq >= 0 && mapq <= 70) atomicAdd(&blk[14 + mapq], 1u);
+    }
+}
 __global__ void stats_single_kernel(const snapb200_single_result *r, uint32_t n, unsigned long long *stats)
 {
+    __shared__ unsigned int blk[SNAPB200_STATS_WORDS];
+    for (int i = threadIdx.x; i < SNAPB200_STATS_WORDS; i += blockDim.x) blk[i] = 0;
+    __syncthreads();
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    uint8_t st = r[t].status;
-    atomicAdd(stats + 0, 1ull);
-    atomicAdd(stats + (st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4), 1ull);
-    if (st != SNAPB200_NOT_FOUND) { int q = r[t].mapq; if (q >= 0 && q <= 70) atomicAdd(stats + 14 + q, 1ull); }
+    const bool valid = t < n;
+    stats_count(blk, valid, valid ? r[t].status : 0, valid ? r[t].mapq : 0, false);
+    __syncthreads();
+    for (int i = threadIdx.x; i < SNAPB200_STATS_WORDS; i += blockDim.x) if (blk[i]) atomicAdd(stats + i, (unsigned long long)blk[i]);
 }
 __global__ void stats_paired_kernel(const snapb200_paired_result *r, uint32_t n, unsigned long long *stats)
 {
+    __shared__ unsigned int blk[SNAPB200_STATS_WORDS];
+    for (int i = threadIdx.x; i < SNAPB200_STATS_WORDS; i += blockDim.x) blk[i] = 0;
+    __syncthreads();
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n) return;
-    const snapb200_paired_result &p = r[t >> 1];
-    int e = t & 1;
-    uint8_t st = p.status[e];
-    atomicAdd(stats + 0, 1ull);
-    atomicAdd(stats + (st == SNAPB200_SINGLE_HIT ? 2 : st == SNAPB200_MULTIPLE_HITS ? 3 : 4), 1ull);
-    if (p.aligned_as_pair) atomicAdd(stats + 6, 1ull);
-    if (st != SNAPB200_NOT_FOUND) { int q = p.mapq[e]; if (q >= 0 && q <= 70) atomicAdd(stats + 14 + q, 1ull); }
+    const bool valid = t < 2 * n;
+    const int e = t & 1;
+    stats_count(blk, valid, valid ? r[t >> 1].status[e] : 0, valid ? r[t >> 1].mapq[e] : 0, valid && r[t >> 1].aligned_as_pair);
+    __syncthreads();
+    for (int i = threadIdx.x; i < SNAPB200_STATS_WORDS; i += blockDim.x) if (blk[i]) atomicAdd(stats + i, (unsigned long long)blk[i]);
 }
 
 // ---- CIGAR against the resident genome (SAM.cpp:1159-1189) ---------------------------------------------------

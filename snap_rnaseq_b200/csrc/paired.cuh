@@ -105,6 +105,7 @@ struct PairedSm {
     uint32_t n_sched_w[2];
     uint32_t total_hits[2][2], popular[2], n_look[2];
     uint32_t list_pos[32];   // counting sort of the candidates by score list (phase 2 -> 3)
+    unsigned long long acc[5];  // this warp's share of the run counters (lookups, locations scored, popular seeds, table probes, hit words)
     uint32_t ring_loc[32];   // phase 2: location and bestPossibleScore of the newest 32 mates (entry i at i & 31)
     uint32_t ring_bp[32];
     // phase 3 exchange

@@ -334,6 +334,70 @@ __device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm 
     sm->n_look[w] = n_sched;
 }
 
+// Lane mode for the candidates of phase 3: lane i scores candidate batch_ids[i] with the current limit, then the mates those
+// candidates will ask about are scored ahead (see phase 3).  Out of line: ordinary pairs never come here, and keeping this
+// out of the main body makes their path through the kernel 10 % faster (instruction cache).
+// (arguments by value: a reference to the kernel's configuration or scratch descriptor would force them onto the stack)
+__device__ __noinline__ void lane_batch_candidates(int ix_slot, int lane_k, uint32_t min_spacing, uint32_t max_spacing, Cand *cands, Mate *mates,
+                                                   uint32_t mate_cap, int16_t *lane_table, PairedSm *sm, const ReadView vf, const ReadView vm,
+                                                   int fewer, uint32_t n_batch, int16_t *L)
+{
+    const int lane = lane_id();
+    const int more = 1 - fewer;
+    PROF(long long t_x = clock64();)
+    // lane mode: lane i scores candidate batch_ids[i] with K = current limit
+    PROF(long long t_y = clock64();)
+    const int K = (int)sm->score_limit;
+    bool act_l = (uint32_t)lane < n_batch;
+    Cand *cl = act_l ? &cands[sm->batch_ids[lane]] : nullptr;
+    int s = SC_NONE, off = 0;
+    double pr = 0;
+    const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
+    score_location_lane(ix_slot, vf, dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, lane_k, L + lane, lane_table + lane, act_l, &s, &pr, &off);
+    if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
+    __syncwarp();
+    PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
+    // Mate look-ahead: a candidate whose fewer end scored s will ask its mates for a score with limit <= K - s.
+    // Each lane walks the mates of its own candidate and, per round, one still-unknown mate per lane is scored.
+    {
+        PROF(long long t_m = clock64();)
+        bool walking = act_l && s >= 0;
+        const int Km = K - (s > 0 ? s : 0);
+        const uint32_t spl = act_l ? cl->set_pair : 0;
+        const int dml = more == 0 ? (int)spl : 1 - (int)spl;
+        const uint32_t cloc = act_l ? cl->loc : 0;
+        uint32_t j = act_l ? cl->mate_index : 0;
+        Mate *mbase = (mates + (size_t)spl * mate_cap);
+        uint32_t n_done = 0;
+        #pragma unroll 1
+        for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
+            Mate *mt = nullptr;
+            #pragma unroll 1
+            while (walking) {
+                Mate *q = &mbase[j];
+                const bool needs = !is_within(q->loc, cloc, min_spacing) && q->best_possible <= (uint32_t)Km &&
+                                   (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < (uint32_t)Km)) &&
+                                   !mate_known(q, (uint32_t)Km);
+                if (j == 0 || !is_within(mbase[j - 1].loc, cloc, max_spacing)) walking = false; else j--;
+                if (needs) { mt = q; break; }
+            }
+            if (!__any_sync(FULL_MASK, mt != nullptr)) break;
+            // the same mate may be wanted by several candidates of the batch: one lane scores it, with the largest limit
+            const unsigned peers = __match_any_sync(FULL_MASK, (unsigned long long)mt);
+            const int gmax = __reduce_max_sync(peers, Km);
+            const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
+            int s2 = SC_NONE, off2 = 0;
+            double pr2 = 0;
+            score_location_lane(ix_slot, vm, dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, lane_k, L + lane, lane_table + lane, mine,
+                                &s2, &pr2, &off2);
+            if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
+            n_done += __popc(__ballot_sync(FULL_MASK, mine));
+            __syncwarp();
+        }
+        PROF(if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; })
+    }
+}
+
 // IntersectingPairedEndAligner::align.  All lanes.  v[0], v[1]: both mates staged (len set, Ns and non-ACGT bases
 // counted by the caller: total_ns, n_bad[2]).
 // Returns 0 = returned early leaving the result untouched, 1 = produced a result, 2 = scratch tier overflow.
@@ -784,59 +848,8 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             n_batch = (uint32_t)__popc(m);
             __syncwarp();
         }
-        if (n_batch >= LANE_MIN_BATCH) {
-            // lane mode: lane i scores candidate batch_ids[i] with K = current limit
-            PROF(long long t_y = clock64();)
-            const int K = (int)sm->score_limit;
-            bool act_l = (uint32_t)lane < n_batch;
-            Cand *cl = act_l ? &sc.cands[sm->batch_ids[lane]] : nullptr;
-            int s = SC_NONE, off = 0;
-            double pr = 0;
-            const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
-            score_location_lane(ix_slot, view(fewer), dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
-            if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
-            __syncwarp();
-            PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
-            // Mate look-ahead: a candidate whose fewer end scored s will ask its mates for a score with limit <= K - s.
-            // Each lane walks the mates of its own candidate and, per round, one still-unknown mate per lane is scored.
-            {
-                PROF(long long t_m = clock64();)
-                bool walking = act_l && s >= 0;
-                const int Km = K - (s > 0 ? s : 0);
-                const uint32_t spl = act_l ? cl->set_pair : 0;
-                const int dml = more == 0 ? (int)spl : 1 - (int)spl;
-                const uint32_t cloc = act_l ? cl->loc : 0;
-                uint32_t j = act_l ? cl->mate_index : 0;
-                Mate *mbase = sc.mates_of(spl);
-                uint32_t n_done = 0;
-                #pragma unroll 1
-                for (int round = 0; round < MATE_LOOKAHEAD_ROUNDS; round++) {
-                    Mate *mt = nullptr;
-                    #pragma unroll 1
-                    while (walking) {
-                        Mate *q = &mbase[j];
-                        const bool needs = !is_within(q->loc, cloc, min_spacing) && q->best_possible <= (uint32_t)Km &&
-                                           (q->score == (uint32_t)-2 || (q->score == (uint32_t)-1 && q->score_limit < (uint32_t)Km)) &&
-                                           !mate_known(q, (uint32_t)Km);
-                        if (j == 0 || !is_within(mbase[j - 1].loc, cloc, max_spacing)) walking = false; else j--;
-                        if (needs) { mt = q; break; }
-                    }
-                    if (!__any_sync(FULL_MASK, mt != nullptr)) break;
-                    // the same mate may be wanted by several candidates of the batch: one lane scores it, with the largest limit
-                    const unsigned peers = __match_any_sync(FULL_MASK, (unsigned long long)mt);
-                    const int gmax = __reduce_max_sync(peers, Km);
-                    const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
-                    int s2 = SC_NONE, off2 = 0;
-                    double pr2 = 0;
-                    score_location_lane(ix_slot, view(more), dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, (int)cfg.lane_k, L + lane, sc.lane_table + lane, mine,
-                                        &s2, &pr2, &off2);
-                    if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
-                    n_done += __popc(__ballot_sync(FULL_MASK, mine));
-                    __syncwarp();
-                }
-                PROF(if (lane == 0 && n_done) { sm->t_phase[5] += clock64() - t_m; sm->t_phase[6] += 1; sm->t_phase[7] += n_done; })
-            }
-        }
+        if (n_batch >= LANE_MIN_BATCH)
+            lane_batch_candidates(ix_slot, (int)cfg.lane_k, min_spacing, max_spacing, sc.cands, sc.mates, sc.mate_cap, sc.lane_table, sm, view(fewer), view(more), fewer, n_batch, L);
         if (lane == 0) sm->act2 = sc.cands[sm->ci].c_score == SC_NONE;
         __syncwarp();
         if (sm->act2) {  // warp mode for this one candidate (small batch, large limit, or a window at the genome's edge)

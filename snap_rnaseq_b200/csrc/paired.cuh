@@ -244,8 +244,11 @@ __device__ __forceinline__ bool hs_next_lower(LaneLookup &l, uint32_t *most_rece
 __device__ __forceinline__ uint32_t hs_best_possible(const LaneLookup &l, uint32_t exh_mine, uint32_t max_exh, uint32_t most_recent,
                                                      uint32_t merge_dist)
 {
+    // isWithin(hit, target, mergeDist) for the current hit and the one before it.  The walk is strictly descending and
+    // most_recent is the maximum over the lanes' current hits, so cur_val <= target < prev_val always: each test is one
+    // subtraction and one compare (no wrap-around: locations + MAX_K stay below 2^32, checked when the index is made).
     const uint32_t target = most_recent + l.so;
-    const bool close = ((l.cur != l.nh) & is_within(l.cur_val, target, merge_dist)) | ((l.cur != 0) & is_within(l.prev_val, target, merge_dist));
+    const bool close = ((l.cur != l.nh) & (target - l.cur_val <= merge_dist)) | ((l.cur != 0) & (l.prev_val - target <= merge_dist));
     const bool miss = l.act & !close;
     // misses per disjoint hit set: lanes of the same set that missed find each other with one match
     const unsigned peers = __match_any_sync(FULL_MASK, miss ? l.sid : 0xffffffffu);

@@ -173,6 +173,7 @@ static int make_index(int device, uint32_t seed_len, uint32_t padding, uint32_t 
                       uint32_t n_bases, const uint32_t *piece_offsets, uint32_t n_pieces, snapb200_index **out,
                       void *adopt_tables = nullptr, void *adopt_overflow = nullptr)
 {
+    if (n_bases > 0xffffff00u) return set_error(SNAPB200_ERR_ARG, "genome of %u bases: locations must stay 256 below 2^32 (the reference stops at 0xfffffff0, GenomeIndex.cpp:372)", n_bases);
     // adopt_*: device allocations (from the device-side builder) to take over instead of uploading host copies
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)

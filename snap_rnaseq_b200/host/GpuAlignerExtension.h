@@ -242,7 +242,7 @@ public:
         std::vector<uint8_t> rc0, rc1;
         Read *read0, *read1;
         bool more = true;
-        double tDrain = 0, tAbi = 0, tReplay = 0, tMark, tCall[3] = {0, 0, 0}, tAlloc = 0;
+        double tDrain = 0, tAbi = 0, tReplay = 0, tMark, tCall[3] = {0, 0, 0};
         unsigned long nReads = 0;
         while (more) {
             s0.clear(); s1.clear();
@@ -325,7 +325,6 @@ public:
         if (getenv("SNAPB200_SHIM_TIMING") != NULL)
             fprintf(stderr, "[snapb200 shim]   C ABI split: transcriptome multi-hit x2 %.2f s, paired %.2f s, CharacterizeSeeds x2 %.2f s, host buffers %.2f s\n",
                     tCall[0], tCall[1], tCall[2], tAbi - tCall[0] - tCall[1] - tCall[2]);
-        (void)tAlloc;
         snapb200_stats st;
         if (snapb200_stats_get(genome_, &st) == SNAPB200_OK) ctx->stats->lvCalls = st.n_locations_scored;
         delete partial;

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) paired_kernel
     sc.lane_table = a.lane_tables + (size_t)slot * lane_table_cells((int)a.cfg.lane_k) * 32;
     sc.order = a.order + (size_t)slot * a.cfg.cand_cap;
     MapqFixList fix = {a.fix, &a.ctr->n_fix, a.fix_cap};
+    if (lane < 2) sm->sc_key[lane] = 0xffffffffu;  // no cached seed schedule yet
     if (lane < 5) sm->acc[lane] = 0;  // the run counters are summed per warp and flushed once (five global atomics per pair otherwise)
     __syncwarp();
     #pragma unroll 1

@@ -105,6 +105,11 @@ struct PairedSm {
     uint32_t n_sched_w[2];
     uint32_t total_hits[2][2], popular[2], n_look[2];
     uint32_t list_pos[32];   // counting sort of the candidates by score list (phase 2 -> 3)
+    // The seed schedule of a read without non-ACGT bases depends only on its length (and the seed count), and the reads of a
+    // batch mostly share one length: the last schedule computed is kept and reused (sc_key = length | seeds << 16).
+    uint32_t sc_key[2], sc_n[2], sched_cached[2];  // one cache per mate slot
+    uint16_t sc_off[2][MAX_LOOKUPS / 2];
+    uint8_t sc_wrap[2][MAX_LOOKUPS / 2];
     unsigned long long acc[5];  // this warp's share of the run counters (lookups, locations scored, popular seeds, table probes, hit words)
     uint32_t ring_loc[32];   // phase 2: location and bestPossibleScore of the newest 32 mates (entry i at i & 31)
     uint32_t ring_bp[32];
@@ -295,19 +300,19 @@ __device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, i
 
 // leader: HashTableHitSet::recordLookup for the lookups of mate w in schedule order (:859-899); results at slot0..
 __device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits,
-                                                   const uint32_t *overflow)
-{
+                                                   const uint32_t *overflow, const uint16_t *sched_off, const uint8_t *sched_wrap)
+{   // sched_off / sched_wrap: this mate's schedule, entry jj (the shared cache or p1's arrays at slot0)
     uint32_t begins = 3;  // bit d: the next lookup of direction d starts a new disjoint hit set
     uint32_t prev_wrap = 0;
     const uint32_t n_sched = sm->n_sched_w[w];
     #pragma unroll 1
     for (uint32_t jj = 0; jj < n_sched; jj++) {
         const uint32_t j = slot0 + jj;
-        if (p1->sched_wrap[j] != prev_wrap) { begins = 3; prev_wrap = p1->sched_wrap[j]; }
+        if (sched_wrap[jj] != prev_wrap) { begins = 3; prev_wrap = sched_wrap[jj]; }
         #pragma unroll 1
         for (int d = 0; d < 2; d++) {
             uint32_t n = p1->raw_n[d][j];
-            uint32_t offset = d == 0 ? p1->sched_off[j] : rlen - seed_len - p1->sched_off[j];
+            uint32_t offset = d == 0 ? sched_off[jj] : rlen - seed_len - sched_off[jj];
             if (n < max_big_hits) {
                 sm->total_hits[w][d] += n;
                 if (begins >> d & 1) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
@@ -440,11 +445,24 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
     for (int pass = 0; pass < (together ? 1 : 2); pass++) {
         __syncwarp();
         if (lane == 0) {
-            if (together) {
-                schedule_seeds_paired(sm, p1, 0, 0, view(0).D(0), rlen0, seed_len, max_seeds, n_bad0 == 0);
-                schedule_seeds_paired(sm, p1, 1, MAX_LOOKUPS / 2, view(1).D(0), rlen1, seed_len, max_seeds, n_bad1 == 0);
-            } else {
-                schedule_seeds_paired(sm, p1, pass, 0, view(pass).D(0), pass ? rlen1 : rlen0, seed_len, max_seeds, (pass ? n_bad1 : n_bad0) == 0);
+            #pragma unroll 1
+            for (int q = together ? 0 : pass; q <= (together ? 1 : pass); q++) {
+                const uint32_t len_q = q ? rlen1 : rlen0, slot0 = together ? (uint32_t)q * (MAX_LOOKUPS / 2) : 0u;
+                const bool plain = (q ? n_bad1 : n_bad0) == 0;  // no base that could invalidate a seed
+                const uint32_t key = len_q | max_seeds << 16;
+                const bool cacheable = plain && max_seeds <= MAX_LOOKUPS / 2;
+                if (cacheable && sm->sc_key[q] == key) {
+                    sm->n_sched_w[q] = sm->sc_n[q];
+                    sm->sched_cached[q] = 1;
+                } else {
+                    schedule_seeds_paired(sm, p1, q, slot0, view(q).D(0), len_q, seed_len, max_seeds, plain);
+                    sm->sched_cached[q] = 0;
+                    if (cacheable) {
+                        sm->sc_key[q] = key; sm->sc_n[q] = sm->n_sched_w[q];
+                        #pragma unroll 1
+                        for (uint32_t i = 0; i < sm->sc_n[q]; i++) { sm->sc_off[q][i] = p1->sched_off[slot0 + i]; sm->sc_wrap[q][i] = p1->sched_wrap[slot0 + i]; }
+                    }
+                }
             }
         }
         __syncwarp();
@@ -454,7 +472,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             uint64_t sf, sr;
             HitList hl[2];
             uint32_t np = 0;
-            pack_seed(view(w).D(0) + p1->sched_off[lane], seed_len, &sf, &sr);
+            pack_seed(view(w).D(0) + (sm->sched_cached[w] ? sm->sc_off[w][jj] : p1->sched_off[lane]), seed_len, &sf, &sr);
             lookup_seed(ix, sf, sr, hl, &np);
             #pragma unroll 1
             for (int d = 0; d < 2; d++) {
@@ -466,11 +484,12 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
         }
         __syncwarp();
         if (lane == 0) {
-            if (together) {
-                record_lookups_paired(sm, p1, 0, 0, rlen0, seed_len, cfg.max_big_hits, ix.overflow);
-                record_lookups_paired(sm, p1, 1, MAX_LOOKUPS / 2, rlen1, seed_len, cfg.max_big_hits, ix.overflow);
-            } else {
-                record_lookups_paired(sm, p1, pass, 0, pass ? rlen1 : rlen0, seed_len, cfg.max_big_hits, ix.overflow);
+            #pragma unroll 1
+            for (int q = together ? 0 : pass; q <= (together ? 1 : pass); q++) {
+                const uint32_t slot0 = together ? (uint32_t)q * (MAX_LOOKUPS / 2) : 0u;
+                const bool cached = sm->sched_cached[q] != 0;
+                record_lookups_paired(sm, p1, q, slot0, q ? rlen1 : rlen0, seed_len, cfg.max_big_hits, ix.overflow,
+                                      cached ? sm->sc_off[q] : p1->sched_off + slot0, cached ? sm->sc_wrap[q] : p1->sched_wrap + slot0);
             }
         }
     }

@@ -298,50 +298,6 @@ __device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, i
     sm->n_sched_w[w] = n;
 }
 
-// leader: HashTableHitSet::recordLookup for the lookups of mate w in schedule order (:859-899); results at slot0..
-__device__ __noinline__ void record_lookups_paired(PairedSm *sm, const Phase1Sm *p1, int w, uint32_t slot0, uint32_t rlen, uint32_t seed_len, uint32_t max_big_hits,
-                                                   const uint32_t *overflow, const uint16_t *sched_off, const uint8_t *sched_wrap)
-{   // sched_off / sched_wrap: this mate's schedule, entry jj (the shared cache or p1's arrays at slot0)
-    uint32_t begins = 3;  // bit d: the next lookup of direction d starts a new disjoint hit set
-    uint32_t prev_wrap = 0;
-    const uint32_t n_sched = sm->n_sched_w[w];
-    #pragma unroll 1
-    for (uint32_t jj = 0; jj < n_sched; jj++) {
-        const uint32_t j = slot0 + jj;
-        if (sched_wrap[jj] != prev_wrap) { begins = 3; prev_wrap = sched_wrap[jj]; }
-        #pragma unroll 1
-        for (int d = 0; d < 2; d++) {
-            uint32_t n = p1->raw_n[d][j];
-            uint32_t offset = d == 0 ? sched_off[jj] : rlen - seed_len - sched_off[jj];
-            if (n < max_big_hits) {
-                sm->total_hits[w][d] += n;
-                if (begins >> d & 1) { sm->cur_set[w][d]++; sm->exhausted[w][d][sm->cur_set[w][d]] = 0; }
-                begins &= ~(1u << d);
-                if (n == 0) {
-                    sm->exhausted[w][d][sm->cur_set[w][d]]++;
-                } else {
-                    const uint32_t *hp = (const uint32_t *)p1->raw_hits[d][j];
-                    const bool single = n == 1;  // the hit sits in the hash-table entry; raw_last is that hit
-                    if (p1->raw_last[d][j] < offset) {  // trim meaningless hits (:882-884); only at the very start of the genome
-                        n--;
-                        #pragma unroll 1
-                        while (n > 0 && __ldg(&hp[n - 1]) < offset) n--;
-                    }
-                    uint32_t k = sm->n_lookups[w][d]++;
-                    sm->hitref[w][d][k] = single ? p1->raw_last[d][j] : (uint32_t)(hp - overflow);
-                    if (single) sm->inline_mask[w][d] |= 1u << k;
-                    sm->nhits[w][d][k] = n;
-                    sm->seedoff[w][d][k] = (uint16_t)offset;
-                    sm->setid[w][d][k] = (uint8_t)sm->cur_set[w][d];
-                }
-            } else {
-                sm->popular[w]++;
-            }
-        }
-    }
-    sm->n_look[w] = n_sched;
-}
-
 // Lane mode for the candidates of phase 3: lane i scores candidate batch_ids[i] with the current limit, then the mates those
 // candidates will ask about are scored ahead (see phase 3).  Out of line: ordinary pairs never come here, and keeping this
 // out of the main body makes their path through the kernel 10 % faster (instruction cache).
@@ -483,13 +439,64 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
             atomicAdd(&sm->n_probes, np + (hl[0].n > 1) + (hl[1].n > 1));  // table slots + overflow count words
         }
         __syncwarp();
-        if (lane == 0) {
+        // HashTableHitSet::recordLookup for every lookup of this round at once (:859-899).  In the reference this is a loop
+        // over the lookups in schedule order; what it computes per direction -- which lookups start a new disjoint hit set
+        // (the first one that is not too popular after each wrap of the seed schedule), the number of hit-less lookups per set,
+        // the compacted list of lookups that have hits -- are prefix counts, i.e. ballots and popcounts.
+        {
+            const uint32_t slot = (uint32_t)lane;  // = jj, or 16 * mate + jj when both mates share the round
+            const unsigned half = together ? 0xffffu << (16 * w) : FULL_MASK;
+            const bool active = jj < sm->n_sched_w[w];
+            const bool cached = sm->sched_cached[w] != 0;
+            const uint32_t s_off = active ? (cached ? (uint32_t)sm->sc_off[w][jj] : (uint32_t)p1->sched_off[slot]) : 0u;
+            const uint32_t s_wrap = active ? (cached ? (uint32_t)sm->sc_wrap[w][jj] : (uint32_t)p1->sched_wrap[slot]) : 0u;
+            const uint32_t rlen_w = w ? rlen1 : rlen0;
+            const unsigned le = (2u << lane) - 1u, lt = (1u << lane) - 1u;
+            const bool writer = jj == 0;  // one lane per mate publishes the per-set totals
             #pragma unroll 1
-            for (int q = together ? 0 : pass; q <= (together ? 1 : pass); q++) {
-                const uint32_t slot0 = together ? (uint32_t)q * (MAX_LOOKUPS / 2) : 0u;
-                const bool cached = sm->sched_cached[q] != 0;
-                record_lookups_paired(sm, p1, q, slot0, q ? rlen1 : rlen0, seed_len, cfg.max_big_hits, ix.overflow,
-                                      cached ? sm->sc_off[q] : p1->sched_off + slot0, cached ? sm->sc_wrap[q] : p1->sched_wrap + slot0);
+            for (int d = 0; d < 2; d++) {
+                uint32_t n = active ? p1->raw_n[d][slot] : 0u;
+                const bool valid = active && n < cfg.max_big_hits;
+                const unsigned popular_m = __ballot_sync(FULL_MASK, active && !valid) & half;
+                // lookups of the same mate and wrap count that are not too popular: the lowest lane of each group starts a set
+                const unsigned grp = __match_any_sync(FULL_MASK, valid ? (s_wrap | (uint32_t)w << 8) : (0x10000u | (uint32_t)lane));
+                const unsigned starts = __ballot_sync(FULL_MASK, valid && lane == __ffs((int)grp) - 1) & half;
+                const uint32_t set_id = (uint32_t)__popc(starts & le) - 1u;  // meaningful for valid lanes
+                const bool empty = valid && n == 0, has = valid && n > 0;
+                const unsigned has_m = __ballot_sync(FULL_MASK, has) & half;
+                // sum of the hit counts of each mate (decides which mate has fewer hits, :342)
+                const uint32_t sum0 = __reduce_add_sync(FULL_MASK, (valid && w == 0) ? n : 0u), sum1 = __reduce_add_sync(FULL_MASK, (valid && w == 1) ? n : 0u);
+                if (jj < MAX_LOOKUPS / 2 || !together) sm->exhausted[w][d][jj] = 0;
+                __syncwarp();
+                const unsigned eg = __match_any_sync(FULL_MASK, empty ? (set_id | (uint32_t)w << 8) : (0x10000u | (uint32_t)lane));
+                if (empty && lane == __ffs((int)eg) - 1) sm->exhausted[w][d][set_id] = (uint8_t)__popc(eg);
+                const uint32_t offset = d == 0 ? s_off : rlen_w - seed_len - s_off;
+                bool single = false;
+                uint32_t k = 0;
+                if (has) {
+                    const uint32_t *hp = (const uint32_t *)p1->raw_hits[d][slot];
+                    single = n == 1;  // the hit sits in the hash-table entry; raw_last is that hit
+                    if (p1->raw_last[d][slot] < offset) {  // trim meaningless hits (:882-884); only at the very start of the genome
+                        n--;
+                        #pragma unroll 1
+                        while (n > 0 && __ldg(&hp[n - 1]) < offset) n--;
+                    }
+                    k = (uint32_t)__popc(has_m & lt);
+                    sm->hitref[w][d][k] = single ? p1->raw_last[d][slot] : (uint32_t)(hp - ix.overflow);
+                    sm->nhits[w][d][k] = n;
+                    sm->seedoff[w][d][k] = (uint16_t)offset;
+                    sm->setid[w][d][k] = (uint8_t)set_id;
+                }
+                const uint32_t inl0 = __reduce_or_sync(FULL_MASK, (single && w == 0) ? 1u << k : 0u), inl1 = __reduce_or_sync(FULL_MASK, (single && w == 1) ? 1u << k : 0u);
+                if (writer && (together || w == pass)) {
+                    sm->total_hits[w][d] = w ? sum1 : sum0;
+                    sm->cur_set[w][d] = (int8_t)(__popc(starts) - 1);
+                    sm->n_lookups[w][d] = (uint8_t)__popc(has_m);
+                    sm->inline_mask[w][d] = w ? inl1 : inl0;
+                    sm->popular[w] += (uint32_t)__popc(popular_m);
+                    sm->n_look[w] = sm->n_sched_w[w];
+                }
+                __syncwarp();
             }
         }
     }

@@ -171,6 +171,7 @@ __device__ __noinline__ int score_location_warp(int ix_slot, const ReadView v, i
 // interleaved rolling rows (shared) and T its column of the full table (HBM scratch).  Lanes whose genome window is not entirely inside the genome return SC_NONE_LANE and are
 // left to score_location_warp.  All 32 lanes must call this together.
 #define SC_NONE_LANE (-3)
+PROF(__device__ unsigned long long g_prof_lane[4];)  // lane-mode calls, live lanes forward, live lanes backward, lanes that scored
 __device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, int dir, uint32_t loc, uint32_t seed_offset, int K, int kl,
                                     int16_t *R, int16_t *T, bool active, int *score, double *match_prob, int *loc_offset)
 {
@@ -188,6 +189,8 @@ __device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, 
     int dummy, off = 0;
     int s1 = lv_lane<1>(v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, kl, R, T, ix_slot, ok, &p1, &dummy);
     const bool ok2 = ok && s1 != -1;
+    PROF({ const unsigned a = __ballot_sync(FULL_MASK, ok), b = __ballot_sync(FULL_MASK, ok2);
+           if (lane_id() == 0) { atomicAdd(&g_prof_lane[0], 1ull); atomicAdd(&g_prof_lane[1], (unsigned long long)__popc(a)); atomicAdd(&g_prof_lane[2], (unsigned long long)__popc(b)); } })
     int s2 = lv_lane<-1>(v.D(dir) + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q(dir) + (int)seed_offset - 1,
                          K - (s1 > 0 ? s1 : 0), kl, R, T, ix_slot, ok2, &p2, &off);
     if (!ok) return;

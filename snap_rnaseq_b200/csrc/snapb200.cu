@@ -950,6 +950,14 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
         double tot = (double)h[0];
         fprintf(stderr, "[snapb200 prof] paired_kernel grid=%d items=%llu cycles/item=%.0f  phase1 %.1f%%  phase2 %.1f%%  lv %.1f%%  leader3 %.1f%%\n", grid,
                 h[5], h[5] ? tot / h[5] : 0.0, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot);
+#ifdef SNAPB200_PROFILE
+        {
+            unsigned long long g[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+            cudaMemcpyFromSymbol(g, g_prof_lane, sizeof(g));
+            cudaMemcpyToSymbol(g_prof_lane, z, sizeof(z));
+            fprintf(stderr, "[snapb200 prof]   lane-mode calls %llu: live lanes forward %.1f, backward %.1f of 32\n", g[0], g[0] ? (double)g[1] / g[0] : 0.0, g[0] ? (double)g[2] / g[0] : 0.0);
+        }
+#endif
         fprintf(stderr, "[snapb200 prof]   lane mode: %llu batches, %.1f locations/batch, %.0f cycles/batch (%.1f%% of kernel cycles); warp mode: %llu calls, %.0f cycles/call (%.1f%%)\n",
                 h[7], h[7] ? (double)h[8] / h[7] : 0.0, h[7] ? (double)h[6] / h[7] : 0.0, 100 * h[6] / tot, h[10], h[10] ? (double)h[9] / h[10] : 0.0, 100 * h[9] / tot);
     }

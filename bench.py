@@ -54,6 +54,23 @@ def measured_traffic(pairs):
         return None
 
 
+def int_alu_roofline(pairs, kernel_ms, sm_mhz):
+    """The second roof SURVEY.md 8(d) names for this path: integer issue.  Thread-instructions per pair come from the committed
+    ncu capture of the same configuration (smsp__inst_executed.sum x threads per instruction / pairs); the peak is
+    148 SMs x 128 lanes x the SM clock sampled during the run.  None for configurations that were not captured."""
+    if (sum(GENOME_CONTIGS) // 1_000_000, READ_LEN) != (3100, 150):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1s2_traffic.json")) as f:
+            per_pair = float(json.load(f)["thread_instructions_per_pair"])
+    except Exception:
+        return None
+    achieved = per_pair * pairs / (kernel_ms * 1e-3) / 1e12
+    peak = 148 * 128 * float(sm_mhz or 1965.0) * 1e6 / 1e12
+    return {"bound": "int-alu issue", "kernel": "paired_kernel", "achieved": achieved, "peak": peak, "unit": "T thread-instructions/s",
+            "frac": achieved / peak, "source": "profiles/r1s2_traffic.json (ncu --set full capture) x pairs / CUDA-event kernel time"}
+
+
 def workload_config(n_gpus, pairs):
     mbp = sum(GENOME_CONTIGS) // 1_000_000
     tag = "C3: " if (mbp, READ_LEN) == (3100, 150) else "C2: " if (mbp, READ_LEN) == (100, 100) else ""
@@ -283,6 +300,7 @@ def run_ours(args):
                          "peak_source": peak_src, "traffic": measured_traffic(pairs), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "per_pair": {"table_probes": per(12) / pairs, "hit_words": per(13) / pairs, "lv_locations": n_lv / pairs,
                                       "lookups": float(out["n_lookups"].mean())}},
+            "roofline_int_alu": int_alu_roofline(pairs, k_ms, (clocks or {}).get("sm_mhz")),
             "index_build_s": t_index,
             "stats_allreduce": {"total_reads": int(tot[0]), "single_hits": int(tot[2]), "multi_hits": int(tot[3]), "not_found": int(tot[4]),
                                 "aligned_as_pairs": int(tot[6]), "locations_scored": int(tot[9]), "lookups": int(tot[8])},

@@ -2,7 +2,7 @@
 index (3.1 Gbp, built on the device, saved in the reference's file format and loaded by the reference's own loader).
 Prints one JSON line: reads compared and % bit-exact for paired (location, strand, edit distance, MAPQ, status per read),
 single-end, the multi-hit form, CharacterizeSeeds tuples and CIGAR strings.  TEST INFRASTRUCTURE (uses oracle/).
-usage: parity_at_scale.py [pairs] [c3|c2]"""
+usage: parity_at_scale.py [pairs] [c3|c2|c5]      (c5: the stress shape -- 1 Gbp genome, 250 bp reads at 4 % error, -d 20)"""
 import json, os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,8 +13,12 @@ from oracle import oracle as O
 from snap_rnaseq_b200 import synth, _abi as A
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 cfg = sys.argv[2] if len(sys.argv) > 2 else "c3"
+max_k = 15
 if cfg == "c3":
     bench.GENOME_CONTIGS, bench.READ_LEN, bench.ERR_RATE = [25_000_000] * 124, 150, 0.01
+elif cfg == "c5":
+    bench.GENOME_CONTIGS, bench.READ_LEN, bench.ERR_RATE = [25_000_000] * 40, 250, 0.04
+    max_k = 20
 L = S.lib(0)
 contigs = bench.make_genome()
 bases, offs = synth.snap_layout(contigs, 500)
@@ -25,7 +29,7 @@ with tempfile.TemporaryDirectory(dir=bench.scratch_dir(sum(bench.GENOME_CONTIGS)
     d = os.path.join(tmp, "idx")
     L.save_index(h, d)
     hc = ref.load_index(d)
-    pp = A.paired_defaults()
+    pp = A.paired_defaults(max_k=max_k)
     n_same = n_tot = 0
     t_ref = t_gpu = 0.0
     chunk = 1_000_000
@@ -42,7 +46,7 @@ with tempfile.TemporaryDirectory(dir=bench.scratch_dir(sum(bench.GENOME_CONTIGS)
     out["paired"] = {"reads": n_tot, "bit_exact_pct": 100.0 * n_same / n_tot, "gpu_reads_per_s_e2e": n_tot / t_gpu, "reference_reads_per_s": n_tot / t_ref}
     m = min(200_000, b0.n)
     s0 = b0.slice(0, m)
-    ps = A.single_defaults()
+    ps = A.single_defaults(max_k=min(max_k, 20))
     g, w = L.single(h, ps, s0), ref.single(hc, ps, s0)
     ok = np.ones(m, bool)
     for f in ("location", "mapq", "status", "score", "direction", "n_scored", "n_lookups"):

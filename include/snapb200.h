@@ -217,6 +217,66 @@ int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_batch *reads, 
                          const uint8_t *directions, int use_m, char *cigars, uint32_t cigar_stride,
                          int32_t *edit_distance);
 
+/* ---- the I/O edges of the path as batch kernels ---------------------------- */
+
+/* n reads as the reference's readers hand them to the run loops: Read::getId/getIdLength, the UNCLIPPED bases and
+ * qualities (Read::getUnclippedData/getUnclippedQuality/getUnclippedLength, upper-cased as Read::init does,
+ * SNAPLib/Read.h:295-327) and the clipping Read::clip chose (getFrontClippedLength, getDataLength;
+ * SNAPLib/Read.h:357-404).  Read i: bases/quals[offsets[i] .. offsets[i+1]), ids[id_offsets[i] .. id_offsets[i+1]). */
+typedef struct {
+    uint32_t n;
+    const uint32_t *offsets;     /* n+1 */
+    const uint8_t *bases;
+    const uint8_t *quals;
+    const uint16_t *front_clip;  /* n */
+    const uint16_t *clipped_len; /* n */
+    const uint32_t *id_offsets;  /* n+1 */
+    const uint8_t *ids;
+} snapb200_sam_reads;
+
+/* Replaces FASTQReader::getNextRead (SNAPLib/FASTQ.cpp:188-246: four lines per record, CR LF tolerated, the
+ * starting-character table of :253-297) + Read::init (upper-casing) + Read::clip(clipping) for every complete record
+ * of `text` (which must begin at a record start, as after FASTQReader::reinit).  clipping: ReadClippingType
+ * (SNAPLib/Read.h:85: 0 none, 1 front, 2 back, 3 both).  Outputs are the arrays of a snapb200_sam_reads (each of
+ * offsets/id_offsets has max_reads+1 entries; bases, quals and ids must hold n_bytes bytes, which always suffices);
+ * *bytes_consumed = offset of the first byte after the last complete record (what data->advance() has consumed).
+ * The clipped read the aligners take is bases + offsets[i] + front_clip[i], clipped_len[i] bytes.
+ * A blank line or an invalid starting character -- where the reference prints and soft_exit(1)s -- returns
+ * SNAPB200_ERR_ARG with the reference's message in snapb200_last_error(); more than max_reads records or a read
+ * longer than 65535 bases: SNAPB200_ERR_LIMIT. */
+int snapb200_fastq_parse(int device, const uint8_t *text, uint64_t n_bytes, int clipping, uint32_t max_reads,
+                         uint32_t *n_reads, uint64_t *bytes_consumed, uint32_t *offsets, uint8_t *bases, uint8_t *quals,
+                         uint16_t *front_clip, uint16_t *clipped_len, uint32_t *id_offsets, uint8_t *ids);
+
+/* The arguments of ReadWriter::writeRead / the per-end fields of PairedAlignmentResult that SAM output uses
+ * (SNAPLib/Read.h:171, SNAPLib/PairedEndAligner.h:31-56).  skip != 0: emit nothing for this read (a transcriptome
+ * alignment, whose CIGAR needs the GTF: LandauVishkinWithCigar::insertSpliceJunctions stays on the host). */
+typedef struct {
+    uint32_t location;
+    int32_t mapq;
+    uint8_t status;    /* AlignmentResult */
+    uint8_t direction; /* Direction */
+    uint8_t skip;
+    uint8_t pad;
+} snapb200_sam_alignment;
+
+/* Replaces SimpleReadWriter::writeRead / writePair (SNAPLib/ReadWriter.cpp:90-217) over SAMFormat::writeRead
+ * (SNAPLib/SAM.cpp:803-1153: getSAMData, computeCigarString with LandauVishkinWithCigar at k = MAX_K-1, soft clips,
+ * FLAG/RNEXT/PNEXT/TLEN, the /1 /2 QNAME trimming, "\tPG:Z:SNAP\tNM:i:%d") for genome alignments of a batch.
+ * reads1/aln1 == NULL: single-end, line i = read i.  Otherwise pair p yields lines 2p and 2p+1 in the order
+ * writePair writes them (the end with the lower location first; it also gets SAM_FIRST_SEGMENT, as in the
+ * reference).  Lines are concatenated into out (no header); line_offsets has n_lines+1 entries and is always
+ * filled.  out == NULL: only measure.  out_capacity too small: SNAPB200_ERR_ARG (line_offsets is valid, so the
+ * caller knows the size).  read_group: ReaderContext::defaultReadGroup or NULL.  Bytes are identical to the
+ * reference's for reads without auxiliary data (FASTQ input). */
+int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads *reads0, const snapb200_sam_reads *reads1,
+                       const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m,
+                       const char *read_group, char *out, uint64_t out_capacity, uint64_t *line_offsets);
+
+/* CUDA-event times (ms) of the kernels of the last snapb200_fastq_parse / snapb200_sam_batch call made by this thread
+ * (no copies), for the streaming roofline of these two stages. */
+int snapb200_io_last_kernel_ms(float *fastq_ms, float *sam_ms);
+
 /* ---- building blocks exposed for known-answer tests -------------------------------------------------- */
 
 /* LandauVishkin<+1/-1>::computeEditDistance (SNAPLib/LandauVishkin.h:211-455) on explicit strings.

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include <pthread.h>
 #include <map>
 #include <set>
@@ -34,6 +35,11 @@
 #include "mapq.h"
 #include "Tables.h"
 #include "BigAlloc.h"
+#include "FASTQ.h"
+#include "SAM.h"
+#include "FileFormat.h"
+#include "DataReader.h"
+#include "DataWriter.h"
 #undef private
 #undef protected
 
@@ -445,4 +451,99 @@ int ref_characterize_batch(void *h, const snapb200_single_params *p, const snapb
     return rc;
 }
 
+// ---- row f2: the reference's FASTQ reader and SAM writer, driven as the run loops drive them ----------------------------
+
+// FASTQReader::create + getNextRead until the file ends (SNAPLib/FASTQ.cpp:55-69, 188-246) with ReaderContext::clipping as
+// given; every Read is copied out in the layout of snapb200_sam_reads.
+static double g_last_seconds = 0;  // time spent inside the reference's own calls by the last ref_fastq_parse / ref_sam_batch
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+double ref_last_seconds(void) { return g_last_seconds; }
+
+int ref_fastq_parse(const char *path, int clipping, unsigned max_reads, unsigned *n_reads, unsigned *offsets, unsigned char *bases,
+                    unsigned char *quals, unsigned short *front_clip, unsigned short *clipped_len, unsigned *id_offsets, unsigned char *ids)
+{
+    ReaderContext ctx;
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.clipping = (ReadClippingType)clipping;
+    FASTQReader *fq = FASTQReader::create(DataSupplier::Default[false], path, 0, 0, ctx);
+    unsigned n = 0;
+    offsets[0] = 0;
+    id_offsets[0] = 0;
+    Read read;
+    g_last_seconds = 0;
+    for (;;) {
+        double t0 = now_s();
+        bool more = n < max_reads && fq->getNextRead(&read);
+        g_last_seconds += now_s() - t0;
+        if (!more) break;
+        unsigned o = offsets[n], io = id_offsets[n], len = read.getUnclippedLength();
+        memcpy(bases + o, read.getUnclippedData(), len);
+        memcpy(quals + o, read.getUnclippedQuality(), len);
+        memcpy(ids + io, read.getId(), read.getIdLength());
+        front_clip[n] = (unsigned short)read.getFrontClippedLength();
+        clipped_len[n] = (unsigned short)read.getDataLength();
+        offsets[n + 1] = o + len;
+        id_offsets[n + 1] = io + read.getIdLength();
+        n++;
+    }
+    *n_reads = n;
+    delete fq;
+    return 0;
+}
+
+static void make_read(Read *r, const snapb200_sam_reads *b, unsigned i, const char *read_group)
+{
+    unsigned o = b->offsets[i], len = b->offsets[i + 1] - o;
+    r->init((const char *)b->ids + b->id_offsets[i], b->id_offsets[i + 1] - b->id_offsets[i], (const char *)b->bases + o,
+            (const char *)b->quals + o, len);
+    // the state Read::clip leaves (Read.h:357-404)
+    r->data += b->front_clip[i];
+    r->quality += b->front_clip[i];
+    r->frontClippedLength = b->front_clip[i];
+    r->dataLength = b->clipped_len[i];
+    r->setReadGroup(read_group);
+}
+
+// SimpleReadWriter::writeRead / writePair (SNAPLib/ReadWriter.cpp:90-217) through the reference's own ReadWriterSupplier and
+// file DataWriter into `path` (no header).  Reads with skip set are not written.
+int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1, const snapb200_sam_alignment *a0,
+                  const snapb200_sam_alignment *a1, int use_m, const char *read_group, const char *path)
+{
+    GenomeIndex *idx = (GenomeIndex *)h;
+    const Genome *genome = idx->getGenome();
+    DataWriterSupplier *dws = DataWriterSupplier::create(path);
+    ReadWriterSupplier *rws = ReadWriterSupplier::create(FileFormat::SAM[use_m ? 1 : 0], dws, genome, NULL, NULL);
+    ReadWriter *w = rws->getWriter();
+    double t0 = now_s();
+    for (unsigned i = 0; i < r0->n; i++) {
+        Read read0, read1;
+        make_read(&read0, r0, i, read_group);
+        if (!r1) {
+            if (a0[i].skip) continue;
+            w->writeRead(&read0, (AlignmentResult)a0[i].status, a0[i].mapq, a0[i].location, (Direction)a0[i].direction, false, 0);
+        } else {
+            make_read(&read1, r1, i, read_group);
+            PairedAlignmentResult res;
+            memset(&res, 0, sizeof(res));
+            const snapb200_sam_alignment *a[2] = {&a0[i], &a1[i]};
+            for (int e = 0; e < 2; e++) {
+                res.status[e] = (AlignmentResult)a[e]->status;
+                res.location[e] = a[e]->location;
+                res.direction[e] = (Direction)a[e]->direction;
+                res.mapq[e] = a[e]->mapq;
+                res.isTranscriptome[e] = false;
+                res.tlocation[e] = 0;
+            }
+            w->writePair(&read0, &read1, &res);
+        }
+    }
+    w->close();
+    g_last_seconds = now_s() - t0;
+    delete w;
+    rws->close();
+    delete rws;
+    return 0;
+}
+
 } // extern "C"
+

@@ -157,3 +157,70 @@ def p32i(a):
 
 def pf64(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ---- row f2: FASTQ parse / SAM text ---------------------------------------------------------------------------
+class SamReadsStruct(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32), ("offsets", C.POINTER(C.c_uint32)), ("bases", C.POINTER(C.c_uint8)),
+        ("quals", C.POINTER(C.c_uint8)), ("front_clip", C.POINTER(C.c_uint16)), ("clipped_len", C.POINTER(C.c_uint16)),
+        ("id_offsets", C.POINTER(C.c_uint32)), ("ids", C.POINTER(C.c_uint8)),
+    ]
+
+
+SAM_ALIGNMENT = np.dtype([("location", "<u4"), ("mapq", "<i4"), ("status", "u1"), ("direction", "u1"), ("skip", "u1"),
+                          ("pad", "u1")], align=True)
+assert SAM_ALIGNMENT.itemsize == 12
+
+
+def p16u(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint16))
+
+
+class SamReads:
+    """Owns the numpy arrays behind a snapb200_sam_reads: unclipped reads + clipping + ids."""
+
+    def __init__(self, offsets, bases, quals, front_clip, clipped_len, id_offsets, ids):
+        self.offsets = np.ascontiguousarray(offsets, np.uint32)
+        self.n = self.offsets.size - 1
+        pad = lambda a: a if a.size else np.zeros(1, a.dtype)
+        self.bases = pad(np.ascontiguousarray(bases, np.uint8))
+        self.quals = pad(np.ascontiguousarray(quals, np.uint8))
+        self.front_clip = pad(np.ascontiguousarray(front_clip, np.uint16))
+        self.clipped_len = pad(np.ascontiguousarray(clipped_len, np.uint16))
+        self.id_offsets = np.ascontiguousarray(id_offsets, np.uint32)
+        self.ids = pad(np.ascontiguousarray(ids, np.uint8))
+        self.c = SamReadsStruct(self.n, p32u(self.offsets), p8(self.bases), p8(self.quals), p16u(self.front_clip),
+                                p16u(self.clipped_len), p32u(self.id_offsets), p8(self.ids))
+
+    @classmethod
+    def from_lists(cls, ids, seqs, quals, front_clip=None, clipped_len=None):
+        b, off = strings_to_offsets([s.encode() if isinstance(s, str) else s for s in seqs])
+        q, _ = strings_to_offsets([s.encode() if isinstance(s, str) else s for s in quals])
+        i, ioff = strings_to_offsets([s.encode() if isinstance(s, str) else s for s in ids])
+        lens = np.diff(off).astype(np.uint16)
+        fc = np.zeros(len(seqs), np.uint16) if front_clip is None else np.asarray(front_clip, np.uint16)
+        cl = (lens - fc) if clipped_len is None else np.asarray(clipped_len, np.uint16)
+        return cls(off, b[:off[-1]], q[:off[-1]], fc, cl, ioff, i[:ioff[-1]])
+
+    def byref(self):
+        return C.byref(self.c)
+
+    def clipped_batch(self):
+        """The reads as the aligners take them (Read::getData/getQuality/getDataLength)."""
+        lens = self.clipped_len[:self.n].astype(np.uint32)
+        if self.n and not self.front_clip[:self.n].any() and np.array_equal(lens, np.diff(self.offsets)) and self.offsets[0] == 0:
+            return Batch(self.bases[:self.offsets[-1]], self.quals[:self.offsets[-1]], self.offsets)
+        off = np.zeros(self.n + 1, np.uint32)
+        np.cumsum(lens, out=off[1:])
+        src = (self.offsets[:-1] + self.front_clip[:self.n]).astype(np.int64)
+        idx = np.repeat(src - off[:-1].astype(np.int64), lens) + np.arange(int(off[-1]), dtype=np.int64)
+        return Batch(self.bases[idx], self.quals[idx], off)
+
+    def same_as(self, o):
+        n = self.n
+        return (n == o.n and np.array_equal(self.offsets, o.offsets) and np.array_equal(self.id_offsets, o.id_offsets)
+                and np.array_equal(self.bases[:self.offsets[-1]], o.bases[:o.offsets[-1]])
+                and np.array_equal(self.quals[:self.offsets[-1]], o.quals[:o.offsets[-1]])
+                and np.array_equal(self.ids[:self.id_offsets[-1]], o.ids[:o.id_offsets[-1]])
+                and np.array_equal(self.front_clip[:n], o.front_clip[:n]) and np.array_equal(self.clipped_len[:n], o.clipped_len[:n]))

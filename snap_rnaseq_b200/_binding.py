@@ -146,6 +146,102 @@ class BatchLib:
         return _cstrings(out, n, stride), ed[:n]
 
 
+    # -- row f2: FASTQ text -> reads, alignments -> SAM text -------------------------------------------------------
+    def fastq_parse(self, text, clipping=0, max_reads=None, bufs=None):
+        """FASTQReader::getNextRead + Read::clip over every complete record of `text` -> (SamReads, bytes_consumed).
+        The CUDA library and tests/hostsim take the text; the compiled reference (prefix ref_) reads a file through its own
+        FASTQReader, so for it `text` is written to a temporary file first."""
+        if isinstance(text, np.ndarray):  # used as is (e.g. a view of pinned memory)
+            t = np.ascontiguousarray(text, np.uint8)
+            nb = t.size
+            raw = None
+        else:
+            raw = bytes(text)
+            nb = len(raw)
+            t = np.frombuffer(raw, np.uint8) if nb else np.zeros(1, np.uint8)
+        if max_reads is None:
+            max_reads = nb // 8 + 1
+        if bufs is not None:  # preallocated outputs: (offsets, id_offsets, bases, quals, ids, front_clip, clipped_len)
+            off, ioff, bases, quals, ids, fc, cl = bufs
+            max_reads = min(off.size, ioff.size) - 1
+            assert min(bases.size, quals.size, ids.size) >= nb and min(fc.size, cl.size) >= max_reads
+        else:
+            off = np.zeros(max_reads + 1, np.uint32)
+            ioff = np.zeros(max_reads + 1, np.uint32)
+            bases = np.zeros(max(nb, 1), np.uint8)
+            quals = np.zeros(max(nb, 1), np.uint8)
+            ids = np.zeros(max(nb, 1), np.uint8)
+            fc = np.zeros(max_reads, np.uint16)
+            cl = np.zeros(max_reads, np.uint16)
+        n = C.c_uint32(0)
+        used = C.c_uint64(0)
+        tail = [C.byref(n)]
+        if self.prefix == "ref_":
+            import os
+            import tempfile
+            # the reference's reader soft_exits on an incomplete record at the end of a *file*; in a run the next buffer
+            # supplies the rest, so the file it is given here ends with the last complete record
+            pos = np.flatnonzero(t[:nb] == 10)
+            keep = int(pos[len(pos) // 4 * 4 - 1]) + 1 if len(pos) >= 4 else 0
+            with tempfile.NamedTemporaryFile(suffix=".fq", delete=False) as f:
+                f.write(t[:keep].tobytes())
+            try:
+                self._check(self.fn("fastq_parse")(f.name.encode(), C.c_int(clipping), C.c_uint32(max_reads), C.byref(n), A.p32u(off), A.p8(bases),
+                                                   A.p8(quals), A.p16u(fc), A.p16u(cl), A.p32u(ioff), A.p8(ids)), "fastq_parse")
+            finally:
+                os.unlink(f.name)
+            used = None
+        else:
+            args = [A.p8(t), C.c_uint64(nb), C.c_int(clipping), C.c_uint32(max_reads), C.byref(n), C.byref(used), A.p32u(off), A.p8(bases),
+                    A.p8(quals), A.p16u(fc), A.p16u(cl), A.p32u(ioff), A.p8(ids)]
+            if self.device is not None:
+                args.insert(0, C.c_int(self.device))
+            self._check(self.fn("fastq_parse")(*args), "fastq_parse")
+            used = int(used.value)
+        k = int(n.value)
+        return A.SamReads(off[:k + 1], bases[:off[k]], quals[:off[k]], fc[:k], cl[:k], ioff[:k + 1], ids[:ioff[k]]), used
+
+    def sam(self, handle, reads0, reads1, aln0, aln1, use_m=False, read_group=None, out=None):
+        """SimpleReadWriter::writeRead / writePair over SAMFormat::writeRead for a batch -> (SAM bytes, line_offsets).
+        out: a uint8 array to write into with ONE call (returns a view of it); otherwise measure first, then write."""
+        a0 = np.ascontiguousarray(aln0, A.SAM_ALIGNMENT)
+        a1 = np.ascontiguousarray(aln1, A.SAM_ALIGNMENT) if reads1 is not None else None
+        n_lines = reads0.n * (2 if reads1 is not None else 1)
+        rg = read_group.encode() if read_group else None
+        r1 = reads1.byref() if reads1 is not None else None
+        p1 = a1.ctypes.data_as(C.c_void_p) if a1 is not None else None
+        if self.prefix == "ref_":
+            import os
+            import tempfile
+            fd, path = tempfile.mkstemp(suffix=".sam")
+            os.close(fd)
+            try:
+                self._check(self.fn("sam_batch")(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg,
+                                                 path.encode()), "sam_batch")
+                with open(path, "rb") as f:
+                    return f.read(), None
+            finally:
+                os.unlink(path)
+        lo = np.zeros(n_lines + 1, np.uint64)
+        plo = lo.ctypes.data_as(C.POINTER(C.c_uint64))
+        f = self.fn("sam_batch")
+        if out is not None:
+            self._check(f(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg, out.ctypes.data_as(C.c_char_p),
+                          C.c_uint64(out.size), plo), "sam_batch")
+            return out[:int(lo[-1])], lo
+        self._check(f(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg, None, C.c_uint64(0), plo), "sam_batch")
+        total = int(lo[-1])
+        out = np.zeros(max(total, 1), np.uint8)
+        self._check(f(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg, out.ctypes.data_as(C.c_char_p),
+                      C.c_uint64(total), plo), "sam_batch")
+        return out[:total].tobytes(), lo
+
+    def io_last_kernel_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        self.fn("io_last_kernel_ms")(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+
 def _cstrings(buf, n, stride):
     out = []
     raw = buf.tobytes()

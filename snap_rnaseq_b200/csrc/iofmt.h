@@ -1,0 +1,424 @@
+// iofmt.h -- the per-record logic of the two I/O edges as plain functions:
+//   * one FASTQ record: line splitting, starting-character checks, clipping   (FASTQReader::getNextRead,
+//     SNAPLib/FASTQ.cpp:188-246, 253-297; Read::clip, SNAPLib/Read.h:357-404)
+//   * one SAM line: every field of SAMFormat::writeRead except the CIGAR walk  (SNAPLib/SAM.cpp:803-1153,
+//     SimpleReadWriter::writePair, SNAPLib/ReadWriter.cpp:132-217)
+// The kernels of iokernels.cuh call these from device code; tests/hostsim compiles the same header with g++ to check
+// the logic against the compiled reference on a box without a GPU (test infrastructure only -- the library has no
+// host execution path for them).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/snapb200.h"
+
+#ifdef __CUDACC__
+#define SNAP_HD __host__ __device__ __forceinline__
+#else
+#define SNAP_HD static inline
+#endif
+
+// ---- FASTQ ------------------------------------------------------------------------------------------------------
+enum { FQ_OK = 0, FQ_BLANK_LINE = 1, FQ_BAD_START = 2, FQ_TOO_LONG = 3 };
+
+struct FqRecord {
+    uint32_t id_start, id_len;    // Read::getId / getIdLength (the '@' is not part of the id)
+    uint32_t data_start, data_len;  // unclipped
+    uint32_t qual_start;
+    uint16_t front_clip, clipped_len;
+    uint32_t end;                 // first byte after the record (FASTQ.cpp:236: one CR after the LF is skipped too)
+    int error;
+};
+
+// FASTQReader::isValidStartingCharacterForNextLine[(i + 3) % 4][c] (FASTQ.cpp:253-297), i = line within the record
+SNAP_HD bool fq_valid_start(int line, uint8_t c)
+{
+    switch (line) {
+        case 0: return c == '@';
+        case 1: return c == 'A' || c == 'C' || c == 'T' || c == 'G' || c == 'N' || c == 'a' || c == 'c' || c == 't' || c == 'g' || c == 'n';
+        case 2: return c == '+';
+        default: return c >= '!' && c <= '~';
+    }
+}
+
+// Record r of a text whose '\n' positions are nl[] (ascending).  text[n_bytes] must be readable (any value but '\r'
+// keeps the reference's behaviour at the end of its buffer, where a NUL follows).
+SNAP_HD FqRecord fq_record(const uint8_t *text, uint64_t n_bytes, const uint32_t *nl, uint32_t r, int clipping)
+{
+    FqRecord rec;
+    rec.error = FQ_OK;
+    rec.id_start = rec.id_len = rec.data_start = rec.data_len = rec.qual_start = rec.end = 0;
+    rec.front_clip = rec.clipped_len = 0;
+    uint32_t start[4], len[4];
+    for (int i = 0; i < 4; i++) {
+        const uint32_t line = 4 * r + i;
+        uint32_t s = 0;
+        if (line > 0) {
+            s = nl[line - 1] + 1;
+            if (s < n_bytes && text[s] == '\r') s++;  // scan = newLine + (newLine[1] == '\r' ? 2 : 1)
+        }
+        const uint32_t e = nl[line];
+        const uint32_t line_len = e - s;  // e >= s: a CR right after the previous LF cannot be an LF
+        if (line_len == 0) { rec.error = FQ_BLANK_LINE; return rec; }
+        if (!fq_valid_start(i, text[s])) { rec.error = FQ_BAD_START; return rec; }
+        start[i] = s;
+        len[i] = line_len - (text[e - 1] == '\r' ? 1 : 0);
+    }
+    const uint32_t e3 = nl[4 * r + 3];
+    rec.end = e3 + 1;
+    if (rec.end < n_bytes && text[rec.end] == '\r') rec.end++;
+    rec.id_start = start[0] + 1;
+    rec.id_len = len[0] - 1;
+    rec.data_start = start[1];
+    rec.data_len = len[1];
+    rec.qual_start = start[3];  // the quality string is taken to be as long as the data (FASTQ.cpp:241)
+    if (rec.data_len > 65535u) { rec.error = FQ_TOO_LONG; return rec; }
+    // Read::clip (Read.h:357-404); clipping: 0 none, 1 front, 2 back, 3 both.  NoClipping is the state after init().
+    uint32_t data_len = rec.data_len, front = 0;
+    if (clipping != 0) {
+        const uint8_t *q = text + rec.qual_start;
+        if (clipping == 2 || clipping == 3) {
+            while (data_len > 0 && q[data_len - 1] == '#') data_len--;
+        }
+        if (clipping == 1 || clipping == 3) {
+            while (front < data_len && q[front] == '#') front++;
+        }
+        if (data_len - front < 50) {
+            data_len = rec.data_len;
+            front = 0;
+        } else {
+            data_len -= front;
+        }
+    }
+    rec.front_clip = (uint16_t)front;
+    rec.clipped_len = (uint16_t)data_len;
+    return rec;
+}
+
+SNAP_HD uint8_t fq_upper(uint8_t c) { return (c >= 0x61 && c <= 0x7a) ? (uint8_t)(c - 0x20) : c; }  // TO_UPPER_CASE, Tables.cpp:74-81
+
+// ---- SAM --------------------------------------------------------------------------------------------------------
+#define SAMF_MULTI_SEGMENT 0x001
+#define SAMF_ALL_ALIGNED 0x002
+#define SAMF_UNMAPPED 0x004
+#define SAMF_NEXT_UNMAPPED 0x008
+#define SAMF_REVERSE_COMPLEMENT 0x010
+#define SAMF_NEXT_REVERSED 0x020
+#define SAMF_FIRST_SEGMENT 0x040
+#define SAMF_LAST_SEGMENT 0x080
+
+#define SAM_NAME_STAR (-1)   // "*"
+#define SAM_NAME_EQUAL (-2)  // "="
+#define SAM_INVALID_LOC 0xffffffffu
+#define SAM_CIGAR_STRIDE 256  // >= 61 runs of at most 4 characters (k = MAX_K-1 = 30 edits) + NUL
+
+struct SamEnd {          // what getSAMData reads of one Read and its alignment
+    uint32_t full_len;   // getUnclippedLength
+    uint32_t front_clip; // getFrontClippedLength
+    uint32_t clipped_len;  // getDataLength
+    uint32_t location;   // already InvalidGenomeLocation when the status is NotFound (ReadWriter.cpp:103-105, 164-166)
+    int direction;
+    int mapq;
+};
+
+struct SamFields {
+    int flags;
+    int rname;  // piece index, SAM_NAME_STAR
+    uint32_t pos;
+    int mapq;
+    int rnext;  // piece index, SAM_NAME_STAR, SAM_NAME_EQUAL
+    uint32_t pnext;
+    long long tlen;
+    uint32_t clip_before, clip_after;
+    int direction;  // FORWARD for an unmapped read (SAM.cpp:857-863)
+    bool mapped;
+};
+
+// Genome::getPieceAtLocation (Genome.cpp:357-374)
+SNAP_HD int sam_piece_at(const uint32_t *piece_begin, int n_pieces, uint32_t location)
+{
+    int low = 0, high = n_pieces - 1;
+    while (low <= high) {
+        const int mid = (low + high) / 2;
+        if (piece_begin[mid] <= location && (mid == n_pieces - 1 || piece_begin[mid + 1] > location)) return mid;
+        if (piece_begin[mid] <= location) low = mid + 1;
+        else high = mid - 1;
+    }
+    return 0;
+}
+
+// getSAMData (SAM.cpp:803-975) without the byte copies
+SNAP_HD SamFields sam_fields(const uint32_t *piece_begin, int n_pieces, const SamEnd &me, bool has_mate, bool first_in_pair, const SamEnd &mate)
+{
+    SamFields f;
+    f.flags = 0;
+    f.rname = SAM_NAME_STAR;
+    f.pos = 0;
+    f.rnext = SAM_NAME_STAR;
+    f.pnext = 0;
+    f.tlen = 0;
+    f.mapq = me.mapq;
+    f.mapped = me.location != SAM_INVALID_LOC;
+    f.direction = f.mapped ? me.direction : 0;
+    if (f.direction == 1) {
+        f.clip_before = me.full_len - me.clipped_len - me.front_clip;
+        f.clip_after = me.front_clip;
+    } else {
+        f.clip_before = me.front_clip;
+        f.clip_after = me.full_len - me.clipped_len - f.clip_before;
+    }
+    if (f.mapped) {
+        if (f.direction == 1) f.flags |= SAMF_REVERSE_COMPLEMENT;
+        f.rname = sam_piece_at(piece_begin, n_pieces, me.location);
+        f.pos = me.location - piece_begin[f.rname] + 1;
+        f.mapq = f.mapq < 0 ? 0 : (f.mapq > 70 ? 70 : f.mapq);
+    } else {
+        f.flags |= SAMF_UNMAPPED;
+        f.mapq = 0;
+    }
+    if (has_mate) {
+        f.flags |= SAMF_MULTI_SEGMENT;
+        f.flags |= first_in_pair ? SAMF_FIRST_SEGMENT : SAMF_LAST_SEGMENT;
+        if (mate.location != SAM_INVALID_LOC) {
+            f.rnext = sam_piece_at(piece_begin, n_pieces, mate.location);
+            f.pnext = mate.location - piece_begin[f.rnext] + 1;
+            if (mate.direction == 1) f.flags |= SAMF_NEXT_REVERSED;
+            if (!f.mapped) {
+                f.rname = f.rnext;
+                f.rnext = SAM_NAME_EQUAL;
+                f.pos = f.pnext;
+            }
+        } else {
+            f.flags |= SAMF_NEXT_UNMAPPED;
+            f.rnext = SAM_NAME_EQUAL;
+            f.pnext = f.pos;
+        }
+        if (f.mapped && mate.location != SAM_INVALID_LOC) {
+            f.flags |= SAMF_ALL_ALIGNED;
+            // the reference mixes unsigned and _int64 here; the conversions are kept (SAM.cpp:949-962)
+            const long long my_start = (long long)(uint32_t)(me.location - f.clip_before);
+            const long long my_end = (long long)(uint32_t)(me.location + me.clipped_len + f.clip_after);
+            const long long mate_before = (long long)mate.front_clip;
+            const long long mate_after = (long long)(uint32_t)(mate.full_len - mate.clipped_len) - mate_before;
+            const long long mate_start = (long long)mate.location - (mate.direction == 1 ? mate_after : mate_before);
+            const long long mate_end = (long long)(uint32_t)(mate.location + mate.clipped_len) + (mate.direction == 0 ? mate_after : mate_before);
+            if (f.rname == f.rnext) {
+                if (my_start < mate_start) f.tlen = mate_end - my_start;
+                else f.tlen = -(my_end - mate_start);
+            }
+        }
+        if (f.rname >= 0 && f.rname == f.rnext) f.rnext = SAM_NAME_EQUAL;
+    }
+    return f;
+}
+
+// which end of pair p is written first, and the QNAME lengths (SimpleReadWriter::writePair, ReadWriter.cpp:147-168)
+SNAP_HD int sam_pair_first(uint32_t loc0_masked, uint32_t loc1_masked) { return loc0_masked > loc1_masked ? 1 : 0; }
+
+SNAP_HD bool sam_pair_trims_ids(const uint8_t *id0, uint32_t len0, const uint8_t *id1, uint32_t len1)
+{
+    if (len0 == len1 && len0 > 2 && id0[len0 - 2] == '/' && id1[len0 - 2] == '/') {
+        const uint8_t c0 = id0[len0 - 1], c1 = id1[len1 - 1];
+        if ((c0 == '1' || c0 == '2') && (c0 == '1' || c1 == '2') && c0 != c1) return true;  // the reference's condition, as written
+    }
+    return false;
+}
+
+SNAP_HD int sam_digits_u64(unsigned long long v)
+{
+    int n = 1;
+    while (v >= 10) { v /= 10; n++; }
+    return n;
+}
+SNAP_HD int sam_digits_i64(long long v)
+{
+    return v < 0 ? 1 + sam_digits_u64((unsigned long long)(-(v + 1)) + 1ull) : sam_digits_u64((unsigned long long)v);
+}
+SNAP_HD char *sam_put_u64(char *p, unsigned long long v)
+{
+    const int n = sam_digits_u64(v);
+    for (int i = n - 1; i >= 0; i--) { p[i] = (char)('0' + (int)(v % 10)); v /= 10; }
+    return p + n;
+}
+SNAP_HD char *sam_put_i64(char *p, long long v)
+{
+    if (v < 0) { *p++ = '-'; return sam_put_u64(p, (unsigned long long)(-(v + 1)) + 1ull); }
+    return sam_put_u64(p, (unsigned long long)v);
+}
+SNAP_HD uint32_t sam_strlen(const char *s, uint32_t cap)
+{
+    uint32_t n = 0;
+    while (n < cap && s[n]) n++;
+    return n;
+}
+
+struct SamNames {  // piece names in HBM
+    const char *blob;
+    const uint32_t *off;  // [n_pieces + 1]
+};
+SNAP_HD uint32_t sam_name_len(const SamNames &nm, int id) { return id >= 0 ? nm.off[id + 1] - nm.off[id] : 1; }
+SNAP_HD char *sam_put_name(char *p, const SamNames &nm, int id)
+{
+    if (id == SAM_NAME_STAR) { *p++ = '*'; return p; }
+    if (id == SAM_NAME_EQUAL) { *p++ = '='; return p; }
+    const uint32_t n = nm.off[id + 1] - nm.off[id];
+    const char *s = nm.blob + nm.off[id];
+    for (uint32_t i = 0; i < n; i++) p[i] = s[i];
+    return p + n;
+}
+
+struct SamLine {  // what the measuring pass leaves for the writing pass
+    uint32_t qname_len;  // after /1 /2 trimming and truncation at the first space (SAM.cpp:1075-1078)
+    uint32_t seq_len;    // "%.*s" stops at a NUL: COMPLEMENT[] of a byte that is not ACGTNn is 0 (Tables.cpp:22-30)
+    uint32_t qual_len;
+    int32_t edit_distance;  // -1 unmapped / CIGAR "*"
+    uint32_t cigar_len;     // of the LV string, without soft clips; 0 => "*"
+};
+
+// The CIGAR field with soft clips (computeCigarString, SAM.cpp:1206-1222) -- length and bytes
+SNAP_HD uint32_t sam_cigar_field_len(const SamFields &f, const SamLine &ln)
+{
+    if (!f.mapped || ln.cigar_len == 0) return 1;
+    uint32_t n = ln.cigar_len;
+    if (f.clip_before > 0) n += sam_digits_u64(f.clip_before) + 1;
+    if (f.clip_after > 0) n += sam_digits_u64(f.clip_after) + 1;
+    return n;
+}
+
+SNAP_HD uint32_t sam_line_len(const SamFields &f, const SamLine &ln, const SamNames &nm, uint32_t rg_len)
+{
+    uint32_t n = ln.qname_len + 1;
+    n += sam_digits_i64(f.flags) + 1;
+    n += sam_name_len(nm, f.rname) + 1;
+    n += sam_digits_u64(f.pos) + 1;
+    n += sam_digits_i64(f.mapq) + 1;
+    n += sam_cigar_field_len(f, ln) + 1;
+    n += sam_name_len(nm, f.rnext) + 1;
+    n += sam_digits_u64(f.pnext) + 1;
+    n += sam_digits_i64(f.tlen) + 1;
+    n += ln.seq_len + 1;
+    n += ln.qual_len;
+    if (rg_len) n += 6 + rg_len;                         // "\tRG:Z:" + group
+    n += 10;                                             // "\tPG:Z:SNAP"
+    n += 6 + sam_digits_i64(ln.edit_distance) + 1;       // "\tNM:i:%d" + "\n"
+    return n;
+}
+
+// Everything before SEQ; returns the position where SEQ starts.
+SNAP_HD char *sam_put_prefix(char *p, const uint8_t *id, const SamFields &f, const SamLine &ln, const SamNames &nm, const char *cigar)
+{
+    for (uint32_t i = 0; i < ln.qname_len; i++) p[i] = (char)id[i];
+    p += ln.qname_len;
+    *p++ = '\t';
+    p = sam_put_i64(p, f.flags); *p++ = '\t';
+    p = sam_put_name(p, nm, f.rname); *p++ = '\t';
+    p = sam_put_u64(p, f.pos); *p++ = '\t';
+    p = sam_put_i64(p, f.mapq); *p++ = '\t';
+    if (!f.mapped || ln.cigar_len == 0) {
+        *p++ = '*';
+    } else {
+        if (f.clip_before > 0) { p = sam_put_u64(p, f.clip_before); *p++ = 'S'; }
+        for (uint32_t i = 0; i < ln.cigar_len; i++) p[i] = cigar[i];
+        p += ln.cigar_len;
+        if (f.clip_after > 0) { p = sam_put_u64(p, f.clip_after); *p++ = 'S'; }
+    }
+    *p++ = '\t';
+    p = sam_put_name(p, nm, f.rnext); *p++ = '\t';
+    p = sam_put_u64(p, f.pnext); *p++ = '\t';
+    p = sam_put_i64(p, f.tlen); *p++ = '\t';
+    return p;
+}
+
+// SEQ, a tab and QUAL, strided over `nlanes` cooperating callers (SAM.cpp:866-885); p = start of SEQ
+SNAP_HD void sam_put_seq_qual(char *p, const uint8_t *bases, const uint8_t *quals, uint32_t full_len, int direction, const SamLine &ln, uint32_t lane,
+                              uint32_t nlanes)
+{
+    for (uint32_t i = lane; i < ln.seq_len; i += nlanes) {
+        uint8_t c;
+        if (direction == 1) {
+            const uint8_t b = bases[full_len - 1 - i];
+            c = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b == 'N' ? 'N' : b == 'n' ? 'n' : 0;
+        } else {
+            c = bases[i];
+        }
+        p[i] = (char)c;
+    }
+    if (lane == 0) p[ln.seq_len] = '\t';
+    char *q = p + ln.seq_len + 1;
+    for (uint32_t i = lane; i < ln.qual_len; i += nlanes) q[i] = (char)(direction == 1 ? quals[full_len - 1 - i] : quals[i]);
+}
+
+// Everything after QUAL; p = first byte after QUAL; returns the end of the line
+SNAP_HD char *sam_put_suffix(char *p, const SamLine &ln, const char *rg, uint32_t rg_len)
+{
+    if (rg_len) {
+        const char t[6] = {'\t', 'R', 'G', ':', 'Z', ':'};
+        for (int i = 0; i < 6; i++) *p++ = t[i];
+        for (uint32_t i = 0; i < rg_len; i++) *p++ = rg[i];
+    }
+    const char t2[16] = {'\t', 'P', 'G', ':', 'Z', ':', 'S', 'N', 'A', 'P', '\t', 'N', 'M', ':', 'i', ':'};
+    for (int i = 0; i < 16; i++) *p++ = t2[i];
+    p = sam_put_i64(p, ln.edit_distance);
+    *p++ = '\n';
+    return p;
+}
+
+// ---- which read a SAM line is ------------------------------------------------------------------------------------------
+struct SamReadsDev {  // a snapb200_sam_reads (arrays resident where the caller runs)
+    const uint32_t *offsets;
+    const uint8_t *bases, *quals;
+    const uint16_t *front_clip, *clipped_len;
+    const uint32_t *id_offsets;
+    const uint8_t *ids;
+};
+
+struct SamInputs {
+    SamReadsDev rd[2];
+    const snapb200_sam_alignment *aln[2];
+    int paired;
+};
+
+struct SamWho {  // which read a line is, and its mate
+    int e;  // 0/1: which batch
+    uint32_t i;
+    bool has_mate, first_in_pair;
+    SamEnd me, mate;
+    bool skip;
+};
+
+SNAP_HD SamEnd sam_end_of(const SamInputs &a, int e, uint32_t i)
+{
+    const snapb200_sam_alignment al = a.aln[e][i];
+    SamEnd s;
+    s.full_len = a.rd[e].offsets[i + 1] - a.rd[e].offsets[i];
+    s.front_clip = a.rd[e].front_clip[i];
+    s.clipped_len = a.rd[e].clipped_len[i];
+    s.location = al.status == SNAPB200_NOT_FOUND ? SAM_INVALID_LOC : al.location;  // ReadWriter.cpp:103-105, 164-166
+    s.direction = al.direction;
+    s.mapq = al.mapq;
+    return s;
+}
+
+// single-end: line i is read i.  Pairs: lines 2p, 2p+1 are the ends of pair p in the order writePair writes them; the one
+// written first is flagged SAM_FIRST_SEGMENT (ReadWriter.cpp:167-189).
+SNAP_HD SamWho sam_who(const SamInputs &a, uint32_t line)
+{
+    SamWho w;
+    if (!a.paired) {
+        w.e = 0; w.i = line; w.has_mate = false; w.first_in_pair = false;
+        w.me = sam_end_of(a, 0, line);
+        w.mate = w.me;
+        w.skip = a.aln[0][line].skip != 0;
+        return w;
+    }
+    const uint32_t p = line >> 1;
+    const SamEnd e0 = sam_end_of(a, 0, p), e1 = sam_end_of(a, 1, p);
+    const int first = sam_pair_first(e0.location, e1.location);
+    w.first_in_pair = (line & 1) == 0;
+    w.e = w.first_in_pair ? first : 1 - first;
+    w.i = p;
+    w.has_mate = true;
+    w.me = w.e ? e1 : e0;
+    w.mate = w.e ? e0 : e1;
+    w.skip = a.aln[w.e][p].skip != 0;
+    return w;
+}

@@ -1,0 +1,253 @@
+// iokernels.cuh -- the I/O edges of the path as batch kernels: FASTQ text -> read arrays,
+// alignments -> SAM text.  Per-record logic is in iofmt.h (each function cites the reference lines it restates); this
+// file holds the data-parallel parts: newline positions by count + scan + scatter, the byte copies, the CIGAR walk
+// (lv_cigar_warp, the same routine cigar_kernel uses) and the line assembly.  Both stages are streaming kernels: their
+// roof is HBM bandwidth (bytes of text in + bytes of arrays out, or the reverse).
+#pragma once
+#include <cub/cub.cuh>
+
+#include "iofmt.h"
+
+// ---- FASTQ -------------------------------------------------------------------------------------------------------
+#define FQ_THREADS 256
+#define FQ_BYTES_PER_THREAD 64  // four 16-byte loads; the text buffer is padded to a multiple of this
+
+__device__ __forceinline__ uint32_t fq_newline_bits(uint32_t w)
+{  // 0x80 in every byte of w that equals '\n'
+    const uint32_t x = w ^ 0x0a0a0a0au;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
+
+__device__ __forceinline__ int fq_count16(const uint4 v)
+{
+    return __popc(fq_newline_bits(v.x)) + __popc(fq_newline_bits(v.y)) + __popc(fq_newline_bits(v.z)) + __popc(fq_newline_bits(v.w));
+}
+
+// pass A: newlines per block
+__global__ void __launch_bounds__(FQ_THREADS) fq_count_kernel(const uint4 *text, uint64_t n_chunks16, uint32_t *block_counts)
+{
+    typedef cub::BlockReduce<int, FQ_THREADS> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    const uint64_t t = (uint64_t)blockIdx.x * FQ_THREADS + threadIdx.x;
+    int c = 0;
+    #pragma unroll
+    for (int j = 0; j < FQ_BYTES_PER_THREAD / 16; j++) {
+        const uint64_t k = t * (FQ_BYTES_PER_THREAD / 16) + j;
+        if (k < n_chunks16) c += fq_count16(text[k]);
+    }
+    const int total = Reduce(tmp).Sum(c);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)total;
+}
+
+// pass B: positions of the newlines, ascending
+__global__ void __launch_bounds__(FQ_THREADS) fq_positions_kernel(const uint4 *text, uint64_t n_chunks16, const uint32_t *block_base, uint32_t *nl)
+{
+    typedef cub::BlockScan<int, FQ_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const uint64_t t = (uint64_t)blockIdx.x * FQ_THREADS + threadIdx.x;
+    uint4 v[FQ_BYTES_PER_THREAD / 16];
+    int c = 0;
+    #pragma unroll
+    for (int j = 0; j < FQ_BYTES_PER_THREAD / 16; j++) {
+        const uint64_t k = t * (FQ_BYTES_PER_THREAD / 16) + j;
+        v[j] = k < n_chunks16 ? text[k] : make_uint4(0, 0, 0, 0);
+        c += fq_count16(v[j]);
+    }
+    int before;
+    Scan(tmp).ExclusiveSum(c, before);
+    if (c == 0) return;
+    uint32_t o = block_base[blockIdx.x] + (uint32_t)before;
+    const uint32_t byte0 = (uint32_t)(t * FQ_BYTES_PER_THREAD);
+    #pragma unroll
+    for (int j = 0; j < FQ_BYTES_PER_THREAD / 16; j++) {
+        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t bits = fq_newline_bits(w[q]);
+            while (bits) {
+                const int b = __ffs((int)bits) - 1;  // 7, 15, 23 or 31
+                nl[o++] = byte0 + j * 16 + q * 4 + (b >> 3);
+                bits &= bits - 1;
+            }
+        }
+    }
+}
+
+struct FqArgs {
+    const uint8_t *text;
+    uint64_t n_bytes;
+    const uint32_t *nl;
+    uint32_t n_reads;
+    int clipping;
+    FqRecord *rec;
+    uint32_t *data_len, *id_len;  // [n_reads + 1], last entry 0: scanned into offsets / id_offsets
+    uint16_t *front_clip, *clipped_len;
+    unsigned long long *first_error;  // min over records of (record << 8 | code)
+};
+
+__global__ void fq_record_kernel(const FqArgs a)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    const FqRecord rec = fq_record(a.text, a.n_bytes, a.nl, r, a.clipping);
+    a.rec[r] = rec;
+    a.data_len[r] = rec.data_len;
+    a.id_len[r] = rec.id_len;
+    a.front_clip[r] = rec.front_clip;
+    a.clipped_len[r] = rec.clipped_len;
+    if (rec.error) atomicMin(a.first_error, ((unsigned long long)r << 8) | (unsigned)rec.error);
+}
+
+struct FqCopyArgs {
+    const uint8_t *text;
+    uint64_t n_bytes;
+    const FqRecord *rec;
+    uint32_t n_reads;
+    const uint32_t *offsets, *id_offsets;
+    uint8_t *bases, *quals, *ids;
+};
+
+// one warp per record: bases (upper-cased), qualities, id
+__global__ void __launch_bounds__(256) fq_copy_kernel(const FqCopyArgs a)
+{
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (r >= a.n_reads) return;
+    const FqRecord rec = a.rec[r];
+    const uint32_t o = a.offsets[r], io = a.id_offsets[r];
+    const uint8_t *d = a.text + rec.data_start, *q = a.text + rec.qual_start, *id = a.text + rec.id_start;
+    const uint64_t q_room = a.n_bytes - rec.qual_start;  // a quality line shorter than the data at the very end of the text
+    for (uint32_t i = lane; i < rec.data_len; i += 32) {
+        a.bases[o + i] = fq_upper(d[i]);
+        a.quals[o + i] = i < q_room ? q[i] : (uint8_t)0;
+    }
+    for (uint32_t i = lane; i < rec.id_len; i += 32) a.ids[io + i] = id[i];
+}
+
+// ---- SAM ---------------------------------------------------------------------------------------------------------
+struct SamArgs {
+    DevIndex ix;
+    SamNames names;
+    SamInputs in;
+    uint32_t n_lines;
+    int use_m;
+    const char *rg;
+    uint32_t rg_len;
+    uint32_t rl;  // shared-memory row for a staged read
+    char *cigars;  // [n_lines][SAM_CIGAR_STRIDE]
+    SamLine *lines;
+    uint64_t *line_len;  // [n_lines + 1], last 0: scanned into line offsets
+    const uint64_t *line_off;
+    char *out;
+    Counters *ctr;
+};
+
+__host__ __device__ inline size_t sam_warp_shared(uint32_t rl) { return cigar_warp_shared(rl); }
+
+// pass 1: CIGAR + the length of every line.  One warp per line.
+__global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    uint8_t *base = smem + sam_warp_shared(a.rl) * warp;
+    int16_t *L = (int16_t *)base;
+    uint8_t *P = base + lv_shared_bytes();
+    uint8_t *W = P + a.rl;
+    #pragma unroll 1
+    for (;;) {
+        const uint32_t line = fetch_work(&a.ctr->work);
+        if (line >= a.n_lines) break;
+        const SamWho w = sam_who(a.in, line);
+        SamLine ln;
+        ln.qname_len = ln.seq_len = ln.qual_len = ln.cigar_len = 0;
+        ln.edit_distance = -1;
+        if (w.skip) {
+            if (lane == 0) { a.lines[line] = ln; a.line_len[line] = 0; }
+            continue;
+        }
+        const SamReadsDev &rd = a.in.rd[w.e];
+        const uint32_t off = rd.offsets[w.i];
+        const uint8_t *bases = rd.bases + off, *quals = rd.quals + off;
+        const SamFields f = sam_fields(a.ix.piece_begin, (int)a.ix.n_pieces, w.me, w.has_mate, w.first_in_pair, w.mate);
+        // QNAME length: /1 /2 trimming for pairs, then truncation at the first space (ReadWriter.cpp:147-161, SAM.cpp:1075-1078)
+        const uint8_t *id = rd.ids + rd.id_offsets[w.i];
+        uint32_t qn = rd.id_offsets[w.i + 1] - rd.id_offsets[w.i];
+        if (a.in.paired) {
+            const SamReadsDev &r0 = a.in.rd[0], &r1 = a.in.rd[1];
+            const uint32_t l0 = r0.id_offsets[w.i + 1] - r0.id_offsets[w.i], l1 = r1.id_offsets[w.i + 1] - r1.id_offsets[w.i];
+            if (sam_pair_trims_ids(r0.ids + r0.id_offsets[w.i], l0, r1.ids + r1.id_offsets[w.i], l1)) qn -= 2;
+        }
+        uint32_t first_space = qn;
+        #pragma unroll 1
+        for (uint32_t b0 = 0; b0 < qn && first_space == qn; b0 += 32) {
+            const uint32_t i = b0 + lane;
+            const unsigned m = __ballot_sync(FULL_MASK, i < qn && id[i] == ' ');
+            if (m) first_space = b0 + __ffs((int)m) - 1;
+        }
+        ln.qname_len = first_space;
+        // SEQ / QUAL lengths as "%.*s" prints them: up to the first NUL
+        uint32_t seq_len = w.me.full_len, qual_len = w.me.full_len;
+        #pragma unroll 1
+        for (uint32_t b0 = 0; b0 < w.me.full_len; b0 += 32) {
+            const uint32_t i = b0 + lane;
+            bool z = false, zq = false;
+            if (i < w.me.full_len) {
+                const uint8_t b = f.direction == 1 ? bases[w.me.full_len - 1 - i] : bases[i];
+                z = f.direction == 1 ? !(b == 'A' || b == 'C' || b == 'G' || b == 'T' || b == 'N' || b == 'n') : b == 0;
+                zq = (f.direction == 1 ? quals[w.me.full_len - 1 - i] : quals[i]) == 0;
+            }
+            const unsigned m = __ballot_sync(FULL_MASK, z), mq = __ballot_sync(FULL_MASK, zq);
+            if (m && seq_len == w.me.full_len) seq_len = b0 + __ffs((int)m) - 1;
+            if (mq && qual_len == w.me.full_len) qual_len = b0 + __ffs((int)mq) - 1;
+        }
+        ln.seq_len = seq_len;
+        ln.qual_len = qual_len;
+        // CIGAR (computeCigarString, SAM.cpp:1159-1204): the clipped read, reverse-complemented for RC, against the genome
+        char *cig = a.cigars + (size_t)line * SAM_CIGAR_STRIDE;
+        if (f.mapped) {
+            const uint32_t len = w.me.clipped_len, loc = w.me.location;
+            if (lane == 0) cig[0] = 0;
+            __syncwarp();
+            if (substring_ok(a.ix, loc, len)) {
+                const uint8_t *cb = bases + w.me.front_clip;
+                #pragma unroll 1
+                for (uint32_t j = lane; j < len; j += 32) P[j] = f.direction == 1 ? rc_base(cb[len - 1 - j]) : cb[j];
+                stage_window(a.ix, loc, len, W);
+                LvStr s;
+                s.p = P; s.ps = 1; s.plen = (int)len;
+                s.t = W + WIN_SLACK; s.ts = 1; s.tlen = (int)len;
+                s.t_lo = -WIN_SLACK; s.t_hi = (int)len + WIN_SLACK;
+                const int e = lv_cigar_warp(s, MAXK - 1, L, cig, SAM_CIGAR_STRIDE, a.use_m != 0);
+                ln.edit_distance = e;  // -1 / -2: the reference prints "*" and NM:i:-1 / -2 (SAM.cpp:1196-1205)
+                if (e >= 0 && lane == 0) ln.cigar_len = sam_strlen(cig, SAM_CIGAR_STRIDE);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            a.lines[line] = ln;
+            a.line_len[line] = sam_line_len(f, ln, a.names, a.rg_len);
+        }
+    }
+}
+
+// pass 2: the bytes.  One warp per line; the leader writes the short fields, all lanes copy SEQ and QUAL.
+__global__ void __launch_bounds__(256) sam_write_kernel(const SamArgs a)
+{
+    const uint32_t line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (line >= a.n_lines) return;
+    const SamWho w = sam_who(a.in, line);
+    if (w.skip) return;
+    const SamLine ln = a.lines[line];
+    const SamReadsDev &rd = a.in.rd[w.e];
+    const uint32_t off = rd.offsets[w.i];
+    const SamFields f = sam_fields(a.ix.piece_begin, (int)a.ix.n_pieces, w.me, w.has_mate, w.first_in_pair, w.mate);
+    char *dst = a.out + a.line_off[line];
+    const uint32_t total = (uint32_t)(a.line_off[line + 1] - a.line_off[line]);
+    // SEQ starts where the suffix, QUAL and SEQ end: everything after SEQ has a known length
+    uint32_t tail = ln.seq_len + 1 + ln.qual_len + (a.rg_len ? 6 + a.rg_len : 0) + 10 + 6 + sam_digits_i64(ln.edit_distance) + 1;
+    char *seq = dst + (total - tail);
+    if (lane == 0) sam_put_prefix(dst, rd.ids + rd.id_offsets[w.i], f, ln, a.names, a.cigars + (size_t)line * SAM_CIGAR_STRIDE);
+    sam_put_seq_qual(seq, rd.bases + off, rd.quals + off, w.me.full_len, f.direction, ln, lane, 32);
+    if (lane == 1) sam_put_suffix(seq + ln.seq_len + 1 + ln.qual_len, ln, a.rg, a.rg_len);
+}

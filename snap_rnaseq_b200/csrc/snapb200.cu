@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "index_build.cuh"
 #include "characterize.cuh"  // after kernels.cuh: uses DevBatch, Counters, fetch_work
+#include "iokernels.cuh"     // FASTQ / SAM batch kernels (row f2); uses lv_cigar_warp, stage_window
 #include <sys/stat.h>
 
 thread_local char g_last_error[512] = "";
@@ -102,6 +103,8 @@ struct snapb200_index {
     snapb200_index_info info;
     std::vector<void *> allocs;
     std::vector<std::string> piece_names;
+    const char *sam_names_blob = nullptr;     // piece names in HBM, uploaded by the first snapb200_sam_batch call
+    const uint32_t *sam_names_off = nullptr;
     std::vector<uint64_t> table_sizes, table_used;
     cudaStream_t stream = nullptr;
     // scratch shared by the synchronous batch entry points (sessions own theirs)
@@ -1638,3 +1641,5 @@ extern "C" int snapb200_stats_reset(snapb200_index *idx)
     CUDA_TRY(cudaMemset(idx->stats, 0, SNAPB200_STATS_WORDS * 8));
     return 0;
 }
+
+#include "io_api.inl"

@@ -1,0 +1,122 @@
+// io_hostsim.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the per-record logic of the FASTQ / SAM batch kernels
+// (snap_rnaseq_b200/csrc/iofmt.h, the header the device code compiles) on the host, so that `pytest -m "not gpu"` can
+// check it against the compiled reference where there is no GPU.  Nothing in the product loads this; the warp-parallel
+// parts of the kernels (newline scan, QNAME/NUL scans, the CIGAR walk) are replaced by serial loops here, and the CIGAR
+// strings are handed in by the test (from the reference's own LandauVishkinWithCigar).
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../../snap_rnaseq_b200/csrc/iofmt.h"
+
+struct HostsimIndex {
+    const uint32_t *piece_begin;
+    uint32_t n_pieces;
+    const char *names_blob;
+    const uint32_t *names_off;
+    const char *cigars[2];       // [n][stride] per end, for the clipped read at its (masked) location and direction
+    const int32_t *edit_distance[2];  // computeEditDistance's return value; -3: off the genome ("*", NM -1)
+    uint32_t cigar_stride;
+};
+
+extern "C" int hostsim_fastq_parse(const uint8_t *text_in, uint64_t n_bytes, int clipping, uint32_t max_reads, uint32_t *n_reads,
+                                   uint64_t *bytes_consumed, uint32_t *offsets, uint8_t *bases, uint8_t *quals, uint16_t *front_clip,
+                                   uint16_t *clipped_len, uint32_t *id_offsets, uint8_t *ids)
+{
+    std::vector<uint8_t> text(text_in, text_in + n_bytes);
+    text.resize(n_bytes + 65536 + 64, 0);
+    std::vector<uint32_t> nl;
+    for (uint64_t i = 0; i < n_bytes; i++) if (text[i] == '\n') nl.push_back((uint32_t)i);
+    const uint32_t n = (uint32_t)(nl.size() / 4);
+    *n_reads = 0;
+    *bytes_consumed = 0;
+    offsets[0] = id_offsets[0] = 0;
+    if (n > max_reads) return -4;
+    for (uint32_t r = 0; r < n; r++) {
+        const FqRecord rec = fq_record(text.data(), n_bytes, nl.data(), r, clipping);
+        if (rec.error) return rec.error == FQ_TOO_LONG ? -4 : -1;
+        const uint32_t o = offsets[r], io = id_offsets[r];
+        for (uint32_t i = 0; i < rec.data_len; i++) {
+            bases[o + i] = fq_upper(text[rec.data_start + i]);
+            quals[o + i] = text[rec.qual_start + i];
+        }
+        memcpy(ids + io, text.data() + rec.id_start, rec.id_len);
+        offsets[r + 1] = o + rec.data_len;
+        id_offsets[r + 1] = io + rec.id_len;
+        front_clip[r] = rec.front_clip;
+        clipped_len[r] = rec.clipped_len;
+        *bytes_consumed = rec.end;
+    }
+    *n_reads = n;
+    return 0;
+}
+
+static SamReadsDev view(const snapb200_sam_reads *r)
+{
+    SamReadsDev d = {r->offsets, r->bases, r->quals, r->front_clip, r->clipped_len, r->id_offsets, r->ids};
+    return d;
+}
+
+extern "C" int hostsim_sam_batch(const HostsimIndex *ix, const snapb200_sam_reads *reads0, const snapb200_sam_reads *reads1,
+                                 const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m, const char *read_group,
+                                 char *out, uint64_t out_capacity, uint64_t *line_offsets)
+{
+    (void)use_m;
+    SamInputs in;
+    in.paired = reads1 != NULL;
+    in.rd[0] = view(reads0);
+    in.aln[0] = aln0;
+    if (in.paired) { in.rd[1] = view(reads1); in.aln[1] = aln1; }
+    const SamNames names = {ix->names_blob, ix->names_off};
+    const uint32_t rg_len = read_group ? (uint32_t)strlen(read_group) : 0;
+    const uint32_t n_lines = reads0->n * (in.paired ? 2 : 1);
+    uint64_t pos = 0;
+    line_offsets[0] = 0;
+    for (uint32_t line = 0; line < n_lines; line++) {
+        const SamWho w = sam_who(in, line);
+        if (w.skip) { line_offsets[line + 1] = pos; continue; }
+        const SamReadsDev &rd = in.rd[w.e];
+        const uint32_t off = rd.offsets[w.i];
+        const uint8_t *bases = rd.bases + off, *quals = rd.quals + off, *id = rd.ids + rd.id_offsets[w.i];
+        const SamFields f = sam_fields(ix->piece_begin, (int)ix->n_pieces, w.me, w.has_mate, w.first_in_pair, w.mate);
+        SamLine ln;
+        uint32_t qn = rd.id_offsets[w.i + 1] - rd.id_offsets[w.i];
+        if (in.paired) {
+            const SamReadsDev &r0 = in.rd[0], &r1 = in.rd[1];
+            if (sam_pair_trims_ids(r0.ids + r0.id_offsets[w.i], r0.id_offsets[w.i + 1] - r0.id_offsets[w.i], r1.ids + r1.id_offsets[w.i],
+                                   r1.id_offsets[w.i + 1] - r1.id_offsets[w.i]))
+                qn -= 2;
+        }
+        ln.qname_len = qn;
+        for (uint32_t i = 0; i < qn; i++) if (id[i] == ' ') { ln.qname_len = i; break; }
+        ln.seq_len = ln.qual_len = w.me.full_len;
+        for (uint32_t i = 0; i < w.me.full_len; i++) {
+            const uint8_t b = f.direction == 1 ? bases[w.me.full_len - 1 - i] : bases[i];
+            const bool z = f.direction == 1 ? !(b == 'A' || b == 'C' || b == 'G' || b == 'T' || b == 'N' || b == 'n') : b == 0;
+            if (z) { ln.seq_len = i; break; }
+        }
+        for (uint32_t i = 0; i < w.me.full_len; i++) if ((f.direction == 1 ? quals[w.me.full_len - 1 - i] : quals[i]) == 0) { ln.qual_len = i; break; }
+        ln.edit_distance = -1;
+        ln.cigar_len = 0;
+        const char *cig = ix->cigars[w.e] + (size_t)w.i * ix->cigar_stride;
+        if (f.mapped) {
+            const int e = ix->edit_distance[w.e][w.i];
+            if (e != -3) {
+                ln.edit_distance = e;
+                if (e >= 0) ln.cigar_len = sam_strlen(cig, ix->cigar_stride);
+            }
+        }
+        const uint32_t len = sam_line_len(f, ln, names, rg_len);
+        if (out) {
+            if (pos + len > out_capacity) return -1;
+            char *dst = out + pos;
+            char *seq = sam_put_prefix(dst, id, f, ln, names, cig);
+            sam_put_seq_qual(seq, bases, quals, w.me.full_len, f.direction, ln, 0, 1);
+            char *end = sam_put_suffix(seq + ln.seq_len + 1 + ln.qual_len, ln, read_group, rg_len);
+            if ((uint32_t)(end - dst) != len) return -100;  // the measuring pass and the writing pass must agree
+        }
+        pos += len;
+        line_offsets[line + 1] = pos;
+    }
+    return 0;
+}

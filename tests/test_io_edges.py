@@ -1,0 +1,219 @@
+"""FASTQ text -> reads and alignments -> SAM text: snapb200_fastq_parse / snapb200_sam_batch
+against the reference's own FASTQReader and SimpleReadWriter + SAMFormat.
+
+  golden:    tests/golden/io_cases.npz, written by the compiled reference (tests/golden/make_golden_io.py)
+  not gpu:   the compiled reference reproduces the golden file; the per-record logic the kernels compile
+             (snap_rnaseq_b200/csrc/iofmt.h) run on the host by tests/hostsim reproduces it too
+  gpu:       the CUDA path through the C ABI against the golden file, and against the compiled reference on fresh inputs
+             (FASTQ text -> parse -> align -> SAM text on the device, byte for byte)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import io_cases
+from golden.make_golden_io import FASTQ_CASES, SAM_CASES
+from snap_rnaseq_b200 import _abi as A
+from snap_rnaseq_b200 import synth
+from snap_rnaseq_b200._binding import BatchLib
+from tests_genome import small_genome
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="session")
+def io_golden():
+    return np.load(os.path.join(HERE, "golden", "io_cases.npz"))
+
+
+def golden_reads(g, key):
+    return A.SamReads(*[g[f"{key}_{f}"] for f in ("offsets", "bases", "quals", "front_clip", "clipped_len", "id_offsets", "ids")])
+
+
+# ---- the host simulation of the device logic (test infrastructure) ------------------------------------------------------
+class HostsimIndex(C.Structure):
+    _fields_ = [("piece_begin", C.POINTER(C.c_uint32)), ("n_pieces", C.c_uint32), ("names_blob", C.c_char_p),
+                ("names_off", C.POINTER(C.c_uint32)), ("cigars", C.c_void_p * 2), ("edit_distance", C.c_void_p * 2),
+                ("cigar_stride", C.c_uint32)]
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    src = os.path.join(HERE, "hostsim", "io_hostsim.cpp")
+    so = os.path.join(HERE, "hostsim", "libiohostsim.so")
+    hdr = os.path.join(os.path.dirname(HERE), "snap_rnaseq_b200", "csrc", "iofmt.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, src], check=True)
+    return BatchLib(C.CDLL(so), "hostsim_")
+
+
+def hostsim_index(cigars, eds):
+    contigs = small_genome()
+    _, piece_off = synth.snap_layout(contigs, 500)
+    blob, off = A.strings_to_offsets([k.encode() for k in contigs])
+    ix = HostsimIndex()
+    keep = [piece_off, blob, off, cigars, eds, bytes(blob[:off[-1]])]
+    ix.piece_begin = A.p32u(piece_off)
+    ix.n_pieces = len(piece_off)
+    ix.names_blob = keep[-1]
+    ix.names_off = A.p32u(off)
+    for e in range(len(cigars)):
+        ix.cigars[e] = cigars[e].ctypes.data
+        ix.edit_distance[e] = eds[e].ctypes.data
+    ix.cigar_stride = 256
+    return ix, keep
+
+
+def check_fastq_golden(impl, g):
+    for seed, n, rlen, clipping in FASTQ_CASES:
+        text = io_cases.fastq_text(seed, n, rlen)
+        got, used = impl.fastq_parse(text, clipping)
+        want = golden_reads(g, f"fq{clipping}")
+        assert got.n == n and got.same_as(want), f"clipping {clipping}"
+        if used is not None:
+            assert text[used:] == b"@partial record\nACGTACGT\n+\n"
+        lens = np.diff(got.offsets)
+        if clipping in (1, 3):
+            assert (got.front_clip[:n] > 0).any()
+        if clipping in (2, 3):
+            assert (got.front_clip[:n].astype(np.int64) + got.clipped_len[:n] < lens).any()
+        if clipping == 0:
+            assert (got.front_clip[:n] == 0).all() and (got.clipped_len[:n] == lens).all()
+
+
+def sam_lines(text, offsets=None):
+    return text.split(b"\n")
+
+
+def assert_same_sam(want, got, what):
+    if want == got:
+        return
+    w, g = want.split(b"\n"), got.split(b"\n")
+    for i, (a, b) in enumerate(zip(w, g)):
+        if a != b:
+            raise AssertionError(f"{what}: line {i} differs\n  expected {a!r}\n  got      {b!r}")
+    raise AssertionError(f"{what}: {len(w)} lines expected, {len(g)} produced")
+
+
+# ---- not gpu -----------------------------------------------------------------------------------------------------------
+def test_reference_reproduces_io_golden(ref, io_golden, small_index_dir):
+    check_fastq_golden(ref, io_golden)
+    h = ref.load_index(small_index_dir)
+    for k, (seed, n, rlen, paired, use_m) in enumerate(SAM_CASES):
+        reads, aln = io_cases.sam_case(seed, n, rlen, paired)
+        sam, _ = ref.sam(h, reads[0], reads[1] if paired else None, aln[0], aln[1] if paired else None, use_m, "grp1" if k == 1 else None)
+        assert_same_sam(io_golden[f"sam{k}"].tobytes(), sam, f"case {k}")
+
+
+def test_hostsim_fastq(hostsim, io_golden):
+    check_fastq_golden(hostsim, io_golden)
+    # the shapes the reference rejects (FASTQ.cpp:214-223): a blank line, a bad starting character
+    for bad in (b"@a\nACGT\n+\nIIII\n\n@b\nACGT\n+\nIIII\n", b"@a\nACGT\n+\nIIII\n@b\nXCGT\n+\nIIII\n", b"a\nACGT\n+\nIIII\n"):
+        with pytest.raises(RuntimeError):
+            hostsim.fastq_parse(bad, 0)
+    r, used = hostsim.fastq_parse(b"", 0)
+    assert r.n == 0 and used == 0
+
+
+def test_hostsim_sam(hostsim, io_golden):
+    for k, (seed, n, rlen, paired, use_m) in enumerate(SAM_CASES):
+        reads, aln = io_cases.sam_case(seed, n, rlen, paired)
+        ends = 2 if paired else 1
+        cig = [np.ascontiguousarray(io_golden[f"sam{k}_cigar{e}"]) for e in range(ends)]
+        eds = [np.ascontiguousarray(io_golden[f"sam{k}_ed{e}"], np.int32) for e in range(ends)]
+        ix, keep = hostsim_index(cig, eds)
+        sam, lo = hostsim.sam(C.byref(ix), reads[0], reads[1] if paired else None, aln[0], aln[1] if paired else None, use_m,
+                              "grp1" if k == 1 else None)
+        want = io_golden[f"sam{k}"].tobytes()
+        assert_same_sam(want, sam, f"case {k}")
+        assert int(lo[-1]) == len(want) and all(sam[int(o) - 1:int(o)] == b"\n" for o in lo[1:])
+
+
+def test_golden_covers_the_branches(io_golden):
+    """The golden SAM text must contain what the cases were built to produce (so a silent change of the generator shows)."""
+    text = b"".join(io_golden[f"sam{k}"].tobytes() for k in range(len(SAM_CASES)))
+    lines = [ln.split(b"\t") for ln in text.split(b"\n") if ln]
+    flags = {int(f[1]) for f in lines}
+    assert any(f & 0x4 for f in flags) and any(f & 0x8 for f in flags) and any(f & 0x2 for f in flags) and any(f & 0x10 for f in flags)
+    assert any(f[5] == b"*" and not int(f[1]) & 0x4 for f in lines)            # mapped but no CIGAR (NM:i:-1)
+    assert any(b"S" in f[5] for f in lines) and any(f[6] not in (b"=", b"*") for f in lines)
+    assert any(int(f[8]) < 0 for f in lines) and any(int(f[8]) > 0 for f in lines)
+    assert any(len(f[9]) < len(f[10]) for f in lines)                           # SEQ cut at the NUL of COMPLEMENT[]
+    assert any(f[-3].startswith(b"RG:Z:grp1") for f in lines) and any(b" " not in f[0] for f in lines)
+    assert any(f[0].endswith(b"/1") for f in lines) and any(not f[0].endswith((b"/1", b"/2")) for f in lines)
+
+
+# ---- gpu ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def handle(cuda, small_index_dir):
+    h = cuda.load_index(small_index_dir)
+    yield h
+    cuda.close_index(h)
+
+
+@pytest.mark.gpu
+def test_cuda_fastq_golden(cuda, io_golden):
+    check_fastq_golden(cuda, io_golden)
+    for bad in (b"@a\nACGT\n+\nIIII\n\n@b\nACGT\n+\nIIII\n", b"@a\nACGT\n+\nIIII\n@b\nXCGT\n+\nIIII\n", b"a\nACGT\n+\nIIII\n"):
+        with pytest.raises(RuntimeError):
+            cuda.fastq_parse(bad, 0)
+    r, used = cuda.fastq_parse(b"", 0)
+    assert r.n == 0 and used == 0
+    r, used = cuda.fastq_parse(b"@only\nACGT\n+\n", 0)
+    assert r.n == 0 and used == 0
+
+
+@pytest.mark.gpu
+def test_cuda_sam_golden(cuda, handle, io_golden):
+    for k, (seed, n, rlen, paired, use_m) in enumerate(SAM_CASES):
+        reads, aln = io_cases.sam_case(seed, n, rlen, paired)
+        sam, lo = cuda.sam(handle, reads[0], reads[1] if paired else None, aln[0], aln[1] if paired else None, use_m,
+                           "grp1" if k == 1 else None)
+        want = io_golden[f"sam{k}"].tobytes()
+        assert_same_sam(want, sam, f"case {k}")
+        assert int(lo[-1]) == len(want)
+    # skip: nothing is written for the read, the neighbours are unchanged
+    reads, aln = io_cases.sam_case(11, 300, 100, False)
+    full, lo = cuda.sam(handle, reads[0], None, aln[0], None)
+    aln[0]["skip"][::3] = 1
+    part, lo2 = cuda.sam(handle, reads[0], None, aln[0], None)
+    keep = b"".join(full[int(lo[i]):int(lo[i + 1])] for i in range(300) if i % 3)
+    assert part == keep and all(lo2[i] == lo2[i + 1] for i in range(0, 300, 3))
+    # empty batch
+    e = A.SamReads(np.zeros(1, np.uint32), [], [], [], [], np.zeros(1, np.uint32), [])
+    sam, lo = cuda.sam(handle, e, None, np.zeros(0, A.SAM_ALIGNMENT), None)
+    assert sam == b"" and list(lo) == [0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rlen,clipping,seed", [(100, 3, 41), (150, 2, 42), (250, 0, 43)])
+def test_cuda_fastq_to_sam_pipeline(cuda, handle, ref, small_index_dir, rlen, clipping, seed):
+    """FASTQ text of both mates -> snapb200_fastq_parse -> snapb200_paired_batch -> snapb200_sam_batch, against the
+    reference's FASTQReader -> ChimericPairedEndAligner -> SimpleReadWriter::writePair on the same bytes."""
+    hc = ref.load_index(small_index_dir)
+    texts = [io_cases.fastq_text(seed + e, 1500, rlen, crlf_frac=0.05 * e, partial_tail=False) for e in range(2)]
+    got = [cuda.fastq_parse(t, clipping)[0] for t in texts]
+    want = [ref.fastq_parse(t, clipping)[0] for t in texts]
+    assert got[0].same_as(want[0]) and got[1].same_as(want[1])
+    pp = A.paired_defaults(max_k=15 if rlen < 250 else 20)
+    b0, b1 = got[0].clipped_batch(), got[1].clipped_batch()
+    res = cuda.paired(handle, pp, b0, b1)
+    res_ref = ref.paired(hc, pp, b0, b1)
+    aln = []
+    for e in range(2):
+        a = np.zeros(b0.n, A.SAM_ALIGNMENT)
+        for f in ("location", "mapq", "status", "direction"):
+            a[f] = res[f][:, e]
+            assert np.array_equal(res[f][:, e], res_ref[f][:, e])
+        aln.append(a)
+    for use_m in (False, True):
+        sam, _ = cuda.sam(handle, got[0], got[1], aln[0], aln[1], use_m)
+        sam_ref, _ = ref.sam(hc, want[0], want[1], aln[0], aln[1], use_m)
+        assert_same_sam(sam_ref, sam, f"use_m={use_m}")
+    # single-end lines of the same reads
+    sam, _ = cuda.sam(handle, got[1], None, aln[1], None, False, "rg7")
+    sam_ref, _ = ref.sam(hc, want[1], None, aln[1], None, False, "rg7")
+    assert_same_sam(sam_ref, sam, "single")

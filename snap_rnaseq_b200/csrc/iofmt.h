@@ -226,7 +226,9 @@ SNAP_HD bool sam_pair_trims_ids(const uint8_t *id0, uint32_t len0, const uint8_t
 SNAP_HD int sam_digits_u64(unsigned long long v)
 {
     int n = 1;
-    while (v >= 10) { v /= 10; n++; }
+    while (v > 0xffffffffull) { v /= 10; n++; }
+    uint32_t w = (uint32_t)v;  // 64-bit division is a subroutine on the GPU; nearly every field fits 32 bits
+    while (w >= 10) { w /= 10; n++; }
     return n;
 }
 SNAP_HD int sam_digits_i64(long long v)
@@ -236,7 +238,10 @@ SNAP_HD int sam_digits_i64(long long v)
 SNAP_HD char *sam_put_u64(char *p, unsigned long long v)
 {
     const int n = sam_digits_u64(v);
-    for (int i = n - 1; i >= 0; i--) { p[i] = (char)('0' + (int)(v % 10)); v /= 10; }
+    int i = n - 1;
+    for (; v > 0xffffffffull; i--) { p[i] = (char)('0' + (int)(v % 10)); v /= 10; }
+    uint32_t w = (uint32_t)v;
+    for (; i >= 0; i--) { p[i] = (char)('0' + (int)(w % 10)); w /= 10; }
     return p + n;
 }
 SNAP_HD char *sam_put_i64(char *p, long long v)

@@ -105,6 +105,7 @@ struct FqCopyArgs {
     uint32_t n_reads;
     const uint32_t *offsets, *id_offsets;
     uint8_t *bases, *quals, *ids;
+    const unsigned long long *first_error;  // nothing is copied once a record failed (the call returns an error)
 };
 
 // one warp per record: bases (upper-cased), qualities, id
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) fq_copy_kernel(const FqCopyArgs a)
 {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (r >= a.n_reads) return;
+    if (r >= a.n_reads || *a.first_error != ~0ull) return;
     const FqRecord rec = a.rec[r];
     const uint32_t o = a.offsets[r], io = a.id_offsets[r];
     const uint8_t *d = a.text + rec.data_start, *q = a.text + rec.qual_start, *id = a.text + rec.id_start;

@@ -286,6 +286,19 @@ __device__ int lv_cigar_warp(const LvStr &s_in, int k, int16_t *L, char *cigar, 
         straight += __popc(__ballot_sync(FULL_MASK, mism));
     }
     straight += plen - end;
+    // The mismatch-only case walks every base (LandauVishkin.cpp:368-395).  The comparisons are done by the whole warp, 32
+    // positions per ballot, into the L table (dead once e and d are known in this case); the leader then only visits the
+    // positions where match turns into mismatch or back.
+    uint32_t *eq_words = (uint32_t *)L;
+    if (straight == e && !use_m) {
+        #pragma unroll 1
+        for (int base = 0; base < end; base += 32) {
+            const int i = base + lane;
+            const unsigned m = __ballot_sync(FULL_MASK, i < end && lv_pat(s, i) == lv_txt(s, i));
+            if (lane == 0) eq_words[base >> 5] = m;
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
         CigarOut o = {cigar, cigar_len};
         bool ok = true;
@@ -294,14 +307,23 @@ __device__ int lv_cigar_warp(const LvStr &s_in, int k, int16_t *L, char *cigar, 
                 ok = cigar_put(o, plen, 'M');
             } else {
                 int start = 0;
-                bool matching = lv_pat(s, 0) == lv_txt(s, 0);
+                bool matching = (eq_words[0] & 1u) != 0;
                 #pragma unroll 1
-                for (int i = 0; i < end && ok; i++) {
-                    bool m = lv_pat(s, i) == lv_txt(s, i);
-                    if (m != matching) {
+                for (int base = 0; base < end && ok; base += 32) {
+                    const int valid = min(32, end - base);
+                    const uint32_t vmask = valid == 32 ? 0xffffffffu : ((1u << valid) - 1u);
+                    const uint32_t w = eq_words[base >> 5];
+                    uint32_t todo = vmask;  // positions of this word not yet passed
+                    #pragma unroll 1
+                    while (ok) {
+                        const uint32_t x = (matching ? ~w : w) & todo;  // positions whose state differs from the current run's
+                        if (!x) break;
+                        const int j = __ffs((int)x) - 1;
+                        const int i = base + j;
                         ok = cigar_put(o, i - start, matching ? '=' : 'X');
-                        matching = m;
+                        matching = !matching;
                         start = i;
+                        todo = j == 31 ? 0u : (vmask & ~((2u << j) - 1u));
                     }
                 }
                 if (ok && plen > start) {

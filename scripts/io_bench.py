@@ -26,7 +26,7 @@ from snap_rnaseq_b200 import _abi as A, synth  # noqa: E402
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 mbp = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 rlen = int(sys.argv[3]) if len(sys.argv) > 3 else 150
-SAMPLE = 100_000
+SAMPLE = 1_000_000  # pairs the compiled reference re-does for the parity check and its own timing (one thread: a few seconds)
 
 
 def fastq_bytes(batch, mate):

@@ -9,21 +9,27 @@ struct IoScratch {  // device buffers of the calling thread, kept between calls
     DevBuf s_off[2], s_bases[2], s_quals[2], s_front[2], s_clip[2], s_idoff[2], s_ids[2], s_aln[2];
     DevBuf cigars, lines, line_len, line_off, out, rg;
     float fastq_ms = 0, sam_ms = 0;
+    void drop()  // give the device memory back (another device is asked for, or the thread ends)
+    {
+        if (device < 0) return;
+        DevBuf *all[] = {&text, &block_counts, &block_base, &nl, &rec, &data_len, &id_len, &front, &clip, &err, &offsets, &id_offsets, &bases,
+                         &quals, &ids, &cub_tmp, &cigars, &lines, &line_len, &line_off, &out, &rg,
+                         &s_off[0], &s_off[1], &s_bases[0], &s_bases[1], &s_quals[0], &s_quals[1], &s_front[0], &s_front[1],
+                         &s_clip[0], &s_clip[1], &s_idoff[0], &s_idoff[1], &s_ids[0], &s_ids[1], &s_aln[0], &s_aln[1]};
+        if (cudaSetDevice(device) == cudaSuccess) {  // fails harmlessly once the process is tearing the context down
+            for (DevBuf *b : all) b->release();
+            if (stream) cudaStreamDestroy(stream);
+            for (auto &e : ev) if (e) cudaEventDestroy(e);
+        }
+        stream = nullptr;
+        for (auto &e : ev) e = nullptr;
+        device = -1;
+    }
+    ~IoScratch() { drop(); }
     int use(int dev)
     {
         if (device != dev) {
-            DevBuf *all[] = {&text, &block_counts, &block_base, &nl, &rec, &data_len, &id_len, &front, &clip, &err, &offsets, &id_offsets, &bases,
-                             &quals, &ids, &cub_tmp, &cigars, &lines, &line_len, &line_off, &out, &rg,
-                             &s_off[0], &s_off[1], &s_bases[0], &s_bases[1], &s_quals[0], &s_quals[1], &s_front[0], &s_front[1],
-                             &s_clip[0], &s_clip[1], &s_idoff[0], &s_idoff[1], &s_ids[0], &s_ids[1], &s_aln[0], &s_aln[1]};
-            if (device >= 0) {
-                cudaSetDevice(device);
-                for (DevBuf *b : all) b->release();
-                if (stream) cudaStreamDestroy(stream);
-                for (auto &e : ev) if (e) cudaEventDestroy(e);
-                stream = nullptr;
-                for (auto &e : ev) e = nullptr;
-            }
+            drop();
             CUDA_TRY(cudaSetDevice(dev));
             CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
             for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
@@ -284,7 +290,7 @@ extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads 
     if ((rc = io.out.ensure(total + 16))) return rc;
     a.out = io.out.as<char>();
     CUDA_TRY(cudaEventRecord(io.ev[2], io.stream));
-    sam_write_kernel<<<(uint32_t)(((uint64_t)n_lines * 32 + 255) / 256), 256, 0, io.stream>>>(a);
+    sam_write_kernel<<<(uint32_t)(((uint64_t)n_lines * SAM_WRITE_LANES + 255) / 256), 256, 0, io.stream>>>(a);
     CUDA_TRY(cudaEventRecord(io.ev[3], io.stream));
     CUDA_TRY(cudaMemcpyAsync(out, io.out.p, total, cudaMemcpyDeviceToHost, io.stream));
     CUDA_TRY(cudaStreamSynchronize(io.stream));

@@ -108,6 +108,36 @@ struct FqCopyArgs {
     const unsigned long long *first_error;  // nothing is copied once a record failed (the call returns an error)
 };
 
+// n bytes from src to dst by one warp, four at a time: words are stored at dst's alignment and assembled from the two
+// aligned source words that hold them (funnel shift), so neither side needs a particular alignment.  Up to 7 bytes beyond
+// src + n are read (never stored): the text buffer is padded.  UPPER: TO_UPPER_CASE on every byte (Tables.cpp:74-81).
+__device__ __forceinline__ uint32_t fq_upper4(uint32_t v)
+{
+    const uint32_t t = v & 0x7f7f7f7fu;
+    const uint32_t ge = (t + 0x1f1f1f1fu) & 0x80808080u;   // byte >= 0x61
+    const uint32_t le = ~(t + 0x05050505u) & 0x80808080u;  // byte <= 0x7a
+    const uint32_t m = ge & le & ~v & 0x80808080u;          // ... and below 0x80
+    return v - (m >> 2);
+}
+
+template <bool UPPER>
+__device__ __forceinline__ void fq_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
+{
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < head) dst[lane] = UPPER ? fq_upper(src[lane]) : src[lane];
+    const uint32_t nw = (n - head) >> 2;
+    const uint8_t *s = src + head;
+    const uint32_t *sw = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)((uintptr_t)s & 3) * 8;
+    uint32_t *dw = (uint32_t *)(dst + head);
+    for (uint32_t w = lane; w < nw; w += 32) {
+        const uint32_t v = __funnelshift_r(sw[w], sw[w + 1], sh);
+        dw[w] = UPPER ? fq_upper4(v) : v;
+    }
+    const uint32_t done = head + 4 * nw;
+    if (lane < n - done) dst[done + lane] = UPPER ? fq_upper(src[done + lane]) : src[done + lane];
+}
+
 // one warp per record: bases (upper-cased), qualities, id
 __global__ void __launch_bounds__(256) fq_copy_kernel(const FqCopyArgs a)
 {
@@ -116,13 +146,11 @@ __global__ void __launch_bounds__(256) fq_copy_kernel(const FqCopyArgs a)
     if (r >= a.n_reads || *a.first_error != ~0ull) return;
     const FqRecord rec = a.rec[r];
     const uint32_t o = a.offsets[r], io = a.id_offsets[r];
-    const uint8_t *d = a.text + rec.data_start, *q = a.text + rec.qual_start, *id = a.text + rec.id_start;
-    const uint64_t q_room = a.n_bytes - rec.qual_start;  // a quality line shorter than the data at the very end of the text
-    for (uint32_t i = lane; i < rec.data_len; i += 32) {
-        a.bases[o + i] = fq_upper(d[i]);
-        a.quals[o + i] = i < q_room ? q[i] : (uint8_t)0;
-    }
-    for (uint32_t i = lane; i < rec.id_len; i += 32) a.ids[io + i] = id[i];
+    // a quality line shorter than the bases at the very end of the text: the reference reads on (FASTQ.cpp:241); the buffer is
+    // zero-padded for 64 KiB past the text, which is what is copied then
+    fq_copy_bytes<true>(a.bases + o, a.text + rec.data_start, rec.data_len, lane);
+    fq_copy_bytes<false>(a.quals + o, a.text + rec.qual_start, rec.data_len, lane);
+    fq_copy_bytes<false>(a.ids + io, a.text + rec.id_start, rec.id_len, lane);
 }
 
 // ---- SAM ---------------------------------------------------------------------------------------------------------
@@ -231,11 +259,14 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
     }
 }
 
-// pass 2: the bytes.  One warp per line; the leader writes the short fields, all lanes copy SEQ and QUAL.
+// pass 2: the bytes.  Half a warp per line (no warp-wide primitive is used here, and two lines per warp keep twice the loads in
+// flight: the kernel waits on dependent global loads, not on bandwidth); its first lane writes the short fields before SEQ, its
+// second lane the ones after QUAL, all SAM_WRITE_LANES lanes copy SEQ and QUAL.
+#define SAM_WRITE_LANES 16
 __global__ void __launch_bounds__(256) sam_write_kernel(const SamArgs a)
 {
-    const uint32_t line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t line = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / SAM_WRITE_LANES);
+    const uint32_t lane = threadIdx.x % SAM_WRITE_LANES;
     if (line >= a.n_lines) return;
     const SamWho w = sam_who(a.in, line);
     if (w.skip) return;
@@ -249,6 +280,6 @@ __global__ void __launch_bounds__(256) sam_write_kernel(const SamArgs a)
     uint32_t tail = ln.seq_len + 1 + ln.qual_len + (a.rg_len ? 6 + a.rg_len : 0) + 10 + 6 + sam_digits_i64(ln.edit_distance) + 1;
     char *seq = dst + (total - tail);
     if (lane == 0) sam_put_prefix(dst, rd.ids + rd.id_offsets[w.i], f, ln, a.names, a.cigars + (size_t)line * SAM_CIGAR_STRIDE);
-    sam_put_seq_qual(seq, rd.bases + off, rd.quals + off, w.me.full_len, f.direction, ln, lane, 32);
+    sam_put_seq_qual(seq, rd.bases + off, rd.quals + off, w.me.full_len, f.direction, ln, lane, SAM_WRITE_LANES);
     if (lane == 1) sam_put_suffix(seq + ln.seq_len + 1 + ln.qual_len, ln, a.rg, a.rg_len);
 }

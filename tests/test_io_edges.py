@@ -217,3 +217,32 @@ def test_cuda_fastq_to_sam_pipeline(cuda, handle, ref, small_index_dir, rlen, cl
     sam, _ = cuda.sam(handle, got[1], None, aln[1], None, False, "rg7")
     sam_ref, _ = ref.sam(hc, want[1], None, aln[1], None, False, "rg7")
     assert_same_sam(sam_ref, sam, "single")
+
+
+@pytest.mark.gpu
+def test_cuda_io_concurrent_callers(cuda, handle, io_golden):
+    """The reference runs these per worker thread (-t N); every calling thread has its own device buffers and stream."""
+    import threading
+    seed, n, rlen, paired, use_m = SAM_CASES[0]
+    reads, aln = io_cases.sam_case(seed, n, rlen, paired)
+    want_sam = io_golden["sam0"].tobytes()
+    text = io_cases.fastq_text(*FASTQ_CASES[3][:3])
+    want_fq = golden_reads(io_golden, "fq3")
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(5):
+                sam, _ = cuda.sam(handle, reads[0], reads[1], aln[0], aln[1], use_m)
+                assert sam == want_sam
+                got, _ = cuda.fastq_parse(text, 3)
+                assert got.same_as(want_fq)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors

@@ -310,6 +310,11 @@ def run_ours(args):
             line["probe_stage"] = probe_stage(L, h, bases.size)
         except Exception as e:  # diagnostics only
             line["probe_stage"] = {"error": str(e)}
+        if world == 1:
+            try:
+                line["io_edges"] = io_edges_stage(L, h, b0, b1, out)
+            except Exception as e:  # diagnostics only: the stages either side of the hot path
+                line["io_edges"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(L, h, b0, b1, params, out)
         emit(line)
@@ -318,6 +323,72 @@ def run_ours(args):
     L.close_index(h)
     if world > 1:
         dist.destroy_process_group()
+
+
+def io_edges_stage(L, h, b0, b1, results):
+    """The stages either side of the hot path on this step's batch: FASTQ text of both mates ->
+    snapb200_fastq_parse -> read arrays, and this step's alignments -> snapb200_sam_batch -> SAM text.  Kernel time (CUDA events, no
+    copies), end-to-end time of the C-ABI call from pinned host buffers, and the algorithmic bytes (text + arrays, each counted once)
+    against the measured HBM copy peak.  Parity and the reference's own reader / writer timed beside: scripts/io_bench.py,
+    profiles/README.md (session 3)."""
+    import torch
+    from snap_rnaseq_b200 import _abi as A
+    from snap_rnaseq_b200 import synth
+
+    def pinned(n, dtype):
+        return torch.empty(n, dtype=dtype).pin_memory().numpy()
+
+    pairs = b0.n
+    texts = []
+    for e, b in enumerate((b0, b1)):
+        t = synth.fastq_fixed(b, e)
+        p = pinned(t.size, torch.uint8)
+        np.copyto(p, t)
+        texts.append(p)
+    nb = texts[0].size
+    bufs = [(pinned(pairs + 1, torch.int32).view(np.uint32), pinned(pairs + 1, torch.int32).view(np.uint32), pinned(nb, torch.uint8),
+             pinned(nb, torch.uint8), pinned(nb, torch.uint8), pinned(pairs, torch.int16).view(np.uint16), pinned(pairs, torch.int16).view(np.uint16))
+            for _ in range(2)]
+    for _ in range(3):  # the third repetition counts
+        reads, k_fq, t_fq = [], 0.0, 0.0
+        for t, bf in zip(texts, bufs):
+            t0 = time.perf_counter()
+            r, used = L.fastq_parse(t, 3, bufs=bf)
+            t_fq += time.perf_counter() - t0
+            k_fq += L.io_last_kernel_ms()[0]
+            if used != t.size or r.n != pairs:
+                raise RuntimeError("fastq_parse did not consume the text")
+            reads.append(r)
+    same_reads = bool(np.array_equal(reads[0].bases[:b0.bases.size], b0.bases) and np.array_equal(reads[1].quals[:b1.quals.size], b1.quals))
+    aln = []
+    for e in range(2):
+        a = np.zeros(pairs, A.SAM_ALIGNMENT)
+        for f in ("location", "mapq", "status", "direction"):
+            a[f] = results[f][:, e]
+        aln.append(a)
+    buf = pinned(2 * pairs * (2 * READ_LEN + 220), torch.uint8)
+    for _ in range(3):
+        t0 = time.perf_counter()
+        sam, lo = L.sam(h, reads[0], reads[1], aln[0], aln[1], False, None, out=buf)
+        t_sam = time.perf_counter() - t0
+        k_sam = L.io_last_kernel_ms()[1]
+    peak, _ = measured_peaks()
+    arrays = sum(int(r.offsets[-1]) * 2 + int(r.id_offsets[-1]) + r.n * 12 for r in reads)
+    fq_bytes = sum(t.size for t in texts) + arrays
+    mapped = int((aln[0]["status"] != 0).sum() + (aln[1]["status"] != 0).sum())
+    sam_bytes = arrays + 2 * pairs * 12 + mapped * (READ_LEN + 80) + int(lo[-1])
+    n_lines = int(np.count_nonzero(np.frombuffer(sam, np.uint8) == 10)) if len(sam) < (1 << 31) else None
+    return {
+        "fastq_parse": {"reads_per_s_kernels": 2 * pairs / (k_fq * 1e-3), "reads_per_s_e2e": 2 * pairs / t_fq, "kernel_ms": k_fq, "e2e_ms": t_fq * 1e3,
+                        "text_bytes": int(sum(t.size for t in texts)), "arrays_match_the_batch": same_reads,
+                        "roofline": {"bound": "hbm", "achieved": fq_bytes / (k_fq * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": fq_bytes / (k_fq * 1e-3) / 1e9 / peak}},
+        "sam_text": {"reads_per_s_kernels": 2 * pairs / (k_sam * 1e-3), "reads_per_s_e2e": 2 * pairs / t_sam, "kernel_ms": k_sam, "e2e_ms": t_sam * 1e3,
+                     "sam_bytes": int(lo[-1]), "lines": n_lines,
+                     "roofline": {"bound": "hbm", "achieved": sam_bytes / (k_sam * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": sam_bytes / (k_sam * 1e-3) / 1e9 / peak}},
+        "parity": "tests/test_io_edges.py, scripts/io_bench.py (2 M reads / 752 MB of SAM text identical to the reference's FASTQReader and SAMFormat)",
+    }
 
 
 def probe_stage(L, h, n_bases):

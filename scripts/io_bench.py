@@ -29,29 +29,6 @@ rlen = int(sys.argv[3]) if len(sys.argv) > 3 else 150
 SAMPLE = 1_000_000  # pairs the compiled reference re-does for the parity check and its own timing (one thread: a few seconds)
 
 
-def fastq_bytes(batch, mate):
-    """Fixed-width records built column-wise: @r<8 hex>/<mate> LF seq LF + LF qual LF."""
-    n = batch.n
-    w = 1 + 11 + 1 + rlen + 3 + rlen + 1
-    rec = np.empty((n, w), np.uint8)
-    rec[:, 0] = ord("@")
-    rec[:, 1] = ord("r")
-    idx = np.arange(n, dtype=np.uint64)
-    hexd = np.frombuffer(b"0123456789abcdef", np.uint8)
-    for k in range(8):
-        rec[:, 2 + k] = hexd[(idx >> np.uint64(4 * (7 - k))) & np.uint64(15)]
-    rec[:, 10] = ord("/")
-    rec[:, 11] = ord("1") + mate
-    rec[:, 12] = 10
-    rec[:, 13:13 + rlen] = batch.bases.reshape(n, rlen)
-    rec[:, 13 + rlen] = 10
-    rec[:, 14 + rlen] = ord("+")
-    rec[:, 15 + rlen] = 10
-    rec[:, 16 + rlen:16 + 2 * rlen] = batch.quals.reshape(n, rlen)
-    rec[:, 16 + 2 * rlen] = 10
-    return rec.reshape(-1)
-
-
 def main():
     L = S.lib(0)
     bench.GENOME_CONTIGS, bench.READ_LEN, bench.ERR_RATE = [25_000_000] * max(1, mbp // 25), rlen, 0.01
@@ -59,7 +36,7 @@ def main():
     bases, offs = synth.snap_layout(contigs, 500)
     h = L.build_index(bases, offs, piece_names=list(contigs), seed_len=20)
     b0, b1 = bench.make_pairs(contigs, pairs, seed=77)
-    texts = [fastq_bytes(b0, 0), fastq_bytes(b1, 1)]
+    texts = [synth.fastq_fixed(b0, 0), synth.fastq_fixed(b1, 1)]
     peak, peak_src = bench.measured_peaks()
     out = {"pairs": pairs, "genome_mbp": mbp, "read_len": rlen, "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
 

@@ -276,3 +276,29 @@ def write_fastq_plain(path, batch, mate=0, prefix="r"):
         for i in range(batch.n):
             b, q = batch.read(i)
             f.write(f"@{prefix}{i:x}/{mate + 1}\n{b}\n+\n{q}\n".encode())
+
+
+def fastq_fixed(batch, mate=0):
+    """FASTQ text (uint8 array) of a batch of equal-length reads, built column-wise: @r<8 hex digits>/<mate+1> LF bases LF + LF
+    qualities LF.  Used by the I/O-edge measurements (scripts/io_bench.py, bench.py io_edges)."""
+    n = batch.n
+    rlen = int(batch.offsets[1] - batch.offsets[0]) if n else 0
+    assert n == 0 or int(batch.offsets[-1]) == n * rlen
+    w = 1 + 11 + 1 + rlen + 3 + rlen + 1
+    rec = np.empty((n, w), np.uint8)
+    rec[:, 0] = ord("@")
+    rec[:, 1] = ord("r")
+    idx = np.arange(n, dtype=np.uint64)
+    hexd = np.frombuffer(b"0123456789abcdef", np.uint8)
+    for k in range(8):
+        rec[:, 2 + k] = hexd[(idx >> np.uint64(4 * (7 - k))) & np.uint64(15)]
+    rec[:, 10] = ord("/")
+    rec[:, 11] = ord("1") + mate
+    rec[:, 12] = 10
+    rec[:, 13:13 + rlen] = batch.bases.reshape(n, rlen)
+    rec[:, 13 + rlen] = 10
+    rec[:, 14 + rlen] = ord("+")
+    rec[:, 15 + rlen] = 10
+    rec[:, 16 + rlen:16 + 2 * rlen] = batch.quals.reshape(n, rlen)
+    rec[:, 16 + 2 * rlen] = 10
+    return rec.reshape(-1)

@@ -248,6 +248,13 @@ int snapb200_fastq_parse(int device, const uint8_t *text, uint64_t n_bytes, int 
                          uint32_t *n_reads, uint64_t *bytes_consumed, uint32_t *offsets, uint8_t *bases, uint8_t *quals,
                          uint16_t *front_clip, uint16_t *clipped_len, uint32_t *id_offsets, uint8_t *ids);
 
+/* Replaces FASTQReader::skipPartialRecord (SNAPLib/FASTQ.cpp:113-184), which FASTQReader::reinit runs when a reader is given a
+ * byte range that does not start at offset 0 (RangeSplitter hands every worker thread such ranges, SNAPLib/RangeSplitter.h:37-55):
+ * *offset = where the first record begins in `text` (n_bytes if there is none), i.e. where the text given to
+ * snapb200_fastq_parse must start.  Host logic (it looks at a few lines; no device is involved), which is how one file is
+ * sharded over host threads and GPUs. */
+int snapb200_fastq_record_start(const uint8_t *text, uint64_t n_bytes, uint64_t *offset);
+
 /* The arguments of ReadWriter::writeRead / the per-end fields of PairedAlignmentResult that SAM output uses
  * (SNAPLib/Read.h:171, SNAPLib/PairedEndAligner.h:31-56).  skip != 0: emit nothing for this read (a transcriptome
  * alignment, whose CIGAR needs the GTF: LandauVishkinWithCigar::insertSpliceJunctions stays on the host). */

@@ -491,6 +491,21 @@ int ref_fastq_parse(const char *path, int clipping, unsigned max_reads, unsigned
     return 0;
 }
 
+// FASTQReader::create with a starting offset runs reinit -> skipPartialRecord (SNAPLib/FASTQ.cpp:88-112); *file_offset = where
+// the reader stands afterwards (the first record it will return), or -1 when it found none.
+int ref_fastq_record_start(const char *path, long long start, long long *file_offset)
+{
+    ReaderContext ctx;
+    memset(&ctx, 0, sizeof(ctx));
+    FASTQReader *fq = FASTQReader::create(DataSupplier::Default[false], path, start, 0, ctx);
+    char *buffer;
+    _int64 valid;
+    if (!fq->data->getData(&buffer, &valid) || valid <= 0 || buffer[0] != '@') *file_offset = -1;
+    else *file_offset = fq->data->getFileOffset();
+    delete fq;
+    return 0;
+}
+
 static void make_read(Read *r, const snapb200_sam_reads *b, unsigned i, const char *read_group)
 {
     unsigned o = b->offsets[i], len = b->offsets[i + 1] - o;

@@ -201,6 +201,14 @@ class BatchLib:
         k = int(n.value)
         return A.SamReads(off[:k + 1], bases[:off[k]], quals[:off[k]], fc[:k], cl[:k], ioff[:k + 1], ids[:ioff[k]]), used
 
+    def fastq_record_start(self, text):
+        """FASTQReader::skipPartialRecord: offset of the first record in a buffer that may begin mid-record (len(text) if none)."""
+        raw = bytes(text)
+        off = C.c_uint64(0)
+        t = np.frombuffer(raw, np.uint8) if raw else np.zeros(1, np.uint8)
+        self._check(self.fn("fastq_record_start")(A.p8(t), C.c_uint64(len(raw)), C.byref(off)), "fastq_record_start")
+        return int(off.value)
+
     def sam(self, handle, reads0, reads1, aln0, aln1, use_m=False, read_group=None, out=None):
         """SimpleReadWriter::writeRead / writePair over SAMFormat::writeRead for a batch -> (SAM bytes, line_offsets).
         out: a uint8 array to write into with ONE call (returns a view of it); otherwise measure first, then write."""

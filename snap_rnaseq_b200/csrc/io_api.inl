@@ -60,6 +60,13 @@ static int io_scan(IoScratch &io, const T *in, T *out, size_t n)
     return 0;
 }
 
+extern "C" int snapb200_fastq_record_start(const uint8_t *text, uint64_t n_bytes, uint64_t *offset)
+{
+    if (!offset || (n_bytes && !text)) return set_error(SNAPB200_ERR_ARG, "null argument");
+    *offset = n_bytes ? fq_record_start(text, n_bytes) : 0;
+    return 0;
+}
+
 extern "C" int snapb200_fastq_parse(int device, const uint8_t *text, uint64_t n_bytes, int clipping, uint32_t max_reads, uint32_t *n_reads,
                                     uint64_t *bytes_consumed, uint32_t *offsets, uint8_t *bases, uint8_t *quals, uint16_t *front_clip,
                                     uint16_t *clipped_len, uint32_t *id_offsets, uint8_t *ids)

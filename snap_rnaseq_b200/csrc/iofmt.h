@@ -94,6 +94,40 @@ SNAP_HD FqRecord fq_record(const uint8_t *text, uint64_t n_bytes, const uint32_t
     return rec;
 }
 
+// FASTQReader::skipPartialRecord (FASTQ.cpp:113-184): where the first record begins in a buffer that may start in the middle
+// of one -- the pattern {start of buffer | LF} '@' ... LF {ACTGNactg}* [CR] LF '+'.  Returns n_bytes when there is none.
+// Bytes at and beyond n_bytes read as NUL (the reference's buffers end with one).
+SNAP_HD uint64_t fq_record_start(const uint8_t *text, uint64_t n_bytes)
+{
+#define FQ_AT(i) ((i) < n_bytes ? text[(i)] : (uint8_t)0)
+    uint64_t first = 0;
+    if (FQ_AT(0) != '@') {
+        while (first < n_bytes && text[first] != '\n' && text[first] != 0) first++;
+        if (first >= n_bytes || text[first] != '\n') return n_bytes;
+        first++;
+    }
+    for (;;) {
+        if (first >= n_bytes) return n_bytes;
+        uint64_t second = first;
+        while (second < n_bytes && text[second] != '\n' && text[second] != 0) second++;
+        if (second >= n_bytes || text[second] != '\n') return n_bytes;
+        second++;
+        if (text[first] != '@') { first = second; continue; }
+        uint64_t third = second;
+        for (;;) {
+            const uint8_t c = FQ_AT(third);
+            if (c == 'A' || c == 'C' || c == 'T' || c == 'G' || c == 'N' || c == 'a' || c == 'c' || c == 't' || c == 'g') third++;
+            else break;
+        }
+        if (FQ_AT(third) == '\r') third++;
+        if (FQ_AT(third) != '\n') { first = second; continue; }
+        third++;
+        if (FQ_AT(third) != '+') { first = second; continue; }
+        return first;
+    }
+#undef FQ_AT
+}
+
 SNAP_HD uint8_t fq_upper(uint8_t c) { return (c >= 0x61 && c <= 0x7a) ? (uint8_t)(c - 0x20) : c; }  // TO_UPPER_CASE, Tables.cpp:74-81
 
 // ---- SAM --------------------------------------------------------------------------------------------------------

@@ -51,6 +51,12 @@ extern "C" int hostsim_fastq_parse(const uint8_t *text_in, uint64_t n_bytes, int
     return 0;
 }
 
+extern "C" int hostsim_fastq_record_start(const uint8_t *text, uint64_t n_bytes, uint64_t *offset)
+{
+    *offset = n_bytes ? fq_record_start(text, n_bytes) : 0;
+    return 0;
+}
+
 static SamReadsDev view(const snapb200_sam_reads *r)
 {
     SamReadsDev d = {r->offsets, r->bases, r->quals, r->front_clip, r->clipped_len, r->id_offsets, r->ids};

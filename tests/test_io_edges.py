@@ -132,6 +132,42 @@ def test_hostsim_sam(hostsim, io_golden):
         assert int(lo[-1]) == len(want) and all(sam[int(o) - 1:int(o)] == b"\n" for o in lo[1:])
 
 
+def test_record_start_matches_the_reference(cuda, hostsim, ref, tmp_path):
+    """FASTQReader::skipPartialRecord: for byte ranges that begin anywhere (inside an id, the bases, the '+' line, a quality
+    string that starts with '@' or '+'), the first record the reference's reader stands on is the one the C ABI reports.
+    snapb200_fastq_record_start is host logic, so this runs without a GPU."""
+    import ctypes
+    text = io_cases.fastq_text(5, 400, 100, crlf_frac=0.15, partial_tail=False)
+    path = tmp_path / "x.fq"
+    path.write_bytes(text)
+    ref.lib.ref_fastq_record_start.restype = ctypes.c_int
+    rng = np.random.default_rng(3)
+    starts = sorted({int(x) for x in rng.integers(1, len(text) - 2000, size=300)} | {1, 2, 5})
+    record_starts = {0} | {m + 1 for m in np.flatnonzero(np.frombuffer(text, np.uint8) == 10)}
+    n_mid_quality = 0
+    for st in starts:
+        off = ctypes.c_longlong(0)
+        assert ref.lib.ref_fastq_record_start(str(path).encode(), ctypes.c_longlong(st), ctypes.byref(off)) == 0
+        want = off.value - st
+        got = cuda.fastq_record_start(text[st:])
+        assert got == hostsim.fastq_record_start(text[st:])
+        assert got == want, f"range starting at {st}: reference skips {want} bytes, C ABI {got}"
+        assert st + got in record_starts and text[st + got:st + got + 1] == b"@"
+        n_mid_quality += text[st:st + 1] in (b"@", b"+")
+    assert n_mid_quality > 0
+    # parsing from the reported start gives the tail of the records parsed from the beginning
+    st = starts[len(starts) // 2]
+    got = hostsim.fastq_record_start(text[st:])
+    whole, _ = hostsim.fastq_parse(text, 3)
+    part, _ = hostsim.fastq_parse(text[st + got:], 3)
+    k = whole.n - part.n
+    assert part.n > 0 and np.array_equal(part.clipped_len[:part.n], whole.clipped_len[k:whole.n])
+    assert part.ids[:part.id_offsets[-1]].tobytes() == whole.ids[whole.id_offsets[k]:whole.id_offsets[-1]].tobytes()
+    # nothing that looks like a record
+    assert cuda.fastq_record_start(b"ACGTACGT\nIIIIIIII\n") == len(b"ACGTACGT\nIIIIIIII\n")
+    assert cuda.fastq_record_start(b"") == 0
+
+
 def test_golden_covers_the_branches(io_golden):
     """The golden SAM text must contain what the cases were built to produce (so a silent change of the generator shows)."""
     text = b"".join(io_golden[f"sam{k}"].tobytes() for k in range(len(SAM_CASES)))
@@ -246,3 +282,51 @@ def test_cuda_io_concurrent_callers(cuda, handle, io_golden):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.gpu
+def test_cuda_io_round_trip_properties(cuda, handle):
+    """Size-independent properties on a batch too large to hand-check (200 k reads): the parsed arrays rebuild the FASTQ text
+    they came from; every SAM line carries its read (reversed and complemented when flagged 0x10), line offsets tile the output,
+    and mates point at each other."""
+    contigs = small_genome()
+    n, rlen = 100_000, 150
+    sim = synth.simulate(contigs, n, rlen, paired=True, err=0.02, seed=77, frag=(250, 450))
+    b0, b1 = sim["batches"]
+    texts = [synth.fastq_fixed(b0, 0), synth.fastq_fixed(b1, 1)]
+    reads = []
+    for t, b in zip(texts, (b0, b1)):
+        r, used = cuda.fastq_parse(t, 0)
+        assert used == t.size and r.n == n
+        ids = r.ids[:r.id_offsets[-1]].reshape(n, 11)
+        rebuilt = np.concatenate([np.full((n, 1), ord("@"), np.uint8), ids, np.full((n, 1), 10, np.uint8), r.bases[:n * rlen].reshape(n, rlen),
+                                  np.frombuffer(b"\n+\n", np.uint8)[None, :].repeat(n, 0), r.quals[:n * rlen].reshape(n, rlen),
+                                  np.full((n, 1), 10, np.uint8)], axis=1).reshape(-1)
+        assert np.array_equal(rebuilt, t)
+        reads.append(r)
+    res = cuda.paired(handle, A.paired_defaults(), b0, b1)
+    aln = []
+    for e in range(2):
+        a = np.zeros(n, A.SAM_ALIGNMENT)
+        for f in ("location", "mapq", "status", "direction"):
+            a[f] = res[f][:, e]
+        aln.append(a)
+    sam, lo = cuda.sam(handle, reads[0], reads[1], aln[0], aln[1])
+    assert len(lo) == 2 * n + 1 and int(lo[-1]) == len(sam) and np.all(np.diff(lo.astype(np.int64)) > 0)
+    lines = sam.split(b"\n")
+    assert lines[-1] == b"" and len(lines) == 2 * n + 1
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    for p in range(0, n, 37):
+        f1, f2 = lines[2 * p].split(b"\t"), lines[2 * p + 1].split(b"\t")
+        assert f1[0] == f2[0] == b"r%08x" % p
+        fl1, fl2 = int(f1[1]), int(f2[1])
+        assert fl1 & 0x41 == 0x41 and fl2 & 0x81 == 0x81
+        assert bool(fl1 & 0x20) == bool(fl2 & 0x10) or fl2 & 0x4      # mate strand mirrors the mate's own strand when it is mapped
+        assert abs(int(f1[8])) == abs(int(f2[8]))
+        mates = {b0.read(p), b1.read(p)}
+        for f, fl in ((f1, fl1), (f2, fl2)):
+            seq, qual = f[9], f[10]
+            if fl & 0x10:
+                seq, qual = seq.translate(comp)[::-1], qual[::-1]
+            assert (seq.decode(), qual.decode()) in mates
+            assert f[-1].startswith(b"NM:i:") and f[-2] == b"PG:Z:SNAP"

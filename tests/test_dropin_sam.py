@@ -17,7 +17,17 @@ B200 = os.path.join(ROOT, "oracle", "_ref", "snap-rna-b200")
 
 
 def run(cmd, cwd):
-    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # The reference's own reader has a timing-dependent failure with -t > 1: RangeSplitter sizes the ranges from the threads' speed
+    # (SNAPLib/RangeSplitter.cpp:50-92), and when the last range happens to begin inside the last record of the file,
+    # FASTQReader::skipPartialRecord finds no record, reinit returns without advancing (FASTQ.cpp:104-111, 131-134) and the next
+    # getNextRead parses from the middle of a record: "FASTQ file has invalid starting character" + soft_exit(1).  Seen once in
+    # ~100 runs of this file (in the unmodified reader, which both binaries share); such a run says nothing about the aligners
+    # and is repeated.
+    for attempt in range(4):
+        r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 and "FASTQ file has invalid starting character" in r.stdout and attempt < 3:
+            continue
+        break
     assert r.returncode == 0, " ".join(cmd) + "\n" + r.stdout[-3000:]
     return r.stdout
 

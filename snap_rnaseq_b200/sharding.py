@@ -55,3 +55,23 @@ def stats_from_results(paired_results):
     ok = (st != A.NOT_FOUND) & (mq >= 0) & (mq <= 70)
     w[14:14 + 71] = np.bincount(mq[ok], minlength=71)[:71]
     return w
+
+
+def fastq_shard_bounds(lib, text, world_size):
+    """Byte ranges of one FASTQ text for `world_size` readers, as the reference splits a file over its worker threads: the file is
+    cut at arbitrary offsets (RangeSplitter, SNAPLib/RangeSplitter.cpp:50-92) and a reader owns the records that START inside its
+    range -- it skips to the first whole record (FASTQReader::skipPartialRecord = snapb200_fastq_record_start) and reads on past the
+    end of its range to finish the last one.  Returns world_size + 1 offsets; rank r parses text[b[r]:b[r+1]], which holds exactly
+    its records, with snapb200_fastq_parse.  Ranks whose cut lands after the last record start get an empty range."""
+    text = memoryview(text)
+    n = len(text)
+    bounds = [0]
+    for r in range(1, world_size):
+        cut = n * r // world_size
+        cut = max(cut, bounds[-1])
+        # a record is assumed to fit the look-ahead window, as the reference assumes it fits its buffer (FASTQ.cpp:116-117)
+        window = text[cut:cut + (1 << 20)]
+        skip = lib.fastq_record_start(window) if cut < n else 0
+        bounds.append(cut + skip if skip < len(window) or cut + len(window) < n else n)
+    bounds.append(n)
+    return bounds

@@ -112,3 +112,60 @@ def test_stats_allreduce_gloo_world2():
         assert p.exitcode == 0
     for rank, total, expect in got:
         assert np.array_equal(total, expect), f"rank {rank}: reduced stats differ from the unsharded ones"
+
+
+def _fastq_worker(rank, world, port, q):
+    """Each rank takes its byte range of one FASTQ text (found with the product's snapb200_fastq_record_start) and parses it; the
+    per-record logic runs through tests/hostsim here because this box has no GPU (on a GPU box the same ranges go to
+    snapb200_fastq_parse).  The only exchange is the read count (gloo all-reduce), as for the statistics."""
+    import ctypes
+    import subprocess
+    import torch
+    import torch.distributed as dist
+    import snap_rnaseq_b200 as S
+    from snap_rnaseq_b200._binding import BatchLib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import io_cases
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    if rank == 0 and not os.path.exists(so):
+        subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    dist.barrier()
+    hostsim = BatchLib(ctypes.CDLL(so), "hostsim_")
+    text = io_cases.fastq_text(5, 400, 100, crlf_frac=0.1, partial_tail=False)
+    bounds = sharding.fastq_shard_bounds(S.lib(), text, world)
+    mine, used = hostsim.fastq_parse(text[bounds[rank]:bounds[rank + 1]], 3)
+    assert used == bounds[rank + 1] - bounds[rank]
+    t = torch.tensor([mine.n], dtype=torch.int64)
+    dist.all_reduce(t)
+    q.put((rank, int(t[0]), bounds, mine.ids[:mine.id_offsets[-1]].tobytes(), mine.clipped_len[:mine.n].tolist()))
+    dist.destroy_process_group()
+
+
+def test_fastq_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fastq_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] == 400 and got[0][2] == got[1][2]
+    bounds = got[0][2]
+    assert 0 < bounds[1] < bounds[2] and len(got[0][4]) > 100 and len(got[1][4]) > 100
+    # the shards, in rank order, are the unsharded parse
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ctypes
+    import io_cases
+    from snap_rnaseq_b200._binding import BatchLib
+    hostsim = BatchLib(ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim", "libiohostsim.so")), "hostsim_")
+    whole, _ = hostsim.fastq_parse(io_cases.fastq_text(5, 400, 100, crlf_frac=0.1, partial_tail=False), 3)
+    assert got[0][3] + got[1][3] == whole.ids[:whole.id_offsets[-1]].tobytes()
+    assert got[0][4] + got[1][4] == whole.clipped_len[:whole.n].tolist()

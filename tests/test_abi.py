@@ -67,6 +67,29 @@ def test_no_gpu_means_failure_not_fallback():
         L.lv(1, [b"abc"], [b"abc"], None, [2])
     with pytest.raises(RuntimeError):
         L.load_index("/nonexistent")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        L.fastq_parse(b"@a\nACGT\n+\nIIII\n", 0)
+
+
+def test_io_struct_layouts_match_header(tmp_path):
+    """snapb200_sam_reads / snapb200_sam_alignment as gcc sees them against the ctypes / numpy mirrors."""
+    import subprocess
+
+    from snap_rnaseq_b200 import _abi as A
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "snapb200.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(snapb200_sam_reads), offsetof(snapb200_sam_reads,front_clip),'
+        ' offsetof(snapb200_sam_reads,ids), sizeof(snapb200_sam_alignment), offsetof(snapb200_sam_alignment,mapq),'
+        ' offsetof(snapb200_sam_alignment,status), offsetof(snapb200_sam_alignment,skip));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    assert got[0] == C.sizeof(A.SamReadsStruct)
+    assert got[1] == A.SamReadsStruct.front_clip.offset and got[2] == A.SamReadsStruct.ids.offset
+    assert got[3] == A.SAM_ALIGNMENT.itemsize
+    assert got[4] == A.SAM_ALIGNMENT.fields["mapq"][1] and got[5] == A.SAM_ALIGNMENT.fields["status"][1]
+    assert got[6] == A.SAM_ALIGNMENT.fields["skip"][1]
 
 
 def test_product_does_not_reference_the_oracle():

@@ -40,6 +40,8 @@
 #include "FileFormat.h"
 #include "DataReader.h"
 #include "DataWriter.h"
+#include "AlignmentFilter.h"
+#include "GTFReader.h"
 #undef private
 #undef protected
 
@@ -560,5 +562,99 @@ int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_read
     return 0;
 }
 
+// ---- row f3 (next): AlignmentFilter as the paired run loop drives it -------------------------------------------------------
+// No CUDA counterpart exists yet; these entry points pin the reference's behaviour (tests/golden/filter_cases.npz) so that the
+// device version has an oracle from its first line.
+
+// GTFReader as AlignerContext creates it (SNAPLib/AlignerContext.cpp:265-267); out_prefix names the files WriteReadCounts writes.
+void *ref_gtf_load(const char *gtf_path, const char *out_prefix)
+{
+    GTFReader *g = new GTFReader(strdup(out_prefix));
+    g->Load(std::string(gtf_path));
+    return g;
+}
+
+// AlignerContext::finishIteration's GTF epilogue (SNAPLib/AlignerContext.cpp:126-127)
+int ref_gtf_finish(void *gtf)
+{
+    GTFReader *g = (GTFReader *)gtf;
+    g->AnalyzeReadIntervals();
+    g->WriteReadCounts();
+    return 0;
+}
+
+struct ref_filter_result {  // the fields of PairedAlignmentResult that leave the loop (writePair / updateStats)
+    unsigned location[2];
+    unsigned tlocation[2];
+    int score[2];
+    int mapq[2];
+    unsigned char status[2];
+    unsigned char direction[2];
+    unsigned char is_transcriptome[2];
+    unsigned char pad[2];
+};
+
+// The part of PairedAlignerContext::runIterationThread between the aligner calls and writePair (SNAPLib/PairedAligner.cpp:
+// 575-663): AlignmentFilter over the transcriptome multi-hits of both ends and the genome pair, Filter(), forceSpacing and the
+// "cheese" MAPQ rule.  Alignments come in as the aligners (or the CUDA library) produced them; reads as the reader did.
+// One thread, pairs in order: the filter updates shared GTF counters (SNAPLib/GTFReader.h) whose totals ref_gtf_finish writes.
+int ref_filter_paired_batch(void *h_genome, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
+                            unsigned min_spacing, unsigned max_spacing, int force_spacing, unsigned conf_diff, unsigned max_dist,
+                            unsigned max_hits_to_get, const int *n0, const unsigned *l0, const unsigned char *rc0, const int *sc0,
+                            const int *n1, const unsigned *l1, const unsigned char *rc1, const int *sc1, const snapb200_paired_result *genome_res,
+                            ref_filter_result *out)
+{
+    GenomeIndex *idx = (GenomeIndex *)h_genome, *tidx = (GenomeIndex *)h_transcriptome;
+    GTFReader *g = (GTFReader *)gtf;
+    // partialAligner, SNAPLib/PairedAligner.cpp:518-530 (explorePopularSeeds / stopOnFirstHit at their defaults, false)
+    BaseAligner *partial = new BaseAligner(idx, 300, max_dist, MAX_READ_LENGTH, 12, 0.0, 2, NULL, NULL);
+    for (unsigned i = 0; i < r0->n; i++) {
+        Read read0, read1;
+        make_read(&read0, r0, i, NULL);
+        make_read(&read1, r1, i, NULL);
+        PairedAlignmentResult result;
+        memset(&result, 0, sizeof(result));
+        for (int e = 0; e < 2; e++) {
+            result.status[e] = (AlignmentResult)genome_res[i].status[e];
+            result.location[e] = genome_res[i].location[e];
+            result.direction[e] = (Direction)genome_res[i].direction[e];
+            result.score[e] = genome_res[i].score[e];
+            result.mapq[e] = genome_res[i].mapq[e];
+            result.isTranscriptome[e] = false;
+        }
+        result.fromAlignTogether = genome_res[i].from_align_together != 0;
+        result.alignedAsPair = genome_res[i].aligned_as_pair != 0;
+        AlignmentFilter filter(&read0, &read1, idx->getGenome(), tidx->getGenome(), g, min_spacing, max_spacing, conf_diff, max_dist,
+                               idx->getSeedLength(), partial);
+        const size_t base = (size_t)i * max_hits_to_get;
+        for (int k = 0; k < n0[i]; k++) filter.AddAlignment(l0[base + k], rc0[base + k] ? RC : FORWARD, sc0[base + k], 0, true, false);
+        for (int k = 0; k < n1[i]; k++) filter.AddAlignment(l1[base + k], rc1[base + k] ? RC : FORWARD, sc1[base + k], 0, true, true);
+        filter.AddAlignment(result.location[0], result.direction[0], result.score[0], result.mapq[0], false, false);
+        filter.AddAlignment(result.location[1], result.direction[1], result.score[1], result.mapq[1], false, true);
+        filter.Filter(&result);
+        if (force_spacing && isOneLocation(result.status[0]) != isOneLocation(result.status[1])) {
+            result.status[0] = result.status[1] = NotFound;
+            result.location[0] = result.location[1] = InvalidGenomeLocation;
+        }
+        if (result.score[0] + result.score[1] >= 5) {  // "cheese"
+            if (result.mapq[0] < 50) result.mapq[0] /= 2;
+            if (result.mapq[1] < 50) result.mapq[1] /= 2;
+        }
+        memset(&out[i], 0, sizeof(out[i]));
+        for (int e = 0; e < 2; e++) {
+            out[i].location[e] = result.location[e];
+            out[i].tlocation[e] = result.isTranscriptome[e] ? result.tlocation[e] : 0;
+            out[i].score[e] = result.score[e];
+            out[i].mapq[e] = result.mapq[e];
+            out[i].status[e] = (unsigned char)result.status[e];
+            out[i].direction[e] = (unsigned char)result.direction[e];
+            out[i].is_transcriptome[e] = result.isTranscriptome[e] ? 1 : 0;
+        }
+    }
+    partial->~BaseAligner();
+    return 0;
+}
+
 } // extern "C"
+
 

@@ -44,5 +44,21 @@ def build(force=False, verbose=False, profile=False):
     return out
 
 
+VARIANT_DIR = os.path.join(HERE, "variants")  # experiment builds (scripts/ab_variants.py); *.so is git-ignored and travels with gpurun
+
+
+def build_variant(name, flags, verbose=False):
+    """The same library compiled with extra flags (e.g. -DLANE_K_EXTRA=3) into variants/libsnapb200_<name>.so."""
+    os.makedirs(VARIANT_DIR, exist_ok=True)
+    out = os.path.join(VARIANT_DIR, f"libsnapb200_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "snapb200.cu")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))

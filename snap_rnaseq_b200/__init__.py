@@ -235,3 +235,31 @@ class SAMFormat:
     @staticmethod
     def computeCigarString(index, batch, locations, directions, useM=False):
         return lib(index.device).cigar(index.h, batch, locations, directions, useM)
+
+    @staticmethod
+    def writeReads(index, reads, alignments, useM=False, readGroup=None):
+        """SimpleReadWriter::writeRead over SAMFormat::writeRead (SNAPLib/ReadWriter.cpp:90-130, SAM.cpp:977-1153) for a batch of
+        single-end reads (_abi.SamReads + SAM_ALIGNMENT records) -> (SAM bytes, line offsets)."""
+        return lib(index.device).sam(index.h, reads, None, alignments, None, useM, readGroup)
+
+    @staticmethod
+    def writePairs(index, reads0, reads1, alignments0, alignments1, useM=False, readGroup=None):
+        """SimpleReadWriter::writePair (SNAPLib/ReadWriter.cpp:132-217): two lines per pair, the end with the lower location first."""
+        return lib(index.device).sam(index.h, reads0, reads1, alignments0, alignments1, useM, readGroup)
+
+
+class FASTQReader:
+    """FASTQReader (SNAPLib/FASTQ.cpp) in batch form: every complete record of a text at once."""
+
+    def __init__(self, clipping=0, device=0):
+        self.clipping = clipping  # ReadClippingType, SNAPLib/Read.h:85
+        self.device = device
+
+    def skipPartialRecord(self, text):
+        """Offset of the first record in a buffer that may begin mid-record (FASTQ.cpp:113-184); len(text) if there is none."""
+        return lib(self.device).fastq_record_start(text)
+
+    def getReads(self, text):
+        """getNextRead until the text is exhausted (FASTQ.cpp:188-246) -> (_abi.SamReads, bytes consumed)."""
+        return lib(self.device).fastq_parse(text, self.clipping)
+

@@ -249,6 +249,11 @@ def test_cuda_fastq_to_sam_pipeline(cuda, handle, ref, small_index_dir, rlen, cl
         sam, _ = cuda.sam(handle, got[0], got[1], aln[0], aln[1], use_m)
         sam_ref, _ = ref.sam(hc, want[0], want[1], aln[0], aln[1], use_m)
         assert_same_sam(sam_ref, sam, f"use_m={use_m}")
+    # the same through the reference-named mirror of the package
+    import snap_rnaseq_b200 as S
+    gi = S.GenomeIndex(handle, 0)
+    assert S.SAMFormat.writePairs(gi, got[0], got[1], aln[0], aln[1], True)[0] == sam
+    assert S.FASTQReader(clipping).getReads(texts[0])[0].same_as(got[0])
     # single-end lines of the same reads
     sam, _ = cuda.sam(handle, got[1], None, aln[1], None, False, "rg7")
     sam_ref, _ = ref.sam(hc, want[1], None, aln[1], None, False, "rg7")

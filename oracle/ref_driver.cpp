@@ -655,6 +655,65 @@ int ref_filter_paired_batch(void *h_genome, void *h_transcriptome, void *gtf, co
     return 0;
 }
 
+// The annotation as the filter sees it, for checking a flat-table loader: one line per transcript
+//   T <transcript_id> <chr> <gene_id> <start> <end> <n> then n x (type start end)     (GTFTranscript::exons order)
+// and per gene   G <gene_id> <chr> <start> <end>.   Written to `path`.
+int ref_gtf_export(void *gtf, const char *path)
+{
+    GTFReader *g = (GTFReader *)gtf;
+    FILE *f = fopen(path, "w");
+    if (!f) return -1;
+    for (transcript_map::iterator it = g->transcripts.begin(); it != g->transcripts.end(); ++it) {
+        GTFTranscript &t = it->second;
+        fprintf(f, "T\t%s\t%s\t%s\t%u\t%u\t%u", it->first.c_str(), t.chr.c_str(), t.gene_id.c_str(), t.start, t.end, (unsigned)t.exons.size());
+        for (feature_list::iterator e = t.exons.begin(); e != t.exons.end(); ++e) fprintf(f, "\t%u\t%u\t%u", (*e)->type, (*e)->start, (*e)->end);
+        fprintf(f, "\n");
+    }
+    for (gene_map::iterator it = g->genes.begin(); it != g->genes.end(); ++it)
+        fprintf(f, "G\t%s\t%s\t%u\t%u\n", it->first.c_str(), it->second.chr.c_str(), it->second.start, it->second.end);
+    fclose(f);
+    return 0;
+}
+
+// What AlignmentFilter::AddAlignment + HashAlignment leave in the two maps of one pair (AlignmentFilter.cpp:113-214), in map
+// (string-key) order: for end e (0 = the map the run loop fills from read 0, i.e. the member called mate1), up to `cap` records of
+//   location, pos, pos_end, pos_original, score, direction, isTranscriptome  (7 unsigned each) and the key strings, NUL-separated.
+int ref_filter_alignments(void *h_genome, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
+                          unsigned i, unsigned max_dist, unsigned max_hits_to_get, const int *n0, const unsigned *l0, const unsigned char *rc0,
+                          const int *sc0, const int *n1, const unsigned *l1, const unsigned char *rc1, const int *sc1,
+                          const snapb200_paired_result *genome_res, unsigned cap, unsigned *counts, unsigned *records, char *keys, unsigned keys_cap)
+{
+    GenomeIndex *idx = (GenomeIndex *)h_genome, *tidx = (GenomeIndex *)h_transcriptome;
+    Read read0, read1;
+    make_read(&read0, r0, i, NULL);
+    make_read(&read1, r1, i, NULL);
+    AlignmentFilter filter(&read0, &read1, idx->getGenome(), tidx->getGenome(), (GTFReader *)gtf, 50, 1000, 2, max_dist, idx->getSeedLength(), NULL);
+    const size_t base = (size_t)i * max_hits_to_get;
+    for (int k = 0; k < n0[i]; k++) filter.AddAlignment(l0[base + k], rc0[base + k] ? RC : FORWARD, sc0[base + k], 0, true, false);
+    for (int k = 0; k < n1[i]; k++) filter.AddAlignment(l1[base + k], rc1[base + k] ? RC : FORWARD, sc1[base + k], 0, true, true);
+    filter.AddAlignment(genome_res[i].location[0], (Direction)genome_res[i].direction[0], genome_res[i].score[0], genome_res[i].mapq[0], false, false);
+    filter.AddAlignment(genome_res[i].location[1], (Direction)genome_res[i].direction[1], genome_res[i].score[1], genome_res[i].mapq[1], false, true);
+    alignment_map *maps[2] = {&filter.mate1, &filter.mate0};  // read 0's alignments live in the member called mate1 (isMate0 = false)
+    unsigned kp = 0;
+    for (int e = 0; e < 2; e++) {
+        unsigned c = 0;
+        for (alignment_map::iterator it = maps[e]->begin(); it != maps[e]->end(); ++it, ++c) {
+            if (c >= cap) return -2;
+            Alignment &a = it->second;
+            unsigned *r = records + ((size_t)e * cap + c) * 7;
+            r[0] = a.location; r[1] = a.pos; r[2] = a.pos_end; r[3] = a.pos_original; r[4] = (unsigned)a.score; r[5] = (unsigned)a.direction;
+            r[6] = a.isTranscriptome ? 1 : 0;
+            size_t len = it->first.size() + 1;
+            if (kp + len > keys_cap) return -3;
+            memcpy(keys + kp, it->first.c_str(), len);
+            kp += (unsigned)len;
+        }
+        counts[e] = c;
+    }
+    return 0;
+}
+
 } // extern "C"
+
 
 

@@ -126,3 +126,31 @@ extern "C" int hostsim_sam_batch(const HostsimIndex *ix, const snapb200_sam_read
     }
     return 0;
 }
+
+// ---- row f3 groundwork: the alignment lists of one pair, as AlignmentFilter builds them ------------------------------------------
+#include "../../snap_rnaseq_b200/csrc/filterfmt.h"
+
+extern "C" int hostsim_filter_alignments(const FltTables *t, uint32_t len0, uint32_t len1, uint32_t max_dist, int n0, const uint32_t *l0,
+                                         const uint8_t *rc0, const int32_t *sc0, int n1, const uint32_t *l1, const uint8_t *rc1, const int32_t *sc1,
+                                         const snapb200_paired_result *g, uint32_t cap, uint32_t *counts, uint32_t *records)
+{
+    std::vector<FltAln> lists[2];
+    lists[0].resize(cap + 1);
+    lists[1].resize(cap + 1);
+    uint32_t n[2] = {0, 0};
+    FltAln a;
+    for (int k = 0; k < n0; k++) if (flt_make_alignment(*t, l0[k], rc0[k] ? 1 : 0, sc0[k], 0, true, len0, max_dist, &a)) { if (n[0] >= cap) return -2; n[0] = flt_insert(*t, lists[0].data(), n[0], a); }
+    for (int k = 0; k < n1; k++) if (flt_make_alignment(*t, l1[k], rc1[k] ? 1 : 0, sc1[k], 0, true, len1, max_dist, &a)) { if (n[1] >= cap) return -2; n[1] = flt_insert(*t, lists[1].data(), n[1], a); }
+    const uint32_t lens[2] = {len0, len1};
+    for (int e = 0; e < 2; e++)
+        if (flt_make_alignment(*t, g->location[e], g->direction[e], g->score[e], g->mapq[e], false, lens[e], max_dist, &a)) { if (n[e] >= cap) return -2; n[e] = flt_insert(*t, lists[e].data(), n[e], a); }
+    for (int e = 0; e < 2; e++) {
+        counts[e] = n[e];
+        for (uint32_t c = 0; c < n[e]; c++) {
+            const FltAln &x = lists[e][c];
+            uint32_t *r = records + ((size_t)e * cap + c) * 7;
+            r[0] = x.location; r[1] = x.pos; r[2] = x.pos_end; r[3] = x.pos_original; r[4] = (uint32_t)x.score; r[5] = x.direction; r[6] = x.is_transcriptome;
+        }
+    }
+    return 0;
+}

@@ -47,3 +47,132 @@ def test_reference_filter_reproduces_golden(ref, port, golden_filter, tmp_path):
     r = golden_filter["result"]
     assert r["is_transcriptome"].sum() > 100 and (r["status"] == 0).sum() > 50
     assert (r["location"] != golden_filter["genome_location"]).any(axis=1).sum() > 100
+
+
+# ---- first pieces of the device filter (snap_rnaseq_b200/csrc/filterfmt.h) on the host ------------------------------------------
+import ctypes as C  # noqa: E402
+
+
+class FltTables(C.Structure):
+    _fields_ = [("piece_begin", C.POINTER(C.c_uint32)), ("n_pieces", C.c_uint32), ("chr_names", C.c_char_p), ("chr_name_off", C.POINTER(C.c_uint32)),
+                ("tpiece_begin", C.POINTER(C.c_uint32)), ("n_tpieces", C.c_uint32), ("tpiece_transcript", C.POINTER(C.c_int32)),
+                ("t_chr", C.POINTER(C.c_int32)), ("t_gene", C.POINTER(C.c_int32)), ("t_end", C.POINTER(C.c_uint32)),
+                ("t_feat_first", C.POINTER(C.c_uint32)), ("f_type", C.POINTER(C.c_uint32)), ("f_start", C.POINTER(C.c_uint32)),
+                ("f_end", C.POINTER(C.c_uint32))]
+
+
+def genome_pieces(index_dir):
+    """(names, beginning offsets) from the `Genome` file of an index directory (SNAPLib/Genome.cpp:126-158)."""
+    with open(os.path.join(index_dir, "Genome"), "rb") as f:
+        n_pieces = int(f.readline().split()[1])
+        rows = [f.readline().decode().rstrip("\n").split(" ", 1) for _ in range(n_pieces)]
+    return [r[1] for r in rows], np.array([int(r[0]) for r in rows], np.uint32)
+
+
+def flat_tables(export_path, gdir, tdir):
+    from snap_rnaseq_b200 import _abi as A
+    chr_names, piece_begin = genome_pieces(gdir)
+    t_names, tpiece_begin = genome_pieces(tdir)
+    transcripts, genes = {}, {}
+    for line in open(export_path):
+        p = line.rstrip("\n").split("\t")
+        if p[0] == "T":
+            n = int(p[6])
+            feats = [(int(p[7 + 3 * k]), int(p[8 + 3 * k]), int(p[9 + 3 * k])) for k in range(n)]
+            transcripts[p[1]] = (p[2], p[3], int(p[4]), int(p[5]), feats)
+        else:
+            genes[p[1]] = (p[2], int(p[3]), int(p[4]))
+    t_ids, g_ids = sorted(transcripts), sorted(genes)
+    keep = {}
+    keep["piece_begin"], keep["tpiece_begin"] = piece_begin, tpiece_begin
+    blob, off = A.strings_to_offsets([c.encode() for c in chr_names])
+    keep["chr_blob"], keep["chr_off"] = bytes(blob[:off[-1]]), off
+    keep["tpiece_transcript"] = np.array([t_ids.index(n) for n in t_names], np.int32)
+    keep["t_chr"] = np.array([chr_names.index(transcripts[t][0]) for t in t_ids], np.int32)
+    keep["t_gene"] = np.array([g_ids.index(transcripts[t][1]) for t in t_ids], np.int32)
+    keep["t_end"] = np.array([transcripts[t][3] for t in t_ids], np.uint32)
+    first = np.zeros(len(t_ids) + 1, np.uint32)
+    np.cumsum([len(transcripts[t][4]) for t in t_ids], out=first[1:])
+    keep["t_feat_first"] = first
+    feats = [f for t in t_ids for f in transcripts[t][4]]
+    for k, name in enumerate(("f_type", "f_start", "f_end")):
+        keep[name] = np.array([f[k] for f in feats], np.uint32)
+    T = FltTables()
+    T.piece_begin, T.n_pieces = A.p32u(piece_begin), len(piece_begin)
+    T.chr_names, T.chr_name_off = keep["chr_blob"], A.p32u(off)
+    T.tpiece_begin, T.n_tpieces = A.p32u(tpiece_begin), len(tpiece_begin)
+    T.tpiece_transcript = A.p32i(keep["tpiece_transcript"])
+    T.t_chr, T.t_gene, T.t_end = A.p32i(keep["t_chr"]), A.p32i(keep["t_gene"]), A.p32u(keep["t_end"])
+    T.t_feat_first = A.p32u(first)
+    T.f_type, T.f_start, T.f_end = A.p32u(keep["f_type"]), A.p32u(keep["f_start"]), A.p32u(keep["f_end"])
+    return T, keep
+
+
+def test_alignment_lists_match_the_reference(ref, tmp_path):
+    """AddAlignment + HashAlignment for every pair: the de-duplicated lists of both ends, in the string order of the reference's map
+    keys, from the flat-table functions of filterfmt.h against the maps inside the reference's own AlignmentFilter."""
+    import subprocess
+    from oracle import oracle as O
+    from snap_rnaseq_b200 import _abi as A
+    d = str(tmp_path)
+    contigs = F.build_workspace(d, O.REF_BIN)
+    (b0, b1), sam_reads = F.reads(contigs, d, n=600)
+    hg, ht = ref.load_index(os.path.join(d, "gidx")), ref.load_index(os.path.join(d, "tidx"))
+    hits, genome_res, pp = F.alignments(ref, hg, ht, b0, b1)
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "lists").encode()))
+    assert lib.ref_gtf_export(g, os.path.join(d, "gtf.tsv").encode()) == 0
+    T, keep = flat_tables(os.path.join(d, "gtf.tsv"), os.path.join(d, "gidx"), os.path.join(d, "tidx"))
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    cap, mh = 2048, F.MAX_HITS_TO_GET
+    (n0, l0, r0, s0), (n1, l1, r1, s1) = hits
+    res = np.ascontiguousarray(genome_res, A.PAIRED_RESULT)
+    lens0, lens1 = np.diff(b0.offsets), np.diff(b1.offsets)
+    # the simulated reads give short lists; pairs 300.. get fabricated hits instead (the filter takes whatever the aligners hand it):
+    # dozens of transcriptome locations per end with scores around the maxDist gate, exact repeats with other scores (the tie rules of
+    # HashAlignment), reads that run off the end of a transcript, and genome locations anywhere
+    rng = np.random.default_rng(12)
+    tb = keep["tpiece_begin"].astype(np.int64)
+    tlen = np.diff(np.append(tb, tb[-1] + 3000))
+    glen = int(keep["piece_begin"][-1]) + 150000
+    for i in range(300, b0.n):
+        for (cnt, loc, rcs, sc) in hits:
+            k = int(rng.integers(1, 60))
+            p = rng.integers(0, len(tb), size=k)
+            loc[i, :k] = (tb[p] + (rng.random(k) * (tlen[p] - 400)).astype(np.int64)).astype(np.uint32)
+            sc[i, :k] = rng.integers(0, 19, size=k)
+            rcs[i, :k] = rng.integers(0, 2, size=k)
+            dup = rng.integers(0, k, size=k // 3)          # the same place again, with another score / strand
+            loc[i, k:k + len(dup)] = loc[i, dup]
+            sc[i, k:k + len(dup)] = np.maximum(0, sc[i, dup] + rng.integers(-1, 2, size=len(dup)))
+            rcs[i, k:k + len(dup)] = rng.integers(0, 2, size=len(dup))
+            cnt[i] = k + len(dup)
+        for e in range(2):
+            res["location"][i, e] = int(rng.integers(600, glen)) if rng.random() < 0.9 else 0xFFFFFFFF
+            res["score"][i, e] = int(rng.integers(0, 19))
+            res["mapq"][i, e] = int(rng.integers(0, 71))
+            res["direction"][i, e] = int(rng.integers(0, 2))
+    n_lists = n_entries = n_transcriptome = 0
+    for i in range(b0.n):
+        cw, cg = np.zeros(2, np.uint32), np.zeros(2, np.uint32)
+        rw, rg = np.zeros((2, cap, 7), np.uint32), np.zeros((2, cap, 7), np.uint32)
+        keys = C.create_string_buffer(1 << 16)
+        rc = lib.ref_filter_alignments(hg, ht, g, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(i), C.c_uint(15), C.c_uint(mh), A.p32i(n0), A.p32u(l0),
+                                       A.p8(r0), A.p32i(s0), A.p32i(n1), A.p32u(l1), A.p8(r1), A.p32i(s1), res.ctypes.data_as(C.c_void_p), C.c_uint(cap),
+                                       A.p32u(cw), A.p32u(rw), keys, C.c_uint(1 << 16))
+        assert rc == 0
+        rc = hs.hostsim_filter_alignments(C.byref(T), C.c_uint(int(lens0[i])), C.c_uint(int(lens1[i])), C.c_uint(15), C.c_int(int(n0[i])), A.p32u(l0[i]),
+                                          A.p8(r0[i]), A.p32i(s0[i]), C.c_int(int(n1[i])), A.p32u(l1[i]), A.p8(r1[i]), A.p32i(s1[i]),
+                                          C.c_void_p(res[i:i + 1].ctypes.data), C.c_uint(cap), A.p32u(cg), A.p32u(rg))
+        assert rc == 0
+        assert np.array_equal(cw, cg), (i, cw, cg)
+        for e in range(2):
+            assert np.array_equal(rw[e, :cw[e]], rg[e, :cg[e]]), (i, e, rw[e, :cw[e]], rg[e, :cg[e]])
+            n_lists += 1
+            n_entries += int(cw[e])
+            n_transcriptome += int(rw[e, :cw[e], 6].sum())
+    assert n_entries > 4 * n_lists and n_transcriptome > 3000  # lists with many entries, transcriptome alignments among them

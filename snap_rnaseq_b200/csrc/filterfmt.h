@@ -26,6 +26,8 @@ struct FltTables {
     // transcripts: chromosome (as a genome piece index), gene, end, and their features in GTFTranscript::exons order
     const int32_t *t_chr, *t_gene; const uint32_t *t_end; const uint32_t *t_feat_first;  // [n_transcripts + 1]
     const uint32_t *f_type, *f_start, *f_end;
+    // genes: chromosome (genome piece index) and extent
+    const int32_t *g_chr; const uint32_t *g_start, *g_end;
 };
 
 struct FltAln {  // class Alignment, SNAPLib/AlignmentFilter.h:41-69, with names as indices
@@ -147,4 +149,239 @@ FLT_HD uint32_t flt_insert(const FltTables &t, FltAln *list, uint32_t n, const F
     for (uint32_t k = n; k > lo; k--) list[k] = list[k - 1];
     list[lo] = a;
     return n + 1;
+}
+
+// ---- AlignmentFilter::Filter: classification of every (read 0 alignment, read 1 alignment) combination and the decision ------------
+enum { FLT_NO_RC = 0, FLT_INTRAGENE = 1, FLT_INTRACHR = 2, FLT_INTERCHR = 3 };
+
+struct FltPair {  // class AlignmentPair (AlignmentFilter.cpp:62-77): align1 = read 0's alignment, align2 = read 1's
+    uint32_t a1, a2;  // indices into the two lists
+    int32_t distance;
+    uint32_t score;
+    bool operator<(const FltPair &o) const { return score < o.score; }  // AlignmentFilter.cpp:95-97
+};
+
+// GTFGene::CheckBoundary with the default buffer of 1000 (SNAPLib/GTFReader.cpp:890-902); unsigned arithmetic as there
+FLT_HD bool flt_check_boundary(const FltTables &t, int gene, int chr, uint32_t pos)
+{
+    if (t.g_chr[gene] != chr) return false;
+    const uint32_t lo = t.g_start[gene] - 1000u + 1u;
+    return pos >= (lo > 1u ? lo : 1u) && pos <= t.g_end[gene] + 1000u;
+}
+
+FLT_HD FltPair flt_make_pair(const FltAln &a1, const FltAln &a2, uint32_t i1, uint32_t i2)
+{
+    FltPair p;
+    p.a1 = i1; p.a2 = i2; p.distance = 0;
+    p.score = (uint32_t)(a1.score + a2.score);
+    if (a1.direction && !a2.direction) p.distance = (int32_t)(a1.pos - a2.pos);
+    else if (!a1.direction && a2.direction) p.distance = (int32_t)(a2.pos - a1.pos);
+    return p;
+}
+
+// m1 = an alignment of read 0, m0 = an alignment of read 1 (the reference's names, AlignmentFilter.cpp:343-500)
+FLT_HD int flt_classify(const FltTables &t, const FltAln &m0, const FltAln &m1)
+{
+    if ((m0.direction != 0) == (m1.direction != 0)) return FLT_NO_RC;
+    if (m0.is_transcriptome && m1.is_transcriptome) {
+        if (m0.chr != m1.chr) return FLT_INTERCHR;
+        if (flt_check_boundary(t, m0.gene, m1.chr, m1.pos)) return FLT_INTRAGENE;
+        if (flt_check_boundary(t, m1.gene, m0.chr, m0.pos)) return FLT_INTRAGENE;
+        return FLT_INTRACHR;
+    }
+    if (m0.is_transcriptome) {
+        if (m0.chr != m1.chr) return FLT_INTERCHR;
+        return flt_check_boundary(t, m0.gene, m1.chr, m1.pos) ? FLT_INTRAGENE : FLT_INTRACHR;
+    }
+    if (m1.is_transcriptome) {
+        if (m0.chr != m1.chr) return FLT_INTERCHR;
+        return flt_check_boundary(t, m1.gene, m0.chr, m0.pos) ? FLT_INTRAGENE : FLT_INTRACHR;
+    }
+    return FLT_INTRAGENE;  // two genome alignments: "we can't be sure" (AlignmentFilter.cpp:462-464)
+}
+
+struct FltResult {  // the fields of PairedAlignmentResult the filter writes
+    uint32_t location[2], tlocation[2];
+    int32_t score[2], mapq[2];
+    uint8_t status[2], direction[2], is_transcriptome[2];
+};
+
+// ProcessPairs (AlignmentFilter.cpp:1061-1180) once pairs[0] (and pairs[1]) are the elements std::sort leaves in front.
+FLT_HD void flt_process_pairs(const FltTables &t, const FltAln *list0, const FltAln *list1, const FltPair *pairs, uint32_t n_pairs, uint32_t conf_diff,
+                              uint32_t *genome_mapq, FltResult *r)
+{
+    const FltAln *al[2] = {&list0[pairs[0].a1], &list1[pairs[0].a2]};
+    for (int e = 0; e < 2; e++) {
+        if (al[e]->is_transcriptome) {
+            r->tlocation[e] = al[e]->location;
+            r->location[e] = t.piece_begin[al[e]->chr] + al[e]->pos - 1;  // Genome::getOffsetOfPiece(rname) + pos - 1
+        } else {
+            r->tlocation[e] = 0;
+            r->location[e] = al[e]->location;
+        }
+        r->direction[e] = al[e]->direction;
+        r->score[e] = al[e]->score;
+        r->is_transcriptome[e] = al[e]->is_transcriptome;
+    }
+    if (!al[0]->is_transcriptome && !al[1]->is_transcriptome) *genome_mapq = (uint32_t)al[0]->mapq;
+    bool unique = n_pairs == 1;
+    if (!unique) unique = (uint32_t)(pairs[1].score - pairs[0].score) >= conf_diff;
+    const uint32_t mq = *genome_mapq < 70u ? *genome_mapq : 70u;
+    for (int e = 0; e < 2; e++) {
+        r->mapq[e] = unique ? (int32_t)mq : 1;
+        r->status[e] = unique ? 1 : 2;  // SingleHit : MultipleHits
+    }
+}
+
+// CheckNoRC (AlignmentFilter.cpp:1039-1059)
+FLT_HD void flt_check_no_rc(const FltAln *list0, const FltAln *list1, const FltPair *no_rc, uint32_t n, FltResult *r)
+{
+    for (uint32_t k = 0; k < n; k++) {
+        if (list0[no_rc[k].a1].chr == list1[no_rc[k].a2].chr && no_rc[k].score < (uint32_t)(r->score[0] + r->score[1])) {
+            r->status[0] = r->status[1] = 2;
+            r->mapq[0] = r->mapq[1] = 1;
+        }
+    }
+}
+
+// FindPartialMatches (AlignmentFilter.cpp:957-1037) over the CharacterizeSeeds tuples of both reads (snapb200_characterize_batch
+// layout: segment 2*read + direction, ascending (location, seed offset)).
+FLT_HD void flt_partial_locations(const uint32_t *locs, const uint16_t *offs, uint64_t lo, uint64_t hi, bool rc, uint32_t read_len, uint32_t *out, uint32_t *n)
+{
+    uint64_t k = lo;
+    while (k < hi) {
+        uint64_t e = k;
+        while (e + 1 < hi && locs[e + 1] == locs[k]) e++;
+        out[(*n)++] = rc ? locs[k] + (read_len - offs[e]) : locs[k] + offs[k];  // smallest offset of the forward map, largest of the RC map
+        k = e + 1;
+    }
+}
+
+FLT_HD bool flt_partial_match(const FltTables &t, const uint32_t *l0, uint32_t n0, const uint32_t *l1, uint32_t n1, uint32_t max_spacing)
+{
+    for (uint32_t i = 0; i < n0; i++) {
+        for (uint32_t j = 0; j < n1; j++) {
+            const int p0 = flt_piece_at(t.piece_begin, (int)t.n_pieces, l0[i]), p1 = flt_piece_at(t.piece_begin, (int)t.n_pieces, l1[j]);
+            if (p0 != p1) continue;
+            const int pos0 = (int)(l0[i] - t.piece_begin[p0] + 1), pos1 = (int)(l1[j] - t.piece_begin[p1] + 1);
+            const uint32_t d = (uint32_t)(pos1 > pos0 ? pos1 - pos0 : pos0 - pos1);
+            if (d < max_spacing) return true;
+        }
+    }
+    return false;
+}
+
+// ---- std::sort as libstdc++ implements it (bits/stl_algo.h: introsort, threshold 16, median of three, final insertion sort) -----
+// ProcessPairs sorts the pairs by score alone and takes the first two, so WHICH of several equal-scored pairs ends up in front is
+// decided by this algorithm; the device version has to run the same one.  Mirrors GCC >= 4.9 (the toolchain the oracle is built with).
+FLT_HD void flt_swap(FltPair &a, FltPair &b) { const FltPair t = a; a = b; b = t; }
+
+FLT_HD void flt_adjust_heap(FltPair *first, long hole, long len, FltPair value)
+{
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (first[child] < first[child - 1]) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;  // __push_heap
+    while (hole > top && first[parent] < value) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+FLT_HD void flt_heap_sort(FltPair *first, long len)  // __partial_sort(first, last, last): make_heap + sort_heap
+{
+    if (len >= 2) {
+        for (long parent = (len - 2) / 2;; parent--) {
+            flt_adjust_heap(first, parent, len, first[parent]);
+            if (parent == 0) break;
+        }
+    }
+    for (long last = len; last > 1;) {
+        --last;
+        const FltPair value = first[last];
+        first[last] = first[0];
+        flt_adjust_heap(first, 0, last, value);
+    }
+}
+
+FLT_HD void flt_unguarded_linear_insert(FltPair *last)
+{
+    const FltPair val = *last;
+    FltPair *next = last - 1;
+    while (val < *next) { *last = *next; last = next; --next; }
+    *last = val;
+}
+
+FLT_HD void flt_insertion_sort(FltPair *first, FltPair *last)
+{
+    if (first == last) return;
+    for (FltPair *i = first + 1; i != last; ++i) {
+        if (*i < *first) {
+            const FltPair val = *i;
+            for (FltPair *p = i; p != first; --p) *p = *(p - 1);
+            *first = val;
+        } else {
+            flt_unguarded_linear_insert(i);
+        }
+    }
+}
+
+FLT_HD void flt_sort_pairs(FltPair *first, long n)
+{
+    if (n <= 0) return;
+    // __introsort_loop with an explicit stack of (begin, end, depth) instead of the recursion on the right part
+    long stack_b[64], stack_e[64];
+    int stack_d[64], sp = 0;
+    int depth = 0;
+    for (long k = n; k > 1; k >>= 1) depth++;  // __lg(n)
+    depth *= 2;
+    long b = 0, e = n;
+    for (;;) {
+        while (e - b > 16) {
+            if (depth == 0) { flt_heap_sort(first + b, e - b); break; }
+            --depth;
+            // __unguarded_partition_pivot
+            const long mid = b + (e - b) / 2;
+            FltPair &r = first[b], &x = first[b + 1], &y = first[mid], &z = first[e - 1];
+            if (x < y) { if (y < z) flt_swap(r, y); else if (x < z) flt_swap(r, z); else flt_swap(r, x); }
+            else if (x < z) flt_swap(r, x);
+            else if (y < z) flt_swap(r, z);
+            else flt_swap(r, y);
+            long lo = b + 1, hi = e;
+            for (;;) {
+                while (first[lo] < first[b]) ++lo;
+                --hi;
+                while (first[b] < first[hi]) --hi;
+                if (!(lo < hi)) break;
+                flt_swap(first[lo], first[hi]);
+                ++lo;
+            }
+            // recurse on [lo, e) first, as libstdc++ does, then continue with [b, lo): order does not change the result, the
+            // two parts are disjoint -- so the right part goes on the stack and the loop goes on with the left one
+            stack_b[sp] = lo; stack_e[sp] = e; stack_d[sp] = depth; sp++;
+            e = lo;
+        }
+        if (sp == 0) break;
+        sp--;
+        b = stack_b[sp]; e = stack_e[sp]; depth = stack_d[sp];
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        flt_insertion_sort(first, first + 16);
+        for (FltPair *i = first + 16; i != first + n; ++i) flt_unguarded_linear_insert(i);
+    } else {
+        flt_insertion_sort(first, first + n);
+    }
 }

@@ -154,3 +154,95 @@ extern "C" int hostsim_filter_alignments(const FltTables *t, uint32_t len0, uint
     }
     return 0;
 }
+
+// AlignmentFilter::Filter for one pair on the host: lists as above, every combination classified in the reference's loop order,
+// flt_sort_pairs (the mirror of libstdc++'s std::sort, checked against std::sort below) for ProcessPairs.
+#include <algorithm>
+extern "C" int hostsim_filter_pair(const FltTables *t, uint32_t len0, uint32_t len1, uint32_t max_dist, uint32_t max_spacing, uint32_t conf_diff,
+                                   int force_spacing, int n0, const uint32_t *l0, const uint8_t *rc0, const int32_t *sc0, int n1, const uint32_t *l1,
+                                   const uint8_t *rc1, const int32_t *sc1, const snapb200_paired_result *g, const uint64_t *seg0, const uint32_t *clocs0,
+                                   const uint16_t *coffs0, const uint64_t *seg1, const uint32_t *clocs1, const uint16_t *coffs1, uint32_t pair_index,
+                                   FltResult *out)
+{
+    const uint32_t cap = 2048;
+    std::vector<FltAln> lists[2];
+    lists[0].resize(cap + 1);
+    lists[1].resize(cap + 1);
+    uint32_t n[2] = {0, 0};
+    FltAln a;
+    for (int k = 0; k < n0; k++) if (flt_make_alignment(*t, l0[k], rc0[k] ? 1 : 0, sc0[k], 0, true, len0, max_dist, &a)) n[0] = flt_insert(*t, lists[0].data(), n[0], a);
+    for (int k = 0; k < n1; k++) if (flt_make_alignment(*t, l1[k], rc1[k] ? 1 : 0, sc1[k], 0, true, len1, max_dist, &a)) n[1] = flt_insert(*t, lists[1].data(), n[1], a);
+    const uint32_t lens[2] = {len0, len1};
+    for (int e = 0; e < 2; e++)
+        if (flt_make_alignment(*t, g->location[e], g->direction[e], g->score[e], g->mapq[e], false, lens[e], max_dist, &a)) n[e] = flt_insert(*t, lists[e].data(), n[e], a);
+    std::vector<FltPair> cls[4];
+    for (uint32_t j = 0; j < n[1]; j++)        // the reference's outer loop runs over its `mate0` map = read 1's alignments
+        for (uint32_t i = 0; i < n[0]; i++)
+            cls[flt_classify(*t, lists[1][j], lists[0][i])].push_back(flt_make_pair(lists[0][i], lists[1][j], i, j));
+    FltResult r;
+    memset(&r, 0, sizeof(r));
+    for (int e = 0; e < 2; e++) {  // what the run loop hands in (PairedAligner.cpp:575-578, 620)
+        r.location[e] = g->location[e]; r.score[e] = g->score[e]; r.mapq[e] = g->mapq[e]; r.status[e] = g->status[e]; r.direction[e] = g->direction[e];
+    }
+    uint32_t genome_mapq = 70;
+    auto partial = [&]() {
+        std::vector<uint32_t> p0(1 << 16), p1(1 << 16);
+        uint32_t c0 = 0, c1 = 0;
+        const uint64_t s = 2ull * pair_index;  // snapb200_characterize_batch layout: segment 2 * read + direction
+        flt_partial_locations(clocs0, coffs0, seg0[s], seg0[s + 1], false, len0, p0.data(), &c0);
+        flt_partial_locations(clocs0, coffs0, seg0[s + 1], seg0[s + 2], true, len0, p0.data(), &c0);
+        flt_partial_locations(clocs1, coffs1, seg1[s], seg1[s + 1], false, len1, p1.data(), &c1);
+        flt_partial_locations(clocs1, coffs1, seg1[s + 1], seg1[s + 2], true, len1, p1.data(), &c1);
+        if (flt_partial_match(*t, p0.data(), c0, p1.data(), c1, max_spacing)) { r.status[0] = r.status[1] = 2; r.mapq[0] = r.mapq[1] = 1; }
+    };
+    auto process = [&](std::vector<FltPair> &v) {
+        if (v.size() > 1) flt_sort_pairs(v.data(), (long)v.size());
+        flt_process_pairs(*t, lists[0].data(), lists[1].data(), v.data(), (uint32_t)v.size(), conf_diff, &genome_mapq, &r);
+    };
+    if (!cls[FLT_INTRAGENE].empty()) {
+        process(cls[FLT_INTRAGENE]);
+    } else if (!cls[FLT_INTRACHR].empty()) {
+        process(cls[FLT_INTRACHR]);
+        if (r.status[0] == 1) flt_check_no_rc(lists[0].data(), lists[1].data(), cls[FLT_NO_RC].data(), (uint32_t)cls[FLT_NO_RC].size(), &r);
+        if (!((uint32_t)cls[FLT_INTRACHR][0].distance <= max_spacing)) {
+            if (r.status[0] == 1) partial();
+        }
+    } else if (!cls[FLT_INTERCHR].empty()) {
+        process(cls[FLT_INTERCHR]);
+        if (r.status[0] == 1) flt_check_no_rc(lists[0].data(), lists[1].data(), cls[FLT_NO_RC].data(), (uint32_t)cls[FLT_NO_RC].size(), &r);
+        if (r.status[0] == 1) partial();
+    } else if (!cls[FLT_NO_RC].empty()) {
+        process(cls[FLT_NO_RC]);
+        if (r.status[0] == 1) partial();
+    } else {
+        memset(&r, 0, sizeof(r));  // NotFound, location 0 (not InvalidGenomeLocation), FORWARD (AlignmentFilter.cpp:717-735)
+    }
+    const bool one0 = r.status[0] == 1, one1 = r.status[1] == 1;  // isOneLocation: SingleHit (CertainHit does not occur here)
+    if (force_spacing && one0 != one1) { r.status[0] = r.status[1] = 0; r.location[0] = r.location[1] = 0xffffffffu; }
+    if (r.score[0] + r.score[1] >= 5) {  // "cheese", PairedAligner.cpp:653-663
+        if (r.mapq[0] < 50) r.mapq[0] /= 2;
+        if (r.mapq[1] < 50) r.mapq[1] /= 2;
+    }
+    for (int e = 0; e < 2; e++) if (!r.is_transcriptome[e]) r.tlocation[e] = 0;
+    *out = r;
+    return 0;
+}
+
+
+// flt_sort_pairs against std::sort on the same sequence of scores: the permutations must be identical, ties included
+extern "C" int hostsim_sort_check(const uint32_t *scores, uint32_t n, uint32_t *mine, uint32_t *theirs)
+{
+    std::vector<FltPair> a(n & 0x7fffffffu), b(n & 0x7fffffffu);
+    for (uint32_t i = 0; i < (n & 0x7fffffffu); i++) { a[i].a1 = i; a[i].a2 = 0; a[i].distance = 0; a[i].score = scores[i]; b[i] = a[i]; }
+    if (n & 0x80000000u) {  // high bit: the heapsort fallback of introsort alone, against std::partial_sort(first, last, last)
+        n &= 0x7fffffffu;
+        a.resize(n); b.resize(n);
+        flt_heap_sort(a.data(), (long)n);
+        std::partial_sort(b.begin(), b.end(), b.end());
+    } else {
+        flt_sort_pairs(a.data(), (long)n);
+        std::sort(b.begin(), b.end());
+    }
+    for (uint32_t i = 0; i < n; i++) { mine[i] = a[i].a1; theirs[i] = b[i].a1; }
+    return 0;
+}

@@ -58,7 +58,7 @@ class FltTables(C.Structure):
                 ("tpiece_begin", C.POINTER(C.c_uint32)), ("n_tpieces", C.c_uint32), ("tpiece_transcript", C.POINTER(C.c_int32)),
                 ("t_chr", C.POINTER(C.c_int32)), ("t_gene", C.POINTER(C.c_int32)), ("t_end", C.POINTER(C.c_uint32)),
                 ("t_feat_first", C.POINTER(C.c_uint32)), ("f_type", C.POINTER(C.c_uint32)), ("f_start", C.POINTER(C.c_uint32)),
-                ("f_end", C.POINTER(C.c_uint32))]
+                ("f_end", C.POINTER(C.c_uint32)), ("g_chr", C.POINTER(C.c_int32)), ("g_start", C.POINTER(C.c_uint32)), ("g_end", C.POINTER(C.c_uint32))]
 
 
 def genome_pieces(index_dir):
@@ -105,6 +105,10 @@ def flat_tables(export_path, gdir, tdir):
     T.t_chr, T.t_gene, T.t_end = A.p32i(keep["t_chr"]), A.p32i(keep["t_gene"]), A.p32u(keep["t_end"])
     T.t_feat_first = A.p32u(first)
     T.f_type, T.f_start, T.f_end = A.p32u(keep["f_type"]), A.p32u(keep["f_start"]), A.p32u(keep["f_end"])
+    keep["g_chr"] = np.array([chr_names.index(genes[g][0]) for g in g_ids], np.int32)
+    keep["g_start"] = np.array([genes[g][1] for g in g_ids], np.uint32)
+    keep["g_end"] = np.array([genes[g][2] for g in g_ids], np.uint32)
+    T.g_chr, T.g_start, T.g_end = A.p32i(keep["g_chr"]), A.p32u(keep["g_start"]), A.p32u(keep["g_end"])
     return T, keep
 
 
@@ -176,3 +180,76 @@ def test_alignment_lists_match_the_reference(ref, tmp_path):
             n_entries += int(cw[e])
             n_transcriptome += int(rw[e, :cw[e], 6].sum())
     assert n_entries > 4 * n_lists and n_transcriptome > 3000  # lists with many entries, transcriptome alignments among them
+
+
+FLT_RESULT = np.dtype([("location", "<u4", (2,)), ("tlocation", "<u4", (2,)), ("score", "<i4", (2,)), ("mapq", "<i4", (2,)),
+                       ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,))], align=True)
+
+
+def test_filter_decision_matches_the_reference(ref, golden_filter, tmp_path):
+    """The whole per-pair decision (classification of every combination, ProcessPairs, CheckNoRC, FindPartialMatches, forceSpacing,
+    the MAPQ halving) from the flat-table functions against the golden records of the reference's AlignmentFilter, 1500 pairs."""
+    import subprocess
+    from oracle import oracle as O
+    from snap_rnaseq_b200 import _abi as A
+    d = str(tmp_path)
+    contigs = F.build_workspace(d, O.REF_BIN)
+    (b0, b1), sam_reads = F.reads(contigs, d)
+    hg, ht = ref.load_index(os.path.join(d, "gidx")), ref.load_index(os.path.join(d, "tidx"))
+    hits, genome_res, pp = F.alignments(ref, hg, ht, b0, b1)
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "dec").encode()))
+    assert lib.ref_gtf_export(g, os.path.join(d, "gtf.tsv").encode()) == 0
+    T, keep = flat_tables(os.path.join(d, "gtf.tsv"), os.path.join(d, "gidx"), os.path.join(d, "tidx"))
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    # the partialAligner's CharacterizeSeeds (PairedAligner.cpp:518-527: maxHits 300, 12 seeds)
+    cp = A.single_defaults(max_hits=300, num_seeds=12)
+    ch = [ref.characterize(hg, cp, b) for b in (b0, b1)]
+    (n0, l0, r0, s0), (n1, l1, r1, s1) = hits
+    res = np.ascontiguousarray(genome_res, A.PAIRED_RESULT)
+    lens0, lens1 = np.diff(b0.offsets), np.diff(b1.offsets)
+    out = np.zeros(b0.n, FLT_RESULT)
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+    p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+    for i in range(b0.n):
+        rc = hs.hostsim_filter_pair(C.byref(T), C.c_uint(int(lens0[i])), C.c_uint(int(lens1[i])), C.c_uint(15), C.c_uint(pp.max_spacing), C.c_uint(2),
+                                    C.c_int(int(pp.force_spacing)), C.c_int(int(n0[i])), A.p32u(l0[i]), A.p8(r0[i]), A.p32i(s0[i]), C.c_int(int(n1[i])),
+                                    A.p32u(l1[i]), A.p8(r1[i]), A.p32i(s1[i]), C.c_void_p(res[i:i + 1].ctypes.data), p64(ch[0][0]), A.p32u(ch[0][1]),
+                                    p16(ch[0][2]), p64(ch[1][0]), A.p32u(ch[1][1]), p16(ch[1][2]), C.c_uint(i), C.c_void_p(out[i:i + 1].ctypes.data))
+        assert rc == 0
+    want = golden_filter["result"]
+    bad = [i for i in range(b0.n) if any(not np.array_equal(want[f][i], out[f][i]) for f in FLT_RESULT.names)]
+    assert not bad, (len(bad), bad[:10], [(want[i], out[i]) for i in bad[:3]])
+
+
+def test_sort_mirror_is_std_sort(tmp_path):
+    """ProcessPairs takes pairs[0] and pairs[1] after std::sort on the score alone: the mirror of libstdc++'s introsort in
+    filterfmt.h must leave every element where std::sort leaves it, for short and long sequences, with few and many ties, sorted,
+    reversed and organ-pipe inputs (the shapes that drive the median-of-three and the depth limit)."""
+    import subprocess
+    from snap_rnaseq_b200 import _abi as A
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    rng = np.random.default_rng(4)
+    cases = []
+    for n in list(range(1, 40)) + [63, 64, 65, 100, 257, 1000, 4096, 20000]:
+        for hi in (1, 2, 3, 10, 31, 1000):
+            cases.append(rng.integers(0, hi, size=n).astype(np.uint32))
+        cases.append(np.arange(n, dtype=np.uint32))
+        cases.append(np.arange(n, dtype=np.uint32)[::-1].copy())
+        cases.append(np.minimum(np.arange(n), np.arange(n)[::-1]).astype(np.uint32))
+        cases.append((np.arange(n) // 3).astype(np.uint32))
+    for sc in cases:
+        mine, theirs = np.zeros(sc.size, np.uint32), np.zeros(sc.size, np.uint32)
+        hs.hostsim_sort_check(A.p32u(sc), C.c_uint(sc.size), A.p32u(mine), A.p32u(theirs))
+        assert np.array_equal(mine, theirs), (sc.size, sc[:20])
+        assert np.all(np.diff(sc[mine].astype(np.int64)) >= 0)
+        # the depth-limit fallback (heapsort) is not reached by these inputs inside std::sort, so it is compared on its own
+        hs.hostsim_sort_check(A.p32u(sc), C.c_uint(sc.size | 0x80000000), A.p32u(mine), A.p32u(theirs))
+        assert np.array_equal(mine, theirs), ("heap", sc.size, sc[:20])

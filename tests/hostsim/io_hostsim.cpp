@@ -246,3 +246,23 @@ extern "C" int hostsim_sort_check(const uint32_t *scores, uint32_t n, uint32_t *
     for (uint32_t i = 0; i < n; i++) { mine[i] = a[i].a1; theirs[i] = b[i].a1; }
     return 0;
 }
+
+// The annotation loader (gtf_tables.h) written out in the format of oracle/ref_driver.cpp::ref_gtf_export, for a byte comparison
+#include "../../snap_rnaseq_b200/csrc/gtf_tables.h"
+#include <stdio.h>
+extern "C" int hostsim_gtf_export(const char *gtf_path, const char *out_path)
+{
+    GtfTables t;
+    if (!gtf_load_tables(gtf_path, &t)) return -1;
+    FILE *f = fopen(out_path, "w");
+    if (!f) return -2;
+    for (size_t i = 0; i < t.transcripts.size(); i++) {
+        const GtfTranscriptRow &r = t.transcripts[i];
+        fprintf(f, "T\t%s\t%s\t%s\t%u\t%u\t%u", r.id.c_str(), r.chr.c_str(), r.gene_id.c_str(), r.start, r.end, (unsigned)r.features.size());
+        for (size_t k = 0; k < r.features.size(); k++) fprintf(f, "\t%u\t%u\t%u", r.features[k].type, r.features[k].start, r.features[k].end);
+        fprintf(f, "\n");
+    }
+    for (size_t i = 0; i < t.genes.size(); i++) fprintf(f, "G\t%s\t%s\t%u\t%u\n", t.genes[i].id.c_str(), t.genes[i].chr.c_str(), t.genes[i].start, t.genes[i].end);
+    fclose(f);
+    return 0;
+}

@@ -253,3 +253,75 @@ def test_sort_mirror_is_std_sort(tmp_path):
         # the depth-limit fallback (heapsort) is not reached by these inputs inside std::sort, so it is compared on its own
         hs.hostsim_sort_check(A.p32u(sc), C.c_uint(sc.size | 0x80000000), A.p32u(mine), A.p32u(theirs))
         assert np.array_equal(mine, theirs), ("heap", sc.size, sc[:20])
+
+
+def random_gtf(rng, path):
+    """Annotations with what the loader's quirks react to: several isoforms per gene sharing exons, lines in any order, single-exon
+    transcripts as the first or a later line of their gene, non-exon features, comments, GFF3-style Parent, attributes in any order,
+    doubled spaces and a single quote inside an attribute (the reference splits fields at tabs AND single quotes)."""
+    lines = ["# a comment line"]
+    for gi in range(int(rng.integers(3, 12))):
+        chrom = f"chr{int(rng.integers(1, 4))}"
+        gene = f"G{gi:03d}" if rng.random() < 0.9 else f"G{gi:03d}x"
+        base = int(rng.integers(1000, 100000))
+        exons = []
+        p = base
+        for _ in range(int(rng.integers(1, 7))):
+            ln = int(rng.integers(50, 400))
+            exons.append((p, p + ln - 1))
+            p += ln + int(rng.integers(50, 900))
+        glines = []
+        for ti in range(int(rng.integers(1, 4))):
+            tid = f"{gene}.t{ti}"
+            k = int(rng.integers(1, len(exons) + 1))
+            chosen = sorted(rng.choice(len(exons), size=k, replace=False))
+            for e in chosen:
+                s, en = exons[e]
+                if rng.random() < 0.15:
+                    en += int(rng.integers(1, 30))       # an isoform-specific exon end: another feature key
+                style = rng.random()
+                if style < 0.6:
+                    attr = f'gene_id "{gene}"; transcript_id "{tid}"; gene_name "{gene}n"; transcript_name "{tid}n";'
+                elif style < 0.8:
+                    attr = f'transcript_id "{tid}"; gene_id "{gene}";'
+                elif style < 0.9:
+                    attr = f'Parent={gene};transcript_id={tid};'
+                else:
+                    attr = f'gene_id "{gene}";'                  # no transcript id: the gene id stands in
+                glines.append("\t".join([chrom, "src", "exon", str(s), str(en), ".", "+-"[int(rng.integers(0, 2))], ".", attr]))
+            if rng.random() < 0.3:
+                glines.append("\t".join([chrom, "src", "CDS", str(exons[0][0]), str(exons[0][1]), ".", "+", "0", f'gene_id "{gene}"; transcript_id "{tid}";']))
+        if rng.random() < 0.5:
+            rng.shuffle(glines)
+        lines += glines
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def test_annotation_tables_match_the_reference(ref, tmp_path):
+    """gtf_tables.h (the loader the device filter will use) against the reference's GTFReader, through the same text export: the
+    annotation of the test workspace and 40 random ones."""
+    import subprocess
+    from oracle import oracle as O
+    d = str(tmp_path)
+    F.build_workspace(d, O.REF_BIN)
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    rng = np.random.default_rng(21)
+    paths = [os.path.join(d, "a.gtf")]
+    for k in range(40):
+        paths.append(os.path.join(d, f"r{k}.gtf"))
+        random_gtf(rng, paths[-1])
+    n_unprocessed = 0
+    for p in paths:
+        g = C.c_void_p(lib.ref_gtf_load(p.encode(), (p + ".out").encode()))
+        assert lib.ref_gtf_export(g, (p + ".ref.tsv").encode()) == 0
+        assert hs.hostsim_gtf_export(p.encode(), (p + ".mine.tsv").encode()) == 0
+        want, got = open(p + ".ref.tsv").read(), open(p + ".mine.tsv").read()
+        assert want == got, (p, [(a, b) for a, b in zip(want.split("\n"), got.split("\n")) if a != b][:3])
+        n_unprocessed += sum(1 for ln in want.split("\n") if ln.startswith("T") and ln.split("\t")[6] == "0")
+    assert n_unprocessed > 10  # transcripts the reference never processes (empty exon lists) occur and are reproduced

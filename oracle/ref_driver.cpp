@@ -713,7 +713,41 @@ int ref_filter_alignments(void *h_genome, void *h_transcriptome, void *gtf, cons
     return 0;
 }
 
+// The host half of a device filter: the GTF statistics of a batch, replayed in input order from per-pair event records (layout of
+// FltEvent, snap_rnaseq_b200/csrc/filterfmt.h) through the reference's own public GTFReader methods -- what the shim will do once
+// the decision itself comes from the device.  transcript_ids / chr_names: the strings behind the indices.
+struct ref_flt_event { int kind, unaligned, transcript[2], chr[2]; unsigned pos_original[2], pos[2], pos_end[2]; };
+int ref_filter_replay_events(void *h_genome, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
+                             unsigned max_dist, const ref_flt_event *ev, const char *const *transcript_ids, const char *const *chr_names)
+{
+    GenomeIndex *idx = (GenomeIndex *)h_genome, *tidx = (GenomeIndex *)h_transcriptome;
+    GTFReader *g = (GTFReader *)gtf;
+    BaseAligner *partial = new BaseAligner(idx, 300, max_dist, MAX_READ_LENGTH, 12, 0.0, 2, NULL, NULL);
+    for (unsigned i = 0; i < r0->n; i++) {
+        Read read0, read1;
+        make_read(&read0, r0, i, NULL);
+        make_read(&read1, r1, i, NULL);
+        const ref_flt_event &e = ev[i];
+        if (e.unaligned) {
+            AlignmentFilter filter(&read0, &read1, idx->getGenome(), tidx->getGenome(), g, 50, 1000, 2, max_dist, idx->getSeedLength(), partial);
+            filter.UnalignedRead(e.unaligned == 1 ? &read0 : &read1, idx->getSeedLength());
+        }
+        std::string t0 = e.transcript[0] >= 0 ? transcript_ids[e.transcript[0]] : "", t1 = e.transcript[1] >= 0 ? transcript_ids[e.transcript[1]] : "";
+        std::string id(read0.getId(), read0.getIdLength());
+        if (e.kind == 1) {  // AlignmentFilter.cpp:536-541: the lengths are passed crossed, as there
+            g->IncrementReadCount(t0, e.pos_original[0], e.pos[0], read1.getDataLength(), t1, e.pos_original[1], e.pos[1], read0.getDataLength());
+        } else if (e.kind == 2) {
+            g->IntrachromosomalPair(chr_names[e.chr[0]], e.pos[0], e.pos_end[0], chr_names[e.chr[1]], e.pos[1], e.pos_end[1], id);
+        } else if (e.kind == 3) {
+            g->InterchromosomalPair(chr_names[e.chr[0]], e.pos[0], e.pos_end[0], chr_names[e.chr[1]], e.pos[1], e.pos_end[1], id);
+        }
+    }
+    partial->~BaseAligner();
+    return 0;
+}
+
 } // extern "C"
+
 
 
 

@@ -385,3 +385,17 @@ FLT_HD void flt_sort_pairs(FltPair *first, long n)
         flt_insertion_sort(first, first + n);
     }
 }
+
+// ---- what the host still has to do per pair: the GTF statistics -------------------------------------------------------------------
+// None of them feeds back into the pair's result, so the kernel reports WHAT to count and the host calls the reference's own public
+// GTFReader methods in input order (AlignmentFilter.cpp:529-713): IncrementReadCount for a unique same-gene pair,
+// IntrachromosomalPair / InterchromosomalPair for unique distant pairs, and UnalignedRead for a read without any alignment whose mate
+// has some.
+enum { FLT_EV_NONE = 0, FLT_EV_INCREMENT = 1, FLT_EV_INTRACHR = 2, FLT_EV_INTERCHR = 3 };
+struct FltEvent {
+    int32_t kind;
+    int32_t unaligned;        // 0 none, 1: UnalignedRead(read 0), 2: UnalignedRead(read 1)
+    int32_t transcript[2];    // of pairs[0].align1 / align2; -1 for a genome alignment (the reference passes "")
+    int32_t chr[2];
+    uint32_t pos_original[2], pos[2], pos_end[2];
+};

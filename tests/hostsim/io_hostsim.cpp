@@ -162,7 +162,7 @@ extern "C" int hostsim_filter_pair(const FltTables *t, uint32_t len0, uint32_t l
                                    int force_spacing, int n0, const uint32_t *l0, const uint8_t *rc0, const int32_t *sc0, int n1, const uint32_t *l1,
                                    const uint8_t *rc1, const int32_t *sc1, const snapb200_paired_result *g, const uint64_t *seg0, const uint32_t *clocs0,
                                    const uint16_t *coffs0, const uint64_t *seg1, const uint32_t *clocs1, const uint16_t *coffs1, uint32_t pair_index,
-                                   FltResult *out)
+                                   FltResult *out, FltEvent *ev)
 {
     const uint32_t cap = 2048;
     std::vector<FltAln> lists[2];
@@ -185,6 +185,17 @@ extern "C" int hostsim_filter_pair(const FltTables *t, uint32_t len0, uint32_t l
         r.location[e] = g->location[e]; r.score[e] = g->score[e]; r.mapq[e] = g->mapq[e]; r.status[e] = g->status[e]; r.direction[e] = g->direction[e];
     }
     uint32_t genome_mapq = 70;
+    memset(ev, 0, sizeof(*ev));
+    if (n[0] == 0 && n[1] != 0) ev->unaligned = 1;  // the reference's mate1 map (read 0's alignments) is empty: UnalignedRead(read0)
+    if (n[1] == 0 && n[0] != 0) ev->unaligned = 2;
+    auto event = [&](int kind, const FltPair &p) {
+        ev->kind = kind;
+        const FltAln *al[2] = {&lists[0][p.a1], &lists[1][p.a2]};
+        for (int e = 0; e < 2; e++) {
+            ev->transcript[e] = al[e]->transcript; ev->chr[e] = al[e]->chr;
+            ev->pos_original[e] = al[e]->pos_original; ev->pos[e] = al[e]->pos; ev->pos_end[e] = al[e]->pos_end;
+        }
+    };
     auto partial = [&]() {
         std::vector<uint32_t> p0(1 << 16), p1(1 << 16);
         uint32_t c0 = 0, c1 = 0;
@@ -201,19 +212,26 @@ extern "C" int hostsim_filter_pair(const FltTables *t, uint32_t len0, uint32_t l
     };
     if (!cls[FLT_INTRAGENE].empty()) {
         process(cls[FLT_INTRAGENE]);
+        if (r.status[0] == 1) event(FLT_EV_INCREMENT, cls[FLT_INTRAGENE][0]);
     } else if (!cls[FLT_INTRACHR].empty()) {
         process(cls[FLT_INTRACHR]);
         if (r.status[0] == 1) flt_check_no_rc(lists[0].data(), lists[1].data(), cls[FLT_NO_RC].data(), (uint32_t)cls[FLT_NO_RC].size(), &r);
         if (!((uint32_t)cls[FLT_INTRACHR][0].distance <= max_spacing)) {
             if (r.status[0] == 1) partial();
+            if (r.status[0] == 1) event(FLT_EV_INTRACHR, cls[FLT_INTRACHR][0]);
         }
     } else if (!cls[FLT_INTERCHR].empty()) {
         process(cls[FLT_INTERCHR]);
         if (r.status[0] == 1) flt_check_no_rc(lists[0].data(), lists[1].data(), cls[FLT_NO_RC].data(), (uint32_t)cls[FLT_NO_RC].size(), &r);
         if (r.status[0] == 1) partial();
+        if (r.status[0] == 1) event(FLT_EV_INTERCHR, cls[FLT_INTERCHR][0]);
     } else if (!cls[FLT_NO_RC].empty()) {
         process(cls[FLT_NO_RC]);
         if (r.status[0] == 1) partial();
+        if (r.status[0] == 1) {
+            const FltPair &p0 = cls[FLT_NO_RC][0];
+            event(lists[0][p0.a1].chr == lists[1][p0.a2].chr ? FLT_EV_INTRACHR : FLT_EV_INTERCHR, p0);
+        }
     } else {
         memset(&r, 0, sizeof(r));  // NotFound, location 0 (not InvalidGenomeLocation), FORWARD (AlignmentFilter.cpp:717-735)
     }

@@ -186,6 +186,10 @@ FLT_RESULT = np.dtype([("location", "<u4", (2,)), ("tlocation", "<u4", (2,)), ("
                        ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,))], align=True)
 
 
+FLT_EVENT = np.dtype([("kind", "<i4"), ("unaligned", "<i4"), ("transcript", "<i4", (2,)), ("chr", "<i4", (2,)), ("pos_original", "<u4", (2,)),
+                      ("pos", "<u4", (2,)), ("pos_end", "<u4", (2,))], align=True)
+
+
 def test_filter_decision_matches_the_reference(ref, golden_filter, tmp_path):
     """The whole per-pair decision (classification of every combination, ProcessPairs, CheckNoRC, FindPartialMatches, forceSpacing,
     the MAPQ halving) from the flat-table functions against the golden records of the reference's AlignmentFilter, 1500 pairs."""
@@ -213,17 +217,35 @@ def test_filter_decision_matches_the_reference(ref, golden_filter, tmp_path):
     res = np.ascontiguousarray(genome_res, A.PAIRED_RESULT)
     lens0, lens1 = np.diff(b0.offsets), np.diff(b1.offsets)
     out = np.zeros(b0.n, FLT_RESULT)
+    events = np.zeros(b0.n, FLT_EVENT)
     p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
     p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
     for i in range(b0.n):
         rc = hs.hostsim_filter_pair(C.byref(T), C.c_uint(int(lens0[i])), C.c_uint(int(lens1[i])), C.c_uint(15), C.c_uint(pp.max_spacing), C.c_uint(2),
                                     C.c_int(int(pp.force_spacing)), C.c_int(int(n0[i])), A.p32u(l0[i]), A.p8(r0[i]), A.p32i(s0[i]), C.c_int(int(n1[i])),
                                     A.p32u(l1[i]), A.p8(r1[i]), A.p32i(s1[i]), C.c_void_p(res[i:i + 1].ctypes.data), p64(ch[0][0]), A.p32u(ch[0][1]),
-                                    p16(ch[0][2]), p64(ch[1][0]), A.p32u(ch[1][1]), p16(ch[1][2]), C.c_uint(i), C.c_void_p(out[i:i + 1].ctypes.data))
+                                    p16(ch[0][2]), p64(ch[1][0]), A.p32u(ch[1][1]), p16(ch[1][2]), C.c_uint(i), C.c_void_p(out[i:i + 1].ctypes.data),
+                                    C.c_void_p(events[i:i + 1].ctypes.data))
         assert rc == 0
     want = golden_filter["result"]
     bad = [i for i in range(b0.n) if any(not np.array_equal(want[f][i], out[f][i]) for f in FLT_RESULT.names)]
     assert not bad, (len(bad), bad[:10], [(want[i], out[i]) for i in bad[:3]])
+    # The statistics: the per-pair event records, replayed in input order through the reference's own public GTFReader methods on a
+    # fresh GTFReader (what the shim does once the decision comes from the device), must leave the files the reference's filter leaves.
+    assert (events["kind"] == 1).sum() > 300 and (events["kind"] >= 2).sum() > 5 and (events["unaligned"] > 0).sum() > 20
+    g2 = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "replay").encode()))
+    t_ids = [ln.split("\t")[1] for ln in open(os.path.join(d, "gtf.tsv")) if ln.startswith("T")]
+    chr_names, _ = genome_pieces(os.path.join(d, "gidx"))
+    arr = lambda names: (C.c_char_p * len(names))(*[n.encode() for n in names])
+    rc = lib.ref_filter_replay_events(hg, ht, g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(events.ctypes.data), arr(t_ids),
+                                      arr(chr_names))
+    assert rc == 0
+    lib.ref_gtf_finish(g2)
+    produced = sorted(f for f in os.listdir(d) if f.startswith("replay"))
+    assert len(produced) >= 8
+    for f in produced:
+        key = "file_" + (f[len("replay"):].strip("._") or "main")
+        assert open(os.path.join(d, f), "rb").read() == golden_filter[key].tobytes(), f
 
 
 def test_sort_mirror_is_std_sort(tmp_path):

@@ -158,6 +158,9 @@ struct FltPair {  // class AlignmentPair (AlignmentFilter.cpp:62-77): align1 = r
     uint32_t a1, a2;  // indices into the two lists
     int32_t distance;
     uint32_t score;
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
     bool operator<(const FltPair &o) const { return score < o.score; }  // AlignmentFilter.cpp:95-97
 };
 
@@ -399,3 +402,123 @@ struct FltEvent {
     int32_t chr[2];
     uint32_t pos_original[2], pos[2], pos_end[2];
 };
+
+// ---- the whole per-pair filter as one function over caller-provided scratch (no allocation, no recursion): what a kernel runs -------
+struct FltParams { uint32_t max_dist, max_spacing, conf_diff; int32_t force_spacing; };
+
+struct FltPairInput {
+    uint32_t len[2];                       // data length of read 0 / read 1
+    int32_t n_hits[2];                     // transcriptome multi-hits of each read (snapb200_single_multihit_batch)
+    const uint32_t *hit_loc[2];
+    const uint8_t *hit_rc[2];
+    const int32_t *hit_score[2];
+    uint32_t g_location[2];                // the genome pair (snapb200_paired_batch)
+    int32_t g_score[2], g_mapq[2];
+    uint8_t g_status[2], g_direction[2];
+    const uint32_t *ch_loc[2];             // CharacterizeSeeds tuples of each read (snapb200_characterize_batch): locations, seed offsets,
+    const uint16_t *ch_off[2];
+    uint64_t ch_range[2][3];               // and the bounds of the forward and RC segment: [fwd begin, fwd end = rc begin, rc end)
+};
+
+struct FltScratch {
+    FltAln *list[2]; uint32_t list_cap;    // room for list_cap + 1 entries each
+    FltPair *pairs; uint32_t pair_cap;
+    uint32_t *ploc[2]; uint32_t ploc_cap;
+};
+
+enum { FLT_OK = 0, FLT_SCRATCH_TOO_SMALL = 1 };
+
+FLT_HD int flt_filter_pair(const FltTables &t, const FltParams &prm, const FltPairInput &in, const FltScratch &sc, FltResult *out, FltEvent *ev)
+{
+    uint32_t n[2] = {0, 0};
+    FltAln a;
+    for (int e = 0; e < 2; e++) {
+        for (int k = 0; k < in.n_hits[e]; k++) {
+            if (!flt_make_alignment(t, in.hit_loc[e][k], in.hit_rc[e][k] ? 1 : 0, in.hit_score[e][k], 0, true, in.len[e], prm.max_dist, &a)) continue;
+            if (n[e] >= sc.list_cap) return FLT_SCRATCH_TOO_SMALL;
+            n[e] = flt_insert(t, sc.list[e], n[e], a);
+        }
+    }
+    for (int e = 0; e < 2; e++) {
+        if (!flt_make_alignment(t, in.g_location[e], in.g_direction[e], in.g_score[e], in.g_mapq[e], false, in.len[e], prm.max_dist, &a)) continue;
+        if (n[e] >= sc.list_cap) return FLT_SCRATCH_TOO_SMALL;
+        n[e] = flt_insert(t, sc.list[e], n[e], a);
+    }
+    const FltAln *l0 = sc.list[0], *l1 = sc.list[1];
+    FltResult r;
+    for (int e = 0; e < 2; e++) {
+        r.location[e] = in.g_location[e]; r.tlocation[e] = 0; r.score[e] = in.g_score[e]; r.mapq[e] = in.g_mapq[e];
+        r.status[e] = in.g_status[e]; r.direction[e] = in.g_direction[e]; r.is_transcriptome[e] = 0;
+    }
+    ev->kind = FLT_EV_NONE;
+    ev->unaligned = (n[0] == 0 && n[1] != 0) ? 1 : (n[1] == 0 && n[0] != 0) ? 2 : 0;
+    for (int e = 0; e < 2; e++) { ev->transcript[e] = -1; ev->chr[e] = 0; ev->pos_original[e] = ev->pos[e] = ev->pos_end[e] = 0; }
+    // which class decides: the first non-empty one in the order intragene, intrachromosomal, interchromosomal, no_rc
+    uint32_t count[4] = {0, 0, 0, 0};
+    for (uint32_t j = 0; j < n[1]; j++)
+        for (uint32_t i = 0; i < n[0]; i++) count[flt_classify(t, l1[j], l0[i])]++;
+    const int order[4] = {FLT_INTRAGENE, FLT_INTRACHR, FLT_INTERCHR, FLT_NO_RC};
+    int chosen = -1;
+    for (int k = 0; k < 4 && chosen < 0; k++) if (count[order[k]]) chosen = order[k];
+    if (chosen < 0) {
+        for (int e = 0; e < 2; e++) { r.location[e] = 0; r.tlocation[e] = 0; r.score[e] = 0; r.mapq[e] = 0; r.status[e] = 0; r.direction[e] = 0; r.is_transcriptome[e] = 0; }
+    } else {
+        if (count[chosen] > sc.pair_cap) return FLT_SCRATCH_TOO_SMALL;
+        uint32_t np = 0;
+        for (uint32_t j = 0; j < n[1]; j++)  // the reference's loop order: its outer map holds read 1's alignments
+            for (uint32_t i = 0; i < n[0]; i++)
+                if (flt_classify(t, l1[j], l0[i]) == chosen) sc.pairs[np++] = flt_make_pair(l0[i], l1[j], i, j);
+        if (np > 1) flt_sort_pairs(sc.pairs, (long)np);
+        uint32_t genome_mapq = 70;
+        flt_process_pairs(t, l0, l1, sc.pairs, np, prm.conf_diff, &genome_mapq, &r);
+        const FltPair p0 = sc.pairs[0];
+        bool report = false;
+        int kind = FLT_EV_NONE;
+        if (chosen == FLT_INTRAGENE) {
+            report = r.status[0] == 1;
+            kind = FLT_EV_INCREMENT;
+        } else {
+            if (chosen != FLT_NO_RC && r.status[0] == 1 && count[FLT_NO_RC]) {  // CheckNoRC: any same-chromosome same-strand pair that scores better
+                const uint32_t sum = (uint32_t)(r.score[0] + r.score[1]);
+                bool hit = false;
+                for (uint32_t j = 0; j < n[1] && !hit; j++)
+                    for (uint32_t i = 0; i < n[0] && !hit; i++)
+                        if (flt_classify(t, l1[j], l0[i]) == FLT_NO_RC && l0[i].chr == l1[j].chr && (uint32_t)(l0[i].score + l1[j].score) < sum) hit = true;
+                if (hit) { r.status[0] = r.status[1] = 2; r.mapq[0] = r.mapq[1] = 1; }
+            }
+            const bool near = chosen == FLT_INTRACHR && (uint32_t)p0.distance <= prm.max_spacing;  // int against unsigned, as in the reference
+            if (!near) {
+                if (r.status[0] == 1) {  // FindPartialMatches
+                    uint32_t c[2] = {0, 0};
+                    for (int e = 0; e < 2; e++) {
+                        if (in.ch_range[e][2] - in.ch_range[e][0] > sc.ploc_cap) return FLT_SCRATCH_TOO_SMALL;
+                        flt_partial_locations(in.ch_loc[e], in.ch_off[e], in.ch_range[e][0], in.ch_range[e][1], false, in.len[e], sc.ploc[e], &c[e]);
+                        flt_partial_locations(in.ch_loc[e], in.ch_off[e], in.ch_range[e][1], in.ch_range[e][2], true, in.len[e], sc.ploc[e], &c[e]);
+                    }
+                    if (flt_partial_match(t, sc.ploc[0], c[0], sc.ploc[1], c[1], prm.max_spacing)) { r.status[0] = r.status[1] = 2; r.mapq[0] = r.mapq[1] = 1; }
+                }
+                report = r.status[0] == 1;
+                kind = chosen == FLT_INTRACHR ? FLT_EV_INTRACHR
+                     : chosen == FLT_INTERCHR ? FLT_EV_INTERCHR
+                     : (l0[p0.a1].chr == l1[p0.a2].chr ? FLT_EV_INTRACHR : FLT_EV_INTERCHR);
+            }
+        }
+        if (report) {
+            ev->kind = kind;
+            const FltAln *al[2] = {&l0[p0.a1], &l1[p0.a2]};
+            for (int e = 0; e < 2; e++) {
+                ev->transcript[e] = al[e]->transcript; ev->chr[e] = al[e]->chr;
+                ev->pos_original[e] = al[e]->pos_original; ev->pos[e] = al[e]->pos; ev->pos_end[e] = al[e]->pos_end;
+            }
+        }
+    }
+    // the run loop's epilogue (PairedAligner.cpp:646-663)
+    if (prm.force_spacing && (r.status[0] == 1) != (r.status[1] == 1)) { r.status[0] = r.status[1] = 0; r.location[0] = r.location[1] = FLT_INVALID_LOC; }
+    if (r.score[0] + r.score[1] >= 5) {
+        if (r.mapq[0] < 50) r.mapq[0] /= 2;
+        if (r.mapq[1] < 50) r.mapq[1] /= 2;
+    }
+    for (int e = 0; e < 2; e++) if (!r.is_transcriptome[e]) r.tlocation[e] = 0;
+    *out = r;
+    return FLT_OK;
+}

@@ -186,6 +186,7 @@ extern "C" int hostsim_filter_pair(const FltTables *t, uint32_t len0, uint32_t l
     }
     uint32_t genome_mapq = 70;
     memset(ev, 0, sizeof(*ev));
+    ev->transcript[0] = ev->transcript[1] = -1;
     if (n[0] == 0 && n[1] != 0) ev->unaligned = 1;  // the reference's mate1 map (read 0's alignments) is empty: UnalignedRead(read0)
     if (n[1] == 0 && n[0] != 0) ev->unaligned = 2;
     auto event = [&](int kind, const FltPair &p) {
@@ -283,4 +284,33 @@ extern "C" int hostsim_gtf_export(const char *gtf_path, const char *out_path)
     for (size_t i = 0; i < t.genes.size(); i++) fprintf(f, "G\t%s\t%s\t%u\t%u\n", t.genes[i].id.c_str(), t.genes[i].chr.c_str(), t.genes[i].start, t.genes[i].end);
     fclose(f);
     return 0;
+}
+
+
+// The same pair through flt_filter_pair: the allocation-free form a kernel will run (fixed scratch, no STL)
+extern "C" int hostsim_filter_pair_flat(const FltTables *t, uint32_t len0, uint32_t len1, uint32_t max_dist, uint32_t max_spacing, uint32_t conf_diff,
+                                        int force_spacing, int n0, const uint32_t *l0, const uint8_t *rc0, const int32_t *sc0, int n1, const uint32_t *l1,
+                                        const uint8_t *rc1, const int32_t *sc1, const snapb200_paired_result *g, const uint64_t *seg0, const uint32_t *clocs0,
+                                        const uint16_t *coffs0, const uint64_t *seg1, const uint32_t *clocs1, const uint16_t *coffs1, uint32_t pair_index,
+                                        uint32_t list_cap, uint32_t pair_cap, uint32_t ploc_cap, FltResult *out, FltEvent *ev)
+{
+    std::vector<FltAln> la(list_cap + 1), lb(list_cap + 1);
+    std::vector<FltPair> pairs(pair_cap + 1);
+    std::vector<uint32_t> pa(ploc_cap + 1), pb(ploc_cap + 1);
+    FltScratch sc;
+    sc.list[0] = la.data(); sc.list[1] = lb.data(); sc.list_cap = list_cap;
+    sc.pairs = pairs.data(); sc.pair_cap = pair_cap;
+    sc.ploc[0] = pa.data(); sc.ploc[1] = pb.data(); sc.ploc_cap = ploc_cap;
+    FltParams prm = {max_dist, max_spacing, conf_diff, force_spacing};
+    FltPairInput in;
+    in.len[0] = len0; in.len[1] = len1;
+    in.n_hits[0] = n0; in.n_hits[1] = n1;
+    in.hit_loc[0] = l0; in.hit_loc[1] = l1; in.hit_rc[0] = rc0; in.hit_rc[1] = rc1; in.hit_score[0] = sc0; in.hit_score[1] = sc1;
+    for (int e = 0; e < 2; e++) {
+        in.g_location[e] = g->location[e]; in.g_score[e] = g->score[e]; in.g_mapq[e] = g->mapq[e]; in.g_status[e] = g->status[e]; in.g_direction[e] = g->direction[e];
+    }
+    const uint64_t s = 2ull * pair_index;
+    in.ch_loc[0] = clocs0; in.ch_off[0] = coffs0; in.ch_loc[1] = clocs1; in.ch_off[1] = coffs1;
+    for (int k = 0; k < 3; k++) { in.ch_range[0][k] = seg0[s + k]; in.ch_range[1][k] = seg1[s + k]; }
+    return flt_filter_pair(*t, prm, in, sc, out, ev);
 }

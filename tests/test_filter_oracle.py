@@ -230,6 +230,22 @@ def test_filter_decision_matches_the_reference(ref, golden_filter, tmp_path):
     want = golden_filter["result"]
     bad = [i for i in range(b0.n) if any(not np.array_equal(want[f][i], out[f][i]) for f in FLT_RESULT.names)]
     assert not bad, (len(bad), bad[:10], [(want[i], out[i]) for i in bad[:3]])
+    # flt_filter_pair, the allocation-free form a kernel runs (fixed scratch, classes counted first, only the deciding class
+    # materialised and sorted): same records, same events; and it reports scratch that is too small instead of overrunning it
+    out2, events2 = np.zeros(b0.n, FLT_RESULT), np.zeros(b0.n, FLT_EVENT)
+    overflow = 0
+    for i in range(b0.n):
+        for caps in ((4, 4, 64), (2048, 1 << 16, 1 << 16)):
+            rc = hs.hostsim_filter_pair_flat(C.byref(T), C.c_uint(int(lens0[i])), C.c_uint(int(lens1[i])), C.c_uint(15), C.c_uint(pp.max_spacing), C.c_uint(2),
+                                             C.c_int(int(pp.force_spacing)), C.c_int(int(n0[i])), A.p32u(l0[i]), A.p8(r0[i]), A.p32i(s0[i]), C.c_int(int(n1[i])),
+                                             A.p32u(l1[i]), A.p8(r1[i]), A.p32i(s1[i]), C.c_void_p(res[i:i + 1].ctypes.data), p64(ch[0][0]), A.p32u(ch[0][1]),
+                                             p16(ch[0][2]), p64(ch[1][0]), A.p32u(ch[1][1]), p16(ch[1][2]), C.c_uint(i), C.c_uint(caps[0]), C.c_uint(caps[1]),
+                                             C.c_uint(caps[2]), C.c_void_p(out2[i:i + 1].ctypes.data), C.c_void_p(events2[i:i + 1].ctypes.data))
+            if rc == 0:
+                break
+            overflow += 1
+        assert rc == 0
+    assert np.array_equal(out2, out) and np.array_equal(events2, events) and overflow > 0
     # The statistics: the per-pair event records, replayed in input order through the reference's own public GTFReader methods on a
     # fresh GTFReader (what the shim does once the decision comes from the device), must leave the files the reference's filter leaves.
     assert (events["kind"] == 1).sum() > 300 and (events["kind"] >= 2).sum() > 5 and (events["unaligned"] > 0).sum() > 20
@@ -347,3 +363,24 @@ def test_annotation_tables_match_the_reference(ref, tmp_path):
         assert want == got, (p, [(a, b) for a, b in zip(want.split("\n"), got.split("\n")) if a != b][:3])
         n_unprocessed += sum(1 for ln in want.split("\n") if ln.startswith("T") and ln.split("\t")[6] == "0")
     assert n_unprocessed > 10  # transcripts the reference never processes (empty exon lists) occur and are reproduced
+
+
+def test_filter_header_compiles_for_the_device(tmp_path):
+    """filterfmt.h is host/device code: a one-thread-per-pair kernel around flt_filter_pair must cross-compile for sm_100a without a
+    single host-only call (the kernel itself is the next round's work; this keeps the header device-clean until then)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(HERE)
+    src = tmp_path / "flt_check.cu"
+    src.write_text('#include "%s"\n'
+                   'struct KArgs { FltTables t; FltParams p; const FltPairInput *in; const FltScratch *sc; FltResult *out; FltEvent *ev; int *rc; unsigned n; };\n'
+                   '__global__ void flt_kernel(KArgs a) {\n'
+                   '    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;\n'
+                   '    if (i < a.n) a.rc[i] = flt_filter_pair(a.t, a.p, a.in[i], a.sc[i], &a.out[i], &a.ev[i]);\n'
+                   '}\n' % os.path.join(root, "snap_rnaseq_b200", "csrc", "filterfmt.h"))
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-Werror", "all-warnings", "-c", str(src), "-o",
+                        str(tmp_path / "flt_check.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]

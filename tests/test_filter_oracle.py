@@ -384,3 +384,80 @@ def test_filter_header_compiles_for_the_device(tmp_path):
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-Werror", "all-warnings", "-c", str(src), "-o",
                         str(tmp_path / "flt_check.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_filter_decision_on_fabricated_hits(ref, tmp_path):
+    """The simulated reads give the filter short lists.  Here every pair gets dozens of fabricated transcriptome hits per end (scores
+    around the maxDist gate, repeats of the same place, both strands) and a genome pair anywhere, so that the classes hold hundreds
+    of combinations with many equal scores -- the regime where the string order of the maps and libstdc++'s sort decide which pair is
+    reported.  flt_filter_pair against the reference's AlignmentFilter on the same inputs, records and statistics files."""
+    import subprocess
+    from oracle import oracle as O
+    from snap_rnaseq_b200 import _abi as A
+    d = str(tmp_path)
+    contigs = F.build_workspace(d, O.REF_BIN)
+    (b0, b1), sam_reads = F.reads(contigs, d, n=500, seed=19)
+    hg, ht = ref.load_index(os.path.join(d, "gidx")), ref.load_index(os.path.join(d, "tidx"))
+    hits, genome_res, pp = F.alignments(ref, hg, ht, b0, b1)
+    res = np.ascontiguousarray(genome_res, A.PAIRED_RESULT).copy()
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "want").encode()))
+    assert lib.ref_gtf_export(g, os.path.join(d, "gtf.tsv").encode()) == 0
+    T, keep = flat_tables(os.path.join(d, "gtf.tsv"), os.path.join(d, "gidx"), os.path.join(d, "tidx"))
+    rng = np.random.default_rng(77)
+    tb = keep["tpiece_begin"].astype(np.int64)
+    tlen = np.diff(np.append(tb, tb[-1] + 3000))
+    real = np.flatnonzero(np.array([c != "chrDecoy" for c in genome_pieces(os.path.join(d, "gidx"))[0]]))
+    pb = keep["piece_begin"].astype(np.int64)
+    for i in range(b0.n):
+        few = rng.random() < 0.3  # some pairs keep one or two hits so that every class gets to decide somewhere
+        for (cnt, loc, rcs, sc) in hits:
+            k = int(rng.integers(1, 3)) if few else int(rng.integers(5, 45))
+            p = rng.integers(1, len(tb), size=k)  # not the decoy transcript
+            loc[i, :k] = (tb[p] + (rng.random(k) * np.maximum(1, tlen[p] - 300)).astype(np.int64)).astype(np.uint32)
+            sc[i, :k] = rng.integers(0, 18, size=k) if rng.random() < 0.5 else rng.integers(0, 3, size=k)
+            rcs[i, :k] = rng.integers(0, 2, size=k)
+            dup = rng.integers(0, k, size=k // 3)
+            loc[i, k:k + len(dup)] = loc[i, dup]
+            sc[i, k:k + len(dup)] = np.maximum(0, sc[i, dup] + rng.integers(-1, 2, size=len(dup)))
+            rcs[i, k:k + len(dup)] = rng.integers(0, 2, size=len(dup))
+            cnt[i] = k + len(dup)
+        for e in range(2):
+            c = int(rng.choice(real))
+            res["location"][i, e] = int(pb[c] + rng.integers(0, 150000)) if rng.random() < 0.85 else 0xFFFFFFFF
+            res["score"][i, e] = int(rng.integers(0, 18))
+            res["mapq"][i, e] = int(rng.integers(0, 71))
+            res["direction"][i, e] = int(rng.integers(0, 2))
+            res["status"][i, e] = int(rng.integers(0, 3))
+    want = F.run_reference_filter(ref, hg, ht, os.path.join(d, "a.gtf"), os.path.join(d, "want"), sam_reads, hits, res, pp)
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    ch = [ref.characterize(hg, A.single_defaults(max_hits=300, num_seeds=12), b) for b in (b0, b1)]
+    (n0, l0, r0, s0), (n1, l1, r1, s1) = hits
+    lens0, lens1 = np.diff(b0.offsets), np.diff(b1.offsets)
+    out, events = np.zeros(b0.n, FLT_RESULT), np.zeros(b0.n, FLT_EVENT)
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+    p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+    for i in range(b0.n):
+        rc = hs.hostsim_filter_pair_flat(C.byref(T), C.c_uint(int(lens0[i])), C.c_uint(int(lens1[i])), C.c_uint(15), C.c_uint(pp.max_spacing), C.c_uint(2),
+                                         C.c_int(int(pp.force_spacing)), C.c_int(int(n0[i])), A.p32u(l0[i]), A.p8(r0[i]), A.p32i(s0[i]), C.c_int(int(n1[i])),
+                                         A.p32u(l1[i]), A.p8(r1[i]), A.p32i(s1[i]), C.c_void_p(res[i:i + 1].ctypes.data), p64(ch[0][0]), A.p32u(ch[0][1]),
+                                         p16(ch[0][2]), p64(ch[1][0]), A.p32u(ch[1][1]), p16(ch[1][2]), C.c_uint(i), C.c_uint(2048), C.c_uint(1 << 16),
+                                         C.c_uint(1 << 16), C.c_void_p(out[i:i + 1].ctypes.data), C.c_void_p(events[i:i + 1].ctypes.data))
+        assert rc == 0
+    bad = [i for i in range(b0.n) if any(not np.array_equal(want[f][i], out[f][i]) for f in FLT_RESULT.names)]
+    assert not bad, (len(bad), bad[:10], [(want[i], out[i]) for i in bad[:3]])
+    kinds = np.bincount(events["kind"], minlength=4)
+    assert kinds[1] > 20 and kinds[2] > 5 and kinds[3] > 2 and (out["status"] == 2).any() and (out["is_transcriptome"] == 1).sum() > 200
+    g2 = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "replay").encode()))
+    t_ids = [ln.split("\t")[1] for ln in open(os.path.join(d, "gtf.tsv")) if ln.startswith("T")]
+    chr_names, _ = genome_pieces(os.path.join(d, "gidx"))
+    arr = lambda names: (C.c_char_p * len(names))(*[n.encode() for n in names])
+    assert lib.ref_filter_replay_events(hg, ht, g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(events.ctypes.data), arr(t_ids),
+                                        arr(chr_names)) == 0
+    lib.ref_gtf_finish(g2)
+    for f in sorted(x for x in os.listdir(d) if x.startswith("replay")):
+        assert open(os.path.join(d, f), "rb").read() == open(os.path.join(d, "want" + f[len("replay"):]), "rb").read(), f

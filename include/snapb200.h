@@ -284,6 +284,55 @@ int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads *reads0, co
  * (no copies), for the streaming roofline of these two stages. */
 int snapb200_io_last_kernel_ms(float *fastq_ms, float *sam_ms);
 
+/* ---- RNA mode: AlignmentFilter -- FIRST VERSION, see DESIGN.md section 10 -------------------------
+ * The per-pair logic (snap_rnaseq_b200/csrc/filterfmt.h) is verified on the host against the reference's AlignmentFilter; the kernel
+ * around it is one thread per pair and, at the time of writing, has not been timed.  The annotation is loaded with the reference's
+ * GTFReader semantics (csrc/gtf_tables.h). */
+typedef struct snapb200_annotation snapb200_annotation; /* exon / gene tables of a GTF in HBM, tied to a genome + transcriptome index pair */
+
+/* Replaces GTFReader::Load (SNAPLib/GTFReader.cpp:1245-1361) for what the filter reads.  Every transcriptome piece must be a
+ * transcript of the annotation and every transcript's chromosome a piece of the genome (the reference exits otherwise). */
+int snapb200_annotation_open(snapb200_index *genome, snapb200_index *transcriptome, const char *gtf_path, snapb200_annotation **out);
+void snapb200_annotation_close(snapb200_annotation *a);
+
+typedef struct {
+    uint32_t max_spacing;      /* -s max                                         */
+    uint32_t force_spacing;    /* -fs                                            */
+    uint32_t conf_diff;        /* AlignerOptions::confDiff (-c)                   */
+    uint32_t max_dist;         /* options->maxDist.start (-d)                     */
+    uint32_t max_hits_to_get;  /* row stride of the multi-hit arrays (1000, SNAPLib/PairedAligner.cpp:584) */
+} snapb200_filter_params;
+
+/* The fields of PairedAlignmentResult that leave the loop after AlignmentFilter::Filter, forceSpacing and the MAPQ halving
+ * (SNAPLib/PairedAligner.cpp:620-663). */
+typedef struct {
+    uint32_t location[2], tlocation[2];
+    int32_t score[2], mapq[2];
+    uint8_t status[2], direction[2], is_transcriptome[2], pad[2];
+} snapb200_filter_result;
+
+/* What the host still has to count for the pair, through the reference's own public GTFReader methods:
+ * kind 1 IncrementReadCount, 2 IntrachromosomalPair, 3 InterchromosomalPair with the two chosen alignments (transcript = index in
+ * transcript-id order or -1, chr = genome piece index); unaligned 1 / 2: AlignmentFilter::UnalignedRead(read 0 / read 1). */
+typedef struct {
+    int32_t kind, unaligned, transcript[2], chr[2];
+    uint32_t pos_original[2], pos[2], pos_end[2];
+} snapb200_filter_event;
+
+/* Replaces the AlignmentFilter section of PairedAlignerContext::runIterationThread (SNAPLib/PairedAligner.cpp:582-663;
+ * AlignmentFilter::AddAlignment / Filter, SNAPLib/AlignmentFilter.cpp:140-740) for a batch of n pairs.  Inputs are what the other
+ * entry points return: the transcriptome multi-hits of both reads (snapb200_single_multihit_batch: counts[n] and rows of
+ * max_hits_to_get), the genome pairs (snapb200_paired_batch) and the CharacterizeSeeds tuples of both reads
+ * (snapb200_characterize_batch with the partialAligner's parameters: seg_offsets[2n+1], locations, seed_offsets).  len0/len1: data
+ * lengths of the reads.  needs_host[i] != 0: the pair has more alignments or combinations than the device scratch holds; its
+ * result and event are not valid and the caller runs the reference's AlignmentFilter for it. */
+int snapb200_filter_paired_batch(snapb200_annotation *a, const snapb200_filter_params *params, uint32_t n, const uint32_t *len0,
+                                 const uint32_t *len1, const int32_t *n0, const uint32_t *loc0, const uint8_t *rc0, const int32_t *score0,
+                                 const int32_t *n1, const uint32_t *loc1, const uint8_t *rc1, const int32_t *score1,
+                                 const snapb200_paired_result *genome_pairs, const uint64_t *seg0, const uint32_t *ch_loc0,
+                                 const uint16_t *ch_off0, const uint64_t *seg1, const uint32_t *ch_loc1, const uint16_t *ch_off1,
+                                 snapb200_filter_result *results, snapb200_filter_event *events, uint8_t *needs_host);
+
 /* ---- building blocks exposed for known-answer tests -------------------------------------------------- */
 
 /* LandauVishkin<+1/-1>::computeEditDistance (SNAPLib/LandauVishkin.h:211-455) on explicit strings.

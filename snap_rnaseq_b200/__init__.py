@@ -83,6 +83,38 @@ class Snapb200(BatchLib):
     def stats_reset(self, h):
         self._check(self.lib.snapb200_stats_reset(h), "stats_reset")
 
+    # -- row f3: AlignmentFilter (first version) --------------------------------------------------------
+    def annotation_open(self, genome, transcriptome, gtf_path):
+        h = C.c_void_p()
+        self._check(self.lib.snapb200_annotation_open(genome, transcriptome, str(gtf_path).encode(), C.byref(h)), "annotation_open")
+        return h
+
+    def annotation_close(self, a):
+        self.lib.snapb200_annotation_close.restype = None
+        self.lib.snapb200_annotation_close(a)
+
+    def filter_paired(self, annotation, params, len0, len1, hits0, hits1, genome_pairs, ch0, ch1):
+        """snapb200_filter_paired_batch.  hits = (counts, locations[n, mh], rcs, scores) of snapb200_single_multihit_batch; ch =
+        (seg_offsets, locations, seed_offsets) of snapb200_characterize_batch -> (results, events, needs_host)."""
+        n = len(len0)
+        l0, l1 = np.ascontiguousarray(len0, np.uint32), np.ascontiguousarray(len1, np.uint32)
+        g = np.ascontiguousarray(genome_pairs, A.PAIRED_RESULT)
+        res, ev, nh = np.zeros(n, A.FILTER_RESULT), np.zeros(n, A.FILTER_EVENT), np.zeros(max(n, 1), np.uint8)
+        hs = []
+        for (cnt, loc, rcs, sc) in (hits0, hits1):
+            hs += [A.p32i(np.ascontiguousarray(cnt, np.int32)), A.p32u(np.ascontiguousarray(loc, np.uint32)), A.p8(np.ascontiguousarray(rcs, np.uint8)),
+                   A.p32i(np.ascontiguousarray(sc, np.int32))]
+        cs = []
+        keep = []
+        for (seg, locs, offs) in (ch0, ch1):
+            seg, locs, offs = np.ascontiguousarray(seg, np.uint64), np.ascontiguousarray(locs, np.uint32), np.ascontiguousarray(offs, np.uint16)
+            keep += [seg, locs, offs]
+            cs += [seg.ctypes.data_as(C.POINTER(C.c_uint64)), A.p32u(locs), offs.ctypes.data_as(C.POINTER(C.c_uint16))]
+        self._check(self.lib.snapb200_filter_paired_batch(annotation, C.byref(params), C.c_uint32(n), A.p32u(l0), A.p32u(l1), *hs,
+                                                          g.ctypes.data_as(C.c_void_p), *cs, res.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p),
+                                                          A.p8(nh)), "filter_paired_batch")
+        return res, ev, nh[:n]
+
     def device_count(self):
         return int(self.lib.snapb200_device_count())
 

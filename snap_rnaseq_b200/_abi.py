@@ -224,3 +224,16 @@ class SamReads:
                 and np.array_equal(self.quals[:self.offsets[-1]], o.quals[:o.offsets[-1]])
                 and np.array_equal(self.ids[:self.id_offsets[-1]], o.ids[:o.id_offsets[-1]])
                 and np.array_equal(self.front_clip[:n], o.front_clip[:n]) and np.array_equal(self.clipped_len[:n], o.clipped_len[:n]))
+
+
+# ---- row f3: AlignmentFilter -----------------------------------------------------------------------------------
+class FilterParams(C.Structure):
+    _fields_ = [("max_spacing", C.c_uint32), ("force_spacing", C.c_uint32), ("conf_diff", C.c_uint32), ("max_dist", C.c_uint32),
+                ("max_hits_to_get", C.c_uint32)]
+
+
+FILTER_RESULT = np.dtype([("location", "<u4", (2,)), ("tlocation", "<u4", (2,)), ("score", "<i4", (2,)), ("mapq", "<i4", (2,)),
+                          ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,)), ("pad", "u1", (2,))])
+FILTER_EVENT = np.dtype([("kind", "<i4"), ("unaligned", "<i4"), ("transcript", "<i4", (2,)), ("chr", "<i4", (2,)), ("pos_original", "<u4", (2,)),
+                         ("pos", "<u4", (2,)), ("pos_end", "<u4", (2,))])
+assert FILTER_RESULT.itemsize == 40 and FILTER_EVENT.itemsize == 48

@@ -1643,3 +1643,4 @@ extern "C" int snapb200_stats_reset(snapb200_index *idx)
 }
 
 #include "io_api.inl"
+#include "filter_api.inl"

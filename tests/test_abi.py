@@ -81,7 +81,9 @@ def test_io_struct_layouts_match_header(tmp_path):
         '#include <stdio.h>\n#include <stddef.h>\n#include "snapb200.h"\n'
         'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(snapb200_sam_reads), offsetof(snapb200_sam_reads,front_clip),'
         ' offsetof(snapb200_sam_reads,ids), sizeof(snapb200_sam_alignment), offsetof(snapb200_sam_alignment,mapq),'
-        ' offsetof(snapb200_sam_alignment,status), offsetof(snapb200_sam_alignment,skip));return 0;}\n')
+        ' offsetof(snapb200_sam_alignment,status), offsetof(snapb200_sam_alignment,skip));'
+        'printf("%zu %zu %zu %zu %zu\\n", sizeof(snapb200_filter_result), offsetof(snapb200_filter_result,status), sizeof(snapb200_filter_event),'
+        ' offsetof(snapb200_filter_event,pos), sizeof(snapb200_filter_params));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
@@ -90,6 +92,8 @@ def test_io_struct_layouts_match_header(tmp_path):
     assert got[3] == A.SAM_ALIGNMENT.itemsize
     assert got[4] == A.SAM_ALIGNMENT.fields["mapq"][1] and got[5] == A.SAM_ALIGNMENT.fields["status"][1]
     assert got[6] == A.SAM_ALIGNMENT.fields["skip"][1]
+    assert got[7] == A.FILTER_RESULT.itemsize and got[8] == A.FILTER_RESULT.fields["status"][1]
+    assert got[9] == A.FILTER_EVENT.itemsize and got[10] == A.FILTER_EVENT.fields["pos"][1] and got[11] == C.sizeof(A.FilterParams)
 
 
 def test_product_does_not_reference_the_oracle():

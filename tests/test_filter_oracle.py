@@ -461,3 +461,15 @@ def test_filter_decision_on_fabricated_hits(ref, tmp_path):
     lib.ref_gtf_finish(g2)
     for f in sorted(x for x in os.listdir(d) if x.startswith("replay")):
         assert open(os.path.join(d, f), "rb").read() == open(os.path.join(d, "want" + f[len("replay"):]), "rb").read(), f
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="snapb200_filter_paired_batch (one thread per pair around the host-verified flt_filter_pair) was written after the "
+                                        "round's GPU budget was spent: this is its first run on a device, in its own process so that a fault cannot "
+                                        "touch the other tests; it reports XPASS when the kernel reproduces the reference's AlignmentFilter")
+def test_cuda_filter_first_run():
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(HERE, "filter_gpu_check.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "FILTER_GPU_OK" in r.stdout, r.stdout[-3000:]

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SNAPB200_ABI_VERSION 1
+#define SNAPB200_ABI_VERSION 2
 
 enum {
     SNAPB200_OK = 0,
@@ -284,16 +284,23 @@ int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads *reads0, co
  * (no copies), for the streaming roofline of these two stages. */
 int snapb200_io_last_kernel_ms(float *fastq_ms, float *sam_ms);
 
-/* ---- RNA mode: AlignmentFilter -- FIRST VERSION, see DESIGN.md section 10 -------------------------
- * The per-pair logic (snap_rnaseq_b200/csrc/filterfmt.h) is verified on the host against the reference's AlignmentFilter; the kernel
- * around it is one thread per pair and, at the time of writing, has not been timed.  The annotation is loaded with the reference's
- * GTFReader semantics (csrc/gtf_tables.h). */
-typedef struct snapb200_annotation snapb200_annotation; /* exon / gene tables of a GTF in HBM, tied to a genome + transcriptome index pair */
+/* ---- RNA mode: AlignmentFilter on the device ------------------------------
+ * One warp per pair (snap_rnaseq_b200/csrc/filter_warp.cuh) over the per-element rules of csrc/filterfmt.h, which are verified on
+ * the host against the reference's AlignmentFilter.  The annotation is loaded with the reference's GTFReader semantics
+ * (csrc/gtf_tables.h). */
+typedef struct snapb200_annotation snapb200_annotation; /* exon / gene tables of a GTF in HBM, for a genome + transcriptome index pair */
 
 /* Replaces GTFReader::Load (SNAPLib/GTFReader.cpp:1245-1361) for what the filter reads.  Every transcriptome piece must be a
- * transcript of the annotation and every transcript's chromosome a piece of the genome (the reference exits otherwise). */
+ * transcript of the annotation and every transcript's chromosome a piece of the genome (the reference exits otherwise).  The handle
+ * keeps its own copies of what it needs from the two indices (piece tables, names), so it may outlive them; it lives on the genome
+ * index's device. */
 int snapb200_annotation_open(snapb200_index *genome, snapb200_index *transcriptome, const char *gtf_path, snapb200_annotation **out);
 void snapb200_annotation_close(snapb200_annotation *a);
+/* Names behind the indices of snapb200_filter_event: transcript ids in the order of the reference's transcript map (std::map by id),
+ * chromosome names = genome piece names.  NULL when out of range.  Valid until snapb200_annotation_close. */
+uint32_t snapb200_annotation_transcript_count(const snapb200_annotation *a);
+const char *snapb200_annotation_transcript_id(const snapb200_annotation *a, uint32_t index);
+const char *snapb200_annotation_chromosome(const snapb200_annotation *a, uint32_t index);
 
 typedef struct {
     uint32_t max_spacing;      /* -s max                                         */
@@ -304,11 +311,13 @@ typedef struct {
 } snapb200_filter_params;
 
 /* The fields of PairedAlignmentResult that leave the loop after AlignmentFilter::Filter, forceSpacing and the MAPQ halving
- * (SNAPLib/PairedAligner.cpp:620-663). */
+ * (SNAPLib/PairedAligner.cpp:620-663).  fromAlignTogether is always false after Filter. */
 typedef struct {
     uint32_t location[2], tlocation[2];
     int32_t score[2], mapq[2];
-    uint8_t status[2], direction[2], is_transcriptome[2], pad[2];
+    uint8_t status[2], direction[2], is_transcriptome[2];
+    uint8_t aligned_as_pair; /* result->alignedAsPair: set only when a same-gene pair decided (AlignmentFilter.cpp:543-548) */
+    uint8_t pad;
 } snapb200_filter_result;
 
 /* What the host still has to count for the pair, through the reference's own public GTFReader methods:
@@ -332,6 +341,47 @@ int snapb200_filter_paired_batch(snapb200_annotation *a, const snapb200_filter_p
                                  const snapb200_paired_result *genome_pairs, const uint64_t *seg0, const uint32_t *ch_loc0,
                                  const uint16_t *ch_off0, const uint64_t *seg1, const uint32_t *ch_loc1, const uint16_t *ch_off1,
                                  snapb200_filter_result *results, snapb200_filter_event *events, uint8_t *needs_host);
+
+/* ---- RNA mode, whole pair loop: what one iteration of PairedAlignerContext::runIterationThread computes for a batch ------------
+ * (SNAPLib/PairedAligner.cpp:582-663): transcriptomeAligner->AlignRead x2 with maxHitsToGet, g_aligner->align, the partialAligner's
+ * CharacterizeSeeds for both reads, AlignmentFilter::Filter, forceSpacing and the MAPQ halving -- with every intermediate (multi-hit
+ * lists, genome pairs, seed tuples) staying in HBM.  A batch object owns pinned host staging for its inputs and outputs and one
+ * worker thread: submit() copies the reads into pinned memory and returns; wait() blocks until the device work and the downloads are
+ * done.  Two objects per host thread give the double buffering north_star asks for: the host replays batch k (GTF counters, SAM
+ * output) while batch k+1 is on the device.  The three handles must live on the same device. */
+typedef struct snapb200_rna_batch snapb200_rna_batch;
+
+typedef struct {
+    snapb200_paired_params paired;         /* g_aligner (ChimericPairedEndAligner), PairedAligner.cpp:470-481               */
+    snapb200_single_params transcriptome;  /* transcriptomeAligner incl. max_hits_to_get (1000), PairedAligner.cpp:512, 584 */
+    snapb200_single_params partial;        /* partialAligner: max_hits 300, num_seeds 12, PairedAligner.cpp:518-527        */
+    snapb200_filter_params filter;
+} snapb200_rna_params;
+
+/* Pointers into the batch object's pinned host memory; valid until the next submit on the same object.
+ * hits: CSR over reads -- read i of mate e has hit_offsets[e][i+1] - hit_offsets[e][i] transcriptome multi-hits (AlignRead's
+ * multiHitLocations / RCs / Scores in the reference's order).  seg_offsets / ch_*: snapb200_characterize_batch layout. */
+typedef struct {
+    uint32_t n;
+    const snapb200_filter_result *results;
+    const snapb200_filter_event *events;
+    const uint8_t *needs_host;
+    const snapb200_paired_result *genome_pairs;
+    const uint32_t *hit_offsets[2];
+    const uint32_t *hit_locations[2];
+    const uint8_t *hit_rcs[2];
+    const int32_t *hit_scores[2];
+    const uint64_t *seg_offsets[2];
+    const uint32_t *ch_locations[2];
+    const uint16_t *ch_seed_offsets[2];
+    float device_ms;   /* wall time of the device work of this batch (uploads, kernels, downloads), for the shim's timing report */
+} snapb200_rna_view;
+
+int snapb200_rna_batch_create(snapb200_annotation *a, snapb200_index *genome, snapb200_index *transcriptome, snapb200_rna_batch **out);
+void snapb200_rna_batch_destroy(snapb200_rna_batch *b);
+int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0,
+                              const snapb200_read_batch *reads1);
+int snapb200_rna_batch_wait(snapb200_rna_batch *b, snapb200_rna_view *view);
 
 /* ---- building blocks exposed for known-answer tests -------------------------------------------------- */
 

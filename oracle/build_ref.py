@@ -38,6 +38,16 @@ PATCHES = [
     ("SNAPLib/ContaminationFilter.cpp", 81, "}", "return 0;"),
     ("SNAPLib/ReadReader.cpp", 44, "}", "return false;"),
 ]
+# The two probabilities IntersectingPairedEndAligner::align hands computeMAPQ (probabilityOfAllPairs / probabilityOfBestPair,
+# IntersectingPairedEndAligner.cpp:249-252, 741) are locals of align(); they are copied to a thread-local the driver reads so that
+# the CUDA path's p_all / p_best are compared with the reference itself and not only with the port.  (file, 1-based line, text that
+# must be on that line, line inserted BEFORE it.)  Listed bottom-up so that earlier line numbers stay valid.
+INSERT_PATCHES = [
+    ("SNAPLib/IntersectingPairedEndAligner.cpp", 722, "if (bestPairScore == 65536) {",
+     "    snapref_pair_p[0] = probabilityOfAllPairs; snapref_pair_p[1] = probabilityOfBestPair;"),
+    ("SNAPLib/IntersectingPairedEndAligner.cpp", 141, "void",
+     "__thread double snapref_pair_p[2] = {0, 0};"),
+]
 # operator= without a return value (ContaminationFilter.h:41)
 INLINE_PATCHES = [
     ("SNAPLib/ContaminationFilter.h", 41, "count = rhs.count; };", "count = rhs.count; return *this; };"),
@@ -57,6 +67,14 @@ def patch_tree(work):
         if got != expect:
             raise SystemExit(f"{rel}:{line}: expected {expect!r}, found {got!r} -- reference changed?")
         lines[line - 1] = "    " + stmt + " " + lines[line - 1]
+        open(p, "w", encoding="latin-1").write("\n".join(lines))
+    for rel, line, expect, stmt in INSERT_PATCHES:
+        p = os.path.join(work, rel)
+        lines = open(p, encoding="latin-1").read().split("\n")
+        got = lines[line - 1].strip()
+        if got != expect:
+            raise SystemExit(f"{rel}:{line}: expected {expect!r}, found {got!r} -- reference changed?")
+        lines.insert(line - 1, stmt)
         open(p, "w", encoding="latin-1").write("\n".join(lines))
     for rel, line, old, new in INLINE_PATCHES:
         p = os.path.join(work, rel)

@@ -291,30 +291,57 @@ int ref_single_multihit_batch(void *h, const snapb200_single_params *p, const sn
     return run_single(h, p, reads, res, hit_counts, hit_locations, hit_rcs, hit_scores, nthreads);
 }
 
+// probabilityOfAllPairs / probabilityOfBestPair of the last IntersectingPairedEndAligner::align on this thread: locals of align()
+// in the reference, copied out by the two inserted lines of oracle/build_ref.py (INSERT_PATCHES)
+extern __thread double snapref_pair_p[2];
+
+// The aligner objects one worker thread of PairedAlignerContext::runIterationThread owns (SNAPLib/PairedAligner.cpp:459-481)
+struct PairedAligners {
+    BigAllocator *alloc;
+    IntersectingPairedEndAligner *inter;
+    ChimericPairedEndAligner *chim;
+};
+
+static PairedAligners *paired_aligners_create(GenomeIndex *index, const snapb200_paired_params *p)
+{
+    PairedAligners *a = new PairedAligners();
+    size_t pool = IntersectingPairedEndAligner::getBigAllocatorReservation(
+        index, p->max_big_hits, p->max_read_size, index->getSeedLength(), p->num_seeds, p->seed_coverage, p->max_k,
+        p->extra_search_depth, p->max_candidate_pool_size);
+    a->alloc = new BigAllocator(pool);
+    a->inter = new IntersectingPairedEndAligner(
+        index, p->max_read_size, p->max_hits, p->max_k, p->num_seeds, p->seed_coverage, p->min_spacing, p->max_spacing,
+        p->max_big_hits, p->extra_search_depth, p->max_candidate_pool_size, a->alloc);
+    a->chim = new ChimericPairedEndAligner(
+        index, p->max_read_size, p->max_hits, p->max_k, p->num_seeds, p->seed_coverage, p->min_spacing, p->max_spacing,
+        p->force_spacing != 0, p->extra_search_depth, a->inter);
+    return a;
+}
+
+static void paired_aligners_destroy(PairedAligners *a)
+{
+    delete a->chim;
+    a->inter->~IntersectingPairedEndAligner();
+    delete a->alloc;
+    delete a;
+}
+
 struct PairedJob {
     GenomeIndex *idx;
     const snapb200_paired_params *p;
     const snapb200_read_batch *r0, *r1;
     snapb200_paired_result *res;
     unsigned begin, end;
+    PairedAligners *aligners;  // NULL: construct for this call and destroy afterwards
 };
 
 static void *paired_worker(void *arg)
 {
     PairedJob *j = (PairedJob *)arg;
-    const snapb200_paired_params *p = j->p;
-    GenomeIndex *index = j->idx;
-    // SNAPLib/PairedAligner.cpp:459-481
-    size_t pool = IntersectingPairedEndAligner::getBigAllocatorReservation(
-        index, p->max_big_hits, p->max_read_size, index->getSeedLength(), p->num_seeds, p->seed_coverage, p->max_k,
-        p->extra_search_depth, p->max_candidate_pool_size);
-    BigAllocator *alloc = new BigAllocator(pool);
-    IntersectingPairedEndAligner *inter = new IntersectingPairedEndAligner(
-        index, p->max_read_size, p->max_hits, p->max_k, p->num_seeds, p->seed_coverage, p->min_spacing, p->max_spacing,
-        p->max_big_hits, p->extra_search_depth, p->max_candidate_pool_size, alloc);
-    ChimericPairedEndAligner *chim = new ChimericPairedEndAligner(
-        index, p->max_read_size, p->max_hits, p->max_k, p->num_seeds, p->seed_coverage, p->min_spacing, p->max_spacing,
-        p->force_spacing != 0, p->extra_search_depth, inter);
+    PairedAligners *own = j->aligners ? NULL : paired_aligners_create(j->idx, j->p);
+    PairedAligners *al = j->aligners ? j->aligners : own;
+    IntersectingPairedEndAligner *inter = al->inter;
+    ChimericPairedEndAligner *chim = al->chim;
     std::vector<char> b[2], q[2];
     for (unsigned i = j->begin; i < j->end; i++) {
         Read reads[2];
@@ -332,6 +359,7 @@ static void *paired_worker(void *arg)
         pr.location[0] = pr.location[1] = InvalidGenomeLocation;
         _int64 s0 = inter->getLocationsScored();
         inter->countOfHashTableLookups[0] = inter->countOfHashTableLookups[1] = 0;
+        snapref_pair_p[0] = snapref_pair_p[1] = 0;
         chim->align(&reads[0], &reads[1], &pr);
         snapb200_paired_result *r = &j->res[i];
         memset(r, 0, sizeof(*r));
@@ -346,12 +374,10 @@ static void *paired_worker(void *arg)
         r->aligned_as_pair = pr.alignedAsPair;
         r->n_lv_calls = (uint32_t)(inter->getLocationsScored() - s0);
         r->n_lookups = inter->countOfHashTableLookups[0] + inter->countOfHashTableLookups[1];
-        r->p_all = NAN; // locals of align() in the reference; only the port and the CUDA path expose them
-        r->p_best = NAN;
+        r->p_all = snapref_pair_p[0];  // 0 when IntersectingPairedEndAligner::align returned before phase 3
+        r->p_best = snapref_pair_p[1];
     }
-    delete chim;
-    inter->~IntersectingPairedEndAligner();
-    delete alloc;
+    if (own) paired_aligners_destroy(own);
     return NULL;
 }
 
@@ -364,7 +390,7 @@ int ref_paired_batch(void *h, const snapb200_paired_params *p, const snapb200_re
     std::vector<pthread_t> th(nthreads);
     for (int t = 0; t < nthreads; t++) {
         PairedJob &j = jobs[t];
-        j.idx = (GenomeIndex *)h; j.p = p; j.r0 = r0; j.r1 = r1; j.res = res;
+        j.idx = (GenomeIndex *)h; j.p = p; j.r0 = r0; j.r1 = r1; j.res = res; j.aligners = NULL;
         j.begin = (unsigned)((unsigned long long)r0->n * t / nthreads);
         j.end = (unsigned)((unsigned long long)r0->n * (t + 1) / nthreads);
     }
@@ -372,6 +398,49 @@ int ref_paired_batch(void *h, const snapb200_paired_params *p, const snapb200_re
     for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, paired_worker, &jobs[t]);
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     return 0;
+}
+
+// The same with the aligner objects of every thread kept alive between calls, as a worker thread of the reference keeps them for a
+// whole run (SNAPLib/PairedAligner.cpp:459-527 constructs once per thread per run): what bench.py --impl reference times, so that
+// constructing a BigAllocator + IntersectingPairedEndAligner + ChimericPairedEndAligner is not inside every timed step.
+struct PairedPool {
+    GenomeIndex *idx;
+    snapb200_paired_params p;
+    std::vector<PairedAligners *> aligners;
+};
+
+void *ref_paired_pool_create(void *h, const snapb200_paired_params *p, int nthreads)
+{
+    ref_init();
+    PairedPool *pool = new PairedPool();
+    pool->idx = (GenomeIndex *)h;
+    pool->p = *p;
+    for (int t = 0; t < (nthreads < 1 ? 1 : nthreads); t++) pool->aligners.push_back(paired_aligners_create(pool->idx, p));
+    return pool;
+}
+
+int ref_paired_pool_run(void *vp, const snapb200_read_batch *r0, const snapb200_read_batch *r1, snapb200_paired_result *res)
+{
+    PairedPool *pool = (PairedPool *)vp;
+    const int nthreads = (int)pool->aligners.size();
+    std::vector<PairedJob> jobs(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        PairedJob &j = jobs[t];
+        j.idx = pool->idx; j.p = &pool->p; j.r0 = r0; j.r1 = r1; j.res = res; j.aligners = pool->aligners[t];
+        j.begin = (unsigned)((unsigned long long)r0->n * t / nthreads);
+        j.end = (unsigned)((unsigned long long)r0->n * (t + 1) / nthreads);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, paired_worker, &jobs[t]);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+
+void ref_paired_pool_destroy(void *vp)
+{
+    PairedPool *pool = (PairedPool *)vp;
+    for (size_t t = 0; t < pool->aligners.size(); t++) paired_aligners_destroy(pool->aligners[t]);
+    delete pool;
 }
 
 // SAMFormat::computeCigarString's aligner call (SNAPLib/SAM.cpp:1159-1189): text = genome at location,
@@ -591,7 +660,8 @@ struct ref_filter_result {  // the fields of PairedAlignmentResult that leave th
     unsigned char status[2];
     unsigned char direction[2];
     unsigned char is_transcriptome[2];
-    unsigned char pad[2];
+    unsigned char aligned_as_pair;  // result.alignedAsPair after Filter (feeds the %Pairs column, PairedAligner.cpp:733-735)
+    unsigned char pad;
 };
 
 // The part of PairedAlignerContext::runIterationThread between the aligner calls and writePair (SNAPLib/PairedAligner.cpp:
@@ -650,8 +720,21 @@ int ref_filter_paired_batch(void *h_genome, void *h_transcriptome, void *gtf, co
             out[i].direction[e] = (unsigned char)result.direction[e];
             out[i].is_transcriptome[e] = result.isTranscriptome[e] ? 1 : 0;
         }
+        out[i].aligned_as_pair = result.alignedAsPair ? 1 : 0;
     }
     partial->~BaseAligner();
+    return 0;
+}
+
+// How many intervals the filter has recorded so far (two per IntrachromosomalPair / ...Splice call): [intra pairs, intra splices,
+// inter pairs, inter splices].  For sizing the host share of the replay (scripts/filter_host_profile.py).
+int ref_gtf_interval_counts(void *gtf, unsigned long long *out)
+{
+    GTFReader *g = (GTFReader *)gtf;
+    out[0] = g->intrachromosomal_pairs.read_intervals.size();
+    out[1] = g->intrachromosomal_splices.read_intervals.size();
+    out[2] = g->interchromosomal_pairs.read_intervals.size();
+    out[3] = g->interchromosomal_splices.read_intervals.size();
     return 0;
 }
 
@@ -717,8 +800,20 @@ int ref_filter_alignments(void *h_genome, void *h_transcriptome, void *gtf, cons
 // FltEvent, snap_rnaseq_b200/csrc/filterfmt.h) through the reference's own public GTFReader methods -- what the shim will do once
 // the decision itself comes from the device.  transcript_ids / chr_names: the strings behind the indices.
 struct ref_flt_event { int kind, unaligned, transcript[2], chr[2]; unsigned pos_original[2], pos[2], pos_end[2]; };
+struct ref_flt_splice { unsigned pair; int kind, chr[2]; unsigned pos[2], pos_end[2]; };
+// splice_off / splices: when given, the novel-splice records of every pair (FltSplice, [splice_off[i], splice_off[i+1])) are handed to
+// GTFReader::IntrachromosomalSplice / InterchromosomalSplice instead of running AlignmentFilter::UnalignedRead for the flagged reads
+int ref_filter_replay_events2(void *h_genome, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
+                              unsigned max_dist, const ref_flt_event *ev, const char *const *transcript_ids, const char *const *chr_names,
+                              const unsigned long long *splice_off, const ref_flt_splice *splices);
 int ref_filter_replay_events(void *h_genome, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
                              unsigned max_dist, const ref_flt_event *ev, const char *const *transcript_ids, const char *const *chr_names)
+{
+    return ref_filter_replay_events2(h_genome, h_transcriptome, gtf, r0, r1, max_dist, ev, transcript_ids, chr_names, NULL, NULL);
+}
+int ref_filter_replay_events2(void *h_genome, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
+                              unsigned max_dist, const ref_flt_event *ev, const char *const *transcript_ids, const char *const *chr_names,
+                              const unsigned long long *splice_off, const ref_flt_splice *splices)
 {
     GenomeIndex *idx = (GenomeIndex *)h_genome, *tidx = (GenomeIndex *)h_transcriptome;
     GTFReader *g = (GTFReader *)gtf;
@@ -728,9 +823,17 @@ int ref_filter_replay_events(void *h_genome, void *h_transcriptome, void *gtf, c
         make_read(&read0, r0, i, NULL);
         make_read(&read1, r1, i, NULL);
         const ref_flt_event &e = ev[i];
-        if (e.unaligned) {
+        if (e.unaligned && splice_off == NULL) {
             AlignmentFilter filter(&read0, &read1, idx->getGenome(), tidx->getGenome(), g, 50, 1000, 2, max_dist, idx->getSeedLength(), partial);
             filter.UnalignedRead(e.unaligned == 1 ? &read0 : &read1, idx->getSeedLength());
+        } else if (e.unaligned) {
+            Read *rd = e.unaligned == 1 ? &read0 : &read1;
+            std::string rid(rd->getId(), rd->getIdLength());
+            for (unsigned long long q = splice_off[i]; q < splice_off[i + 1]; q++) {
+                const ref_flt_splice &sp = splices[q];
+                if (sp.kind == 2) g->IntrachromosomalSplice(chr_names[sp.chr[0]], sp.pos[0], sp.pos_end[0], chr_names[sp.chr[1]], sp.pos[1], sp.pos_end[1], rid);
+                else g->InterchromosomalSplice(chr_names[sp.chr[0]], sp.pos[0], sp.pos_end[0], chr_names[sp.chr[1]], sp.pos[1], sp.pos_end[1], rid);
+            }
         }
         std::string t0 = e.transcript[0] >= 0 ? transcript_ids[e.transcript[0]] : "", t1 = e.transcript[1] >= 0 ? transcript_ids[e.transcript[1]] : "";
         std::string id(read0.getId(), read0.getIdLength());

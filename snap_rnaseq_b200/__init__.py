@@ -115,6 +115,58 @@ class Snapb200(BatchLib):
                                                           A.p8(nh)), "filter_paired_batch")
         return res, ev, nh[:n]
 
+    def annotation_names(self, a):
+        """(transcript ids in the reference's map order, chromosome names) behind the indices of the filter events."""
+        self.lib.snapb200_annotation_transcript_id.restype = C.c_char_p
+        self.lib.snapb200_annotation_chromosome.restype = C.c_char_p
+        self.lib.snapb200_annotation_transcript_count.restype = C.c_uint32
+        nt = self.lib.snapb200_annotation_transcript_count(a)
+        t = [self.lib.snapb200_annotation_transcript_id(a, C.c_uint32(i)).decode() for i in range(nt)]
+        c, i = [], 0
+        while True:
+            s = self.lib.snapb200_annotation_chromosome(a, C.c_uint32(i))
+            if s is None:
+                break
+            c.append(s.decode())
+            i += 1
+        return t, c
+
+    # -- the whole RNA pair loop of a batch, intermediates resident in HBM (snapb200_rna_batch_*) ---------------------------------
+    def rna_batch_create(self, annotation, genome, transcriptome):
+        h = C.c_void_p()
+        self._check(self.lib.snapb200_rna_batch_create(annotation, genome, transcriptome, C.byref(h)), "rna_batch_create")
+        return h
+
+    def rna_batch_destroy(self, b):
+        self.lib.snapb200_rna_batch_destroy.restype = None
+        self.lib.snapb200_rna_batch_destroy(b)
+
+    def rna_batch_submit(self, b, params, b0, b1):
+        self._check(self.lib.snapb200_rna_batch_submit(b, C.byref(params), b0.byref(), b1.byref()), "rna_batch_submit")
+
+    def rna_batch_wait(self, b):
+        """-> dict of numpy COPIES of the batch object's pinned outputs (the views die with the next submit)."""
+        v = A.RnaView()
+        self._check(self.lib.snapb200_rna_batch_wait(b, C.byref(v)), "rna_batch_wait")
+        n = v.n
+
+        def arr(ptr, count, dtype):
+            if not count or not ptr:
+                return np.zeros(0, dtype)
+            dt = np.dtype(dtype)
+            return np.frombuffer((C.c_uint8 * (count * dt.itemsize)).from_address(ptr), dtype=dt, count=count).copy()
+
+        out = {"n": n, "device_ms": v.device_ms, "results": arr(v.results, n, A.FILTER_RESULT), "events": arr(v.events, n, A.FILTER_EVENT),
+               "needs_host": arr(v.needs_host, n, np.uint8), "genome_pairs": arr(v.genome_pairs, n, A.PAIRED_RESULT), "hits": [], "ch": []}
+        for e in range(2):
+            off = arr(v.hit_offsets[e], n + 1, np.uint32)
+            t = int(off[-1]) if n else 0
+            out["hits"].append((off, arr(v.hit_locations[e], t, np.uint32), arr(v.hit_rcs[e], t, np.uint8), arr(v.hit_scores[e], t, np.int32)))
+            seg = arr(v.seg_offsets[e], 2 * n + 1, np.uint64)
+            t = int(seg[-1]) if n else 0
+            out["ch"].append((seg, arr(v.ch_locations[e], t, np.uint32), arr(v.ch_seed_offsets[e], t, np.uint16)))
+        return out
+
     def device_count(self):
         return int(self.lib.snapb200_device_count())
 

@@ -233,7 +233,30 @@ class FilterParams(C.Structure):
 
 
 FILTER_RESULT = np.dtype([("location", "<u4", (2,)), ("tlocation", "<u4", (2,)), ("score", "<i4", (2,)), ("mapq", "<i4", (2,)),
-                          ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,)), ("pad", "u1", (2,))])
+                          ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,)), ("aligned_as_pair", "u1"), ("pad", "u1")])
 FILTER_EVENT = np.dtype([("kind", "<i4"), ("unaligned", "<i4"), ("transcript", "<i4", (2,)), ("chr", "<i4", (2,)), ("pos_original", "<u4", (2,)),
                          ("pos", "<u4", (2,)), ("pos_end", "<u4", (2,))])
 assert FILTER_RESULT.itemsize == 40 and FILTER_EVENT.itemsize == 48
+
+
+class RnaParams(C.Structure):
+    """snapb200_rna_params: the aligner objects of one worker thread of the paired RNA loop (SNAPLib/PairedAligner.cpp:459-527)."""
+    _fields_ = [("paired", PairedParams), ("transcriptome", SingleParams), ("partial", SingleParams), ("filter", FilterParams)]
+
+
+class RnaView(C.Structure):
+    """snapb200_rna_view: pointers into the batch object's pinned host memory."""
+    _fields_ = [("n", C.c_uint32), ("results", C.c_void_p), ("events", C.c_void_p), ("needs_host", C.c_void_p), ("genome_pairs", C.c_void_p),
+                ("hit_offsets", C.c_void_p * 2), ("hit_locations", C.c_void_p * 2), ("hit_rcs", C.c_void_p * 2), ("hit_scores", C.c_void_p * 2),
+                ("seg_offsets", C.c_void_p * 2), ("ch_locations", C.c_void_p * 2), ("ch_seed_offsets", C.c_void_p * 2), ("device_ms", C.c_float)]
+
+
+def rna_defaults(conf_diff=2):
+    """`snap-rna paired` defaults for the three aligners of the RNA loop and the filter (SNAPLib/PairedAligner.cpp:470-527, 582-584)."""
+    pp = paired_defaults()
+    tp = SingleParams(max_hits=pp.max_hits, max_k=pp.max_k, max_read_size=MAX_READ_LENGTH, num_seeds=pp.num_seeds, seed_coverage=pp.seed_coverage,
+                      extra_search_depth=pp.extra_search_depth, explore_popular_seeds=0, stop_on_first_hit=0, max_hits_to_get=1000)
+    cp = SingleParams(max_hits=300, max_k=pp.max_k, max_read_size=MAX_READ_LENGTH, num_seeds=12, seed_coverage=pp.seed_coverage,
+                      extra_search_depth=pp.extra_search_depth, explore_popular_seeds=0, stop_on_first_hit=0, max_hits_to_get=0)
+    fp = FilterParams(pp.max_spacing, pp.force_spacing, conf_diff, pp.max_k, 1000)
+    return RnaParams(pp, tp, cp, fp)

@@ -1,88 +1,90 @@
-// filter_api.inl -- snapb200_annotation_open / snapb200_filter_paired_batch (include/snapb200.h).
-// First version: one thread per pair around flt_filter_pair (filterfmt.h), whose logic is verified on the host against the
-// reference's AlignmentFilter (tests/test_filter_oracle.py).  Included at the end of snapb200.cu.
-#include "filterfmt.h"
+// filter_api.inl -- snapb200_annotation_*, snapb200_filter_paired_batch and snapb200_rna_batch_* (include/snapb200.h; SURVEY.md
+// section 8 row f3).  The kernel is filter_warp.cuh (one warp per pair) over the per-element rules of filterfmt.h, whose logic is
+// verified on the host against the reference's AlignmentFilter (tests/test_filter_oracle.py).  Included at the end of snapb200.cu.
+#include <condition_variable>
+#include <map>
+#include <thread>
+
+#include "filter_warp.cuh"
 #include "gtf_tables.h"
 
-struct snapb200_annotation {
-    snapb200_index *genome = nullptr;
-    FltTables t;                     // device pointers
-    std::vector<void *> allocs;
-    uint32_t n_transcripts = 0, n_genes = 0;
-};
-
-struct FilterArgs {
-    FltTables t;
-    FltParams prm;
-    uint32_t n, mh;
-    const uint32_t *len[2];
-    const int32_t *n_hits[2];
-    const uint32_t *loc[2];
-    const uint8_t *rc[2];
-    const int32_t *score[2];
-    const snapb200_paired_result *g;
-    const uint64_t *seg[2];
-    const uint32_t *ch_loc[2];
-    const uint16_t *ch_off[2];
-    FltResult *out;
-    FltEvent *ev;
-    uint8_t *needs_host;
-    // scratch, one slice per thread of the grid
-    FltAln *lists; uint32_t list_cap;
-    FltPair *pairs; uint32_t pair_cap;
-    uint32_t *ploc; uint32_t ploc_cap;
-};
-
-__global__ void __launch_bounds__(128) filter_kernel(const FilterArgs a)
-{
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    FltScratch sc;
-    sc.list_cap = a.list_cap; sc.pair_cap = a.pair_cap; sc.ploc_cap = a.ploc_cap;
-    sc.list[0] = a.lists + (size_t)tid * 2 * (a.list_cap + 1);
-    sc.list[1] = sc.list[0] + (a.list_cap + 1);
-    sc.pairs = a.pairs + (size_t)tid * a.pair_cap;
-    sc.ploc[0] = a.ploc + (size_t)tid * 2 * a.ploc_cap;
-    sc.ploc[1] = sc.ploc[0] + a.ploc_cap;
-    for (uint32_t i = tid; i < a.n; i += nthreads) {
-        FltPairInput in;
-        for (int e = 0; e < 2; e++) {
-            in.len[e] = a.len[e][i];
-            in.n_hits[e] = a.n_hits[e][i];
-            in.hit_loc[e] = a.loc[e] + (size_t)i * a.mh;
-            in.hit_rc[e] = a.rc[e] + (size_t)i * a.mh;
-            in.hit_score[e] = a.score[e] + (size_t)i * a.mh;
-            in.g_location[e] = a.g[i].location[e]; in.g_score[e] = a.g[i].score[e]; in.g_mapq[e] = a.g[i].mapq[e];
-            in.g_status[e] = a.g[i].status[e]; in.g_direction[e] = a.g[i].direction[e];
-            in.ch_loc[e] = a.ch_loc[e]; in.ch_off[e] = a.ch_off[e];
-            for (int k = 0; k < 3; k++) in.ch_range[e][k] = a.seg[e][2 * (size_t)i + k];
-        }
-        FltResult r;
-        FltEvent ev;
-        const int rc = flt_filter_pair(a.t, a.prm, in, sc, &r, &ev);
-        a.needs_host[i] = (uint8_t)rc;
-        if (rc == FLT_OK) { a.out[i] = r; a.ev[i] = ev; }
+// Device buffers of one filter launch: grow once, reused by every later call (no cudaMalloc / cudaFree per batch).
+struct FilterWorkspace {
+    std::mutex lock;
+    cudaStream_t stream = nullptr;
+    DevBuf scratch, work, out, ev, flags;
+    DevBuf in[17];  // staged inputs of snapb200_filter_paired_batch (host arrays -> HBM)
+    std::vector<FltResult> h_out;
+    void release()
+    {
+        scratch.release(); work.release(); out.release(); ev.release(); flags.release();
+        for (DevBuf &b : in) b.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
     }
-}
+};
+
+struct snapb200_annotation {
+    int device = 0;
+    int sm_count = 0;
+    FltTables t;                     // device pointers, all owned by this handle
+    const uint32_t *chr_rank = nullptr;
+    std::vector<void *> allocs;
+    std::vector<std::string> transcript_ids, chr_names;
+    uint32_t n_genes = 0;
+    FilterWorkspace ws[2];           // two concurrent callers of snapb200_filter_paired_batch; a third waits
+    std::atomic<unsigned> ws_rr{0};
+};
 
 template <class T>
-static int ann_upload(snapb200_annotation *a, const std::vector<T> &v, const T **dst)
+static int ann_upload(snapb200_annotation *a, const T *src, size_t count, const T **dst)
 {
     void *p = nullptr;
-    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     a->allocs.push_back(p);
-    if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (count && (e = cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return set_error(SNAPB200_ERR_CUDA, "annotation upload failed: %s", cudaGetErrorString(e));
     *dst = (const T *)p;
     return 0;
 }
+template <class T>
+static int ann_upload(snapb200_annotation *a, const std::vector<T> &v, const T **dst) { return ann_upload(a, v.data(), v.size(), dst); }
 
 extern "C" void snapb200_annotation_close(snapb200_annotation *a)
 {
     if (!a) return;
-    if (a->genome) cudaSetDevice(a->genome->device);
+    cudaSetDevice(a->device);
+    for (FilterWorkspace &w : a->ws) w.release();
     for (void *p : a->allocs) cudaFree(p);
     delete a;
+}
+
+extern "C" uint32_t snapb200_annotation_transcript_count(const snapb200_annotation *a) { return a ? (uint32_t)a->transcript_ids.size() : 0; }
+extern "C" const char *snapb200_annotation_transcript_id(const snapb200_annotation *a, uint32_t i)
+{
+    return a && i < a->transcript_ids.size() ? a->transcript_ids[i].c_str() : nullptr;
+}
+extern "C" const char *snapb200_annotation_chromosome(const snapb200_annotation *a, uint32_t i)
+{
+    return a && i < a->chr_names.size() ? a->chr_names[i].c_str() : nullptr;
+}
+
+// The order of the map keys name + '_' + decimal(pos) between two different chromosomes is that of name + '_' alone unless one
+// "name_" is a prefix of the other (then the digits take part).  ranks: position of every "name_" in strcmp order, or empty.
+static std::vector<uint32_t> chromosome_ranks(const std::vector<std::string> &names)
+{
+    std::vector<std::string> keyed;
+    for (const std::string &n : names) keyed.push_back(n + "_");
+    for (size_t i = 0; i < keyed.size(); i++)
+        for (size_t j = 0; j < keyed.size(); j++)
+            if (i != j && keyed[j].compare(0, keyed[i].size(), keyed[i]) == 0) return std::vector<uint32_t>();  // prefix (or duplicate name)
+    std::vector<uint32_t> order(keyed.size()), rank(keyed.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keyed[x] < keyed[y]; });
+    for (size_t i = 0; i < order.size(); i++) rank[order[i]] = (uint32_t)i;
+    return rank;
 }
 
 extern "C" int snapb200_annotation_open(snapb200_index *genome, snapb200_index *transcriptome, const char *gtf_path, snapb200_annotation **out)
@@ -126,18 +128,31 @@ extern "C" int snapb200_annotation_open(snapb200_index *genome, snapb200_index *
     }
     CUDA_TRY(cudaSetDevice(genome->device));
     snapb200_annotation *a = new snapb200_annotation();
-    a->genome = genome;
-    a->n_transcripts = (uint32_t)g.transcripts.size();
+    a->device = genome->device;
+    a->sm_count = genome->sm_count;
     a->n_genes = (uint32_t)g.genes.size();
+    a->chr_names = genome->piece_names;
+    for (size_t i = 0; i < g.transcripts.size(); i++) a->transcript_ids.push_back(g.transcripts[i].id);
     memset(&a->t, 0, sizeof(a->t));
-    a->t.piece_begin = genome->dev.piece_begin; a->t.n_pieces = genome->dev.n_pieces;
-    a->t.tpiece_begin = transcriptome->dev.piece_begin; a->t.n_tpieces = transcriptome->dev.n_pieces;
+    // the handle keeps its own copies of the two piece tables, so closing an index first cannot leave the kernel reading freed HBM
+    std::vector<uint32_t> pb(genome->dev.n_pieces), tpb(transcriptome->dev.n_pieces);
+    cudaError_t e = cudaSuccess;
+    if (!pb.empty()) e = cudaMemcpy(pb.data(), genome->dev.piece_begin, pb.size() * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && !tpb.empty()) e = cudaMemcpy(tpb.data(), transcriptome->dev.piece_begin, tpb.size() * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete a; return set_error(SNAPB200_ERR_CUDA, "reading the piece tables: %s", cudaGetErrorString(e)); }
+    a->t.n_pieces = genome->dev.n_pieces;
+    a->t.n_tpieces = transcriptome->dev.n_pieces;
+    a->t.n_genes = (uint32_t)g.genes.size();
+    a->t.gene_tree_min_stop = (!g.genes.empty() && g.genes.size() < 64) ? (int32_t)g.genes[0].start : INT32_MIN;  // flt_gene_found
+    const std::vector<uint32_t> rank = chromosome_ranks(genome->piece_names);
     int rc = 0;
-    if ((rc = ann_upload(a, names, &a->t.chr_names)) || (rc = ann_upload(a, name_off, &a->t.chr_name_off)) ||
+    if ((rc = ann_upload(a, pb, &a->t.piece_begin)) || (rc = ann_upload(a, tpb, &a->t.tpiece_begin)) ||
+        (rc = ann_upload(a, names, &a->t.chr_names)) || (rc = ann_upload(a, name_off, &a->t.chr_name_off)) ||
         (rc = ann_upload(a, tpiece_transcript, &a->t.tpiece_transcript)) || (rc = ann_upload(a, t_chr, &a->t.t_chr)) ||
         (rc = ann_upload(a, t_gene, &a->t.t_gene)) || (rc = ann_upload(a, t_end, &a->t.t_end)) || (rc = ann_upload(a, t_first, &a->t.t_feat_first)) ||
         (rc = ann_upload(a, f_type, &a->t.f_type)) || (rc = ann_upload(a, f_start, &a->t.f_start)) || (rc = ann_upload(a, f_end, &a->t.f_end)) ||
-        (rc = ann_upload(a, g_chr, &a->t.g_chr)) || (rc = ann_upload(a, g_start, &a->t.g_start)) || (rc = ann_upload(a, g_end, &a->t.g_end))) {
+        (rc = ann_upload(a, g_chr, &a->t.g_chr)) || (rc = ann_upload(a, g_start, &a->t.g_start)) || (rc = ann_upload(a, g_end, &a->t.g_end)) ||
+        (!rank.empty() && (rc = ann_upload(a, rank, &a->chr_rank)))) {
         snapb200_annotation_close(a);
         return rc;
     }
@@ -145,16 +160,39 @@ extern "C" int snapb200_annotation_open(snapb200_index *genome, snapb200_index *
     return 0;
 }
 
-template <class T>
-static int flt_to_device(std::vector<void *> &tmp, const T *src, size_t count, const T **dst, cudaStream_t st)
+// ---- one launch of filter_warp_kernel over device-resident inputs ------------------------------------------------------------
+static const uint32_t FW_PAIR_CAP = 8192, FW_PLOC_CAP = 8192;
+
+// k: everything but scratch / work filled in by the caller (device pointers).  Enqueued on `st`; no synchronisation.
+static int filter_launch(snapb200_annotation *a, FilterWarpArgs &k, DevBuf &scratch, DevBuf &work, cudaStream_t st)
 {
-    void *p = nullptr;
-    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    tmp.push_back(p);
-    if (count) CUDA_TRY(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
-    *dst = (const T *)p;
+    k.t = a->t;
+    k.chr_rank = a->chr_rank;
+    k.list_cap = k.mh + 1;
+    k.pair_cap = FW_PAIR_CAP;
+    k.ploc_cap = FW_PLOC_CAP;
+    k.scratch_per_warp = fw_scratch_bytes(k.list_cap, k.pair_cap, k.ploc_cap);
+    const uint32_t warps_per_cta = 8;
+    uint32_t ctas = std::min<uint32_t>((k.n + warps_per_cta - 1) / warps_per_cta, (uint32_t)a->sm_count * 2);
+    if (ctas < 1) ctas = 1;
+    int rc;
+    if ((rc = scratch.ensure((size_t)ctas * warps_per_cta * k.scratch_per_warp))) return rc;
+    if ((rc = work.ensure(64))) return rc;
+    k.scratch = scratch.as<uint8_t>();
+    k.work = work.as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(work.p, 0, 64, st));
+    filter_warp_kernel<<<ctas, warps_per_cta * 32, 0, st>>>(k);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <class T>
+static int flt_stage(DevBuf &buf, const T *src, size_t count, const T **dst, cudaStream_t st)
+{
+    int rc = buf.ensure(std::max<size_t>(count, 1) * sizeof(T));
+    if (rc) return rc;
+    if (count) CUDA_TRY(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *dst = buf.as<T>();
     return 0;
 }
 
@@ -171,67 +209,322 @@ extern "C" int snapb200_filter_paired_batch(snapb200_annotation *a, const snapb2
         return set_error(SNAPB200_ERR_ARG, "null argument");
     if (!n) return 0;
     const uint32_t mh = params->max_hits_to_get;
-    if (!mh) return set_error(SNAPB200_ERR_ARG, "max_hits_to_get is 0");
+    if (!mh || mh > 65535) return set_error(SNAPB200_ERR_ARG, "max_hits_to_get must be 1..65535");
     for (uint32_t i = 0; i < n; i++)
         if (n0[i] < 0 || n1[i] < 0 || (uint32_t)n0[i] > mh || (uint32_t)n1[i] > mh) return set_error(SNAPB200_ERR_ARG, "pair %u: hit count outside 0..max_hits_to_get", i);
-    CUDA_TRY(cudaSetDevice(a->genome->device));
-    cudaStream_t st = nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    std::vector<void *> tmp;
-    FilterArgs k;
+    const size_t t0 = (size_t)seg0[2 * (size_t)n], t1 = (size_t)seg1[2 * (size_t)n];
+    if ((t0 && (!ch_loc0 || !ch_off0)) || (t1 && (!ch_loc1 || !ch_off1))) return set_error(SNAPB200_ERR_ARG, "seg offsets announce seed tuples but the tuple arrays are NULL");
+    CUDA_TRY(cudaSetDevice(a->device));
+    int slot = -1;
+    for (int q = 0; q < 2 && slot < 0; q++) if (a->ws[q].lock.try_lock()) slot = q;
+    if (slot < 0) { slot = (int)(a->ws_rr.fetch_add(1) & 1); a->ws[slot].lock.lock(); }
+    FilterWorkspace &w = a->ws[slot];
+    struct Unlock { std::mutex &m; ~Unlock() { m.unlock(); } } unlock{w.lock};
+    if (!w.stream) CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    cudaStream_t st = w.stream;
+    FilterWarpArgs k;
     memset(&k, 0, sizeof(k));
-    k.t = a->t;
     k.prm.max_dist = params->max_dist; k.prm.max_spacing = params->max_spacing; k.prm.conf_diff = params->conf_diff; k.prm.force_spacing = (int32_t)params->force_spacing;
     k.n = n; k.mh = mh;
+    const size_t rows = (size_t)n * mh;
     int rc = 0;
-    FltResult *d_out = nullptr;
-    FltEvent *d_ev = nullptr;
-    do {
-        const size_t rows = (size_t)n * mh;
-        if ((rc = flt_to_device(tmp, len0, n, &k.len[0], st)) || (rc = flt_to_device(tmp, len1, n, &k.len[1], st)) ||
-            (rc = flt_to_device(tmp, n0, n, &k.n_hits[0], st)) || (rc = flt_to_device(tmp, n1, n, &k.n_hits[1], st)) ||
-            (rc = flt_to_device(tmp, loc0, rows, &k.loc[0], st)) || (rc = flt_to_device(tmp, loc1, rows, &k.loc[1], st)) ||
-            (rc = flt_to_device(tmp, rc0, rows, &k.rc[0], st)) || (rc = flt_to_device(tmp, rc1, rows, &k.rc[1], st)) ||
-            (rc = flt_to_device(tmp, score0, rows, &k.score[0], st)) || (rc = flt_to_device(tmp, score1, rows, &k.score[1], st)) ||
-            (rc = flt_to_device(tmp, genome_pairs, n, &k.g, st)) || (rc = flt_to_device(tmp, seg0, 2 * (size_t)n + 1, &k.seg[0], st)) ||
-            (rc = flt_to_device(tmp, seg1, 2 * (size_t)n + 1, &k.seg[1], st)) || (rc = flt_to_device(tmp, ch_loc0, (size_t)seg0[2 * (size_t)n], &k.ch_loc[0], st)) ||
-            (rc = flt_to_device(tmp, ch_off0, (size_t)seg0[2 * (size_t)n], &k.ch_off[0], st)) ||
-            (rc = flt_to_device(tmp, ch_loc1, (size_t)seg1[2 * (size_t)n], &k.ch_loc[1], st)) ||
-            (rc = flt_to_device(tmp, ch_off1, (size_t)seg1[2 * (size_t)n], &k.ch_off[1], st)))
-            break;
-        const uint32_t threads = 128, blocks = std::min<uint32_t>((n + threads - 1) / threads, (uint32_t)a->genome->sm_count * 4);
-        const size_t nthreads = (size_t)threads * blocks;
-        k.list_cap = mh + 1; k.pair_cap = 4096; k.ploc_cap = 2048;
-        void *p = nullptr;
-        cudaError_t e;
-        if ((e = cudaMalloc(&p, nthreads * 2 * (k.list_cap + 1) * sizeof(FltAln))) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter scratch: %s", cudaGetErrorString(e)); break; }
-        tmp.push_back(p); k.lists = (FltAln *)p;
-        if ((e = cudaMalloc(&p, nthreads * k.pair_cap * sizeof(FltPair))) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter scratch: %s", cudaGetErrorString(e)); break; }
-        tmp.push_back(p); k.pairs = (FltPair *)p;
-        if ((e = cudaMalloc(&p, nthreads * 2 * k.ploc_cap * sizeof(uint32_t))) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter scratch: %s", cudaGetErrorString(e)); break; }
-        tmp.push_back(p); k.ploc = (uint32_t *)p;
-        if ((e = cudaMalloc(&p, (size_t)n * sizeof(FltResult))) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter results: %s", cudaGetErrorString(e)); break; }
-        tmp.push_back(p); d_out = (FltResult *)p;
-        if ((e = cudaMalloc(&p, (size_t)n * sizeof(FltEvent))) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter events: %s", cudaGetErrorString(e)); break; }
-        tmp.push_back(p); d_ev = (FltEvent *)p;
-        if ((e = cudaMalloc(&p, n)) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter flags: %s", cudaGetErrorString(e)); break; }
-        tmp.push_back(p); k.needs_host = (uint8_t *)p;
-        cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(FltResult), st);
-        cudaMemsetAsync(d_ev, 0, (size_t)n * sizeof(FltEvent), st);
-        k.out = d_out; k.ev = d_ev;
-        filter_kernel<<<blocks, threads, 0, st>>>(k);
-        if ((e = cudaGetLastError()) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter_kernel launch: %s", cudaGetErrorString(e)); break; }
-        std::vector<FltResult> h_out(n);
-        cudaMemcpyAsync(h_out.data(), d_out, (size_t)n * sizeof(FltResult), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(events, d_ev, (size_t)n * sizeof(FltEvent), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(needs_host, k.needs_host, n, cudaMemcpyDeviceToHost, st);
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "filter_kernel: %s", cudaGetErrorString(e)); break; }
-        for (uint32_t i = 0; i < n; i++) {
-            memset(&results[i], 0, sizeof(results[i]));
-            memcpy(&results[i], &h_out[i], sizeof(FltResult));
+    if ((rc = flt_stage(w.in[0], len0, n, &k.len[0], st)) || (rc = flt_stage(w.in[1], len1, n, &k.len[1], st)) ||
+        (rc = flt_stage(w.in[2], n0, n, &k.n_hits[0], st)) || (rc = flt_stage(w.in[3], n1, n, &k.n_hits[1], st)) ||
+        (rc = flt_stage(w.in[4], loc0, rows, &k.loc[0], st)) || (rc = flt_stage(w.in[5], loc1, rows, &k.loc[1], st)) ||
+        (rc = flt_stage(w.in[6], rc0, rows, &k.rc[0], st)) || (rc = flt_stage(w.in[7], rc1, rows, &k.rc[1], st)) ||
+        (rc = flt_stage(w.in[8], score0, rows, &k.score[0], st)) || (rc = flt_stage(w.in[9], score1, rows, &k.score[1], st)) ||
+        (rc = flt_stage(w.in[10], genome_pairs, n, &k.g, st)) ||
+        (rc = flt_stage(w.in[11], (const unsigned long long *)seg0, 2 * (size_t)n + 1, &k.seg[0], st)) ||
+        (rc = flt_stage(w.in[12], (const unsigned long long *)seg1, 2 * (size_t)n + 1, &k.seg[1], st)) ||
+        (rc = flt_stage(w.in[13], ch_loc0, t0, &k.ch_loc[0], st)) || (rc = flt_stage(w.in[14], ch_off0, t0, &k.ch_off[0], st)) ||
+        (rc = flt_stage(w.in[15], ch_loc1, t1, &k.ch_loc[1], st)) || (rc = flt_stage(w.in[16], ch_off1, t1, &k.ch_off[1], st)))
+        return rc;
+    if ((rc = w.out.ensure((size_t)n * sizeof(FltResult))) || (rc = w.ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = w.flags.ensure(n))) return rc;
+    CUDA_TRY(cudaMemsetAsync(w.out.p, 0, (size_t)n * sizeof(FltResult), st));
+    CUDA_TRY(cudaMemsetAsync(w.ev.p, 0, (size_t)n * sizeof(FltEvent), st));
+    k.out = w.out.as<FltResult>(); k.ev = w.ev.as<FltEvent>(); k.needs_host = w.flags.as<uint8_t>();
+    if ((rc = filter_launch(a, k, w.scratch, w.work, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(results, w.out.p, (size_t)n * sizeof(FltResult), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(events, w.ev.p, (size_t)n * sizeof(FltEvent), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(needs_host, w.flags.p, n, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "filter_warp_kernel: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- the whole RNA pair loop of one batch, intermediates resident in HBM ------------------------------------------------------
+// dense multi-hit rows of one mate -> CSR (counts scanned into offsets by cub, then one thread per row copies its hits)
+__global__ void mh_compact_kernel(uint32_t n, uint32_t mh, const int32_t *counts, const uint32_t *off, const uint32_t *locs, const uint8_t *rcs,
+                                  const int32_t *scores, uint32_t *o_loc, uint8_t *o_rc, int32_t *o_score)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = (uint32_t)counts[i], o = off[i];
+    for (uint32_t k = 0; k < c; k++) {
+        o_loc[o + k] = locs[(size_t)i * mh + k];
+        o_rc[o + k] = rcs[(size_t)i * mh + k];
+        o_score[o + k] = scores[(size_t)i * mh + k];
+    }
+}
+
+struct PinBuf {  // pinned host memory that only grows
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct snapb200_rna_batch {
+    snapb200_annotation *ann = nullptr;
+    snapb200_index *genome = nullptr, *transcriptome = nullptr;
+    // pinned staging: inputs (copied at submit) and outputs (filled by the worker)
+    PinBuf in_off[2], in_bases[2], in_quals[2];
+    PinBuf h_res, h_ev, h_flags, h_pairs, h_hoff[2], h_hloc[2], h_hrc[2], h_hscore[2], h_seg[2], h_cloc[2], h_coff[2];
+    // device-resident intermediates owned by the batch (the sessions' buffers are reused by other callers between the phases)
+    DevBuf d_hoff[2], d_hloc[2], d_hrc[2], d_hscore[2], d_seg[2], d_cnt[2], d_cloc[2], d_coff[2], d_keys[2], d_tmp, d_res, d_ev, d_flags;
+    snapb200_rna_params params;
+    uint32_t n = 0;
+    float device_ms = 0;
+    // worker thread
+    std::thread worker;
+    std::mutex m;
+    std::condition_variable cv;
+    int state = 0;  // 0 idle, 1 submitted, 2 done, 3 shutting down
+    int rc = 0;
+    char error[512] = "";
+};
+
+static double rna_now()
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec + t.tv_nsec * 1e-9;
+}
+
+static int rna_run(snapb200_rna_batch *b)
+{
+    const uint32_t n = b->n;
+    const bool timing = getenv("SNAPB200_RNA_TIMING") != nullptr;  // where a batch spends its time on the device side (stderr)
+    double tt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tm = rna_now(), tn;
+#define RNA_MARK(i) do { tn = rna_now(); tt[i] += tn - tm; tm = tn; } while (0)
+    const snapb200_rna_params &P = b->params;
+    snapb200_read_batch r[2];
+    for (int e = 0; e < 2; e++) { r[e].n = n; r[e].offsets = b->in_off[e].as<uint32_t>(); r[e].bases = b->in_bases[e].as<uint8_t>(); r[e].quals = b->in_quals[e].as<uint8_t>(); }
+    uint32_t m0, m1;
+    int rc;
+    if ((rc = validate_batch(&r[0], &m0)) || (rc = validate_batch(&r[1], &m1))) return rc;
+    const uint32_t mh = P.transcriptome.max_hits_to_get;
+    if (!mh || mh > 65535) return set_error(SNAPB200_ERR_ARG, "transcriptome.max_hits_to_get must be 1..65535");
+    CUDA_TRY(cudaSetDevice(b->genome->device));
+    uint32_t total_hits[2] = {0, 0};
+    // phase T: the transcriptome aligner's multi-hits of both mates (PairedAligner.cpp:584-605), compacted to CSR
+    {
+        BatchSlot slot(b->transcriptome);
+        if ((rc = slot.open())) return rc;
+        snapb200_session *s = slot.s;
+        RNA_MARK(0);
+        for (int e = 0; e < 2; e++) {
+            if ((rc = snapb200_session_upload(s, 0, &r[e])) || (rc = snapb200_session_run_single(s, &P.transcriptome))) return rc;
+            RNA_MARK(1);
+            if ((rc = b->d_hoff[e].ensure((size_t)(n + 1) * 4))) return rc;
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s->mh_counts.as<int32_t>(), b->d_hoff[e].as<uint32_t>(), (int)n + 1, s->stream);
+            if ((rc = b->d_tmp.ensure(tmp_bytes))) return rc;
+            // counts[n] is scratch past the last read: the scan's n-th output (the total) only needs inputs 0..n-1
+            if ((rc = s->mh_counts.ensure((size_t)(n + 1) * 4))) return rc;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(b->d_tmp.p, tmp_bytes, s->mh_counts.as<int32_t>(), b->d_hoff[e].as<uint32_t>(), (int)n + 1, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(&total_hits[e], b->d_hoff[e].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            const size_t th = std::max<uint32_t>(total_hits[e], 1);
+            if ((rc = b->d_hloc[e].ensure(th * 4)) || (rc = b->d_hrc[e].ensure(th)) || (rc = b->d_hscore[e].ensure(th * 4))) return rc;
+            mh_compact_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, mh, s->mh_counts.as<int32_t>(), b->d_hoff[e].as<uint32_t>(), s->mh_locs.as<uint32_t>(),
+                                                                      s->mh_rcs.as<uint8_t>(), s->mh_scores.as<int32_t>(), b->d_hloc[e].as<uint32_t>(),
+                                                                      b->d_hrc[e].as<uint8_t>(), b->d_hscore[e].as<int32_t>());
+            CUDA_TRY(cudaGetLastError());
+            if ((rc = b->h_hoff[e].ensure((size_t)(n + 1) * 4)) || (rc = b->h_hloc[e].ensure(th * 4)) || (rc = b->h_hrc[e].ensure(th)) || (rc = b->h_hscore[e].ensure(th * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(b->h_hoff[e].p, b->d_hoff[e].p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+            if (total_hits[e]) {
+                CUDA_TRY(cudaMemcpyAsync(b->h_hloc[e].p, b->d_hloc[e].p, (size_t)total_hits[e] * 4, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(b->h_hrc[e].p, b->d_hrc[e].p, (size_t)total_hits[e], cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(b->h_hscore[e].p, b->d_hscore[e].p, (size_t)total_hits[e] * 4, cudaMemcpyDeviceToHost, s->stream));
+            }
+            CUDA_TRY(cudaStreamSynchronize(s->stream));  // the session's dense rows are reused by the next mate / the next caller
+            RNA_MARK(2);
         }
-    } while (0);
-    for (void *p : tmp) cudaFree(p);
-    cudaStreamDestroy(st);
-    return rc;
+    }
+    // phase G: the genome pair, the partial aligner's seed tuples, the filter
+    {
+        BatchSlot slot(b->genome);
+        if ((rc = slot.open())) return rc;
+        snapb200_session *s = slot.s;
+        RNA_MARK(3);
+        if ((rc = snapb200_session_upload(s, 0, &r[0])) || (rc = snapb200_session_upload(s, 1, &r[1]))) return rc;
+        if ((rc = snapb200_session_run_paired(s, &P.paired))) return rc;
+        if ((rc = b->h_pairs.ensure((size_t)n * sizeof(snapb200_paired_result)))) return rc;
+        rc = snapb200_session_download_paired(s, b->h_pairs.as<snapb200_paired_result>());
+        if (rc) return rc;  // includes ERR_LIMIT: the reference exits there
+        if (!s->host_fix.empty())  // the libm re-evaluations of download_paired, mirrored into the resident records the filter reads
+            for (const MapqFix &f : s->host_fix) {
+                const uint32_t pi = f.is_paired_rule ? f.index : f.index >> 1;
+                CUDA_TRY(cudaMemcpyAsync(s->paired_res.as<snapb200_paired_result>() + pi, b->h_pairs.as<snapb200_paired_result>() + pi,
+                                         sizeof(snapb200_paired_result), cudaMemcpyHostToDevice, s->stream));
+            }
+        RNA_MARK(4);
+        uint64_t tuples[2] = {0, 0};
+        for (int e = 0; e < 2; e++)
+            if ((rc = characterize_device(b->genome, s, e, &P.partial, std::max(m0, m1), b->d_cnt[e], b->d_seg[e], b->d_keys[0], b->d_keys[1], b->d_tmp, b->d_cloc[e],
+                                          b->d_coff[e], &tuples[e]))) return rc;
+        RNA_MARK(5);
+        FilterWarpArgs k;
+        memset(&k, 0, sizeof(k));
+        k.prm.max_dist = P.filter.max_dist; k.prm.max_spacing = P.filter.max_spacing; k.prm.conf_diff = P.filter.conf_diff; k.prm.force_spacing = (int32_t)P.filter.force_spacing;
+        k.n = n; k.mh = mh;
+        k.len_is_offsets = 1;
+        for (int e = 0; e < 2; e++) {
+            k.len[e] = s->offsets[e].as<uint32_t>();
+            k.mh_off[e] = b->d_hoff[e].as<uint32_t>(); k.loc[e] = b->d_hloc[e].as<uint32_t>(); k.rc[e] = b->d_hrc[e].as<uint8_t>(); k.score[e] = b->d_hscore[e].as<int32_t>();
+            k.seg[e] = b->d_seg[e].as<unsigned long long>(); k.ch_loc[e] = b->d_cloc[e].as<uint32_t>(); k.ch_off[e] = b->d_coff[e].as<uint16_t>();
+        }
+        k.g = s->paired_res.as<snapb200_paired_result>();
+        if ((rc = b->d_res.ensure((size_t)n * sizeof(FltResult))) || (rc = b->d_ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = b->d_flags.ensure(n))) return rc;
+        CUDA_TRY(cudaMemsetAsync(b->d_res.p, 0, (size_t)n * sizeof(FltResult), s->stream));
+        CUDA_TRY(cudaMemsetAsync(b->d_ev.p, 0, (size_t)n * sizeof(FltEvent), s->stream));
+        k.out = b->d_res.as<FltResult>(); k.ev = b->d_ev.as<FltEvent>(); k.needs_host = b->d_flags.as<uint8_t>();
+        if ((rc = filter_launch(b->ann, k, s->f_scratch, s->f_work, s->stream))) return rc;
+        s->total_launches++;
+        if ((rc = b->h_res.ensure((size_t)n * sizeof(FltResult))) || (rc = b->h_ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = b->h_flags.ensure(n))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->h_res.p, b->d_res.p, (size_t)n * sizeof(FltResult), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->h_ev.p, b->d_ev.p, (size_t)n * sizeof(FltEvent), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->h_flags.p, b->d_flags.p, n, cudaMemcpyDeviceToHost, s->stream));
+        for (int e = 0; e < 2; e++) {
+            const size_t t = std::max<uint64_t>(tuples[e], 1);
+            if ((rc = b->h_seg[e].ensure((2 * (size_t)n + 1) * 8)) || (rc = b->h_cloc[e].ensure(t * 4)) || (rc = b->h_coff[e].ensure(t * 2))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(b->h_seg[e].p, b->d_seg[e].p, (2 * (size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+            if (tuples[e]) {
+                CUDA_TRY(cudaMemcpyAsync(b->h_cloc[e].p, b->d_cloc[e].p, tuples[e] * 4, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(b->h_coff[e].p, b->d_coff[e].p, tuples[e] * 2, cudaMemcpyDeviceToHost, s->stream));
+            }
+        }
+        cudaError_t e2 = cudaStreamSynchronize(s->stream);
+        if (e2 != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "rna batch: %s", cudaGetErrorString(e2));
+        RNA_MARK(6);
+    }
+    if (timing)
+        fprintf(stderr, "[snapb200 rna] %u pairs on device %d: wait T slot %.3f s, multi-hit kernels %.3f, compaction + download %.3f, wait G slot %.3f, paired %.3f, "
+                        "CharacterizeSeeds x2 %.3f, filter + downloads %.3f\n", n, b->genome->device, tt[0], tt[1], tt[2], tt[3], tt[4], tt[5], tt[6]);
+#undef RNA_MARK
+    return 0;
+}
+
+static void rna_worker(snapb200_rna_batch *b)
+{
+    std::unique_lock<std::mutex> lk(b->m);
+    for (;;) {
+        b->cv.wait(lk, [&] { return b->state == 1 || b->state == 3; });
+        if (b->state == 3) return;
+        lk.unlock();
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        const int rc = b->n ? rna_run(b) : 0;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        lk.lock();
+        b->rc = rc;
+        b->device_ms = (float)((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+        if (rc) { strncpy(b->error, g_last_error, sizeof(b->error) - 1); b->error[sizeof(b->error) - 1] = 0; }
+        b->state = 2;
+        b->cv.notify_all();
+    }
+}
+
+extern "C" int snapb200_rna_batch_create(snapb200_annotation *a, snapb200_index *genome, snapb200_index *transcriptome, snapb200_rna_batch **out)
+{
+    if (!a || !genome || !transcriptome || !out) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (a->device != genome->device || a->device != transcriptome->device) return set_error(SNAPB200_ERR_ARG, "annotation, genome and transcriptome index must be on one device");
+    snapb200_rna_batch *b = new snapb200_rna_batch();
+    b->ann = a; b->genome = genome; b->transcriptome = transcriptome;
+    b->worker = std::thread(rna_worker, b);
+    *out = b;
+    return 0;
+}
+
+extern "C" void snapb200_rna_batch_destroy(snapb200_rna_batch *b)
+{
+    if (!b) return;
+    {
+        std::unique_lock<std::mutex> lk(b->m);
+        b->cv.wait(lk, [&] { return b->state != 1; });
+        b->state = 3;
+        b->cv.notify_all();
+    }
+    b->worker.join();
+    cudaSetDevice(b->genome->device);
+    PinBuf *pins[] = {&b->in_off[0], &b->in_off[1], &b->in_bases[0], &b->in_bases[1], &b->in_quals[0], &b->in_quals[1], &b->h_res, &b->h_ev, &b->h_flags, &b->h_pairs,
+                      &b->h_hoff[0], &b->h_hoff[1], &b->h_hloc[0], &b->h_hloc[1], &b->h_hrc[0], &b->h_hrc[1], &b->h_hscore[0], &b->h_hscore[1], &b->h_seg[0], &b->h_seg[1],
+                      &b->h_cloc[0], &b->h_cloc[1], &b->h_coff[0], &b->h_coff[1]};
+    for (PinBuf *p : pins) p->release();
+    DevBuf *devs[] = {&b->d_hoff[0], &b->d_hoff[1], &b->d_hloc[0], &b->d_hloc[1], &b->d_hrc[0], &b->d_hrc[1], &b->d_hscore[0], &b->d_hscore[1], &b->d_seg[0], &b->d_seg[1],
+                      &b->d_cnt[0], &b->d_cnt[1], &b->d_cloc[0], &b->d_cloc[1], &b->d_coff[0], &b->d_coff[1], &b->d_keys[0], &b->d_keys[1], &b->d_tmp, &b->d_res, &b->d_ev,
+                      &b->d_flags};
+    for (DevBuf *d : devs) d->release();
+    delete b;
+}
+
+extern "C" int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0, const snapb200_read_batch *reads1)
+{
+    if (!b || !params || !reads0 || !reads1) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (reads0->n != reads1->n) return set_error(SNAPB200_ERR_ARG, "mate batches differ in size");
+    std::unique_lock<std::mutex> lk(b->m);
+    if (b->state == 1) return set_error(SNAPB200_ERR_ARG, "rna batch: a submitted batch has not been waited for");
+    CUDA_TRY(cudaSetDevice(b->genome->device));
+    const snapb200_read_batch *r[2] = {reads0, reads1};
+    const uint32_t n = reads0->n;
+    for (int e = 0; e < 2 && n; e++) {
+        if (!r[e]->offsets || !r[e]->bases || !r[e]->quals) return set_error(SNAPB200_ERR_ARG, "null read batch");
+        const size_t nb = r[e]->offsets[n];
+        int rc;
+        if ((rc = b->in_off[e].ensure((size_t)(n + 1) * 4)) || (rc = b->in_bases[e].ensure(nb + 16)) || (rc = b->in_quals[e].ensure(nb + 16))) return rc;
+        memcpy(b->in_off[e].p, r[e]->offsets, (size_t)(n + 1) * 4);
+        memcpy(b->in_bases[e].p, r[e]->bases, nb);
+        memcpy(b->in_quals[e].p, r[e]->quals, nb);
+    }
+    b->params = *params;
+    b->n = n;
+    b->state = 1;
+    b->cv.notify_all();
+    return 0;
+}
+
+extern "C" int snapb200_rna_batch_wait(snapb200_rna_batch *b, snapb200_rna_view *view)
+{
+    if (!b || !view) return set_error(SNAPB200_ERR_ARG, "null argument");
+    std::unique_lock<std::mutex> lk(b->m);
+    if (b->state == 0) return set_error(SNAPB200_ERR_ARG, "rna batch: nothing was submitted");
+    b->cv.wait(lk, [&] { return b->state == 2; });
+    b->state = 0;
+    if (b->rc) { strncpy(g_last_error, b->error, sizeof(g_last_error) - 1); return b->rc; }
+    memset(view, 0, sizeof(*view));
+    view->n = b->n;
+    view->device_ms = b->device_ms;
+    if (!b->n) return 0;
+    view->results = b->h_res.as<snapb200_filter_result>();
+    view->events = b->h_ev.as<snapb200_filter_event>();
+    view->needs_host = b->h_flags.as<uint8_t>();
+    view->genome_pairs = b->h_pairs.as<snapb200_paired_result>();
+    for (int e = 0; e < 2; e++) {
+        view->hit_offsets[e] = b->h_hoff[e].as<uint32_t>(); view->hit_locations[e] = b->h_hloc[e].as<uint32_t>();
+        view->hit_rcs[e] = b->h_hrc[e].as<uint8_t>(); view->hit_scores[e] = b->h_hscore[e].as<int32_t>();
+        view->seg_offsets[e] = b->h_seg[e].as<uint64_t>(); view->ch_locations[e] = b->h_cloc[e].as<uint32_t>(); view->ch_seed_offsets[e] = b->h_coff[e].as<uint16_t>();
+    }
+    return 0;
 }

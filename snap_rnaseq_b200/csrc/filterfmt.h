@@ -1,6 +1,6 @@
-// filterfmt.h -- first pieces of the device AlignmentFilter (NOT a product path yet: nothing in the
-// library includes this file).  Plain functions over flat tables, written the way iofmt.h is: the kernels of the next round will
-// call them, and tests/hostsim runs them on the host against the compiled reference today.
+// filterfmt.h -- the per-element rules of the device AlignmentFilter as plain host/device functions
+// over flat tables, written the way iofmt.h is: filter_warp.cuh (the warp-per-pair kernel behind snapb200_filter_paired_batch and
+// snapb200_rna_batch_*) calls them on the device, and tests/hostsim runs the same header on the host against the compiled reference.
 //   flt_make_alignment  AlignmentFilter::AddAlignment      (SNAPLib/AlignmentFilter.cpp:140-214)
 //   flt_genomic_position GTFTranscript::GenomicPosition    (SNAPLib/GTFReader.cpp:1075-1107)
 //   flt_key_compare     the order of std::map<std::string, Alignment> keyed rname + '_' + ToString(pos) (AlignmentFilter.cpp:29)
@@ -26,8 +26,10 @@ struct FltTables {
     // transcripts: chromosome (as a genome piece index), gene, end, and their features in GTFTranscript::exons order
     const int32_t *t_chr, *t_gene; const uint32_t *t_end; const uint32_t *t_feat_first;  // [n_transcripts + 1]
     const uint32_t *f_type, *f_start, *f_end;
-    // genes: chromosome (genome piece index) and extent
+    // genes: chromosome (genome piece index) and extent, in gene-id order (the reference's gene map)
     const int32_t *g_chr; const uint32_t *g_start, *g_end;
+    uint32_t n_genes;
+    int32_t gene_tree_min_stop;  // see flt_gene_found
 };
 
 struct FltAln {  // class Alignment, SNAPLib/AlignmentFilter.h:41-69, with names as indices
@@ -207,6 +209,8 @@ struct FltResult {  // the fields of PairedAlignmentResult the filter writes
     uint32_t location[2], tlocation[2];
     int32_t score[2], mapq[2];
     uint8_t status[2], direction[2], is_transcriptome[2];
+    uint8_t aligned_as_pair;  // result->alignedAsPair as Filter leaves it: true only when a same-gene pair decided (AlignmentFilter.cpp:543-548)
+    uint8_t pad;
 };
 
 // ProcessPairs (AlignmentFilter.cpp:1061-1180) once pairs[0] (and pairs[1]) are the elements std::sort leaves in front.
@@ -265,7 +269,7 @@ FLT_HD bool flt_partial_match(const FltTables &t, const uint32_t *l0, uint32_t n
     for (uint32_t i = 0; i < n0; i++) {
         for (uint32_t j = 0; j < n1; j++) {
             const int p0 = flt_piece_at(t.piece_begin, (int)t.n_pieces, l0[i]), p1 = flt_piece_at(t.piece_begin, (int)t.n_pieces, l1[j]);
-            if (p0 != p1) continue;
+            if (p0 != p1 || p0 < 0) continue;  // before the first contig the reference dereferences a NULL piece; such locations never match here
             const int pos0 = (int)(l0[i] - t.piece_begin[p0] + 1), pos1 = (int)(l1[j] - t.piece_begin[p1] + 1);
             const uint32_t d = (uint32_t)(pos1 > pos0 ? pos1 - pos0 : pos0 - pos1);
             if (d < max_spacing) return true;
@@ -389,6 +393,105 @@ FLT_HD void flt_sort_pairs(FltPair *first, long n)
     }
 }
 
+// ---- AlignmentFilter::UnalignedRead (AlignmentFilter.cpp:742-933): the novel-splice search of a read without any alignment -------------
+// Every distinct location of the read's seed maps becomes a partial alignment (the stretch of the read its seeds cover); every two of
+// them that together cover the read and do not overlap are a candidate splice -- within reach of a gene that covers the first (dropped:
+// the reference records nothing if there is any), on one chromosome, or on two.  The reference hands each to
+// GTFReader::IntrachromosomalSplice / InterchromosomalSplice; here they are records the host appends to the same interval maps.
+struct FltSeg { int32_t chr; uint32_t pos, pos_end, score; };
+
+// GTFReader::IntervalGenes -> IntervalTree::findOverlapping (IntervalTree.h:192-211) finds a gene iff it overlaps [start, stop] (int
+// comparisons) -- except that a tree of fewer than 64 intervals is a single UNSORTED node (:135-137, the root only sorts when it
+// splits) whose scan is skipped altogether when stop < the start of the first interval in insertion order, i.e. of the first gene in
+// gene-id order: gene_tree_min_stop is that start for n_genes < 64 and INT_MIN otherwise.
+FLT_HD bool flt_gene_found(const FltTables &t, uint32_t g, int chr, uint32_t start, uint32_t stop)
+{
+    return t.g_chr[g] == chr && (int32_t)t.g_end[g] >= (int32_t)start && (int32_t)t.g_start[g] <= (int32_t)stop && (int32_t)stop >= t.gene_tree_min_stop;
+}
+
+enum { FLT_SPLICE_NONE = 0, FLT_SPLICE_GENE = 1, FLT_SPLICE_INTRACHR = 2, FLT_SPLICE_INTERCHR = 3 };
+
+// the tests of the pair loop (:809-876) up to the gene query: NONE, INTERCHR, or "same chromosome" (returned as INTRACHR; the
+// caller then asks flt_splice_in_gene)
+FLT_HD int flt_splice_class(const FltSeg &a0, const FltSeg &a1, uint32_t read_len, uint32_t seed_len)
+{
+    if ((uint32_t)((int32_t)a0.score + (int32_t)a1.score) < read_len - seed_len) return FLT_SPLICE_NONE;  // int sum against unsigned, as there
+    if (!(a0.pos > a1.pos_end) && !(a1.pos > a0.pos_end)) return FLT_SPLICE_NONE;
+    return a0.chr != a1.chr ? FLT_SPLICE_INTERCHR : FLT_SPLICE_INTRACHR;
+}
+
+FLT_HD bool flt_splice_in_gene(const FltTables &t, const FltSeg &a0, const FltSeg &a1)
+{
+    for (uint32_t g = 0; g < t.n_genes; g++)
+        if (flt_gene_found(t, g, a0.chr, a0.pos, a0.pos_end) && flt_check_boundary(t, (int)g, a1.chr, a1.pos)) return true;
+    return false;
+}
+
+// The partial alignments in the reference's order (forward map ascending, then RC map ascending) from the CharacterizeSeeds tuples
+// (snapb200_characterize_batch layout).  Returns their number, or -1 if there are more than cap.  A location before the first
+// contig -- where the reference dereferences a NULL piece -- yields no segment.
+FLT_HD int flt_unaligned_segments(const FltTables &t, const uint32_t *locs, const uint16_t *offs, uint64_t lo, uint64_t mid, uint64_t hi, uint32_t read_len,
+                                  uint32_t seed_len, FltSeg *out, uint32_t cap)
+{
+    uint32_t n = 0;
+    uint64_t k = lo;
+    while (k < hi) {
+        const bool rc = k >= mid;
+        const uint64_t end = rc ? hi : mid;
+        uint64_t e = k;
+        while (e + 1 < end && locs[e + 1] == locs[k]) e++;
+        const int p = flt_piece_at(t.piece_begin, (int)t.n_pieces, locs[k]);
+        if (p >= 0) {
+            if (n >= cap) return -1;
+            const uint32_t length = (uint32_t)(offs[e] - offs[k]) + seed_len;  // (largest - smallest seed offset) + seedLen
+            const int32_t pos0 = (int32_t)(locs[k] - t.piece_begin[p] + 1);
+            const uint32_t start = rc ? (uint32_t)pos0 + read_len - ((uint32_t)offs[e] + seed_len) : (uint32_t)pos0 + offs[k];
+            out[n].chr = p; out[n].pos = start; out[n].pos_end = start + length - 1; out[n].score = length;
+            n++;
+        }
+        k = e + 1;
+    }
+    return (int)n;
+}
+
+struct FltSplice {  // one GTFReader::IntrachromosomalSplice (kind 2) / InterchromosomalSplice (kind 3) call
+    uint32_t pair;      // pair index in the batch; the read id is read 0's or read 1's, whichever UnalignedRead was called for
+    int32_t kind;
+    int32_t chr[2];
+    uint32_t pos[2], pos_end[2];
+};
+
+// The whole search for one read, serially (the specification the warp version of filter_warp.cuh is tested against).  out may be
+// NULL (count only).  Returns the number of records, *kind = which call they are for.
+FLT_HD uint64_t flt_unaligned_splices(const FltTables &t, const FltSeg *seg, uint32_t n, uint32_t read_len, uint32_t seed_len, uint32_t pair, int *kind,
+                                      FltSplice *out)
+{
+    uint64_t c_intra = 0, c_inter = 0;
+    bool gene = false;
+    for (uint32_t i = 0; i < n && !gene; i++)
+        for (uint32_t j = i + 1; j < n; j++) {
+            const int c = flt_splice_class(seg[i], seg[j], read_len, seed_len);
+            if (c == FLT_SPLICE_INTERCHR) c_inter++;
+            else if (c == FLT_SPLICE_INTRACHR) { if (flt_splice_in_gene(t, seg[i], seg[j])) { gene = true; break; } c_intra++; }
+        }
+    *kind = gene ? FLT_SPLICE_NONE : c_intra ? FLT_SPLICE_INTRACHR : c_inter ? FLT_SPLICE_INTERCHR : FLT_SPLICE_NONE;
+    if (*kind == FLT_SPLICE_NONE) return 0;
+    const uint64_t total = *kind == FLT_SPLICE_INTRACHR ? c_intra : c_inter;
+    if (out) {
+        uint64_t w = 0;
+        for (uint32_t i = 0; i < n; i++)
+            for (uint32_t j = i + 1; j < n; j++) {
+                int c = flt_splice_class(seg[i], seg[j], read_len, seed_len);
+                if (c != *kind) continue;
+                FltSplice &s = out[w++];
+                s.pair = pair; s.kind = c;
+                s.chr[0] = seg[i].chr; s.pos[0] = seg[i].pos; s.pos_end[0] = seg[i].pos_end;
+                s.chr[1] = seg[j].chr; s.pos[1] = seg[j].pos; s.pos_end[1] = seg[j].pos_end;
+            }
+    }
+    return total;
+}
+
 // ---- what the host still has to do per pair: the GTF statistics -------------------------------------------------------------------
 // None of them feeds back into the pair's result, so the kernel reports WHAT to count and the host calls the reference's own public
 // GTFReader methods in input order (AlignmentFilter.cpp:529-713): IncrementReadCount for a unique same-gene pair,
@@ -450,6 +553,7 @@ FLT_HD int flt_filter_pair(const FltTables &t, const FltParams &prm, const FltPa
         r.location[e] = in.g_location[e]; r.tlocation[e] = 0; r.score[e] = in.g_score[e]; r.mapq[e] = in.g_mapq[e];
         r.status[e] = in.g_status[e]; r.direction[e] = in.g_direction[e]; r.is_transcriptome[e] = 0;
     }
+    r.aligned_as_pair = 0; r.pad = 0;
     ev->kind = FLT_EV_NONE;
     ev->unaligned = (n[0] == 0 && n[1] != 0) ? 1 : (n[1] == 0 && n[0] != 0) ? 2 : 0;
     for (int e = 0; e < 2; e++) { ev->transcript[e] = -1; ev->chr[e] = 0; ev->pos_original[e] = ev->pos[e] = ev->pos_end[e] = 0; }
@@ -477,6 +581,7 @@ FLT_HD int flt_filter_pair(const FltTables &t, const FltParams &prm, const FltPa
         if (chosen == FLT_INTRAGENE) {
             report = r.status[0] == 1;
             kind = FLT_EV_INCREMENT;
+            r.aligned_as_pair = 1;
         } else {
             if (chosen != FLT_NO_RC && r.status[0] == 1 && count[FLT_NO_RC]) {  // CheckNoRC: any same-chromosome same-strand pair that scores better
                 const uint32_t sum = (uint32_t)(r.score[0] + r.score[1]);

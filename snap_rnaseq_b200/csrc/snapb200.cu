@@ -509,6 +509,7 @@ struct snapb200_session {
     DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
     DevBuf p_cands, p_mates, p_anchors, p_lane_tables, p_order;
     DevBuf w_keys[2], w_vals[2], w_tmp;  // work ordering of the paired path (weigh_kernel + radix sort)
+    DevBuf f_scratch, f_work;            // per-warp scratch of filter_warp_kernel when it runs on this session's stream (rna batches)
     uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
     uint32_t anchors_warps = 0;
     // last run
@@ -558,7 +559,7 @@ extern "C" void snapb200_session_destroy(snapb200_session *s)
                      &s->paired_res, &s->fb_single_res, &s->retry_list, &s->fallback_list, &s->fb_positions, &s->fix, &s->counters,
                      &s->mh_counts, &s->mh_locs, &s->mh_rcs, &s->mh_scores, &s->s_pool, &s->s_anchors, &s->s_lists, &s->s_epochs,
                      &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables, &s->p_order,
-                     &s->w_keys[0], &s->w_keys[1], &s->w_vals[0], &s->w_vals[1], &s->w_tmp};
+                     &s->w_keys[0], &s->w_keys[1], &s->w_vals[0], &s->w_vals[1], &s->w_tmp, &s->f_scratch, &s->f_work};
     for (DevBuf *b : all) b->release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1301,6 +1302,70 @@ extern "C" int snapb200_cigar_batch(snapb200_index *idx, const snapb200_read_bat
 }
 
 // ---- CharacterizeSeeds -------------------------------------------------------------------------------------------
+// One launch group over the batch resident in slot `mate_slot` of `ss`; the results stay in HBM: d_off = exclusive segment offsets
+// [2k + 1] (the last one is the number of tuples, also returned), d_loc / d_so = the ordered tuples.  The stream is idle on return
+// only as far as the tuple count needed it; the caller synchronises before reading the buffers from the host.
+static int characterize_device(snapb200_index *idx, snapb200_session *ss, int mate_slot, const snapb200_single_params *params, uint32_t max_len,
+                               DevBuf &d_cnt, DevBuf &d_off, DevBuf &d_keys0, DevBuf &d_keys1, DevBuf &d_tmp, DevBuf &d_loc, DevBuf &d_so, uint64_t *total_out,
+                               bool count_only = false)
+{
+    const uint32_t k = ss->n[mate_slot];
+    const size_t n_seg = (size_t)2 * k;
+    int rc;
+    if ((rc = d_cnt.ensure((n_seg + 1) * 8)) || (rc = d_off.ensure((n_seg + 1) * 8))) return rc;
+    CharArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ix = idx->dev; a.b = dev_batch(ss, mate_slot);
+    a.max_hits = params->max_hits; a.max_k = params->max_k; a.num_seeds = params->num_seeds;
+    a.explore = params->explore_popular_seeds; a.seed_coverage = params->seed_coverage;
+    a.rl = std::max(32u, (max_len + 15) & ~15u);
+    a.ctr = ss->counters.as<Counters>();
+    const size_t smem = char_warp_shared(a.rl) * WARPS_PER_CTA;
+    int per_sm;
+    const int grid_c = grid_for(characterize_kernel<false>, smem, idx->sm_count, &per_sm);
+    const int grid_e = grid_for(characterize_kernel<true>, smem, idx->sm_count, &per_sm);
+    // pass 1: segment sizes
+    CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, (n_seg + 1) * 8, ss->stream));
+    if ((rc = reset_work(ss))) return rc;
+    a.seg = d_cnt.as<unsigned long long>();
+    characterize_kernel<false><<<grid_c, CTA_THREADS, smem, ss->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "characterize_kernel launch: %s", cudaGetErrorString(e));
+    ss->total_launches++;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt.as<unsigned long long>(), d_off.as<unsigned long long>(), n_seg + 1, ss->stream);
+    if ((rc = d_tmp.ensure(tmp_bytes))) return rc;
+    e = cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_cnt.as<unsigned long long>(), d_off.as<unsigned long long>(), n_seg + 1, ss->stream);
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "characterize scan: %s", cudaGetErrorString(e));
+    unsigned long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_off.as<unsigned long long>() + n_seg, 8, cudaMemcpyDeviceToHost, ss->stream));
+    e = cudaStreamSynchronize(ss->stream);
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "characterize_kernel: %s", cudaGetErrorString(e));
+    *total_out = total;
+    if (!total || count_only) return 0;
+    if ((rc = d_keys0.ensure(total * 8)) || (rc = d_keys1.ensure(total * 8)) || (rc = d_loc.ensure(total * 4)) || (rc = d_so.ensure(total * 2))) return rc;
+    // pass 2: one key per tuple, then order every segment
+    if ((rc = reset_work(ss))) return rc;
+    a.seg = d_off.as<unsigned long long>();
+    a.keys = d_keys0.as<unsigned long long>();
+    characterize_kernel<true><<<grid_e, CTA_THREADS, smem, ss->stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "characterize_kernel launch: %s", cudaGetErrorString(e));
+    ss->total_launches++;
+    int seg_bits = 1;
+    while (((size_t)1 << seg_bits) < n_seg) seg_bits++;
+    cub::DoubleBuffer<unsigned long long> kb(d_keys0.as<unsigned long long>(), d_keys1.as<unsigned long long>());
+    tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, kb, (unsigned long long)total, 0, CHAR_SEG_SHIFT + seg_bits, ss->stream);
+    if ((rc = d_tmp.ensure(tmp_bytes))) return rc;
+    e = cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, kb, (unsigned long long)total, 0, CHAR_SEG_SHIFT + seg_bits, ss->stream);
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "characterize sort: %s", cudaGetErrorString(e));
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    characterize_split_kernel<<<blocks, 256, 0, ss->stream>>>(kb.Current(), total, d_loc.as<uint32_t>(), d_so.as<uint16_t>());
+    ss->total_launches++;
+    return 0;
+}
+
 extern "C" int snapb200_characterize_batch(snapb200_index *idx, const snapb200_single_params *params, const snapb200_read_batch *reads,
                                            uint64_t *seg_offsets, uint32_t *locations, uint16_t *seed_offsets, uint64_t capacity)
 {
@@ -1327,67 +1392,23 @@ extern "C" int snapb200_characterize_batch(snapb200_index *idx, const snapb200_s
         snapb200_read_batch sb = sub_batch(reads, lo, hi, off_store);
         if ((rc = snapb200_session_upload(ss, 0, &sb))) break;
         const size_t n_seg = (size_t)2 * k;
-        if ((rc = d_seg.ensure((n_seg + 1) * 8)) || (rc = d_off.ensure((n_seg + 1) * 8))) break;
-        CharArgs a;
-        memset(&a, 0, sizeof(a));
-        a.ix = idx->dev; a.b = dev_batch(ss, 0);
-        a.max_hits = params->max_hits; a.max_k = params->max_k; a.num_seeds = params->num_seeds;
-        a.explore = params->explore_popular_seeds; a.seed_coverage = params->seed_coverage;
-        a.rl = std::max(32u, (m + 15) & ~15u);
-        a.ctr = ss->counters.as<Counters>();
-        const size_t smem = char_warp_shared(a.rl) * WARPS_PER_CTA;
-        int per_sm;
-        const int grid_c = grid_for(characterize_kernel<false>, smem, idx->sm_count, &per_sm);
-        const int grid_e = grid_for(characterize_kernel<true>, smem, idx->sm_count, &per_sm);
-        // pass 1: segment sizes
-        cudaMemsetAsync(d_seg.p, 0, (n_seg + 1) * 8, ss->stream);
-        if ((rc = reset_work(ss))) break;
-        a.seg = d_seg.as<unsigned long long>();
-        characterize_kernel<false><<<grid_c, CTA_THREADS, smem, ss->stream>>>(a);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize_kernel launch: %s", cudaGetErrorString(e)); break; }
-        ss->total_launches++;
-        size_t tmp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_seg.as<unsigned long long>(), d_off.as<unsigned long long>(), n_seg + 1, ss->stream);
-        if ((rc = d_tmp.ensure(tmp_bytes))) break;
-        e = cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_seg.as<unsigned long long>(), d_off.as<unsigned long long>(), n_seg + 1, ss->stream);
-        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize scan: %s", cudaGetErrorString(e)); break; }
+        uint64_t total = 0;
+        if ((rc = characterize_device(idx, ss, 0, params, m, d_seg, d_off, d_keys0, d_keys1, d_tmp, d_loc, d_so, &total, locations == nullptr))) break;
         cudaMemcpyAsync(seg_offsets + (size_t)2 * lo, d_off.p, (n_seg + 1) * 8, cudaMemcpyDeviceToHost, ss->stream);
-        e = cudaStreamSynchronize(ss->stream);
-        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize_kernel: %s", cudaGetErrorString(e)); break; }
-        const uint64_t total = seg_offsets[(size_t)2 * lo + n_seg];
-        if (base) for (size_t q = 0; q <= n_seg; q++) seg_offsets[(size_t)2 * lo + q] += base;
         if (locations && total) {
             if (base + total > capacity) {
+                cudaStreamSynchronize(ss->stream);
+                if (base) for (size_t q = 0; q <= n_seg; q++) seg_offsets[(size_t)2 * lo + q] += base;
                 rc = set_error(SNAPB200_ERR_ARG, "characterize: output capacity %llu too small (reads %u..%u alone need %llu more tuples)",
                                (unsigned long long)capacity, lo, hi, (unsigned long long)total);
                 break;
             }
-            if ((rc = d_keys0.ensure(total * 8)) || (rc = d_keys1.ensure(total * 8)) || (rc = d_loc.ensure(total * 4)) || (rc = d_so.ensure(total * 2))) break;
-            // pass 2: one key per tuple, then order every segment
-            if ((rc = reset_work(ss))) break;
-            a.seg = d_off.as<unsigned long long>();
-            a.keys = d_keys0.as<unsigned long long>();
-            characterize_kernel<true><<<grid_e, CTA_THREADS, smem, ss->stream>>>(a);
-            e = cudaGetLastError();
-            if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize_kernel launch: %s", cudaGetErrorString(e)); break; }
-            ss->total_launches++;
-            int seg_bits = 1;
-            while (((size_t)1 << seg_bits) < n_seg) seg_bits++;
-            cub::DoubleBuffer<unsigned long long> kb(d_keys0.as<unsigned long long>(), d_keys1.as<unsigned long long>());
-            tmp_bytes = 0;
-            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, kb, (unsigned long long)total, 0, CHAR_SEG_SHIFT + seg_bits, ss->stream);
-            if ((rc = d_tmp.ensure(tmp_bytes))) break;
-            e = cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, kb, (unsigned long long)total, 0, CHAR_SEG_SHIFT + seg_bits, ss->stream);
-            if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize sort: %s", cudaGetErrorString(e)); break; }
-            const unsigned blocks = (unsigned)((total + 255) / 256);
-            characterize_split_kernel<<<blocks, 256, 0, ss->stream>>>(kb.Current(), total, d_loc.as<uint32_t>(), d_so.as<uint16_t>());
-            ss->total_launches++;
             cudaMemcpyAsync(locations + base, d_loc.p, total * 4, cudaMemcpyDeviceToHost, ss->stream);
             cudaMemcpyAsync(seed_offsets + base, d_so.p, total * 2, cudaMemcpyDeviceToHost, ss->stream);
-            e = cudaStreamSynchronize(ss->stream);
-            if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize emit: %s", cudaGetErrorString(e)); break; }
         }
+        cudaError_t e = cudaStreamSynchronize(ss->stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "characterize emit: %s", cudaGetErrorString(e)); break; }
+        if (base) for (size_t q = 0; q <= n_seg; q++) seg_offsets[(size_t)2 * lo + q] += base;
         base += total;
     }
     d_seg.release(); d_off.release(); d_keys0.release(); d_keys1.release(); d_tmp.release(); d_loc.release(); d_so.release();

@@ -74,18 +74,15 @@ public:
         params_.stop_on_first_hit = 0; params_.max_hits_to_get = 0;
         current_[0] = current_[1] = NULL;
         index_ = 0;
+        memset(view_, 0, sizeof(view_));
     }
 
-    // one device call per mate for the whole batch; returns the library's status
-    int compute(snapb200_index *idx, int mate, const snapb200_read_batch *reads)
+    const snapb200_single_params &params() const { return params_; }
+
+    // the seed tuples of a whole batch, as snapb200_rna_batch_wait hands them out (borrowed: valid until the next submit)
+    void borrow(int mate, const uint64_t *seg, const uint32_t *loc, const uint16_t *off)
     {
-        Maps &m = maps_[mate];
-        m.seg.assign((size_t)2 * reads->n + 1, 0);
-        int rc = snapb200_characterize_batch(idx, &params_, reads, &m.seg[0], NULL, NULL, 0);
-        if (rc != SNAPB200_OK) return rc;
-        const size_t total = (size_t)m.seg[(size_t)2 * reads->n];
-        m.loc.resize(total + 1); m.off.resize(total + 1);
-        return snapb200_characterize_batch(idx, &params_, reads, &m.seg[0], &m.loc[0], &m.off[0], total);
+        view_[mate].seg = seg; view_[mate].loc = loc; view_[mate].off = off;
     }
 
     // the filter is about to be run on read i of the batch, whose mates live at r0 / r1 (r0 may be NULL: single end)
@@ -100,7 +97,7 @@ public:
         if (hitDirection != NULL) *hitDirection = FORWARD;
         if (finalScore != NULL) *finalScore = 0xffff;
         const int mate = (inputRead == current_[1] && current_[0] != NULL) ? 1 : 0;
-        const Maps &m = maps_[mate];
+        const View &m = view_[mate];
         seed_map *out[2] = {&map, &mapRC};
         for (int d = 0; d < 2; d++) {
             const size_t s = (size_t)2 * index_ + d;
@@ -114,36 +111,37 @@ public:
     }
 
 private:
-    struct Maps { std::vector<uint64_t> seg; std::vector<uint32_t> loc; std::vector<uint16_t> off; };
-    Maps maps_[2];
+    struct View { const uint64_t *seg; const uint32_t *loc; const uint16_t *off; };
+    View view_[2];
     snapb200_single_params params_;
     const Read *current_[2];
     unsigned index_;
 };
 
+// AlignmentFilter::UnalignedRead (the novel-splice search over the seed maps of a read without alignments, SNAPLib/AlignmentFilter.cpp:
+// 742-933) is protected; the extension calls it for the reads the device filter flags (snapb200_filter_event::unaligned).
+class FilterAccess : public AlignmentFilter {
+public:
+    FilterAccess(Read *r0, Read *r1, const Genome *g, const Genome *t, GTFReader *gtf, unsigned minSpacing, unsigned maxSpacing, unsigned confDiff,
+                 unsigned maxDist, unsigned seedLen, BaseAligner *special)
+        : AlignmentFilter(r0, r1, g, t, gtf, minSpacing, maxSpacing, confDiff, maxDist, seedLen, special) {}
+    void unaligned(Read *read, unsigned minDiff) { UnalignedRead(read, minDiff); }
+};
+
 class GpuAlignerExtension : public AlignerExtension {
 public:
-    explicit GpuAlignerExtension(int device = 0, unsigned batchReads = 1u << 17)
-        : device_(device), batch_(batchReads), genome_(NULL), transcriptome_(NULL), contamination_(NULL), owner_(true) {}
+    // batchReads: pairs (or reads) per device batch.  Devices: every visible GPU (SNAPB200_DEVICES=n limits it); batches are dealt
+    // round-robin over them from this one process (GTF counters are process-global, so one process drives all).
+    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true) {}
 
-    virtual ~GpuAlignerExtension() {}  // indices stay resident for the life of the process (see open())
+    virtual ~GpuAlignerExtension() {}  // indices stay resident for the life of the process (see deviceSet())
 
     // One copy per worker thread (ParallelTask); the HBM-resident indices are shared, read-only.
     virtual AlignerExtension *copy()
     {
-        GpuAlignerExtension *c = new GpuAlignerExtension(device_, batch_);
-        c->genome_ = genome_; c->transcriptome_ = transcriptome_; c->contamination_ = contamination_;
-        c->genomeDir_ = genomeDir_; c->transcriptomeDir_ = transcriptomeDir_; c->contaminationDir_ = contaminationDir_;
+        GpuAlignerExtension *c = new GpuAlignerExtension(batch_);
         c->owner_ = false;
         return c;
-    }
-
-    // AlignerContext::initialize() has loaded the host-side GenomeIndex objects; mirror them into HBM once.
-    void attach(const AlignerOptions *options)
-    {
-        open(options->indexDir, &genome_, &genomeDir_);
-        open(options->transcriptomeDir, &transcriptome_, &transcriptomeDir_);
-        if (options->contaminationDir != NULL) open(options->contaminationDir, &contamination_, &contaminationDir_);
     }
 
     // ---- single end: replaces the loop at SNAPLib/SingleAligner.cpp:243-304 ----
@@ -151,209 +149,178 @@ public:
     {
         if (ctx->index == NULL) return false;  // "-" index: I/O only, leave it to the reference
         SingleAlignerContext *sc = (SingleAlignerContext *)ctx;
-        if (genome_ == NULL) attach(ctx->options);
+        const std::vector<DeviceSet> &devs = deviceSets(ctx->options, false);
         snapb200_single_params p = singleParams(ctx);
-        // the aligner AlignmentFilter calls CharacterizeSeeds on (SingleAligner.cpp:168 passes g_aligner); served from the device
+        // the aligner AlignmentFilter would call CharacterizeSeeds on (SingleAligner.cpp:168 passes g_aligner); FilterSingle never does
         GpuSeedCharacterizer *partial = new GpuSeedCharacterizer(ctx->index, ctx->maxHits, ctx->maxDist, ctx->numSeedsFromCommandLine,
                                                                  ctx->seedCoverage, ctx->extraSearchDepth,
                                                                  ctx->options->explorePopularSeeds);
         ReadStore store;
         std::vector<snapb200_single_result> tres, gres, cres;
+        std::vector<uint32_t> contamIdx;
         Read *read;
         bool more = true;
         while (more) {
             store.clear();
-            std::vector<char> useful;
             while (store.size() < batch_ && (more = (NULL != (read = supplier->getNextRead())))) {
                 ctx->stats->totalReads++;
                 bool quality = read->qualityFilter(ctx->options->minPercentAbovePhred, ctx->options->minPhred, ctx->options->phredOffset);
                 bool ok = !(read->getDataLength() < 50 || read->countOfNs() > ctx->maxDist || !quality);  // SingleAligner.cpp:247-254
-                store.add(read);
-                useful.push_back(ok);
+                store.add(read, ok);
             }
             if (store.size() == 0) break;
+            const DeviceSet &dev = devs[nextDevice(devs.size())];
             snapb200_read_batch rb = store.batch();
-            tres.resize(store.size()); gres.resize(store.size());
-            check(snapb200_single_batch(transcriptome_, &p, &rb, &tres[0]));
-            check(snapb200_single_batch(genome_, &p, &rb, &gres[0]));
-            check(partial->compute(genome_, 0, &rb));
-            bool needContam = false;
-            std::vector<AlignmentResult> final(store.size(), NotFound);
-            // replay, in input order
-            for (unsigned i = 0; i < store.size(); i++) {
+            tres.resize(rb.n + 1); gres.resize(rb.n + 1);
+            check(snapb200_single_batch(dev.transcriptome, &p, &rb, &tres[0]));
+            check(snapb200_single_batch(dev.genome, &p, &rb, &gres[0]));
+            // pass 1: the filter's verdict per read (no side effects on shared state); reads still unaligned go to the contamination index
+            const unsigned n = store.size();
+            std::vector<AlignmentResult> status(n, NotFound);
+            std::vector<unsigned> location(n, InvalidGenomeLocation), tlocation(n, 0);
+            std::vector<Direction> direction(n, FORWARD);
+            std::vector<int> score(n, 0), mapq(n, 0);
+            std::vector<char> isT(n, 0);
+            contamIdx.clear();
+            for (unsigned i = 0; i < n; i++) {
+                const int di = store.deviceIndex(i);
+                if (di < 0) continue;
                 Read r;
                 store.get(i, &r, ctx->clipping);
-                if (!useful[i]) {
+                bool isTranscriptome = false;
+                AlignmentFilter filter(NULL, &r, ctx->index->getGenome(), ctx->transcriptome->getGenome(), ctx->gtf, 0, 0,
+                                       ctx->options->confDiff, ctx->options->maxDist.start, ctx->index->getSeedLength(), partial);
+                filter.AddAlignment(tres[di].location, tres[di].direction, tres[di].score, tres[di].mapq, true, true);
+                filter.AddAlignment(gres[di].location, gres[di].direction, gres[di].score, gres[di].mapq, false, true);
+                status[i] = filter.FilterSingle(&location[i], &direction[i], &score[i], &mapq[i], &isTranscriptome, &tlocation[i]);
+                isT[i] = isTranscriptome;
+                if (status[i] == NotFound && dev.contamination != NULL) contamIdx.push_back(i);
+            }
+            if (!contamIdx.empty()) {  // SingleAligner.cpp:282-294, batched
+                ReadStore sub;
+                for (size_t q = 0; q < contamIdx.size(); q++) sub.addFrom(store, contamIdx[q]);
+                snapb200_read_batch cb = sub.batch();
+                cres.resize(cb.n);
+                check(snapb200_single_batch(dev.contamination, &p, &cb, &cres[0]));
+                for (size_t q = 0; q < contamIdx.size(); q++)
+                    if (cres[q].status != NotFound) ctx->c_filter->AddAlignment(cres[q].location, cres[q].direction, cres[q].score, cres[q].mapq, false, false);
+            }
+            // pass 2: output and statistics, in input order
+            for (unsigned i = 0; i < n; i++) {
+                Read r;
+                store.get(i, &r, ctx->clipping);
+                if (store.deviceIndex(i) < 0) {
                     if (ctx->readWriter != NULL && ctx->options->passFilter(&r, NotFound))
                         ctx->readWriter->writeRead(&r, NotFound, 0, InvalidGenomeLocation, false, false, 0);
                     continue;
                 }
                 ctx->stats->usefulReads++;
-                unsigned location = InvalidGenomeLocation, tlocation = 0;
-                Direction direction = FORWARD;
-                int score = 0, mapq = 0;
-                bool isTranscriptome = false;
-                partial->select(i, NULL, &r);
-                AlignmentFilter filter(NULL, &r, ctx->index->getGenome(), ctx->transcriptome->getGenome(), ctx->gtf, 0, 0,
-                                       ctx->options->confDiff, ctx->options->maxDist.start, ctx->index->getSeedLength(), partial);
-                filter.AddAlignment(tres[i].location, tres[i].direction, tres[i].score, tres[i].mapq, true, true);
-                filter.AddAlignment(gres[i].location, gres[i].direction, gres[i].score, gres[i].mapq, false, true);
-                AlignmentResult result = filter.FilterSingle(&location, &direction, &score, &mapq, &isTranscriptome, &tlocation);
-                if (result == NotFound && contamination_ != NULL) {
-                    snapb200_read_batch one = store.one(i);
-                    snapb200_single_result c;
-                    check(snapb200_single_batch(contamination_, &p, &one, &c));
-                    if (c.status != NotFound) ctx->c_filter->AddAlignment(c.location, c.direction, c.score, c.mapq, false, false);
-                }
                 bool wasError = false;
-                if (result != NotFound && ctx->computeError) wasError = wgsimReadMisaligned(&r, location, ctx->index, ctx->options->misalignThreshold);
-                AlignerContext2::writeRead(sc, &r, result, location, direction, isTranscriptome, tlocation, score, mapq);
-                AlignerContext2::updateStats(sc, &r, result, location, score, mapq, wasError);
+                if (status[i] != NotFound && ctx->computeError) wasError = wgsimReadMisaligned(&r, location[i], ctx->index, ctx->options->misalignThreshold);
+                AlignerContext2::writeRead(sc, &r, status[i], location[i], direction[i], isT[i] != 0, tlocation[i], score[i], mapq[i]);
+                AlignerContext2::updateStats(sc, &r, status[i], location[i], score[i], mapq[i], wasError);
             }
-            (void)needContam;
         }
         delete partial;
         return true;
     }
 
     // ---- paired end: replaces the loop at SNAPLib/PairedAligner.cpp:547-668 ----
+    // Two batch objects per thread: while batch k is on a device (transcriptome multi-hits, genome pair, seed tuples and the
+    // AlignmentFilter decision, all resident in HBM), the thread drains the supplier into batch k+1 and replays batch k-1: the
+    // GTF counters through GTFReader's public methods, writePair, updateStats -- in input order.
     virtual bool runIterationThread(PairedReadSupplier *supplier, AlignerContext *ctx)
     {
         if (ctx->index == NULL) return false;
         PairedAlignerContext *pc = (PairedAlignerContext *)ctx;
-        if (genome_ == NULL) attach(ctx->options);
-        snapb200_paired_params pp;
+        const double tEnter = now();
+        const std::vector<DeviceSet> &devs = deviceSets(ctx->options, true);
+        const double tInit = now() - tEnter;
+        threadEnters();
+        snapb200_rna_params P;
+        snapb200_paired_params &pp = P.paired;
         pp.max_hits = ctx->maxHits; pp.max_k = ctx->maxDist; pp.max_read_size = MAX_READ_LENGTH;
         pp.num_seeds = ctx->numSeedsFromCommandLine; pp.seed_coverage = ctx->seedCoverage;
         pp.min_spacing = AlignerContext2::minSpacing(pc); pp.max_spacing = AlignerContext2::maxSpacing(pc);
         pp.force_spacing = AlignerContext2::forceSpacing(pc); pp.max_big_hits = AlignerContext2::maxBigHits(pc);
         pp.extra_search_depth = ctx->extraSearchDepth; pp.max_candidate_pool_size = AlignerContext2::maxCandidatePoolSize(pc);
-        snapb200_single_params tp = singleParams(ctx);  // transcriptomeAligner, PairedAligner.cpp:512
-        const unsigned maxHitsToGet = 1000;             // PairedAligner.cpp:584
-        tp.max_hits_to_get = maxHitsToGet;
+        P.transcriptome = singleParams(ctx);             // transcriptomeAligner, PairedAligner.cpp:512
+        P.transcriptome.max_hits_to_get = 1000;          // PairedAligner.cpp:584
         // partialAligner, PairedAligner.cpp:518-527: maxHits 300, 12 seeds; its CharacterizeSeeds is served from the device
         GpuSeedCharacterizer *partial = new GpuSeedCharacterizer(ctx->index, 300, ctx->maxDist, 12, ctx->seedCoverage, ctx->extraSearchDepth,
                                                                  ctx->options->explorePopularSeeds);
-        ReadStore s0, s1;
-        std::vector<snapb200_paired_result> res, cres;
-        std::vector<snapb200_single_result> t0, t1;
-        std::vector<int32_t> n0, n1, sc0, sc1;
-        std::vector<uint32_t> l0, l1;
-        std::vector<uint8_t> rc0, rc1;
-        Read *read0, *read1;
-        bool more = true;
-        double tDrain = 0, tAbi = 0, tReplay = 0, tMark, tCall[3] = {0, 0, 0};
-        unsigned long nReads = 0;
-        while (more) {
-            s0.clear(); s1.clear();
-            std::vector<char> skip;
-            tMark = now();
-            while (s0.size() < batch_ && (more = supplier->getNextReadPair(&read0, &read1))) {
-                if (!AlignerContext2::ignoreMismatchedIDs(pc)) Read::checkIdMatch(read0, read1);
-                ctx->stats->totalReads += 2;
-                int maxDist = ctx->maxDist;
-                bool useful0 = read0->getDataLength() >= 50 && (int)read0->countOfNs() <= maxDist;
-                bool useful1 = read1->getDataLength() >= 50 && (int)read1->countOfNs() <= maxDist;
-                bool quality0 = read0->qualityFilter(ctx->options->minPercentAbovePhred, ctx->options->minPhred, ctx->options->phredOffset);
-                bool bad = (!useful0 && !useful1) || (!quality0 || !quality0);  // sic, PairedAligner.cpp:564
-                if (!bad) ctx->stats->usefulReads += (useful0 && useful1) ? 2 : 1;
-                s0.add(read0); s1.add(read1);
-                skip.push_back(bad);
-            }
-            const unsigned n = s0.size();
-            tDrain += now() - tMark;
-            if (n == 0) break;
-            nReads += 2ul * n;
-            tMark = now();
-            snapb200_read_batch b0 = s0.batch(), b1 = s1.batch();
-            res.resize(n); t0.resize(n); t1.resize(n); n0.resize(n); n1.resize(n);
-            l0.resize((size_t)n * maxHitsToGet); l1.resize((size_t)n * maxHitsToGet); rc0.resize((size_t)n * maxHitsToGet);
-            rc1.resize((size_t)n * maxHitsToGet); sc0.resize((size_t)n * maxHitsToGet); sc1.resize((size_t)n * maxHitsToGet);
-            double tc = now();
-            check(snapb200_single_multihit_batch(transcriptome_, &tp, &b0, &t0[0], &n0[0], &l0[0], &rc0[0], &sc0[0]));
-            check(snapb200_single_multihit_batch(transcriptome_, &tp, &b1, &t1[0], &n1[0], &l1[0], &rc1[0], &sc1[0]));
-            tCall[0] += now() - tc; tc = now();
-            check(snapb200_paired_batch(genome_, &pp, &b0, &b1, &res[0]));
-            tCall[1] += now() - tc; tc = now();
-            check(partial->compute(genome_, 0, &b0));
-            check(partial->compute(genome_, 1, &b1));
-            tCall[2] += now() - tc;
-            tAbi += now() - tMark;
-            tMark = now();
-            for (unsigned i = 0; i < n; i++) {
-                Read r0, r1;
-                s0.get(i, &r0, ctx->clipping); s1.get(i, &r1, ctx->clipping);
-                PairedAlignmentResult result;
-                if (skip[i]) {
-                    result.status[0] = result.status[1] = NotFound;
-                    result.location[0] = result.location[1] = InvalidGenomeLocation;
-                    AlignerContext2::writePair(pc, &r0, &r1, &result);
-                    continue;
-                }
-                toReference(res[i], &result);
-                partial->select(i, &r0, &r1);
-                AlignmentFilter filter(&r0, &r1, ctx->index->getGenome(), ctx->transcriptome->getGenome(), ctx->gtf, pp.min_spacing,
-                                       pp.max_spacing, ctx->options->confDiff, ctx->options->maxDist.start, ctx->index->getSeedLength(), partial);
-                for (int k = 0; k < n0[i]; k++) filter.AddAlignment(l0[(size_t)i * maxHitsToGet + k], rc0[(size_t)i * maxHitsToGet + k], sc0[(size_t)i * maxHitsToGet + k], 0, true, false);
-                for (int k = 0; k < n1[i]; k++) filter.AddAlignment(l1[(size_t)i * maxHitsToGet + k], rc1[(size_t)i * maxHitsToGet + k], sc1[(size_t)i * maxHitsToGet + k], 0, true, true);
-                filter.AddAlignment(result.location[0], result.direction[0], result.score[0], result.mapq[0], false, false);
-                filter.AddAlignment(result.location[1], result.direction[1], result.score[1], result.mapq[1], false, true);
-                filter.Filter(&result);
-                if (result.status[0] == NotFound && result.status[1] == NotFound && contamination_ != NULL) {
-                    snapb200_read_batch c0 = s0.one(i), c1 = s1.one(i);
-                    snapb200_paired_result c;
-                    check(snapb200_paired_batch(contamination_, &pp, &c0, &c1, &c));
-                    if (c.status[0] != NotFound && c.status[1] != NotFound) {
-                        ctx->c_filter->AddAlignment(c.location[0], c.direction[0], c.score[0], c.mapq[0], false, false);
-                        ctx->c_filter->AddAlignment(c.location[1], c.direction[1], c.score[1], c.mapq[1], false, true);
-                    }
-                }
-                if (pp.force_spacing && isOneLocation(result.status[0]) != isOneLocation(result.status[1])) {
-                    result.status[0] = result.status[1] = NotFound;
-                    result.location[0] = result.location[1] = InvalidGenomeLocation;
-                }
-                if (result.score[0] + result.score[1] >= 5) {  // "cheese", PairedAligner.cpp:653-663
-                    if (result.mapq[0] < 50) result.mapq[0] /= 2;
-                    if (result.mapq[1] < 50) result.mapq[1] /= 2;
-                }
-                AlignerContext2::writePair(pc, &r0, &r1, &result);
-                AlignerContext2::updateStats(pc, &r0, &r1, &result);
-            }
-            tReplay += now() - tMark;
+        P.partial = partial->params();
+        P.filter.max_spacing = pp.max_spacing; P.filter.conf_diff = ctx->options->confDiff; P.filter.max_dist = ctx->options->maxDist.start;
+        P.filter.max_hits_to_get = P.transcriptome.max_hits_to_get;
+        P.filter.force_spacing = 0;  // applied below, after the contamination step, where the run loop applies it (PairedAligner.cpp:633-651)
+        PairBatch pb[2];
+        Timing tm;
+        int cur = 0;
+        fill(pb[cur], supplier, ctx, pc, tm);
+        if (pb[cur].n) submit(pb[cur], devs, P);
+        while (pb[cur].n) {
+            const int nxt = cur ^ 1;
+            fill(pb[nxt], supplier, ctx, pc, tm);       // host work that overlaps the device work of pb[cur]
+            if (pb[nxt].n) submit(pb[nxt], devs, P);
+            replay(pb[cur], devs, P, partial, ctx, pc, tm);
+            cur = nxt;
         }
-        report("paired", tDrain, tAbi, tReplay, nReads);
+        const double tLoop = now() - tEnter - tInit, td = now();
+        for (int k = 0; k < 2; k++) pb[k].destroy();
+        tm.report();
         if (getenv("SNAPB200_SHIM_TIMING") != NULL)
-            fprintf(stderr, "[snapb200 shim]   C ABI split: transcriptome multi-hit x2 %.2f s, paired %.2f s, CharacterizeSeeds x2 %.2f s, host buffers %.2f s\n",
-                    tCall[0], tCall[1], tCall[2], tAbi - tCall[0] - tCall[1] - tCall[2]);
-        snapb200_stats st;
-        if (snapb200_stats_get(genome_, &st) == SNAPB200_OK) ctx->stats->lvCalls = st.n_locations_scored;
+            fprintf(stderr, "[snapb200 shim]   thread wall: opening the device handles (or waiting for the thread that does) %.2f s, batch loop %.2f s, "
+                            "releasing the batch objects %.2f s\n", tInit, tLoop, now() - td);
+        ctx->stats->lvCalls = threadLeaves(devs);
         delete partial;
         return true;
     }
 
 private:
-    // Owns copies of reads (id, unclipped bases, qualities) so they outlive the supplier's buffers, and
-    // exposes the clipped reads as a snapb200_read_batch.
+    // Owns copies of reads (id, unclipped bases, qualities) so they outlive the supplier's buffers, and exposes the clipped reads
+    // of the pairs that go to the device as a snapb200_read_batch.
     struct ReadStore {
         std::vector<char> ids, bases, quals;          // unclipped, back to back
         std::vector<unsigned> idOff, off;             // n+1
-        std::vector<uint8_t> cbases, cquals;          // clipped, what the aligner sees
+        std::vector<uint8_t> cbases, cquals;          // clipped, what the aligner sees (device reads only)
         std::vector<uint32_t> coff;
+        std::vector<int> devIdx;                      // index in the device batch, -1: not aligned (the run loops' early-outs)
         std::vector<const char *> readGroups;         // Read::getReadGroup(): owned by the reader context, outlives the batch
         ReadStore() { clear(); }
-        void clear() { ids.clear(); bases.clear(); quals.clear(); cbases.clear(); cquals.clear(); readGroups.clear(); idOff.assign(1, 0); off.assign(1, 0); coff.assign(1, 0); }
+        void clear()
+        {
+            ids.clear(); bases.clear(); quals.clear(); cbases.clear(); cquals.clear(); readGroups.clear(); devIdx.clear();
+            idOff.assign(1, 0); off.assign(1, 0); coff.assign(1, 0);
+        }
         unsigned size() const { return (unsigned)off.size() - 1; }
-        void add(Read *r)
+        unsigned deviceSize() const { return (unsigned)coff.size() - 1; }
+        int deviceIndex(unsigned i) const { return devIdx[i]; }
+        void add(Read *r, bool toDevice)
         {
             ids.insert(ids.end(), r->getId(), r->getId() + r->getIdLength());
             idOff.push_back((unsigned)ids.size());
             bases.insert(bases.end(), r->getUnclippedData(), r->getUnclippedData() + r->getUnclippedLength());
             quals.insert(quals.end(), r->getUnclippedQuality(), r->getUnclippedQuality() + r->getUnclippedLength());
             off.push_back((unsigned)bases.size());
-            cbases.insert(cbases.end(), (const uint8_t *)r->getData(), (const uint8_t *)r->getData() + r->getDataLength());
-            cquals.insert(cquals.end(), (const uint8_t *)r->getQuality(), (const uint8_t *)r->getQuality() + r->getDataLength());
-            coff.push_back((uint32_t)cbases.size());
             readGroups.push_back(r->getReadGroup());
+            if (toDevice) {
+                devIdx.push_back((int)deviceSize());
+                cbases.insert(cbases.end(), (const uint8_t *)r->getData(), (const uint8_t *)r->getData() + r->getDataLength());
+                cquals.insert(cquals.end(), (const uint8_t *)r->getQuality(), (const uint8_t *)r->getQuality() + r->getDataLength());
+                coff.push_back((uint32_t)cbases.size());
+            } else {
+                devIdx.push_back(-1);
+            }
+        }
+        // the clipped read i of another store, as a device read of this one (contamination sub-batches)
+        void addFrom(const ReadStore &o, unsigned i)
+        {
+            const int d = o.devIdx[i];
+            idOff.push_back(0); off.push_back(0); readGroups.push_back(NULL);
+            devIdx.push_back((int)deviceSize());
+            cbases.insert(cbases.end(), o.cbases.begin() + o.coff[d], o.cbases.begin() + o.coff[d + 1]);
+            cquals.insert(cquals.end(), o.cquals.begin() + o.coff[d], o.cquals.begin() + o.coff[d + 1]);
+            coff.push_back((uint32_t)cbases.size());
         }
         void get(unsigned i, Read *r, ReadClippingType clipping)
         {
@@ -363,17 +330,255 @@ private:
         }
         snapb200_read_batch batch() const
         {
-            snapb200_read_batch b = {size(), &coff[0], cbases.empty() ? NULL : &cbases[0], cquals.empty() ? NULL : &cquals[0]};
-            return b;
-        }
-        uint32_t oneOff[2];
-        snapb200_read_batch one(unsigned i)
-        {
-            oneOff[0] = 0; oneOff[1] = coff[i + 1] - coff[i];
-            snapb200_read_batch b = {1, oneOff, &cbases[coff[i]], &cquals[coff[i]]};
+            static const uint8_t none = 0;
+            snapb200_read_batch b = {deviceSize(), &coff[0], cbases.empty() ? &none : &cbases[0], cquals.empty() ? &none : &cquals[0]};
             return b;
         }
     };
+
+    // The HBM-resident handles of one device.  Process-wide cache, like the reference's own index cache (AlignerContext.cpp:42-47):
+    // every worker thread ends up with the same handles.
+    struct DeviceSet {
+        int device;
+        snapb200_index *genome, *transcriptome, *contamination;
+        snapb200_annotation *annotation;
+        std::vector<std::string> transcriptIds;  // behind snapb200_filter_event::transcript
+    };
+
+    static const std::vector<DeviceSet> &deviceSets(const AlignerOptions *options, bool needAnnotation)
+    {
+        static pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+        static std::vector<DeviceSet> sets;
+        static std::string key;
+        pthread_mutex_lock(&lock);
+        std::string k = std::string(options->indexDir) + "\n" + options->transcriptomeDir + "\n" + (options->contaminationDir ? options->contaminationDir : "") +
+                        "\n" + options->annotation;
+        if (sets.empty() || k != key) {
+            // (a process that chains runs over different indices keeps the earlier handles resident, as the reference keeps its globals)
+            sets.clear();
+            int n = snapb200_device_count();
+            if (const char *e = getenv("SNAPB200_DEVICES")) { int v = atoi(e); if (v >= 1 && v < n) n = v; }
+            if (n < 1) { fprintf(stderr, "snapb200: no CUDA device available (this build has no CPU path)\n"); soft_exit(1); }
+            for (int d = 0; d < n; d++) {
+                DeviceSet s;
+                s.device = d; s.contamination = NULL; s.annotation = NULL;
+                check(snapb200_index_open(options->indexDir, d, &s.genome));
+                check(snapb200_index_open(options->transcriptomeDir, d, &s.transcriptome));
+                if (options->contaminationDir != NULL) check(snapb200_index_open(options->contaminationDir, d, &s.contamination));
+                sets.push_back(s);
+            }
+            key = k;
+        }
+        if (needAnnotation && sets[0].annotation == NULL)
+            for (size_t d = 0; d < sets.size(); d++) {
+                check(snapb200_annotation_open(sets[d].genome, sets[d].transcriptome, options->annotation, &sets[d].annotation));
+                const uint32_t nt = snapb200_annotation_transcript_count(sets[d].annotation);
+                for (uint32_t t = 0; t < nt; t++) sets[d].transcriptIds.push_back(snapb200_annotation_transcript_id(sets[d].annotation, t));
+            }
+        pthread_mutex_unlock(&lock);
+        return sets;
+    }
+
+    // batches are dealt round-robin over the devices, whichever thread they come from (g = batch % nGPU)
+    static size_t nextDevice(size_t nDevices)
+    {
+        static volatile unsigned counter = 0;
+        return (size_t)(__sync_fetch_and_add(&counter, 1u) % (unsigned)nDevices);
+    }
+
+    // lvCalls (the stats line's column) is g_aligner->getLocationsScored(): locations scored by the intersecting aligner and its
+    // single-end fallback on the genome index (ChimericPairedEndAligner.h:59-61).  The device keeps that counter per index, so the
+    // thread that leaves last reports what has not been reported yet and the others report 0: the threads' sum is the total.
+    static volatile int &activeThreads() { static volatile int v = 0; return v; }
+    static volatile long long &reportedLv() { static volatile long long v = 0; return v; }
+    static void threadEnters() { __sync_fetch_and_add(&activeThreads(), 1); }
+    static long long threadLeaves(const std::vector<DeviceSet> &devs)
+    {
+        static pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+        pthread_mutex_lock(&lock);
+        long long mine = 0;
+        if (__sync_sub_and_fetch(&activeThreads(), 1) == 0) {
+            long long total = 0;
+            for (size_t d = 0; d < devs.size(); d++) {
+                snapb200_stats st;
+                if (snapb200_stats_get(devs[d].genome, &st) == SNAPB200_OK) total += st.n_locations_scored;
+            }
+            mine = total - reportedLv();
+            reportedLv() = total;
+        }
+        pthread_mutex_unlock(&lock);
+        return mine;
+    }
+
+    struct Timing {
+        double drain, wait, replay, filterHost, unaligned, gtf, write, deviceMs;
+        unsigned long reads, batches, hostPairs;
+        Timing() : drain(0), wait(0), replay(0), filterHost(0), unaligned(0), gtf(0), write(0), deviceMs(0), reads(0), batches(0), hostPairs(0) {}
+        void report() const
+        {
+            if (getenv("SNAPB200_SHIM_TIMING") == NULL) return;
+            fprintf(stderr, "[snapb200 shim] paired thread: %lu reads in %lu batches, drain %.2f s, waiting for the device %.2f s (device busy %.2f s), "
+                            "host replay %.2f s (UnalignedRead %.2f, GTF counters %.2f, writePair+stats %.2f, reference filter for %lu overflow pairs %.2f)\n",
+                    reads, batches, drain, wait, deviceMs * 1e-3, replay, unaligned, gtf, write, hostPairs, filterHost);
+        }
+    };
+
+    struct PairBatch {
+        ReadStore s0, s1;
+        unsigned n;                      // pairs drained (device pairs: s0.deviceSize())
+        std::vector<snapb200_rna_batch *> objs;  // one per device, created on first use
+        int dev;
+        PairBatch() : n(0), dev(0) {}
+        void destroy() { for (size_t d = 0; d < objs.size(); d++) if (objs[d]) snapb200_rna_batch_destroy(objs[d]); objs.clear(); }
+    };
+
+    void fill(PairBatch &b, PairedReadSupplier *supplier, AlignerContext *ctx, PairedAlignerContext *pc, Timing &tm)
+    {
+        const double t0 = now();
+        b.s0.clear(); b.s1.clear();
+        Read *read0, *read1;
+        while (b.s0.size() < batch_ && supplier->getNextReadPair(&read0, &read1)) {
+            if (!AlignerContext2::ignoreMismatchedIDs(pc)) Read::checkIdMatch(read0, read1);
+            ctx->stats->totalReads += 2;
+            int maxDist = ctx->maxDist;
+            bool useful0 = read0->getDataLength() >= 50 && (int)read0->countOfNs() <= maxDist;
+            bool useful1 = read1->getDataLength() >= 50 && (int)read1->countOfNs() <= maxDist;
+            bool quality0 = read0->qualityFilter(ctx->options->minPercentAbovePhred, ctx->options->minPhred, ctx->options->phredOffset);
+            bool bad = (!useful0 && !useful1) || (!quality0 || !quality0);  // sic, PairedAligner.cpp:564
+            if (!bad) ctx->stats->usefulReads += (useful0 && useful1) ? 2 : 1;
+            b.s0.add(read0, !bad); b.s1.add(read1, !bad);
+        }
+        b.n = b.s0.size();
+        tm.drain += now() - t0;
+        tm.reads += 2ul * b.n;
+    }
+
+    void submit(PairBatch &b, const std::vector<DeviceSet> &devs, const snapb200_rna_params &P)
+    {
+        b.dev = (int)nextDevice(devs.size());
+        if (b.objs.size() < devs.size()) b.objs.resize(devs.size(), NULL);
+        if (b.objs[b.dev] == NULL) check(snapb200_rna_batch_create(devs[b.dev].annotation, devs[b.dev].genome, devs[b.dev].transcriptome, &b.objs[b.dev]));
+        snapb200_read_batch r0 = b.s0.batch(), r1 = b.s1.batch();
+        check(snapb200_rna_batch_submit(b.objs[b.dev], &P, &r0, &r1));
+    }
+
+    void replay(PairBatch &b, const std::vector<DeviceSet> &devs, const snapb200_rna_params &P, GpuSeedCharacterizer *partial, AlignerContext *ctx,
+                PairedAlignerContext *pc, Timing &tm)
+    {
+        const DeviceSet &dev = devs[b.dev];
+        const snapb200_paired_params &pp = P.paired;
+        double t0 = now();
+        snapb200_rna_view v;
+        check(snapb200_rna_batch_wait(b.objs[b.dev], &v));
+        tm.wait += now() - t0;
+        tm.deviceMs += v.device_ms;
+        tm.batches++;
+        t0 = now();
+        const bool fine = getenv("SNAPB200_SHIM_TIMING") != NULL;
+        for (int e = 0; e < 2; e++) partial->borrow(e, v.seg_offsets[e], v.ch_locations[e], v.ch_seed_offsets[e]);
+        const unsigned seedLen = ctx->index->getSeedLength();
+        const Genome *genome = ctx->index->getGenome();
+        std::vector<PairedAlignmentResult> results(b.n);
+        std::vector<unsigned> contam;
+        // pass 1: the pair's result and its GTF counters, in input order
+        for (unsigned i = 0; i < b.n; i++) {
+            PairedAlignmentResult &result = results[i];
+            const int di = b.s0.deviceIndex(i);
+            if (di < 0) {
+                result.status[0] = result.status[1] = NotFound;
+                result.location[0] = result.location[1] = InvalidGenomeLocation;
+                continue;
+            }
+            Read r0, r1;
+            b.s0.get(i, &r0, ctx->clipping); b.s1.get(i, &r1, ctx->clipping);
+            if (v.needs_host[di]) {  // more alignments / combinations than the device scratch holds: the reference's class decides
+                const double th = now();
+                toReference(v.genome_pairs[di], &result);
+                partial->select((unsigned)di, &r0, &r1);
+                AlignmentFilter filter(&r0, &r1, genome, ctx->transcriptome->getGenome(), ctx->gtf, pp.min_spacing, pp.max_spacing, ctx->options->confDiff,
+                                       ctx->options->maxDist.start, seedLen, partial);
+                for (uint32_t k = v.hit_offsets[0][di]; k < v.hit_offsets[0][di + 1]; k++) filter.AddAlignment(v.hit_locations[0][k], v.hit_rcs[0][k] ? RC : FORWARD, v.hit_scores[0][k], 0, true, false);
+                for (uint32_t k = v.hit_offsets[1][di]; k < v.hit_offsets[1][di + 1]; k++) filter.AddAlignment(v.hit_locations[1][k], v.hit_rcs[1][k] ? RC : FORWARD, v.hit_scores[1][k], 0, true, true);
+                filter.AddAlignment(result.location[0], result.direction[0], result.score[0], result.mapq[0], false, false);
+                filter.AddAlignment(result.location[1], result.direction[1], result.score[1], result.mapq[1], false, true);
+                filter.Filter(&result);
+                tm.filterHost += now() - th;
+                tm.hostPairs++;
+            } else {
+                const snapb200_filter_result &fr = v.results[di];
+                const snapb200_filter_event &ev = v.events[di];
+                for (int e = 0; e < 2; e++) {
+                    result.status[e] = (AlignmentResult)fr.status[e]; result.location[e] = fr.location[e]; result.direction[e] = (Direction)fr.direction[e];
+                    result.score[e] = fr.score[e]; result.mapq[e] = fr.mapq[e]; result.isTranscriptome[e] = fr.is_transcriptome[e] != 0;
+                    result.tlocation[e] = fr.tlocation[e];
+                }
+                result.fromAlignTogether = false;
+                result.alignedAsPair = fr.aligned_as_pair != 0;
+                result.nanosInAlignTogether = 0; result.nLVCalls = v.genome_pairs[di].n_lv_calls; result.nSmallHits = 0;
+                if (ev.unaligned) {  // AlignmentFilter.cpp:331-340: the novel-splice search of the read that has no alignment at all
+                    const double tu = fine ? now() : 0;
+                    partial->select((unsigned)di, &r0, &r1);
+                    FilterAccess fa(&r0, &r1, genome, ctx->transcriptome->getGenome(), ctx->gtf, pp.min_spacing, pp.max_spacing, ctx->options->confDiff,
+                                    ctx->options->maxDist.start, seedLen, partial);
+                    fa.unaligned(ev.unaligned == 1 ? &r0 : &r1, seedLen);
+                    if (fine) tm.unaligned += now() - tu;
+                }
+                if (ev.kind) {
+                    const double tg = fine ? now() : 0;
+                    const Genome::Piece *pieces = genome->getPieces();
+                    if (ev.kind == 1) {  // AlignmentFilter.cpp:536-541 (the lengths are passed crossed there)
+                        ctx->gtf->IncrementReadCount(ev.transcript[0] >= 0 ? dev.transcriptIds[ev.transcript[0]] : std::string(), ev.pos_original[0], ev.pos[0],
+                                                     r1.getDataLength(), ev.transcript[1] >= 0 ? dev.transcriptIds[ev.transcript[1]] : std::string(),
+                                                     ev.pos_original[1], ev.pos[1], r0.getDataLength());
+                    } else {
+                        const std::string id(r0.getId(), r0.getIdLength());
+                        if (ev.kind == 2) ctx->gtf->IntrachromosomalPair(pieces[ev.chr[0]].name, ev.pos[0], ev.pos_end[0], pieces[ev.chr[1]].name, ev.pos[1], ev.pos_end[1], id);
+                        else ctx->gtf->InterchromosomalPair(pieces[ev.chr[0]].name, ev.pos[0], ev.pos_end[0], pieces[ev.chr[1]].name, ev.pos[1], ev.pos_end[1], id);
+                    }
+                    if (fine) tm.gtf += now() - tg;
+                }
+            }
+            if (result.status[0] == NotFound && result.status[1] == NotFound && dev.contamination != NULL) contam.push_back(i);
+        }
+        if (!contam.empty()) {  // PairedAligner.cpp:633-646, one device call for all unaligned pairs of the batch
+            ReadStore c0, c1;
+            for (size_t q = 0; q < contam.size(); q++) { c0.addFrom(b.s0, contam[q]); c1.addFrom(b.s1, contam[q]); }
+            snapb200_read_batch r0 = c0.batch(), r1 = c1.batch();
+            std::vector<snapb200_paired_result> cres(contam.size());
+            check(snapb200_paired_batch(dev.contamination, &pp, &r0, &r1, &cres[0]));
+            for (size_t q = 0; q < contam.size(); q++) {
+                const snapb200_paired_result &c = cres[q];
+                if (c.status[0] != NotFound && c.status[1] != NotFound) {
+                    ctx->c_filter->AddAlignment(c.location[0], c.direction[0], c.score[0], c.mapq[0], false, false);
+                    ctx->c_filter->AddAlignment(c.location[1], c.direction[1], c.score[1], c.mapq[1], false, true);
+                }
+            }
+        }
+        // pass 2: forceSpacing, the MAPQ halving where the host filter ran, output and statistics
+        const double tw = now();
+        for (unsigned i = 0; i < b.n; i++) {
+            Read r0, r1;
+            b.s0.get(i, &r0, ctx->clipping); b.s1.get(i, &r1, ctx->clipping);
+            PairedAlignmentResult &result = results[i];
+            const int di = b.s0.deviceIndex(i);
+            if (di < 0) {
+                AlignerContext2::writePair(pc, &r0, &r1, &result);
+                continue;
+            }
+            if (pp.force_spacing && isOneLocation(result.status[0]) != isOneLocation(result.status[1])) {
+                result.status[0] = result.status[1] = NotFound;
+                result.location[0] = result.location[1] = InvalidGenomeLocation;
+            }
+            if (v.needs_host[di] && result.score[0] + result.score[1] >= 5) {  // "cheese", PairedAligner.cpp:653-663 (the device applied it already)
+                if (result.mapq[0] < 50) result.mapq[0] /= 2;
+                if (result.mapq[1] < 50) result.mapq[1] /= 2;
+            }
+            AlignerContext2::writePair(pc, &r0, &r1, &result);
+            AlignerContext2::updateStats(pc, &r0, &r1, &result);
+        }
+        tm.write += now() - tw;
+        tm.replay += now() - t0;
+    }
 
     static void toReference(const snapb200_paired_result &g, PairedAlignmentResult *r)
     {
@@ -395,37 +600,11 @@ private:
         return p;
     }
 
-    // Process-wide cache of HBM-resident indices, like the reference's own index cache (AlignerContext.cpp:42-47):
-    // every worker thread's copy of the extension ends up with the same handles.
-    void open(const char *dir, snapb200_index **slot, std::string *name)
-    {
-        if (*slot != NULL && *name == dir) return;
-        static pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
-        static std::map<std::string, snapb200_index *> cache;
-        pthread_mutex_lock(&lock);
-        std::map<std::string, snapb200_index *>::iterator it = cache.find(dir);
-        if (it == cache.end()) {
-            snapb200_index *h = NULL;
-            check(snapb200_index_open(dir, device_, &h));
-            it = cache.insert(std::make_pair(std::string(dir), h)).first;
-        }
-        *slot = it->second;
-        *name = dir;
-        pthread_mutex_unlock(&lock);
-    }
-
-    // SNAPB200_SHIM_TIMING=1: per worker thread, seconds spent draining the supplier, inside the C ABI and replaying the
-    // host post-processing (printed to stderr when the thread finishes)
     static double now()
     {
         struct timeval tv;
         gettimeofday(&tv, NULL);
         return tv.tv_sec + tv.tv_usec * 1e-6;
-    }
-    static void report(const char *what, double drain, double abi, double replay, unsigned long reads)
-    {
-        if (getenv("SNAPB200_SHIM_TIMING") != NULL)
-            fprintf(stderr, "[snapb200 shim] %s thread: %lu reads, drain %.2f s, C ABI %.2f s, host replay %.2f s\n", what, reads, drain, abi, replay);
     }
 
     static void check(int rc)
@@ -436,9 +615,6 @@ private:
         }
     }
 
-    int device_;
     unsigned batch_;
-    snapb200_index *genome_, *transcriptome_, *contamination_;
-    std::string genomeDir_, transcriptomeDir_, contaminationDir_;
     bool owner_;
 };

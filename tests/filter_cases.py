@@ -51,7 +51,7 @@ def alignments(impl, h_genome, h_transcriptome, b0, b1):
 
 
 FILTER_RESULT = np.dtype([("location", "<u4", (2,)), ("tlocation", "<u4", (2,)), ("score", "<i4", (2,)), ("mapq", "<i4", (2,)),
-                          ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,)), ("pad", "u1", (2,))])
+                          ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,)), ("aligned_as_pair", "u1"), ("pad", "u1")])
 
 
 def run_reference_filter(ref, h_genome, h_transcriptome, gtf_path, out_prefix, sam_reads, hits, genome_res, pp, conf_diff=2, max_dist=15):
@@ -71,3 +71,35 @@ def run_reference_filter(ref, h_genome, h_transcriptome, gtf_path, out_prefix, s
     assert rc == 0
     lib.ref_gtf_finish(g)
     return out
+
+
+def fabricate_hits(hits, res, tpiece_begin, piece_begin, chr_names, n, seed=77):
+    """Overwrites the filter's inputs of every pair with dozens of fabricated transcriptome hits per end (scores around the maxDist
+    gate, repeats of the same place with other scores / strands) and a genome pair anywhere, so that the classes hold hundreds of
+    combinations with many equal scores -- the regime where the string order of the map keys and libstdc++'s sort decide which pair
+    is reported.  Some pairs keep one or two hits so that every class gets to decide somewhere."""
+    rng = np.random.default_rng(seed)
+    tb = tpiece_begin.astype(np.int64)
+    tlen = np.diff(np.append(tb, tb[-1] + 3000))
+    real = np.flatnonzero(np.array([c != "chrDecoy" for c in chr_names]))
+    pb = piece_begin.astype(np.int64)
+    for i in range(n):
+        few = rng.random() < 0.3
+        for (cnt, loc, rcs, sc) in hits:
+            k = int(rng.integers(1, 3)) if few else int(rng.integers(5, 45))
+            p = rng.integers(1, len(tb), size=k)  # not the decoy transcript
+            loc[i, :k] = (tb[p] + (rng.random(k) * np.maximum(1, tlen[p] - 300)).astype(np.int64)).astype(np.uint32)
+            sc[i, :k] = rng.integers(0, 18, size=k) if rng.random() < 0.5 else rng.integers(0, 3, size=k)
+            rcs[i, :k] = rng.integers(0, 2, size=k)
+            dup = rng.integers(0, k, size=k // 3)
+            loc[i, k:k + len(dup)] = loc[i, dup]
+            sc[i, k:k + len(dup)] = np.maximum(0, sc[i, dup] + rng.integers(-1, 2, size=len(dup)))
+            rcs[i, k:k + len(dup)] = rng.integers(0, 2, size=len(dup))
+            cnt[i] = k + len(dup)
+        for e in range(2):
+            c = int(rng.choice(real))
+            res["location"][i, e] = int(pb[c] + rng.integers(0, 150000)) if rng.random() < 0.85 else 0xFFFFFFFF
+            res["score"][i, e] = int(rng.integers(0, 18))
+            res["mapq"][i, e] = int(rng.integers(0, 71))
+            res["direction"][i, e] = int(rng.integers(0, 2))
+            res["status"][i, e] = int(rng.integers(0, 3))

@@ -213,6 +213,7 @@ extern "C" int hostsim_filter_pair(const FltTables *t, uint32_t len0, uint32_t l
     };
     if (!cls[FLT_INTRAGENE].empty()) {
         process(cls[FLT_INTRAGENE]);
+        r.aligned_as_pair = 1;  // AlignmentFilter.cpp:543-548; every other exit of Filter leaves alignedAsPair false
         if (r.status[0] == 1) event(FLT_EV_INCREMENT, cls[FLT_INTRAGENE][0]);
     } else if (!cls[FLT_INTRACHR].empty()) {
         process(cls[FLT_INTRACHR]);
@@ -313,4 +314,19 @@ extern "C" int hostsim_filter_pair_flat(const FltTables *t, uint32_t len0, uint3
     in.ch_loc[0] = clocs0; in.ch_off[0] = coffs0; in.ch_loc[1] = clocs1; in.ch_off[1] = coffs1;
     for (int k = 0; k < 3; k++) { in.ch_range[0][k] = seg0[s + k]; in.ch_range[1][k] = seg1[s + k]; }
     return flt_filter_pair(*t, prm, in, sc, out, ev);
+}
+
+
+// AlignmentFilter::UnalignedRead as records (flt_unaligned_segments + flt_unaligned_splices, the serial specification): the splice
+// records of read `which` (1: read 0, 2: read 1) of one pair.  out == NULL: count.  Returns the count, -1 if there are more than
+// seg_cap partial alignments.
+extern "C" long long hostsim_unaligned_splices(const FltTables *t, uint32_t read_len, uint32_t seed_len, const uint64_t *seg, const uint32_t *clocs,
+                                               const uint16_t *coffs, uint32_t pair_index, uint32_t seg_cap, FltSplice *out)
+{
+    std::vector<FltSeg> segs(seg_cap + 1);
+    const uint64_t s = 2ull * pair_index;
+    const int n = flt_unaligned_segments(*t, clocs, coffs, seg[s], seg[s + 1], seg[s + 2], read_len, seed_len, segs.data(), seg_cap);
+    if (n < 0) return -1;
+    int kind = 0;
+    return (long long)flt_unaligned_splices(*t, segs.data(), (uint32_t)n, read_len, seed_len, pair_index, &kind, out);
 }

@@ -1,0 +1,151 @@
+"""AlignmentFilter on the device: the warp-per-pair kernel behind snapb200_filter_paired_batch and the
+whole RNA pair loop of a batch (snapb200_rna_batch_*) against the compiled reference's own AlignmentFilter, driven as
+SNAPLib/PairedAligner.cpp:575-663 drives it -- records field by field, and the per-pair event records replayed into the reference's
+GTFReader so that the nine statistics files it writes are compared byte for byte."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import filter_cases as F
+from test_filter_oracle import genome_pieces
+
+pytestmark = pytest.mark.gpu
+FIELDS = [f for f in F.FILTER_RESULT.names if f != "pad"]
+
+
+@pytest.fixture(scope="module")
+def ws(tmp_path_factory, ref, cuda):
+    """Genome + GTF + both indices built by the reference's command line, loaded by the reference and by the CUDA library."""
+    from oracle import oracle as O
+    d = str(tmp_path_factory.mktemp("cuda_filter"))
+    contigs = F.build_workspace(d, O.REF_BIN)
+    gdir, tdir, gtf = os.path.join(d, "gidx"), os.path.join(d, "tidx"), os.path.join(d, "a.gtf")
+    hg, ht = cuda.load_index(gdir), cuda.load_index(tdir)
+    ann = cuda.annotation_open(hg, ht, gtf)
+    rg, rt = ref.load_index(gdir), ref.load_index(tdir)
+    yield dict(d=d, contigs=contigs, gdir=gdir, tdir=tdir, gtf=gtf, hg=hg, ht=ht, ann=ann, rg=rg, rt=rt)
+    cuda.annotation_close(ann)
+    cuda.close_index(hg)
+    cuda.close_index(ht)
+
+
+def assert_same_records(want, got, what):
+    bad = [i for i in range(len(want)) if any(not np.array_equal(want[f][i], got[f][i]) for f in FIELDS)]
+    assert not bad, (what, len(bad), bad[:10], [(want[i], got[i]) for i in bad[:3]])
+
+
+def replay_and_compare(ref, cuda, w, sam_reads, events, want_prefix, tag):
+    """The event records through the reference's own public GTFReader methods on a fresh GTFReader: same statistics files."""
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    d = w["d"]
+    g2 = C.c_void_p(lib.ref_gtf_load(w["gtf"].encode(), os.path.join(d, tag).encode()))
+    t_ids, chr_names = cuda.annotation_names(w["ann"])
+    assert chr_names == genome_pieces(w["gdir"])[0]
+    arr = lambda names: (C.c_char_p * len(names))(*[x.encode() for x in names])
+    evc = np.ascontiguousarray(events)
+    assert lib.ref_filter_replay_events(w["rg"], w["rt"], g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(evc.ctypes.data), arr(t_ids),
+                                        arr(chr_names)) == 0
+    lib.ref_gtf_finish(g2)
+    produced = sorted(x for x in os.listdir(d) if x.startswith(tag))
+    assert len(produced) >= 8
+    for f in produced:
+        assert open(os.path.join(d, f), "rb").read() == open(os.path.join(d, want_prefix + f[len(tag):]), "rb").read(), f
+
+
+def test_cuda_filter_matches_the_reference_and_the_golden_file(ref, cuda, ws):
+    """1500 simulated spliced / chimeric pairs; every input of the filter produced by the CUDA library itself."""
+    from snap_rnaseq_b200 import _abi as A
+    w = ws
+    (b0, b1), sam_reads = F.reads(w["contigs"], w["d"])
+    hits, genome_res, pp = F.alignments(cuda, w["hg"], w["ht"], b0, b1)
+    ch = [cuda.characterize(w["hg"], A.single_defaults(max_hits=300, num_seeds=12), b) for b in (b0, b1)]
+    prm = A.FilterParams(pp.max_spacing, pp.force_spacing, 2, 15, F.MAX_HITS_TO_GET)
+    res, ev, needs_host = cuda.filter_paired(w["ann"], prm, np.diff(b0.offsets), np.diff(b1.offsets), hits[0], hits[1], genome_res, ch[0], ch[1])
+    assert not needs_host.any()
+    want = F.run_reference_filter(ref, w["rg"], w["rt"], w["gtf"], os.path.join(w["d"], "want_a"), sam_reads, hits, genome_res, pp)
+    assert_same_records(want, res, "CUDA filter vs reference")
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filter_cases.npz"))
+    assert_same_records(golden["result"], res, "CUDA filter vs golden file")
+    assert res["aligned_as_pair"].sum() > 500 and (res["is_transcriptome"] == 1).sum() > 100
+    replay_and_compare(ref, cuda, w, sam_reads, ev, "want_a", "replay_a")
+
+
+def test_cuda_filter_on_fabricated_hits(ref, cuda, ws):
+    """Dozens of fabricated hits per end: classes of hundreds of combinations, most of them tied -- the order of the map keys, the
+    de-duplication rule and the introsort mirror decide the reported pair (the > 16 combinations with a tie at the minimum path)."""
+    from snap_rnaseq_b200 import _abi as A
+    w = ws
+    (b0, b1), sam_reads = F.reads(w["contigs"], w["d"], n=500, seed=19)
+    hits, genome_res, pp = F.alignments(cuda, w["hg"], w["ht"], b0, b1)
+    res_in = np.ascontiguousarray(genome_res, A.PAIRED_RESULT).copy()
+    chr_names, piece_begin = genome_pieces(w["gdir"])
+    _, tpiece_begin = genome_pieces(w["tdir"])
+    F.fabricate_hits(hits, res_in, tpiece_begin, piece_begin, chr_names, b0.n)
+    ch = [cuda.characterize(w["hg"], A.single_defaults(max_hits=300, num_seeds=12), b) for b in (b0, b1)]
+    prm = A.FilterParams(pp.max_spacing, pp.force_spacing, 2, 15, F.MAX_HITS_TO_GET)
+    res, ev, needs_host = cuda.filter_paired(w["ann"], prm, np.diff(b0.offsets), np.diff(b1.offsets), hits[0], hits[1], res_in, ch[0], ch[1])
+    assert not needs_host.any()
+    want = F.run_reference_filter(ref, w["rg"], w["rt"], w["gtf"], os.path.join(w["d"], "want_b"), sam_reads, hits, res_in, pp)
+    assert_same_records(want, res, "CUDA filter vs reference, fabricated hits")
+    kinds = np.bincount(ev["kind"], minlength=4)
+    assert kinds[1] > 20 and kinds[2] > 5 and kinds[3] > 2 and (res["status"] == 2).any()
+    replay_and_compare(ref, cuda, w, sam_reads, ev, "want_b", "replay_b")
+    # empty batch and argument errors
+    e = cuda.filter_paired(w["ann"], prm, np.zeros(0, np.uint32), np.zeros(0, np.uint32), tuple(a[:0] for a in hits[0]), tuple(a[:0] for a in hits[1]),
+                           res_in[:0], (np.zeros(1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint16)),
+                           (np.zeros(1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint16)))
+    assert len(e[0]) == 0
+    bad = (hits[0][0].copy(), hits[0][1], hits[0][2], hits[0][3])
+    bad[0][3] = F.MAX_HITS_TO_GET + 1
+    with pytest.raises(RuntimeError, match="hit count"):
+        cuda.filter_paired(w["ann"], prm, np.diff(b0.offsets), np.diff(b1.offsets), bad, hits[1], res_in, ch[0], ch[1])
+
+
+def test_rna_batch_is_the_pair_loop_of_the_reference(ref, cuda, ws):
+    """snapb200_rna_batch_*: transcriptome multi-hits, genome pair, CharacterizeSeeds and the filter in one submission with the
+    intermediates resident in HBM -- against the reference's aligners + AlignmentFilter with the same per-thread aligner parameters
+    (PairedAligner.cpp:470-527), twice through the same batch object (buffers are reused) and with two objects in flight."""
+    from snap_rnaseq_b200 import _abi as A
+    w = ws
+    P = A.rna_defaults()
+    objs = [cuda.rna_batch_create(w["ann"], w["hg"], w["ht"]) for _ in range(2)]
+    cases = []
+    for k, (n, seed) in enumerate(((1500, 8), (700, 23))):
+        (b0, b1), sam_reads = F.reads(w["contigs"], w["d"], n=n, seed=seed)
+        cases.append((b0, b1, sam_reads))
+        cuda.rna_batch_submit(objs[k], P, b0, b1)       # both in flight
+    outs = [cuda.rna_batch_wait(objs[k]) for k in range(2)]
+    cuda.rna_batch_submit(objs[0], P, cases[1][0], cases[1][1])  # the first object again, with the other batch
+    again = cuda.rna_batch_wait(objs[0])
+    for f in FIELDS:
+        assert np.array_equal(again["results"][f], outs[1]["results"][f]), f
+    assert np.array_equal(again["events"], outs[1]["events"])
+    for k, (b0, b1, sam_reads) in enumerate(cases):
+        o = outs[k]
+        assert o["n"] == b0.n and not o["needs_host"].any()
+        # the intermediates the view exposes are what the separate entry points return
+        hits = []
+        for e, b in enumerate((b0, b1)):
+            _, cnt, locs, rcs, scores = ref.single_multihit(w["rt"], P.transcriptome, b)
+            off, hl, hr, hs = o["hits"][e]
+            assert np.array_equal(np.diff(off.astype(np.int64)), cnt)
+            m = np.arange(locs.shape[1])[None, :] < cnt[:, None]
+            assert np.array_equal(hl, locs[m]) and np.array_equal(hr, rcs[m]) and np.array_equal(hs, scores[m])
+            hits.append((np.ascontiguousarray(cnt, np.int32), np.ascontiguousarray(locs, np.uint32), np.ascontiguousarray(rcs, np.uint8),
+                         np.ascontiguousarray(scores, np.int32)))
+            seg, cl, co = ref.characterize(w["rg"], P.partial, b)
+            assert np.array_equal(o["ch"][e][0], seg) and np.array_equal(o["ch"][e][1], cl) and np.array_equal(o["ch"][e][2], co)
+        genome_res = ref.paired(w["rg"], P.paired, b0, b1)
+        for f in ("location", "score", "mapq", "status", "direction", "p_all", "p_best"):
+            assert np.array_equal(o["genome_pairs"][f], genome_res[f]), f
+        want = F.run_reference_filter(ref, w["rg"], w["rt"], w["gtf"], os.path.join(w["d"], f"want_r{k}"), sam_reads, hits, genome_res, P.paired)
+        assert_same_records(want, o["results"], f"rna batch {k} vs reference")
+        replay_and_compare(ref, cuda, w, sam_reads, o["events"], f"want_r{k}", f"replay_r{k}")
+    # an empty batch is legal
+    cuda.rna_batch_submit(objs[1], P, cases[0][0].slice(0, 0), cases[0][1].slice(0, 0))
+    assert cuda.rna_batch_wait(objs[1])["n"] == 0
+    for h in objs:
+        cuda.rna_batch_destroy(h)

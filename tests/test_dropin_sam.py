@@ -71,6 +71,17 @@ def workspace(tmp_path_factory):
     r0, r1 = synth.simulate_rna(contigs, os.path.join(d, "a.gtf"), 4000, 100, seed=8)
     synth.write_fastq_plain(os.path.join(d, "x1.fq"), r0, mate=0)
     synth.write_fastq_plain(os.path.join(d, "x2.fq"), r1, mate=1)
+    # the contamination database of BASELINE.json configs[3] (-ct): two contigs no read of the sample comes from, an index of them,
+    # and the RNA pairs above followed by 600 pairs drawn from the contaminants (both mate files keep equal byte sizes)
+    contam = synth.random_contigs([60000, 40000], seed=77, prefix="bug")
+    synth.write_fasta(os.path.join(d, "c.fa"), contam)
+    run([REF, "index", "c.fa", "cidx", "-s", "20", "-t1"], d)
+    simc = synth.simulate(contam, 600, 100, paired=True, err=0.02, seed=78)
+    for mate, name in enumerate(("y1.fq", "y2.fq")):
+        synth.write_fastq_plain(os.path.join(d, "c%d.fq" % mate), simc["batches"][mate], mate=mate, prefix="c")
+        with open(os.path.join(d, name), "wb") as f:
+            f.write(open(os.path.join(d, "x%d.fq" % (mate + 1)), "rb").read())
+            f.write(open(os.path.join(d, "c%d.fq" % mate), "rb").read())
     return d
 
 
@@ -99,3 +110,31 @@ def test_rna_mode_spliced_and_chimeric_pairs_sam_identical(workspace):
     a, b = sam_records(os.path.join(d, "ref_x.sam")), sam_records(os.path.join(d, "gpu_x.sam"))
     assert_same(a, b, 8000)
     assert sum("N" in r.split("\t")[5] for r in a) > 30  # spliced alignments (N in the CIGAR) are really in there
+
+
+SIDE_FILES = ("gene_id.counts.txt", "gene_name.counts.txt", "transcript_id.counts.txt", "transcript_name.counts.txt", "junction_id.counts.txt",
+              "junction_name.counts.txt", "read_intervals.txt", "interchromosomal_intervals.gtf", "intrachromosomal_intervals.gtf")
+
+
+def test_rna_mode_with_contamination_filter_sam_and_statistics_identical(workspace):
+    """C4 with the contamination database (-ct, SNAPLib/PairedAligner.cpp:633-646, ContaminationFilter.cpp:60-112): pairs neither
+    index places are aligned against the contaminants and counted per contig.  One worker thread, so that besides the sorted SAM
+    records every statistics file the run leaves (GTF read counts, junction counts, fusion intervals, contaminant counts) can be
+    compared byte for byte -- they are written from the GTFReader / ContaminationFilter state the extension's replay feeds."""
+    d = workspace
+    run([REF, "paired", "gidx", "tidx", "a.gtf", "y1.fq", "y2.fq", "-o", "ref_y.sam", "-t", "1", "-ct", "cidx"], d)
+    run([B200, "paired", "gidx", "tidx", "a.gtf", "y1.fq", "y2.fq", "-o", "gpu_y.sam", "-t", "1", "-ct", "cidx"], d)
+    a, b = sam_records(os.path.join(d, "ref_y.sam")), sam_records(os.path.join(d, "gpu_y.sam"))
+    assert_same(a, b, 2 * (4000 + 600))
+    want = open(os.path.join(d, "ref_y.contaminants.txt")).read()
+    assert want == open(os.path.join(d, "gpu_y.contaminants.txt")).read()
+    assert sum(int(l.split("\t")[1]) for l in want.split("\n") if l) > 400  # the contaminant pairs were really counted
+    for f in SIDE_FILES:
+        assert open(os.path.join(d, "ref_y." + f), "rb").read() == open(os.path.join(d, "gpu_y." + f), "rb").read(), f
+    # the stats line of the run (AlignerContext.cpp:372-393) up to the Reads/s column, lvCalls included
+    def stats_line(out):
+        rows = [l for l in out.split("\n") if l.startswith("16000")]
+        return rows[-1].split("\t")[:10]
+    ref_out = run([REF, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "ref_z.sam", "-t", "1"], d)
+    gpu_out = run([B200, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "gpu_z.sam", "-t", "1"], d)
+    assert stats_line(ref_out) == stats_line(gpu_out), (stats_line(ref_out), stats_line(gpu_out))

@@ -58,7 +58,8 @@ class FltTables(C.Structure):
                 ("tpiece_begin", C.POINTER(C.c_uint32)), ("n_tpieces", C.c_uint32), ("tpiece_transcript", C.POINTER(C.c_int32)),
                 ("t_chr", C.POINTER(C.c_int32)), ("t_gene", C.POINTER(C.c_int32)), ("t_end", C.POINTER(C.c_uint32)),
                 ("t_feat_first", C.POINTER(C.c_uint32)), ("f_type", C.POINTER(C.c_uint32)), ("f_start", C.POINTER(C.c_uint32)),
-                ("f_end", C.POINTER(C.c_uint32)), ("g_chr", C.POINTER(C.c_int32)), ("g_start", C.POINTER(C.c_uint32)), ("g_end", C.POINTER(C.c_uint32))]
+                ("f_end", C.POINTER(C.c_uint32)), ("g_chr", C.POINTER(C.c_int32)), ("g_start", C.POINTER(C.c_uint32)), ("g_end", C.POINTER(C.c_uint32)),
+                ("n_genes", C.c_uint32), ("gene_tree_min_stop", C.c_int32)]
 
 
 def genome_pieces(index_dir):
@@ -109,6 +110,8 @@ def flat_tables(export_path, gdir, tdir):
     keep["g_start"] = np.array([genes[g][1] for g in g_ids], np.uint32)
     keep["g_end"] = np.array([genes[g][2] for g in g_ids], np.uint32)
     T.g_chr, T.g_start, T.g_end = A.p32i(keep["g_chr"]), A.p32u(keep["g_start"]), A.p32u(keep["g_end"])
+    T.n_genes = len(g_ids)
+    T.gene_tree_min_stop = int(keep["g_start"][0]) if 0 < len(g_ids) < 64 else -(1 << 31)  # flt_gene_found: the unsorted single-node tree
     return T, keep
 
 
@@ -183,11 +186,41 @@ def test_alignment_lists_match_the_reference(ref, tmp_path):
 
 
 FLT_RESULT = np.dtype([("location", "<u4", (2,)), ("tlocation", "<u4", (2,)), ("score", "<i4", (2,)), ("mapq", "<i4", (2,)),
-                       ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,))], align=True)
+                       ("status", "u1", (2,)), ("direction", "u1", (2,)), ("is_transcriptome", "u1", (2,)), ("aligned_as_pair", "u1"), ("pad", "u1")], align=True)
 
 
 FLT_EVENT = np.dtype([("kind", "<i4"), ("unaligned", "<i4"), ("transcript", "<i4", (2,)), ("chr", "<i4", (2,)), ("pos_original", "<u4", (2,)),
                       ("pos", "<u4", (2,)), ("pos_end", "<u4", (2,))], align=True)
+
+
+FLT_SPLICE = np.dtype([("pair", "<u4"), ("kind", "<i4"), ("chr", "<i4", (2,)), ("pos", "<u4", (2,)), ("pos_end", "<u4", (2,))], align=True)
+
+
+def splice_records(hs, T, events, ch, lens, seed_len=20, seg_cap=1 << 16):
+    """AlignmentFilter::UnalignedRead of every flagged read as records (the serial specification in filterfmt.h): offsets[n + 1], records."""
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+    p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+    hs.hostsim_unaligned_splices.restype = C.c_longlong
+    n = len(events)
+    counts = np.zeros(n + 1, np.uint64)
+    parts = []
+    for i in np.flatnonzero(events["unaligned"] > 0):
+        e = int(events["unaligned"][i]) - 1
+        args = (C.byref(T), C.c_uint(int(lens[e][i])), C.c_uint(seed_len), p64(ch[e][0]), A_p32u(ch[e][1]), p16(ch[e][2]), C.c_uint(int(i)), C.c_uint(seg_cap))
+        c = hs.hostsim_unaligned_splices(*args, None)
+        assert c >= 0
+        if c:
+            rec = np.zeros(c, FLT_SPLICE)
+            assert hs.hostsim_unaligned_splices(*args, C.c_void_p(rec.ctypes.data)) == c
+            parts.append(rec)
+        counts[i + 1] = c
+    off = np.cumsum(counts).astype(np.uint64)
+    return off, (np.concatenate(parts) if parts else np.zeros(0, FLT_SPLICE))
+
+
+def A_p32u(a):
+    from snap_rnaseq_b200 import _abi as A
+    return A.p32u(a)
 
 
 def test_filter_decision_matches_the_reference(ref, golden_filter, tmp_path):
@@ -262,6 +295,71 @@ def test_filter_decision_matches_the_reference(ref, golden_filter, tmp_path):
     for f in produced:
         key = "file_" + (f[len("replay"):].strip("._") or "main")
         assert open(os.path.join(d, f), "rb").read() == golden_filter[key].tobytes(), f
+    # the same with UnalignedRead replaced by its records (what the device emits): the files must not change.  This annotation has 11
+    # genes, i.e. the reference's gene interval tree is the single unsorted node whose scan can be skipped (flt_gene_found).
+    off, recs = splice_records(hs, T, events, ch, (lens0, lens1))
+    g3 = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "replay2").encode()))
+    rc = lib.ref_filter_replay_events2(hg, ht, g3, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(events.ctypes.data), arr(t_ids),
+                                       arr(chr_names), off.ctypes.data_as(C.c_void_p), C.c_void_p(recs.ctypes.data))
+    assert rc == 0
+    lib.ref_gtf_finish(g3)
+    for f in sorted(x for x in os.listdir(d) if x.startswith("replay2")):
+        key = "file_" + (f[len("replay2"):].strip("._") or "main")
+        assert open(os.path.join(d, f), "rb").read() == golden_filter[key].tobytes(), f
+
+
+def test_unaligned_read_records_on_a_larger_annotation(ref, tmp_path):
+    """UnalignedRead as records against the reference's own UnalignedRead on a 6 Mbp genome with > 64 genes (the reference's gene
+    interval tree splits and sorts there) and repeat families that give unaligned reads hundreds of partial alignments: the interval
+    maps after the replay -- and the files written from them -- must be identical."""
+    import subprocess
+    from oracle import oracle as O
+    from snap_rnaseq_b200 import _abi as A, synth
+    d = str(tmp_path)
+    contigs = {"chrDecoy": synth.random_contigs([2000], seed=99)["chr1"]}
+    contigs.update(synth.random_contigs([3_000_000] * 2, seed=20))
+    synth.inject_repeats({k: v for k, v in contigs.items() if k != "chrDecoy"}, frac=0.04, seed=21)
+    synth.write_fasta(os.path.join(d, "g.fa"), contigs)
+    synth.make_gtf(os.path.join(d, "a.gtf"), contigs)
+    for cmd in ([O.REF_BIN, "index", "g.fa", "gidx", "-s", "20", "-t4"], [O.REF_BIN, "transcriptome", "a.gtf", "g.fa", "tidx", "-t4", "-s", "20"]):
+        r = subprocess.run(cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-2000:]
+    (b0, b1), sam_reads = F.reads(contigs, d, n=3000, seed=5)
+    hg, ht = ref.load_index(os.path.join(d, "gidx")), ref.load_index(os.path.join(d, "tidx"))
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "want").encode()))
+    assert lib.ref_gtf_export(g, os.path.join(d, "gtf.tsv").encode()) == 0
+    T, keep = flat_tables(os.path.join(d, "gtf.tsv"), os.path.join(d, "gidx"), os.path.join(d, "tidx"))
+    assert T.n_genes >= 64
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    ch = [ref.characterize(hg, A.single_defaults(max_hits=300, num_seeds=12), b) for b in (b0, b1)]
+    lens = (np.diff(b0.offsets), np.diff(b1.offsets))
+    # every read gets the search (alternating mates), whatever the aligners would have said about it
+    events = np.zeros(b0.n, FLT_EVENT)
+    events["unaligned"] = 1 + (np.arange(b0.n) & 1)
+    t_ids = [ln.split("\t")[1] for ln in open(os.path.join(d, "gtf.tsv")) if ln.startswith("T")]
+    chr_names, _ = genome_pieces(os.path.join(d, "gidx"))
+    arr = lambda names: (C.c_char_p * len(names))(*[n.encode() for n in names])
+    assert lib.ref_filter_replay_events(hg, ht, g, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(events.ctypes.data), arr(t_ids),
+                                        arr(chr_names)) == 0
+    want_counts = np.zeros(4, np.uint64)
+    lib.ref_gtf_interval_counts(g, want_counts.ctypes.data_as(C.c_void_p))
+    lib.ref_gtf_finish(g)
+    off, recs = splice_records(hs, T, events, ch, lens)
+    g2 = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "mine").encode()))
+    assert lib.ref_filter_replay_events2(hg, ht, g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(events.ctypes.data), arr(t_ids),
+                                         arr(chr_names), off.ctypes.data_as(C.c_void_p), C.c_void_p(recs.ctypes.data)) == 0
+    got_counts = np.zeros(4, np.uint64)
+    lib.ref_gtf_interval_counts(g2, got_counts.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(want_counts, got_counts), (want_counts, got_counts)
+    assert want_counts[1] > 1000 and want_counts[1] == 2 * (recs["kind"] == 2).sum() and want_counts[3] == 2 * (recs["kind"] == 3).sum()
+    lib.ref_gtf_finish(g2)
+    for f in sorted(x for x in os.listdir(d) if x.startswith("mine")):
+        assert open(os.path.join(d, f), "rb").read() == open(os.path.join(d, "want" + f[len("mine"):]), "rb").read(), f
 
 
 def test_sort_mirror_is_std_sort(tmp_path):
@@ -405,31 +503,7 @@ def test_filter_decision_on_fabricated_hits(ref, tmp_path):
     g = C.c_void_p(lib.ref_gtf_load(os.path.join(d, "a.gtf").encode(), os.path.join(d, "want").encode()))
     assert lib.ref_gtf_export(g, os.path.join(d, "gtf.tsv").encode()) == 0
     T, keep = flat_tables(os.path.join(d, "gtf.tsv"), os.path.join(d, "gidx"), os.path.join(d, "tidx"))
-    rng = np.random.default_rng(77)
-    tb = keep["tpiece_begin"].astype(np.int64)
-    tlen = np.diff(np.append(tb, tb[-1] + 3000))
-    real = np.flatnonzero(np.array([c != "chrDecoy" for c in genome_pieces(os.path.join(d, "gidx"))[0]]))
-    pb = keep["piece_begin"].astype(np.int64)
-    for i in range(b0.n):
-        few = rng.random() < 0.3  # some pairs keep one or two hits so that every class gets to decide somewhere
-        for (cnt, loc, rcs, sc) in hits:
-            k = int(rng.integers(1, 3)) if few else int(rng.integers(5, 45))
-            p = rng.integers(1, len(tb), size=k)  # not the decoy transcript
-            loc[i, :k] = (tb[p] + (rng.random(k) * np.maximum(1, tlen[p] - 300)).astype(np.int64)).astype(np.uint32)
-            sc[i, :k] = rng.integers(0, 18, size=k) if rng.random() < 0.5 else rng.integers(0, 3, size=k)
-            rcs[i, :k] = rng.integers(0, 2, size=k)
-            dup = rng.integers(0, k, size=k // 3)
-            loc[i, k:k + len(dup)] = loc[i, dup]
-            sc[i, k:k + len(dup)] = np.maximum(0, sc[i, dup] + rng.integers(-1, 2, size=len(dup)))
-            rcs[i, k:k + len(dup)] = rng.integers(0, 2, size=len(dup))
-            cnt[i] = k + len(dup)
-        for e in range(2):
-            c = int(rng.choice(real))
-            res["location"][i, e] = int(pb[c] + rng.integers(0, 150000)) if rng.random() < 0.85 else 0xFFFFFFFF
-            res["score"][i, e] = int(rng.integers(0, 18))
-            res["mapq"][i, e] = int(rng.integers(0, 71))
-            res["direction"][i, e] = int(rng.integers(0, 2))
-            res["status"][i, e] = int(rng.integers(0, 3))
+    F.fabricate_hits(hits, res, keep["tpiece_begin"], keep["piece_begin"], genome_pieces(os.path.join(d, "gidx"))[0], b0.n)
     want = F.run_reference_filter(ref, hg, ht, os.path.join(d, "a.gtf"), os.path.join(d, "want"), sam_reads, hits, res, pp)
     here = os.path.dirname(os.path.abspath(__file__))
     so = os.path.join(here, "hostsim", "libiohostsim.so")
@@ -463,13 +537,3 @@ def test_filter_decision_on_fabricated_hits(ref, tmp_path):
         assert open(os.path.join(d, f), "rb").read() == open(os.path.join(d, "want" + f[len("replay"):]), "rb").read(), f
 
 
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="snapb200_filter_paired_batch (one thread per pair around the host-verified flt_filter_pair) was written after the "
-                                        "round's GPU budget was spent: this is its first run on a device, in its own process so that a fault cannot "
-                                        "touch the other tests; it reports XPASS when the kernel reproduces the reference's AlignmentFilter")
-def test_cuda_filter_first_run():
-    import subprocess
-    import sys
-    r = subprocess.run([sys.executable, os.path.join(HERE, "filter_gpu_check.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-    print(r.stdout[-3000:])
-    assert r.returncode == 0 and "FILTER_GPU_OK" in r.stdout, r.stdout[-3000:]

@@ -328,6 +328,16 @@ typedef struct {
     uint32_t pos_original[2], pos[2], pos_end[2];
 } snapb200_filter_event;
 
+/* One novel-splice candidate of AlignmentFilter::UnalignedRead (SNAPLib/AlignmentFilter.cpp:742-933): the two partial alignments of a
+ * read without any alignment that the reference hands to GTFReader::IntrachromosomalSplice (kind 2) or InterchromosomalSplice (kind 3)
+ * together with the read's id (read 0's or read 1's of pair `pair`, as snapb200_filter_event::unaligned says).  chr = genome piece. */
+typedef struct {
+    uint32_t pair;
+    int32_t kind;
+    int32_t chr[2];
+    uint32_t pos[2], pos_end[2];
+} snapb200_splice;
+
 /* Replaces the AlignmentFilter section of PairedAlignerContext::runIterationThread (SNAPLib/PairedAligner.cpp:582-663;
  * AlignmentFilter::AddAlignment / Filter, SNAPLib/AlignmentFilter.cpp:140-740) for a batch of n pairs.  Inputs are what the other
  * entry points return: the transcriptome multi-hits of both reads (snapb200_single_multihit_batch: counts[n] and rows of
@@ -374,6 +384,12 @@ typedef struct {
     const uint64_t *seg_offsets[2];
     const uint32_t *ch_locations[2];
     const uint16_t *ch_seed_offsets[2];
+    /* AlignmentFilter::UnalignedRead of every read events[i].unaligned flags, as records in the reference's loop order: pair i owns
+     * splices[splice_offsets[i] .. splice_offsets[i+1]).  splice_overflow[i] != 0: the read has more partial alignments than the
+     * device scratch holds; no records, the caller runs UnalignedRead itself (from seg_offsets / ch_*). */
+    const uint64_t *splice_offsets;
+    const snapb200_splice *splices;
+    const uint8_t *splice_overflow;
     float device_ms;   /* wall time of the device work of this batch (uploads, kernels, downloads), for the shim's timing report */
 } snapb200_rna_view;
 

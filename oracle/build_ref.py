@@ -54,6 +54,13 @@ INLINE_PATCHES = [
     # the one-word change of INTEGRATION.md section 3: CharacterizeSeeds becomes virtual so that the extension's
     # GpuSeedCharacterizer can serve it from device results (no effect on the reference's own behaviour)
     ("SNAPLib/BaseAligner.h", 88, "AlignmentResult", "virtual AlignmentResult"),
+    # the other change of INTEGRATION.md section 3: the friend declaration the reference already grants AlignerContext2 in its three
+    # context classes, extended to the fusion-interval bookkeeping, so that the extension can append a batch's novel-splice intervals
+    # under ONE lock acquisition instead of one GTFReader::IntrachromosomalSplice call (= one acquisition of a process-wide lock with
+    # two allocations inside) per candidate.  No effect on the reference's own behaviour.
+    ("SNAPLib/GTFReader.h", 56, "class ReadInterval {", "class ReadInterval { friend class AlignerContext2;"),
+    ("SNAPLib/GTFReader.h", 134, "class ReadIntervalMap {", "class ReadIntervalMap { friend class AlignerContext2;"),
+    ("SNAPLib/GTFReader.h", 318, "class GTFReader {", "class GTFReader { friend class AlignerContext2;"),
 ]
 
 CXXFLAGS = ["-O3", "-fPIC", "-w", "-fpermissive", "-std=gnu++98", "-Wno-format", "-msse", "-pthread"]

@@ -165,6 +165,9 @@ class Snapb200(BatchLib):
             seg = arr(v.seg_offsets[e], 2 * n + 1, np.uint64)
             t = int(seg[-1]) if n else 0
             out["ch"].append((seg, arr(v.ch_locations[e], t, np.uint32), arr(v.ch_seed_offsets[e], t, np.uint16)))
+        soff = arr(v.splice_offsets, n + 1, np.uint64)
+        out["splice_offsets"], out["splices"] = soff, arr(v.splices, int(soff[-1]) if n else 0, A.SPLICE)
+        out["splice_overflow"] = arr(v.splice_overflow, n, np.uint8)
         return out
 
     def device_count(self):

@@ -24,7 +24,12 @@ struct FilterWorkspace {
     }
 };
 
+struct RnaPool;
+static void rna_pool_release(RnaPool *p);
+
 struct snapb200_annotation {
+    RnaPool *pool = nullptr;         // staging / intermediates of the rna batches in flight (created by the first snapb200_rna_batch_create)
+    std::mutex pool_lock;
     int device = 0;
     int sm_count = 0;
     FltTables t;                     // device pointers, all owned by this handle
@@ -57,6 +62,7 @@ extern "C" void snapb200_annotation_close(snapb200_annotation *a)
     if (!a) return;
     cudaSetDevice(a->device);
     for (FilterWorkspace &w : a->ws) w.release();
+    if (a->pool) rna_pool_release(a->pool);
     for (void *p : a->allocs) cudaFree(p);
     delete a;
 }
@@ -203,7 +209,8 @@ extern "C" int snapb200_filter_paired_batch(snapb200_annotation *a, const snapb2
                                             const uint16_t *ch_off0, const uint64_t *seg1, const uint32_t *ch_loc1, const uint16_t *ch_off1,
                                             snapb200_filter_result *results, snapb200_filter_event *events, uint8_t *needs_host)
 {
-    static_assert(sizeof(snapb200_filter_result) == sizeof(FltResult) && sizeof(snapb200_filter_event) == sizeof(FltEvent), "ABI structs mirror filterfmt.h");
+    static_assert(sizeof(snapb200_filter_result) == sizeof(FltResult) && sizeof(snapb200_filter_event) == sizeof(FltEvent) && sizeof(snapb200_splice) == sizeof(FltSplice),
+                  "ABI structs mirror filterfmt.h");
     if (!a || !params || (n && (!len0 || !len1 || !n0 || !loc0 || !rc0 || !score0 || !n1 || !loc1 || !rc1 || !score1 || !genome_pairs || !seg0 || !seg1 ||
                                 !results || !events || !needs_host)))
         return set_error(SNAPB200_ERR_ARG, "null argument");
@@ -285,14 +292,64 @@ struct PinBuf {  // pinned host memory that only grows
     template <class T> T *as() const { return (T *)p; }
 };
 
+// Pinned staging and device-resident intermediates of one batch in flight.  A small pool per annotation (RNA_POOL of them, allocated
+// on first use and kept): cudaMalloc / cudaFree / cudaHostAlloc synchronise the whole device, so nothing is allocated per batch or
+// per host thread once the pool is warm; a batch borrows a set for the duration of its device work.
+struct RnaResources {
+    PinBuf in_off[2], in_bases[2], in_quals[2];
+    PinBuf h_res, h_ev, h_flags, h_pairs, h_hoff[2], h_hloc[2], h_hrc[2], h_hscore[2], h_seg[2], h_cloc[2], h_coff[2], h_soff, h_splices, h_sover;
+    // (the sessions' own buffers are reused by other callers between the two phases of a batch, so the intermediates live here)
+    DevBuf d_hoff[2], d_hloc[2], d_hrc[2], d_hscore[2], d_seg[2], d_cnt[2], d_cloc[2], d_coff[2], d_keys[2], d_tmp, d_res, d_ev, d_flags, d_scount, d_soff, d_skind, d_sover, d_splices;
+    void release()
+    {
+        PinBuf *pins[] = {&in_off[0], &in_off[1], &in_bases[0], &in_bases[1], &in_quals[0], &in_quals[1], &h_res, &h_ev, &h_flags, &h_pairs,
+                          &h_hoff[0], &h_hoff[1], &h_hloc[0], &h_hloc[1], &h_hrc[0], &h_hrc[1], &h_hscore[0], &h_hscore[1], &h_seg[0], &h_seg[1],
+                          &h_cloc[0], &h_cloc[1], &h_coff[0], &h_coff[1], &h_soff, &h_splices, &h_sover};
+        for (PinBuf *q : pins) q->release();
+        DevBuf *devs[] = {&d_hoff[0], &d_hoff[1], &d_hloc[0], &d_hloc[1], &d_hrc[0], &d_hrc[1], &d_hscore[0], &d_hscore[1], &d_seg[0], &d_seg[1],
+                          &d_cnt[0], &d_cnt[1], &d_cloc[0], &d_cloc[1], &d_coff[0], &d_coff[1], &d_keys[0], &d_keys[1], &d_tmp, &d_res, &d_ev,
+                          &d_flags, &d_scount, &d_soff, &d_skind, &d_sover, &d_splices};
+        for (DevBuf *q : devs) q->release();
+    }
+};
+
+#define RNA_POOL 4
+struct RnaPool {
+    std::mutex m;
+    std::condition_variable cv;
+    RnaResources *all[RNA_POOL] = {nullptr, nullptr, nullptr, nullptr};
+    bool busy[RNA_POOL] = {false, false, false, false};
+    RnaResources *acquire()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            for (int q = 0; q < RNA_POOL; q++)
+                if (!busy[q]) { busy[q] = true; if (!all[q]) all[q] = new RnaResources(); return all[q]; }
+            cv.wait(lk);
+        }
+    }
+    void give_back(RnaResources *r)
+    {
+        std::lock_guard<std::mutex> lk(m);
+        for (int q = 0; q < RNA_POOL; q++) if (all[q] == r) busy[q] = false;
+        cv.notify_one();
+    }
+    void release() { for (int q = 0; q < RNA_POOL; q++) if (all[q]) { all[q]->release(); delete all[q]; all[q] = nullptr; } }
+};
+
+static void rna_pool_release(RnaPool *p) { p->release(); delete p; }
+
+struct HostArr {  // plain host memory of the batch object (inputs copied at submit, outputs copied out of the pinned staging)
+    std::vector<uint8_t> v;
+    void set(const void *src, size_t bytes) { v.resize(bytes + 16); if (bytes) memcpy(v.data(), src, bytes); }
+    template <class T> T *as() { return (T *)v.data(); }
+};
+
 struct snapb200_rna_batch {
     snapb200_annotation *ann = nullptr;
     snapb200_index *genome = nullptr, *transcriptome = nullptr;
-    // pinned staging: inputs (copied at submit) and outputs (filled by the worker)
-    PinBuf in_off[2], in_bases[2], in_quals[2];
-    PinBuf h_res, h_ev, h_flags, h_pairs, h_hoff[2], h_hloc[2], h_hrc[2], h_hscore[2], h_seg[2], h_cloc[2], h_coff[2];
-    // device-resident intermediates owned by the batch (the sessions' buffers are reused by other callers between the phases)
-    DevBuf d_hoff[2], d_hloc[2], d_hrc[2], d_hscore[2], d_seg[2], d_cnt[2], d_cloc[2], d_coff[2], d_keys[2], d_tmp, d_res, d_ev, d_flags;
+    HostArr in_off[2], in_bases[2], in_quals[2];
+    HostArr o_res, o_ev, o_flags, o_pairs, o_hoff[2], o_hloc[2], o_hrc[2], o_hscore[2], o_seg[2], o_cloc[2], o_coff[2], o_soff, o_splices, o_sover;
     snapb200_rna_params params;
     uint32_t n = 0;
     float device_ms = 0;
@@ -312,7 +369,7 @@ static double rna_now()
     return t.tv_sec + t.tv_nsec * 1e-9;
 }
 
-static int rna_run(snapb200_rna_batch *b)
+static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
 {
     const uint32_t n = b->n;
     const bool timing = getenv("SNAPB200_RNA_TIMING") != nullptr;  // where a batch spends its time on the device side (stderr)
@@ -320,7 +377,7 @@ static int rna_run(snapb200_rna_batch *b)
 #define RNA_MARK(i) do { tn = rna_now(); tt[i] += tn - tm; tm = tn; } while (0)
     const snapb200_rna_params &P = b->params;
     snapb200_read_batch r[2];
-    for (int e = 0; e < 2; e++) { r[e].n = n; r[e].offsets = b->in_off[e].as<uint32_t>(); r[e].bases = b->in_bases[e].as<uint8_t>(); r[e].quals = b->in_quals[e].as<uint8_t>(); }
+    for (int e = 0; e < 2; e++) { r[e].n = n; r[e].offsets = R.in_off[e].as<uint32_t>(); r[e].bases = R.in_bases[e].as<uint8_t>(); r[e].quals = R.in_quals[e].as<uint8_t>(); }
     uint32_t m0, m1;
     int rc;
     if ((rc = validate_batch(&r[0], &m0)) || (rc = validate_batch(&r[1], &m1))) return rc;
@@ -337,27 +394,27 @@ static int rna_run(snapb200_rna_batch *b)
         for (int e = 0; e < 2; e++) {
             if ((rc = snapb200_session_upload(s, 0, &r[e])) || (rc = snapb200_session_run_single(s, &P.transcriptome))) return rc;
             RNA_MARK(1);
-            if ((rc = b->d_hoff[e].ensure((size_t)(n + 1) * 4))) return rc;
+            if ((rc = R.d_hoff[e].ensure((size_t)(n + 1) * 4))) return rc;
             size_t tmp_bytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s->mh_counts.as<int32_t>(), b->d_hoff[e].as<uint32_t>(), (int)n + 1, s->stream);
-            if ((rc = b->d_tmp.ensure(tmp_bytes))) return rc;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s->mh_counts.as<int32_t>(), R.d_hoff[e].as<uint32_t>(), (int)n + 1, s->stream);
+            if ((rc = R.d_tmp.ensure(tmp_bytes))) return rc;
             // counts[n] is scratch past the last read: the scan's n-th output (the total) only needs inputs 0..n-1
             if ((rc = s->mh_counts.ensure((size_t)(n + 1) * 4))) return rc;
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(b->d_tmp.p, tmp_bytes, s->mh_counts.as<int32_t>(), b->d_hoff[e].as<uint32_t>(), (int)n + 1, s->stream));
-            CUDA_TRY(cudaMemcpyAsync(&total_hits[e], b->d_hoff[e].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(R.d_tmp.p, tmp_bytes, s->mh_counts.as<int32_t>(), R.d_hoff[e].as<uint32_t>(), (int)n + 1, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(&total_hits[e], R.d_hoff[e].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, s->stream));
             CUDA_TRY(cudaStreamSynchronize(s->stream));
             const size_t th = std::max<uint32_t>(total_hits[e], 1);
-            if ((rc = b->d_hloc[e].ensure(th * 4)) || (rc = b->d_hrc[e].ensure(th)) || (rc = b->d_hscore[e].ensure(th * 4))) return rc;
-            mh_compact_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, mh, s->mh_counts.as<int32_t>(), b->d_hoff[e].as<uint32_t>(), s->mh_locs.as<uint32_t>(),
-                                                                      s->mh_rcs.as<uint8_t>(), s->mh_scores.as<int32_t>(), b->d_hloc[e].as<uint32_t>(),
-                                                                      b->d_hrc[e].as<uint8_t>(), b->d_hscore[e].as<int32_t>());
+            if ((rc = R.d_hloc[e].ensure(th * 4)) || (rc = R.d_hrc[e].ensure(th)) || (rc = R.d_hscore[e].ensure(th * 4))) return rc;
+            mh_compact_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, mh, s->mh_counts.as<int32_t>(), R.d_hoff[e].as<uint32_t>(), s->mh_locs.as<uint32_t>(),
+                                                                      s->mh_rcs.as<uint8_t>(), s->mh_scores.as<int32_t>(), R.d_hloc[e].as<uint32_t>(),
+                                                                      R.d_hrc[e].as<uint8_t>(), R.d_hscore[e].as<int32_t>());
             CUDA_TRY(cudaGetLastError());
-            if ((rc = b->h_hoff[e].ensure((size_t)(n + 1) * 4)) || (rc = b->h_hloc[e].ensure(th * 4)) || (rc = b->h_hrc[e].ensure(th)) || (rc = b->h_hscore[e].ensure(th * 4))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(b->h_hoff[e].p, b->d_hoff[e].p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+            if ((rc = R.h_hoff[e].ensure((size_t)(n + 1) * 4)) || (rc = R.h_hloc[e].ensure(th * 4)) || (rc = R.h_hrc[e].ensure(th)) || (rc = R.h_hscore[e].ensure(th * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(R.h_hoff[e].p, R.d_hoff[e].p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
             if (total_hits[e]) {
-                CUDA_TRY(cudaMemcpyAsync(b->h_hloc[e].p, b->d_hloc[e].p, (size_t)total_hits[e] * 4, cudaMemcpyDeviceToHost, s->stream));
-                CUDA_TRY(cudaMemcpyAsync(b->h_hrc[e].p, b->d_hrc[e].p, (size_t)total_hits[e], cudaMemcpyDeviceToHost, s->stream));
-                CUDA_TRY(cudaMemcpyAsync(b->h_hscore[e].p, b->d_hscore[e].p, (size_t)total_hits[e] * 4, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(R.h_hloc[e].p, R.d_hloc[e].p, (size_t)total_hits[e] * 4, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(R.h_hrc[e].p, R.d_hrc[e].p, (size_t)total_hits[e], cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(R.h_hscore[e].p, R.d_hscore[e].p, (size_t)total_hits[e] * 4, cudaMemcpyDeviceToHost, s->stream));
             }
             CUDA_TRY(cudaStreamSynchronize(s->stream));  // the session's dense rows are reused by the next mate / the next caller
             RNA_MARK(2);
@@ -371,20 +428,20 @@ static int rna_run(snapb200_rna_batch *b)
         RNA_MARK(3);
         if ((rc = snapb200_session_upload(s, 0, &r[0])) || (rc = snapb200_session_upload(s, 1, &r[1]))) return rc;
         if ((rc = snapb200_session_run_paired(s, &P.paired))) return rc;
-        if ((rc = b->h_pairs.ensure((size_t)n * sizeof(snapb200_paired_result)))) return rc;
-        rc = snapb200_session_download_paired(s, b->h_pairs.as<snapb200_paired_result>());
+        if ((rc = R.h_pairs.ensure((size_t)n * sizeof(snapb200_paired_result)))) return rc;
+        rc = snapb200_session_download_paired(s, R.h_pairs.as<snapb200_paired_result>());
         if (rc) return rc;  // includes ERR_LIMIT: the reference exits there
         if (!s->host_fix.empty())  // the libm re-evaluations of download_paired, mirrored into the resident records the filter reads
             for (const MapqFix &f : s->host_fix) {
                 const uint32_t pi = f.is_paired_rule ? f.index : f.index >> 1;
-                CUDA_TRY(cudaMemcpyAsync(s->paired_res.as<snapb200_paired_result>() + pi, b->h_pairs.as<snapb200_paired_result>() + pi,
+                CUDA_TRY(cudaMemcpyAsync(s->paired_res.as<snapb200_paired_result>() + pi, R.h_pairs.as<snapb200_paired_result>() + pi,
                                          sizeof(snapb200_paired_result), cudaMemcpyHostToDevice, s->stream));
             }
         RNA_MARK(4);
         uint64_t tuples[2] = {0, 0};
         for (int e = 0; e < 2; e++)
-            if ((rc = characterize_device(b->genome, s, e, &P.partial, std::max(m0, m1), b->d_cnt[e], b->d_seg[e], b->d_keys[0], b->d_keys[1], b->d_tmp, b->d_cloc[e],
-                                          b->d_coff[e], &tuples[e]))) return rc;
+            if ((rc = characterize_device(b->genome, s, e, &P.partial, std::max(m0, m1), R.d_cnt[e], R.d_seg[e], R.d_keys[0], R.d_keys[1], R.d_tmp, R.d_cloc[e],
+                                          R.d_coff[e], &tuples[e]))) return rc;
         RNA_MARK(5);
         FilterWarpArgs k;
         memset(&k, 0, sizeof(k));
@@ -393,27 +450,68 @@ static int rna_run(snapb200_rna_batch *b)
         k.len_is_offsets = 1;
         for (int e = 0; e < 2; e++) {
             k.len[e] = s->offsets[e].as<uint32_t>();
-            k.mh_off[e] = b->d_hoff[e].as<uint32_t>(); k.loc[e] = b->d_hloc[e].as<uint32_t>(); k.rc[e] = b->d_hrc[e].as<uint8_t>(); k.score[e] = b->d_hscore[e].as<int32_t>();
-            k.seg[e] = b->d_seg[e].as<unsigned long long>(); k.ch_loc[e] = b->d_cloc[e].as<uint32_t>(); k.ch_off[e] = b->d_coff[e].as<uint16_t>();
+            k.mh_off[e] = R.d_hoff[e].as<uint32_t>(); k.loc[e] = R.d_hloc[e].as<uint32_t>(); k.rc[e] = R.d_hrc[e].as<uint8_t>(); k.score[e] = R.d_hscore[e].as<int32_t>();
+            k.seg[e] = R.d_seg[e].as<unsigned long long>(); k.ch_loc[e] = R.d_cloc[e].as<uint32_t>(); k.ch_off[e] = R.d_coff[e].as<uint16_t>();
         }
         k.g = s->paired_res.as<snapb200_paired_result>();
-        if ((rc = b->d_res.ensure((size_t)n * sizeof(FltResult))) || (rc = b->d_ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = b->d_flags.ensure(n))) return rc;
-        CUDA_TRY(cudaMemsetAsync(b->d_res.p, 0, (size_t)n * sizeof(FltResult), s->stream));
-        CUDA_TRY(cudaMemsetAsync(b->d_ev.p, 0, (size_t)n * sizeof(FltEvent), s->stream));
-        k.out = b->d_res.as<FltResult>(); k.ev = b->d_ev.as<FltEvent>(); k.needs_host = b->d_flags.as<uint8_t>();
+        if ((rc = R.d_res.ensure((size_t)n * sizeof(FltResult))) || (rc = R.d_ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = R.d_flags.ensure(n))) return rc;
+        CUDA_TRY(cudaMemsetAsync(R.d_res.p, 0, (size_t)n * sizeof(FltResult), s->stream));
+        CUDA_TRY(cudaMemsetAsync(R.d_ev.p, 0, (size_t)n * sizeof(FltEvent), s->stream));
+        k.out = R.d_res.as<FltResult>(); k.ev = R.d_ev.as<FltEvent>(); k.needs_host = R.d_flags.as<uint8_t>();
         if ((rc = filter_launch(b->ann, k, s->f_scratch, s->f_work, s->stream))) return rc;
         s->total_launches++;
-        if ((rc = b->h_res.ensure((size_t)n * sizeof(FltResult))) || (rc = b->h_ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = b->h_flags.ensure(n))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(b->h_res.p, b->d_res.p, (size_t)n * sizeof(FltResult), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaMemcpyAsync(b->h_ev.p, b->d_ev.p, (size_t)n * sizeof(FltEvent), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaMemcpyAsync(b->h_flags.p, b->d_flags.p, n, cudaMemcpyDeviceToHost, s->stream));
+        // AlignmentFilter::UnalignedRead of the reads the filter flagged, as records (count, scan, emit)
+        unsigned long long n_splices = 0;
+        {
+            SpliceArgs sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.t = b->ann->t; sa.n = n; sa.seed_len = b->genome->dev.seed_len;
+            sa.ev = k.ev; sa.pair_needs_host = k.needs_host;
+            for (int e = 0; e < 2; e++) { sa.offsets[e] = k.len[e]; sa.seg[e] = k.seg[e]; sa.ch_loc[e] = k.ch_loc[e]; sa.ch_off[e] = k.ch_off[e]; }
+            sa.seg_cap = 4096;
+            sa.scratch_per_warp = splice_scratch_bytes(sa.seg_cap);
+            const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>((n + 7) / 8, (uint32_t)b->ann->sm_count));
+            if ((rc = s->f_scratch.ensure((size_t)ctas * 8 * sa.scratch_per_warp))) return rc;
+            if ((rc = R.d_scount.ensure((size_t)(n + 1) * 8)) || (rc = R.d_soff.ensure((size_t)(n + 1) * 8)) || (rc = R.d_skind.ensure(n)) || (rc = R.d_sover.ensure(n))) return rc;
+            CUDA_TRY(cudaMemsetAsync(R.d_scount.p, 0, (size_t)(n + 1) * 8, s->stream));
+            CUDA_TRY(cudaMemsetAsync(R.d_skind.p, 0, n, s->stream));
+            CUDA_TRY(cudaMemsetAsync(R.d_sover.p, 0, n, s->stream));
+            CUDA_TRY(cudaMemsetAsync(s->f_work.p, 0, 64, s->stream));
+            sa.scratch = s->f_scratch.as<uint8_t>(); sa.work = s->f_work.as<uint32_t>();
+            sa.counts = R.d_scount.as<unsigned long long>(); sa.kind = R.d_skind.as<uint8_t>(); sa.overflow = R.d_sover.as<uint8_t>();
+            splice_kernel<false><<<ctas, 256, 0, s->stream>>>(sa);
+            CUDA_TRY(cudaGetLastError());
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, R.d_scount.as<unsigned long long>(), R.d_soff.as<unsigned long long>(), (int)n + 1, s->stream);
+            if ((rc = R.d_tmp.ensure(tmp_bytes))) return rc;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(R.d_tmp.p, tmp_bytes, R.d_scount.as<unsigned long long>(), R.d_soff.as<unsigned long long>(), (int)n + 1, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(&n_splices, R.d_soff.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if ((rc = R.h_soff.ensure((size_t)(n + 1) * 8)) || (rc = R.h_sover.ensure(n)) || (rc = R.h_splices.ensure(std::max<unsigned long long>(n_splices, 1) * sizeof(FltSplice)))) return rc;
+            if (n_splices) {
+                if ((rc = R.d_splices.ensure(n_splices * sizeof(FltSplice)))) return rc;
+                CUDA_TRY(cudaMemsetAsync(s->f_work.p, 0, 64, s->stream));
+                sa.counts = R.d_soff.as<unsigned long long>();
+                sa.out = R.d_splices.as<FltSplice>();
+                splice_kernel<true><<<ctas, 256, 0, s->stream>>>(sa);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaMemcpyAsync(R.h_splices.p, R.d_splices.p, n_splices * sizeof(FltSplice), cudaMemcpyDeviceToHost, s->stream));
+            }
+            CUDA_TRY(cudaMemcpyAsync(R.h_soff.p, R.d_soff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(R.h_sover.p, R.d_sover.p, n, cudaMemcpyDeviceToHost, s->stream));
+            s->total_launches += 2;
+        }
+        if ((rc = R.h_res.ensure((size_t)n * sizeof(FltResult))) || (rc = R.h_ev.ensure((size_t)n * sizeof(FltEvent))) || (rc = R.h_flags.ensure(n))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(R.h_res.p, R.d_res.p, (size_t)n * sizeof(FltResult), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(R.h_ev.p, R.d_ev.p, (size_t)n * sizeof(FltEvent), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(R.h_flags.p, R.d_flags.p, n, cudaMemcpyDeviceToHost, s->stream));
         for (int e = 0; e < 2; e++) {
             const size_t t = std::max<uint64_t>(tuples[e], 1);
-            if ((rc = b->h_seg[e].ensure((2 * (size_t)n + 1) * 8)) || (rc = b->h_cloc[e].ensure(t * 4)) || (rc = b->h_coff[e].ensure(t * 2))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(b->h_seg[e].p, b->d_seg[e].p, (2 * (size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+            if ((rc = R.h_seg[e].ensure((2 * (size_t)n + 1) * 8)) || (rc = R.h_cloc[e].ensure(t * 4)) || (rc = R.h_coff[e].ensure(t * 2))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(R.h_seg[e].p, R.d_seg[e].p, (2 * (size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
             if (tuples[e]) {
-                CUDA_TRY(cudaMemcpyAsync(b->h_cloc[e].p, b->d_cloc[e].p, tuples[e] * 4, cudaMemcpyDeviceToHost, s->stream));
-                CUDA_TRY(cudaMemcpyAsync(b->h_coff[e].p, b->d_coff[e].p, tuples[e] * 2, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(R.h_cloc[e].p, R.d_cloc[e].p, tuples[e] * 4, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaMemcpyAsync(R.h_coff[e].p, R.d_coff[e].p, tuples[e] * 2, cudaMemcpyDeviceToHost, s->stream));
             }
         }
         cudaError_t e2 = cudaStreamSynchronize(s->stream);
@@ -425,6 +523,41 @@ static int rna_run(snapb200_rna_batch *b)
                         "CharacterizeSeeds x2 %.3f, filter + downloads %.3f\n", n, b->genome->device, tt[0], tt[1], tt[2], tt[3], tt[4], tt[5], tt[6]);
 #undef RNA_MARK
     return 0;
+}
+
+// The device work of one batch: borrow a resource set, stage the inputs in pinned memory, run, copy the outputs out of the pinned staging.
+static int rna_run(snapb200_rna_batch *b)
+{
+    {
+        std::lock_guard<std::mutex> g(b->ann->pool_lock);
+        if (!b->ann->pool) b->ann->pool = new RnaPool();
+    }
+    RnaResources *res = b->ann->pool->acquire();
+    RnaResources &R = *res;
+    const uint32_t n = b->n;
+    int rc = 0;
+    cudaSetDevice(b->genome->device);
+    for (int e = 0; e < 2 && !rc; e++) {
+        const size_t nb = b->in_off[e].as<uint32_t>()[n];
+        if ((rc = R.in_off[e].ensure((size_t)(n + 1) * 4)) || (rc = R.in_bases[e].ensure(nb + 16)) || (rc = R.in_quals[e].ensure(nb + 16))) break;
+        memcpy(R.in_off[e].p, b->in_off[e].v.data(), (size_t)(n + 1) * 4);
+        memcpy(R.in_bases[e].p, b->in_bases[e].v.data(), nb);
+        memcpy(R.in_quals[e].p, b->in_quals[e].v.data(), nb);
+    }
+    if (!rc) rc = rna_run_on(b, R);
+    if (!rc) {
+        b->o_res.set(R.h_res.p, (size_t)n * sizeof(FltResult)); b->o_ev.set(R.h_ev.p, (size_t)n * sizeof(FltEvent)); b->o_flags.set(R.h_flags.p, n);
+        b->o_pairs.set(R.h_pairs.p, (size_t)n * sizeof(snapb200_paired_result));
+        for (int e = 0; e < 2; e++) {
+            const size_t th = R.h_hoff[e].as<uint32_t>()[n], tt = (size_t)R.h_seg[e].as<uint64_t>()[2 * (size_t)n];
+            b->o_hoff[e].set(R.h_hoff[e].p, (size_t)(n + 1) * 4); b->o_hloc[e].set(R.h_hloc[e].p, th * 4); b->o_hrc[e].set(R.h_hrc[e].p, th); b->o_hscore[e].set(R.h_hscore[e].p, th * 4);
+            b->o_seg[e].set(R.h_seg[e].p, (2 * (size_t)n + 1) * 8); b->o_cloc[e].set(R.h_cloc[e].p, tt * 4); b->o_coff[e].set(R.h_coff[e].p, tt * 2);
+        }
+        const size_t ns = (size_t)R.h_soff.as<uint64_t>()[n];
+        b->o_soff.set(R.h_soff.p, (size_t)(n + 1) * 8); b->o_splices.set(R.h_splices.p, ns * sizeof(FltSplice)); b->o_sover.set(R.h_sover.p, n);
+    }
+    b->ann->pool->give_back(res);
+    return rc;
 }
 
 static void rna_worker(snapb200_rna_batch *b)
@@ -468,15 +601,6 @@ extern "C" void snapb200_rna_batch_destroy(snapb200_rna_batch *b)
         b->cv.notify_all();
     }
     b->worker.join();
-    cudaSetDevice(b->genome->device);
-    PinBuf *pins[] = {&b->in_off[0], &b->in_off[1], &b->in_bases[0], &b->in_bases[1], &b->in_quals[0], &b->in_quals[1], &b->h_res, &b->h_ev, &b->h_flags, &b->h_pairs,
-                      &b->h_hoff[0], &b->h_hoff[1], &b->h_hloc[0], &b->h_hloc[1], &b->h_hrc[0], &b->h_hrc[1], &b->h_hscore[0], &b->h_hscore[1], &b->h_seg[0], &b->h_seg[1],
-                      &b->h_cloc[0], &b->h_cloc[1], &b->h_coff[0], &b->h_coff[1]};
-    for (PinBuf *p : pins) p->release();
-    DevBuf *devs[] = {&b->d_hoff[0], &b->d_hoff[1], &b->d_hloc[0], &b->d_hloc[1], &b->d_hrc[0], &b->d_hrc[1], &b->d_hscore[0], &b->d_hscore[1], &b->d_seg[0], &b->d_seg[1],
-                      &b->d_cnt[0], &b->d_cnt[1], &b->d_cloc[0], &b->d_cloc[1], &b->d_coff[0], &b->d_coff[1], &b->d_keys[0], &b->d_keys[1], &b->d_tmp, &b->d_res, &b->d_ev,
-                      &b->d_flags};
-    for (DevBuf *d : devs) d->release();
     delete b;
 }
 
@@ -486,17 +610,14 @@ extern "C" int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_r
     if (reads0->n != reads1->n) return set_error(SNAPB200_ERR_ARG, "mate batches differ in size");
     std::unique_lock<std::mutex> lk(b->m);
     if (b->state == 1) return set_error(SNAPB200_ERR_ARG, "rna batch: a submitted batch has not been waited for");
-    CUDA_TRY(cudaSetDevice(b->genome->device));
     const snapb200_read_batch *r[2] = {reads0, reads1};
     const uint32_t n = reads0->n;
     for (int e = 0; e < 2 && n; e++) {
         if (!r[e]->offsets || !r[e]->bases || !r[e]->quals) return set_error(SNAPB200_ERR_ARG, "null read batch");
         const size_t nb = r[e]->offsets[n];
-        int rc;
-        if ((rc = b->in_off[e].ensure((size_t)(n + 1) * 4)) || (rc = b->in_bases[e].ensure(nb + 16)) || (rc = b->in_quals[e].ensure(nb + 16))) return rc;
-        memcpy(b->in_off[e].p, r[e]->offsets, (size_t)(n + 1) * 4);
-        memcpy(b->in_bases[e].p, r[e]->bases, nb);
-        memcpy(b->in_quals[e].p, r[e]->quals, nb);
+        b->in_off[e].set(r[e]->offsets, (size_t)(n + 1) * 4);
+        b->in_bases[e].set(r[e]->bases, nb);
+        b->in_quals[e].set(r[e]->quals, nb);
     }
     b->params = *params;
     b->n = n;
@@ -517,14 +638,17 @@ extern "C" int snapb200_rna_batch_wait(snapb200_rna_batch *b, snapb200_rna_view 
     view->n = b->n;
     view->device_ms = b->device_ms;
     if (!b->n) return 0;
-    view->results = b->h_res.as<snapb200_filter_result>();
-    view->events = b->h_ev.as<snapb200_filter_event>();
-    view->needs_host = b->h_flags.as<uint8_t>();
-    view->genome_pairs = b->h_pairs.as<snapb200_paired_result>();
+    view->results = b->o_res.as<snapb200_filter_result>();
+    view->events = b->o_ev.as<snapb200_filter_event>();
+    view->needs_host = b->o_flags.as<uint8_t>();
+    view->genome_pairs = b->o_pairs.as<snapb200_paired_result>();
     for (int e = 0; e < 2; e++) {
-        view->hit_offsets[e] = b->h_hoff[e].as<uint32_t>(); view->hit_locations[e] = b->h_hloc[e].as<uint32_t>();
-        view->hit_rcs[e] = b->h_hrc[e].as<uint8_t>(); view->hit_scores[e] = b->h_hscore[e].as<int32_t>();
-        view->seg_offsets[e] = b->h_seg[e].as<uint64_t>(); view->ch_locations[e] = b->h_cloc[e].as<uint32_t>(); view->ch_seed_offsets[e] = b->h_coff[e].as<uint16_t>();
+        view->hit_offsets[e] = b->o_hoff[e].as<uint32_t>(); view->hit_locations[e] = b->o_hloc[e].as<uint32_t>();
+        view->hit_rcs[e] = b->o_hrc[e].as<uint8_t>(); view->hit_scores[e] = b->o_hscore[e].as<int32_t>();
+        view->seg_offsets[e] = b->o_seg[e].as<uint64_t>(); view->ch_locations[e] = b->o_cloc[e].as<uint32_t>(); view->ch_seed_offsets[e] = b->o_coff[e].as<uint16_t>();
     }
+    view->splice_offsets = b->o_soff.as<uint64_t>();
+    view->splices = b->o_splices.as<snapb200_splice>();
+    view->splice_overflow = b->o_sover.as<uint8_t>();
     return 0;
 }

@@ -367,3 +367,154 @@ __global__ void __launch_bounds__(256) filter_warp_kernel(const FilterWarpArgs a
         __syncwarp();
     }
 }
+
+// ---- AlignmentFilter::UnalignedRead as records, one warp per flagged read (the serial specification is flt_unaligned_splices) ---------
+// Pass COUNT sizes every read's record list (and says which GTFReader call it is for), a scan turns the sizes into offsets, pass EMIT
+// writes the records in the reference's loop order.  Per read: the partial alignments are built by ordered ballot compaction over the
+// seed tuples; every alignment gets the (at most SPLICE_GENES) genes that cover it, found by all lanes over the gene table, so that
+// the gene test of a candidate is a few boundary checks; the n (n - 1) / 2 candidates are tested 32 per step.
+#define SPLICE_GENES 4
+
+struct SpliceArgs {
+    FltTables t;
+    uint32_t n, seed_len;
+    const uint32_t *offsets[2];          // read batch offsets (read length = offsets[i + 1] - offsets[i])
+    const FltEvent *ev;
+    const uint8_t *pair_needs_host;      // pairs whose filter result is not valid are skipped (the host runs the reference for them)
+    const unsigned long long *seg[2];
+    const uint32_t *ch_loc[2];
+    const uint16_t *ch_off[2];
+    unsigned long long *counts;          // COUNT: [n + 1] out; EMIT: exclusive offsets in
+    uint8_t *kind;                       // [n] FLT_SPLICE_* of the read's records (COUNT out, EMIT in)
+    uint8_t *overflow;                   // [n] more partial alignments than the scratch holds: the host runs UnalignedRead itself
+    FltSplice *out;                      // EMIT
+    uint32_t *work;
+    uint8_t *scratch;
+    size_t scratch_per_warp;
+    uint32_t seg_cap;
+};
+
+struct SpliceGenes { uint32_t n; int32_t g[SPLICE_GENES]; };  // n > SPLICE_GENES: too many, scan the table
+
+__host__ __device__ inline size_t splice_scratch_bytes(uint32_t seg_cap) { return (size_t)seg_cap * (sizeof(FltSeg) + sizeof(SpliceGenes)); }
+
+__device__ __forceinline__ bool splice_in_gene(const FltTables &t, const FltSeg &a0, const SpliceGenes &sg, const FltSeg &a1)
+{
+    if (sg.n > SPLICE_GENES) return flt_splice_in_gene(t, a0, a1);
+    for (uint32_t q = 0; q < sg.n; q++) if (flt_check_boundary(t, sg.g[q], a1.chr, a1.pos)) return true;
+    return false;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) splice_kernel(const SpliceArgs a)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = lane_id();
+    FltSeg *segs = (FltSeg *)(a.scratch + (size_t)warp * a.scratch_per_warp);
+    SpliceGenes *genes = (SpliceGenes *)(segs + a.seg_cap);
+    const FltTables &t = a.t;
+    for (;;) {
+        const uint32_t i = fetch_work(a.work);
+        if (i >= a.n) break;
+        const int which = a.pair_needs_host[i] ? 0 : a.ev[i].unaligned;
+        if (!which) continue;
+        if (EMIT && (a.overflow[i] || a.kind[i] == FLT_SPLICE_NONE)) continue;
+        const int e = which - 1;
+        const uint32_t read_len = a.offsets[e][i + 1] - a.offsets[e][i];
+        const unsigned long long lo = a.seg[e][2 * (size_t)i], mid = a.seg[e][2 * (size_t)i + 1], hi = a.seg[e][2 * (size_t)i + 2];
+        // the partial alignments, in the order of the reference's vector: forward map ascending, then RC map ascending
+        uint32_t n = 0;
+        bool over = false;
+        #pragma unroll 1
+        for (unsigned long long q0 = lo; q0 < hi && !over; q0 += 32) {
+            const unsigned long long q = q0 + lane;
+            bool first = false;
+            FltSeg s;
+            if (q < hi) {
+                const bool rc = q >= mid;
+                const unsigned long long begin = rc ? mid : lo, end = rc ? hi : mid;
+                const uint32_t loc = a.ch_loc[e][q];
+                first = q == begin || a.ch_loc[e][q - 1] != loc;
+                if (first) {
+                    unsigned long long last = q;
+                    while (last + 1 < end && a.ch_loc[e][last + 1] == loc) last++;
+                    const int p = flt_piece_at(t.piece_begin, (int)t.n_pieces, loc);
+                    if (p < 0) first = false;
+                    else {
+                        const uint32_t o0 = a.ch_off[e][q], o1 = a.ch_off[e][last], length = (o1 - o0) + a.seed_len;
+                        const int32_t pos0 = (int32_t)(loc - t.piece_begin[p] + 1);
+                        const uint32_t start = rc ? (uint32_t)pos0 + read_len - (o1 + a.seed_len) : (uint32_t)pos0 + o0;
+                        s.chr = p; s.pos = start; s.pos_end = start + length - 1; s.score = length;
+                    }
+                }
+            }
+            const uint32_t b = __ballot_sync(FULL_MASK, first);
+            const uint32_t at = n + __popc(b & ((1u << lane) - 1));
+            over = n + __popc(b) > a.seg_cap;
+            if (first && !over) segs[at] = s;
+            n += __popc(b);
+        }
+        if (over) {
+            if (!EMIT && lane == 0) { a.overflow[i] = 1; a.counts[i] = 0; a.kind[i] = FLT_SPLICE_NONE; }
+            continue;
+        }
+        __syncwarp();
+        // the genes that cover each alignment (GTFReader::IntervalGenes), all lanes over the gene table
+        #pragma unroll 1
+        for (uint32_t k = 0; k < n; k++) {
+            const FltSeg s = segs[k];
+            uint32_t cnt = 0;
+            #pragma unroll 1
+            for (uint32_t g0 = 0; g0 < t.n_genes; g0 += 32) {
+                const uint32_t g = g0 + lane;
+                const bool hit = g < t.n_genes && flt_gene_found(t, g, s.chr, s.pos, s.pos_end);
+                const uint32_t b = __ballot_sync(FULL_MASK, hit);
+                if (hit) { const uint32_t at = cnt + __popc(b & ((1u << lane) - 1)); if (at < SPLICE_GENES) genes[k].g[at] = (int32_t)g; }
+                cnt += __popc(b);
+            }
+            if (lane == 0) genes[k].n = cnt;
+        }
+        __syncwarp();
+        // the candidate loop (AlignmentFilter.cpp:809-876)
+        const int want = EMIT ? (int)a.kind[i] : 0;
+        unsigned long long c_intra = 0, c_inter = 0, w = EMIT ? a.counts[i] : 0;
+        bool gene = false;
+        #pragma unroll 1
+        for (uint32_t k = 0; k + 1 < n && !gene; k++) {
+            const FltSeg s0 = segs[k];
+            const SpliceGenes sg = genes[k];
+            #pragma unroll 1
+            for (uint32_t j0 = k + 1; j0 < n; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                int c = FLT_SPLICE_NONE;
+                FltSeg s1;
+                if (j < n) {
+                    s1 = segs[j];
+                    c = flt_splice_class(s0, s1, read_len, a.seed_len);
+                    if (!EMIT && c == FLT_SPLICE_INTRACHR && splice_in_gene(t, s0, sg, s1)) c = FLT_SPLICE_GENE;
+                }
+                if (!EMIT) {
+                    if (__any_sync(FULL_MASK, c == FLT_SPLICE_GENE)) { gene = true; break; }
+                    c_intra += __popc(__ballot_sync(FULL_MASK, c == FLT_SPLICE_INTRACHR));
+                    c_inter += __popc(__ballot_sync(FULL_MASK, c == FLT_SPLICE_INTERCHR));
+                } else {
+                    const uint32_t b = __ballot_sync(FULL_MASK, c == want);
+                    if (c == want) {
+                        FltSplice &o = a.out[w + __popc(b & ((1u << lane) - 1))];
+                        o.pair = i; o.kind = c;
+                        o.chr[0] = s0.chr; o.pos[0] = s0.pos; o.pos_end[0] = s0.pos_end;
+                        o.chr[1] = s1.chr; o.pos[1] = s1.pos; o.pos_end[1] = s1.pos_end;
+                    }
+                    w += __popc(b);
+                }
+            }
+        }
+        if (!EMIT && lane == 0) {
+            const int kind = gene ? FLT_SPLICE_NONE : c_intra ? FLT_SPLICE_INTRACHR : c_inter ? FLT_SPLICE_INTERCHR : FLT_SPLICE_NONE;
+            a.kind[i] = (uint8_t)kind;
+            a.overflow[i] = 0;
+            a.counts[i] = kind == FLT_SPLICE_INTRACHR ? c_intra : kind == FLT_SPLICE_INTERCHR ? c_inter : 0;
+        }
+        __syncwarp();
+    }
+}

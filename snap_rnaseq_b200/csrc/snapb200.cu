@@ -346,24 +346,30 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
     int rc = 0;
     std::vector<uint64_t> sizes(n_tables), starts(n_tables), counts(n_tables);
     uint32_t overflow_words = 0;
+    // every failure inside the block leaves through the cleanup below (a CUDA_TRY would return and leak up to ~120 GB of build buffers)
+#define IB_TRY(expr)                                                                                                          \
+    {                                                                                                                         \
+        cudaError_t _e = (expr);                                                                                              \
+        if (_e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); break; } \
+    }
     do {
         if ((rc = dev_alloc(&d_genome, (size_t)n_bases + 64))) break;
-        CUDA_TRY(cudaMemset(d_genome, 'n', (size_t)n_bases + 64));
-        CUDA_TRY(cudaMemcpy(d_genome, bases, n_bases, cudaMemcpyHostToDevice));
+        IB_TRY(cudaMemset(d_genome, 'n', (size_t)n_bases + 64));
+        IB_TRY(cudaMemcpy(d_genome, bases, n_bases, cudaMemcpyHostToDevice));
         if ((rc = dev_alloc(&k0, n_pos)) || (rc = dev_alloc(&k1, n_pos)) || (rc = dev_alloc(&v0, n_pos)) || (rc = dev_alloc(&v1, n_pos)) ||
             (rc = dev_alloc(&d_nvalid, 1)) || (rc = dev_alloc(&d_tcount, n_tables))) break;
-        CUDA_TRY(cudaMemset(d_nvalid, 0, 8));
-        CUDA_TRY(cudaMemset(d_tcount, 0, (size_t)n_tables * 8));
+        IB_TRY(cudaMemset(d_nvalid, 0, 8));
+        IB_TRY(cudaMemset(d_tcount, 0, (size_t)n_tables * 8));
         const int T = 256;
         ib_emit_kernel<<<(n_pos + T - 1) / T, T>>>(d_genome, n_pos, seed_len, k0, v0, d_nvalid);
-        CUDA_TRY(cudaGetLastError());
+        IB_TRY(cudaGetLastError());
         size_t tmp_bytes = 0;
         const int end_bit = 2 * (int)seed_len + 1 > 63 ? 64 : 64;  // invalid keys (all ones) must sort last: use all bits
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, (unsigned long long)n_pos, 0, end_bit);
-        CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, (unsigned long long)n_pos, 0, end_bit));
+        IB_TRY(cudaMalloc(&tmp, tmp_bytes));
+        IB_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, (unsigned long long)n_pos, 0, end_bit));
         unsigned long long n_valid64 = 0;
-        CUDA_TRY(cudaMemcpy(&n_valid64, d_nvalid, 8, cudaMemcpyDeviceToHost));
+        IB_TRY(cudaMemcpy(&n_valid64, d_nvalid, 8, cudaMemcpyDeviceToHost));
         const uint32_t n_valid = (uint32_t)n_valid64;
         cudaFree(tmp); tmp = nullptr;
         cudaFree(k0); k0 = nullptr;
@@ -374,38 +380,38 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
             ib_heads_kernel<<<(n_valid + T - 1) / T, T>>>(k1, n_valid, head);
             tmp_bytes = 0;
             cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, head, rid, (unsigned long long)n_valid);
-            CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-            CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, rid, (unsigned long long)n_valid));
+            IB_TRY(cudaMalloc(&tmp, tmp_bytes));
+            IB_TRY(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, rid, (unsigned long long)n_valid));
             cudaFree(tmp); tmp = nullptr;
-            CUDA_TRY(cudaMemcpy(&n_runs, rid + (n_valid - 1), 4, cudaMemcpyDeviceToHost));
+            IB_TRY(cudaMemcpy(&n_runs, rid + (n_valid - 1), 4, cudaMemcpyDeviceToHost));
             // buffers are released as soon as they are dead: at 3.1 Gbp the peak stays near 120 GB of the 180 GB
             if ((rc = dev_alloc(&run_start, (size_t)n_runs + 1))) break;
             ib_run_start_kernel<<<(n_valid + T - 1) / T, T>>>(head, rid, n_valid, run_start);
-            CUDA_TRY(cudaMemcpy(run_start + n_runs, &n_valid, 4, cudaMemcpyHostToDevice));
+            IB_TRY(cudaMemcpy(run_start + n_runs, &n_valid, 4, cudaMemcpyHostToDevice));
             cudaFree(head); head = nullptr;
             if ((rc = dev_alloc(&need, (size_t)n_runs + 1)) || (rc = dev_alloc(&ovf_off, (size_t)n_runs + 1))) break;
-            CUDA_TRY(cudaMemset(d_nvalid, 0, 8));
+            IB_TRY(cudaMemset(d_nvalid, 0, 8));
             ib_run_need_kernel<<<(n_runs + T - 1) / T, T>>>(run_start, n_runs, need, d_nvalid);
-            CUDA_TRY(cudaMemset(need + n_runs, 0, 4));
+            IB_TRY(cudaMemset(need + n_runs, 0, 4));
             unsigned long long need_total = 0;  // 64-bit total first: the 32-bit prefix sum below must not wrap
-            CUDA_TRY(cudaMemcpy(&need_total, d_nvalid, 8, cudaMemcpyDeviceToHost));
+            IB_TRY(cudaMemcpy(&need_total, d_nvalid, 8, cudaMemcpyDeviceToHost));
             if ((uint64_t)n_bases + need_total > 0xfffffff0ull) { rc = set_error(SNAPB200_ERR_LIMIT, "too many overflow entries for this seed length (GenomeIndex.cpp:492-495)"); break; }
             tmp_bytes = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, need, ovf_off, (unsigned long long)n_runs + 1);
-            CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, need, ovf_off, (unsigned long long)n_runs + 1));
+            IB_TRY(cudaMalloc(&tmp, tmp_bytes));
+            IB_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, need, ovf_off, (unsigned long long)n_runs + 1));
             cudaFree(tmp); tmp = nullptr;
             cudaFree(need); need = nullptr;
-            CUDA_TRY(cudaMemcpy(&overflow_words, ovf_off + n_runs, 4, cudaMemcpyDeviceToHost));
+            IB_TRY(cudaMemcpy(&overflow_words, ovf_off + n_runs, 4, cudaMemcpyDeviceToHost));
             if ((rc = dev_alloc(&d_overflow, (size_t)overflow_words + 4))) break;
             ib_fill_overflow_kernel<<<(n_valid + T - 1) / T, T>>>(rid, run_start, ovf_off, v1, n_valid, d_overflow);
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaDeviceSynchronize());
+            IB_TRY(cudaGetLastError());
+            IB_TRY(cudaDeviceSynchronize());
             cudaFree(rid); rid = nullptr;
             ib_count_tables_kernel<<<(n_runs + T - 1) / T, T>>>(k1, run_start, n_runs, d_tcount);
-            CUDA_TRY(cudaGetLastError());
+            IB_TRY(cudaGetLastError());
         }
-        CUDA_TRY(cudaMemcpy(counts.data(), d_tcount, (size_t)n_tables * 8, cudaMemcpyDeviceToHost));
+        IB_TRY(cudaMemcpy(counts.data(), d_tcount, (size_t)n_tables * 8, cudaMemcpyDeviceToHost));
         uint64_t total = 0;
         for (uint32_t i = 0; i < n_tables; i++) {
             sizes[i] = std::max<uint64_t>(64, (uint64_t)((double)counts[i] * (1.0 + slack) * 1.1) + 16);
@@ -413,15 +419,16 @@ extern "C" int snapb200_index_build(int device, const uint8_t *bases, uint32_t n
             total += sizes[i];
         }
         if ((rc = dev_alloc(&d_tables, total)) || (rc = dev_alloc(&d_tstart, n_tables)) || (rc = dev_alloc(&d_tsize, n_tables))) break;
-        CUDA_TRY(cudaMemset(d_tables, 0xff, total * sizeof(HtEntry)));  // free entries: value1 == InvalidGenomeLocation
-        CUDA_TRY(cudaMemcpy(d_tstart, starts.data(), (size_t)n_tables * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(d_tsize, sizes.data(), (size_t)n_tables * 8, cudaMemcpyHostToDevice));
+        IB_TRY(cudaMemset(d_tables, 0xff, total * sizeof(HtEntry)));  // free entries: value1 == InvalidGenomeLocation
+        IB_TRY(cudaMemcpy(d_tstart, starts.data(), (size_t)n_tables * 8, cudaMemcpyHostToDevice));
+        IB_TRY(cudaMemcpy(d_tsize, sizes.data(), (size_t)n_tables * 8, cudaMemcpyHostToDevice));
         if (n_runs) {
             ib_insert_kernel<<<(n_runs + T - 1) / T, T>>>(k1, run_start, ovf_off, v1, n_runs, n_bases, d_tables, d_tstart, d_tsize);
-            CUDA_TRY(cudaGetLastError());
+            IB_TRY(cudaGetLastError());
         }
-        CUDA_TRY(cudaDeviceSynchronize());
+        IB_TRY(cudaDeviceSynchronize());
     } while (0);
+#undef IB_TRY
     if (!d_overflow && !rc) rc = dev_alloc(&d_overflow, 4);  // a genome without repeated seeds still gets a table to point at
     void *frees[] = {d_genome, k0, k1, d_nvalid, d_tcount, v0, v1, head, rid, run_start, need, ovf_off, tmp, d_tstart, d_tsize};
     for (void *p : frees) if (p) cudaFree(p);
@@ -509,6 +516,7 @@ struct snapb200_session {
     DevBuf s_pool, s_anchors, s_lists, s_epochs, s_hitc, s_hitl, s_hitr;
     DevBuf p_cands, p_mates, p_anchors, p_lane_tables, p_order;
     DevBuf w_keys[2], w_vals[2], w_tmp;  // work ordering of the paired path (weigh_kernel + radix sort)
+    DevBuf retry_tmp;                    // sorted retry list of the next scratch tier (kept: cudaMalloc / cudaFree synchronise the device)
     DevBuf f_scratch, f_work;            // per-warp scratch of filter_warp_kernel when it runs on this session's stream (rna batches)
     uint32_t anchors_tsize = 0;   // table size the anchor buffer was zeroed for
     uint32_t anchors_warps = 0;
@@ -538,14 +546,14 @@ extern "C" int snapb200_session_create(snapb200_index *idx, uint32_t max_items, 
     s->idx = idx;
     s->max_items = max_items;
     s->max_read_len = max_read_len;
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&s->ev0));
-    CUDA_TRY(cudaEventCreate(&s->ev1));
-    CUDA_TRY(cudaEventCreate(&s->evm0));
-    CUDA_TRY(cudaEventCreate(&s->evm1));
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&s->ev0)) != cudaSuccess ||
+        (e = cudaEventCreate(&s->ev1)) != cudaSuccess || (e = cudaEventCreate(&s->evm0)) != cudaSuccess || (e = cudaEventCreate(&s->evm1)) != cudaSuccess) {
+        snapb200_session_destroy(s);
+        return set_error(SNAPB200_ERR_CUDA, "session_create: %s", cudaGetErrorString(e));
+    }
     int rc;
-    if ((rc = s->counters.ensure(sizeof(Counters)))) return rc;
-    if ((rc = s->fix.ensure(sizeof(MapqFix) * FIX_CAP))) return rc;
+    if ((rc = s->counters.ensure(sizeof(Counters))) || (rc = s->fix.ensure(sizeof(MapqFix) * FIX_CAP))) { snapb200_session_destroy(s); return rc; }
     *out = s;
     return 0;
 }
@@ -559,7 +567,7 @@ extern "C" void snapb200_session_destroy(snapb200_session *s)
                      &s->paired_res, &s->fb_single_res, &s->retry_list, &s->fallback_list, &s->fb_positions, &s->fix, &s->counters,
                      &s->mh_counts, &s->mh_locs, &s->mh_rcs, &s->mh_scores, &s->s_pool, &s->s_anchors, &s->s_lists, &s->s_epochs,
                      &s->s_hitc, &s->s_hitl, &s->s_hitr, &s->p_cands, &s->p_mates, &s->p_anchors, &s->p_lane_tables, &s->p_order,
-                     &s->w_keys[0], &s->w_keys[1], &s->w_vals[0], &s->w_vals[1], &s->w_tmp, &s->f_scratch, &s->f_work};
+                     &s->w_keys[0], &s->w_keys[1], &s->w_vals[0], &s->w_vals[1], &s->w_tmp, &s->retry_tmp, &s->f_scratch, &s->f_work};
     for (DevBuf *b : all) b->release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -807,7 +815,7 @@ static int run_single_tiers(snapb200_session *s, const SingleCfg &cfg, uint32_t 
     const int n_tiers = single_tiers(s->idx, cfg, max_len, tiers);
     int rc;
     if ((rc = s->retry_list.ensure(((size_t)std::max(n_items, s->max_items) + 1) * 4))) return rc;
-    DevBuf tmp;
+    DevBuf &tmp = s->retry_tmp;
     const uint32_t *pos = positions;
     uint32_t n = n_items;
     for (int t = 0; t < n_tiers; t++) {
@@ -829,7 +837,6 @@ static int run_single_tiers(snapb200_session *s, const SingleCfg &cfg, uint32_t 
         pos = tmp.as<uint32_t>();
         n = c.n_retry;
     }
-    if (tmp.p) { cudaStreamSynchronize(s->stream); tmp.release(); }
     return rc;
 }
 
@@ -1018,7 +1025,7 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
             CUDA_TRY(cudaMemcpyAsync(list.data(), s->retry_list.p, (size_t)c.n_retry * 4, cudaMemcpyDeviceToHost, s->stream));
             CUDA_TRY(cudaStreamSynchronize(s->stream));
             std::sort(list.begin(), list.end());
-            DevBuf tmp;
+            DevBuf &tmp = s->retry_tmp;
             if ((rc = tmp.ensure((size_t)c.n_retry * 4))) return rc;
             CUDA_TRY(cudaMemcpyAsync(tmp.p, list.data(), (size_t)c.n_retry * 4, cudaMemcpyHostToDevice, s->stream));
             CUDA_TRY(cudaMemsetAsync((char *)s->counters.p + offsetof(Counters, n_retry), 0, 4, s->stream));
@@ -1030,7 +1037,6 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
             int g = (int)std::min<size_t>((size_t)grid, std::max<size_t>(1, warps / WARPS_PER_CTA));
             rc = launch_paired(s, p, big, g, tmp.as<uint32_t>(), c.n_retry);
             if (!rc) rc = read_counters(s, &c);
-            tmp.release();
             if (rc) return rc;
         }
         // single-end fallback for the pairs the intersecting aligner could not place

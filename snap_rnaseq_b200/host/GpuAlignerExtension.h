@@ -54,6 +54,36 @@ public:
     static unsigned maxBigHits(PairedAlignerContext *c) { return c->intersectingAlignerMaxHits; }
     static unsigned maxCandidatePoolSize(PairedAlignerContext *c) { return c->maxCandidatePoolSize; }
     static bool ignoreMismatchedIDs(PairedAlignerContext *c) { return c->ignoreMismatchedIDs; }
+
+    // ReadIntervalMap::AddInterval (SNAPLib/GTFReader.cpp:287-305) for many intervals: the two ReadInterval objects of every
+    // candidate are built by the calling thread, outside any lock; the map's lock is taken once to append them all, in order.
+    // (Needs the friend declarations of INTEGRATION.md section 3 in ReadInterval, ReadIntervalMap and GTFReader.)
+    struct SpliceBatch {
+        std::vector<ReadInterval *> mates[2];  // [0] intrachromosomal, [1] interchromosomal; consecutive entries are a pair
+        void add(bool intra, const std::string &chr0, unsigned start0, unsigned end0, const std::string &chr1, unsigned start1, unsigned end1,
+                 const std::string &id)
+        {
+            ReadInterval *m0 = new ReadInterval(chr0, start0, end0, id, true);
+            ReadInterval *m1 = new ReadInterval(chr1, start1, end1, id, true);
+            m0->mate.insert(m1);
+            m1->mate.insert(m0);
+            std::vector<ReadInterval *> &v = mates[intra ? 0 : 1];
+            v.push_back(m0); v.push_back(m1);
+        }
+        void flush(GTFReader *gtf)
+        {
+            for (int k = 0; k < 2; k++) {
+                if (mates[k].empty()) continue;
+                ReadIntervalMap &m = k == 0 ? gtf->intrachromosomal_splices : gtf->interchromosomal_splices;
+                AcquireExclusiveLock(&m.mutex);
+                m.read_intervals.reserve(m.read_intervals.size() + mates[k].size());
+                for (size_t q = 0; q < mates[k].size(); q++)
+                    m.read_intervals.push_back(Interval<ReadInterval *>(mates[k][q]->start, mates[k][q]->end, mates[k][q]));
+                ReleaseExclusiveLock(&m.mutex);
+                mates[k].clear();
+            }
+        }
+    };
 };
 
 // BaseAligner::CharacterizeSeeds served from the device.  AlignmentFilter holds a
@@ -142,6 +172,24 @@ public:
         GpuAlignerExtension *c = new GpuAlignerExtension(batch_);
         c->owner_ = false;
         return c;
+    }
+
+    // Starts placing the indices (and, for `paired`, the annotation tables) in HBM on a background thread, so that it overlaps the
+    // reference's own loading of its host-side indices and GTF (AlignerContext::initialize).  argv: what follows the sub-command --
+    // <genome-idx> <transcriptome-idx> <gtf> ... [-ct <contamination-idx>] (SingleAligner.cpp:52-72, PairedAligner.cpp:290-310).
+    // Optional: without it the first worker thread opens the handles.
+    static void prefetch(int argc, const char **argv, bool paired)
+    {
+        processStart();
+        if (argc < 3 || strcmp(argv[0], "-") == 0) return;
+        Prefetch *p = new Prefetch();
+        p->index = argv[0]; p->transcriptome = argv[1]; p->annotation = argv[2]; p->paired = paired;
+        for (int i = 3; i + 1 < argc; i++) {
+            if (strcmp(argv[i], ",") == 0) break;
+            if (strcmp(argv[i], "-ct") == 0) { p->contamination = argv[i + 1]; p->haveContamination = true; }
+        }
+        pthread_t th;
+        if (pthread_create(&th, NULL, prefetchMain, p) == 0) pthread_detach(th); else delete p;
     }
 
     // ---- single end: replaces the loop at SNAPLib/SingleAligner.cpp:243-304 ----
@@ -269,14 +317,24 @@ public:
         for (int k = 0; k < 2; k++) pb[k].destroy();
         tm.report();
         if (getenv("SNAPB200_SHIM_TIMING") != NULL)
-            fprintf(stderr, "[snapb200 shim]   thread wall: opening the device handles (or waiting for the thread that does) %.2f s, batch loop %.2f s, "
-                            "releasing the batch objects %.2f s\n", tInit, tLoop, now() - td);
+            fprintf(stderr, "[snapb200 shim]   thread wall: entered at %.2f s after process start, opening the device handles (or waiting for the thread that "
+                            "does) %.2f s, batch loop %.2f s, releasing the batch objects %.2f s, left at %.2f s\n", tEnter - processStart(), tInit, tLoop,
+                    now() - td, now() - processStart());
         ctx->stats->lvCalls = threadLeaves(devs);
         delete partial;
         return true;
     }
 
 private:
+    struct Prefetch { std::string index, transcriptome, annotation, contamination; bool haveContamination, paired; Prefetch() : haveContamination(false), paired(false) {} };
+    static void *prefetchMain(void *arg)
+    {
+        Prefetch *p = (Prefetch *)arg;
+        deviceSets(p->index.c_str(), p->transcriptome.c_str(), p->haveContamination ? p->contamination.c_str() : NULL, p->annotation.c_str(), p->paired);
+        delete p;
+        return NULL;
+    }
+
     // Owns copies of reads (id, unclipped bases, qualities) so they outlive the supplier's buffers, and exposes the clipped reads
     // of the pairs that go to the device as a snapb200_read_batch.
     struct ReadStore {
@@ -343,16 +401,22 @@ private:
         snapb200_index *genome, *transcriptome, *contamination;
         snapb200_annotation *annotation;
         std::vector<std::string> transcriptIds;  // behind snapb200_filter_event::transcript
+        std::vector<std::string> chrNames;       // genome piece names, behind the chr indices of events and splice records
     };
 
     static const std::vector<DeviceSet> &deviceSets(const AlignerOptions *options, bool needAnnotation)
+    {
+        return deviceSets(options->indexDir, options->transcriptomeDir, options->contaminationDir, options->annotation, needAnnotation);
+    }
+
+    static const std::vector<DeviceSet> &deviceSets(const char *indexDir, const char *transcriptomeDir, const char *contaminationDir, const char *annotation,
+                                                    bool needAnnotation)
     {
         static pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
         static std::vector<DeviceSet> sets;
         static std::string key;
         pthread_mutex_lock(&lock);
-        std::string k = std::string(options->indexDir) + "\n" + options->transcriptomeDir + "\n" + (options->contaminationDir ? options->contaminationDir : "") +
-                        "\n" + options->annotation;
+        std::string k = std::string(indexDir) + "\n" + transcriptomeDir + "\n" + (contaminationDir ? contaminationDir : "") + "\n" + annotation;
         if (sets.empty() || k != key) {
             // (a process that chains runs over different indices keeps the earlier handles resident, as the reference keeps its globals)
             sets.clear();
@@ -362,18 +426,25 @@ private:
             for (int d = 0; d < n; d++) {
                 DeviceSet s;
                 s.device = d; s.contamination = NULL; s.annotation = NULL;
-                check(snapb200_index_open(options->indexDir, d, &s.genome));
-                check(snapb200_index_open(options->transcriptomeDir, d, &s.transcriptome));
-                if (options->contaminationDir != NULL) check(snapb200_index_open(options->contaminationDir, d, &s.contamination));
+                const double t0 = now();
+                check(snapb200_index_open(indexDir, d, &s.genome));
+                const double t1 = now();
+                check(snapb200_index_open(transcriptomeDir, d, &s.transcriptome));
+                if (contaminationDir != NULL) check(snapb200_index_open(contaminationDir, d, &s.contamination));
+                if (getenv("SNAPB200_SHIM_TIMING") != NULL)
+                    fprintf(stderr, "[snapb200 shim] device %d: genome index in HBM after %.2f s (CUDA context creation included), the other indices %.2f s; "
+                                    "started %.2f s after process start\n", d, t1 - t0, now() - t1, t0 - processStart());
                 sets.push_back(s);
             }
             key = k;
         }
         if (needAnnotation && sets[0].annotation == NULL)
             for (size_t d = 0; d < sets.size(); d++) {
-                check(snapb200_annotation_open(sets[d].genome, sets[d].transcriptome, options->annotation, &sets[d].annotation));
+                check(snapb200_annotation_open(sets[d].genome, sets[d].transcriptome, annotation, &sets[d].annotation));
                 const uint32_t nt = snapb200_annotation_transcript_count(sets[d].annotation);
                 for (uint32_t t = 0; t < nt; t++) sets[d].transcriptIds.push_back(snapb200_annotation_transcript_id(sets[d].annotation, t));
+                for (uint32_t c = 0; snapb200_annotation_chromosome(sets[d].annotation, c) != NULL; c++)
+                    sets[d].chrNames.push_back(snapb200_annotation_chromosome(sets[d].annotation, c));
             }
         pthread_mutex_unlock(&lock);
         return sets;
@@ -480,6 +551,8 @@ private:
         const Genome *genome = ctx->index->getGenome();
         std::vector<PairedAlignmentResult> results(b.n);
         std::vector<unsigned> contam;
+        AlignerContext2::SpliceBatch splices;
+        const std::vector<std::string> &chrName = dev.chrNames;
         // pass 1: the pair's result and its GTF counters, in input order
         for (unsigned i = 0; i < b.n; i++) {
             PairedAlignmentResult &result = results[i];
@@ -517,29 +590,38 @@ private:
                 result.nanosInAlignTogether = 0; result.nLVCalls = v.genome_pairs[di].n_lv_calls; result.nSmallHits = 0;
                 if (ev.unaligned) {  // AlignmentFilter.cpp:331-340: the novel-splice search of the read that has no alignment at all
                     const double tu = fine ? now() : 0;
-                    partial->select((unsigned)di, &r0, &r1);
-                    FilterAccess fa(&r0, &r1, genome, ctx->transcriptome->getGenome(), ctx->gtf, pp.min_spacing, pp.max_spacing, ctx->options->confDiff,
-                                    ctx->options->maxDist.start, seedLen, partial);
-                    fa.unaligned(ev.unaligned == 1 ? &r0 : &r1, seedLen);
+                    Read *ur = ev.unaligned == 1 ? &r0 : &r1;
+                    if (v.splice_overflow[di]) {  // more partial alignments than the device scratch holds: the reference's own search
+                        partial->select((unsigned)di, &r0, &r1);
+                        FilterAccess fa(&r0, &r1, genome, ctx->transcriptome->getGenome(), ctx->gtf, pp.min_spacing, pp.max_spacing, ctx->options->confDiff,
+                                        ctx->options->maxDist.start, seedLen, partial);
+                        fa.unaligned(ur, seedLen);
+                    } else if (v.splice_offsets[di + 1] > v.splice_offsets[di]) {
+                        const std::string id(ur->getId(), ur->getIdLength());
+                        for (uint64_t q = v.splice_offsets[di]; q < v.splice_offsets[di + 1]; q++) {
+                            const snapb200_splice &sp = v.splices[q];
+                            splices.add(sp.kind == 2, chrName[sp.chr[0]], sp.pos[0], sp.pos_end[0], chrName[sp.chr[1]], sp.pos[1], sp.pos_end[1], id);
+                        }
+                    }
                     if (fine) tm.unaligned += now() - tu;
                 }
                 if (ev.kind) {
                     const double tg = fine ? now() : 0;
-                    const Genome::Piece *pieces = genome->getPieces();
                     if (ev.kind == 1) {  // AlignmentFilter.cpp:536-541 (the lengths are passed crossed there)
                         ctx->gtf->IncrementReadCount(ev.transcript[0] >= 0 ? dev.transcriptIds[ev.transcript[0]] : std::string(), ev.pos_original[0], ev.pos[0],
                                                      r1.getDataLength(), ev.transcript[1] >= 0 ? dev.transcriptIds[ev.transcript[1]] : std::string(),
                                                      ev.pos_original[1], ev.pos[1], r0.getDataLength());
                     } else {
                         const std::string id(r0.getId(), r0.getIdLength());
-                        if (ev.kind == 2) ctx->gtf->IntrachromosomalPair(pieces[ev.chr[0]].name, ev.pos[0], ev.pos_end[0], pieces[ev.chr[1]].name, ev.pos[1], ev.pos_end[1], id);
-                        else ctx->gtf->InterchromosomalPair(pieces[ev.chr[0]].name, ev.pos[0], ev.pos_end[0], pieces[ev.chr[1]].name, ev.pos[1], ev.pos_end[1], id);
+                        if (ev.kind == 2) ctx->gtf->IntrachromosomalPair(chrName[ev.chr[0]], ev.pos[0], ev.pos_end[0], chrName[ev.chr[1]], ev.pos[1], ev.pos_end[1], id);
+                        else ctx->gtf->InterchromosomalPair(chrName[ev.chr[0]], ev.pos[0], ev.pos_end[0], chrName[ev.chr[1]], ev.pos[1], ev.pos_end[1], id);
                     }
                     if (fine) tm.gtf += now() - tg;
                 }
             }
             if (result.status[0] == NotFound && result.status[1] == NotFound && dev.contamination != NULL) contam.push_back(i);
         }
+        splices.flush(ctx->gtf);
         if (!contam.empty()) {  // PairedAligner.cpp:633-646, one device call for all unaligned pairs of the batch
             ReadStore c0, c1;
             for (size_t q = 0; q < contam.size(); q++) { c0.addFrom(b.s0, contam[q]); c1.addFrom(b.s1, contam[q]); }
@@ -599,6 +681,8 @@ private:
         p.explore_popular_seeds = ctx->options->explorePopularSeeds; p.stop_on_first_hit = ctx->options->stopOnFirstHit; p.max_hits_to_get = 0;
         return p;
     }
+
+    static double processStart() { static const double t = now(); return t; }
 
     static double now()
     {

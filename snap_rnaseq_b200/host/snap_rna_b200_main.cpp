@@ -28,6 +28,8 @@ int main(int argc, const char **argv)
     } else {
         for (int i = 1; i < argc;) {
             unsigned nArgsConsumed = 0;
+            if (strcmp(argv[i], "single") == 0 || strcmp(argv[i], "paired") == 0)  // optional: HBM loading overlaps the host-side loading
+                GpuAlignerExtension::prefetch(argc - (i + 1), argv + i + 1, strcmp(argv[i], "paired") == 0);
             if (strcmp(argv[i], "single") == 0) {
                 SingleAlignerContext single(new GpuAlignerExtension());
                 single.runAlignment(argc - (i + 1), argv + i + 1, version, &nArgsConsumed);

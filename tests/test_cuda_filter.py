@@ -36,8 +36,9 @@ def assert_same_records(want, got, what):
     assert not bad, (what, len(bad), bad[:10], [(want[i], got[i]) for i in bad[:3]])
 
 
-def replay_and_compare(ref, cuda, w, sam_reads, events, want_prefix, tag):
-    """The event records through the reference's own public GTFReader methods on a fresh GTFReader: same statistics files."""
+def replay_and_compare(ref, cuda, w, sam_reads, events, want_prefix, tag, splices=None):
+    """The event records through the reference's own public GTFReader methods on a fresh GTFReader: same statistics files.
+    splices = (offsets, records): the novel-splice records replace the UnalignedRead calls."""
     lib = ref.lib
     lib.ref_gtf_load.restype = C.c_void_p
     d = w["d"]
@@ -46,8 +47,13 @@ def replay_and_compare(ref, cuda, w, sam_reads, events, want_prefix, tag):
     assert chr_names == genome_pieces(w["gdir"])[0]
     arr = lambda names: (C.c_char_p * len(names))(*[x.encode() for x in names])
     evc = np.ascontiguousarray(events)
-    assert lib.ref_filter_replay_events(w["rg"], w["rt"], g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(evc.ctypes.data), arr(t_ids),
-                                        arr(chr_names)) == 0
+    if splices is None:
+        assert lib.ref_filter_replay_events(w["rg"], w["rt"], g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(evc.ctypes.data), arr(t_ids),
+                                            arr(chr_names)) == 0
+    else:
+        off, recs = np.ascontiguousarray(splices[0], np.uint64), np.ascontiguousarray(splices[1])
+        assert lib.ref_filter_replay_events2(w["rg"], w["rt"], g2, sam_reads[0].byref(), sam_reads[1].byref(), C.c_uint(15), C.c_void_p(evc.ctypes.data), arr(t_ids),
+                                             arr(chr_names), off.ctypes.data_as(C.c_void_p), C.c_void_p(recs.ctypes.data)) == 0
     lib.ref_gtf_finish(g2)
     produced = sorted(x for x in os.listdir(d) if x.startswith(tag))
     assert len(produced) >= 8
@@ -144,6 +150,10 @@ def test_rna_batch_is_the_pair_loop_of_the_reference(ref, cuda, ws):
         want = F.run_reference_filter(ref, w["rg"], w["rt"], w["gtf"], os.path.join(w["d"], f"want_r{k}"), sam_reads, hits, genome_res, P.paired)
         assert_same_records(want, o["results"], f"rna batch {k} vs reference")
         replay_and_compare(ref, cuda, w, sam_reads, o["events"], f"want_r{k}", f"replay_r{k}")
+        # the novel-splice records of the flagged reads instead of UnalignedRead on the host: same files
+        assert not o["splice_overflow"].any() and len(o["splices"]) > 0 and (o["events"]["unaligned"] > 0).sum() > 20
+        assert np.all(np.diff(o["splice_offsets"].astype(np.int64))[o["events"]["unaligned"] == 0] == 0)
+        replay_and_compare(ref, cuda, w, sam_reads, o["events"], f"want_r{k}", f"replay_s{k}", splices=(o["splice_offsets"], o["splices"]))
     # an empty batch is legal
     cuda.rna_batch_submit(objs[1], P, cases[0][0].slice(0, 0), cases[0][1].slice(0, 0))
     assert cuda.rna_batch_wait(objs[1])["n"] == 0

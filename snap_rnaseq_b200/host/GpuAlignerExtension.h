@@ -76,7 +76,6 @@ public:
                 if (mates[k].empty()) continue;
                 ReadIntervalMap &m = k == 0 ? gtf->intrachromosomal_splices : gtf->interchromosomal_splices;
                 AcquireExclusiveLock(&m.mutex);
-                m.read_intervals.reserve(m.read_intervals.size() + mates[k].size());
                 for (size_t q = 0; q < mates[k].size(); q++)
                     m.read_intervals.push_back(Interval<ReadInterval *>(mates[k][q]->start, mates[k][q]->end, mates[k][q]));
                 ReleaseExclusiveLock(&m.mutex);
@@ -162,7 +161,10 @@ class GpuAlignerExtension : public AlignerExtension {
 public:
     // batchReads: pairs (or reads) per device batch.  Devices: every visible GPU (SNAPB200_DEVICES=n limits it); batches are dealt
     // round-robin over them from this one process (GTF counters are process-global, so one process drives all).
-    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true) {}
+    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true)
+    {
+        if (const char *e = getenv("SNAPB200_SHIM_BATCH")) { int v = atoi(e); if (v >= 16) batch_ = (unsigned)v; }  // tests: many small batches
+    }
 
     virtual ~GpuAlignerExtension() {}  // indices stay resident for the life of the process (see deviceSet())
 
@@ -484,6 +486,7 @@ private:
     struct Timing {
         double drain, wait, replay, filterHost, unaligned, gtf, write, deviceMs;
         unsigned long reads, batches, hostPairs;
+        std::vector<unsigned long> perDevice;  // batches each device took
         Timing() : drain(0), wait(0), replay(0), filterHost(0), unaligned(0), gtf(0), write(0), deviceMs(0), reads(0), batches(0), hostPairs(0) {}
         void report() const
         {
@@ -491,6 +494,9 @@ private:
             fprintf(stderr, "[snapb200 shim] paired thread: %lu reads in %lu batches, drain %.2f s, waiting for the device %.2f s (device busy %.2f s), "
                             "host replay %.2f s (UnalignedRead %.2f, GTF counters %.2f, writePair+stats %.2f, reference filter for %lu overflow pairs %.2f)\n",
                     reads, batches, drain, wait, deviceMs * 1e-3, replay, unaligned, gtf, write, hostPairs, filterHost);
+            fprintf(stderr, "[snapb200 shim]   batches per device:");
+            for (size_t d = 0; d < perDevice.size(); d++) fprintf(stderr, " gpu%zu=%lu", d, perDevice[d]);
+            fprintf(stderr, "\n");
         }
     };
 
@@ -544,6 +550,8 @@ private:
         tm.wait += now() - t0;
         tm.deviceMs += v.device_ms;
         tm.batches++;
+        if (tm.perDevice.size() <= (size_t)b.dev) tm.perDevice.resize(b.dev + 1, 0);
+        tm.perDevice[b.dev]++;
         t0 = now();
         const bool fine = getenv("SNAPB200_SHIM_TIMING") != NULL;
         for (int e = 0; e < 2; e++) partial->borrow(e, v.seg_offsets[e], v.ch_locations[e], v.ch_seed_offsets[e]);

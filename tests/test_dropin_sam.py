@@ -138,3 +138,26 @@ def test_rna_mode_with_contamination_filter_sam_and_statistics_identical(workspa
     ref_out = run([REF, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "ref_z.sam", "-t", "1"], d)
     gpu_out = run([B200, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "gpu_z.sam", "-t", "1"], d)
     assert stats_line(ref_out) == stats_line(gpu_out), (stats_line(ref_out), stats_line(gpu_out))
+
+
+def test_rna_mode_batches_dealt_over_all_gpus(workspace):
+    """one process, batches dealt round-robin over the GPUs of the box (g = batch % nGPU), the GTF counters
+    staying in that one process.  With small batches (SNAPB200_SHIM_BATCH) every device gets several; SAM records and statistics
+    files must not depend on how many devices took part.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a single-GPU box."""
+    import snap_rnaseq_b200 as S
+    if S.lib().device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    d = workspace
+    env = dict(os.environ, SNAPB200_SHIM_BATCH="512", SNAPB200_SHIM_TIMING="1")
+    run([REF, "paired", "gidx", "tidx", "a.gtf", "y1.fq", "y2.fq", "-o", "ref_m.sam", "-t", "1", "-ct", "cidx"], d)
+    for tag, ndev in (("gpu_m1", "1"), ("gpu_m2", "2")):
+        e = dict(env, SNAPB200_DEVICES=ndev)
+        r = subprocess.run([B200, "paired", "gidx", "tidx", "a.gtf", "y1.fq", "y2.fq", "-o", tag + ".sam", "-t", "1", "-ct", "cidx"], cwd=d, env=e,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        per_dev = [l for l in r.stdout.split("\n") if "batches per device:" in l]
+        counts = [int(x.split("=")[1]) for x in per_dev[-1].split(":")[1].split()]
+        assert len(counts) == int(ndev) and min(counts) >= 3, (ndev, per_dev)  # every device really took batches
+        assert_same(sam_records(os.path.join(d, "ref_m.sam")), sam_records(os.path.join(d, tag + ".sam")), 2 * (4000 + 600))
+        for f in SIDE_FILES + ("contaminants.txt",):
+            assert open(os.path.join(d, "ref_m." + f), "rb").read() == open(os.path.join(d, tag + "." + f), "rb").read(), (tag, f)

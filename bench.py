@@ -317,10 +317,25 @@ def run_ours(args):
                 line["io_edges"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(L, h, b0, b1, params, out)
+        if world == 1 and not args.no_dropin:
+            # The reference's own command line with and without the extension (BASELINE.json configs[3], RNA mode): what a user of
+            # `snap-rna paired` sees.  Runs after this process has released the GPU-resident index.
+            for s_ in sessions:
+                s_.close()
+            sessions.clear()
+            L.close_index(h)
+            h = None
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                from dropin_bench import run_dropin
+                line["dropin"], _ = run_dropin(pairs=args.dropin_pairs, mbp=40, reps=2)
+            except Exception as e:  # diagnostics: the headline numbers above stand without it
+                line["dropin"] = {"error": str(e)[-500:]}
         emit(line)
     for s_ in sessions:
         s_.close()
-    L.close_index(h)
+    if h is not None:
+        L.close_index(h)
     if world > 1:
         dist.destroy_process_group()
 
@@ -572,6 +587,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the `dropin` key (the reference's command line with / without the extension)")
+    ap.add_argument("--dropin-pairs", type=int, default=300_000)
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "custom"],
                     help="c3 (default) = BASELINE.json configs[2]: 3.1 Gbp genome, 2x150 bp, 1 %% error; c2 = configs[1]: 100 Mbp, 2x100 bp, 2 %%")
     ap.add_argument("--genome-mbp", type=int, default=None, help="with --config custom: synthetic genome size (contigs of 25 Mbp)")

@@ -438,6 +438,11 @@ int snapb200_gather_bench(int device, uint64_t bytes, uint32_t n, uint32_t iters
 /* computeMAPQ (SNAPLib/mapq.h:32-65), evaluated on the device the way the aligner kernels do. */
 int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, const double *p_best,
                         const int32_t *score, const int32_t *popular_seeds_skipped, int32_t *mapq);
+/* Same; host_reevaluated[i] != 0 where the device's -10*log10(1 - pBest/pAll) landed within 1e-9 of an integer and the library
+ * re-evaluated computeMAPQ with the host's libm, as the aligner entry points do (the value the reference truncates, mapq.h:51, is
+ * last-ulp sensitive exactly there).  For tests that force this path. */
+int snapb200_mapq_batch_ex(int device, uint32_t n, const double *p_all, const double *p_best, const int32_t *score,
+                           const int32_t *popular_seeds_skipped, int32_t *mapq, uint8_t *host_reevaluated);
 
 /* ---- device-resident sessions (what bench.py times; also what a pipelined host uses) ---------------- */
 
@@ -478,6 +483,9 @@ typedef struct {
  * the multi-GPU host can sum it with one all-reduce (NCCL), as AlignerStats::add does per thread
  * (SNAPLib/AlignerStats.cpp:75-102). */
 int snapb200_stats_get(snapb200_index *idx, snapb200_stats *out);
+/* The sum over the per-GPU copies of one index (one host process drives all GPUs of a box): what
+ * AlignerStats::add does over the reference's per-thread objects. */
+int snapb200_stats_sum(snapb200_index *const *indices, uint32_t n, snapb200_stats *out);
 int snapb200_stats_reset(snapb200_index *idx);
 
 const char *snapb200_last_error(void);

@@ -42,6 +42,7 @@
 #include "DataWriter.h"
 #include "AlignmentFilter.h"
 #include "GTFReader.h"
+#include "ProbabilityDistance.h"
 #undef private
 #undef protected
 
@@ -185,6 +186,16 @@ int ref_mapq_batch(unsigned n, const double *p_all, const double *p_best, const 
 {
     for (unsigned i = 0; i < n; i++) mapq[i] = computeMAPQ(p_all[i], p_best[i], score[i], popular[i]);
     return 0;
+}
+
+// ProbabilityDistance::compute (SNAPLib/ProbabilityDistance.cpp:53-135); the object is 1.2 MB, hence the heap
+int ref_probability_distance(double snp_prob, double gap_open_prob, double gap_extension_prob, const char *reference, const char *read,
+                             const char *quality, int read_len, int max_start_shift, int max_shift, double *match_probability)
+{
+    ProbabilityDistance *pd = new ProbabilityDistance(snp_prob, gap_open_prob, gap_extension_prob);
+    int rc = pd->compute(reference, read, quality, read_len, max_start_shift, max_shift, match_probability);
+    delete pd;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

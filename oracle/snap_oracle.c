@@ -1659,3 +1659,54 @@ int oracle_cigar_batch(void *h, const snapb200_read_batch *reads, const uint32_t
     }
     return 0;
 }
+
+/* ProbabilityDistance::compute (SNAPLib/ProbabilityDistance.cpp:53-135) with the constructor's tables (:18-50).  The class is
+ * constructed by every BaseAligner (BaseAligner.cpp:98) but `compute` is called by no aligner -- the match probability that feeds
+ * MAPQ comes from LandauVishkin -- so there is no device counterpart; this restatement exists so that the reference's 16 KATs
+ * (tests/ProbabilityDistanceTest.cpp:15-70) pin it and the 1e-6 agreement north_star asks for is checked against the compiled
+ * reference (tests/test_oracle.py).  reference / read / quality as there; `reference` must be readable from -max_shift to
+ * read_len + max_shift (the reference's own tests read outside their literals).  Three-state log-probability DP over
+ * (read position, shift): NO_GAP / READ_GAP / REF_GAP. */
+#define PD_MAX_SHIFT 20
+#define PD_NO_PROB (-1000000.0)
+static double pd_max3(double a, double b, double c) { double m = a > b ? a : b; return m > c ? m : c; }
+
+int oracle_probability_distance(double snp_prob, double gap_open_prob, double gap_extension_prob, const char *reference, const char *read,
+                                const char *quality, int read_len, int max_start_shift, int max_shift, double *match_probability)
+{
+    if (read_len < 0 || read_len > SNAPB200_MAX_READ_LENGTH || max_shift >= PD_MAX_SHIFT || max_start_shift > max_shift) return -1;
+    const double gap_open = log(gap_open_prob), gap_ext = log(gap_extension_prob);
+    double match_lp[256], mismatch_lp[256];
+    for (int q = 0; q < 256; q++) {
+        if (q < 33) { match_lp[q] = PD_NO_PROB; mismatch_lp[q] = PD_NO_PROB; continue; }
+        const double error_prob = pow(10.0, -(q - 33) / 10.0);
+        const double match_prob = (1.0 - error_prob) * (1.0 - snp_prob);
+        match_lp[q] = log(match_prob);
+        mismatch_lp[q] = log(1.0 - match_prob);
+    }
+    const int W = 2 * PD_MAX_SHIFT + 1;
+    double (*d)[3] = (double (*)[3])malloc(sizeof(double) * 3 * W * (size_t)(read_len + 1));
+    if (!d) return -1;
+#define PD(r, s, g) d[(size_t)(r) * W + PD_MAX_SHIFT + (s)][g]
+    for (int s = -max_shift - 1; s <= max_shift + 1; s++) {
+        PD(0, s, 1) = PD_NO_PROB;
+        PD(0, s, 2) = PD_NO_PROB;
+        PD(0, s, 0) = (s < -max_start_shift || s > max_start_shift) ? PD_NO_PROB : log(1.0);
+    }
+    for (int r = 1; r <= read_len; r++) {
+        for (int g = 0; g < 3; g++) { PD(r, -max_shift - 1, g) = PD_NO_PROB; PD(r, max_shift + 1, g) = PD_NO_PROB; }
+        for (int s = -max_shift; s <= max_shift; s++) {
+            const double base = (read[r - 1] == reference[r - 1 + s]) ? match_lp[(unsigned char)quality[r - 1]] : mismatch_lp[(unsigned char)quality[r - 1]];
+            PD(r, s, 0) = pd_max3(PD(r - 1, s, 0) + base, PD(r - 1, s, 2) + base, PD(r - 1, s, 1) + base);
+            PD(r, s, 1) = pd_max3(PD(r - 1, s + 1, 0) + gap_open, PD(r - 1, s + 1, 2) + gap_open, PD(r - 1, s + 1, 1) + gap_ext);
+            PD(r, s, 2) = pd_max3(PD(r, s - 1, 0) + gap_open, PD(r, s - 1, 2) + gap_ext, PD(r, s - 1, 1) + gap_open);
+        }
+    }
+    double best = PD_NO_PROB;
+    for (int s = -max_shift; s <= max_shift; s++)
+        for (int g = 0; g < 3; g++) if (PD(read_len, s, g) > best) best = PD(read_len, s, g);
+#undef PD
+    free(d);
+    *match_probability = exp(best);
+    return 5;  /* "a somewhat arbitrary score" (:133) */
+}

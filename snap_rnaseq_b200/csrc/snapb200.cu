@@ -1548,6 +1548,12 @@ extern "C" int snapb200_lookup_seed_batch(snapb200_index *idx, uint32_t n, const
 extern "C" int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, const double *p_best, const int32_t *score,
                                    const int32_t *popular_seeds_skipped, int32_t *mapq)
 {
+    return snapb200_mapq_batch_ex(device, n, p_all, p_best, score, popular_seeds_skipped, mapq, nullptr);
+}
+
+extern "C" int snapb200_mapq_batch_ex(int device, uint32_t n, const double *p_all, const double *p_best, const int32_t *score,
+                                      const int32_t *popular_seeds_skipped, int32_t *mapq, uint8_t *host_reevaluated)
+{
     snapb200_index *x;
     int rc = tables_for(device, &x);
     if (rc) return rc;
@@ -1568,6 +1574,7 @@ extern "C" int snapb200_mapq_batch(int device, uint32_t n, const double *p_all, 
         cudaError_t e = cudaStreamSynchronize(x->stream);
         if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "mapq_kernel: %s", cudaGetErrorString(e)); break; }
         for (uint32_t i = 0; i < n; i++) if (flags[i]) mapq[i] = compute_mapq_host(p_all[i], p_best[i], score[i], popular_seeds_skipped[i]);
+        if (host_reevaluated) memcpy(host_reevaluated, flags.data(), n);
     } while (0);
     DevBuf *all[] = {&a, &b, &c, &d, &o, &f};
     for (DevBuf *q : all) q->release();
@@ -1658,6 +1665,24 @@ extern "C" int snapb200_stats_get(snapb200_index *idx, snapb200_stats *out)
     for (int i = 0; i < SNAPB200_STATS_WORDS; i++) o[i] = (int64_t)w[i];
     out->useful_reads = out->total_reads - out->n_reads_ignored_ns;
     out->lv_calls = out->n_locations_scored;
+    return 0;
+}
+
+// AlignerStats::add over the per-GPU copies of an index (SNAPLib/AlignerStats.cpp:75-102 sums the per-thread objects): one host
+// process drives all GPUs of the box, so the reduction is a host sum; processes on several boxes reduce this flat int64 vector with
+// one all-reduce (bench.py does, over NCCL).
+extern "C" int snapb200_stats_sum(snapb200_index *const *indices, uint32_t n, snapb200_stats *out)
+{
+    if (!out || (n && !indices)) return set_error(SNAPB200_ERR_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    int64_t *o = (int64_t *)out;
+    for (uint32_t i = 0; i < n; i++) {
+        snapb200_stats one;
+        int rc = snapb200_stats_get(indices[i], &one);
+        if (rc) return rc;
+        const int64_t *w = (const int64_t *)&one;
+        for (int k = 0; k < SNAPB200_STATS_WORDS; k++) o[k] += w[k];
+    }
     return 0;
 }
 

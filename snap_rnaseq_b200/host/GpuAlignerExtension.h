@@ -471,11 +471,10 @@ private:
         pthread_mutex_lock(&lock);
         long long mine = 0;
         if (__sync_sub_and_fetch(&activeThreads(), 1) == 0) {
-            long long total = 0;
-            for (size_t d = 0; d < devs.size(); d++) {
-                snapb200_stats st;
-                if (snapb200_stats_get(devs[d].genome, &st) == SNAPB200_OK) total += st.n_locations_scored;
-            }
+            std::vector<snapb200_index *> copies;
+            for (size_t d = 0; d < devs.size(); d++) copies.push_back(devs[d].genome);
+            snapb200_stats st;
+            const long long total = snapb200_stats_sum(&copies[0], (uint32_t)copies.size(), &st) == SNAPB200_OK ? st.n_locations_scored : 0;
             mine = total - reportedLv();
             reportedLv() = total;
         }

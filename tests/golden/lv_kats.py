@@ -30,3 +30,25 @@ CIGAR_KATS = [
     ("abc", "abcde", 3, False, "3=2X"), ("abc", "abcde", 3, True, "5M"),
     ("abc", "abXde", 3, False, "2=3X"), ("abc", "abXde", 3, True, "5M"),
 ]
+
+# ProbabilityDistance KATs, tests/ProbabilityDistanceTest.cpp:15-70 of the reference (fixture: ProbabilityDistance(0.1, 0.01, 0.2);
+# ASSERT_NEAR there is +-1 %, tests/TestLib.h:136-141): (reference, read, quality, maxStartShift, maxShift, expected probability)
+Q10 = chr(43)
+PROBABILITY_DISTANCE_KATS = [
+    ("A", "A", "I", 0, 0, 0.9),
+    ("A", "C", "I", 0, 0, 0.1),
+    ("A", "C", Q10, 0, 0, 0.19),
+    ("A", "A", "I", 1, 2, 0.9),
+    ("A", "C", "I", 1, 2, 0.1),
+    ("A", "C", Q10, 1, 2, 0.19),
+    ("AAAAA", "AAAAA", "IIIII", 1, 2, 0.9 ** 5),
+    ("AAAAA", "AACAA", "IIIII", 1, 2, 0.9 ** 4 * 0.1),
+    ("ACGTA", "ACGGTA", "IIIIII", 1, 2, 0.9 ** 5 * 0.01),
+    ("ACGTA", "ACTA", "IIII", 1, 2, 0.9 ** 2 * 0.1 ** 2),
+    ("ACGTACGT", "ACGTTACGT", "IIIIIIIII", 1, 2, 0.9 ** 8 * 0.01),
+    ("ACGTACGT", "ACGACGT", "IIIIIII", 1, 2, 0.9 ** 7 * 0.01),
+    ("ACGTACGT", "ACTACGT", "IIIIIII", 0, 2, 0.9 ** 7 * 0.01),
+    ("ACGTACGT", "ACTACGT", "IIIIIII", 1, 2, 0.9 ** 5 * 0.1 ** 2),
+    ("ACGTACGT", "ACGTTTACGT", "IIIIIIIIII", 1, 2, 0.9 ** 8 * 0.01 * 0.2),
+    ("ACGTTTACGT", "ACGTACGT", "IIIIIIII", 1, 2, 0.9 ** 8 * 0.01 * 0.2),
+]

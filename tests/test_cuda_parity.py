@@ -37,6 +37,22 @@ def test_golden_mapq(cuda, golden):
     P.check_golden_mapq(cuda, golden)
 
 
+def test_mapq_near_integers_force_the_host_reevaluation(cuda, ref):
+    """computeMAPQ truncates -10 * log10(1 - pBest / pAll) (mapq.h:51): CUDA's log10 and glibc's may differ in the last ulp, which
+    matters exactly when the value is within ulps of an integer.  The kernels flag such values and the library re-evaluates them
+    with libm; these vectors sit on and around every integer 1..68, so the path is taken (and the results are the reference's)."""
+    import ctypes as C
+    from test_oracle import near_integer_mapq_vectors
+    pa, pb, sc, po = near_integer_mapq_vectors()
+    want = ref.mapq(pa, pb, sc, po)
+    np.testing.assert_array_equal(cuda.mapq(pa, pb, sc, po), want)
+    out, flags = np.zeros(len(pa), np.int32), np.zeros(len(pa), np.uint8)
+    rc = cuda.lib.snapb200_mapq_batch_ex(C.c_int(cuda.device), C.c_uint32(len(pa)), A.pf64(pa), A.pf64(pb), A.p32i(sc), A.p32i(po), A.p32i(out), A.p8(flags))
+    assert rc == 0
+    np.testing.assert_array_equal(out, want)
+    assert flags.sum() > 300, int(flags.sum())  # the near-integer vectors were re-evaluated on the host
+
+
 def test_golden_lookup(cuda, handle, golden):
     P.check_golden_lookup(cuda, handle, golden)
 

@@ -43,6 +43,13 @@ PATCHES = [
 # the CUDA path's p_all / p_best are compared with the reference itself and not only with the port.  (file, 1-based line, text that
 # must be on that line, line inserted BEFORE it.)  Listed bottom-up so that earlier line numbers stay valid.
 INSERT_PATCHES = [
+    # INTEGRATION.md section 3, third change: with the alignment core on the GPU the host copy of the hash tables (48 GB at 3.1 Gbp)
+    # is dead weight -- the extension needs only the genome text (SAM output) and the seed length.  SNAPB200_GENOME_ONLY (set by
+    # snap-rna-b200's main, never by the reference's) makes GenomeIndex::loadFromDirectory skip the overflow table and the hash
+    # tables.  Two inserted lines; without the variable the function is unchanged.
+    ("SNAPLib/GenomeIndex.cpp", 945, 'snprintf(filenameBuffer,filenameBufferSize,"%s%cGenome",directoryName,PATH_SEP);', "    }"),
+    ("SNAPLib/GenomeIndex.cpp", 887, "index->overflowTable = (unsigned *)BigAlloc(index->overflowTableSize * sizeof(*(index->overflowTable)),&index->overflowTableVirtualAllocSize);",
+     '    if (getenv("SNAPB200_GENOME_ONLY") != NULL) { index->nHashTables = 0; } else {'),
     ("SNAPLib/IntersectingPairedEndAligner.cpp", 722, "if (bestPairScore == 65536) {",
      "    snapref_pair_p[0] = probabilityOfAllPairs; snapref_pair_p[1] = probabilityOfBestPair;"),
     ("SNAPLib/IntersectingPairedEndAligner.cpp", 141, "void",

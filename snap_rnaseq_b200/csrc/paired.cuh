@@ -670,6 +670,20 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                     if (!resume && (sm->stop || sm->pos >= n_cands)) { need = NEED_DONE; break; }
                     const int ci = resume ? sm->ci : (int)sc.order[sm->pos];
                     const Cand *c = &sc.cands[ci];
+#ifdef PF_CANDS
+                    // the leader's loads are a dependent chain through HBM-resident scratch (order -> candidate -> its mates): ask
+                    // for the records of the candidates a few positions ahead now, so that they are in L1 when their turn comes
+                    if (!resume) {
+                        if (sm->pos + PF_CANDS < n_cands) {
+                            const uint32_t nj = sc.order[sm->pos + PF_CANDS];
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(&sc.cands[nj]));
+                        }
+                        if (sm->pos + PF_CANDS / 2 < n_cands) {
+                            const Cand *nc = &sc.cands[sc.order[sm->pos + PF_CANDS / 2]];
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(&sc.mates_of(nc->set_pair)[nc->mate_index]));
+                        }
+                    }
+#endif
                     if (!resume) {
                         if ((uint32_t)c->list > sm->score_limit) { need = NEED_DONE; break; }  // lists beyond the limit are never served (:527-530)
                         sm->n_lv++;
@@ -701,6 +715,9 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                 #pragma unroll 1
                 for (;;) {
                     Mate *m = &mbase[sm->mi];
+#ifdef PF_MATES
+                    if (sm->mi >= PF_MATES) asm volatile("prefetch.global.L1 [%0];" ::"l"(&mbase[sm->mi - PF_MATES]));  // the walk goes down the array
+#endif
                     int act = 0;
                     if (sm->state == ST_MATES_RESUME) {  // the warp has just scored this mate for sm->m_limit
                         act = 2;

@@ -185,6 +185,15 @@ __device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, 
     const int seed_len = (int)ix.seed_len;
     const int tail = (int)seed_offset + seed_len;
     const uint8_t *g = ix.genome + loc;
+#ifdef LANE_PREFETCH
+    // every lane asks for the 128-byte lines of its own window up front, so that their HBM latencies overlap instead of being paid one
+    // line at a time along the walk (the window is [loc - MAXK, loc + rlen + MAXK): two or three lines)
+    if (ok) {
+        const uintptr_t lo = ((uintptr_t)g - MAXK) & ~(uintptr_t)127, hi = (uintptr_t)g + rlen + MAXK;
+        #pragma unroll 1
+        for (uintptr_t a = lo; a < hi; a += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
+#endif
     double p1 = 0, p2 = 0;
     int dummy, off = 0;
     int s1 = lv_lane<1>(v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, kl, R, T, ix_slot, ok, &p1, &dummy);

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -1238,6 +1239,28 @@ extern "C" int snapb200_single_multihit_batch(snapb200_index *idx, const snapb20
     return single_batch_impl(idx, params, reads, results, hit_counts, hit_locations, hit_rcs, hit_scores);
 }
 
+// One worker of snapb200_paired_batch: chunks first, first + stride, ... on one of the index's internal sessions.
+static int paired_chunks(snapb200_index *idx, const snapb200_paired_params *params, const snapb200_read_batch *reads0, const snapb200_read_batch *reads1,
+                         snapb200_paired_result *results, uint32_t first, uint32_t stride, uint32_t CHUNK, int *limit_rc)
+{
+    BatchSlot slot(idx);
+    int rc;
+    if ((rc = slot.open())) return rc;
+    snapb200_session *cur = slot.s;
+    const uint32_t n = reads0->n;
+    std::vector<uint32_t> off_store[2];
+    for (uint64_t lo64 = (uint64_t)first * CHUNK; lo64 < n; lo64 += (uint64_t)stride * CHUNK) {
+        const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)std::min<uint64_t>(n, lo64 + CHUNK);
+        snapb200_read_batch a = sub_batch(reads0, lo, hi, off_store[0]);
+        snapb200_read_batch b = sub_batch(reads1, lo, hi, off_store[1]);
+        if ((rc = snapb200_session_upload(cur, 0, &a)) || (rc = snapb200_session_upload(cur, 1, &b))) return rc;
+        if ((rc = snapb200_session_run_paired(cur, params))) return rc;
+        rc = snapb200_session_download_paired(cur, results + lo);
+        if (rc == SNAPB200_ERR_LIMIT) *limit_rc = rc; else if (rc) return rc;
+    }
+    return 0;
+}
+
 extern "C" int snapb200_paired_batch(snapb200_index *idx, const snapb200_paired_params *params, const snapb200_read_batch *reads0,
                                      const snapb200_read_batch *reads1, snapb200_paired_result *results)
 {
@@ -1246,23 +1269,27 @@ extern "C" int snapb200_paired_batch(snapb200_index *idx, const snapb200_paired_
     uint32_t m0, m1;
     int rc;
     if ((rc = validate_batch(reads0, &m0)) || (rc = validate_batch(reads1, &m1))) return rc;
-    BatchSlot slot(idx);
-    if ((rc = slot.open())) return rc;
-    snapb200_session *cur = slot.s;
-    const uint32_t n = reads0->n;
-    std::vector<uint32_t> off_store[2];
-    int limit_rc = 0;
     const uint32_t CHUNK = chunk_size();
-    for (uint32_t lo = 0; lo < n; lo += CHUNK) {
-        const uint32_t hi = std::min(n, lo + CHUNK);
-        snapb200_read_batch a = sub_batch(reads0, lo, hi, off_store[0]);
-        snapb200_read_batch b = sub_batch(reads1, lo, hi, off_store[1]);
-        if ((rc = snapb200_session_upload(cur, 0, &a)) || (rc = snapb200_session_upload(cur, 1, &b))) return rc;
-        if ((rc = snapb200_session_run_paired(cur, params))) return rc;
-        rc = snapb200_session_download_paired(cur, results + lo);
-        if (rc == SNAPB200_ERR_LIMIT) limit_rc = rc; else if (rc) return rc;
+    int limit_rc[2] = {0, 0};
+    if (reads0->n <= CHUNK) {
+        rc = paired_chunks(idx, params, reads0, reads1, results, 0, 1, CHUNK, &limit_rc[0]);
+        return rc ? rc : limit_rc[0];
     }
-    return limit_rc;
+    // More than one launch group: even and odd chunks go through the two internal sessions from two host threads, so the upload
+    // of chunk k+1 and the download of chunk k-1 (and the host round trips inside a run: scratch-tier retries, counters) overlap
+    // the kernels of chunk k -- what two concurrent callers get, inside one call.
+    int rc2 = 0;
+    char err2[sizeof(g_last_error)] = "";
+    std::thread odd([&] {
+        rc2 = paired_chunks(idx, params, reads0, reads1, results, 1, 2, CHUNK, &limit_rc[1]);
+        if (rc2) { strncpy(err2, g_last_error, sizeof(err2) - 1); err2[sizeof(err2) - 1] = 0; }
+    });
+    rc = paired_chunks(idx, params, reads0, reads1, results, 0, 2, CHUNK, &limit_rc[0]);
+    odd.join();
+    if (!rc && rc2) { rc = rc2; strncpy(g_last_error, err2, sizeof(g_last_error) - 1); }
+    if (rc) return rc;
+    if (limit_rc[0] || limit_rc[1]) return set_error(SNAPB200_ERR_LIMIT, "a pair exceeded the reference's candidate pool (-mcp); the reference exits here");
+    return 0;
 }
 
 // ---- CIGAR -----------------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 // single/paired contexts are constructed with a GpuAlignerExtension (the two-line change INTEGRATION.md shows).
 // `index` and `transcriptome` are the reference's own host-side builders.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "stdafx.h"
@@ -28,8 +29,12 @@ int main(int argc, const char **argv)
     } else {
         for (int i = 1; i < argc;) {
             unsigned nArgsConsumed = 0;
-            if (strcmp(argv[i], "single") == 0 || strcmp(argv[i], "paired") == 0)  // optional: HBM loading overlaps the host-side loading
+            if (strcmp(argv[i], "single") == 0 || strcmp(argv[i], "paired") == 0) {
+                // the hash tables live in HBM only: the host keeps the genome text (SAM output) and the seed length
+                setenv("SNAPB200_GENOME_ONLY", "1", 1);
+                // optional: HBM loading overlaps the host-side loading
                 GpuAlignerExtension::prefetch(argc - (i + 1), argv + i + 1, strcmp(argv[i], "paired") == 0);
+            }
             if (strcmp(argv[i], "single") == 0) {
                 SingleAlignerContext single(new GpuAlignerExtension());
                 single.runAlignment(argc - (i + 1), argv + i + 1, version, &nArgsConsumed);

@@ -27,9 +27,9 @@ __device__ __forceinline__ uint32_t round8(uint32_t x) { return (x + 7u) & ~7u; 
 // the lane mode (lane_roll_cells(lane_k) cells x 32 lanes)
 __host__ __device__ inline size_t lv_shared_bytes(int lane_k = 0)
 {
-    size_t lane_cells = lane_k > 0 ? (size_t)lane_roll_cells(lane_k) * 32 : 0;
-    size_t cells = LV_CELLS > lane_cells ? LV_CELLS : lane_cells;
-    return (cells * 2 + 15) & ~(size_t)15;
+    size_t lane_bytes = lane_k > 0 ? (size_t)lane_roll_cells(lane_k) * 32 * sizeof(lane_cell_t) : 0;
+    size_t bytes = (size_t)LV_CELLS * 2 > lane_bytes ? (size_t)LV_CELLS * 2 : lane_bytes;
+    return (bytes + 15) & ~(size_t)15;
 }
 
 __device__ __forceinline__ uint32_t fetch_work(uint32_t *counter)
@@ -142,7 +142,7 @@ struct PairedArgs {
     uint32_t n_items;
     snapb200_paired_result *results;
     uint32_t force_spacing;
-    Cand *cands; Mate *mates; Anchor *anchors; int16_t *lane_tables; uint32_t *order;  // [warp slot][...]
+    Cand *cands; Mate *mates; Anchor *anchors; lane_cell_t *lane_tables; uint32_t *order;  // [warp slot][...]
     Counters *ctr; uint32_t *retry_list, *fallback_list; MapqFix *fix; uint32_t fix_cap;
     unsigned long long *stats;
     unsigned long long *prof;  // optional cycle accounting [8] (builds with -DSNAPB200_PROFILE)
@@ -158,7 +158,13 @@ __host__ __device__ inline size_t paired_warp_shared(uint32_t rl, uint32_t lane_
     return s;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 24 / WARPS_PER_CTA) paired_kernel(const PairedArgs a)
+#ifndef PAIRED_WARPS_PER_SM
+// Measured on C3 (scripts/ab_variants.py, profiles/r2_ab_*.log): 16 / 18 / 20 / 24 / 28 / 32 warps per SM = 73.3 / 69.8 / 66.9 / 67.8 / 69.0 /
+// 79.8 ms per million pairs.  The kernel is instruction-fetch and L1 bound: beyond 24 warps the registers drop to 64 (spills) and the
+// shared memory of the extra warps comes out of the L1 that the per-warp scratch in HBM is served from.
+#define PAIRED_WARPS_PER_SM 24
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, PAIRED_WARPS_PER_SM / WARPS_PER_CTA) paired_kernel(const PairedArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();

@@ -405,6 +405,20 @@ __device__ int lv_cigar_warp(const LvStr &s_in, int k, int16_t *L, char *cigar, 
 // The largest score limit handled in lane mode, `kl`, is a property of the launch: max_k + extra_search_depth of the
 // run (17 with the paired defaults, 22 for the -d 20 stress configuration), so the shared-memory rows are as wide as the
 // run can need and no wider.
+// A cell of the rolling rows holds -2 .. pattern length.  One byte (biased by 2) is enough for the strings lane mode is used on
+// (reads of at most LANE_MAX_READ bases; longer reads are scored in warp mode), and halves the shared memory of a warp's rows --
+// which is what decides how many warps an SM holds.  -DLANE_ROWS_I16 builds the 16-bit rows of the first version.
+#ifdef LANE_ROWS_I16
+typedef int16_t lane_cell_t;
+#define LC_BIAS 0
+#define LANE_MAX_READ 500
+#else
+typedef uint8_t lane_cell_t;
+#define LC_BIAS 2
+#define LANE_MAX_READ 250
+#endif
+#define LC_ST(v) ((lane_cell_t)((v) + LC_BIAS))
+#define LC_LD(x) ((int)(x) - LC_BIAS)
 __host__ __device__ inline int lane_rowp(int kl) { return 2 * kl + 3; }  // a row: diagonals -kl..kl plus one cell either side, so that a row's out-of-band neighbours exist
 __host__ __device__ inline int lane_roll_cells(int kl) { return 2 * lane_rowp(kl); }          // per lane: previous row + current row (shared memory)
 __host__ __device__ inline int lane_table_cells(int kl) { return (kl + 1) * (kl + 1); }       // per lane: the full triangular table (HBM scratch)
@@ -443,9 +457,9 @@ __device__ __forceinline__ int lane_run(const uint8_t *p, const uint8_t *t, int 
 }
 
 // full table (HBM scratch): cell (e,d) of this lane at T[(e*e+d+e)*32]; cells outside the band read as -2
-__device__ __forceinline__ int lane_get(const int16_t *T, int e, int d)
+__device__ __forceinline__ int lane_get(const lane_cell_t *T, int e, int d)
 {
-    return (d >= -e && d <= e) ? (int)T[(e * e + d + e) * 32] : -2;
+    return (d >= -e && d <= e) ? LC_LD(T[(e * e + d + e) * 32]) : -2;
 }
 // rolling rows (shared): row parity (e&1), diagonal d of this lane at R[((e&1)*rowp + d + kl + 1)*32]
 
@@ -455,7 +469,7 @@ __device__ __forceinline__ int lane_get(const int16_t *T, int e, int d)
 // column of the full table in HBM scratch (written on the way, read only by the backtrace of successful lanes).
 // k may differ between lanes.  Returns the score or -1.
 template <int DIR>
-__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int kl, int16_t *R, int16_t *T, int ix_slot,
+__device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int kl, lane_cell_t *R, lane_cell_t *T, int ix_slot,
                        bool live_in, double *match_prob, int *net_indel)
 {
     const int rowp = lane_rowp(kl);
@@ -467,8 +481,8 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
     int l0 = 0;
     if (live) {
         l0 = lane_run<DIR>(p, t, 0, 0, plen);
-        R[(kl + 1) * 32] = (int16_t)l0;
-        T[0] = (int16_t)l0;
+        R[(kl + 1) * 32] = LC_ST(l0);
+        T[0] = LC_ST(l0);
         if (l0 == plen) {  // LandauVishkin.h:290-305 (text is never shorter than the pattern here)
             result = 0;
             *match_prob = ix.perfect[plen];
@@ -481,23 +495,23 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
         if (live && e > kmax) live = false;
         if (!__any_sync(FULL_MASK, live)) break;
         // this lane's column of the previous and the current row, centred on diagonal 0
-        int16_t *prev = R + ((((e - 1) & 1) * rowp) + kl + 1) * 32, *cur = R + (((e & 1) * rowp) + kl + 1) * 32;
-        int16_t *Te = T + (e * e + e) * 32;
+        lane_cell_t *prev = R + ((((e - 1) & 1) * rowp) + kl + 1) * 32, *cur = R + (((e & 1) * rowp) + kl + 1) * 32;
+        lane_cell_t *Te = T + (e * e + e) * 32;
         if (live) {  // cells just outside the band of row e-1 read as -2 (never written by the reference); no range tests below
-            prev[e * 32] = -2; prev[-e * 32] = -2; prev[(e + 1) * 32] = -2; prev[-(e + 1) * 32] = -2;
+            prev[e * 32] = LC_ST(-2); prev[-e * 32] = LC_ST(-2); prev[(e + 1) * 32] = LC_ST(-2); prev[-(e + 1) * 32] = LC_ST(-2);
         }
         int d = 0;  // visiting order 0,+1,-1,+2,-2,...
         #pragma unroll 1
         for (int r = 0; r <= 2 * e; r++) {
             if (live) {
-                int best = (int)prev[d * 32] + 1;
-                const int left = (int)prev[(d - 1) * 32];
+                int best = LC_LD(prev[d * 32]) + 1;
+                const int left = LC_LD(prev[(d - 1) * 32]);
                 if (left > best) best = left;
-                const int right = (int)prev[(d + 1) * 32] + 1;
+                const int right = LC_LD(prev[(d + 1) * 32]) + 1;
                 if (right > best) best = right;
                 if (best < plen) best += lane_run<DIR>(p, t, best, d + best, plen);
-                cur[d * 32] = (int16_t)best;
-                Te[d * 32] = (int16_t)best;
+                cur[d * 32] = LC_ST(best);
+                Te[d * 32] = LC_ST(best);
                 if (best == plen) { result = e; win_d = d; live = false; }
             }
             d = d > 0 ? -d : 1 - d;

@@ -65,6 +65,7 @@ struct PairedCfg {
     uint32_t cand_cap, mate_cap, anchor_cap;  // this scratch tier
     uint32_t hard_limit;                       // 1: caps are the reference's pool sizes (overflow = its soft_exit)
     uint32_t lane_k;                           // largest score limit scored in lane mode = max_k + extra (sizes the LV rows)
+    uint32_t lane_gate;                        // a limit is scored in lane mode iff limit < lane_gate: lane_k + 1, or 0 when the reads are too long for the one-byte rows
     uint32_t rl;
 };
 
@@ -74,7 +75,7 @@ struct PairedScratch {
     uint32_t mate_cap;
     __device__ __forceinline__ Mate *mates_of(uint32_t sp) const { return mates + (size_t)sp * mate_cap; }
     Anchor *anchors;
-    int16_t *lane_table;  // lane_table_cells(cfg.lane_k) * 32 cells: the full L tables of a lane-mode batch
+    lane_cell_t *lane_table;  // lane_table_cells(cfg.lane_k) * 32 cells: the full L tables of a lane-mode batch
     uint32_t *order;      // cand_cap entries: candidate indices in phase 3's visiting order
 };
 
@@ -303,7 +304,7 @@ __device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, i
 // out of the main body makes their path through the kernel 10 % faster (instruction cache).
 // (arguments by value: a reference to the kernel's configuration or scratch descriptor would force them onto the stack)
 __device__ __noinline__ void lane_batch_candidates(int ix_slot, int lane_k, uint32_t min_spacing, uint32_t max_spacing, Cand *cands, Mate *mates,
-                                                   uint32_t mate_cap, int16_t *lane_table, PairedSm *sm, const ReadView vf, const ReadView vm,
+                                                   uint32_t mate_cap, lane_cell_t *lane_table, PairedSm *sm, const ReadView vf, const ReadView vm,
                                                    int fewer, uint32_t n_batch, int16_t *L)
 {
     const int lane = lane_id();
@@ -317,7 +318,7 @@ __device__ __noinline__ void lane_batch_candidates(int ix_slot, int lane_k, uint
     int s = SC_NONE, off = 0;
     double pr = 0;
     const int dl = act_l ? (fewer == 0 ? (int)cl->set_pair : 1 - (int)cl->set_pair) : 0;
-    score_location_lane(ix_slot, vf, dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, lane_k, L + lane, lane_table + lane, act_l, &s, &pr, &off);
+    score_location_lane(ix_slot, vf, dl, act_l ? cl->loc : 0, act_l ? cl->seed_offset : 0, K, lane_k, (lane_cell_t *)L + lane, lane_table + lane, act_l, &s, &pr, &off);
     if (act_l && s != SC_NONE) { cl->c_score = (int16_t)s; cl->c_k = (uint8_t)K; cl->c_off = (int8_t)off; cl->c_prob = pr; }
     __syncwarp();
     PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += n_batch; })
@@ -352,7 +353,7 @@ __device__ __noinline__ void lane_batch_candidates(int ix_slot, int lane_k, uint
             const bool mine = mt != nullptr && lane == __ffs((int)peers) - 1;
             int s2 = SC_NONE, off2 = 0;
             double pr2 = 0;
-            score_location_lane(ix_slot, vm, dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, lane_k, L + lane, lane_table + lane, mine,
+            score_location_lane(ix_slot, vm, dml, mine ? mt->loc : 0, mine ? mt->seed_offset : 0, gmax, lane_k, (lane_cell_t *)L + lane, lane_table + lane, mine,
                                 &s2, &pr2, &off2);
             if (mine && s2 != SC_NONE) { mt->s_score = (int16_t)s2; mt->s_k = (uint8_t)gmax; mt->s_off = (int8_t)off2; mt->s_prob = pr2; }
             n_done += __popc(__ballot_sync(FULL_MASK, mine));
@@ -692,7 +693,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                     if (cs == SC_NONE) {  // not scored yet: the warp scores it and the next unscored candidates in visiting order
                         sm->ci = ci; sm->c_loc = c->loc; sm->c_seedoff = c->seed_offset; sm->c_sp = c->set_pair;
                         sm->state = ST_PICK_RESUME;
-                        need = sm->score_limit <= cfg.lane_k ? NEED_CAND_BATCH : NEED_CAND_WARP;
+                        need = sm->score_limit < cfg.lane_gate ? NEED_CAND_BATCH : NEED_CAND_WARP;
                         break;
                     }
                     if (!(cs >= 0 && (uint32_t)cs <= sm->score_limit)) {  // scoreLocation says -1 for the limit in force: next candidate
@@ -733,7 +734,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                                 // not known well enough: gather the mates further down this candidate's range that will need a score
                                 sm->m_loc = m->loc; sm->m_seedoff = m->seed_offset;
                                 uint32_t nb = 0;
-                                const bool lane_ok = m_limit <= cfg.lane_k;
+                                const bool lane_ok = m_limit < cfg.lane_gate;
                                 uint32_t j = sm->mi;
                                 #pragma unroll 1
                                 for (;;) {
@@ -859,7 +860,7 @@ __device__ int paired_intersect_warp(int ix_slot, const PairedCfg &cfg, const Pa
                 Mate *ml = act_l ? &sc.mates_of(sp)[sm->batch_ids[lane]] : nullptr;
                 int s = SC_NONE, off = 0;
                 double pr = 0;
-                score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, (int)cfg.lane_k, L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
+                score_location_lane(ix_slot, view(more), dir_m, act_l ? ml->loc : 0, act_l ? ml->seed_offset : 0, K, (int)cfg.lane_k, (lane_cell_t *)L + lane, sc.lane_table + lane, act_l, &s, &pr, &off);
                 if (act_l && s != SC_NONE) { ml->s_score = (int16_t)s; ml->s_k = (uint8_t)K; ml->s_off = (int8_t)off; ml->s_prob = pr; }
                 __syncwarp();
                 PROF(if (lane == 0) { sm->t_phase[5] += clock64() - t_y; sm->t_phase[6] += 1; sm->t_phase[7] += nb; })

@@ -925,10 +925,10 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     if ((rc = s->p_cands.ensure(warps * cfg.cand_cap * sizeof(Cand)))) return rc;
     if ((rc = s->p_mates.ensure(warps * 2 * cfg.mate_cap * sizeof(Mate)))) return rc;
     if ((rc = s->p_anchors.ensure(warps * cfg.anchor_cap * sizeof(Anchor)))) return rc;
-    if ((rc = s->p_lane_tables.ensure(warps * lane_table_cells((int)cfg.lane_k) * 32 * sizeof(int16_t)))) return rc;
+    if ((rc = s->p_lane_tables.ensure(warps * lane_table_cells((int)cfg.lane_k) * 32 * sizeof(lane_cell_t)))) return rc;
     if ((rc = s->p_order.ensure(warps * cfg.cand_cap * sizeof(uint32_t)))) return rc;
     a.cands = s->p_cands.as<Cand>(); a.mates = s->p_mates.as<Mate>(); a.anchors = s->p_anchors.as<Anchor>();
-    a.lane_tables = s->p_lane_tables.as<int16_t>();
+    a.lane_tables = s->p_lane_tables.as<lane_cell_t>();
     a.order = s->p_order.as<uint32_t>();
     a.ctr = s->counters.as<Counters>();
     a.retry_list = s->retry_list.as<uint32_t>(); a.fallback_list = s->fallback_list.as<uint32_t>();
@@ -1002,6 +1002,7 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
     uint64_t ref_pool = std::min<uint64_t>(p->max_candidate_pool_size, (uint64_t)p->max_big_hits * ctor_seeds * 2);
     int per_sm = 1;
     cfg.lane_k = p->max_k + p->extra_search_depth;  // < MAXK (checked above)
+    cfg.lane_gate = s->max_len_seen <= LANE_MAX_READ ? cfg.lane_k + 1 : 0;
     const size_t smem = paired_warp_shared(rl, cfg.lane_k) * WARPS_PER_CTA;
     int grid = grid_for(paired_kernel, smem, x->sm_count, &per_sm);
     if (const char *e = getenv("SNAPB200_CTAS_PER_SM")) {  // experiments only: fewer resident CTAs than fit

@@ -456,6 +456,35 @@ __device__ __forceinline__ int lane_run(const uint8_t *p, const uint8_t *t, int 
     return n < rem ? n : rem;
 }
 
+// the same with the direction as a run-time value: one copy of the code for both passes (the kernel is instruction-fetch bound)
+__device__ __forceinline__ int lane_run_rt(const int DIR, const uint8_t *p, const uint8_t *t, int pi, int ti, int plen)
+{
+    const int rem = plen - pi;
+    if (rem <= 0) return 0;
+    // first byte compared in memory order: string(i) lives at base + DIR * i; a step covers 4 bytes at [a, a+3]
+    const uintptr_t pa = (uintptr_t)(DIR > 0 ? p + pi : p - pi - 3), ta = (uintptr_t)(DIR > 0 ? t + ti : t - ti - 3);
+    const uint32_t *pw = (const uint32_t *)(pa & ~(uintptr_t)3), *tw = (const uint32_t *)(ta & ~(uintptr_t)3);
+    const unsigned psh = (unsigned)(pa & 3) * 8, tsh = (unsigned)(ta & 3) * 8;
+    uint32_t p0 = pw[0], p1 = pw[1], t0 = tw[0], t1 = tw[1];
+    int n = 0;
+    #pragma unroll 1
+    for (;;) {
+        // the words the next step needs: one further along the walk (up for DIR > 0, down for DIR < 0)
+        pw += DIR; tw += DIR;
+        const uint32_t pn = DIR > 0 ? pw[1] : pw[0], tn = DIR > 0 ? tw[1] : tw[0];
+        uint32_t x = __funnelshift_r(p0, p1, psh) ^ __funnelshift_r(t0, t1, tsh);
+        if (x) {
+            if (DIR < 0) x = __byte_perm(x, 0, 0x0123);  // string order is descending addresses
+            n += (__ffs((int)x) - 1) >> 3;
+            break;
+        }
+        n += 4;
+        if (n >= rem) break;
+        if (DIR > 0) { p0 = p1; p1 = pn; t0 = t1; t1 = tn; } else { p1 = p0; p0 = pn; t1 = t0; t0 = tn; }
+    }
+    return n < rem ? n : rem;
+}
+
 // full table (HBM scratch): cell (e,d) of this lane at T[(e*e+d+e)*32]; cells outside the band read as -2
 __device__ __forceinline__ int lane_get(const lane_cell_t *T, int e, int d)
 {
@@ -510,6 +539,105 @@ __device__ __noinline__ int lv_lane(const uint8_t *p, int plen, const uint8_t *t
                 const int right = LC_LD(prev[(d + 1) * 32]) + 1;
                 if (right > best) best = right;
                 if (best < plen) best += lane_run<DIR>(p, t, best, d + best, plen);
+                cur[d * 32] = LC_ST(best);
+                Te[d * 32] = LC_ST(best);
+                if (best == plen) { result = e; win_d = d; live = false; }
+            }
+            d = d > 0 ? -d : 1 - d;
+        }
+    }
+    if (result >= 1) {  // backtrace, LandauVishkin.h:379-431
+        char act[MAXK + 1];
+        short matched[MAXK + 1];
+        int cur_d = win_d;
+        #pragma unroll 1
+        for (int ce = result; ce >= 1; ce--) {
+            int up = lane_get(T, ce - 1, cur_d) + 1, left = lane_get(T, ce - 1, cur_d - 1), right = lane_get(T, ce - 1, cur_d + 1) + 1;
+            int best = up;
+            char a = 'X';
+            if (left > best) { best = left; a = 'D'; }
+            if (right > best) { best = right; a = 'I'; }
+            const int here = (ce == result) ? plen : lane_get(T, ce, cur_d);
+            act[ce] = a;
+            matched[ce] = (short)(here - best);  // bases matched after the edit = L[ce][d] - (value before extension)
+            cur_d += a == 'I' ? 1 : (a == 'D' ? -1 : 0);
+        }
+        double prob = 1.0;
+        int indel = 0, ce = 1, offset = l0;
+        #pragma unroll 1
+        while (ce <= result) {
+            const char a = act[ce];
+            int count = 1;
+            #pragma unroll 1
+            while (ce + 1 <= result && matched[ce] == 0 && act[ce + 1] == a) { count++; ce++; }
+            if (a == 'I') {
+                prob *= ix.indel[count];
+                offset += count;
+                indel += count;
+            } else if (a == 'D') {
+                prob *= ix.indel[count];
+                offset -= count;
+                indel -= count;
+            } else {
+                #pragma unroll 1
+                for (int i = 0; i < count; i++) {
+                    int qi = min(plen - 1, max(offset, 0));
+                    prob *= ix.phred[q[qi * DIR]];
+                    offset++;
+                }
+            }
+            offset += matched[ce];
+            ce++;
+        }
+        prob *= ix.perfect[plen - result];
+        *match_prob = prob;
+        *net_indel = indel;
+    }
+    return result;
+}
+
+// one body for both directions (see lane_run_rt)
+__device__ __noinline__ int lv_lane_rt(const int DIR, const uint8_t *p, int plen, const uint8_t *t, const uint8_t *q, int k, int kl, lane_cell_t *R, lane_cell_t *T, int ix_slot,
+                       bool live_in, double *match_prob, int *net_indel)
+{
+    const int rowp = lane_rowp(kl);
+    const DevIndex &ix = c_index[ix_slot];  // only the probability tables are used
+    int result = -1, win_d = 0;
+    *match_prob = 0.0;
+    *net_indel = 0;
+    bool live = live_in;
+    int l0 = 0;
+    if (live) {
+        l0 = lane_run_rt(DIR, p, t, 0, 0, plen);
+        R[(kl + 1) * 32] = LC_ST(l0);
+        T[0] = LC_ST(l0);
+        if (l0 == plen) {  // LandauVishkin.h:290-305 (text is never shorter than the pattern here)
+            result = 0;
+            *match_prob = ix.perfect[plen];
+            live = false;
+        }
+    }
+    const int kmax = min(k > 0 ? k : 0, kl);
+    #pragma unroll 1
+    for (int e = 1; e <= kl; e++) {
+        if (live && e > kmax) live = false;
+        if (!__any_sync(FULL_MASK, live)) break;
+        // this lane's column of the previous and the current row, centred on diagonal 0
+        lane_cell_t *prev = R + ((((e - 1) & 1) * rowp) + kl + 1) * 32, *cur = R + (((e & 1) * rowp) + kl + 1) * 32;
+        lane_cell_t *Te = T + (e * e + e) * 32;
+        if (live) {  // cells just outside the band of row e-1 read as -2 (never written by the reference); no range tests below
+            prev[e * 32] = LC_ST(-2); prev[-e * 32] = LC_ST(-2); prev[(e + 1) * 32] = LC_ST(-2); prev[-(e + 1) * 32] = LC_ST(-2);
+        }
+        int d = 0;  // visiting order 0,+1,-1,+2,-2,...
+        #pragma unroll 1
+        for (int r = 0; r <= 2 * e; r++) {
+            if (live) {
+                int best = LC_LD(prev[d * 32]) + 1;
+                const int left = LC_LD(prev[(d - 1) * 32]);
+                if (left > best) best = left;
+                const int right = LC_LD(prev[(d + 1) * 32]) + 1;
+                if (right > best) best = right;
+                if (best < plen) best += lane_run_rt(DIR, p, t, best, d + best, plen);
                 cur[d * 32] = LC_ST(best);
                 Te[d * 32] = LC_ST(best);
                 if (best == plen) { result = e; win_d = d; live = false; }

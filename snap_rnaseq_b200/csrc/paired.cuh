@@ -20,7 +20,9 @@
 #define MATE_LOOKAHEAD_ROUNDS 2  // mates scored ahead per candidate of a lane-mode batch
 #endif
 #ifndef LANE_MIN_BATCH
-#define LANE_MIN_BATCH 3  // fewer pending locations than this: the warp-cooperative LV is used
+#define LANE_MIN_BATCH 1  // fewer pending locations than this: the warp-cooperative LV is used.  Round 2: 1 -- every location that may be
+                          // scored in lane mode is (63.5 -> 62.0 ms per million C3 pairs): the warp-mode routines stay in the binary for windows at
+                          // the genome's edge, limits above lane_k and long reads, but are no longer fetched by ordinary pairs
 #endif
 
 struct __align__(8) Mate {  // ScoringMateCandidate (IntersectingPairedEndAligner.h:401-423)

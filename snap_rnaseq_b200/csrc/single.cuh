@@ -196,12 +196,21 @@ __device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, 
 #endif
     double p1 = 0, p2 = 0;
     int dummy, off = 0;
+#ifndef LANE_TEMPLATE_DIR  // one run-time-direction body for both passes: 7 KB less code to fetch, 66.4 -> 63.8 ms per million C3 pairs
+    int s1 = lv_lane_rt(1, v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, kl, R, T, ix_slot, ok, &p1, &dummy);
+#else
     int s1 = lv_lane<1>(v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, kl, R, T, ix_slot, ok, &p1, &dummy);
+#endif
     const bool ok2 = ok && s1 != -1;
     PROF({ const unsigned a = __ballot_sync(FULL_MASK, ok), b = __ballot_sync(FULL_MASK, ok2);
            if (lane_id() == 0) { atomicAdd(&g_prof_lane[0], 1ull); atomicAdd(&g_prof_lane[1], (unsigned long long)__popc(a)); atomicAdd(&g_prof_lane[2], (unsigned long long)__popc(b)); } })
+#ifndef LANE_TEMPLATE_DIR
+    int s2 = lv_lane_rt(-1, v.D(dir) + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q(dir) + (int)seed_offset - 1,
+                        K - (s1 > 0 ? s1 : 0), kl, R, T, ix_slot, ok2, &p2, &off);
+#else
     int s2 = lv_lane<-1>(v.D(dir) + (int)seed_offset - 1, (int)seed_offset, g + (int)seed_offset - 1, v.Q(dir) + (int)seed_offset - 1,
                          K - (s1 > 0 ? s1 : 0), kl, R, T, ix_slot, ok2, &p2, &off);
+#endif
     if (!ok) return;
     if (s1 == -1 || s2 == -1) { *score = -1; return; }
     *score = s1 + s2;

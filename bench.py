@@ -43,12 +43,12 @@ CPU_SAMPLE_PAIRS = 200_000
 
 def measured_traffic(pairs):
     """dram__bytes_read + dram__bytes_write of paired_kernel per launch, from the committed `ncu --set full` capture of the
-    same configuration (profiles/r1s2_traffic.json: bytes per pair of a 200 k-pair launch), scaled to this launch's pairs.
+    same configuration (profiles/r2_traffic.json: bytes per pair of a 200 k-pair launch), scaled to this launch's pairs.
     None for configurations that were not captured."""
     if (sum(GENOME_CONTIGS) // 1_000_000, READ_LEN) != (3100, 150):
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1s2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             return float(json.load(f)["dram_bytes_per_pair"]) * pairs
     except Exception:
         return None
@@ -61,14 +61,14 @@ def int_alu_roofline(pairs, kernel_ms, sm_mhz):
     if (sum(GENOME_CONTIGS) // 1_000_000, READ_LEN) != (3100, 150):
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1s2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             per_pair = float(json.load(f)["thread_instructions_per_pair"])
     except Exception:
         return None
     achieved = per_pair * pairs / (kernel_ms * 1e-3) / 1e12
     peak = 148 * 128 * float(sm_mhz or 1965.0) * 1e6 / 1e12
     return {"bound": "int-alu issue", "kernel": "paired_kernel", "achieved": achieved, "peak": peak, "unit": "T thread-instructions/s",
-            "frac": achieved / peak, "source": "profiles/r1s2_traffic.json (ncu --set full capture) x pairs / CUDA-event kernel time"}
+            "frac": achieved / peak, "source": "profiles/r2_traffic.json (ncu --set full capture) x pairs / CUDA-event kernel time"}
 
 
 def workload_config(n_gpus, pairs):

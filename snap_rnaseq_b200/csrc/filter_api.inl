@@ -175,6 +175,10 @@ static int filter_launch(snapb200_annotation *a, FilterWarpArgs &k, DevBuf &scra
     k.t = a->t;
     k.chr_rank = a->chr_rank;
     k.list_cap = k.mh + 1;
+    if (const char *e = getenv("SNAPB200_FILTER_LIST_CAP")) {  // tests: a tiny scratch forces the needs_host path of the callers
+        const long v = atol(e);
+        if (v >= 1 && (uint32_t)v < k.list_cap) k.list_cap = (uint32_t)v;
+    }
     k.pair_cap = FW_PAIR_CAP;
     k.ploc_cap = FW_PLOC_CAP;
     k.scratch_per_warp = fw_scratch_bytes(k.list_cap, k.pair_cap, k.ploc_cap);
@@ -469,6 +473,10 @@ static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
             sa.ev = k.ev; sa.pair_needs_host = k.needs_host;
             for (int e = 0; e < 2; e++) { sa.offsets[e] = k.len[e]; sa.seg[e] = k.seg[e]; sa.ch_loc[e] = k.ch_loc[e]; sa.ch_off[e] = k.ch_off[e]; }
             sa.seg_cap = 4096;
+            if (const char *e = getenv("SNAPB200_SPLICE_SEG_CAP")) {  // tests: forces splice_overflow (the caller runs UnalignedRead itself)
+                const long v = atol(e);
+                if (v >= 1 && v < 4096) sa.seg_cap = (uint32_t)v;
+            }
             sa.scratch_per_warp = splice_scratch_bytes(sa.seg_cap);
             const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>((n + 7) / 8, (uint32_t)b->ann->sm_count));
             if ((rc = s->f_scratch.ensure((size_t)ctas * 8 * sa.scratch_per_warp))) return rc;

@@ -161,3 +161,21 @@ def test_rna_mode_batches_dealt_over_all_gpus(workspace):
         assert_same(sam_records(os.path.join(d, "ref_m.sam")), sam_records(os.path.join(d, tag + ".sam")), 2 * (4000 + 600))
         for f in SIDE_FILES + ("contaminants.txt",):
             assert open(os.path.join(d, "ref_m." + f), "rb").read() == open(os.path.join(d, tag + "." + f), "rb").read(), (tag, f)
+
+
+def test_rna_mode_device_scratch_overflow_falls_back_to_the_reference_classes(workspace):
+    """Pairs with more alignments than the device filter's scratch holds (`needs_host`) and reads with more partial alignments than
+    the novel-splice kernel's (`splice_overflow`) are decided by the reference's own AlignmentFilter / UnalignedRead inside the
+    extension, fed from the batch view (multi-hit lists, seed tuples).  Tiny scratch sizes force both paths for a large share of
+    the pairs; SAM records and statistics files must not change."""
+    d = workspace
+    run([REF, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "ref_o.sam", "-t", "1"], d)
+    env = dict(os.environ, SNAPB200_FILTER_LIST_CAP="1", SNAPB200_SPLICE_SEG_CAP="3", SNAPB200_SHIM_TIMING="1")
+    r = subprocess.run([B200, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "gpu_o.sam", "-t", "1"], cwd=d, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    fell_back = [int(l.split("reference filter for ")[1].split(" ")[0]) for l in r.stdout.split("\n") if "reference filter for " in l]
+    assert sum(fell_back) > 300, fell_back  # the overflow path really ran
+    assert_same(sam_records(os.path.join(d, "ref_o.sam")), sam_records(os.path.join(d, "gpu_o.sam")), 8000)
+    for f in SIDE_FILES:
+        assert open(os.path.join(d, "ref_o." + f), "rb").read() == open(os.path.join(d, "gpu_o." + f), "rb").read(), f

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include <malloc.h>
 #include <pthread.h>
 #include <sys/time.h>
 
@@ -60,9 +61,32 @@ public:
     // (Needs the friend declarations of INTEGRATION.md section 3 in ReadInterval, ReadIntervalMap and GTFReader.)
     struct SpliceBatch {
         std::vector<ReadInterval *> mates[2];  // [0] intrachromosomal, [1] interchromosomal; consecutive entries are a pair
+        // glibc grows a thread's malloc arena one mprotect (a write lock on the process's address space) per few pages; sixteen
+        // worker threads allocating ~750 bytes per record spend most of their time waiting for each other there.  Asking for a
+        // large block and freeing it again (with trimming disabled, see pregrowSetup) leaves the arena's top chunk that large, so
+        // the next ~30 k records are carved out of it without a system call.
+        size_t sinceGrow;
+        SpliceBatch() : sinceGrow(~(size_t)0 / 2) {}
+        static void pregrowSetup()
+        {
+            static bool done = false;
+            if (done) return;
+            done = true;
+            mallopt(M_MMAP_THRESHOLD, 32 << 20);   // so that the 28 MB request below comes from the arena, not from mmap
+            mallopt(M_TRIM_THRESHOLD, 1 << 30);    // and stays with the arena when it is freed
+        }
+        void pregrow()
+        {
+            if (getenv("SNAPB200_NO_PREGROW") != NULL) return;
+            void *p = malloc(28 << 20);
+            if (p != NULL) { memset(p, 0, 28 << 20); free(p); }  // touched here, once, by this thread: the page faults too are paid in bulk
+            sinceGrow = 0;
+        }
         void add(bool intra, const std::string &chr0, unsigned start0, unsigned end0, const std::string &chr1, unsigned start1, unsigned end1,
                  const std::string &id)
         {
+            if (sinceGrow > (24u << 20)) pregrow();
+            sinceGrow += 800;
             ReadInterval *m0 = new ReadInterval(chr0, start0, end0, id, true);
             ReadInterval *m1 = new ReadInterval(chr1, start1, end1, id, true);
             m0->mate.insert(m1);
@@ -164,6 +188,7 @@ public:
     explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true)
     {
         if (const char *e = getenv("SNAPB200_SHIM_BATCH")) { int v = atoi(e); if (v >= 16) batch_ = (unsigned)v; }  // tests: many small batches
+        AlignerContext2::SpliceBatch::pregrowSetup();  // main thread (copies are made from this object), before the workers allocate
     }
 
     virtual ~GpuAlignerExtension() {}  // indices stay resident for the life of the process (see deviceSet())
@@ -305,6 +330,7 @@ public:
         P.filter.force_spacing = 0;  // applied below, after the contamination step, where the run loop applies it (PairedAligner.cpp:633-651)
         PairBatch pb[2];
         Timing tm;
+        AlignerContext2::SpliceBatch splices;  // the thread's novel-splice intervals between two appends
         int cur = 0;
         fill(pb[cur], supplier, ctx, pc, tm);
         if (pb[cur].n) submit(pb[cur], devs, P);
@@ -312,7 +338,7 @@ public:
             const int nxt = cur ^ 1;
             fill(pb[nxt], supplier, ctx, pc, tm);       // host work that overlaps the device work of pb[cur]
             if (pb[nxt].n) submit(pb[nxt], devs, P);
-            replay(pb[cur], devs, P, partial, ctx, pc, tm);
+            replay(pb[cur], devs, P, partial, ctx, pc, tm, splices);
             cur = nxt;
         }
         const double tLoop = now() - tEnter - tInit, td = now();
@@ -539,7 +565,7 @@ private:
     }
 
     void replay(PairBatch &b, const std::vector<DeviceSet> &devs, const snapb200_rna_params &P, GpuSeedCharacterizer *partial, AlignerContext *ctx,
-                PairedAlignerContext *pc, Timing &tm)
+                PairedAlignerContext *pc, Timing &tm, AlignerContext2::SpliceBatch &splices)
     {
         const DeviceSet &dev = devs[b.dev];
         const snapb200_paired_params &pp = P.paired;
@@ -558,7 +584,6 @@ private:
         const Genome *genome = ctx->index->getGenome();
         std::vector<PairedAlignmentResult> results(b.n);
         std::vector<unsigned> contam;
-        AlignerContext2::SpliceBatch splices;
         const std::vector<std::string> &chrName = dev.chrNames;
         // pass 1: the pair's result and its GTF counters, in input order
         for (unsigned i = 0; i < b.n; i++) {

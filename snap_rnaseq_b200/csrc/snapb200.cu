@@ -17,7 +17,10 @@
 #include "index_build.cuh"
 #include "characterize.cuh"  // after kernels.cuh: uses DevBatch, Counters, fetch_work
 #include "iokernels.cuh"     // FASTQ / SAM batch kernels (row f2); uses lv_cigar_warp, stage_window
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 thread_local char g_last_error[512] = "";
 
@@ -270,62 +273,111 @@ static bool read_file(const std::string &path, std::vector<char> &out)
     return got == (size_t)sz;
 }
 
+// A read-only mapping of a whole file: the index files go from the page cache to HBM without a copy in host memory (at 3.1 Gbp the
+// hash tables are 48 GB).
+struct MappedFile {
+    const char *p = nullptr;
+    size_t size = 0;
+    bool open(const std::string &path)
+    {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+        size = (size_t)st.st_size;
+        if (size) {
+            void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { ::close(fd); return false; }
+            madvise(m, size, MADV_SEQUENTIAL);
+            p = (const char *)m;
+        }
+        ::close(fd);
+        return true;
+    }
+    ~MappedFile() { if (p) munmap((void *)p, size); }
+};
+
 // File formats: GenomeIndex.cpp:646-710 (GenomeIndex, OverflowTable, GenomeIndexHash), HashTable.cpp:181-215
 // (per table: u32 magic 0xb111b010, size_t tableSize, size_t usedElementCount, entries), Genome.cpp:126-158.
 extern "C" int snapb200_index_open(const char *dir, int device, snapb200_index **out)
 {
     if (!dir || !out) return set_error(SNAPB200_ERR_ARG, "null argument");
     std::string d(dir);
-    std::vector<char> meta, ovf, hash, genome;
+    std::vector<char> meta;
     if (!read_file(d + "/GenomeIndex", meta)) return set_error(SNAPB200_ERR_IO, "cannot read %s/GenomeIndex", dir);
     meta.push_back(0);
     unsigned major, minor, n_tables, overflow_words, seed_len, padding;
     if (sscanf(meta.data(), "%u %u %u %u %u %u", &major, &minor, &n_tables, &overflow_words, &seed_len, &padding) != 6)
         return set_error(SNAPB200_ERR_IO, "%s/GenomeIndex: expected six integers", dir);
-    if (!read_file(d + "/OverflowTable", ovf) || ovf.size() < (size_t)overflow_words * 4)
+    MappedFile ovf, hash, genome;
+    if (!ovf.open(d + "/OverflowTable") || ovf.size < (size_t)overflow_words * 4)
         return set_error(SNAPB200_ERR_IO, "cannot read %s/OverflowTable (%u words expected)", dir, overflow_words);
-    if (!read_file(d + "/GenomeIndexHash", hash)) return set_error(SNAPB200_ERR_IO, "cannot read %s/GenomeIndexHash", dir);
-    std::vector<uint64_t> sizes(n_tables);
-    std::vector<char> entries;
-    entries.reserve(hash.size());
+    if (!hash.open(d + "/GenomeIndexHash")) return set_error(SNAPB200_ERR_IO, "cannot read %s/GenomeIndexHash", dir);
+    std::vector<uint64_t> sizes(n_tables), file_pos(n_tables);
     size_t pos = 0;
+    uint64_t total = 0;
     for (unsigned i = 0; i < n_tables; i++) {
-        if (pos + 20 > hash.size()) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash truncated at table %u", i);
+        if (pos + 20 > hash.size) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash truncated at table %u", i);
         uint32_t magic;
         uint64_t size, used;
-        memcpy(&magic, &hash[pos], 4); memcpy(&size, &hash[pos + 4], 8); memcpy(&used, &hash[pos + 12], 8);
+        memcpy(&magic, hash.p + pos, 4); memcpy(&size, hash.p + pos + 4, 8); memcpy(&used, hash.p + pos + 12, 8);
         pos += 20;
         if (magic != 0xb111b010u) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash: bad magic at table %u", i);
-        if (size == 0 || pos + size * 12 > hash.size()) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash: bad size at table %u", i);
+        if (size == 0 || pos + size * 12 > hash.size) return set_error(SNAPB200_ERR_IO, "GenomeIndexHash: bad size at table %u", i);
         sizes[i] = size;
-        entries.insert(entries.end(), hash.begin() + pos, hash.begin() + pos + size * 12);
+        file_pos[i] = pos;
+        total += size;
         pos += size * 12;
     }
-    std::vector<char>().swap(hash);
-    if (!read_file(d + "/Genome", genome)) return set_error(SNAPB200_ERR_IO, "cannot read %s/Genome", dir);
+    if (!genome.open(d + "/Genome") || !genome.size) return set_error(SNAPB200_ERR_IO, "cannot read %s/Genome", dir);
     unsigned n_bases = 0, n_pieces = 0;
     size_t gp = 0;
+    const char *gbeg = genome.p, *gend = genome.p + genome.size;
     {
-        size_t eol = std::find(genome.begin(), genome.end(), '\n') - genome.begin();
-        if (eol >= genome.size()) return set_error(SNAPB200_ERR_IO, "Genome: no header line");
-        std::string line(genome.begin(), genome.begin() + eol);
+        const char *eol = (const char *)memchr(gbeg, '\n', genome.size);
+        if (!eol) return set_error(SNAPB200_ERR_IO, "Genome: no header line");
+        std::string line(gbeg, eol);
         if (sscanf(line.c_str(), "%u %u", &n_bases, &n_pieces) != 2) return set_error(SNAPB200_ERR_IO, "Genome: bad header");
-        gp = eol + 1;
+        gp = (size_t)(eol - gbeg) + 1;
     }
     std::vector<uint32_t> pieces(n_pieces);
     std::vector<std::string> names;
     for (unsigned i = 0; i < n_pieces; i++) {
-        size_t eol = std::find(genome.begin() + gp, genome.end(), '\n') - genome.begin();
-        if (eol >= genome.size()) return set_error(SNAPB200_ERR_IO, "Genome: truncated piece table");
-        std::string line(genome.begin() + gp, genome.begin() + eol);
+        const char *eol = gp < genome.size ? (const char *)memchr(gbeg + gp, '\n', genome.size - gp) : nullptr;
+        if (!eol) return set_error(SNAPB200_ERR_IO, "Genome: truncated piece table");
+        std::string line(gbeg + gp, eol);
         pieces[i] = (uint32_t)atoi(line.c_str());
         size_t sp = line.find(' ');
         names.push_back(sp == std::string::npos ? std::string("piece") + std::to_string(i) : line.substr(sp + 1));
-        gp = eol + 1;
+        gp = (size_t)(eol - gbeg) + 1;
     }
-    if (gp + n_bases > genome.size()) return set_error(SNAPB200_ERR_IO, "Genome: %u bases expected", n_bases);
-    int rc = make_index(device, seed_len, padding, n_tables, sizes.data(), entries.data(), (const uint32_t *)ovf.data(), overflow_words,
-                        (const uint8_t *)genome.data() + gp, n_bases, pieces.data(), n_pieces, out);
+    if (gp + n_bases > genome.size) return set_error(SNAPB200_ERR_IO, "Genome: %u bases expected", n_bases);
+    (void)gend;
+    // the tables go table by table from the mapping to their place in one device allocation, which make_index adopts (and frees
+    // if it fails after adopting; what it rejects before that is checked here first)
+    if (seed_len < 16 || seed_len > 25) return set_error(SNAPB200_ERR_ARG, "seed length %u unsupported (16..25, SeedSequencer.h)", seed_len);
+    {
+        uint32_t expect_tables = 1;
+        for (uint32_t i = 16; i < seed_len; i++) expect_tables *= 4;
+        if (n_tables != expect_tables) return set_error(SNAPB200_ERR_IO, "index has %u hash tables, seed length %u needs %u", n_tables, seed_len, expect_tables);
+    }
+    if (n_bases > 0xffffff00u) return set_error(SNAPB200_ERR_ARG, "genome of %u bases: locations must stay 256 below 2^32 (the reference stops at 0xfffffff0, GenomeIndex.cpp:372)", n_bases);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(SNAPB200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return set_error(SNAPB200_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    prefer_blocking_sync(device);
+    CUDA_TRY(cudaSetDevice(device));
+    HtEntry *d_tables = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_tables, std::max<uint64_t>(total, 1) * sizeof(HtEntry));
+    if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "cudaMalloc(%llu) for the hash tables failed: %s", (unsigned long long)(total * sizeof(HtEntry)), cudaGetErrorString(e));
+    uint64_t start = 0;
+    for (unsigned i = 0; i < n_tables; i++) {
+        e = cudaMemcpy(d_tables + start, hash.p + file_pos[i], sizes[i] * sizeof(HtEntry), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(d_tables); return set_error(SNAPB200_ERR_CUDA, "uploading hash table %u: %s", i, cudaGetErrorString(e)); }
+        start += sizes[i];
+    }
+    int rc = make_index(device, seed_len, padding, n_tables, sizes.data(), nullptr, (const uint32_t *)ovf.p, overflow_words,
+                        (const uint8_t *)genome.p + gp, n_bases, pieces.data(), n_pieces, out, d_tables, nullptr);
     if (!rc) (*out)->piece_names = names;
     return rc;
 }

@@ -1,5 +1,5 @@
-// gtf_tables.h -- the annotation as flat tables for the device AlignmentFilter (row f3 groundwork; host code, included by nothing
-// in the library yet).  Restates what GTFReader::Load / Parse / GTFGene::Process / GTFTranscript::Process leave behind
+// gtf_tables.h -- the annotation as flat tables for the device AlignmentFilter (row f3; host code, used by
+// snapb200_annotation_open in filter_api.inl).  Restates what GTFReader::Load / Parse / GTFGene::Process / GTFTranscript::Process leave behind
 // (SNAPLib/GTFReader.cpp:646-713, 857-872, 972-1019, 1245-1361) for the parts the filter reads: per transcript its chromosome, gene,
 // extent and the exon / intron list GenomicPosition walks; per gene its chromosome and extent.  The reference's behaviour is kept where
 // it decides results, including what looks like accidents.

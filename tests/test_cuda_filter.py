@@ -159,3 +159,71 @@ def test_rna_batch_is_the_pair_loop_of_the_reference(ref, cuda, ws):
     assert cuda.rna_batch_wait(objs[1])["n"] == 0
     for h in objs:
         cuda.rna_batch_destroy(h)
+
+
+def test_cuda_filter_fuzz_against_the_serial_specification(cuda, ws, ref):
+    """The warp schedule of filter_warp.cuh against the serial specification it parallelises (flt_filter_pair of filterfmt.h, run on
+    the host by tests/hostsim and verified against the reference by tests/test_filter_oracle.py): random pairs with up to 600 hits
+    per end over all transcripts, few distinct scores (ties everywhere), repeated places -- lists far longer than a warp, classes of
+    up to tens of thousands of combinations, so every strided loop, the rank sort, the ordered compaction and the introsort path run
+    many times.  Pairs either side reports as too large for its scratch are compared only where both decided."""
+    import ctypes as C
+    import subprocess
+    from snap_rnaseq_b200 import _abi as A
+    from test_filter_oracle import FLT_EVENT, FLT_RESULT, flat_tables
+    w = ws
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(w["gtf"].encode(), os.path.join(w["d"], "fuzz").encode()))
+    assert lib.ref_gtf_export(g, os.path.join(w["d"], "gtf_fuzz.tsv").encode()) == 0
+    T, keep = flat_tables(os.path.join(w["d"], "gtf_fuzz.tsv"), w["gdir"], w["tdir"])
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    n, mh = 240, F.MAX_HITS_TO_GET
+    (b0, b1), _ = F.reads(w["contigs"], w["d"], n=n, seed=31)
+    rng = np.random.default_rng(9)
+    tb = keep["tpiece_begin"].astype(np.int64)
+    tlen = np.diff(np.append(tb, tb[-1] + 3000))
+    pb = keep["piece_begin"].astype(np.int64)
+    hits = []
+    for e in range(2):
+        cnt, loc, rcs, sc = np.zeros(n, np.int32), np.zeros((n, mh), np.uint32), np.zeros((n, mh), np.uint8), np.zeros((n, mh), np.int32)
+        for i in range(n):
+            k = int(rng.choice([0, 1, 3, 20, 70, 200, 600]))
+            p = rng.integers(1, len(tb), size=k)
+            places = (tb[p] + (rng.random(k) * np.maximum(1, tlen[p] - 250)).astype(np.int64)).astype(np.uint32)
+            if k > 4:  # repeated places with other scores / strands: HashAlignment's replace rule
+                places[rng.integers(0, k, size=k // 4)] = places[rng.integers(0, k, size=k // 4)]
+            cnt[i], loc[i, :k], rcs[i, :k], sc[i, :k] = k, places, rng.integers(0, 2, size=k), rng.integers(0, int(rng.choice([2, 4, 17])), size=k)
+        hits.append((cnt, loc, rcs, sc))
+    res_in = np.zeros(n, A.PAIRED_RESULT)
+    for e in range(2):
+        res_in["location"][:, e] = np.where(rng.random(n) < 0.85, pb[rng.integers(1, len(pb), size=n)] + rng.integers(0, 150000, size=n), 0xFFFFFFFF)
+        res_in["score"][:, e], res_in["mapq"][:, e] = rng.integers(0, 17, size=n), rng.integers(0, 71, size=n)
+        res_in["direction"][:, e], res_in["status"][:, e] = rng.integers(0, 2, size=n), rng.integers(0, 3, size=n)
+    ch = [cuda.characterize(w["hg"], A.single_defaults(max_hits=300, num_seeds=12), b) for b in (b0, b1)]
+    prm = A.FilterParams(1000, 0, 2, 15, mh)
+    res, ev, needs_host = cuda.filter_paired(w["ann"], prm, np.diff(b0.offsets), np.diff(b1.offsets), hits[0], hits[1], res_in, ch[0], ch[1])
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+    p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+    lens0, lens1 = np.diff(b0.offsets), np.diff(b1.offsets)
+    (n0, l0, r0, s0), (n1, l1, r1, s1) = hits
+    compared = sorted_path = 0
+    for i in range(n):
+        want, wev = np.zeros(1, FLT_RESULT), np.zeros(1, FLT_EVENT)
+        rc = hs.hostsim_filter_pair_flat(C.byref(T), C.c_uint(int(lens0[i])), C.c_uint(int(lens1[i])), C.c_uint(15), C.c_uint(1000), C.c_uint(2), C.c_int(0),
+                                         C.c_int(int(n0[i])), A.p32u(l0[i]), A.p8(r0[i]), A.p32i(s0[i]), C.c_int(int(n1[i])), A.p32u(l1[i]), A.p8(r1[i]),
+                                         A.p32i(s1[i]), C.c_void_p(res_in[i:i + 1].ctypes.data), p64(ch[0][0]), A.p32u(ch[0][1]), p16(ch[0][2]), p64(ch[1][0]),
+                                         A.p32u(ch[1][1]), p16(ch[1][2]), C.c_uint(i), C.c_uint(1001), C.c_uint(1 << 20), C.c_uint(1 << 16),
+                                         C.c_void_p(want.ctypes.data), C.c_void_p(wev.ctypes.data))
+        if rc != 0 or needs_host[i]:
+            continue
+        compared += 1
+        sorted_path += int(n0[i]) * int(n1[i]) > 64
+        for f in FIELDS:
+            assert np.array_equal(want[f][0], res[f][i]), (i, f, int(n0[i]), int(n1[i]), want[0], res[i])
+        for f in FLT_EVENT.names:
+            assert np.array_equal(wev[f][0], ev[f][i]), (i, f, wev[0], ev[i])
+    assert compared > 0.6 * n and sorted_path > 40, (compared, sorted_path, int(needs_host.sum()))

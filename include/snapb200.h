@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SNAPB200_ABI_VERSION 2
+#define SNAPB200_ABI_VERSION 3
 
 enum {
     SNAPB200_OK = 0,
@@ -256,15 +256,17 @@ int snapb200_fastq_parse(int device, const uint8_t *text, uint64_t n_bytes, int 
 int snapb200_fastq_record_start(const uint8_t *text, uint64_t n_bytes, uint64_t *offset);
 
 /* The arguments of ReadWriter::writeRead / the per-end fields of PairedAlignmentResult that SAM output uses
- * (SNAPLib/Read.h:171, SNAPLib/PairedEndAligner.h:31-56).  skip != 0: emit nothing for this read (a transcriptome
- * alignment, whose CIGAR needs the GTF: LandauVishkinWithCigar::insertSpliceJunctions stays on the host). */
+ * (SNAPLib/Read.h:171, SNAPLib/PairedEndAligner.h:31-56).  skip != 0: emit nothing for this read.  is_transcriptome != 0: the
+ * alignment was found in the transcriptome at tlocation (location is its genome position, as AlignmentFilter reports it); only
+ * snapb200_sam_batch_rna takes such alignments. */
 typedef struct {
     uint32_t location;
     int32_t mapq;
     uint8_t status;    /* AlignmentResult */
     uint8_t direction; /* Direction */
     uint8_t skip;
-    uint8_t pad;
+    uint8_t is_transcriptome; /* PairedAlignmentResult::isTranscriptome / writeRead's isTranscriptome */
+    uint32_t tlocation;       /* PairedAlignmentResult::tlocation */
 } snapb200_sam_alignment;
 
 /* Replaces SimpleReadWriter::writeRead / writePair (SNAPLib/ReadWriter.cpp:90-217) over SAMFormat::writeRead
@@ -280,6 +282,19 @@ int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads *reads0, co
                        const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m,
                        const char *read_group, char *out, uint64_t out_capacity, uint64_t *line_offsets);
 
+/* (opened by snapb200_annotation_open, below) */
+typedef struct snapb200_annotation snapb200_annotation; /* exon / gene tables of a GTF in HBM, for a genome + transcriptome index pair */
+
+/* The same for RNA mode: alignments with is_transcriptome set get their CIGAR from the transcriptome text at tlocation with the
+ * splice junctions of their transcript inserted (SAMFormat::writeRead's transcriptome branch, SNAPLib/SAM.cpp:1046-1061, over
+ * LandauVishkinWithCigar::insertSpliceJunctions, SNAPLib/LandauVishkin.cpp:119-250, and GTFTranscript::Junctions,
+ * SNAPLib/GTFReader.cpp:1109-1139).  genome and transcriptome must be the pair the annotation was opened with and live on its
+ * device.  A spliced CIGAR longer than 511 characters: SNAPB200_ERR_LIMIT. */
+int snapb200_sam_batch_rna(snapb200_annotation *annotation, snapb200_index *genome, snapb200_index *transcriptome,
+                           const snapb200_sam_reads *reads0, const snapb200_sam_reads *reads1, const snapb200_sam_alignment *aln0,
+                           const snapb200_sam_alignment *aln1, int use_m, const char *read_group, char *out, uint64_t out_capacity,
+                           uint64_t *line_offsets);
+
 /* CUDA-event times (ms) of the kernels of the last snapb200_fastq_parse / snapb200_sam_batch call made by this thread
  * (no copies), for the streaming roofline of these two stages. */
 int snapb200_io_last_kernel_ms(float *fastq_ms, float *sam_ms);
@@ -288,7 +303,6 @@ int snapb200_io_last_kernel_ms(float *fastq_ms, float *sam_ms);
  * One warp per pair (snap_rnaseq_b200/csrc/filter_warp.cuh) over the per-element rules of csrc/filterfmt.h, which are verified on
  * the host against the reference's AlignmentFilter.  The annotation is loaded with the reference's GTFReader semantics
  * (csrc/gtf_tables.h). */
-typedef struct snapb200_annotation snapb200_annotation; /* exon / gene tables of a GTF in HBM, for a genome + transcriptome index pair */
 
 /* Replaces GTFReader::Load (SNAPLib/GTFReader.cpp:1245-1361) for what the filter reads.  Every transcriptome piece must be a
  * transcript of the annotation and every transcript's chromosome a piece of the genome (the reference exits otherwise).  The handle

@@ -603,13 +603,14 @@ static void make_read(Read *r, const snapb200_sam_reads *b, unsigned i, const ch
 
 // SimpleReadWriter::writeRead / writePair (SNAPLib/ReadWriter.cpp:90-217) through the reference's own ReadWriterSupplier and
 // file DataWriter into `path` (no header).  Reads with skip set are not written.
-int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1, const snapb200_sam_alignment *a0,
-                  const snapb200_sam_alignment *a1, int use_m, const char *read_group, const char *path)
+int ref_sam_batch_rna(void *h, void *h_transcriptome, void *gtf, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1,
+                      const snapb200_sam_alignment *a0, const snapb200_sam_alignment *a1, int use_m, const char *read_group, const char *path)
 {
     GenomeIndex *idx = (GenomeIndex *)h;
     const Genome *genome = idx->getGenome();
+    const Genome *transcriptome = h_transcriptome ? ((GenomeIndex *)h_transcriptome)->getGenome() : NULL;
     DataWriterSupplier *dws = DataWriterSupplier::create(path);
-    ReadWriterSupplier *rws = ReadWriterSupplier::create(FileFormat::SAM[use_m ? 1 : 0], dws, genome, NULL, NULL);
+    ReadWriterSupplier *rws = ReadWriterSupplier::create(FileFormat::SAM[use_m ? 1 : 0], dws, genome, transcriptome, (const GTFReader *)gtf);
     ReadWriter *w = rws->getWriter();
     double t0 = now_s();
     for (unsigned i = 0; i < r0->n; i++) {
@@ -617,8 +618,10 @@ int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_read
         make_read(&read0, r0, i, read_group);
         if (!r1) {
             if (a0[i].skip) continue;
-            w->writeRead(&read0, (AlignmentResult)a0[i].status, a0[i].mapq, a0[i].location, (Direction)a0[i].direction, false, 0);
+            w->writeRead(&read0, (AlignmentResult)a0[i].status, a0[i].mapq, a0[i].location, (Direction)a0[i].direction, a0[i].is_transcriptome != 0,
+                         a0[i].tlocation);
         } else {
+            if (a0[i].skip || a1[i].skip) continue;
             make_read(&read1, r1, i, read_group);
             PairedAlignmentResult res;
             memset(&res, 0, sizeof(res));
@@ -628,8 +631,8 @@ int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_read
                 res.location[e] = a[e]->location;
                 res.direction[e] = (Direction)a[e]->direction;
                 res.mapq[e] = a[e]->mapq;
-                res.isTranscriptome[e] = false;
-                res.tlocation[e] = 0;
+                res.isTranscriptome[e] = a[e]->is_transcriptome != 0;
+                res.tlocation[e] = a[e]->tlocation;
             }
             w->writePair(&read0, &read1, &res);
         }
@@ -640,6 +643,21 @@ int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_read
     rws->close();
     delete rws;
     return 0;
+}
+
+int ref_sam_batch(void *h, const snapb200_sam_reads *r0, const snapb200_sam_reads *r1, const snapb200_sam_alignment *a0,
+                  const snapb200_sam_alignment *a1, int use_m, const char *read_group, const char *path)
+{
+    return ref_sam_batch_rna(h, NULL, NULL, r0, r1, a0, a1, use_m, read_group, path);
+}
+
+// LandauVishkinWithCigar::insertSpliceJunctions (SNAPLib/LandauVishkin.cpp:119-250) on a token list (count, operator, count, ...) as
+// computeCigarString leaves it; the string goes to out.  Returns what the reference returns (the number of operators, -2: no space).
+int ref_splice_cigar(void *gtf, const unsigned *tokens, unsigned n_tokens, const char *transcript_id, unsigned pos, char *out, int out_len)
+{
+    LandauVishkinWithCigar lv;
+    std::vector<unsigned> t(tokens, tokens + n_tokens);
+    return lv.insertSpliceJunctions((const GTFReader *)gtf, t, std::string(transcript_id), pos, out, out_len);
 }
 
 // ---- row f3 (next): AlignmentFilter as the paired run loop drives it -------------------------------------------------------

@@ -169,8 +169,8 @@ class SamReadsStruct(C.Structure):
 
 
 SAM_ALIGNMENT = np.dtype([("location", "<u4"), ("mapq", "<i4"), ("status", "u1"), ("direction", "u1"), ("skip", "u1"),
-                          ("pad", "u1")], align=True)
-assert SAM_ALIGNMENT.itemsize == 12
+                          ("is_transcriptome", "u1"), ("tlocation", "<u4")], align=True)
+assert SAM_ALIGNMENT.itemsize == 16
 
 
 def p16u(a):

@@ -209,9 +209,11 @@ class BatchLib:
         self._check(self.fn("fastq_record_start")(A.p8(t), C.c_uint64(len(raw)), C.byref(off)), "fastq_record_start")
         return int(off.value)
 
-    def sam(self, handle, reads0, reads1, aln0, aln1, use_m=False, read_group=None, out=None):
+    def sam(self, handle, reads0, reads1, aln0, aln1, use_m=False, read_group=None, out=None, rna=None):
         """SimpleReadWriter::writeRead / writePair over SAMFormat::writeRead for a batch -> (SAM bytes, line_offsets).
-        out: a uint8 array to write into with ONE call (returns a view of it); otherwise measure first, then write."""
+        out: a uint8 array to write into with ONE call (returns a view of it); otherwise measure first, then write.
+        rna = (annotation handle [the reference: its GTFReader], transcriptome index handle): alignments may be transcriptome ones
+        (snapb200_sam_batch_rna)."""
         a0 = np.ascontiguousarray(aln0, A.SAM_ALIGNMENT)
         a1 = np.ascontiguousarray(aln1, A.SAM_ALIGNMENT) if reads1 is not None else None
         n_lines = reads0.n * (2 if reads1 is not None else 1)
@@ -224,8 +226,12 @@ class BatchLib:
             fd, path = tempfile.mkstemp(suffix=".sam")
             os.close(fd)
             try:
-                self._check(self.fn("sam_batch")(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg,
-                                                 path.encode()), "sam_batch")
+                if rna is not None:
+                    self._check(self.fn("sam_batch_rna")(handle, rna[1], rna[0], reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)),
+                                                         rg, path.encode()), "sam_batch_rna")
+                else:
+                    self._check(self.fn("sam_batch")(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg,
+                                                     path.encode()), "sam_batch")
                 with open(path, "rb") as f:
                     return f.read(), None
             finally:
@@ -233,6 +239,9 @@ class BatchLib:
         lo = np.zeros(n_lines + 1, np.uint64)
         plo = lo.ctypes.data_as(C.POINTER(C.c_uint64))
         f = self.fn("sam_batch")
+        if rna is not None:
+            g = self.fn("sam_batch_rna")
+            f = lambda h, *rest: g(rna[0], h, rna[1], *rest)
         if out is not None:
             self._check(f(handle, reads0.byref(), r1, a0.ctypes.data_as(C.c_void_p), p1, C.c_int(int(use_m)), rg, out.ctypes.data_as(C.c_char_p),
                           C.c_uint64(out.size), plo), "sam_batch")

@@ -67,6 +67,19 @@ extern "C" void snapb200_annotation_close(snapb200_annotation *a)
     delete a;
 }
 
+extern "C" int snapb200_sam_batch_rna(snapb200_annotation *ann, snapb200_index *genome, snapb200_index *transcriptome, const snapb200_sam_reads *reads0,
+                                      const snapb200_sam_reads *reads1, const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m,
+                                      const char *read_group, char *out, uint64_t out_capacity, uint64_t *line_offsets)
+{
+    if (!ann || !genome || !transcriptome) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (genome->device != ann->device || transcriptome->device != ann->device)
+        return set_error(SNAPB200_ERR_ARG, "the annotation lives on device %d, the indices on %d and %d", ann->device, genome->device, transcriptome->device);
+    if (genome->dev.n_pieces != ann->t.n_pieces || transcriptome->dev.n_pieces != ann->t.n_tpieces)
+        return set_error(SNAPB200_ERR_ARG, "not the index pair the annotation was opened with (%u / %u pieces against %u / %u)", genome->dev.n_pieces,
+                         transcriptome->dev.n_pieces, ann->t.n_pieces, ann->t.n_tpieces);
+    return sam_batch_impl(genome, &transcriptome->dev, &ann->t, reads0, reads1, aln0, aln1, use_m, read_group, out, out_capacity, line_offsets);
+}
+
 extern "C" uint32_t snapb200_annotation_transcript_count(const snapb200_annotation *a) { return a ? (uint32_t)a->transcript_ids.size() : 0; }
 extern "C" const char *snapb200_annotation_transcript_id(const snapb200_annotation *a, uint32_t i)
 {

@@ -199,7 +199,7 @@ static int sam_names(snapb200_index *x, SamNames *out)
     return 0;
 }
 
-static int sam_validate(const snapb200_sam_reads *r, const snapb200_sam_alignment *al, uint32_t *max_len)
+static int sam_validate(const snapb200_sam_reads *r, const snapb200_sam_alignment *al, uint32_t *max_len, bool rna)
 {
     if (!r) return set_error(SNAPB200_ERR_ARG, "null reads");
     if (r->n && (!r->offsets || !r->bases || !r->quals || !r->front_clip || !r->clipped_len || !r->id_offsets || !r->ids || !al))
@@ -210,6 +210,8 @@ static int sam_validate(const snapb200_sam_reads *r, const snapb200_sam_alignmen
         const uint32_t len = r->offsets[i + 1] - r->offsets[i];
         if ((uint32_t)r->front_clip[i] + r->clipped_len[i] > len) return set_error(SNAPB200_ERR_ARG, "read %u: clipping exceeds the read", i);
         m = std::max(m, len);
+        if (!rna && al[i].is_transcriptome && !al[i].skip)
+            return set_error(SNAPB200_ERR_ARG, "read %u is a transcriptome alignment: its CIGAR needs the annotation, use snapb200_sam_batch_rna", i);
     }
     // SAMFormat::writeRead fails for reads longer than its MAX_READ buffers (SAM.cpp:1000-1001, 868-870)
     if (m > SNAPB200_MAX_READ_LENGTH) return set_error(SNAPB200_ERR_ARG, "read of %u bases exceeds MAX_READ_LENGTH %d", m, SNAPB200_MAX_READ_LENGTH);
@@ -217,17 +219,18 @@ static int sam_validate(const snapb200_sam_reads *r, const snapb200_sam_alignmen
     return 0;
 }
 
-extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads *reads0, const snapb200_sam_reads *reads1,
-                                  const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m, const char *read_group,
-                                  char *out, uint64_t out_capacity, uint64_t *line_offsets)
+// tix / tables: the transcriptome and the annotation of snapb200_sam_batch_rna (filter_api.inl), NULL for genome alignments only
+static int sam_batch_impl(snapb200_index *idx, const DevIndex *tix, const FltTables *tables, const snapb200_sam_reads *reads0,
+                          const snapb200_sam_reads *reads1, const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m,
+                          const char *read_group, char *out, uint64_t out_capacity, uint64_t *line_offsets)
 {
     if (!idx || !reads0 || !line_offsets) return set_error(SNAPB200_ERR_ARG, "null argument");
-    const bool paired = reads1 != nullptr;
+    const bool paired = reads1 != nullptr, rna = tables != nullptr;
     if (paired && (reads1->n != reads0->n)) return set_error(SNAPB200_ERR_ARG, "mate batches differ in size (%u vs %u)", reads0->n, reads1->n);
     uint32_t max_len = 0;
-    int rc = sam_validate(reads0, aln0, &max_len);
+    int rc = sam_validate(reads0, aln0, &max_len, rna);
     if (rc) return rc;
-    if (paired && (rc = sam_validate(reads1, aln1, &max_len))) return rc;
+    if (paired && (rc = sam_validate(reads1, aln1, &max_len, rna))) return rc;
     const uint32_t n = reads0->n;
     if (paired && n > 0x7fffffffu) return set_error(SNAPB200_ERR_ARG, "too many pairs");
     const uint32_t n_lines = paired ? 2 * n : n;
@@ -240,6 +243,9 @@ extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads 
     memset(&a, 0, sizeof(a));
     if ((rc = sam_names(idx, &a.names))) return rc;
     a.ix = idx->dev;
+    a.rna = rna;
+    a.cigar_stride = rna ? SAM_SPLICED_CIGAR_STRIDE : SAM_CIGAR_STRIDE;
+    if (rna) { a.tix = *tix; a.tables = *tables; }
     const snapb200_sam_reads *rs[2] = {reads0, reads1};
     const snapb200_sam_alignment *as[2] = {aln0, aln1};
     for (int e = 0; e < (paired ? 2 : 1); e++) {
@@ -268,7 +274,7 @@ extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads 
     const size_t rg_len = read_group ? strlen(read_group) : 0;
     if ((rc = io.rg.ensure(rg_len + 16))) return rc;
     if (rg_len) CUDA_TRY(cudaMemcpyAsync(io.rg.p, read_group, rg_len, cudaMemcpyHostToDevice, io.stream));
-    if ((rc = io.cigars.ensure((size_t)n_lines * SAM_CIGAR_STRIDE)) || (rc = io.lines.ensure((size_t)n_lines * sizeof(SamLine))) ||
+    if ((rc = io.cigars.ensure((size_t)n_lines * a.cigar_stride)) || (rc = io.lines.ensure((size_t)n_lines * sizeof(SamLine))) ||
         (rc = io.line_len.ensure((size_t)(n_lines + 1) * 8)) || (rc = io.line_off.ensure((size_t)(n_lines + 1) * 8)) || (rc = io.err.ensure(sizeof(Counters))))
         return rc;
     a.n_lines = n_lines; a.in.paired = paired; a.use_m = use_m; a.rg = io.rg.as<char>(); a.rg_len = (uint32_t)rg_len;
@@ -290,6 +296,13 @@ extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads 
     float ms0 = 0, ms1 = 0;
     cudaEventElapsedTime(&ms0, io.ev[0], io.ev[1]);
     io.sam_ms = ms0;
+    if (rna) {
+        Counters c;
+        CUDA_TRY(cudaMemcpy(&c, io.err.p, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c.n_limit)
+            return set_error(SNAPB200_ERR_LIMIT, "%u spliced CIGAR strings exceed %d characters (the last one on line %u)", c.n_limit, SAM_SPLICED_CIGAR_STRIDE - 1,
+                             c.pad[0] - 1);
+    }
     if (!out) return 0;
     const uint64_t total = line_offsets[n_lines];
     if (total > out_capacity) return set_error(SNAPB200_ERR_ARG, "SAM text needs %llu bytes, out_capacity is %llu", (unsigned long long)total, (unsigned long long)out_capacity);
@@ -305,4 +318,11 @@ extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads 
     cudaEventElapsedTime(&ms1, io.ev[2], io.ev[3]);
     io.sam_ms = ms0 + ms1;
     return 0;
+}
+
+extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads *reads0, const snapb200_sam_reads *reads1,
+                                  const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m, const char *read_group,
+                                  char *out, uint64_t out_capacity, uint64_t *line_offsets)
+{
+    return sam_batch_impl(idx, nullptr, nullptr, reads0, reads1, aln0, aln1, use_m, read_group, out, out_capacity, line_offsets);
 }

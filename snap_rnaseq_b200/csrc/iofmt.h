@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "../../include/snapb200.h"
+#include "filterfmt.h"  // FltTables: the exon / intron lists of the transcripts, for the CIGAR of a transcriptome alignment
 
 #ifdef __CUDACC__
 #define SNAP_HD __host__ __device__ __forceinline__
@@ -144,6 +145,7 @@ SNAP_HD uint8_t fq_upper(uint8_t c) { return (c >= 0x61 && c <= 0x7a) ? (uint8_t
 #define SAM_NAME_EQUAL (-2)  // "="
 #define SAM_INVALID_LOC 0xffffffffu
 #define SAM_CIGAR_STRIDE 256  // >= 61 runs of at most 4 characters (k = MAX_K-1 = 30 edits) + NUL
+#define SAM_SPLICED_CIGAR_STRIDE 512  // the same with soft clips and splice junctions inserted; a longer one is reported, not truncated
 
 struct SamEnd {          // what getSAMData reads of one Read and its alignment
     uint32_t full_len;   // getUnclippedLength
@@ -311,11 +313,89 @@ struct SamLine {  // what the measuring pass leaves for the writing pass
     uint32_t qual_len;
     int32_t edit_distance;  // -1 unmapped / CIGAR "*"
     uint32_t cigar_len;     // of the LV string, without soft clips; 0 => "*"
+    uint32_t spliced;       // a transcriptome alignment: the string is the whole field as insertSpliceJunctions leaves it (clips included;
+                            // empty when the CIGAR could not be computed, SAM.cpp:1046-1061)
 };
+
+// One "%d%c" of writeCigar (LandauVishkin.cpp:27-63): a count <= 0 writes nothing.  false: out of space.
+SNAP_HD bool sam_cigar_put(char *out, uint32_t cap, uint32_t *n, int count, char op)
+{
+    if (count <= 0) return true;
+    const int d = sam_digits_u64((unsigned long long)count);
+    if (*n + (uint32_t)d + 1 > cap) return false;
+    sam_put_u64(out + *n, (unsigned long long)count);
+    out[*n + d] = op;
+    *n += (uint32_t)d + 1;
+    return true;
+}
+
+// LandauVishkinWithCigar::insertSpliceJunctions (SNAPLib/LandauVishkin.cpp:119-250) over GTFTranscript::Junctions
+// (SNAPLib/GTFReader.cpp:1109-1139), for the tokens computeCigarString leaves (SAM.cpp:1206-1219: the soft clip before, the runs of the
+// LV string `lv`, the soft clip after).  tr = the transcript of the transcriptome piece the alignment lies in, pos = its 1-based
+// position in that transcript.  Kept as the reference does it, including: a junction is reported for an exon that ends exactly where
+// the run ends (so a CIGAR can end in an N run); 'D' runs advance through the transcript, 'I' and 'S' do not; an intron of length
+// <= 0 (abutting or overlapping exons) splits the run but prints nothing.  Returns the length written to out, -1 if cap is too small.
+SNAP_HD int sam_splice_cigar(const FltTables &t, int tr, uint32_t pos, const char *lv, uint32_t lv_len, uint32_t clip_before, uint32_t clip_after,
+                             char *out, uint32_t cap)
+{
+    uint32_t n = 0, prev = pos, current = pos, p = 0;
+    int stage = 0;  // 0 the clip before, 1 the runs of lv, 2 the clip after
+    for (;;) {
+        uint32_t length;
+        char op;
+        if (stage == 0) {
+            stage = 1;
+            if (!clip_before) continue;
+            length = clip_before; op = 'S';
+        } else if (stage == 1) {
+            if (p >= lv_len) { stage = 2; continue; }
+            length = 0;
+            while (p < lv_len && lv[p] >= '0' && lv[p] <= '9') length = length * 10 + (uint32_t)(lv[p++] - '0');
+            op = p < lv_len ? lv[p++] : 'M';
+        } else if (stage == 2) {
+            stage = 3;
+            if (!clip_after) continue;
+            length = clip_after; op = 'S';
+        } else {
+            break;
+        }
+        if (op == 'I' || op == 'S') {
+            if (!sam_cigar_put(out, cap, &n, (int)length, op)) return -1;
+            continue;
+        }
+        current += length - 1;
+        uint32_t remainder = length;
+        if (tr >= 0) {
+            const uint32_t query = prev, end_pos = prev + length;  // Junctions(prev, length): prev moves below, the query does not
+            uint32_t cur_pos = 0;
+            for (uint32_t k = t.t_feat_first[tr]; k < t.t_feat_first[tr + 1]; k++) {
+                const uint32_t type = t.f_type[k], flen = t.f_end[k] - t.f_start[k] + 1;
+                if (type == FLT_EXON) cur_pos += flen;
+                if (query > cur_pos) continue;
+                if (type == FLT_EXON) {
+                    if (cur_pos >= end_pos) break;
+                } else if (type == 2) {  // INTRON
+                    const uint32_t first = cur_pos + 1;
+                    if (first == pos) continue;
+                    const int step = (int)(first - prev);
+                    remainder -= (uint32_t)step;
+                    if (step > 0 && !sam_cigar_put(out, cap, &n, step, op)) return -1;
+                    if (!sam_cigar_put(out, cap, &n, (int)flen, 'N')) return -1;
+                    prev += (uint32_t)step;
+                }
+            }
+        }
+        if (!sam_cigar_put(out, cap, &n, (int)remainder, op)) return -1;  // the whole run when no junction was found
+        current += 1;
+        prev = current;
+    }
+    return (int)n;
+}
 
 // The CIGAR field with soft clips (computeCigarString, SAM.cpp:1206-1222) -- length and bytes
 SNAP_HD uint32_t sam_cigar_field_len(const SamFields &f, const SamLine &ln)
 {
+    if (f.mapped && ln.spliced) return ln.cigar_len;
     if (!f.mapped || ln.cigar_len == 0) return 1;
     uint32_t n = ln.cigar_len;
     if (f.clip_before > 0) n += sam_digits_u64(f.clip_before) + 1;
@@ -352,7 +432,10 @@ SNAP_HD char *sam_put_prefix(char *p, const uint8_t *id, const SamFields &f, con
     p = sam_put_name(p, nm, f.rname); *p++ = '\t';
     p = sam_put_u64(p, f.pos); *p++ = '\t';
     p = sam_put_i64(p, f.mapq); *p++ = '\t';
-    if (!f.mapped || ln.cigar_len == 0) {
+    if (f.mapped && ln.spliced) {
+        for (uint32_t i = 0; i < ln.cigar_len; i++) p[i] = cigar[i];
+        p += ln.cigar_len;
+    } else if (!f.mapped || ln.cigar_len == 0) {
         *p++ = '*';
     } else {
         if (f.clip_before > 0) { p = sam_put_u64(p, f.clip_before); *p++ = 'S'; }

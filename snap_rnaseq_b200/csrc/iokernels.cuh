@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(256) fq_copy_kernel(const FqCopyArgs a)
 // ---- SAM ---------------------------------------------------------------------------------------------------------
 struct SamArgs {
     DevIndex ix;
+    DevIndex tix;       // the transcriptome (rna != 0): the text a transcriptome alignment's CIGAR is computed against
+    FltTables tables;   // the annotation (rna != 0): transcript of a transcriptome piece, its exon / intron list
+    int rna;
+    uint32_t cigar_stride;  // SAM_CIGAR_STRIDE, SAM_SPLICED_CIGAR_STRIDE when rna
     SamNames names;
     SamInputs in;
     uint32_t n_lines;
@@ -163,7 +167,7 @@ struct SamArgs {
     const char *rg;
     uint32_t rg_len;
     uint32_t rl;  // shared-memory row for a staged read
-    char *cigars;  // [n_lines][SAM_CIGAR_STRIDE]
+    char *cigars;  // [n_lines][cigar_stride]
     SamLine *lines;
     uint64_t *line_len;  // [n_lines + 1], last 0: scanned into line offsets
     const uint64_t *line_off;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
         if (line >= a.n_lines) break;
         const SamWho w = sam_who(a.in, line);
         SamLine ln;
-        ln.qname_len = ln.seq_len = ln.qual_len = ln.cigar_len = 0;
+        ln.qname_len = ln.seq_len = ln.qual_len = ln.cigar_len = ln.spliced = 0;
         ln.edit_distance = -1;
         if (w.skip) {
             if (lane == 0) { a.lines[line] = ln; a.line_len[line] = 0; }
@@ -231,30 +235,58 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
         }
         ln.seq_len = seq_len;
         ln.qual_len = qual_len;
-        // CIGAR (computeCigarString, SAM.cpp:1159-1204): the clipped read, reverse-complemented for RC, against the genome
-        char *cig = a.cigars + (size_t)line * SAM_CIGAR_STRIDE;
+        // CIGAR (computeCigarString, SAM.cpp:1159-1204): the clipped read, reverse-complemented for RC, against the genome -- or, for
+        // a transcriptome alignment, against the transcriptome at tlocation, with the junctions of its transcript inserted
+        // (SAM.cpp:1046-1061)
+        char *cig = a.cigars + (size_t)line * a.cigar_stride;
         if (f.mapped) {
-            const uint32_t len = w.me.clipped_len, loc = w.me.location;
+            const snapb200_sam_alignment al = a.in.aln[w.e][w.i];
+            const bool spliced = a.rna && al.is_transcriptome != 0;
+            const DevIndex &ix = spliced ? a.tix : a.ix;
+            const uint32_t len = w.me.clipped_len, loc = spliced ? al.tlocation : w.me.location;
+            ln.spliced = spliced;
             if (lane == 0) cig[0] = 0;
             __syncwarp();
-            if (substring_ok(a.ix, loc, len)) {
+            int e = -1;
+            if (substring_ok(ix, loc, len)) {
                 const uint8_t *cb = bases + w.me.front_clip;
                 #pragma unroll 1
                 for (uint32_t j = lane; j < len; j += 32) P[j] = f.direction == 1 ? rc_base(cb[len - 1 - j]) : cb[j];
-                stage_window(a.ix, loc, len, W);
+                stage_window(ix, loc, len, W);
                 LvStr s;
                 s.p = P; s.ps = 1; s.plen = (int)len;
                 s.t = W + WIN_SLACK; s.ts = 1; s.tlen = (int)len;
                 s.t_lo = -WIN_SLACK; s.t_hi = (int)len + WIN_SLACK;
-                const int e = lv_cigar_warp(s, MAXK - 1, L, cig, SAM_CIGAR_STRIDE, a.use_m != 0);
+                e = lv_cigar_warp(s, MAXK - 1, L, cig, SAM_CIGAR_STRIDE, a.use_m != 0);
                 ln.edit_distance = e;  // -1 / -2: the reference prints "*" and NM:i:-1 / -2 (SAM.cpp:1196-1205)
                 if (e >= 0 && lane == 0) ln.cigar_len = sam_strlen(cig, SAM_CIGAR_STRIDE);
             }
             __syncwarp();
+            if (spliced) {
+                // the runs move to shared memory (the LV table is dead), the leader writes the spliced string over them in HBM; a
+                // CIGAR that could not be computed leaves no tokens, and the reference then prints an empty field
+                char *runs = (char *)L;
+                const uint32_t n_runs = __shfl_sync(FULL_MASK, e >= 0 ? ln.cigar_len : 0u, 0);
+                #pragma unroll 1
+                for (uint32_t j = lane; j < n_runs; j += 32) runs[j] = cig[j];
+                __syncwarp();
+                if (lane == 0) {
+                    int n = 0;
+                    if (e >= 0) {
+                        const int piece = flt_piece_at(a.tables.tpiece_begin, (int)a.tables.n_tpieces, loc);
+                        const int tr = piece >= 0 ? a.tables.tpiece_transcript[piece] : -1;
+                        n = sam_splice_cigar(a.tables, tr, loc - a.tables.tpiece_begin[piece < 0 ? 0 : piece] + 1, runs, n_runs, f.clip_before, f.clip_after,
+                                             cig, a.cigar_stride);
+                        if (n < 0) { atomicAdd(&a.ctr->n_limit, 1u); atomicMax(&a.ctr->pad[0], line + 1); ln.spliced = 2; n = 0; }
+                    }
+                    ln.cigar_len = (uint32_t)n;
+                }
+                __syncwarp();
+            }
         }
         if (lane == 0) {
             a.lines[line] = ln;
-            a.line_len[line] = sam_line_len(f, ln, a.names, a.rg_len);
+            a.line_len[line] = ln.spliced == 2 ? 0 : sam_line_len(f, ln, a.names, a.rg_len);  // 2: the spliced CIGAR does not fit its slot
         }
     }
 }
@@ -271,6 +303,7 @@ __global__ void __launch_bounds__(256) sam_write_kernel(const SamArgs a)
     const SamWho w = sam_who(a.in, line);
     if (w.skip) return;
     const SamLine ln = a.lines[line];
+    if (ln.spliced == 2) return;
     const SamReadsDev &rd = a.in.rd[w.e];
     const uint32_t off = rd.offsets[w.i];
     const SamFields f = sam_fields(a.ix.piece_begin, (int)a.ix.n_pieces, w.me, w.has_mate, w.first_in_pair, w.mate);
@@ -279,7 +312,7 @@ __global__ void __launch_bounds__(256) sam_write_kernel(const SamArgs a)
     // SEQ starts where the suffix, QUAL and SEQ end: everything after SEQ has a known length
     uint32_t tail = ln.seq_len + 1 + ln.qual_len + (a.rg_len ? 6 + a.rg_len : 0) + 10 + 6 + sam_digits_i64(ln.edit_distance) + 1;
     char *seq = dst + (total - tail);
-    if (lane == 0) sam_put_prefix(dst, rd.ids + rd.id_offsets[w.i], f, ln, a.names, a.cigars + (size_t)line * SAM_CIGAR_STRIDE);
+    if (lane == 0) sam_put_prefix(dst, rd.ids + rd.id_offsets[w.i], f, ln, a.names, a.cigars + (size_t)line * a.cigar_stride);
     sam_put_seq_qual(seq, rd.bases + off, rd.quals + off, w.me.full_len, f.direction, ln, lane, SAM_WRITE_LANES);
     if (lane == 1) sam_put_suffix(seq + ln.seq_len + 1 + ln.qual_len, ln, a.rg, a.rg_len);
 }

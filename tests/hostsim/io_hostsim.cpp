@@ -330,3 +330,10 @@ extern "C" long long hostsim_unaligned_splices(const FltTables *t, uint32_t read
     int kind = 0;
     return (long long)flt_unaligned_splices(*t, segs.data(), (uint32_t)n, read_len, seed_len, pair_index, &kind, out);
 }
+
+// ---- the CIGAR of a transcriptome alignment (iofmt.h: sam_splice_cigar) -----------------------------------------------------------
+extern "C" int hostsim_splice_cigar(const FltTables *t, int tr, uint32_t pos, const char *lv, uint32_t lv_len, uint32_t clip_before, uint32_t clip_after,
+                                    char *out, uint32_t cap)
+{
+    return sam_splice_cigar(*t, tr, pos, lv, lv_len, clip_before, clip_after, out, cap);
+}

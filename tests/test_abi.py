@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/snapb200.h but not exported"
     lib.snapb200_abi_version.restype = C.c_int
-    assert lib.snapb200_abi_version() == 2
+    assert lib.snapb200_abi_version() == 3
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -85,7 +85,8 @@ def test_io_struct_layouts_match_header(tmp_path):
         'printf("%zu %zu %zu %zu %zu\\n", sizeof(snapb200_filter_result), offsetof(snapb200_filter_result,status), sizeof(snapb200_filter_event),'
         ' offsetof(snapb200_filter_event,pos), sizeof(snapb200_filter_params));'
         'printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(snapb200_filter_result,aligned_as_pair), sizeof(snapb200_rna_params), offsetof(snapb200_rna_params,filter),'
-        ' sizeof(snapb200_rna_view), offsetof(snapb200_rna_view,seg_offsets), offsetof(snapb200_rna_view,device_ms));return 0;}\n')
+        ' sizeof(snapb200_rna_view), offsetof(snapb200_rna_view,seg_offsets), offsetof(snapb200_rna_view,device_ms));'
+        'printf("%zu %zu\\n", offsetof(snapb200_sam_alignment,is_transcriptome), offsetof(snapb200_sam_alignment,tlocation));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
@@ -94,6 +95,7 @@ def test_io_struct_layouts_match_header(tmp_path):
     assert got[3] == A.SAM_ALIGNMENT.itemsize
     assert got[4] == A.SAM_ALIGNMENT.fields["mapq"][1] and got[5] == A.SAM_ALIGNMENT.fields["status"][1]
     assert got[6] == A.SAM_ALIGNMENT.fields["skip"][1]
+    assert got[-2] == A.SAM_ALIGNMENT.fields["is_transcriptome"][1] and got[-1] == A.SAM_ALIGNMENT.fields["tlocation"][1]
     assert got[7] == A.FILTER_RESULT.itemsize and got[8] == A.FILTER_RESULT.fields["status"][1]
     assert got[9] == A.FILTER_EVENT.itemsize and got[10] == A.FILTER_EVENT.fields["pos"][1] and got[11] == C.sizeof(A.FilterParams)
     assert got[12] == A.FILTER_RESULT.fields["aligned_as_pair"][1]

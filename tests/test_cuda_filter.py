@@ -227,3 +227,61 @@ def test_cuda_filter_fuzz_against_the_serial_specification(cuda, ws, ref):
         for f in FLT_EVENT.names:
             assert np.array_equal(wev[f][0], ev[f][i]), (i, f, wev[0], ev[i])
     assert compared > 0.6 * n and sorted_path > 40, (compared, sorted_path, int(needs_host.sum()))
+
+
+def test_cuda_sam_of_transcriptome_alignments(ref, cuda, ws):
+    """snapb200_sam_batch_rna against SimpleReadWriter::writePair / writeRead of the reference with its transcriptome and GTFReader
+    (SAM.cpp:1046-1061, LandauVishkin.cpp:119-250): the filter's own results for 1500 simulated spliced / chimeric pairs (several
+    hundred transcriptome alignments, most of them across junctions), pairs and single reads, with = / X and with M; then the same
+    with soft clips forced on a third of the reads and some transcriptome alignments moved to where no CIGAR can be computed (the
+    reference then prints an empty field for a transcriptome alignment, where a genome one gets *)."""
+    from snap_rnaseq_b200 import _abi as A
+    w = ws
+    (b0, b1), sam_reads = F.reads(w["contigs"], w["d"])
+    hits, genome_res, pp = F.alignments(cuda, w["hg"], w["ht"], b0, b1)
+    ch = [cuda.characterize(w["hg"], A.single_defaults(max_hits=300, num_seeds=12), b) for b in (b0, b1)]
+    prm = A.FilterParams(pp.max_spacing, pp.force_spacing, 2, 15, F.MAX_HITS_TO_GET)
+    res, _, _ = cuda.filter_paired(w["ann"], prm, np.diff(b0.offsets), np.diff(b1.offsets), hits[0], hits[1], genome_res, ch[0], ch[1])
+    aln = []
+    for e in range(2):
+        a = np.zeros(b0.n, A.SAM_ALIGNMENT)
+        for f in ("location", "mapq", "status", "direction", "is_transcriptome", "tlocation"):
+            a[f] = res[f][:, e]
+        aln.append(a)
+    assert (aln[0]["is_transcriptome"] == 1).sum() > 100
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(w["gtf"].encode(), os.path.join(w["d"], "sam_rna").encode()))
+    rng = np.random.default_rng(3)
+    for clipped in (False, True):
+        if clipped:
+            for r in sam_reads:
+                lens = np.diff(r.offsets).astype(np.int64)
+                pick = rng.random(r.n) < 0.33
+                front = np.where(pick, rng.integers(0, 6, size=r.n), 0)
+                back = np.where(pick, rng.integers(0, 6, size=r.n), 0)
+                r.front_clip[:] = front.astype(np.uint16)
+                r.clipped_len[:] = (lens - front - back).astype(np.uint16)
+            # transcriptome alignments moved to where the read does not align (no CIGAR within 30 edits) or onto a piece boundary
+            _, tpiece_begin = genome_pieces(w["tdir"])
+            for a in aln:
+                t = np.flatnonzero(a["is_transcriptome"] == 1)
+                a["tlocation"][t[:12]] += 41
+                a["tlocation"][t[12:16]] = tpiece_begin[2:6] - 20
+        for use_m in (False, True):
+            want = ref.sam(w["rg"], sam_reads[0], sam_reads[1], aln[0], aln[1], use_m, None, rna=(g, w["rt"]))[0]
+            got, lo = cuda.sam(w["hg"], sam_reads[0], sam_reads[1], aln[0], aln[1], use_m, None, rna=(w["ann"], w["ht"]))
+            assert bytes(got) == want, next((a, b) for a, b in zip(want.split(b"\n"), bytes(got).split(b"\n")) if a != b)
+            assert lo[-1] == len(want)
+            n_junction = sum(1 for ln in want.split(b"\n") if ln and b"N" in ln.split(b"\t")[5])
+            assert n_junction > 20
+            if clipped:
+                assert sum(1 for ln in want.split(b"\n") if ln and ln.split(b"\t")[5] == b"") > 0  # the empty field of a failed transcriptome CIGAR
+        want = ref.sam(w["rg"], sam_reads[1], None, aln[1], None, False, "grp", rna=(g, w["rt"]))[0]
+        got, _ = cuda.sam(w["hg"], sam_reads[1], None, aln[1], None, False, "grp", rna=(w["ann"], w["ht"]))
+        assert bytes(got) == want
+    # the genome-only entry point refuses what it cannot format
+    with pytest.raises(RuntimeError, match="snapb200_sam_batch_rna"):
+        cuda.sam(w["hg"], sam_reads[0], sam_reads[1], aln[0], aln[1])
+    with pytest.raises(RuntimeError, match="index pair"):
+        cuda.sam(w["ht"], sam_reads[0], sam_reads[1], aln[0], aln[1], rna=(w["ann"], w["ht"]))

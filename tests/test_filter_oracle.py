@@ -537,3 +537,104 @@ def test_filter_decision_on_fabricated_hits(ref, tmp_path):
         assert open(os.path.join(d, f), "rb").read() == open(os.path.join(d, "want" + f[len("replay"):]), "rb").read(), f
 
 
+
+
+def feature_tables(export_path):
+    """FltTables with only what sam_splice_cigar reads: the exon / intron list of every transcript, in transcript-id order."""
+    from snap_rnaseq_b200 import _abi as A
+    transcripts = {}
+    for line in open(export_path):
+        p = line.rstrip("\n").split("\t")
+        if p[0] == "T":
+            transcripts[p[1]] = [(int(p[7 + 3 * k]), int(p[8 + 3 * k]), int(p[9 + 3 * k])) for k in range(int(p[6]))]
+    t_ids = sorted(transcripts)
+    keep = {"first": np.zeros(len(t_ids) + 1, np.uint32)}
+    np.cumsum([len(transcripts[t]) for t in t_ids], out=keep["first"][1:])
+    feats = [f for t in t_ids for f in transcripts[t]] or [(0, 0, 0)]
+    for k, name in enumerate(("f_type", "f_start", "f_end")):
+        keep[name] = np.array([f[k] for f in feats], np.uint32)
+    T = FltTables()
+    T.t_feat_first = A.p32u(keep["first"])
+    T.f_type, T.f_start, T.f_end = A.p32u(keep["f_type"]), A.p32u(keep["f_start"]), A.p32u(keep["f_end"])
+    return T, keep, t_ids, transcripts
+
+
+def test_spliced_cigar_matches_the_reference(ref, tmp_path):
+    """sam_splice_cigar (iofmt.h; the leader lane of sam_measure_kernel runs it for transcriptome alignments) against
+    LandauVishkinWithCigar::insertSpliceJunctions over GTFTranscript::Junctions (SNAPLib/LandauVishkin.cpp:119-250,
+    SNAPLib/GTFReader.cpp:1109-1139): random run lists (= X M I D, soft clips) at random positions of the transcripts of random
+    annotations, plus one with abutting and overlapping exons (introns of length 0 and below) and one-base exons; reads that start on
+    an exon's first base, end on its last base (the reference then ends the CIGAR with an N run) or run past the transcript."""
+    import subprocess
+    d = str(tmp_path)
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libiohostsim.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(here, "hostsim", "io_hostsim.cpp")], check=True)
+    hs = C.CDLL(so)
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    rng = np.random.default_rng(5)
+    paths = []
+    for k in range(12):
+        paths.append(os.path.join(d, f"r{k}.gtf"))
+        random_gtf(rng, paths[-1])
+    odd = os.path.join(d, "odd.gtf")
+    with open(odd, "w") as f:
+        rows = [(100, 149), (150, 199), (200, 200), (201, 260), (250, 300), (400, 400), (402, 450), (1000, 1100)]  # abutting, one base, overlapping
+        for gi in range(2):  # the first line of a gene does not register its transcript: give every gene a throw-away first line
+            f.write(f'chr1\ts\texon\t10\t20\t.\t+\t.\tgene_id "O{gi}"; transcript_id "O{gi}.first";\n')
+            for (s, e) in rows[gi:]:
+                f.write(f'chr1\ts\texon\t{s}\t{e}\t.\t+\t.\tgene_id "O{gi}"; transcript_id "O{gi}.t";\n')
+    paths.append(odd)
+    n_cases = n_spliced = n_tail_n = 0
+    for p in paths:
+        g = C.c_void_p(lib.ref_gtf_load(p.encode(), (p + ".out").encode()))
+        assert lib.ref_gtf_export(g, (p + ".tsv").encode()) == 0
+        T, keep, t_ids, transcripts = feature_tables(p + ".tsv")
+        for tr, tid in enumerate(t_ids):
+            feats = transcripts[tid]
+            exon_len = [e - s + 1 for (ty, s, e) in feats if ty == 1]
+            total = sum(exon_len)
+            ends = np.cumsum(exon_len) if exon_len else np.array([50])
+            for _ in range(25):
+                # a read of 30..150 transcript bases; start / end snapped to exon boundaries now and then
+                span = int(rng.integers(30, 151))
+                pos = int(rng.integers(1, max(2, total + 20)))
+                r = rng.random()
+                if r < 0.2:
+                    pos = int(rng.choice(ends)) + 1            # the first base of an exon
+                elif r < 0.4:
+                    pos = max(1, int(rng.choice(ends)) - span + 1)   # ends on the last base of an exon (without I / D)
+                runs, left, with_indels = [], span, rng.random() < 0.5
+                style_m = rng.random() < 0.3
+                while left > 0:
+                    n = int(min(left, rng.integers(1, 60)))
+                    op = "M" if style_m else "=X"[int(rng.integers(0, 2))]
+                    if with_indels and rng.random() < 0.25:
+                        op = "ID"[int(rng.integers(0, 2))]
+                        n = int(rng.integers(1, 4))
+                    if runs and runs[-1][1] == op:
+                        runs[-1] = (runs[-1][0] + n, op)
+                    else:
+                        runs.append((n, op))
+                    if op != "I":
+                        left -= n
+                cb, ca = (int(rng.integers(0, 12)) if rng.random() < 0.3 else 0 for _ in range(2))
+                lv = "".join(f"{n}{op}" for n, op in runs).encode()
+                tokens = ([cb, ord("S")] if cb else []) + [x for n, op in runs for x in (n, ord(op))] + ([ca, ord("S")] if ca else [])
+                tok = np.array(tokens, np.uint32)
+                want = C.create_string_buffer(4096)
+                rc = lib.ref_splice_cigar(g, tok.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint(len(tok)), tid.encode(), C.c_uint(pos), want, C.c_int(4096))
+                assert rc >= 0
+                got = C.create_string_buffer(4096)
+                n = hs.hostsim_splice_cigar(C.byref(T), C.c_int(tr), C.c_uint(pos), lv, C.c_uint(len(lv)), C.c_uint(cb), C.c_uint(ca), got, C.c_uint(4095))
+                assert n >= 0 and got.raw[:n] == want.value, (p, tid, pos, lv, cb, ca, want.value, got.raw[:max(n, 0)])
+                n_cases += 1
+                n_spliced += b"N" in want.value
+                n_tail_n += want.value.endswith(b"N")
+                # a slot that is one character too small is reported, never overrun
+                if n > 0:
+                    small = C.create_string_buffer(b"\xee" * (n + 8))
+                    assert hs.hostsim_splice_cigar(C.byref(T), C.c_int(tr), C.c_uint(pos), lv, C.c_uint(len(lv)), C.c_uint(cb), C.c_uint(ca), small, C.c_uint(n - 1)) == -1
+                    assert small.raw[n - 1:n + 8] == b"\xee" * 9
+    assert n_cases > 500 and n_spliced > 100 and n_tail_n > 5, (n_cases, n_spliced, n_tail_n)

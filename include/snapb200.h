@@ -405,12 +405,24 @@ typedef struct {
     const snapb200_splice *splices;
     const uint8_t *splice_overflow;
     float device_ms;   /* wall time of the device work of this batch (uploads, kernels, downloads), for the shim's timing report */
+    /* snapb200_rna_batch_submit_sam only (NULL otherwise): what SimpleReadWriter::writePair writes for pair i is
+     * sam_text[sam_line_offsets[2i] .. sam_line_offsets[2i+2]) -- two lines, the end with the lower location first -- with the
+     * filter's result (after the forceSpacing rule of PairedAligner.cpp:648-651) as the alignment.  A pair whose range is empty
+     * was not formatted (needs_host[i], or a spliced CIGAR too long for its slot): the caller writes it with the reference's writer. */
+    const char *sam_text;
+    const uint64_t *sam_line_offsets;
 } snapb200_rna_view;
 
 int snapb200_rna_batch_create(snapb200_annotation *a, snapb200_index *genome, snapb200_index *transcriptome, snapb200_rna_batch **out);
 void snapb200_rna_batch_destroy(snapb200_rna_batch *b);
 int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0,
                               const snapb200_read_batch *reads1);
+/* The same, and the SAM lines of every pair as the last stage of the submission (snapb200_sam_batch_rna on the resident reads and
+ * results): sam0 / sam1 hold the unclipped reads, their ids and the clipping of the same n pairs (reads0 / reads1 are their clipped
+ * parts, as the aligners see them). */
+int snapb200_rna_batch_submit_sam(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0,
+                                  const snapb200_read_batch *reads1, const snapb200_sam_reads *sam0, const snapb200_sam_reads *sam1,
+                                  int use_m, const char *read_group);
 int snapb200_rna_batch_wait(snapb200_rna_batch *b, snapb200_rna_view *view);
 
 /* ---- building blocks exposed for known-answer tests -------------------------------------------------- */

@@ -141,8 +141,14 @@ class Snapb200(BatchLib):
         self.lib.snapb200_rna_batch_destroy.restype = None
         self.lib.snapb200_rna_batch_destroy(b)
 
-    def rna_batch_submit(self, b, params, b0, b1):
-        self._check(self.lib.snapb200_rna_batch_submit(b, C.byref(params), b0.byref(), b1.byref()), "rna_batch_submit")
+    def rna_batch_submit(self, b, params, b0, b1, sam=None):
+        """sam = (SamReads of mate 0, of mate 1, use_m, read group or None): also format the SAM lines (snapb200_rna_batch_submit_sam)."""
+        if sam is None:
+            self._check(self.lib.snapb200_rna_batch_submit(b, C.byref(params), b0.byref(), b1.byref()), "rna_batch_submit")
+        else:
+            rg = sam[3].encode() if sam[3] else None
+            self._check(self.lib.snapb200_rna_batch_submit_sam(b, C.byref(params), b0.byref(), b1.byref(), sam[0].byref(), sam[1].byref(), C.c_int(int(sam[2])), rg),
+                        "rna_batch_submit_sam")
 
     def rna_batch_wait(self, b):
         """-> dict of numpy COPIES of the batch object's pinned outputs (the views die with the next submit)."""
@@ -168,6 +174,9 @@ class Snapb200(BatchLib):
         soff = arr(v.splice_offsets, n + 1, np.uint64)
         out["splice_offsets"], out["splices"] = soff, arr(v.splices, int(soff[-1]) if n else 0, A.SPLICE)
         out["splice_overflow"] = arr(v.splice_overflow, n, np.uint8)
+        if v.sam_line_offsets:
+            out["sam_line_offsets"] = arr(v.sam_line_offsets, 2 * n + 1, np.uint64)
+            out["sam_text"] = arr(v.sam_text, int(out["sam_line_offsets"][-1]), np.uint8).tobytes()
         return out
 
     def device_count(self):

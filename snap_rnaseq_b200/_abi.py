@@ -249,7 +249,8 @@ class RnaView(C.Structure):
     _fields_ = [("n", C.c_uint32), ("results", C.c_void_p), ("events", C.c_void_p), ("needs_host", C.c_void_p), ("genome_pairs", C.c_void_p),
                 ("hit_offsets", C.c_void_p * 2), ("hit_locations", C.c_void_p * 2), ("hit_rcs", C.c_void_p * 2), ("hit_scores", C.c_void_p * 2),
                 ("seg_offsets", C.c_void_p * 2), ("ch_locations", C.c_void_p * 2), ("ch_seed_offsets", C.c_void_p * 2),
-                ("splice_offsets", C.c_void_p), ("splices", C.c_void_p), ("splice_overflow", C.c_void_p), ("device_ms", C.c_float)]
+                ("splice_offsets", C.c_void_p), ("splices", C.c_void_p), ("splice_overflow", C.c_void_p), ("device_ms", C.c_float),
+                ("sam_text", C.c_void_p), ("sam_line_offsets", C.c_void_p)]
 
 
 SPLICE = np.dtype([("pair", "<u4"), ("kind", "<i4"), ("chr", "<i4", (2,)), ("pos", "<u4", (2,)), ("pos_end", "<u4", (2,))])

@@ -314,6 +314,9 @@ struct PinBuf {  // pinned host memory that only grows
 // per host thread once the pool is warm; a batch borrows a set for the duration of its device work.
 struct RnaResources {
     PinBuf in_off[2], in_bases[2], in_quals[2];
+    // the SAM stage (snapb200_rna_batch_submit_sam): unclipped reads, ids and clipping in; text and line offsets out
+    PinBuf s_off[2], s_bases[2], s_quals[2], s_front[2], s_clip[2], s_idoff[2], s_ids[2], s_rg, h_sam, h_samoff;
+    DevBuf ds_off[2], ds_bases[2], ds_quals[2], ds_front[2], ds_clip[2], ds_idoff[2], ds_ids[2], ds_rg, ds_aln[2], ds_cigars, ds_lines, ds_len, ds_lineoff, ds_ctr, ds_out;
     PinBuf h_res, h_ev, h_flags, h_pairs, h_hoff[2], h_hloc[2], h_hrc[2], h_hscore[2], h_seg[2], h_cloc[2], h_coff[2], h_soff, h_splices, h_sover;
     // (the sessions' own buffers are reused by other callers between the two phases of a batch, so the intermediates live here)
     DevBuf d_hoff[2], d_hloc[2], d_hrc[2], d_hscore[2], d_seg[2], d_cnt[2], d_cloc[2], d_coff[2], d_keys[2], d_tmp, d_res, d_ev, d_flags, d_scount, d_soff, d_skind, d_sover, d_splices;
@@ -323,6 +326,15 @@ struct RnaResources {
                           &h_hoff[0], &h_hoff[1], &h_hloc[0], &h_hloc[1], &h_hrc[0], &h_hrc[1], &h_hscore[0], &h_hscore[1], &h_seg[0], &h_seg[1],
                           &h_cloc[0], &h_cloc[1], &h_coff[0], &h_coff[1], &h_soff, &h_splices, &h_sover};
         for (PinBuf *q : pins) q->release();
+        for (int e = 0; e < 2; e++) {
+            PinBuf *sp[] = {&s_off[e], &s_bases[e], &s_quals[e], &s_front[e], &s_clip[e], &s_idoff[e], &s_ids[e]};
+            for (PinBuf *q : sp) q->release();
+            DevBuf *sd[] = {&ds_off[e], &ds_bases[e], &ds_quals[e], &ds_front[e], &ds_clip[e], &ds_idoff[e], &ds_ids[e], &ds_aln[e]};
+            for (DevBuf *q : sd) q->release();
+        }
+        s_rg.release(); h_sam.release(); h_samoff.release();
+        DevBuf *sd2[] = {&ds_rg, &ds_cigars, &ds_lines, &ds_len, &ds_lineoff, &ds_ctr, &ds_out};
+        for (DevBuf *q : sd2) q->release();
         DevBuf *devs[] = {&d_hoff[0], &d_hoff[1], &d_hloc[0], &d_hloc[1], &d_hrc[0], &d_hrc[1], &d_hscore[0], &d_hscore[1], &d_seg[0], &d_seg[1],
                           &d_cnt[0], &d_cnt[1], &d_cloc[0], &d_cloc[1], &d_coff[0], &d_coff[1], &d_keys[0], &d_keys[1], &d_tmp, &d_res, &d_ev,
                           &d_flags, &d_scount, &d_soff, &d_skind, &d_sover, &d_splices};
@@ -366,6 +378,11 @@ struct snapb200_rna_batch {
     snapb200_annotation *ann = nullptr;
     snapb200_index *genome = nullptr, *transcriptome = nullptr;
     HostArr in_off[2], in_bases[2], in_quals[2];
+    bool want_sam = false;  // snapb200_rna_batch_submit_sam
+    int use_m = 0;
+    std::string read_group;
+    HostArr s_off[2], s_bases[2], s_quals[2], s_front[2], s_clip[2], s_idoff[2], s_ids[2], o_sam, o_samoff;
+    uint32_t sam_max_len = 0;
     HostArr o_res, o_ev, o_flags, o_pairs, o_hoff[2], o_hloc[2], o_hrc[2], o_hscore[2], o_seg[2], o_cloc[2], o_coff[2], o_soff, o_splices, o_sover;
     snapb200_rna_params params;
     uint32_t n = 0;
@@ -384,6 +401,100 @@ static double rna_now()
     struct timespec t;
     clock_gettime(CLOCK_MONOTONIC, &t);
     return t.tv_sec + t.tv_nsec * 1e-9;
+}
+
+// The arguments writePair gets for every pair: the filter's result after the forceSpacing rule of the run loop (PairedAligner.cpp:648-651).
+// Pairs the reference's own filter has to decide are skipped.
+__global__ void rna_sam_alignments_kernel(uint32_t n, const FltResult *res, const uint8_t *needs_host, int force_spacing, snapb200_sam_alignment *a0,
+                                          snapb200_sam_alignment *a1)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FltResult r = res[i];
+    const bool drop = force_spacing && (r.status[0] == SNAPB200_SINGLE_HIT) != (r.status[1] == SNAPB200_SINGLE_HIT);
+    snapb200_sam_alignment *out[2] = {a0 + i, a1 + i};
+    for (int e = 0; e < 2; e++) {
+        snapb200_sam_alignment a;
+        a.location = drop ? 0xffffffffu : r.location[e];
+        a.mapq = r.mapq[e];
+        a.status = drop ? (uint8_t)SNAPB200_NOT_FOUND : r.status[e];
+        a.direction = r.direction[e];
+        a.skip = needs_host[i] ? 1 : 0;
+        a.is_transcriptome = r.is_transcriptome[e];
+        a.tlocation = r.tlocation[e];
+        *out[e] = a;
+    }
+}
+
+// The last stage of a submission made with snapb200_rna_batch_submit_sam, on the genome session's stream after the filter.
+static int rna_sam_stage(snapb200_rna_batch *b, RnaResources &R, cudaStream_t stream)
+{
+    const uint32_t n = b->n, n_lines = 2 * n;
+    int rc;
+    SamArgs a;
+    memset(&a, 0, sizeof(a));
+    if ((rc = sam_names(b->genome, &a.names))) return rc;
+    a.ix = b->genome->dev; a.tix = b->transcriptome->dev; a.tables = b->ann->t; a.rna = 1; a.cigar_stride = SAM_SPLICED_CIGAR_STRIDE;
+    for (int e = 0; e < 2; e++) {
+        const size_t nb = R.s_off[e].as<uint32_t>()[n], ni = R.s_idoff[e].as<uint32_t>()[n];
+        if ((rc = R.ds_off[e].ensure((size_t)(n + 1) * 4)) || (rc = R.ds_bases[e].ensure(nb + 16)) || (rc = R.ds_quals[e].ensure(nb + 16)) ||
+            (rc = R.ds_front[e].ensure((size_t)n * 2)) || (rc = R.ds_clip[e].ensure((size_t)n * 2)) || (rc = R.ds_idoff[e].ensure((size_t)(n + 1) * 4)) ||
+            (rc = R.ds_ids[e].ensure(ni + 16)) || (rc = R.ds_aln[e].ensure((size_t)n * sizeof(snapb200_sam_alignment))))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(R.ds_off[e].p, R.s_off[e].p, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, stream));
+        if (nb) {
+            CUDA_TRY(cudaMemcpyAsync(R.ds_bases[e].p, R.s_bases[e].p, nb, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(R.ds_quals[e].p, R.s_quals[e].p, nb, cudaMemcpyHostToDevice, stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(R.ds_front[e].p, R.s_front[e].p, (size_t)n * 2, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(R.ds_clip[e].p, R.s_clip[e].p, (size_t)n * 2, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(R.ds_idoff[e].p, R.s_idoff[e].p, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, stream));
+        if (ni) CUDA_TRY(cudaMemcpyAsync(R.ds_ids[e].p, R.s_ids[e].p, ni, cudaMemcpyHostToDevice, stream));
+        a.in.rd[e].offsets = R.ds_off[e].as<uint32_t>(); a.in.rd[e].bases = R.ds_bases[e].as<uint8_t>(); a.in.rd[e].quals = R.ds_quals[e].as<uint8_t>();
+        a.in.rd[e].front_clip = R.ds_front[e].as<uint16_t>(); a.in.rd[e].clipped_len = R.ds_clip[e].as<uint16_t>();
+        a.in.rd[e].id_offsets = R.ds_idoff[e].as<uint32_t>(); a.in.rd[e].ids = R.ds_ids[e].as<uint8_t>();
+        a.in.aln[e] = R.ds_aln[e].as<snapb200_sam_alignment>();
+    }
+    rna_sam_alignments_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, R.d_res.as<FltResult>(), R.d_flags.as<uint8_t>(), (int)b->params.filter.force_spacing,
+                                                                   R.ds_aln[0].as<snapb200_sam_alignment>(), R.ds_aln[1].as<snapb200_sam_alignment>());
+    CUDA_TRY(cudaGetLastError());
+    const size_t rg_len = b->read_group.size();
+    if ((rc = R.ds_rg.ensure(rg_len + 16)) || (rc = R.s_rg.ensure(rg_len + 16))) return rc;
+    if (rg_len) {
+        memcpy(R.s_rg.p, b->read_group.data(), rg_len);
+        CUDA_TRY(cudaMemcpyAsync(R.ds_rg.p, R.s_rg.p, rg_len, cudaMemcpyHostToDevice, stream));
+    }
+    if ((rc = R.ds_cigars.ensure((size_t)n_lines * a.cigar_stride)) || (rc = R.ds_lines.ensure((size_t)n_lines * sizeof(SamLine))) ||
+        (rc = R.ds_len.ensure((size_t)(n_lines + 1) * 8)) || (rc = R.ds_lineoff.ensure((size_t)(n_lines + 1) * 8)) || (rc = R.ds_ctr.ensure(sizeof(Counters))))
+        return rc;
+    a.n_lines = n_lines; a.in.paired = 1; a.use_m = b->use_m; a.rg = R.ds_rg.as<char>(); a.rg_len = (uint32_t)rg_len;
+    a.rl = std::max(32u, (b->sam_max_len + 15) & ~15u);
+    a.cigars = R.ds_cigars.as<char>(); a.lines = R.ds_lines.as<SamLine>(); a.line_len = R.ds_len.as<uint64_t>(); a.line_off = R.ds_lineoff.as<uint64_t>();
+    a.ctr = R.ds_ctr.as<Counters>();
+    CUDA_TRY(cudaMemsetAsync(R.ds_ctr.p, 0, sizeof(Counters), stream));
+    CUDA_TRY(cudaMemsetAsync(R.ds_len.as<uint64_t>() + n_lines, 0, 8, stream));
+    const size_t smem = sam_warp_shared(a.rl) * WARPS_PER_CTA;
+    int per_sm;
+    const int grid = grid_for(sam_measure_kernel, smem, b->genome->sm_count, &per_sm);
+    sam_measure_kernel<<<grid, CTA_THREADS, smem, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a.line_len, R.ds_lineoff.as<uint64_t>(), (int)n_lines + 1, stream);
+    if ((rc = R.d_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(R.d_tmp.p, tmp_bytes, a.line_len, R.ds_lineoff.as<uint64_t>(), (int)n_lines + 1, stream));
+    if ((rc = R.h_samoff.ensure((size_t)(n_lines + 1) * 8))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(R.h_samoff.p, R.ds_lineoff.p, (size_t)(n_lines + 1) * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const uint64_t total = R.h_samoff.as<uint64_t>()[n_lines];
+    if ((rc = R.h_sam.ensure(total + 16))) return rc;
+    if (total) {
+        if ((rc = R.ds_out.ensure(total + 16))) return rc;
+        a.out = R.ds_out.as<char>();
+        sam_write_kernel<<<(uint32_t)(((uint64_t)n_lines * SAM_WRITE_LANES + 255) / 256), 256, 0, stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(R.h_sam.p, R.ds_out.p, total, cudaMemcpyDeviceToHost, stream));
+    }
+    return 0;
 }
 
 static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
@@ -535,6 +646,10 @@ static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
                 CUDA_TRY(cudaMemcpyAsync(R.h_coff[e].p, R.d_coff[e].p, tuples[e] * 2, cudaMemcpyDeviceToHost, s->stream));
             }
         }
+        if (b->want_sam) {
+            if ((rc = rna_sam_stage(b, R, s->stream))) return rc;
+            s->total_launches += 3;
+        }
         cudaError_t e2 = cudaStreamSynchronize(s->stream);
         if (e2 != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "rna batch: %s", cudaGetErrorString(e2));
         RNA_MARK(6);
@@ -564,6 +679,20 @@ static int rna_run(snapb200_rna_batch *b)
         memcpy(R.in_off[e].p, b->in_off[e].v.data(), (size_t)(n + 1) * 4);
         memcpy(R.in_bases[e].p, b->in_bases[e].v.data(), nb);
         memcpy(R.in_quals[e].p, b->in_quals[e].v.data(), nb);
+        if (b->want_sam) {
+            const size_t sb = b->s_off[e].as<uint32_t>()[n], si = b->s_idoff[e].as<uint32_t>()[n];
+            if ((rc = R.s_off[e].ensure((size_t)(n + 1) * 4)) || (rc = R.s_bases[e].ensure(sb + 16)) || (rc = R.s_quals[e].ensure(sb + 16)) ||
+                (rc = R.s_front[e].ensure((size_t)n * 2 + 16)) || (rc = R.s_clip[e].ensure((size_t)n * 2 + 16)) || (rc = R.s_idoff[e].ensure((size_t)(n + 1) * 4)) ||
+                (rc = R.s_ids[e].ensure(si + 16)))
+                break;
+            memcpy(R.s_off[e].p, b->s_off[e].v.data(), (size_t)(n + 1) * 4);
+            memcpy(R.s_bases[e].p, b->s_bases[e].v.data(), sb);
+            memcpy(R.s_quals[e].p, b->s_quals[e].v.data(), sb);
+            memcpy(R.s_front[e].p, b->s_front[e].v.data(), (size_t)n * 2);
+            memcpy(R.s_clip[e].p, b->s_clip[e].v.data(), (size_t)n * 2);
+            memcpy(R.s_idoff[e].p, b->s_idoff[e].v.data(), (size_t)(n + 1) * 4);
+            memcpy(R.s_ids[e].p, b->s_ids[e].v.data(), si);
+        }
     }
     if (!rc) rc = rna_run_on(b, R);
     if (!rc) {
@@ -576,6 +705,10 @@ static int rna_run(snapb200_rna_batch *b)
         }
         const size_t ns = (size_t)R.h_soff.as<uint64_t>()[n];
         b->o_soff.set(R.h_soff.p, (size_t)(n + 1) * 8); b->o_splices.set(R.h_splices.p, ns * sizeof(FltSplice)); b->o_sover.set(R.h_sover.p, n);
+        if (b->want_sam) {
+            b->o_samoff.set(R.h_samoff.p, (2 * (size_t)n + 1) * 8);
+            b->o_sam.set(R.h_sam.p, (size_t)R.h_samoff.as<uint64_t>()[2 * (size_t)n]);
+        }
     }
     b->ann->pool->give_back(res);
     return rc;
@@ -625,12 +758,51 @@ extern "C" void snapb200_rna_batch_destroy(snapb200_rna_batch *b)
     delete b;
 }
 
-extern "C" int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0, const snapb200_read_batch *reads1)
+static int rna_submit(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0, const snapb200_read_batch *reads1,
+                      const snapb200_sam_reads *sam0, const snapb200_sam_reads *sam1, int use_m, const char *read_group)
 {
     if (!b || !params || !reads0 || !reads1) return set_error(SNAPB200_ERR_ARG, "null argument");
     if (reads0->n != reads1->n) return set_error(SNAPB200_ERR_ARG, "mate batches differ in size");
+    const bool want_sam = sam0 != nullptr;
+    uint32_t sam_max_len = 0;
+    if (want_sam) {
+        if (!sam1 || sam0->n != reads0->n || sam1->n != reads0->n) return set_error(SNAPB200_ERR_ARG, "the SAM read batches must hold the same pairs as the read batches");
+        const snapb200_sam_reads *sr[2] = {sam0, sam1};
+        const snapb200_read_batch *rr[2] = {reads0, reads1};
+        for (int e = 0; e < 2 && reads0->n; e++) {
+            const snapb200_sam_reads *r = sr[e];
+            if (!r->offsets || !r->bases || !r->quals || !r->front_clip || !r->clipped_len || !r->id_offsets || !r->ids) return set_error(SNAPB200_ERR_ARG, "null SAM read array");
+            if (r->offsets[0] != 0 || r->id_offsets[0] != 0) return set_error(SNAPB200_ERR_ARG, "SAM read offsets must start at 0");
+            for (uint32_t i = 0; i < r->n; i++) {
+                if (r->offsets[i + 1] < r->offsets[i] || r->id_offsets[i + 1] < r->id_offsets[i]) return set_error(SNAPB200_ERR_ARG, "offsets not monotonic at read %u", i);
+                const uint32_t len = r->offsets[i + 1] - r->offsets[i];
+                if ((uint32_t)r->front_clip[i] + r->clipped_len[i] > len) return set_error(SNAPB200_ERR_ARG, "read %u: clipping exceeds the read", i);
+                if (rr[e]->offsets && rr[e]->offsets[i + 1] - rr[e]->offsets[i] != r->clipped_len[i])
+                    return set_error(SNAPB200_ERR_ARG, "read %u: clipped_len %u is not the length of the aligned read (%u)", i, r->clipped_len[i], rr[e]->offsets[i + 1] - rr[e]->offsets[i]);
+                sam_max_len = std::max(sam_max_len, len);
+            }
+        }
+        if (sam_max_len > SNAPB200_MAX_READ_LENGTH) return set_error(SNAPB200_ERR_ARG, "read of %u bases exceeds MAX_READ_LENGTH %d", sam_max_len, SNAPB200_MAX_READ_LENGTH);
+    }
     std::unique_lock<std::mutex> lk(b->m);
     if (b->state == 1) return set_error(SNAPB200_ERR_ARG, "rna batch: a submitted batch has not been waited for");
+    b->want_sam = want_sam;
+    b->use_m = use_m;
+    b->read_group = read_group ? read_group : "";
+    b->sam_max_len = sam_max_len;
+    if (want_sam && reads0->n) {
+        const snapb200_sam_reads *sr[2] = {sam0, sam1};
+        const uint32_t ns = reads0->n;
+        for (int e = 0; e < 2; e++) {
+            b->s_off[e].set(sr[e]->offsets, (size_t)(ns + 1) * 4);
+            b->s_bases[e].set(sr[e]->bases, sr[e]->offsets[ns]);
+            b->s_quals[e].set(sr[e]->quals, sr[e]->offsets[ns]);
+            b->s_front[e].set(sr[e]->front_clip, (size_t)ns * 2);
+            b->s_clip[e].set(sr[e]->clipped_len, (size_t)ns * 2);
+            b->s_idoff[e].set(sr[e]->id_offsets, (size_t)(ns + 1) * 4);
+            b->s_ids[e].set(sr[e]->ids, sr[e]->id_offsets[ns]);
+        }
+    }
     const snapb200_read_batch *r[2] = {reads0, reads1};
     const uint32_t n = reads0->n;
     for (int e = 0; e < 2 && n; e++) {
@@ -645,6 +817,19 @@ extern "C" int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_r
     b->state = 1;
     b->cv.notify_all();
     return 0;
+}
+
+extern "C" int snapb200_rna_batch_submit(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0, const snapb200_read_batch *reads1)
+{
+    return rna_submit(b, params, reads0, reads1, nullptr, nullptr, 0, nullptr);
+}
+
+extern "C" int snapb200_rna_batch_submit_sam(snapb200_rna_batch *b, const snapb200_rna_params *params, const snapb200_read_batch *reads0,
+                                             const snapb200_read_batch *reads1, const snapb200_sam_reads *sam0, const snapb200_sam_reads *sam1, int use_m,
+                                             const char *read_group)
+{
+    if (!sam0 || !sam1) return set_error(SNAPB200_ERR_ARG, "null SAM read batch");
+    return rna_submit(b, params, reads0, reads1, sam0, sam1, use_m, read_group);
 }
 
 extern "C" int snapb200_rna_batch_wait(snapb200_rna_batch *b, snapb200_rna_view *view)
@@ -671,5 +856,9 @@ extern "C" int snapb200_rna_batch_wait(snapb200_rna_batch *b, snapb200_rna_view 
     view->splice_offsets = b->o_soff.as<uint64_t>();
     view->splices = b->o_splices.as<snapb200_splice>();
     view->splice_overflow = b->o_sover.as<uint8_t>();
+    if (b->want_sam) {
+        view->sam_text = b->o_sam.as<char>();
+        view->sam_line_offsets = b->o_samoff.as<uint64_t>();
+    }
     return 0;
 }

@@ -154,6 +154,28 @@ def test_rna_batch_is_the_pair_loop_of_the_reference(ref, cuda, ws):
         assert not o["splice_overflow"].any() and len(o["splices"]) > 0 and (o["events"]["unaligned"] > 0).sum() > 20
         assert np.all(np.diff(o["splice_offsets"].astype(np.int64))[o["events"]["unaligned"] == 0] == 0)
         replay_and_compare(ref, cuda, w, sam_reads, o["events"], f"want_r{k}", f"replay_s{k}", splices=(o["splice_offsets"], o["splices"]))
+    # the SAM lines as the last stage of the same submission: what writePair writes for the filter's results
+    b0, b1, sam_reads = cases[0]
+    cuda.rna_batch_submit(objs[0], P, b0, b1, sam=(sam_reads[0], sam_reads[1], False, "grp"))
+    o = cuda.rna_batch_wait(objs[0])
+    assert_same_records(outs[0]["results"], o["results"], "with the SAM stage")
+    aln = []
+    for e in range(2):
+        a = np.zeros(b0.n, A.SAM_ALIGNMENT)
+        for f in ("location", "mapq", "status", "direction", "is_transcriptome", "tlocation"):
+            a[f] = o["results"][f][:, e]
+        aln.append(a)
+    lib = ref.lib
+    lib.ref_gtf_load.restype = C.c_void_p
+    g = C.c_void_p(lib.ref_gtf_load(w["gtf"].encode(), os.path.join(w["d"], "sam_stage").encode()))
+    want = ref.sam(w["rg"], sam_reads[0], sam_reads[1], aln[0], aln[1], False, "grp", rna=(g, w["rt"]))[0]
+    assert o["sam_text"] == want
+    lo = o["sam_line_offsets"].astype(np.int64)
+    assert len(lo) == 2 * b0.n + 1 and lo[-1] == len(want) and all(want[lo[k + 1] - 1:lo[k + 1]] == b"\n" for k in range(2 * b0.n))
+    with pytest.raises(RuntimeError, match="clipped_len"):
+        bad = A.SamReads(sam_reads[0].offsets, sam_reads[0].bases, sam_reads[0].quals, sam_reads[0].front_clip, sam_reads[0].clipped_len - 1,
+                         sam_reads[0].id_offsets, sam_reads[0].ids)
+        cuda.rna_batch_submit(objs[0], P, b0, b1, sam=(bad, sam_reads[1], False, None))
     # an empty batch is legal
     cuda.rna_batch_submit(objs[1], P, cases[0][0].slice(0, 0), cases[0][1].slice(0, 0))
     assert cuda.rna_batch_wait(objs[1])["n"] == 0

@@ -29,12 +29,83 @@
 #include "AlignerContext.h"
 #include "AlignmentFilter.h"
 #include "BaseAligner.h"
+#include "DataWriter.h"
+#include "FileFormat.h"
 #include "PairedAligner.h"
 #include "SingleAligner.h"
 #include "WGsim.h"
 #include "exit.h"
 
 #include "snapb200.h"
+
+// SAM output whose lines the device has already formatted (snapb200_rna_batch_submit_sam).  snap-rna-b200's main installs one of
+// these over each FileFormat::SAM[] entry before runAlignment: it is the reference's SAMFormat for everything (format detection,
+// header, sort keys, writeRead for single reads and for pairs the shim leaves to the host) except that, while the calling thread has
+// armed the two lines of a pair, writeRead copies them instead of formatting -- so SimpleReadWriter::writePair
+// (SNAPLib/ReadWriter.cpp:132-217) keeps doing what it does: both lines into one buffer, a fresh buffer and a second try when they
+// do not fit, writer->advance with the sort locations.
+class PreformattedSAMFormat : public FileFormat {
+public:
+    struct Pending { const char *line[2]; size_t len[2]; bool armed; };
+    static Pending &pending() { static __thread Pending p; return p; }  // zero-initialised per thread: not armed
+    static bool &installed() { static bool yes = false; return yes; }
+    static void install()
+    {
+        if (installed()) return;
+        for (int k = 0; k < 2; k++) FileFormat::SAM[k] = new PreformattedSAMFormat(FileFormat::SAM[k]);
+        installed() = true;
+    }
+    // the two lines of the next writePair on this thread, in the order writePair writes them
+    static void arm(const char *first, size_t firstLen, const char *second, size_t secondLen)
+    {
+        Pending &p = pending();
+        p.line[0] = first; p.len[0] = firstLen; p.line[1] = second; p.len[1] = secondLen; p.armed = true;
+    }
+    static void disarm() { pending().armed = false; }
+
+    explicit PreformattedSAMFormat(const FileFormat *inner_) : inner(inner_) {}
+    virtual bool isFormatOf(const char *filename) const { return inner->isFormatOf(filename); }
+    virtual void getSortInfo(const Genome *genome, char *buffer, _int64 bytes, unsigned *o_location, unsigned *o_readBytes, int *o_refID = NULL, int *o_pos = NULL) const
+    { inner->getSortInfo(genome, buffer, bytes, o_location, o_readBytes, o_refID, o_pos); }
+    // SAMFormat::getWriterSupplier (SNAPLib/SAM.cpp:688-707) with this object as the writers' format
+    virtual ReadWriterSupplier *getWriterSupplier(AlignerOptions *options, const Genome *genome, const Genome *transcriptome, const GTFReader *gtf) const
+    {
+        DataWriterSupplier *dataSupplier;
+        if (options->sortOutput) {
+            const size_t len = strlen(options->outputFileTemplate);
+            char *tempFileName = (char *)malloc(5 + len);
+            strcpy(tempFileName, options->outputFileTemplate);
+            strcpy(tempFileName + len, ".tmp");
+            dataSupplier = DataWriterSupplier::sorted(this, genome, tempFileName, options->sortMemory * (1ULL << 30), options->numThreads, options->outputFileTemplate, NULL);
+        } else {
+            dataSupplier = DataWriterSupplier::create(options->outputFileTemplate);
+        }
+        return ReadWriterSupplier::create(this, dataSupplier, genome, transcriptome, gtf);
+    }
+    virtual bool writeHeader(const ReaderContext &context, char *header, size_t headerBufferSize, size_t *headerActualSize, bool sorted, int argc, const char **argv,
+                             const char *version, const char *rgLine) const
+    { return inner->writeHeader(context, header, headerBufferSize, headerActualSize, sorted, argc, argv, version, rgLine); }
+    virtual bool writeRead(const Genome *genome, const Genome *transcriptome, const GTFReader *gtf, LandauVishkinWithCigar *lv, char *buffer, size_t bufferSpace,
+                           size_t *spaceUsed, size_t qnameLen, Read *read, AlignmentResult result, int mapQuality, unsigned genomeLocation, Direction direction,
+                           bool isTranscriptome = false, unsigned tlocation = 0, bool hasMate = false, bool firstInPair = false, Read *mate = NULL,
+                           AlignmentResult mateResult = NotFound, unsigned mateLocation = 0, Direction mateDirection = FORWARD, bool mateIsTranscriptome = false,
+                           unsigned mateTlocation = 0) const
+    {
+        const Pending &p = pending();
+        if (p.armed && hasMate) {
+            const int k = firstInPair ? 0 : 1;
+            if (p.len[k] > bufferSpace) return false;  // as SAMFormat::writeRead when snprintf runs out of space (SAM.cpp:1137-1142)
+            memcpy(buffer, p.line[k], p.len[k]);
+            if (spaceUsed != NULL) *spaceUsed = p.len[k];
+            return true;
+        }
+        return inner->writeRead(genome, transcriptome, gtf, lv, buffer, bufferSpace, spaceUsed, qnameLen, read, result, mapQuality, genomeLocation, direction,
+                                isTranscriptome, tlocation, hasMate, firstInPair, mate, mateResult, mateLocation, mateDirection, mateIsTranscriptome, mateTlocation);
+    }
+
+private:
+    const FileFormat *inner;
+};
 
 // The reference grants `friend class AlignerContext2` in AlignerContext, SingleAlignerContext and
 // PairedAlignerContext (AlignerContext.h:100, SingleAligner.h:63, PairedAligner.h:72) but never defines it:
@@ -185,7 +256,7 @@ class GpuAlignerExtension : public AlignerExtension {
 public:
     // batchReads: pairs (or reads) per device batch.  Devices: every visible GPU (SNAPB200_DEVICES=n limits it); batches are dealt
     // round-robin over them from this one process (GTF counters are process-global, so one process drives all).
-    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true)
+    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true), deviceSam_(false), useM_(false)
     {
         if (const char *e = getenv("SNAPB200_SHIM_BATCH")) { int v = atoi(e); if (v >= 16) batch_ = (unsigned)v; }  // tests: many small batches
         AlignerContext2::SpliceBatch::pregrowSetup();  // main thread (copies are made from this object), before the workers allocate
@@ -328,6 +399,10 @@ public:
         P.filter.max_spacing = pp.max_spacing; P.filter.conf_diff = ctx->options->confDiff; P.filter.max_dist = ctx->options->maxDist.start;
         P.filter.max_hits_to_get = P.transcriptome.max_hits_to_get;
         P.filter.force_spacing = 0;  // applied below, after the contamination step, where the run loop applies it (PairedAligner.cpp:633-651)
+        // SAM text from the device when the output goes through PreformattedSAMFormat (SNAPB200_HOST_SAM=1: the reference's writer formats)
+        deviceSam_ = PreformattedSAMFormat::installed() && ctx->options->outputFileTemplate != NULL &&
+                     FileFormat::SAM[0]->isFormatOf(ctx->options->outputFileTemplate) && getenv("SNAPB200_HOST_SAM") == NULL;
+        useM_ = ctx->options->useM;
         PairBatch pb[2];
         Timing tm;
         AlignerContext2::SpliceBatch splices;  // the thread's novel-splice intervals between two appends
@@ -371,11 +446,14 @@ private:
         std::vector<uint8_t> cbases, cquals;          // clipped, what the aligner sees (device reads only)
         std::vector<uint32_t> coff;
         std::vector<int> devIdx;                      // index in the device batch, -1: not aligned (the run loops' early-outs)
+        std::vector<uint16_t> dFront, dClip;          // Read::getFrontClippedLength / getDataLength of the device reads (SAM stage)
+        std::vector<char> gIds, gBases, gQuals;       // the unclipped device reads gathered, only when some read of the batch is not one
+        std::vector<unsigned> gIdOff, gOff;
         std::vector<const char *> readGroups;         // Read::getReadGroup(): owned by the reader context, outlives the batch
         ReadStore() { clear(); }
         void clear()
         {
-            ids.clear(); bases.clear(); quals.clear(); cbases.clear(); cquals.clear(); readGroups.clear(); devIdx.clear();
+            ids.clear(); bases.clear(); quals.clear(); cbases.clear(); cquals.clear(); readGroups.clear(); devIdx.clear(); dFront.clear(); dClip.clear();
             idOff.assign(1, 0); off.assign(1, 0); coff.assign(1, 0);
         }
         unsigned size() const { return (unsigned)off.size() - 1; }
@@ -394,9 +472,38 @@ private:
                 cbases.insert(cbases.end(), (const uint8_t *)r->getData(), (const uint8_t *)r->getData() + r->getDataLength());
                 cquals.insert(cquals.end(), (const uint8_t *)r->getQuality(), (const uint8_t *)r->getQuality() + r->getDataLength());
                 coff.push_back((uint32_t)cbases.size());
+                dFront.push_back((uint16_t)r->getFrontClippedLength());
+                dClip.push_back((uint16_t)r->getDataLength());
             } else {
                 devIdx.push_back(-1);
             }
+        }
+        // the device reads as snapb200_sam_reads: unclipped bases and qualities, ids, clipping
+        snapb200_sam_reads samBatch()
+        {
+            static const uint8_t none8 = 0;
+            static const uint16_t none16 = 0;
+            snapb200_sam_reads s;
+            s.n = deviceSize();
+            if (s.n == size()) {
+                s.offsets = &off[0]; s.id_offsets = &idOff[0];
+                s.bases = bases.empty() ? &none8 : (const uint8_t *)&bases[0]; s.quals = quals.empty() ? &none8 : (const uint8_t *)&quals[0];
+                s.ids = ids.empty() ? &none8 : (const uint8_t *)&ids[0];
+            } else {
+                gIds.clear(); gBases.clear(); gQuals.clear(); gIdOff.assign(1, 0); gOff.assign(1, 0);
+                for (unsigned i = 0; i < size(); i++) {
+                    if (devIdx[i] < 0) continue;
+                    gIds.insert(gIds.end(), ids.begin() + idOff[i], ids.begin() + idOff[i + 1]);
+                    gBases.insert(gBases.end(), bases.begin() + off[i], bases.begin() + off[i + 1]);
+                    gQuals.insert(gQuals.end(), quals.begin() + off[i], quals.begin() + off[i + 1]);
+                    gIdOff.push_back((unsigned)gIds.size()); gOff.push_back((unsigned)gBases.size());
+                }
+                s.offsets = &gOff[0]; s.id_offsets = &gIdOff[0];
+                s.bases = gBases.empty() ? &none8 : (const uint8_t *)&gBases[0]; s.quals = gQuals.empty() ? &none8 : (const uint8_t *)&gQuals[0];
+                s.ids = gIds.empty() ? &none8 : (const uint8_t *)&gIds[0];
+            }
+            s.front_clip = dFront.empty() ? &none16 : &dFront[0]; s.clipped_len = dClip.empty() ? &none16 : &dClip[0];
+            return s;
         }
         // the clipped read i of another store, as a device read of this one (contamination sub-batches)
         void addFrom(const ReadStore &o, unsigned i)
@@ -510,15 +617,17 @@ private:
 
     struct Timing {
         double drain, wait, replay, filterHost, unaligned, gtf, write, deviceMs;
+        unsigned long devicePairs;  // pairs whose SAM lines the device formatted
         unsigned long reads, batches, hostPairs;
         std::vector<unsigned long> perDevice;  // batches each device took
-        Timing() : drain(0), wait(0), replay(0), filterHost(0), unaligned(0), gtf(0), write(0), deviceMs(0), reads(0), batches(0), hostPairs(0) {}
+        Timing() : drain(0), wait(0), replay(0), filterHost(0), unaligned(0), gtf(0), write(0), deviceMs(0), devicePairs(0), reads(0), batches(0), hostPairs(0) {}
         void report() const
         {
             if (getenv("SNAPB200_SHIM_TIMING") == NULL) return;
             fprintf(stderr, "[snapb200 shim] paired thread: %lu reads in %lu batches, drain %.2f s, waiting for the device %.2f s (device busy %.2f s), "
-                            "host replay %.2f s (UnalignedRead %.2f, GTF counters %.2f, writePair+stats %.2f, reference filter for %lu overflow pairs %.2f)\n",
-                    reads, batches, drain, wait, deviceMs * 1e-3, replay, unaligned, gtf, write, hostPairs, filterHost);
+                            "host replay %.2f s (UnalignedRead %.2f, GTF counters %.2f, writePair+stats %.2f with the SAM lines of %lu pairs formatted on the device, "
+                            "reference filter for %lu overflow pairs %.2f)\n",
+                    reads, batches, drain, wait, deviceMs * 1e-3, replay, unaligned, gtf, write, devicePairs, hostPairs, filterHost);
             fprintf(stderr, "[snapb200 shim]   batches per device:");
             for (size_t d = 0; d < perDevice.size(); d++) fprintf(stderr, " gpu%zu=%lu", d, perDevice[d]);
             fprintf(stderr, "\n");
@@ -530,7 +639,8 @@ private:
         unsigned n;                      // pairs drained (device pairs: s0.deviceSize())
         std::vector<snapb200_rna_batch *> objs;  // one per device, created on first use
         int dev;
-        PairBatch() : n(0), dev(0) {}
+        bool sam;                        // submitted with the SAM stage
+        PairBatch() : n(0), dev(0), sam(false) {}
         void destroy() { for (size_t d = 0; d < objs.size(); d++) if (objs[d]) snapb200_rna_batch_destroy(objs[d]); objs.clear(); }
     };
 
@@ -561,7 +671,25 @@ private:
         if (b.objs.size() < devs.size()) b.objs.resize(devs.size(), NULL);
         if (b.objs[b.dev] == NULL) check(snapb200_rna_batch_create(devs[b.dev].annotation, devs[b.dev].genome, devs[b.dev].transcriptome, &b.objs[b.dev]));
         snapb200_read_batch r0 = b.s0.batch(), r1 = b.s1.batch();
-        check(snapb200_rna_batch_submit(b.objs[b.dev], &P, &r0, &r1));
+        // one read group per batch (FASTQ input: ReaderContext::defaultReadGroup for every read); otherwise the host formats this batch
+        const char *group = NULL;
+        bool uniform = true, first = true;
+        for (unsigned i = 0; i < b.n && uniform; i++)
+            for (int e = 0; e < 2; e++) {
+                const ReadStore &st = e ? b.s1 : b.s0;
+                if (st.devIdx[i] < 0) continue;
+                const char *g = st.readGroups[i];
+                if (g == READ_GROUP_FROM_AUX) { uniform = false; break; }
+                if (first) { group = g; first = false; }
+                else if (g != group && !(g != NULL && group != NULL && strcmp(g, group) == 0)) { uniform = false; break; }
+            }
+        b.sam = deviceSam_ && uniform;
+        if (b.sam) {
+            snapb200_sam_reads q0 = b.s0.samBatch(), q1 = b.s1.samBatch();
+            check(snapb200_rna_batch_submit_sam(b.objs[b.dev], &P, &r0, &r1, &q0, &q1, useM_ ? 1 : 0, group));
+        } else {
+            check(snapb200_rna_batch_submit(b.objs[b.dev], &P, &r0, &r1));
+        }
     }
 
     void replay(PairBatch &b, const std::vector<DeviceSet> &devs, const snapb200_rna_params &P, GpuSeedCharacterizer *partial, AlignerContext *ctx,
@@ -687,7 +815,16 @@ private:
                 if (result.mapq[0] < 50) result.mapq[0] /= 2;
                 if (result.mapq[1] < 50) result.mapq[1] /= 2;
             }
+            if (b.sam && v.sam_line_offsets != NULL) {
+                // the pair's two lines came back with the batch: writePair only places them (an empty range: the host formats)
+                const uint64_t *lo = v.sam_line_offsets + 2 * (size_t)di;
+                if (lo[1] > lo[0] && lo[2] > lo[1]) {
+                    PreformattedSAMFormat::arm(v.sam_text + lo[0], (size_t)(lo[1] - lo[0]), v.sam_text + lo[1], (size_t)(lo[2] - lo[1]));
+                    tm.devicePairs++;
+                }
+            }
             AlignerContext2::writePair(pc, &r0, &r1, &result);
+            PreformattedSAMFormat::disarm();
             AlignerContext2::updateStats(pc, &r0, &r1, &result);
         }
         tm.write += now() - tw;
@@ -733,4 +870,6 @@ private:
 
     unsigned batch_;
     bool owner_;
+    bool deviceSam_;  // paired loop: the SAM lines come back with the batch (PreformattedSAMFormat installed and the output is a .sam file)
+    bool useM_;
 };

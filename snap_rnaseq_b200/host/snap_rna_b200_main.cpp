@@ -32,6 +32,8 @@ int main(int argc, const char **argv)
             if (strcmp(argv[i], "single") == 0 || strcmp(argv[i], "paired") == 0) {
                 // the hash tables live in HBM only: the host keeps the genome text (SAM output) and the seed length
                 setenv("SNAPB200_GENOME_ONLY", "1", 1);
+                // SAM lines that come back formatted from the device are placed by the reference's writer as they are (RNA pair loop)
+                PreformattedSAMFormat::install();
                 // optional: HBM loading overlaps the host-side loading
                 GpuAlignerExtension::prefetch(argc - (i + 1), argv + i + 1, strcmp(argv[i], "paired") == 0);
             }

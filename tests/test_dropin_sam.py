@@ -179,3 +179,39 @@ def test_rna_mode_device_scratch_overflow_falls_back_to_the_reference_classes(wo
     assert_same(sam_records(os.path.join(d, "ref_o.sam")), sam_records(os.path.join(d, "gpu_o.sam")), 8000)
     for f in SIDE_FILES:
         assert open(os.path.join(d, "ref_o." + f), "rb").read() == open(os.path.join(d, "gpu_o." + f), "rb").read(), f
+
+
+def test_rna_mode_sam_lines_are_formatted_on_the_device(workspace):
+    """The pair loop's SAM text comes back with the batch (snapb200_rna_batch_submit_sam) and the reference's writer only places
+    it (PreformattedSAMFormat in the shim): the timing report must say so, the records must be those of the reference -- with = / X
+    and with -M, with a read group (-rg), and in sorted output (-so), where the reference's sorter reads its keys back from the
+    placed lines -- and SNAPB200_HOST_SAM=1 (the reference's SAMFormat formats every line) must give the same file."""
+    d = workspace
+
+    def formatted(out):
+        return sum(int(l.split("with the SAM lines of ")[1].split(" ")[0]) for l in out.split("\n") if "with the SAM lines of " in l)
+
+    def b200(args, **extra):
+        env = dict(os.environ, SNAPB200_SHIM_TIMING="1", SNAPB200_SHIM_BATCH="1024", **extra)
+        r = subprocess.run([B200] + args, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        return r.stdout
+
+    base = ["paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq"]
+    for tag, opts in (("plain", ["-t", "2"]), ("m", ["-t", "2", "-M"]), ("rg", ["-t", "2", "-rg", "sampleA"])):
+        run([REF] + base + ["-o", f"ref_d{tag}.sam"] + opts, d)
+        out = b200(base + ["-o", f"gpu_d{tag}.sam"] + opts)
+        assert formatted(out) > 3900, out[-2000:]  # all but the pairs the run loop never aligns
+        a, b = sam_records(os.path.join(d, f"ref_d{tag}.sam")), sam_records(os.path.join(d, f"gpu_d{tag}.sam"))
+        assert_same(a, b, 8000)
+    assert any("RG:Z:sampleA" in r for r in b)
+    out = b200(base + ["-o", "gpu_dhost.sam", "-t", "2"], SNAPB200_HOST_SAM="1")
+    assert formatted(out) == 0
+    assert_same(sam_records(os.path.join(d, "ref_dplain.sam")), sam_records(os.path.join(d, "gpu_dhost.sam")), 8000)
+    # sorted output, one thread: the same records in the same order
+    run([REF] + base + ["-o", "ref_dso.sam", "-t", "1", "-so"], d)
+    out = b200(base + ["-o", "gpu_dso.sam", "-t", "1", "-so"])
+    assert formatted(out) > 3900
+    body = lambda p: [l for l in open(os.path.join(d, p)).read().split("\n") if l and not l.startswith("@")]
+    a, b = body("ref_dso.sam"), body("gpu_dso.sam")
+    assert len(a) == 8000 and a == b

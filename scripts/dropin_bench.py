@@ -43,7 +43,7 @@ def run_dropin(pairs=300_000, mbp=40, threads=None, reps=2, env=None):
                 align_ms = float(stats[0].split("(at:")[1].split(")")[0]) if stats and "(at:" in stats[0] else None
                 if best is None or t < best["wall_s"]:
                     best = {"wall_s": t, "stats_line": stats, "align_phase_s": align_ms / 1e3 if align_ms else None}
-                shim_lines += [l for l in out.split("\n") if "[snapb200 shim]" in l]
+                shim_lines += [l for l in out.split("\n") if "[snapb200 " in l]
             recs = sorted(l for l in open(os.path.join(d, tag + ".sam")) if not l.startswith("@"))
             side = {}
             for f in sorted(os.listdir(d)):

@@ -501,7 +501,8 @@ static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
 {
     const uint32_t n = b->n;
     const bool timing = getenv("SNAPB200_RNA_TIMING") != nullptr;  // where a batch spends its time on the device side (stderr)
-    double tt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tm = rna_now(), tn;
+    double tt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tm = rna_now(), tn;
+    const double t_begin = tm;
 #define RNA_MARK(i) do { tn = rna_now(); tt[i] += tn - tm; tm = tn; } while (0)
     const snapb200_rna_params &P = b->params;
     snapb200_read_batch r[2];
@@ -520,7 +521,9 @@ static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
         snapb200_session *s = slot.s;
         RNA_MARK(0);
         for (int e = 0; e < 2; e++) {
-            if ((rc = snapb200_session_upload(s, 0, &r[e])) || (rc = snapb200_session_run_single(s, &P.transcriptome))) return rc;
+            if ((rc = snapb200_session_upload(s, 0, &r[e]))) return rc;
+            RNA_MARK(7);
+            if ((rc = snapb200_session_run_single(s, &P.transcriptome))) return rc;
             RNA_MARK(1);
             if ((rc = R.d_hoff[e].ensure((size_t)(n + 1) * 4))) return rc;
             size_t tmp_bytes = 0;
@@ -555,7 +558,9 @@ static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
         snapb200_session *s = slot.s;
         RNA_MARK(3);
         if ((rc = snapb200_session_upload(s, 0, &r[0])) || (rc = snapb200_session_upload(s, 1, &r[1]))) return rc;
+        RNA_MARK(8);
         if ((rc = snapb200_session_run_paired(s, &P.paired))) return rc;
+        RNA_MARK(9);
         if ((rc = R.h_pairs.ensure((size_t)n * sizeof(snapb200_paired_result)))) return rc;
         rc = snapb200_session_download_paired(s, R.h_pairs.as<snapb200_paired_result>());
         if (rc) return rc;  // includes ERR_LIMIT: the reference exits there
@@ -655,8 +660,9 @@ static int rna_run_on(snapb200_rna_batch *b, RnaResources &R)
         RNA_MARK(6);
     }
     if (timing)
-        fprintf(stderr, "[snapb200 rna] %u pairs on device %d: wait T slot %.3f s, multi-hit kernels %.3f, compaction + download %.3f, wait G slot %.3f, paired %.3f, "
-                        "CharacterizeSeeds x2 %.3f, filter + downloads %.3f\n", n, b->genome->device, tt[0], tt[1], tt[2], tt[3], tt[4], tt[5], tt[6]);
+        fprintf(stderr, "[snapb200 rna] %u pairs on device %d, %.3f s in all: wait T slot %.3f s, multi-hit uploads %.3f + kernels %.3f, compaction + download %.3f, "
+                        "wait G slot %.3f, paired upload %.3f + kernels %.3f + download %.3f, CharacterizeSeeds x2 %.3f, filter + SAM + downloads %.3f\n", n,
+                b->genome->device, rna_now() - t_begin, tt[0], tt[7], tt[1], tt[2], tt[3], tt[8], tt[9], tt[4], tt[5], tt[6]);
 #undef RNA_MARK
     return 0;
 }

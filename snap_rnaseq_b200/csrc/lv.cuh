@@ -471,6 +471,7 @@ __device__ __forceinline__ int lane_run_rt(const int DIR, const uint8_t *p, cons
     for (;;) {
         // the words the next step needs: one further along the walk (up for DIR > 0, down for DIR < 0)
         pw += DIR; tw += DIR;
+        // (a second word of look-ahead for the text was measured: 62.6 against 61.8 ms per million pairs, profiles/r2_ab_8.log)
         const uint32_t pn = DIR > 0 ? pw[1] : pw[0], tn = DIR > 0 ? tw[1] : tw[0];
         uint32_t x = __funnelshift_r(p0, p1, psh) ^ __funnelshift_r(t0, t1, tsh);
         if (x) {

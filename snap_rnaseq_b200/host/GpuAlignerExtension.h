@@ -276,6 +276,8 @@ public:
     // reference's own loading of its host-side indices and GTF (AlignerContext::initialize).  argv: what follows the sub-command --
     // <genome-idx> <transcriptome-idx> <gtf> ... [-ct <contamination-idx>] (SingleAligner.cpp:52-72, PairedAligner.cpp:290-310).
     // Optional: without it the first worker thread opens the handles.
+    static double sinceProcessStart() { return now() - processStart(); }  // the first call fixes the origin (snap-rna-b200's main makes it)
+
     static void prefetch(int argc, const char **argv, bool paired)
     {
         processStart();

@@ -15,8 +15,17 @@
 
 #include "GpuAlignerExtension.h"
 
+static void reportExit()
+{
+    if (getenv("SNAPB200_SHIM_TIMING") != NULL)
+        fprintf(stderr, "[snapb200 shim] process exits %.2f s after its start (the handlers registered later, the CUDA runtime's among them, have run)\n",
+                GpuAlignerExtension::sinceProcessStart());
+}
+
 int main(int argc, const char **argv)
 {
+    GpuAlignerExtension::sinceProcessStart();
+    atexit(reportExit);
     const char *version = "0.1alpha-b200";
     printf("Welcome to SNAP-RNA version %s.\n\n", version);
     if (argc < 2) {
@@ -43,6 +52,9 @@ int main(int argc, const char **argv)
             } else if (strcmp(argv[i], "paired") == 0) {
                 PairedAlignerContext paired(new GpuAlignerExtension());
                 paired.runAlignment(argc - (i + 1), argv + i + 1, version, &nArgsConsumed);
+                if (getenv("SNAPB200_SHIM_TIMING") != NULL)
+                    fprintf(stderr, "[snapb200 shim] runAlignment returned %.2f s after process start (the reference's end-of-run GTF analysis included)\n",
+                            GpuAlignerExtension::sinceProcessStart());
             } else {
                 fprintf(stderr, "Invalid command: %s\n", argv[i]);
                 soft_exit(1);

@@ -269,6 +269,15 @@ typedef struct {
     uint32_t tlocation;       /* PairedAlignmentResult::tlocation */
 } snapb200_sam_alignment;
 
+/* use_m of the entry points below: 0, or SNAPB200_SAM_USE_M for AlignerOptions::useM (-M: M instead of = and X); with
+ * SNAPB200_SAM_BAM_RECORDS or-ed in, every "line" is the BAM record BAMFormat::writeRead puts into the writer's buffer instead
+ * (SNAPLib/Bam.cpp:596-790: the BAMAlignment head with bin / n_cigar_op / l_seq, NUL-terminated name -- not cut at a space --, binary
+ * CIGAR operations, 4-bit bases, qualities minus '!', RG:Z / PG:Z:SNAP / NM:i), uncompressed: BGZF stays the writer's filter.  NM of
+ * a read without a location is an uninitialised variable in the reference (Bam.cpp:644); -1 is written.  A name of more than 254
+ * bytes (the reference exits, Bam.cpp:723): SNAPB200_ERR_LIMIT. */
+#define SNAPB200_SAM_USE_M 1
+#define SNAPB200_SAM_BAM_RECORDS 2
+
 /* Replaces SimpleReadWriter::writeRead / writePair (SNAPLib/ReadWriter.cpp:90-217) over SAMFormat::writeRead
  * (SNAPLib/SAM.cpp:803-1153: getSAMData, computeCigarString with LandauVishkinWithCigar at k = MAX_K-1, soft clips,
  * FLAG/RNEXT/PNEXT/TLEN, the /1 /2 QNAME trimming, "\tPG:Z:SNAP\tNM:i:%d") for genome alignments of a batch.

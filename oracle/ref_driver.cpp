@@ -610,7 +610,10 @@ int ref_sam_batch_rna(void *h, void *h_transcriptome, void *gtf, const snapb200_
     const Genome *genome = idx->getGenome();
     const Genome *transcriptome = h_transcriptome ? ((GenomeIndex *)h_transcriptome)->getGenome() : NULL;
     DataWriterSupplier *dws = DataWriterSupplier::create(path);
-    ReadWriterSupplier *rws = ReadWriterSupplier::create(FileFormat::SAM[use_m ? 1 : 0], dws, genome, transcriptome, (const GTFReader *)gtf);
+    // use_m: bit 0 = AlignerOptions::useM, bit 1 = BAM records (BAMFormat::writeRead) instead of SAM lines -- straight into the file,
+    // without the gzip filter BAMFormat::getWriterSupplier would add (Bam.cpp:515-536)
+    const FileFormat *format = (use_m & 2) ? FileFormat::BAM[use_m & 1] : FileFormat::SAM[use_m & 1];
+    ReadWriterSupplier *rws = ReadWriterSupplier::create(format, dws, genome, transcriptome, (const GTFReader *)gtf);
     ReadWriter *w = rws->getWriter();
     double t0 = now_s();
     for (unsigned i = 0; i < r0->n; i++) {

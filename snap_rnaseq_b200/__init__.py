@@ -142,7 +142,8 @@ class Snapb200(BatchLib):
         self.lib.snapb200_rna_batch_destroy(b)
 
     def rna_batch_submit(self, b, params, b0, b1, sam=None):
-        """sam = (SamReads of mate 0, of mate 1, use_m, read group or None): also format the SAM lines (snapb200_rna_batch_submit_sam)."""
+        """sam = (SamReads of mate 0, of mate 1, use_m [or SNAPB200_SAM_* flags: 2 = BAM records], read group or None): also format the
+        SAM lines (snapb200_rna_batch_submit_sam)."""
         if sam is None:
             self._check(self.lib.snapb200_rna_batch_submit(b, C.byref(params), b0.byref(), b1.byref()), "rna_batch_submit")
         else:

@@ -209,11 +209,12 @@ class BatchLib:
         self._check(self.fn("fastq_record_start")(A.p8(t), C.c_uint64(len(raw)), C.byref(off)), "fastq_record_start")
         return int(off.value)
 
-    def sam(self, handle, reads0, reads1, aln0, aln1, use_m=False, read_group=None, out=None, rna=None):
+    def sam(self, handle, reads0, reads1, aln0, aln1, use_m=False, read_group=None, out=None, rna=None, bam=False):
         """SimpleReadWriter::writeRead / writePair over SAMFormat::writeRead for a batch -> (SAM bytes, line_offsets).
         out: a uint8 array to write into with ONE call (returns a view of it); otherwise measure first, then write.
         rna = (annotation handle [the reference: its GTFReader], transcriptome index handle): alignments may be transcriptome ones
-        (snapb200_sam_batch_rna)."""
+        (snapb200_sam_batch_rna).  bam: BAM records (SNAPB200_SAM_BAM_RECORDS) instead of SAM lines."""
+        use_m = int(bool(use_m)) | (2 if bam else 0)
         a0 = np.ascontiguousarray(aln0, A.SAM_ALIGNMENT)
         a1 = np.ascontiguousarray(aln1, A.SAM_ALIGNMENT) if reads1 is not None else None
         n_lines = reads0.n * (2 if reads1 is not None else 1)

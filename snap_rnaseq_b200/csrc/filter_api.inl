@@ -467,7 +467,8 @@ static int rna_sam_stage(snapb200_rna_batch *b, RnaResources &R, cudaStream_t st
     if ((rc = R.ds_cigars.ensure((size_t)n_lines * a.cigar_stride)) || (rc = R.ds_lines.ensure((size_t)n_lines * sizeof(SamLine))) ||
         (rc = R.ds_len.ensure((size_t)(n_lines + 1) * 8)) || (rc = R.ds_lineoff.ensure((size_t)(n_lines + 1) * 8)) || (rc = R.ds_ctr.ensure(sizeof(Counters))))
         return rc;
-    a.n_lines = n_lines; a.in.paired = 1; a.use_m = b->use_m; a.rg = R.ds_rg.as<char>(); a.rg_len = (uint32_t)rg_len;
+    a.n_lines = n_lines; a.in.paired = 1; a.use_m = b->use_m & SNAPB200_SAM_USE_M; a.bam = (b->use_m & SNAPB200_SAM_BAM_RECORDS) != 0;
+    a.rg = R.ds_rg.as<char>(); a.rg_len = (uint32_t)rg_len;
     a.rl = std::max(32u, (b->sam_max_len + 15) & ~15u);
     a.cigars = R.ds_cigars.as<char>(); a.lines = R.ds_lines.as<SamLine>(); a.line_len = R.ds_len.as<uint64_t>(); a.line_off = R.ds_lineoff.as<uint64_t>();
     a.ctr = R.ds_ctr.as<Counters>();

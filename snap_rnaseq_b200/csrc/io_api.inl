@@ -277,7 +277,8 @@ static int sam_batch_impl(snapb200_index *idx, const DevIndex *tix, const FltTab
     if ((rc = io.cigars.ensure((size_t)n_lines * a.cigar_stride)) || (rc = io.lines.ensure((size_t)n_lines * sizeof(SamLine))) ||
         (rc = io.line_len.ensure((size_t)(n_lines + 1) * 8)) || (rc = io.line_off.ensure((size_t)(n_lines + 1) * 8)) || (rc = io.err.ensure(sizeof(Counters))))
         return rc;
-    a.n_lines = n_lines; a.in.paired = paired; a.use_m = use_m; a.rg = io.rg.as<char>(); a.rg_len = (uint32_t)rg_len;
+    a.n_lines = n_lines; a.in.paired = paired; a.use_m = use_m & SNAPB200_SAM_USE_M; a.bam = (use_m & SNAPB200_SAM_BAM_RECORDS) != 0;
+    a.rg = io.rg.as<char>(); a.rg_len = (uint32_t)rg_len;
     a.rl = std::max(32u, (max_len + 15) & ~15u);
     a.cigars = io.cigars.as<char>(); a.lines = io.lines.as<SamLine>(); a.line_len = io.line_len.as<uint64_t>(); a.line_off = io.line_off.as<uint64_t>();
     a.ctr = io.err.as<Counters>();
@@ -300,8 +301,12 @@ static int sam_batch_impl(snapb200_index *idx, const DevIndex *tix, const FltTab
         Counters c;
         CUDA_TRY(cudaMemcpy(&c, io.err.p, sizeof(c), cudaMemcpyDeviceToHost));
         if (c.n_limit)
-            return set_error(SNAPB200_ERR_LIMIT, "%u spliced CIGAR strings exceed %d characters (the last one on line %u)", c.n_limit, SAM_SPLICED_CIGAR_STRIDE - 1,
-                             c.pad[0] - 1);
+            return set_error(SNAPB200_ERR_LIMIT, "%u records cannot be formatted (a spliced CIGAR of more than %d characters; BAM: a name of more than 254 bytes, a "
+                             "transcript with abutting exons under the read); the last one is line %u", c.n_limit, SAM_SPLICED_CIGAR_STRIDE - 1, c.pad[0] - 1);
+    } else if (use_m & SNAPB200_SAM_BAM_RECORDS) {
+        Counters c;
+        CUDA_TRY(cudaMemcpy(&c, io.err.p, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c.n_limit) return set_error(SNAPB200_ERR_LIMIT, "BAM: %u read names exceed 254 bytes (the last one on line %u)", c.n_limit, c.pad[0] - 1);
     }
     if (!out) return 0;
     const uint64_t total = line_offsets[n_lines];

@@ -167,6 +167,8 @@ struct SamFields {
     uint32_t clip_before, clip_after;
     int direction;  // FORWARD for an unmapped read (SAM.cpp:857-863)
     bool mapped;
+    int ref_index, next_ref_index;  // pieceIndex / matePieceIndex as getSAMData leaves them (-1: none): BAM's refID / next_refID
+    bool mate_mapped;
 };
 
 // Genome::getPieceAtLocation (Genome.cpp:357-374)
@@ -194,6 +196,8 @@ SNAP_HD SamFields sam_fields(const uint32_t *piece_begin, int n_pieces, const Sa
     f.tlen = 0;
     f.mapq = me.mapq;
     f.mapped = me.location != SAM_INVALID_LOC;
+    f.ref_index = f.next_ref_index = -1;
+    f.mate_mapped = false;
     f.direction = f.mapped ? me.direction : 0;
     if (f.direction == 1) {
         f.clip_before = me.full_len - me.clipped_len - me.front_clip;
@@ -205,6 +209,7 @@ SNAP_HD SamFields sam_fields(const uint32_t *piece_begin, int n_pieces, const Sa
     if (f.mapped) {
         if (f.direction == 1) f.flags |= SAMF_REVERSE_COMPLEMENT;
         f.rname = sam_piece_at(piece_begin, n_pieces, me.location);
+        f.ref_index = f.rname;
         f.pos = me.location - piece_begin[f.rname] + 1;
         f.mapq = f.mapq < 0 ? 0 : (f.mapq > 70 ? 70 : f.mapq);
     } else {
@@ -216,9 +221,12 @@ SNAP_HD SamFields sam_fields(const uint32_t *piece_begin, int n_pieces, const Sa
         f.flags |= first_in_pair ? SAMF_FIRST_SEGMENT : SAMF_LAST_SEGMENT;
         if (mate.location != SAM_INVALID_LOC) {
             f.rnext = sam_piece_at(piece_begin, n_pieces, mate.location);
+            f.next_ref_index = f.rnext;
+            f.mate_mapped = true;
             f.pnext = mate.location - piece_begin[f.rnext] + 1;
             if (mate.direction == 1) f.flags |= SAMF_NEXT_REVERSED;
             if (!f.mapped) {
+                f.ref_index = f.rnext;
                 f.rname = f.rnext;
                 f.rnext = SAM_NAME_EQUAL;
                 f.pos = f.pnext;
@@ -226,6 +234,7 @@ SNAP_HD SamFields sam_fields(const uint32_t *piece_begin, int n_pieces, const Sa
         } else {
             f.flags |= SAMF_NEXT_UNMAPPED;
             f.rnext = SAM_NAME_EQUAL;
+            f.next_ref_index = f.ref_index;
             f.pnext = f.pos;
         }
         if (f.mapped && mate.location != SAM_INVALID_LOC) {
@@ -315,6 +324,7 @@ struct SamLine {  // what the measuring pass leaves for the writing pass
     uint32_t cigar_len;     // of the LV string, without soft clips; 0 => "*"
     uint32_t spliced;       // a transcriptome alignment: the string is the whole field as insertSpliceJunctions leaves it (clips included;
                             // empty when the CIGAR could not be computed, SAM.cpp:1046-1061)
+    uint32_t n_ops, ref_len;  // BAM records: the number of CIGAR operations and the reference bases they cover
 };
 
 // One "%d%c" of writeCigar (LandauVishkin.cpp:27-63): a count <= 0 writes nothing.  false: out of space.
@@ -336,9 +346,9 @@ SNAP_HD bool sam_cigar_put(char *out, uint32_t cap, uint32_t *n, int count, char
 // the run ends (so a CIGAR can end in an N run); 'D' runs advance through the transcript, 'I' and 'S' do not; an intron of length
 // <= 0 (abutting or overlapping exons) splits the run but prints nothing.  Returns the length written to out, -1 if cap is too small.
 SNAP_HD int sam_splice_cigar(const FltTables &t, int tr, uint32_t pos, const char *lv, uint32_t lv_len, uint32_t clip_before, uint32_t clip_after,
-                             char *out, uint32_t cap)
+                             char *out, uint32_t cap, uint32_t *n_calls = 0)
 {
-    uint32_t n = 0, prev = pos, current = pos, p = 0;
+    uint32_t n = 0, prev = pos, current = pos, p = 0, calls = 0;
     int stage = 0;  // 0 the clip before, 1 the runs of lv, 2 the clip after
     for (;;) {
         uint32_t length;
@@ -360,6 +370,7 @@ SNAP_HD int sam_splice_cigar(const FltTables &t, int tr, uint32_t pos, const cha
             break;
         }
         if (op == 'I' || op == 'S') {
+            calls++;
             if (!sam_cigar_put(out, cap, &n, (int)length, op)) return -1;
             continue;
         }
@@ -379,16 +390,20 @@ SNAP_HD int sam_splice_cigar(const FltTables &t, int tr, uint32_t pos, const cha
                     if (first == pos) continue;
                     const int step = (int)(first - prev);
                     remainder -= (uint32_t)step;
+                    if (step > 0) calls++;
                     if (step > 0 && !sam_cigar_put(out, cap, &n, step, op)) return -1;
+                    calls++;
                     if (!sam_cigar_put(out, cap, &n, (int)flen, 'N')) return -1;
                     prev += (uint32_t)step;
                 }
             }
         }
+        if (remainder > 0) calls++;  // (the reference tests the unsigned remainder, then prints it as an int)
         if (!sam_cigar_put(out, cap, &n, (int)remainder, op)) return -1;  // the whole run when no junction was found
         current += 1;
         prev = current;
     }
+    if (n_calls) *n_calls = calls;  // insertSpliceJunctions' return value: it also counts the runs that printed nothing
     return (int)n;
 }
 
@@ -543,4 +558,140 @@ SNAP_HD SamWho sam_who(const SamInputs &a, uint32_t line)
     w.mate = w.e ? e0 : e1;
     w.skip = a.aln[w.e][p].skip != 0;
     return w;
+}
+
+// ---- BAM records (BAMFormat::writeRead, SNAPLib/Bam.cpp:596-790) ----------------------------------------------------------------
+// The same fields in binary: the 36-byte BAMAlignment head, NUL-terminated name, CIGAR operations (count << 4 | code of "MIDNSHP=X"),
+// bases as nibbles of "=ACMGRSVTWYHKDBN", qualities minus '!', then the optional fields RG:Z (if there is a read group), PG:Z:SNAP and
+// NM:i (int32).  Unlike the SAM writer this one does not cut the name at a space, and a CIGAR that could not be computed is zero
+// operations.  NM of an unmapped read is an uninitialised variable in the reference (Bam.cpp:644); -1 is written here.
+SNAP_HD int bam_reg2bin(int beg, int end)
+{  // BAMAlignment::reg2bin, Bam.cpp:278-291
+    --end;
+    if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
+    if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
+    if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
+    if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
+    if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+    return 0;
+}
+SNAP_HD uint32_t bam_seq_code(uint8_t c)
+{  // BAMAlignment::SeqToCode (Bam.cpp:266-271): position in "=ACMGRSVTWYHKDBN", 0 for everything else
+    switch (c) {
+        case 'A': return 1; case 'C': return 2; case 'M': return 3; case 'G': return 4; case 'R': return 5; case 'S': return 6; case 'V': return 7;
+        case 'T': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12; case 'D': return 13; case 'B': return 14;
+        case 'N': return 15; default: return 0;
+    }
+}
+SNAP_HD uint32_t bam_cigar_code(char op)
+{  // BAMAlignment::CigarToCode: position in "MIDNSHP=X"
+    switch (op) { case 'I': return 1; case 'D': return 2; case 'N': return 3; case 'S': return 4; case 'H': return 5; case 'P': return 6; case '=': return 7; case 'X': return 8; default: return 0; }
+}
+// The runs of a CIGAR string as BAM operations: counts them and the reference bases they cover (CigarCodeToRefBase: M D N P = X),
+// and writes them to out (4 bytes each, any alignment) unless out is NULL.
+SNAP_HD void bam_cigar_ops(const char *s, uint32_t len, uint32_t *n_ops, uint32_t *ref_len, uint8_t *out)
+{
+    uint32_t p = 0, n = 0, ref = 0;
+    while (p < len) {
+        uint32_t count = 0;
+        while (p < len && s[p] >= '0' && s[p] <= '9') count = count * 10 + (uint32_t)(s[p++] - '0');
+        const char op = p < len ? s[p++] : 'M';
+        const uint32_t code = bam_cigar_code(op);
+        if (code != 1 && code != 4 && code != 5) ref += count;
+        if (out) {
+            const uint32_t v = (count << 4) | code;
+            out[4 * n] = (uint8_t)v; out[4 * n + 1] = (uint8_t)(v >> 8); out[4 * n + 2] = (uint8_t)(v >> 16); out[4 * n + 3] = (uint8_t)(v >> 24);
+        }
+        n++;
+    }
+    *n_ops = n;
+    *ref_len = ref;
+}
+// what computeCigarOps / insertSpliceJunctions return: the operations of the string plus one for each soft clip of a genome alignment
+SNAP_HD void bam_count_ops(const SamFields &f, SamLine *ln, const char *cigar)
+{
+    ln->n_ops = ln->ref_len = 0;
+    if (!f.mapped || ln->cigar_len == 0) return;
+    bam_cigar_ops(cigar, ln->cigar_len, &ln->n_ops, &ln->ref_len, (uint8_t *)0);
+    if (!ln->spliced) ln->n_ops += (f.clip_before > 0) + (f.clip_after > 0);
+}
+SNAP_HD uint32_t bam_record_len(const SamLine &ln, uint32_t full_len, uint32_t rg_len)
+{
+    return 36 + ln.qname_len + 1 + 4 * ln.n_ops + (full_len + 1) / 2 + full_len + (rg_len ? 4 + rg_len : 0) + 8 + 7;  // Bam.cpp:709-714
+}
+SNAP_HD void bam_put_u32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+SNAP_HD void bam_put_u16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+// Everything before the bases: head, name, CIGAR operations.  Returns where the bases start.
+SNAP_HD uint8_t *bam_put_head(uint8_t *p, uint32_t record_len, const uint8_t *id, const SamFields &f, const SamLine &ln, uint32_t full_len, const char *cigar)
+{
+    bam_put_u32(p, record_len - 4);
+    bam_put_u32(p + 4, (uint32_t)f.ref_index);
+    bam_put_u32(p + 8, f.pos - 1);
+    p[12] = (uint8_t)(ln.qname_len + 1);
+    p[13] = (uint8_t)f.mapq;
+    const int ref_len = ln.n_ops > 0 ? (int)ln.ref_len : (int)full_len;
+    const int bin = f.mapped ? bam_reg2bin((int)f.pos - 1, (int)f.pos - 1 + ref_len)
+                             : (f.mate_mapped ? bam_reg2bin((int)f.pnext - 1, (int)f.pnext) : bam_reg2bin(-1, 0));
+    bam_put_u16(p + 14, (uint32_t)bin);
+    bam_put_u16(p + 16, ln.n_ops);
+    bam_put_u16(p + 18, (uint32_t)f.flags);
+    bam_put_u32(p + 20, full_len);
+    bam_put_u32(p + 24, (uint32_t)f.next_ref_index);
+    bam_put_u32(p + 28, f.pnext - 1);
+    bam_put_u32(p + 32, (uint32_t)(int)f.tlen);
+    p += 36;
+    for (uint32_t i = 0; i < ln.qname_len; i++) p[i] = id[i];
+    p[ln.qname_len] = 0;
+    p += ln.qname_len + 1;
+    if (ln.n_ops) {
+        uint32_t k = 0, n, r;
+        if (!ln.spliced && f.clip_before > 0) { bam_put_u32(p, (f.clip_before << 4) | 4u); k = 1; }
+        bam_cigar_ops(cigar, ln.cigar_len, &n, &r, p + 4 * k);
+        k += n;
+        if (!ln.spliced && f.clip_after > 0) { bam_put_u32(p + 4 * k, (f.clip_after << 4) | 4u); k++; }
+        p += 4 * k;
+    }
+    return p;
+}
+// bases and qualities, strided over nlanes cooperating callers; p = where the bases start
+SNAP_HD void bam_put_seq_qual(uint8_t *p, const uint8_t *bases, const uint8_t *quals, uint32_t full_len, int direction, uint32_t lane, uint32_t nlanes)
+{
+    const uint32_t nb = (full_len + 1) / 2;
+    for (uint32_t j = lane; j < nb; j += nlanes) {
+        uint32_t v = 0;
+        for (uint32_t h = 0; h < 2; h++) {
+            const uint32_t i = 2 * j + h;
+            uint32_t code = 0;
+            if (i < full_len) {
+                uint8_t c;
+                if (direction == 1) {
+                    const uint8_t b = bases[full_len - 1 - i];
+                    c = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b == 'N' ? 'N' : b == 'n' ? 'n' : 0;
+                } else {
+                    c = bases[i];
+                }
+                code = bam_seq_code(c);
+            }
+            v = (v << 4) | code;
+        }
+        p[j] = (uint8_t)v;
+    }
+    uint8_t *q = p + nb;
+    for (uint32_t i = lane; i < full_len; i += nlanes) q[i] = (uint8_t)((direction == 1 ? quals[full_len - 1 - i] : quals[i]) - '!');
+}
+// the optional fields; p = first byte after the qualities
+SNAP_HD uint8_t *bam_put_aux(uint8_t *p, const SamLine &ln, const char *rg, uint32_t rg_len)
+{
+    if (rg_len) {
+        p[0] = 'R'; p[1] = 'G'; p[2] = 'Z';
+        for (uint32_t i = 0; i < rg_len; i++) p[3 + i] = (uint8_t)rg[i];
+        p[3 + rg_len] = 0;
+        p += 4 + rg_len;
+    }
+    const uint8_t pg[8] = {'P', 'G', 'Z', 'S', 'N', 'A', 'P', 0};
+    for (int i = 0; i < 8; i++) p[i] = pg[i];
+    p += 8;
+    p[0] = 'N'; p[1] = 'M'; p[2] = 'i';
+    bam_put_u32(p + 3, (uint32_t)ln.edit_distance);
+    return p + 7;
 }

@@ -159,6 +159,7 @@ struct SamArgs {
     DevIndex tix;       // the transcriptome (rna != 0): the text a transcriptome alignment's CIGAR is computed against
     FltTables tables;   // the annotation (rna != 0): transcript of a transcriptome piece, its exon / intron list
     int rna;
+    int bam;            // BAM records (BAMFormat::writeRead) instead of SAM lines
     uint32_t cigar_stride;  // SAM_CIGAR_STRIDE, SAM_SPLICED_CIGAR_STRIDE when rna
     SamNames names;
     SamInputs in;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
         if (line >= a.n_lines) break;
         const SamWho w = sam_who(a.in, line);
         SamLine ln;
-        ln.qname_len = ln.seq_len = ln.qual_len = ln.cigar_len = ln.spliced = 0;
+        ln.qname_len = ln.seq_len = ln.qual_len = ln.cigar_len = ln.spliced = ln.n_ops = ln.ref_len = 0;
         ln.edit_distance = -1;
         if (w.skip) {
             if (lane == 0) { a.lines[line] = ln; a.line_len[line] = 0; }
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
             const unsigned m = __ballot_sync(FULL_MASK, i < qn && id[i] == ' ');
             if (m) first_space = b0 + __ffs((int)m) - 1;
         }
-        ln.qname_len = first_space;
+        ln.qname_len = a.bam ? qn : first_space;  // BAMFormat::writeRead copies qnameLen bytes (Bam.cpp:744)
         // SEQ / QUAL lengths as "%.*s" prints them: up to the first NUL
         uint32_t seq_len = w.me.full_len, qual_len = w.me.full_len;
         #pragma unroll 1
@@ -233,8 +234,8 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
             if (m && seq_len == w.me.full_len) seq_len = b0 + __ffs((int)m) - 1;
             if (mq && qual_len == w.me.full_len) qual_len = b0 + __ffs((int)mq) - 1;
         }
-        ln.seq_len = seq_len;
-        ln.qual_len = qual_len;
+        ln.seq_len = a.bam ? w.me.full_len : seq_len;
+        ln.qual_len = a.bam ? w.me.full_len : qual_len;
         // CIGAR (computeCigarString, SAM.cpp:1159-1204): the clipped read, reverse-complemented for RC, against the genome -- or, for
         // a transcriptome alignment, against the transcriptome at tlocation, with the junctions of its transcript inserted
         // (SAM.cpp:1046-1061)
@@ -272,21 +273,34 @@ __global__ void __launch_bounds__(CTA_THREADS) sam_measure_kernel(const SamArgs 
                 __syncwarp();
                 if (lane == 0) {
                     int n = 0;
+                    uint32_t calls = 0;
                     if (e >= 0) {
                         const int piece = flt_piece_at(a.tables.tpiece_begin, (int)a.tables.n_tpieces, loc);
                         const int tr = piece >= 0 ? a.tables.tpiece_transcript[piece] : -1;
                         n = sam_splice_cigar(a.tables, tr, loc - a.tables.tpiece_begin[piece < 0 ? 0 : piece] + 1, runs, n_runs, f.clip_before, f.clip_after,
-                                             cig, a.cigar_stride);
+                                             cig, a.cigar_stride, &calls);
                         if (n < 0) { atomicAdd(&a.ctr->n_limit, 1u); atomicMax(&a.ctr->pad[0], line + 1); ln.spliced = 2; n = 0; }
                     }
                     ln.cigar_len = (uint32_t)n;
+                    if (a.bam && ln.spliced != 2) {
+                        // n_cigar_op is insertSpliceJunctions' return value, which also counts runs that printed nothing (an intron of
+                        // length <= 0): the reference then emits operations it never wrote.  Such a record is left to the caller.
+                        uint32_t ops, ref;
+                        bam_cigar_ops(cig, ln.cigar_len, &ops, &ref, (uint8_t *)0);
+                        if (ops != calls) { atomicAdd(&a.ctr->n_limit, 1u); atomicMax(&a.ctr->pad[0], line + 1); ln.spliced = 2; }
+                    }
                 }
                 __syncwarp();
             }
         }
         if (lane == 0) {
+            if (a.bam) {
+                bam_count_ops(f, &ln, cig);
+                if (ln.qname_len > 254) { atomicAdd(&a.ctr->n_limit, 1u); atomicMax(&a.ctr->pad[0], line + 1); ln.spliced = 2; }  // the reference exits (Bam.cpp:723)
+            }
             a.lines[line] = ln;
-            a.line_len[line] = ln.spliced == 2 ? 0 : sam_line_len(f, ln, a.names, a.rg_len);  // 2: the spliced CIGAR does not fit its slot
+            // spliced == 2: the record is the caller's (CIGAR too long for its slot, or one of the cases above)
+            a.line_len[line] = ln.spliced == 2 ? 0 : (a.bam ? bam_record_len(ln, w.me.full_len, a.rg_len) : sam_line_len(f, ln, a.names, a.rg_len));
         }
     }
 }
@@ -309,6 +323,14 @@ __global__ void __launch_bounds__(256) sam_write_kernel(const SamArgs a)
     const SamFields f = sam_fields(a.ix.piece_begin, (int)a.ix.n_pieces, w.me, w.has_mate, w.first_in_pair, w.mate);
     char *dst = a.out + a.line_off[line];
     const uint32_t total = (uint32_t)(a.line_off[line + 1] - a.line_off[line]);
+    if (a.bam) {
+        uint8_t *rec = (uint8_t *)dst;
+        uint8_t *seq = rec + 36 + ln.qname_len + 1 + 4 * ln.n_ops;
+        if (lane == 0) bam_put_head(rec, total, rd.ids + rd.id_offsets[w.i], f, ln, w.me.full_len, a.cigars + (size_t)line * a.cigar_stride);
+        bam_put_seq_qual(seq, rd.bases + off, rd.quals + off, w.me.full_len, f.direction, lane, SAM_WRITE_LANES);
+        if (lane == 1) bam_put_aux(seq + (w.me.full_len + 1) / 2 + w.me.full_len, ln, a.rg, a.rg_len);
+        return;
+    }
     // SEQ starts where the suffix, QUAL and SEQ end: everything after SEQ has a known length
     uint32_t tail = ln.seq_len + 1 + ln.qual_len + (a.rg_len ? 6 + a.rg_len : 0) + 10 + 6 + sam_digits_i64(ln.edit_distance) + 1;
     char *seq = dst + (total - tail);

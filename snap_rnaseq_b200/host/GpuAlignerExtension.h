@@ -31,6 +31,7 @@
 #include "BaseAligner.h"
 #include "DataWriter.h"
 #include "FileFormat.h"
+#include "GzipDataWriter.h"
 #include "PairedAligner.h"
 #include "SingleAligner.h"
 #include "WGsim.h"
@@ -38,8 +39,8 @@
 
 #include "snapb200.h"
 
-// SAM output whose lines the device has already formatted (snapb200_rna_batch_submit_sam).  snap-rna-b200's main installs one of
-// these over each FileFormat::SAM[] entry before runAlignment: it is the reference's SAMFormat for everything (format detection,
+// SAM / BAM output whose records the device has already formatted (snapb200_rna_batch_submit_sam).  snap-rna-b200's main installs one
+// of these over each FileFormat::SAM[] and FileFormat::BAM[] entry before runAlignment: it is the reference's format for everything (format detection,
 // header, sort keys, writeRead for single reads and for pairs the shim leaves to the host) except that, while the calling thread has
 // armed the two lines of a pair, writeRead copies them instead of formatting -- so SimpleReadWriter::writePair
 // (SNAPLib/ReadWriter.cpp:132-217) keeps doing what it does: both lines into one buffer, a fresh buffer and a second try when they
@@ -52,7 +53,10 @@ public:
     static void install()
     {
         if (installed()) return;
-        for (int k = 0; k < 2; k++) FileFormat::SAM[k] = new PreformattedSAMFormat(FileFormat::SAM[k]);
+        for (int k = 0; k < 2; k++) {
+            FileFormat::SAM[k] = new PreformattedSAMFormat(FileFormat::SAM[k], false);
+            FileFormat::BAM[k] = new PreformattedSAMFormat(FileFormat::BAM[k], true);
+        }
         installed() = true;
     }
     // the two lines of the next writePair on this thread, in the order writePair writes them
@@ -63,15 +67,36 @@ public:
     }
     static void disarm() { pending().armed = false; }
 
-    explicit PreformattedSAMFormat(const FileFormat *inner_) : inner(inner_) {}
+    PreformattedSAMFormat(const FileFormat *inner_, bool bam_) : inner(inner_), bam(bam_) {}
     virtual bool isFormatOf(const char *filename) const { return inner->isFormatOf(filename); }
     virtual void getSortInfo(const Genome *genome, char *buffer, _int64 bytes, unsigned *o_location, unsigned *o_readBytes, int *o_refID = NULL, int *o_pos = NULL) const
     { inner->getSortInfo(genome, buffer, bytes, o_location, o_readBytes, o_refID, o_pos); }
-    // SAMFormat::getWriterSupplier (SNAPLib/SAM.cpp:688-707) with this object as the writers' format
+    // SAMFormat::getWriterSupplier (SNAPLib/SAM.cpp:688-707) / BAMFormat::getWriterSupplier (SNAPLib/Bam.cpp:508-539: the gzip filter,
+    // duplicate marking and the index for sorted output) with this object as the writers' format
     virtual ReadWriterSupplier *getWriterSupplier(AlignerOptions *options, const Genome *genome, const Genome *transcriptome, const GTFReader *gtf) const
     {
         DataWriterSupplier *dataSupplier;
-        if (options->sortOutput) {
+        if (bam) {
+            GzipWriterFilterSupplier *gzipSupplier = DataWriterSupplier::gzip(true, 0x10000, options->numThreads, options->bindToProcessors, options->sortOutput);
+            if (options->sortOutput) {
+                const size_t len = strlen(options->outputFileTemplate);
+                char *tempFileName = (char *)malloc(5 + len);
+                strcpy(tempFileName, options->outputFileTemplate);
+                strcpy(tempFileName + len, ".tmp");
+                DataWriter::FilterSupplier *filters = gzipSupplier;
+                if (!options->noDuplicateMarking) filters = DataWriterSupplier::markDuplicates(genome)->compose(filters);
+                if (!options->noIndex) {
+                    char *indexFileName = (char *)malloc(5 + len);
+                    strcpy(indexFileName, options->outputFileTemplate);
+                    strcpy(indexFileName + len, ".bai");
+                    filters = DataWriterSupplier::bamIndex(indexFileName, genome, gzipSupplier)->compose(filters);
+                }
+                dataSupplier = DataWriterSupplier::sorted(this, genome, tempFileName, options->sortMemory * (1ULL << 30), options->numThreads,
+                                                          options->outputFileTemplate, filters);
+            } else {
+                dataSupplier = DataWriterSupplier::create(options->outputFileTemplate, gzipSupplier);
+            }
+        } else if (options->sortOutput) {
             const size_t len = strlen(options->outputFileTemplate);
             char *tempFileName = (char *)malloc(5 + len);
             strcpy(tempFileName, options->outputFileTemplate);
@@ -105,6 +130,7 @@ public:
 
 private:
     const FileFormat *inner;
+    const bool bam;
 };
 
 // The reference grants `friend class AlignerContext2` in AlignerContext, SingleAlignerContext and
@@ -256,7 +282,7 @@ class GpuAlignerExtension : public AlignerExtension {
 public:
     // batchReads: pairs (or reads) per device batch.  Devices: every visible GPU (SNAPB200_DEVICES=n limits it); batches are dealt
     // round-robin over them from this one process (GTF counters are process-global, so one process drives all).
-    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true), deviceSam_(false), useM_(false)
+    explicit GpuAlignerExtension(unsigned batchReads = 1u << 15) : batch_(batchReads), owner_(true), deviceSam_(false), samFlags_(0)
     {
         if (const char *e = getenv("SNAPB200_SHIM_BATCH")) { int v = atoi(e); if (v >= 16) batch_ = (unsigned)v; }  // tests: many small batches
         AlignerContext2::SpliceBatch::pregrowSetup();  // main thread (copies are made from this object), before the workers allocate
@@ -402,9 +428,10 @@ public:
         P.filter.max_hits_to_get = P.transcriptome.max_hits_to_get;
         P.filter.force_spacing = 0;  // applied below, after the contamination step, where the run loop applies it (PairedAligner.cpp:633-651)
         // SAM text from the device when the output goes through PreformattedSAMFormat (SNAPB200_HOST_SAM=1: the reference's writer formats)
-        deviceSam_ = PreformattedSAMFormat::installed() && ctx->options->outputFileTemplate != NULL &&
-                     FileFormat::SAM[0]->isFormatOf(ctx->options->outputFileTemplate) && getenv("SNAPB200_HOST_SAM") == NULL;
-        useM_ = ctx->options->useM;
+        const bool samFile = ctx->options->outputFileTemplate != NULL && FileFormat::SAM[0]->isFormatOf(ctx->options->outputFileTemplate);
+        const bool bamFile = ctx->options->outputFileTemplate != NULL && !samFile && FileFormat::BAM[0]->isFormatOf(ctx->options->outputFileTemplate);
+        deviceSam_ = PreformattedSAMFormat::installed() && (samFile || bamFile) && getenv("SNAPB200_HOST_SAM") == NULL;
+        samFlags_ = (ctx->options->useM ? SNAPB200_SAM_USE_M : 0) | (bamFile ? SNAPB200_SAM_BAM_RECORDS : 0);
         PairBatch pb[2];
         Timing tm;
         AlignerContext2::SpliceBatch splices;  // the thread's novel-splice intervals between two appends
@@ -688,7 +715,7 @@ private:
         b.sam = deviceSam_ && uniform;
         if (b.sam) {
             snapb200_sam_reads q0 = b.s0.samBatch(), q1 = b.s1.samBatch();
-            check(snapb200_rna_batch_submit_sam(b.objs[b.dev], &P, &r0, &r1, &q0, &q1, useM_ ? 1 : 0, group));
+            check(snapb200_rna_batch_submit_sam(b.objs[b.dev], &P, &r0, &r1, &q0, &q1, samFlags_, group));
         } else {
             check(snapb200_rna_batch_submit(b.objs[b.dev], &P, &r0, &r1));
         }
@@ -872,6 +899,6 @@ private:
 
     unsigned batch_;
     bool owner_;
-    bool deviceSam_;  // paired loop: the SAM lines come back with the batch (PreformattedSAMFormat installed and the output is a .sam file)
-    bool useM_;
+    bool deviceSam_;  // paired loop: the SAM lines / BAM records come back with the batch (PreformattedSAMFormat installed, output .sam or .bam)
+    int samFlags_;    // SNAPB200_SAM_USE_M, SNAPB200_SAM_BAM_RECORDS
 };

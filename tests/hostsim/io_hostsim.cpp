@@ -67,7 +67,7 @@ extern "C" int hostsim_sam_batch(const HostsimIndex *ix, const snapb200_sam_read
                                  const snapb200_sam_alignment *aln0, const snapb200_sam_alignment *aln1, int use_m, const char *read_group,
                                  char *out, uint64_t out_capacity, uint64_t *line_offsets)
 {
-    (void)use_m;
+    const bool bam = (use_m & SNAPB200_SAM_BAM_RECORDS) != 0;
     SamInputs in;
     in.paired = reads1 != NULL;
     in.rd[0] = view(reads0);
@@ -94,7 +94,8 @@ extern "C" int hostsim_sam_batch(const HostsimIndex *ix, const snapb200_sam_read
                 qn -= 2;
         }
         ln.qname_len = qn;
-        for (uint32_t i = 0; i < qn; i++) if (id[i] == ' ') { ln.qname_len = i; break; }
+        ln.spliced = ln.n_ops = ln.ref_len = 0;
+        for (uint32_t i = 0; i < qn && !bam; i++) if (id[i] == ' ') { ln.qname_len = i; break; }
         ln.seq_len = ln.qual_len = w.me.full_len;
         for (uint32_t i = 0; i < w.me.full_len; i++) {
             const uint8_t b = f.direction == 1 ? bases[w.me.full_len - 1 - i] : bases[i];
@@ -111,6 +112,23 @@ extern "C" int hostsim_sam_batch(const HostsimIndex *ix, const snapb200_sam_read
                 ln.edit_distance = e;
                 if (e >= 0) ln.cigar_len = sam_strlen(cig, ix->cigar_stride);
             }
+        }
+        if (bam) {
+            ln.seq_len = ln.qual_len = w.me.full_len;
+            bam_count_ops(f, &ln, cig);
+            const uint32_t len = bam_record_len(ln, w.me.full_len, rg_len);
+            if (out) {
+                if (pos + len > out_capacity) return -1;
+                uint8_t *rec = (uint8_t *)out + pos;
+                uint8_t *seq = bam_put_head(rec, len, id, f, ln, w.me.full_len, cig);
+                if (seq != rec + 36 + ln.qname_len + 1 + 4 * ln.n_ops) return -101;
+                bam_put_seq_qual(seq, bases, quals, w.me.full_len, f.direction, 0, 1);
+                uint8_t *end = bam_put_aux(seq + (w.me.full_len + 1) / 2 + w.me.full_len, ln, read_group, rg_len);
+                if ((uint32_t)(end - rec) != len) return -100;
+            }
+            pos += len;
+            line_offsets[line + 1] = pos;
+            continue;
         }
         const uint32_t len = sam_line_len(f, ln, names, rg_len);
         if (out) {
@@ -333,7 +351,7 @@ extern "C" long long hostsim_unaligned_splices(const FltTables *t, uint32_t read
 
 // ---- the CIGAR of a transcriptome alignment (iofmt.h: sam_splice_cigar) -----------------------------------------------------------
 extern "C" int hostsim_splice_cigar(const FltTables *t, int tr, uint32_t pos, const char *lv, uint32_t lv_len, uint32_t clip_before, uint32_t clip_after,
-                                    char *out, uint32_t cap)
+                                    char *out, uint32_t cap, uint32_t *n_calls)
 {
-    return sam_splice_cigar(*t, tr, pos, lv, lv_len, clip_before, clip_after, out, cap);
+    return sam_splice_cigar(*t, tr, pos, lv, lv_len, clip_before, clip_after, out, cap, n_calls);
 }

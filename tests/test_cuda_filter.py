@@ -172,6 +172,12 @@ def test_rna_batch_is_the_pair_loop_of_the_reference(ref, cuda, ws):
     assert o["sam_text"] == want
     lo = o["sam_line_offsets"].astype(np.int64)
     assert len(lo) == 2 * b0.n + 1 and lo[-1] == len(want) and all(want[lo[k + 1] - 1:lo[k + 1]] == b"\n" for k in range(2 * b0.n))
+    # ... and as BAM records
+    from test_io_fuzz import assert_same_bam
+    cuda.rna_batch_submit(objs[0], P, b0, b1, sam=(sam_reads[0], sam_reads[1], 2, "grp"))
+    o = cuda.rna_batch_wait(objs[0])
+    want = ref.sam(w["rg"], sam_reads[0], sam_reads[1], aln[0], aln[1], False, "grp", rna=(g, w["rt"]), bam=True)[0]
+    assert_same_bam(want, o["sam_text"], "rna batch, BAM records")
     with pytest.raises(RuntimeError, match="clipped_len"):
         bad = A.SamReads(sam_reads[0].offsets, sam_reads[0].bases, sam_reads[0].quals, sam_reads[0].front_clip, sam_reads[0].clipped_len - 1,
                          sam_reads[0].id_offsets, sam_reads[0].ids)
@@ -299,6 +305,12 @@ def test_cuda_sam_of_transcriptome_alignments(ref, cuda, ws):
             assert n_junction > 20
             if clipped:
                 assert sum(1 for ln in want.split(b"\n") if ln and ln.split(b"\t")[5] == b"") > 0  # the empty field of a failed transcriptome CIGAR
+            # the same pairs as BAM records (BAMFormat::writeRead: binary CIGAR operations with the N runs, bin from the reference span)
+            from test_io_fuzz import assert_same_bam, bam_records
+            want = ref.sam(w["rg"], sam_reads[0], sam_reads[1], aln[0], aln[1], use_m, "grp", rna=(g, w["rt"]), bam=True)[0]
+            got, lo = cuda.sam(w["hg"], sam_reads[0], sam_reads[1], aln[0], aln[1], use_m, "grp", rna=(w["ann"], w["ht"]), bam=True)
+            assert_same_bam(want, got, f"BAM records, clipped {clipped} use_m {use_m}")
+            assert int(lo[-1]) == len(want) and len(bam_records(want)) == 2 * b0.n
         want = ref.sam(w["rg"], sam_reads[1], None, aln[1], None, False, "grp", rna=(g, w["rt"]))[0]
         got, _ = cuda.sam(w["hg"], sam_reads[1], None, aln[1], None, False, "grp", rna=(w["ann"], w["ht"]))
         assert bytes(got) == want

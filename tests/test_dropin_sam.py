@@ -3,6 +3,7 @@
 Needs a GPU and oracle/_ref (which travels to the GPU box)."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -215,3 +216,48 @@ def test_rna_mode_sam_lines_are_formatted_on_the_device(workspace):
     body = lambda p: [l for l in open(os.path.join(d, p)).read().split("\n") if l and not l.startswith("@")]
     a, b = body("ref_dso.sam"), body("gpu_dso.sam")
     assert len(a) == 8000 and a == b
+
+
+def bam_body(path):
+    """The records of a BAM file (BGZF members decompressed, header skipped), NM of reads without a location zeroed (uninitialised in
+    the reference, SNAPLib/Bam.cpp:644), sorted."""
+    import gzip
+    import struct
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_io_fuzz import bam_records
+    raw = gzip.open(path).read()
+    assert raw[:4] == b"BAM\x01"
+    l_text, = struct.unpack_from("<i", raw, 4)
+    p = 8 + l_text
+    n_ref, = struct.unpack_from("<i", raw, p)
+    p += 4
+    refs = []
+    for _ in range(n_ref):
+        ln, = struct.unpack_from("<i", raw, p)
+        refs.append(raw[p + 4:p + 4 + ln + 4])
+        p += 4 + ln + 4
+    return refs, sorted(bam_records(raw[p:]))
+
+
+def test_rna_mode_bam_records_are_formatted_on_the_device(workspace):
+    """-o x.bam: the pair loop's BAM records come back with the batch (SNAPB200_SAM_BAM_RECORDS) and go through the reference's
+    writer, BAM filters and BGZF compression; the decompressed record streams must be the same set of records as the reference's,
+    with = / X and with -M, with a read group, and with the reference's own BAMFormat formatting them (SNAPB200_HOST_SAM=1)."""
+    d = workspace
+    base = ["paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq"]
+
+    def formatted(out):
+        return sum(int(l.split("with the SAM lines of ")[1].split(" ")[0]) for l in out.split("\n") if "with the SAM lines of " in l)
+
+    for tag, opts in (("plain", ["-t", "2"]), ("m", ["-t", "2", "-M", "-rg", "sampleB"])):
+        run([REF] + base + ["-o", f"ref_b{tag}.bam"] + opts, d)
+        env = dict(os.environ, SNAPB200_SHIM_TIMING="1", SNAPB200_SHIM_BATCH="1024")
+        r = subprocess.run([B200] + base + ["-o", f"gpu_b{tag}.bam"] + opts, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert formatted(r.stdout) > 3900, r.stdout[-2000:]
+        (refs_a, a), (refs_b, b) = bam_body(os.path.join(d, f"ref_b{tag}.bam")), bam_body(os.path.join(d, f"gpu_b{tag}.bam"))
+        assert refs_a == refs_b and len(a) == 8000 and a == b, next((x, y) for x, y in zip(a, b) if x != y)
+    env = dict(os.environ, SNAPB200_HOST_SAM="1")
+    r = subprocess.run([B200] + base + ["-o", "gpu_bhost.bam", "-t", "2"], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert bam_body(os.path.join(d, "gpu_bhost.bam"))[1] == bam_body(os.path.join(d, "ref_bplain.bam"))[1]

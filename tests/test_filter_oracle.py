@@ -586,7 +586,7 @@ def test_spliced_cigar_matches_the_reference(ref, tmp_path):
             for (s, e) in rows[gi:]:
                 f.write(f'chr1\ts\texon\t{s}\t{e}\t.\t+\t.\tgene_id "O{gi}"; transcript_id "O{gi}.t";\n')
     paths.append(odd)
-    n_cases = n_spliced = n_tail_n = 0
+    n_cases = n_spliced = n_tail_n = n_silent = 0
     for p in paths:
         g = C.c_void_p(lib.ref_gtf_load(p.encode(), (p + ".out").encode()))
         assert lib.ref_gtf_export(g, (p + ".tsv").encode()) == 0
@@ -627,14 +627,17 @@ def test_spliced_cigar_matches_the_reference(ref, tmp_path):
                 rc = lib.ref_splice_cigar(g, tok.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint(len(tok)), tid.encode(), C.c_uint(pos), want, C.c_int(4096))
                 assert rc >= 0
                 got = C.create_string_buffer(4096)
-                n = hs.hostsim_splice_cigar(C.byref(T), C.c_int(tr), C.c_uint(pos), lv, C.c_uint(len(lv)), C.c_uint(cb), C.c_uint(ca), got, C.c_uint(4095))
+                calls = C.c_uint(0)
+                n = hs.hostsim_splice_cigar(C.byref(T), C.c_int(tr), C.c_uint(pos), lv, C.c_uint(len(lv)), C.c_uint(cb), C.c_uint(ca), got, C.c_uint(4095), C.byref(calls))
                 assert n >= 0 and got.raw[:n] == want.value, (p, tid, pos, lv, cb, ca, want.value, got.raw[:max(n, 0)])
+                assert calls.value == rc  # the reference's operator count, which includes runs that print nothing (BAM's n_cigar_op)
+                n_silent += rc != sum(ch.isalpha() or ch == "=" for ch in want.value.decode())
                 n_cases += 1
                 n_spliced += b"N" in want.value
                 n_tail_n += want.value.endswith(b"N")
                 # a slot that is one character too small is reported, never overrun
                 if n > 0:
                     small = C.create_string_buffer(b"\xee" * (n + 8))
-                    assert hs.hostsim_splice_cigar(C.byref(T), C.c_int(tr), C.c_uint(pos), lv, C.c_uint(len(lv)), C.c_uint(cb), C.c_uint(ca), small, C.c_uint(n - 1)) == -1
+                    assert hs.hostsim_splice_cigar(C.byref(T), C.c_int(tr), C.c_uint(pos), lv, C.c_uint(len(lv)), C.c_uint(cb), C.c_uint(ca), small, C.c_uint(n - 1), None) == -1
                     assert small.raw[n - 1:n + 8] == b"\xee" * 9
-    assert n_cases > 500 and n_spliced > 100 and n_tail_n > 5, (n_cases, n_spliced, n_tail_n)
+    assert n_cases > 500 and n_spliced > 100 and n_tail_n > 5 and n_silent > 0, (n_cases, n_spliced, n_tail_n, n_silent)

@@ -158,3 +158,78 @@ def test_fuzz_sam_text_cuda(cuda, cuda_handle, ref, small_index_dir, seed):
             want, _ = ref.sam(h, reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg)
             got, lo = cuda.sam(cuda_handle, reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg)
             assert_same_sam(want, got, f"seed {seed} use_m {use_m} paired {paired}")
+
+
+# ---- BAM records (SNAPB200_SAM_BAM_RECORDS): BAMFormat::writeRead's bytes, uncompressed ------------------------------------------
+def bam_records(raw, mask_undefined=True):
+    """Splits a stream of BAM records.  NM of a read without a location, or whose location has no reference text under it, is an
+    uninitialised variable in the reference (SNAPLib/Bam.cpp:644, 808-825: whatever the previous call left on the stack); those four
+    bytes are zeroed on both sides (records without CIGAR operations)."""
+    import struct
+    raw = bytes(raw)
+    out, p = [], 0
+    while p < len(raw):
+        size, = struct.unpack_from("<i", raw, p)
+        rec = bytearray(raw[p:p + 4 + size])
+        flag, = struct.unpack_from("<H", rec, 18)
+        n_ops, = struct.unpack_from("<H", rec, 16)
+        if mask_undefined and ((flag & 4) or n_ops == 0):
+            rec[-4:] = b"\0\0\0\0"
+        out.append(bytes(rec))
+        p += 4 + size
+    assert p == len(raw)
+    return out
+
+
+def assert_same_bam(want, got, what):
+    a, b = bam_records(want), bam_records(got)
+    assert len(a) == len(b), (what, len(a), len(b))
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert x == y, (what, k, x[:36].hex(), y[:36].hex(), x[36:], y[36:])
+
+
+@pytest.mark.parametrize("seed", range(3 * ROUNDS))
+def test_fuzz_bam_records(hostsim, ref, small_index_dir, seed):
+    """bam_* of iofmt.h (host simulation) against BAMFormat::writeRead through the reference's own writer: random reads, clipping,
+    locations, strands, read groups, ids with spaces (kept in BAM) and /1 /2 suffixes; pairs and single reads; = / X and M."""
+    import io_cases
+    rng = np.random.default_rng(5000 + seed)
+    contigs = small_genome()
+    _, piece_off = synth.snap_layout(contigs, 500)
+    piece_len = np.array([len(v) for v in contigs.values()], np.int64)
+    h = ref.load_index(small_index_dir)
+    for use_m in (False, True):
+        for paired in (False, True):
+            n = int(rng.integers(1, 120))
+            reads, alns = random_sam_case(rng, n, paired, piece_off, piece_len)
+            rg = None if rng.random() < 0.5 else "grp x"
+            want, _ = ref.sam(h, reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg, bam=True)
+            cig, eds = [], []
+            for e in range(len(reads)):
+                b, loc, d = io_cases.clipped_for_cigar(reads[e], alns[e])
+                cg, ed = ref.cigar(h, b, loc, d, use_m, stride=256)
+                cig.append(np.array([c.encode() for c in cg], dtype="S256"))
+                eds.append(np.ascontiguousarray(ed, np.int32))
+            ix, keep = hostsim_index(cig, eds)
+            got, lo = hostsim.sam(C.byref(ix), reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg, bam=True)
+            assert_same_bam(want, got, f"seed {seed} use_m {use_m} paired {paired}")
+            assert int(lo[-1]) == len(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_fuzz_bam_records_cuda(cuda, cuda_handle, ref, small_index_dir, seed):
+    rng = np.random.default_rng(6000 + seed)
+    contigs = small_genome()
+    _, piece_off = synth.snap_layout(contigs, 500)
+    piece_len = np.array([len(v) for v in contigs.values()], np.int64)
+    h = ref.load_index(small_index_dir)
+    for use_m in (False, True):
+        for paired in (False, True):
+            n = int(rng.integers(1, 400))
+            reads, alns = random_sam_case(rng, n, paired, piece_off, piece_len)
+            rg = None if rng.random() < 0.5 else "grp x"
+            want, _ = ref.sam(h, reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg, bam=True)
+            got, lo = cuda.sam(cuda_handle, reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg, bam=True)
+            assert_same_bam(want, got, f"seed {seed} use_m {use_m} paired {paired}")
+            assert int(lo[-1]) == len(want)

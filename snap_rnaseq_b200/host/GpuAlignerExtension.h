@@ -568,6 +568,22 @@ private:
         std::vector<std::string> chrNames;       // genome piece names, behind the chr indices of events and splice records
     };
 
+    struct OpenJob { const char *indexDir, *transcriptomeDir, *contaminationDir; DeviceSet set; };
+    static void *openDevice(void *arg)
+    {
+        OpenJob *j = (OpenJob *)arg;
+        DeviceSet &s = j->set;
+        const double t0 = now();
+        check(snapb200_index_open(j->indexDir, s.device, &s.genome));
+        const double t1 = now();
+        check(snapb200_index_open(j->transcriptomeDir, s.device, &s.transcriptome));
+        if (j->contaminationDir != NULL) check(snapb200_index_open(j->contaminationDir, s.device, &s.contamination));
+        if (getenv("SNAPB200_SHIM_TIMING") != NULL)
+            fprintf(stderr, "[snapb200 shim] device %d: genome index in HBM after %.2f s (CUDA context creation included), the other indices %.2f s; "
+                            "started %.2f s after process start\n", s.device, t1 - t0, now() - t1, t0 - processStart());
+        return NULL;
+    }
+
     static const std::vector<DeviceSet> &deviceSets(const AlignerOptions *options, bool needAnnotation)
     {
         return deviceSets(options->indexDir, options->transcriptomeDir, options->contaminationDir, options->annotation, needAnnotation);
@@ -587,18 +603,18 @@ private:
             int n = snapb200_device_count();
             if (const char *e = getenv("SNAPB200_DEVICES")) { int v = atoi(e); if (v >= 1 && v < n) n = v; }
             if (n < 1) { fprintf(stderr, "snapb200: no CUDA device available (this build has no CPU path)\n"); soft_exit(1); }
+            // one opener thread per device: context creation and the index upload of the devices overlap (each GPU has its own link)
+            std::vector<OpenJob> jobs(n);
+            std::vector<pthread_t> threads(n);
             for (int d = 0; d < n; d++) {
-                DeviceSet s;
-                s.device = d; s.contamination = NULL; s.annotation = NULL;
-                const double t0 = now();
-                check(snapb200_index_open(indexDir, d, &s.genome));
-                const double t1 = now();
-                check(snapb200_index_open(transcriptomeDir, d, &s.transcriptome));
-                if (contaminationDir != NULL) check(snapb200_index_open(contaminationDir, d, &s.contamination));
-                if (getenv("SNAPB200_SHIM_TIMING") != NULL)
-                    fprintf(stderr, "[snapb200 shim] device %d: genome index in HBM after %.2f s (CUDA context creation included), the other indices %.2f s; "
-                                    "started %.2f s after process start\n", d, t1 - t0, now() - t1, t0 - processStart());
-                sets.push_back(s);
+                jobs[d].indexDir = indexDir; jobs[d].transcriptomeDir = transcriptomeDir; jobs[d].contaminationDir = contaminationDir;
+                jobs[d].set.device = d; jobs[d].set.genome = jobs[d].set.transcriptome = jobs[d].set.contamination = NULL; jobs[d].set.annotation = NULL;
+                if (n == 1) openDevice(&jobs[d]);
+                else if (pthread_create(&threads[d], NULL, openDevice, &jobs[d]) != 0) { fprintf(stderr, "snapb200: pthread_create failed\n"); soft_exit(1); }
+            }
+            for (int d = 0; d < n; d++) {
+                if (n > 1) pthread_join(threads[d], NULL);
+                sets.push_back(jobs[d].set);
             }
             key = k;
         }

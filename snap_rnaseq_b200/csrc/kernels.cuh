@@ -187,10 +187,15 @@ __global__ void __launch_bounds__(CTA_THREADS, PAIRED_WARPS_PER_SM / WARPS_PER_C
     if (lane < 2) sm->sc_key[lane] = 0xffffffffu;  // no cached seed schedule yet
     if (lane < 5) sm->acc[lane] = 0;  // the run counters are summed per warp and flushed once (five global atomics per pair otherwise)
     __syncwarp();
+    PROF(if (lane == 0 && a.prof) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(a.prof + 11, t & 0xffffffffffull); })
     #pragma unroll 1
     for (;;) {
         const uint32_t p = fetch_work(&a.ctr->work);
-        if (p >= a.n_items) break;
+        if (p >= a.n_items) {
+            // when this warp found the queue empty: the earliest such time is where the kernel's tail begins, the latest is its end
+            PROF(if (lane == 0 && a.prof) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); t &= 0xffffffffffull; atomicMin(a.prof + 12, t); atomicMax(a.prof + 13, t); atomicAdd(a.prof + 14, t); })
+            break;
+        }
         const uint32_t pi = a.positions ? a.positions[p] : p;
         snapb200_paired_result *r = &a.results[pi];
         const uint32_t off0 = a.b[0].offsets[pi], len0 = a.b[0].offsets[pi + 1] - off0;

@@ -1013,6 +1013,7 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
     if (prof) {
         if ((rc = prof_buf.ensure(128))) return rc;
         CUDA_TRY(cudaMemsetAsync(prof_buf.p, 0, 128, s->stream));
+        CUDA_TRY(cudaMemsetAsync((char *)prof_buf.p + 11 * 8, 0xff, 16, s->stream));  // the two minima
         a.prof = prof_buf.as<unsigned long long>();
     }
     if ((rc = reset_work(s))) return rc;
@@ -1029,6 +1030,12 @@ static int launch_paired(snapb200_session *s, const snapb200_paired_params *p, c
         CUDA_TRY(cudaMemcpyAsync(h, prof_buf.p, 128, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         double tot = (double)h[0];
+        {
+            const double n_warps = (double)grid * WARPS_PER_CTA, span = (double)(h[13] - h[11]) * 1e-6, first_idle = (double)(h[12] - h[11]) * 1e-6;
+            const double mean_exit = ((double)h[14] / n_warps - (double)h[11]) * 1e-6;
+            fprintf(stderr, "[snapb200 prof]   timeline (globaltimer): first warp starts at 0, the first warp finds the queue empty at %.2f ms, the mean warp at %.2f ms, "
+                            "the last at %.2f ms: warps are busy %.1f %% of the kernel\n", first_idle, mean_exit, span, 100 * mean_exit / span);
+        }
         fprintf(stderr, "[snapb200 prof] paired_kernel grid=%d items=%llu cycles/item=%.0f  phase1 %.1f%%  phase2 %.1f%%  lv %.1f%%  leader3 %.1f%%\n", grid,
                 h[5], h[5] ? tot / h[5] : 0.0, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot);
 #ifdef SNAPB200_PROFILE

@@ -218,7 +218,7 @@ def test_rna_mode_sam_lines_are_formatted_on_the_device(workspace):
     assert len(a) == 8000 and a == b
 
 
-def bam_body(path):
+def bam_body(path, ordered=False):
     """The records of a BAM file (BGZF members decompressed, header skipped), NM of reads without a location zeroed (uninitialised in
     the reference, SNAPLib/Bam.cpp:644), sorted."""
     import gzip
@@ -236,7 +236,8 @@ def bam_body(path):
         ln, = struct.unpack_from("<i", raw, p)
         refs.append(raw[p + 4:p + 4 + ln + 4])
         p += 4 + ln + 4
-    return refs, sorted(bam_records(raw[p:]))
+    recs = bam_records(raw[p:])
+    return refs, (recs if ordered else sorted(recs))
 
 
 def test_rna_mode_bam_records_are_formatted_on_the_device(workspace):
@@ -261,3 +262,12 @@ def test_rna_mode_bam_records_are_formatted_on_the_device(workspace):
     r = subprocess.run([B200] + base + ["-o", "gpu_bhost.bam", "-t", "2"], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
     assert bam_body(os.path.join(d, "gpu_bhost.bam"))[1] == bam_body(os.path.join(d, "ref_bplain.bam"))[1]
+    # sorted BAM (-so: the reference's sorter, duplicate marking and index builder read the placed records back): same records, same order
+    run([REF] + base + ["-o", "ref_bso.bam", "-t", "1", "-so"], d)
+    env = dict(os.environ, SNAPB200_SHIM_TIMING="1")
+    r = subprocess.run([B200] + base + ["-o", "gpu_bso.bam", "-t", "1", "-so"], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert formatted(r.stdout) > 3900
+    a, b = bam_body(os.path.join(d, "ref_bso.bam"), ordered=True)[1], bam_body(os.path.join(d, "gpu_bso.bam"), ordered=True)[1]
+    assert len(a) == 8000 and a == b
+    assert os.path.getsize(os.path.join(d, "gpu_bso.bam.bai")) == os.path.getsize(os.path.join(d, "ref_bso.bam.bai"))

@@ -233,3 +233,17 @@ def test_fuzz_bam_records_cuda(cuda, cuda_handle, ref, small_index_dir, seed):
             got, lo = cuda.sam(cuda_handle, reads[0], reads[1] if paired else None, alns[0], alns[1] if paired else None, use_m, rg, bam=True)
             assert_same_bam(want, got, f"seed {seed} use_m {use_m} paired {paired}")
             assert int(lo[-1]) == len(want)
+
+
+@pytest.mark.gpu
+def test_bam_record_name_limit_cuda(cuda, cuda_handle):
+    """BAM's l_read_name is one byte: the reference exits for a name of more than 254 bytes (Bam.cpp:723); the library reports it."""
+    ok = A.SamReads.from_lists([b"n" * 254], [b"ACGT" * 10], [b"I" * 40])
+    bad = A.SamReads.from_lists([b"n" * 255], [b"ACGT" * 10], [b"I" * 40])
+    a = np.zeros(1, A.SAM_ALIGNMENT)
+    a["location"] = A.INVALID_LOCATION
+    got, lo = cuda.sam(cuda_handle, ok, None, a, None, False, None, bam=True)
+    assert len(got) == 36 + 255 + 20 + 40 + 8 + 7 and got[12] == 255
+    with pytest.raises(RuntimeError, match="254"):
+        cuda.sam(cuda_handle, bad, None, a, None, False, None, bam=True)
+    assert len(cuda.sam(cuda_handle, bad, None, a, None, False, None)[0]) > 255  # SAM has no such limit

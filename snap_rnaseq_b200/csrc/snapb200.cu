@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -118,6 +119,7 @@ struct snapb200_index {
     // overlaps the head of the other's.  A third concurrent caller waits.
     struct snapb200_session *batch_session[2] = {nullptr, nullptr};
     std::mutex batch_mutex[2];
+    std::mutex run_turn;  // see paired_chunks: the kernels of one chunk at a time, the copies of the other session overlap them
     std::atomic<unsigned> batch_rr{0};
 };
 
@@ -1330,9 +1332,41 @@ static int paired_chunks(snapb200_index *idx, const snapb200_paired_params *para
         const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)std::min<uint64_t>(n, lo64 + CHUNK);
         snapb200_read_batch a = sub_batch(reads0, lo, hi, off_store[0]);
         snapb200_read_batch b = sub_batch(reads1, lo, hi, off_store[1]);
+        static const bool timing = getenv("SNAPB200_BATCH_TIMING") != nullptr;  // where a chunk's wall time goes (stderr)
+        const auto t0 = std::chrono::steady_clock::now();
         if ((rc = snapb200_session_upload(cur, 0, &a)) || (rc = snapb200_session_upload(cur, 1, &b))) return rc;
-        if ((rc = snapb200_session_run_paired(cur, params))) return rc;
+        const auto t1 = std::chrono::steady_clock::now();
+        // The two sessions take turns on the SMs.  The persistent main kernel fills the device, so the short kernels that follow a
+        // main kernel (scratch-tier retries, the single-end fallback) could not start before the OTHER session's main kernel had
+        // finished: both sessions then completed together, uploaded together, and the device sat idle for the length of an upload in
+        // every cycle (device timeline in profiles/README.md).  With the turn, a chunk's kernels run back to back and the other
+        // session's download and upload fall entirely under them.  The upload is waited for first, so a turn never starts with a copy.
+        {
+            static const bool no_turns = getenv("SNAPB200_NO_TURNS") != nullptr;  // measurement: the behaviour before
+            cudaError_t e = no_turns ? cudaSuccess : cudaStreamSynchronize(cur->stream);
+            if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+            std::unique_lock<std::mutex> turn(idx->run_turn, std::defer_lock);
+            if (!no_turns) turn.lock();
+            if ((rc = snapb200_session_run_paired(cur, params))) return rc;
+        }
+        const auto t2 = std::chrono::steady_clock::now();
         rc = snapb200_session_download_paired(cur, results + lo);
+        if (timing) {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+            static cudaEvent_t base = nullptr;  // device-side timeline: when this chunk's first and main kernels ran, on one clock for all sessions
+            static std::mutex base_lock;
+            {
+                std::lock_guard<std::mutex> g(base_lock);
+                if (!base) { cudaEventCreate(&base); cudaEventRecord(base, cur->stream); cudaEventSynchronize(base); }
+            }
+            float e0 = 0, m0 = 0, m1 = 0, e1 = 0;
+            cudaEventElapsedTime(&e0, base, cur->ev0); cudaEventElapsedTime(&m0, base, cur->evm0);
+            cudaEventElapsedTime(&m1, base, cur->evm1); cudaEventElapsedTime(&e1, base, cur->ev1);
+            fprintf(stderr, "[snapb200 batch] %u pairs on session %d: upload %.1f ms, run %.1f ms (kernels of this chunk %.1f ms, main kernel %.1f ms), download %.1f ms; "
+                            "device timeline: inputs resident at %.1f, main kernel %.1f .. %.1f, last kernel done %.1f\n",
+                    hi - lo, slot.slot, ms(t0, t1), ms(t1, t2), cur->last_ms, cur->main_ms, ms(t2, t3), e0, m0, m1, e1);
+        }
         if (rc == SNAPB200_ERR_LIMIT) *limit_rc = rc; else if (rc) return rc;
     }
     return 0;

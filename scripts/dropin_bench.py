@@ -55,12 +55,27 @@ def run_dropin(pairs=300_000, mbp=40, threads=None, reps=2, env=None):
                          "reads_per_s_align_phase": 2 * pairs / a if a else None, "outside_align_phase_s": best["wall_s"] - a if a else None,
                          "side_files_sha1": side})
             res[tag] = best
+        # extra runs of snap-rna-b200 with other environments (DROPIN_B200_ENVS="A=1;B=2 C=3"): alignment phase and wall clock of each
+        variants = []
+        for spec in [v for v in os.environ.get("DROPIN_B200_ENVS", "").split(";") if v.strip()]:
+            e2 = dict(env if env is not None else os.environ)
+            e2.update(dict(kv.split("=", 1) for kv in spec.split()))
+            t = time.perf_counter()
+            r = subprocess.run([B200, "paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq", "-o", "variant.sam", "-t", str(threads)], cwd=d, stdout=subprocess.PIPE,
+                               stderr=subprocess.STDOUT, text=True, env=e2)
+            wall = time.perf_counter() - t
+            stats = [l for l in r.stdout.split("\n") if l.strip().startswith("16000")][-1:]
+            loops = [float(l.split("batch loop ")[1].split(" s")[0]) for l in r.stdout.split("\n") if "batch loop " in l]
+            recs = sorted(l for l in open(os.path.join(d, "variant.sam")) if not l.startswith("@"))
+            variants.append({"env": spec, "rc": r.returncode, "wall_s": wall, "align_phase_s": float(stats[0].split("(at:")[1].split(")")[0]) / 1e3 if stats else None,
+                             "batch_loop_s_max": max(loops) if loops else None,
+                             "sam_identical": hashlib.sha1("".join(recs).encode()).hexdigest() == res["reference"]["sha1_sorted_records"]})
         same_side = {k: res["reference"]["side_files_sha1"].get(k) == v for k, v in res["b200"]["side_files_sha1"].items()}
         return {"config": f"C4 RNA-seq mode: {mbp} Mbp genome + GTF transcriptome, {pairs} 2x100 bp pairs (50 % spliced fragments, 1 % chimeric), -t {threads}, best of {reps}",
                 "reference": res["reference"], "b200": res["b200"], "speedup_wall": res["reference"]["wall_s"] / res["b200"]["wall_s"],
                 "speedup_align_phase": (res["reference"]["align_phase_s"] / res["b200"]["align_phase_s"]) if res["b200"]["align_phase_s"] else None,
                 "sam_identical": res["reference"]["sha1_sorted_records"] == res["b200"]["sha1_sorted_records"],
-                "statistics_files_identical": bool(same_side) and all(same_side.values()), "reference_index_build_s": t_index,
+                "statistics_files_identical": bool(same_side) and all(same_side.values()), "reference_index_build_s": t_index, "b200_variants": variants,
                 "note": "outside_align_phase_s is index loading plus the reference's own GTF epilogue (GTFReader::AnalyzeReadIntervals / WriteReadCounts, "
                         "AlignerContext.cpp:126-127), unchanged host code that both binaries run; the b200 alignment phase includes CUDA context creation"}, shim_lines
     finally:

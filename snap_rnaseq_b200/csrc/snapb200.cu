@@ -100,6 +100,19 @@ static int compute_mapq_host(double p_all, double p_best, int score, int popular
 
 #define FIX_CAP 65536
 
+// Internal sessions of an index handle: how many callers of the synchronous batch entry points (and batches of the RNA pipeline) can
+// have their device work in flight at once; a further caller waits for one.  Each owns its scratch tiers (a few hundred MB on C3).
+#define MAX_BATCH_SESSIONS 4
+static int batch_sessions()
+{
+    static const int n = [] {
+        const char *e = getenv("SNAPB200_SESSIONS");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= MAX_BATCH_SESSIONS ? v : 2;
+    }();
+    return n;
+}
+
 struct snapb200_index {
     int device = 0;
     int slot = -1;  // position of `dev` in this device's c_index[]
@@ -117,8 +130,8 @@ struct snapb200_index {
     // The synchronous *_batch entry points run on one of two internal sessions (own stream + device buffers each), so two
     // host threads (the reference runs -t N of them) can have batches in flight at once: the tail of one batch's kernels
     // overlaps the head of the other's.  A third concurrent caller waits.
-    struct snapb200_session *batch_session[2] = {nullptr, nullptr};
-    std::mutex batch_mutex[2];
+    struct snapb200_session *batch_session[MAX_BATCH_SESSIONS] = {nullptr, nullptr, nullptr, nullptr};
+    std::mutex batch_mutex[MAX_BATCH_SESSIONS];
     std::mutex run_turn;  // see paired_chunks: the kernels of one chunk at a time, the copies of the other session overlap them
     std::atomic<unsigned> batch_rr{0};
 };
@@ -653,7 +666,7 @@ extern "C" void snapb200_index_close(snapb200_index *x)
 {
     if (!x) return;
     cudaSetDevice(x->device);
-    for (int i = 0; i < 2; i++) if (x->batch_session[i]) snapb200_session_destroy(x->batch_session[i]);
+    for (int i = 0; i < MAX_BATCH_SESSIONS; i++) if (x->batch_session[i]) snapb200_session_destroy(x->batch_session[i]);
     for (void *p : x->allocs) cudaFree(p);
     if (x->slot >= 0) { std::lock_guard<std::mutex> g(g_slot_mutex); g_slot_used[x->device][x->slot] = false; }
     if (x->stats) cudaFree(x->stats);
@@ -1250,9 +1263,10 @@ struct BatchSlot {
     snapb200_session *s = nullptr;
     explicit BatchSlot(snapb200_index *i) : idx(i)
     {
-        for (int k = 0; k < 2 && slot < 0; k++) if (idx->batch_mutex[k].try_lock()) slot = k;
+        const int n = batch_sessions();
+        for (int k = 0; k < n && slot < 0; k++) if (idx->batch_mutex[k].try_lock()) slot = k;
         if (slot < 0) {
-            slot = (int)(idx->batch_rr.fetch_add(1) & 1);
+            slot = (int)(idx->batch_rr.fetch_add(1) % (unsigned)n);
             idx->batch_mutex[slot].lock();
         }
     }

@@ -416,7 +416,8 @@ typedef struct {
     float device_ms;   /* wall time of the device work of this batch (uploads, kernels, downloads), for the shim's timing report */
     /* snapb200_rna_batch_submit_sam only (NULL otherwise): what SimpleReadWriter::writePair writes for pair i is
      * sam_text[sam_line_offsets[2i] .. sam_line_offsets[2i+2]) -- two lines, the end with the lower location first -- with the
-     * filter's result (after the forceSpacing rule of PairedAligner.cpp:648-651) as the alignment.  A pair whose range is empty
+     * filter's result (after the forceSpacing rule of PairedAligner.cpp:648-651, applied when params.paired.force_spacing or
+     * params.filter.force_spacing is set) as the alignment.  A pair whose range is empty
      * was not formatted (needs_host[i], or a spliced CIGAR too long for its slot): the caller writes it with the reference's writer. */
     const char *sam_text;
     const uint64_t *sam_line_offsets;

@@ -455,7 +455,7 @@ static int rna_sam_stage(snapb200_rna_batch *b, RnaResources &R, cudaStream_t st
         a.in.rd[e].id_offsets = R.ds_idoff[e].as<uint32_t>(); a.in.rd[e].ids = R.ds_ids[e].as<uint8_t>();
         a.in.aln[e] = R.ds_aln[e].as<snapb200_sam_alignment>();
     }
-    rna_sam_alignments_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, R.d_res.as<FltResult>(), R.d_flags.as<uint8_t>(), (int)b->params.filter.force_spacing,
+    rna_sam_alignments_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, R.d_res.as<FltResult>(), R.d_flags.as<uint8_t>(), (int)(b->params.filter.force_spacing || b->params.paired.force_spacing),
                                                                    R.ds_aln[0].as<snapb200_sam_alignment>(), R.ds_aln[1].as<snapb200_sam_alignment>());
     CUDA_TRY(cudaGetLastError());
     const size_t rg_len = b->read_group.size();

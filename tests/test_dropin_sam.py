@@ -199,13 +199,14 @@ def test_rna_mode_sam_lines_are_formatted_on_the_device(workspace):
         return r.stdout
 
     base = ["paired", "gidx", "tidx", "a.gtf", "x1.fq", "x2.fq"]
-    for tag, opts in (("plain", ["-t", "2"]), ("m", ["-t", "2", "-M"]), ("rg", ["-t", "2", "-rg", "sampleA"])):
+    for tag, opts in (("plain", ["-t", "2"]), ("m", ["-t", "2", "-M"]), ("rg", ["-t", "2", "-rg", "sampleA"]), ("fs", ["-t", "2", "-fs"])):
         run([REF] + base + ["-o", f"ref_d{tag}.sam"] + opts, d)
         out = b200(base + ["-o", f"gpu_d{tag}.sam"] + opts)
         assert formatted(out) > 3900, out[-2000:]  # all but the pairs the run loop never aligns
         a, b = sam_records(os.path.join(d, f"ref_d{tag}.sam")), sam_records(os.path.join(d, f"gpu_d{tag}.sam"))
         assert_same(a, b, 8000)
-    assert any("RG:Z:sampleA" in r for r in b)
+    assert sam_records(os.path.join(d, "ref_dfs.sam")) != sam_records(os.path.join(d, "ref_dplain.sam"))  # -fs (forceSpacing) really changes records
+    assert any("RG:Z:sampleA" in r for r in sam_records(os.path.join(d, "gpu_drg.sam")))
     out = b200(base + ["-o", "gpu_dhost.sam", "-t", "2"], SNAPB200_HOST_SAM="1")
     assert formatted(out) == 0
     assert_same(sam_records(os.path.join(d, "ref_dplain.sam")), sam_records(os.path.join(d, "gpu_dhost.sam")), 8000)

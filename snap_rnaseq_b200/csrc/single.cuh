@@ -196,6 +196,35 @@ __device__ __noinline__ void score_location_lane(int ix_slot, const ReadView v, 
 #endif
     double p1 = 0, p2 = 0;
     int dummy, off = 0;
+#ifndef NO_LANE_DUAL  // A/B on C3: 61.9 -> 60.3 ms per million pairs (profiles/r2_ab_9.log)
+    // At most 16 locations, all in the lower half of the warp: lane i + 16 runs the backward pass of lane i's location while lane i
+    // runs its forward pass -- one trip through the row loop instead of two.  The backward pass gets the whole limit K instead of
+    // K - s1; LV finds the same distance d2 (the limit only decides when it gives up), and d2 > K - s1 is turned into -1 below.
+    {
+        const unsigned okmask = __ballot_sync(FULL_MASK, ok);
+        if (okmask != 0 && (okmask >> 16) == 0) {
+            const int lane = lane_id(), src = lane & 15;
+            const bool upper = lane >= 16;
+            const int dir_s = __shfl_sync(FULL_MASK, dir, src), K_s = __shfl_sync(FULL_MASK, K, src);
+            const uint32_t loc_s = __shfl_sync(FULL_MASK, loc, src), so_s = __shfl_sync(FULL_MASK, seed_offset, src);
+            const bool ok_s = __shfl_sync(FULL_MASK, (int)ok, src) != 0;
+            const uint8_t *gs = ix.genome + loc_s;
+            const int tail_s = (int)so_s + seed_len;
+            const int at = upper ? (int)so_s - 1 : tail_s;
+            double pp = 0;
+            int oo = 0;
+            const int sd = lv_lane_rt(upper ? -1 : 1, v.D(dir_s) + at, upper ? (int)so_s : (int)rlen - tail_s, gs + at, v.Q(dir_s) + at, K_s, kl, R, T, ix_slot, ok_s, &pp, &oo);
+            const int sb = __shfl_down_sync(FULL_MASK, sd, 16), ob = __shfl_down_sync(FULL_MASK, oo, 16);
+            const double pb = shfl_f64(pp, (lane + 16) & 31);
+            if (!ok) return;
+            if (sd == -1 || sb == -1 || sb > K - (sd > 0 ? sd : 0)) { *score = -1; return; }
+            *score = sd + sb;
+            *match_prob = pp * pb * ix.seed_prob;
+            *loc_offset = ob;
+            return;
+        }
+    }
+#endif
 #ifndef LANE_TEMPLATE_DIR  // one run-time-direction body for both passes: 7 KB less code to fetch, 66.4 -> 63.8 ms per million C3 pairs
     int s1 = lv_lane_rt(1, v.D(dir) + tail, (int)rlen - tail, g + tail, v.Q(dir) + tail, K, kl, R, T, ix_slot, ok, &p1, &dummy);
 #else

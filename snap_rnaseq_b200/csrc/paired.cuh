@@ -302,8 +302,8 @@ __device__ __noinline__ void schedule_seeds_paired(PairedSm *sm, Phase1Sm *p1, i
 }
 
 // Lane mode for the candidates of phase 3: lane i scores candidate batch_ids[i] with the current limit, then the mates those
-// candidates will ask about are scored ahead (see phase 3).  Out of line: ordinary pairs never come here, and keeping this
-// out of the main body makes their path through the kernel 10 % faster (instruction cache).
+// candidates will ask about are scored ahead (see phase 3).  Out of line: one copy, called from the one place of the main body that
+// needs it (with LANE_MIN_BATCH 1 every pair comes here, an ordinary pair with a batch of one candidate and then one mate).
 // (arguments by value: a reference to the kernel's configuration or scratch descriptor would force them onto the stack)
 __device__ __noinline__ void lane_batch_candidates(int ix_slot, int lane_k, uint32_t min_spacing, uint32_t max_spacing, Cand *cands, Mate *mates,
                                                    uint32_t mate_cap, lane_cell_t *lane_table, PairedSm *sm, const ReadView vf, const ReadView vm,

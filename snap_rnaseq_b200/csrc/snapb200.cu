@@ -113,6 +113,12 @@ static int batch_sessions()
     return n;
 }
 
+static bool turns_enabled()
+{
+    static const bool on = getenv("SNAPB200_NO_TURNS") == nullptr;  // SNAPB200_NO_TURNS=1: measurement, the behaviour before
+    return on;
+}
+
 struct snapb200_index {
     int device = 0;
     int slot = -1;  // position of `dev` in this device's c_index[]
@@ -1079,6 +1085,8 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
     if (run_seeds > MAX_LOOKUPS) return set_error(SNAPB200_ERR_ARG, "%u seeds per mate requested; this build holds %d lookups per hit set", run_seeds, MAX_LOOKUPS);
     if (ctor_seeds == 0) return set_error(SNAPB200_ERR_ARG, "num_seeds/seed_coverage give zero seeds");
     int rc;
+    std::unique_lock<std::mutex> turn(x->run_turn, std::defer_lock);  // one session's kernels at a time on this index (see paired_chunks)
+    if (turns_enabled()) turn.lock();
     if ((rc = begin_run(s))) return rc;
     const uint32_t n = s->n[0];
     const uint32_t rl = std::max(32u, (s->max_len_seen + 15) & ~15u);
@@ -1355,12 +1363,10 @@ static int paired_chunks(snapb200_index *idx, const snapb200_paired_params *para
         // finished: both sessions then completed together, uploaded together, and the device sat idle for the length of an upload in
         // every cycle (device timeline in profiles/README.md).  With the turn, a chunk's kernels run back to back and the other
         // session's download and upload fall entirely under them.  The upload is waited for first, so a turn never starts with a copy.
+        // (the turn itself is taken inside snapb200_session_run_paired, so that sessions driven directly take turns as well)
         {
-            static const bool no_turns = getenv("SNAPB200_NO_TURNS") != nullptr;  // measurement: the behaviour before
-            cudaError_t e = no_turns ? cudaSuccess : cudaStreamSynchronize(cur->stream);
+            cudaError_t e = turns_enabled() ? cudaStreamSynchronize(cur->stream) : cudaSuccess;
             if (e != cudaSuccess) return set_error(SNAPB200_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
-            std::unique_lock<std::mutex> turn(idx->run_turn, std::defer_lock);
-            if (!no_turns) turn.lock();
             if ((rc = snapb200_session_run_paired(cur, params))) return rc;
         }
         const auto t2 = std::chrono::steady_clock::now();

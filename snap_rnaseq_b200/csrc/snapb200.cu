@@ -1086,7 +1086,6 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
     if (ctor_seeds == 0) return set_error(SNAPB200_ERR_ARG, "num_seeds/seed_coverage give zero seeds");
     int rc;
     std::unique_lock<std::mutex> turn(x->run_turn, std::defer_lock);  // one session's kernels at a time on this index (see paired_chunks)
-    if (turns_enabled()) turn.lock();
     if ((rc = begin_run(s))) return rc;
     const uint32_t n = s->n[0];
     const uint32_t rl = std::max(32u, (s->max_len_seen + 15) & ~15u);
@@ -1118,6 +1117,9 @@ extern "C" int snapb200_session_run_paired(snapb200_session *s, const snapb200_p
         // heaviest pairs first (see weigh_kernel); SNAPB200_NO_ORDER=1 serves them in input order (experiments)
         const uint32_t *order = nullptr;
         if ((rc = work_order(s, 2, n, p->max_big_hits, &order))) return rc;
+        // the ordering kernels are queued before the turn is taken: they run as soon as the other session's main kernel leaves room,
+        // next to its short post-main kernels, instead of after them
+        if (turns_enabled()) turn.lock();
         if ((rc = launch_paired(s, p, cfg, grid, order, n))) return rc;
         Counters c;
         if ((rc = read_counters(s, &c))) return rc;

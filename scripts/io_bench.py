@@ -100,6 +100,16 @@ def main():
                                     "frac": algo / (k_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": algo,
                                     "kernels": "sam_measure_kernel (CIGAR by Landau-Vishkin + line lengths), cub scan, sam_write_kernel"}}
 
+    # ---- BAM records (the same kernels, SNAPB200_SAM_BAM_RECORDS) -----------------------------------------------------------
+    for rep in range(3):
+        t0 = time.perf_counter()
+        bam, blo = L.sam(h, reads[0], reads[1], aln[0], aln[1], False, None, out=buf, bam=True)
+        e2e_b = time.perf_counter() - t0
+        k_b = L.io_last_kernel_ms()[1]
+    out["bam_records"] = {"records": 2 * pairs, "bam_bytes": int(blo[-1]), "kernel_ms": k_b, "e2e_ms": e2e_b * 1e3,
+                          "reads_per_s_kernels": 2 * pairs / (k_b * 1e-3), "reads_per_s_e2e": 2 * pairs / e2e_b,
+                          "note": "uncompressed BAMFormat::writeRead records; BGZF is the reference's host filter"}
+
     # ---- the reference on a sample: timing + parity ------------------------------------------------------------------------
     from oracle import oracle as O
     if O.have_ref():
@@ -122,10 +132,16 @@ def main():
             a0, a1 = aln[0][:m].copy(), aln[1][:m].copy()
             sam_ref, _ = ref.sam(hc, want[0], want[1], a0, a1, False, None)
             t_sam = ref.lib.ref_last_seconds()  # Read construction + writePair loop + writer close
+            bam_ref, _ = ref.sam(hc, want[0], want[1], a0, a1, False, None, bam=True)
+            t_bam = ref.lib.ref_last_seconds()
         sam_got, _ = L.sam(h, got[0], got[1], a0, a1, False, None)
         out["reference_sample"] = {"pairs": m, "threads": 1, "fastq_reads_per_s": 2 * m / t_fq, "sam_reads_per_s": 2 * m / t_sam,
                                    "fastq_arrays_identical": same_fq, "sam_bytes_identical": bool(sam_got == sam_ref),
                                    "sam_bytes": len(sam_ref)}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_io_fuzz import bam_records
+        bam_got, _ = L.sam(h, got[0], got[1], a0, a1, False, None, bam=True)
+        out["reference_sample"].update({"bam_reads_per_s": 2 * m / t_bam, "bam_records_identical": bam_records(bytes(bam_got)) == bam_records(bam_ref)})
     print(json.dumps(out))
 
 

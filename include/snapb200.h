@@ -304,6 +304,17 @@ int snapb200_sam_batch_rna(snapb200_annotation *annotation, snapb200_index *geno
                            const snapb200_sam_alignment *aln1, int use_m, const char *read_group, char *out, uint64_t out_capacity,
                            uint64_t *line_offsets);
 
+/* BGZF (SAM/BAM specification section 4.1): the container GzipWriterFilter::compressChunk builds for BAM output
+ * (SNAPLib/GzipDataWriter.cpp:281-340: one gzip member per chunk with the "BC" extra field holding the member's size, then CRC-32 and
+ * ISIZE).  Replaces it for the CONTENT, not for zlib's bytes: every `chunk` input bytes (0: 65024, the maximum) become one member whose
+ * deflate stream is this library's own -- a dynamic-Huffman block over the chunk's byte histogram, no string matching, or a stored
+ * block when that is not smaller -- so any BGZF reader inflates exactly `data`, but the file is neither zlib's bytes nor as small as
+ * zlib's.  n_bytes == 0 gives one empty member.  out_capacity must be at least n_bytes + 31 * ceil(n_bytes / chunk) (the stored worst
+ * case); block_offsets (optional) receives n_blocks + 1 offsets into out. */
+int snapb200_bgzf_compress(int device, const uint8_t *data, uint64_t n_bytes, uint32_t chunk, uint8_t *out, uint64_t out_capacity,
+                           uint64_t *out_bytes, uint64_t *block_offsets);
+int snapb200_bgzf_last_kernel_ms(float *ms);
+
 /* CUDA-event times (ms) of the kernels of the last snapb200_fastq_parse / snapb200_sam_batch call made by this thread
  * (no copies), for the streaming roofline of these two stages. */
 int snapb200_io_last_kernel_ms(float *fastq_ms, float *sam_ms);

@@ -254,6 +254,31 @@ class BatchLib:
                       C.c_uint64(total), plo), "sam_batch")
         return out[:total].tobytes(), lo
 
+    def bgzf_compress(self, data, chunk=0, device=0):
+        """snapb200_bgzf_compress (hostsim: the serial specification of csrc/bgzf.h) -> (BGZF bytes, block offsets or None)."""
+        raw = bytes(data)
+        a = np.frombuffer(raw, np.uint8) if raw else np.zeros(1, np.uint8)
+        c = chunk or 65024
+        n_blocks = max(1, (len(raw) + c - 1) // c)
+        out = np.zeros(len(raw) + 31 * n_blocks + 64, np.uint8)
+        if self.prefix == "hostsim_":
+            f = self.lib.hostsim_bgzf_compress
+            f.restype = C.c_longlong
+            n = f(A.p8(a), C.c_uint64(len(raw)), C.c_uint32(c), A.p8(out), C.c_uint64(out.size))
+            if n < 0:
+                raise RuntimeError("hostsim_bgzf_compress failed")
+            return out[:n].tobytes(), None
+        nb = C.c_uint64(0)
+        off = np.zeros(n_blocks + 1, np.uint64)
+        self._check(self.fn("bgzf_compress")(C.c_int(device), A.p8(a), C.c_uint64(len(raw)), C.c_uint32(chunk), A.p8(out), C.c_uint64(out.size), C.byref(nb),
+                                             off.ctypes.data_as(C.POINTER(C.c_uint64))), "bgzf_compress")
+        return out[:int(nb.value)].tobytes(), off
+
+    def bgzf_last_kernel_ms(self):
+        v = C.c_float(0)
+        self.fn("bgzf_last_kernel_ms")(C.byref(v))
+        return v.value
+
     def io_last_kernel_ms(self):
         a, b = C.c_float(0), C.c_float(0)
         self.fn("io_last_kernel_ms")(C.byref(a), C.byref(b))

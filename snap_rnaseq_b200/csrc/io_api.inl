@@ -331,3 +331,87 @@ extern "C" int snapb200_sam_batch(snapb200_index *idx, const snapb200_sam_reads 
 {
     return sam_batch_impl(idx, nullptr, nullptr, reads0, reads1, aln0, aln1, use_m, read_group, out, out_capacity, line_offsets);
 }
+
+// ---- BGZF (row f4b: the compressed container of BAM output; bgzf.h, bgzf_kernels.cuh) ---------------------------------------------
+struct BgzfTables { const uint32_t *crc_table = nullptr, *crc_shift = nullptr; };
+static int bgzf_tables(int device, BgzfTables *out)
+{
+    static std::mutex m;
+    static BgzfTables per_device[64];
+    std::lock_guard<std::mutex> g(m);
+    if (device < 0 || device >= 64) return set_error(SNAPB200_ERR_ARG, "device %d out of range", device);
+    BgzfTables &t = per_device[device];
+    if (!t.crc_table) {
+        uint32_t table[256], shift[17 * 32];
+        for (uint32_t i = 0; i < 256; i++) table[i] = bgzf_crc_table_entry(i);
+        bgzf_crc_shift_build(table, shift);
+        void *a = nullptr, *b = nullptr;
+        CUDA_TRY(cudaMalloc(&a, sizeof(table)));
+        CUDA_TRY(cudaMalloc(&b, sizeof(shift)));
+        CUDA_TRY(cudaMemcpy(a, table, sizeof(table), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(b, shift, sizeof(shift), cudaMemcpyHostToDevice));
+        t.crc_table = (const uint32_t *)a; t.crc_shift = (const uint32_t *)b;
+    }
+    *out = t;
+    return 0;
+}
+
+static thread_local float g_bgzf_ms = 0;
+extern "C" int snapb200_bgzf_last_kernel_ms(float *ms) { if (ms) *ms = g_bgzf_ms; return 0; }
+
+extern "C" int snapb200_bgzf_compress(int device, const uint8_t *data, uint64_t n_bytes, uint32_t chunk, uint8_t *out, uint64_t out_capacity,
+                                      uint64_t *out_bytes, uint64_t *block_offsets)
+{
+    if ((n_bytes && !data) || !out || !out_bytes) return set_error(SNAPB200_ERR_ARG, "null argument");
+    if (chunk == 0) chunk = BGZF_MAX_CHUNK;
+    if (chunk > BGZF_MAX_CHUNK) return set_error(SNAPB200_ERR_ARG, "chunk %u exceeds %u bytes", chunk, BGZF_MAX_CHUNK);
+    const uint64_t nb64 = n_bytes ? (n_bytes + chunk - 1) / chunk : 1;
+    if (nb64 > 0x7fffffffull) return set_error(SNAPB200_ERR_ARG, "too many blocks");
+    const uint32_t n_blocks = (uint32_t)nb64;
+    const uint64_t bound = n_bytes + (uint64_t)n_blocks * (BGZF_HEADER + 5 + BGZF_FOOTER);
+    if (out_capacity < bound) return set_error(SNAPB200_ERR_ARG, "out_capacity %llu is below the worst case %llu", (unsigned long long)out_capacity, (unsigned long long)bound);
+    IoScratch &io = g_io;
+    int rc;
+    if ((rc = io.use(device))) return rc;
+    BgzfTables tables;
+    if ((rc = bgzf_tables(device, &tables))) return rc;
+    DevBuf d_in, d_slots, d_sizes, d_off, d_out, d_work;
+    do {
+        if ((rc = d_in.ensure(n_bytes + 16)) || (rc = d_slots.ensure((size_t)n_blocks * BGZF_SLOT)) || (rc = d_sizes.ensure((size_t)(n_blocks + 1) * 8)) ||
+            (rc = d_off.ensure((size_t)(n_blocks + 1) * 8)) || (rc = d_work.ensure(64)))
+            break;
+        cudaError_t e = cudaSuccess;
+        if (n_bytes) e = cudaMemcpyAsync(d_in.p, data, n_bytes, cudaMemcpyHostToDevice, io.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_slots.p, 0, (size_t)n_blocks * BGZF_SLOT, io.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_sizes.p, 0, (size_t)(n_blocks + 1) * 8, io.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_work.p, 0, 64, io.stream);
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "bgzf: %s", cudaGetErrorString(e)); break; }
+        BgzfArgs a;
+        a.in = d_in.as<uint8_t>(); a.n_bytes = n_bytes; a.chunk = chunk; a.n_blocks = n_blocks; a.slots = d_slots.as<uint8_t>();
+        a.sizes = d_sizes.as<unsigned long long>(); a.crc_table = tables.crc_table; a.crc_shift = tables.crc_shift; a.work = d_work.as<uint32_t>();
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const uint32_t grid = std::min<uint32_t>((n_blocks + BGZF_WARPS - 1) / BGZF_WARPS, (uint32_t)std::max(1, sms) * 8);
+        cudaEventRecord(io.ev[0], io.stream);
+        bgzf_block_kernel<<<grid, BGZF_WARPS * 32, 0, io.stream>>>(a);
+        if ((rc = io_scan(io, d_sizes.as<unsigned long long>(), d_off.as<unsigned long long>(), (size_t)n_blocks + 1))) break;
+        std::vector<unsigned long long> off(n_blocks + 1);
+        e = cudaMemcpyAsync(off.data(), d_off.p, (size_t)(n_blocks + 1) * 8, cudaMemcpyDeviceToHost, io.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(io.stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "bgzf_block_kernel: %s", cudaGetErrorString(e)); break; }
+        const uint64_t total = off[n_blocks];
+        if ((rc = d_out.ensure(total + 16))) break;
+        bgzf_pack_kernel<<<(uint32_t)(((uint64_t)n_blocks * 32 + 255) / 256), 256, 0, io.stream>>>(d_slots.as<uint8_t>(), d_off.as<unsigned long long>(), n_blocks, d_out.as<uint8_t>());
+        cudaEventRecord(io.ev[1], io.stream);
+        e = cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, io.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(io.stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = set_error(SNAPB200_ERR_CUDA, "bgzf_pack_kernel: %s", cudaGetErrorString(e)); break; }
+        cudaEventElapsedTime(&g_bgzf_ms, io.ev[0], io.ev[1]);
+        *out_bytes = total;
+        if (block_offsets) for (uint32_t i = 0; i <= n_blocks; i++) block_offsets[i] = off[i];
+    } while (0);
+    d_in.release(); d_slots.release(); d_sizes.release(); d_off.release(); d_out.release(); d_work.release();
+    return rc;
+}

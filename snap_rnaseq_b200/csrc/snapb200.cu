@@ -18,6 +18,7 @@
 #include "index_build.cuh"
 #include "characterize.cuh"  // after kernels.cuh: uses DevBatch, Counters, fetch_work
 #include "iokernels.cuh"     // FASTQ / SAM batch kernels (row f2); uses lv_cigar_warp, stage_window
+#include "bgzf_kernels.cuh"  // BGZF blocks (row f4b)
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>

@@ -355,3 +355,39 @@ extern "C" int hostsim_splice_cigar(const FltTables *t, int tr, uint32_t pos, co
 {
     return sam_splice_cigar(*t, tr, pos, lv, lv_len, clip_before, clip_after, out, cap, n_calls);
 }
+
+// ---- BGZF blocks (bgzf.h): the serial specification, and the pieces the kernel combines --------------------------------------------
+#include "../../snap_rnaseq_b200/csrc/bgzf.h"
+#include <vector>
+
+extern "C" long long hostsim_bgzf_compress(const uint8_t *in, uint64_t n, uint32_t chunk, uint8_t *out, uint64_t cap)
+{
+    uint32_t table[256];
+    for (uint32_t i = 0; i < 256; i++) table[i] = bgzf_crc_table_entry(i);
+    std::vector<uint32_t> scratch(257 + 257 + 513 + 513);
+    uint64_t pos = 0;
+    for (uint64_t lo = 0; lo < n || (n == 0 && lo == 0); lo += chunk) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - lo);
+        if (pos + BGZF_HEADER + m + 5 + BGZF_FOOTER > cap) return -1;
+        memset(out + pos, 0, BGZF_HEADER + m + 5 + BGZF_FOOTER);
+        pos += bgzf_block_serial(table, in + lo, m, out + pos, scratch.data());
+        if (n == 0) break;
+    }
+    return (long long)pos;
+}
+
+// the CRC of a buffer computed the way 32 lanes do: slices with their own registers, combined through the zero-shift matrices
+extern "C" uint32_t hostsim_bgzf_crc_sliced(const uint8_t *in, uint32_t n, uint32_t slices)
+{
+    uint32_t table[256], shift[17 * 32];
+    for (uint32_t i = 0; i < 256; i++) table[i] = bgzf_crc_table_entry(i);
+    bgzf_crc_shift_build(table, shift);
+    const uint32_t per = (n + slices - 1) / slices;
+    uint32_t total = 0;
+    for (uint32_t k = 0; k < slices; k++) {
+        const uint32_t lo = std::min(n, k * per), hi = std::min(n, lo + per);
+        const uint32_t r = bgzf_crc_raw(table, k == 0 ? 0xffffffffu : 0u, in + lo, hi - lo);
+        total ^= bgzf_crc_zeros(shift, r, n - hi);
+    }
+    return total ^ 0xffffffffu;
+}

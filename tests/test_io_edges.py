@@ -44,8 +44,9 @@ class HostsimIndex(C.Structure):
 def hostsim():
     src = os.path.join(HERE, "hostsim", "io_hostsim.cpp")
     so = os.path.join(HERE, "hostsim", "libiohostsim.so")
-    hdr = os.path.join(os.path.dirname(HERE), "snap_rnaseq_b200", "csrc", "iofmt.h")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    csrc = os.path.join(os.path.dirname(HERE), "snap_rnaseq_b200", "csrc")
+    hdrs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", so, src], check=True)
     return BatchLib(C.CDLL(so), "hostsim_")
 

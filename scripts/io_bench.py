@@ -110,6 +110,24 @@ def main():
                           "reads_per_s_kernels": 2 * pairs / (k_b * 1e-3), "reads_per_s_e2e": 2 * pairs / e2e_b,
                           "note": "uncompressed BAMFormat::writeRead records; BGZF is the reference's host filter"}
 
+    # ---- BGZF container over those BAM records (row f4b; the reference: zlib level 6 per 64 KiB chunk on its host threads) ----------
+    import zlib
+    bam_bytes = bytes(bam[:int(blo[-1])]) if not isinstance(bam, bytes) else bam
+    for rep in range(2):
+        t0 = time.perf_counter()
+        z, zoff = L.bgzf_compress(bam_bytes)
+        e2e_z = time.perf_counter() - t0
+        k_z = L.bgzf_last_kernel_ms()
+    sample = bam_bytes[:64 << 20]
+    t0 = time.perf_counter()
+    zs = sum(len(zlib.compress(sample[i:i + 65536], 6)) for i in range(0, len(sample), 65536))
+    t_zlib = time.perf_counter() - t0
+    import gzip
+    out["bgzf"] = {"input_bytes": len(bam_bytes), "output_bytes": len(z), "ratio": len(z) / len(bam_bytes), "blocks": len(zoff) - 1, "kernel_ms": k_z,
+                   "e2e_ms": e2e_z * 1e3, "gb_per_s_kernels": len(bam_bytes) / (k_z * 1e-3) / 1e9, "gb_per_s_e2e": len(bam_bytes) / e2e_z / 1e9,
+                   "inflates_to_input": gzip.decompress(z[:int(zoff[200])]) == bam_bytes[:200 * 65024],
+                   "zlib_level6_one_thread": {"sample_bytes": len(sample), "ratio": zs / len(sample), "gb_per_s": len(sample) / t_zlib / 1e9}}
+
     # ---- the reference on a sample: timing + parity ------------------------------------------------------------------------
     from oracle import oracle as O
     if O.have_ref():
